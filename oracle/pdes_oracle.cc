@@ -1,0 +1,771 @@
+// TEST INFRASTRUCTURE ONLY.  CPU restatement ("golden model") of SST-core's event-delivery hot path.
+//
+// This is NOT part of the product: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
+// arm may load it.  It restates, event by event and serially, what the reference does, so that the CUDA engine
+// can be checked at sizes the reference itself cannot hold.
+//
+// Parity of THIS file is pinned (tests/test_oracle.py) against
+//   * the reference's golden vectors: tests/refFiles/test_MessageMesh.out, test_RNGComponent_{mersenne,marsaglia,
+//     xorshift}.out (copied as fixtures under tests/golden/ by tests/golden/make_golden.py), and
+//   * outputs of the reference binary itself (oracle/_ref/libexec/sstsim.x) for PHOLD, clock populations and
+//     per-component event-order traces (pdes.trace probe).
+//
+// Reference lines followed (all under /root/reference/src/sst/core/):
+//   activity.h:64-73,230-238   total order (delivery_time, priority<<32|order_tag, queue_order); priorities :29-40
+//   impl/timevortex/timeVortexPQ.cc:62-85   insert stamps queue_order = insertOrder++, pop = heap min
+//   link.cc:623-658            send: t = now + delay*timebase + latency; stamp (tag, delivery_info); insert
+//   baseComponent.cc:541-642   order tag = 1-based sequence number of configureLink calls (component id order)
+//   link.cc:469-479            self links keep tag 0xFFFFFFFF (configureSelfLink: not used by in-scope models)
+//   clock.cc:314-420           one Clock per period; handlers in registration order; first tick at `period`;
+//                              handler returning true is unregistered; re-insert at now+period
+//   simulation.cc:1099-1153    run loop: pop, set time, execute
+//   stopAction.h:27-57         StopAction priority 30: activities AT stop time with priority > 30 do not run
+//   exit.cc:53-79              primary-component refcount; serial: Exit action at now+1 (priority 99)
+//   rng/mersenne.cc:49-159, rng/marsaglia.cc:29-148, rng/xorshift.cc:44-140   generators
+//   rng/discrete.h:40-109, expon.h:73-77, gaussian.h:81-110, poisson.h:73-85, uniform.h   distributions
+//   statapi/stataccumulator.h:89-103,171-194   accumulator update and output fields
+//   testElements/message_mesh/enclosingComponent.cc:29-199, testElements/coreTest_RNGComponent.cc:26-109
+//   and oracle/probe/pdes_elements.cc for the PHOLD / clocknode models (ours, run by the reference core).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <queue>
+#include <string>
+#include <vector>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ RNG
+struct Random
+{
+    virtual ~Random() {}
+    virtual uint32_t u32()     = 0;
+    virtual double   uniform() = 0;
+    int32_t          i32()
+    {
+        uint32_t v = u32();
+        int32_t  r;
+        memcpy(&r, &v, 4);
+        return r;
+    }
+    int64_t i64()
+    {
+        uint32_t lo = u32();
+        uint32_t hi = u32();
+        uint64_t v  = (uint64_t)lo | ((uint64_t)hi << 32);
+        int64_t  r;
+        memcpy(&r, &v, 8);
+        return r;
+    }
+    uint64_t u64()
+    {
+        int64_t  v = i64();
+        uint64_t r;
+        memcpy(&r, &v, 8);
+        return r;
+    }
+};
+
+// rng/mersenne.cc:49-53 (ctor), :56-68 (batch), :76-102 (draw), :149-159 (seed)
+struct Mersenne : Random
+{
+    uint32_t numbers[624];
+    int      index;
+    explicit Mersenne(uint32_t seed)
+    {
+        numbers[0] = seed;
+        index      = 0;
+        for ( int i = 1; i < 624; i++ )
+            numbers[i] = 1812433253u * (numbers[i - 1] ^ (numbers[i - 1] >> 30)) + (uint32_t)i;
+    }
+    void batch()
+    {
+        index = 0;
+        for ( int i = 0; i < 624; ++i ) {
+            uint32_t temp = (numbers[i] & 0x80000000u) + (numbers[(i + 1) % 624] & 0x7fffffffu);
+            numbers[i]    = numbers[(i + 397) % 624] ^ (temp >> 1);
+            if ( temp % 2 != 0 ) numbers[i] ^= 2567483615u;
+        }
+    }
+    uint32_t u32() override
+    {
+        if ( index == 0 ) batch();
+        uint32_t t = numbers[index];
+        t ^= t >> 11;
+        t ^= (t << 7) & 2636928640u;
+        t ^= (t << 15) & 4022730752u;
+        t ^= t >> 18;
+        index = (index + 1) % 624;
+        return t;
+    }
+    double uniform() override
+    {
+        double d;
+        do {
+            d = (double)u32() / 4294967295.0;
+        } while ( d >= 1.0 );
+        return d;
+    }
+};
+
+// rng/marsaglia.cc:29-34 (ctor z,w), :64-87 (generateNext, nextUniform)
+struct Marsaglia : Random
+{
+    uint32_t z, w;
+    Marsaglia(uint32_t z, uint32_t w) : z(z), w(w) {}
+    uint32_t u32() override
+    {
+        z = 36969u * (z & 65535u) + (z >> 16);
+        w = 18000u * (w & 65535u) + (w >> 16);
+        return (z << 16) + w;
+    }
+    double uniform() override
+    {
+        double d;
+        do {
+            d = (double)(uint32_t)(u32() + 1u) * 2.328306435454494e-10;
+        } while ( d >= 1.0 );
+        return d;
+    }
+};
+
+// rng/xorshift.cc:44-50 (ctor), :58-77 (draw), :131-140 (seed)
+struct XorShift : Random
+{
+    uint32_t x, y, z, w;
+    explicit XorShift(uint32_t seed) : x(seed), y(0), z(0), w(0) {}
+    uint32_t u32() override
+    {
+        uint32_t t = x ^ (x << 11);
+        x          = y;
+        y          = z;
+        z          = w;
+        return w   = w ^ (w >> 19) ^ t ^ (t >> 8);
+    }
+    double uniform() override
+    {
+        double d;
+        do {
+            d = (double)u32() / 4294967295.0;
+        } while ( d >= 1.0 );
+        return d;
+    }
+};
+
+Random*
+makeRng(int kind, uint64_t s1, uint64_t s2)
+{
+    switch ( kind ) {
+    case 0:
+        return new Mersenne((uint32_t)s1);
+    case 1:
+        return new Marsaglia((uint32_t)s1, (uint32_t)s2);
+    default:
+        return new XorShift((uint32_t)s1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ statistics
+// statapi/stataccumulator.h:89-95 (addData_impl), statbase.h:393-401 (count++), :171-194 (output fields)
+template <typename T>
+struct Accumulator
+{
+    T        sum = 0, sumsq = 0;
+    T        mn = std::numeric_limits<T>::max();
+    T        mx = std::numeric_limits<T>::min();
+    uint64_t count = 0;
+    void     add(T v)
+    {
+        sum += v;
+        sumsq += v * v;
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+        count++;
+    }
+    // Output order Sum, SumSQ, Count, Min, Max; Min/Max print 0 when nothing was collected.
+    void out(uint64_t* r) const
+    {
+        r[0] = (uint64_t)(int64_t)sum;
+        r[1] = (uint64_t)(int64_t)sumsq;
+        r[2] = count;
+        r[3] = count ? (uint64_t)(int64_t)mn : 0;
+        r[4] = count ? (uint64_t)(int64_t)mx : 0;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ engine
+enum : uint64_t { PRIO_STOP = 30, PRIO_CLOCK = 40, PRIO_EVENT = 50, PRIO_EXIT = 99 };
+enum { KIND_EVENT, KIND_CLOCK, KIND_STOP, KIND_EXIT };
+enum { TYPE_MESH = 1, TYPE_PHOLD = 2, TYPE_CLOCKNODE = 3, TYPE_RNGCOMP = 4 };
+constexpr int      NPARAM   = 8;
+constexpr int      NRESULT  = 32;
+constexpr uint32_t NO_PEER  = 0xFFFFFFFFu;
+
+struct Activity
+{
+    uint64_t time, prio_order, queue_order;
+    int      kind;
+    uint32_t target; // event: receiving directed port; clock: clock index
+    uint64_t payload;
+};
+struct ActGreater
+{
+    bool operator()(const Activity& a, const Activity& b) const
+    {
+        if ( a.time != b.time ) return a.time > b.time;
+        if ( a.prio_order != b.prio_order ) return a.prio_order > b.prio_order;
+        return a.queue_order > b.queue_order;
+    }
+};
+
+inline uint64_t
+mixDelivery(uint64_t h, uint64_t time, uint64_t port, uint64_t payload)
+{
+    uint64_t v = time * 0x9E3779B97F4A7C15ull + (port + 1) * 0xC2B2AE3D27D4EB4Full + payload;
+    h ^= v;
+    h *= 0x100000001B3ull;
+    h ^= h >> 29;
+    return h;
+}
+
+struct Sim;
+struct Component
+{
+    Sim*     sim  = nullptr;
+    uint32_t id   = 0; // global component id (creation order)
+    uint32_t port0 = 0, nports = 0;
+    virtual ~Component() {}
+    virtual void setup() {}
+    virtual void handleEvent(int /*port*/, uint64_t& /*payload*/) {}
+    virtual bool tick(uint64_t /*cycle*/) { return true; }
+    virtual void results(uint64_t* /*r*/) const {}
+    void         send(int port, uint64_t delay, uint64_t payload);
+};
+
+struct ClockObj
+{
+    uint64_t              period;
+    std::vector<uint32_t> handlers; // component ids in registration order
+    uint64_t              cycle = 0;
+};
+
+struct TraceRec
+{
+    uint64_t time;
+    uint32_t comp, port;
+    uint64_t payload;
+};
+
+struct Sim
+{
+    uint32_t                 ncomp = 0;
+    std::vector<Component*>  comps;
+    std::vector<uint32_t>    port_off, peer_port, port_comp, port_tag;
+    std::vector<uint64_t>    latency;
+    std::vector<ClockObj>    clocks;
+    std::priority_queue<Activity, std::vector<Activity>, ActGreater> pq;
+    uint64_t                 insert_order = 0;
+    uint64_t                 now = 0, stop_at = 0, end_time = 0;
+    uint64_t                 events_delivered = 0, clock_ticks = 0;
+    int64_t                  primary = 0;
+    bool                     end_sim = false, in_run = false, stats_on = true, tracing = false;
+    std::vector<TraceRec>    trace;
+
+    ~Sim()
+    {
+        for ( auto c : comps )
+            delete c;
+    }
+    void insert(Activity a)
+    {
+        a.queue_order = insert_order++;
+        pq.push(a);
+    }
+    void registerClock(uint32_t comp, uint64_t period)
+    {
+        // simulation.cc:1403-1427: one Clock per period; created + scheduled on first registration (clock.cc:400-420:
+        // at time 0 the first tick is at `period`).
+        for ( size_t i = 0; i < clocks.size(); ++i )
+            if ( clocks[i].period == period ) {
+                clocks[i].handlers.push_back(comp);
+                return;
+            }
+        ClockObj c;
+        c.period = period;
+        c.handlers.push_back(comp);
+        clocks.push_back(c);
+        insert({ period, PRIO_CLOCK << 32, 0, KIND_CLOCK, (uint32_t)(clocks.size() - 1), 0 });
+    }
+    void primaryOK()
+    {
+        // exit.cc:53-68
+        if ( --primary == 0 ) {
+            end_time = now;
+            insert({ now + 1, PRIO_EXIT << 32, 0, KIND_EXIT, 0, 0 });
+        }
+    }
+    void run()
+    {
+        if ( stop_at ) insert({ stop_at, PRIO_STOP << 32, 0, KIND_STOP, 0, 0 });
+        in_run = true;
+        for ( auto c : comps )
+            c->setup();
+        while ( !end_sim && !pq.empty() ) {
+            Activity a = pq.top();
+            pq.pop();
+            now = a.time;
+            switch ( a.kind ) {
+            case KIND_EVENT:
+            {
+                uint32_t   c = port_comp[a.target];
+                Component* k = comps[c];
+                events_delivered++;
+                if ( tracing ) trace.push_back({ now, c, a.target - k->port0, a.payload });
+                k->handleEvent((int)(a.target - k->port0), a.payload);
+                break;
+            }
+            case KIND_CLOCK:
+            {
+                ClockObj& ck = clocks[a.target];
+                if ( ck.handlers.empty() ) break; // clock.cc:316-319: goes unscheduled
+                ck.cycle++;
+                size_t keep = 0;
+                for ( size_t i = 0; i < ck.handlers.size(); ++i ) {
+                    clock_ticks++;
+                    bool done = comps[ck.handlers[i]]->tick(ck.cycle);
+                    if ( !done ) ck.handlers[keep++] = ck.handlers[i];
+                }
+                ck.handlers.resize(keep);
+                insert({ now + ck.period, PRIO_CLOCK << 32, 0, KIND_CLOCK, a.target, 0 });
+                break;
+            }
+            case KIND_STOP:
+                end_sim  = true;
+                end_time = now;
+                break;
+            case KIND_EXIT:
+                end_sim = true;
+                break;
+            }
+        }
+    }
+};
+
+void
+Component::send(int port, uint64_t delay, uint64_t payload)
+{
+    uint32_t p    = port0 + (uint32_t)port;
+    uint32_t peer = sim->peer_port[p];
+    if ( peer == NO_PEER ) return;
+    uint64_t t = sim->now + delay + sim->latency[p];
+    sim->insert({ t, (PRIO_EVENT << 32) | sim->port_tag[peer], 0, KIND_EVENT, peer, payload });
+}
+
+// ------------------------------------------------------------------------------------------------ models
+// testElements/message_mesh/enclosingComponent.cc
+struct MeshComp : Component
+{
+    int                   my_id, mod;
+    int32_t               message_count = 0;
+    Mersenne              rng;
+    Accumulator<uint64_t> mcnt;
+    std::vector<uint32_t> counts, base; // links per MessagePort, flattened base index
+    MeshComp(const int64_t* p) : my_id((int)p[0]), mod((int)p[1]), rng((uint32_t)(p[0] + 100))
+    {
+        int      ng = (int)p[4];
+        uint32_t b  = 0;
+        for ( int g = 0; g < ng; ++g ) {
+            uint32_t c = (uint32_t)((p[5] >> (8 * g)) & 0xFF);
+            counts.push_back(c);
+            base.push_back(b);
+            b += c;
+        }
+    }
+    void setup() override
+    {
+        // RouteMessage::sendInitialEvents :188-199
+        for ( size_t i = 0; i < counts.size(); i++ )
+            for ( uint32_t j = 0; j < counts[i]; j++ )
+                if ( (rng.u32() % (uint32_t)mod) == 0 ) send((int)(base[i] + j), 0, 0);
+    }
+    void handleEvent(int, uint64_t& payload) override
+    {
+        message_count++; // EnclosingComponent::handleEvent :92-99
+        // RouteMessage::send :179-186
+        int      nextport = (int)(rng.u32() % (uint32_t)counts.size());
+        uint32_t portnum  = rng.u32() % counts[nextport];
+        send((int)(base[nextport] + portnum), 0, payload);
+        if ( sim->stats_on ) mcnt.add(1);
+    }
+    void results(uint64_t* r) const override
+    {
+        r[0] = (uint64_t)(int64_t)message_count;
+        mcnt.out(r + 1);
+    }
+};
+
+// oracle/probe/pdes_elements.cc PholdNode
+struct PholdComp : Component
+{
+    int64_t               id_, init_;
+    uint32_t              dmod;
+    uint64_t              recv = 0, hash = 0;
+    XorShift              rng;
+    Accumulator<uint64_t> delay;
+    PholdComp(const int64_t* p) : id_(p[0]), init_(p[1]), dmod((uint32_t)p[2]), rng((uint32_t)(p[0] + 1)) {}
+    void setup() override
+    {
+        for ( int64_t i = 0; i < init_; ++i ) {
+            uint32_t pp = rng.u32() % nports;
+            uint64_t d  = rng.u32() % dmod;
+            send((int)pp, d, d);
+        }
+    }
+    void handleEvent(int port, uint64_t& payload) override
+    {
+        recv++;
+        if ( sim->stats_on ) delay.add(payload);
+        hash        = mixDelivery(hash, sim->now, (uint64_t)port, payload);
+        uint32_t pp = rng.u32() % nports;
+        uint64_t d  = rng.u32() % dmod;
+        send((int)pp, d, d);
+    }
+    void results(uint64_t* r) const override
+    {
+        r[0] = recv;
+        r[1] = hash;
+        delay.out(r + 2);
+    }
+};
+
+// oracle/probe/pdes_elements.cc ClockNode
+struct ClockNodeComp : Component
+{
+    int32_t          commFreq;
+    uint32_t         neighbor;
+    uint64_t         ticks = 0, last_cycle = 0, recv = 0, hash = 0;
+    Marsaglia        rng;
+    Accumulator<int> count[4];
+    ClockNodeComp(const int64_t* p) : commFreq((int32_t)p[1]), rng((uint32_t)(11 + p[0]), 272727u)
+    {
+        neighbor = rng.u32() % 4;
+    }
+    bool tick(uint64_t cycle) override
+    {
+        ticks++;
+        last_cycle = cycle;
+        if ( (rng.i32() % commFreq) == 0 ) {
+            neighbor = (neighbor + 1) % 4;
+            if ( neighbor < nports && sim->peer_port[port0 + neighbor] != NO_PEER ) {
+                send((int)neighbor, 0, 0);
+                if ( sim->stats_on ) count[neighbor].add(1);
+            }
+        }
+        return false;
+    }
+    void handleEvent(int port, uint64_t&) override
+    {
+        recv++;
+        hash = mixDelivery(hash, sim->now, (uint64_t)port, ticks);
+    }
+    void results(uint64_t* r) const override
+    {
+        r[0] = ticks;
+        r[1] = last_cycle;
+        r[2] = recv;
+        r[3] = hash;
+        for ( int i = 0; i < 4; ++i )
+            count[i].out(r + 4 + 5 * i);
+    }
+};
+
+// testElements/coreTest_RNGComponent.cc:26-109
+struct RngComp : Component
+{
+    Random*  rng;
+    int64_t  max_count;
+    int64_t  rng_count = 0;
+    uint64_t last[5]   = { 0, 0, 0, 0, 0 };
+    uint64_t hash      = 0;
+    RngComp(const int64_t* p) : rng(makeRng((int)p[0], (uint64_t)p[1], (uint64_t)p[2])), max_count(p[3]) {}
+    ~RngComp() { delete rng; }
+    bool tick(uint64_t) override
+    {
+        double   nU  = rng->uniform();
+        uint32_t U32 = rng->u32();
+        uint64_t U64 = rng->u64();
+        int32_t  I32 = rng->i32();
+        int64_t  I64 = rng->i64();
+        rng_count++;
+        memcpy(&last[0], &nU, 8);
+        last[1] = U32;
+        last[2] = U64;
+        last[3] = (uint64_t)(int64_t)I32;
+        last[4] = (uint64_t)I64;
+        for ( int i = 0; i < 5; ++i )
+            hash = mixDelivery(hash, (uint64_t)rng_count, (uint64_t)i, last[i]);
+        if ( rng_count == max_count ) {
+            sim->primaryOK();
+            return true;
+        }
+        return false;
+    }
+    void results(uint64_t* r) const override
+    {
+        r[0] = (uint64_t)rng_count;
+        for ( int i = 0; i < 5; ++i )
+            r[1 + i] = last[i];
+        r[6] = hash;
+    }
+};
+
+} // namespace
+
+// ================================================================================================ C interface
+extern "C" {
+
+// Build a serial simulation from the raw wired-model arrays (same layout the product's C-ABI takes; see
+// include/sstb200.h): component types + 8 int64 params each, directed-port CSR in configureLink order, peer port and
+// send latency per directed port, clock period per component (0 = none), stop time (0 = none).
+void*
+oracle_create(uint32_t ncomp, const uint32_t* comp_type, const int64_t* comp_param, const uint32_t* port_off,
+    const uint32_t* peer_port, const uint64_t* latency, const uint64_t* clock_period, uint64_t stop_at, int stats_on,
+    int tracing)
+{
+    Sim* s      = new Sim();
+    s->ncomp    = ncomp;
+    s->stop_at  = stop_at;
+    s->stats_on = stats_on != 0;
+    s->tracing  = tracing != 0;
+    s->port_off.assign(port_off, port_off + ncomp + 1);
+    uint32_t nport = port_off[ncomp];
+    s->peer_port.assign(peer_port, peer_port + nport);
+    s->latency.assign(latency, latency + nport);
+    s->port_comp.resize(nport);
+    s->port_tag.resize(nport);
+    uint32_t next_tag = 1; // simulation.h:566-572
+    for ( uint32_t c = 0; c < ncomp; ++c ) {
+        const int64_t* p = comp_param + (size_t)c * NPARAM;
+        Component*     k = nullptr;
+        switch ( comp_type[c] ) {
+        case TYPE_MESH:
+            k = new MeshComp(p);
+            break;
+        case TYPE_PHOLD:
+            k = new PholdComp(p);
+            break;
+        case TYPE_CLOCKNODE:
+            k = new ClockNodeComp(p);
+            break;
+        case TYPE_RNGCOMP:
+            k = new RngComp(p);
+            break;
+        default:
+            delete s;
+            return nullptr;
+        }
+        k->sim    = s;
+        k->id     = c;
+        k->port0  = port_off[c];
+        k->nports = port_off[c + 1] - port_off[c];
+        s->comps.push_back(k);
+        for ( uint32_t q = port_off[c]; q < port_off[c + 1]; ++q ) {
+            s->port_comp[q] = c;
+            // connected ports get the next tag in configureLink order.  (configureSelfLink links, which keep tag
+            // 0xFFFFFFFF (link.cc:469-479), are not used by any in-scope model and are not representable here; a
+            // config-graph loopback, peer == own port, is configured like any other link.)
+            s->port_tag[q] = (peer_port[q] == NO_PEER) ? 0 : next_tag++;
+        }
+        // every in-scope model registers as primary and says DoNotEndSim in its constructor
+        s->primary++;
+        if ( clock_period[c] ) s->registerClock(c, clock_period[c]);
+    }
+    return s;
+}
+
+void
+oracle_destroy(void* h)
+{
+    delete (Sim*)h;
+}
+
+void
+oracle_run(void* h)
+{
+    ((Sim*)h)->run();
+}
+
+// results[ncomp][32] u64, type-specific meaning (see include/sstb200.h "result record")
+void
+oracle_results(void* h, uint64_t* out)
+{
+    Sim* s = (Sim*)h;
+    memset(out, 0, sizeof(uint64_t) * NRESULT * s->ncomp);
+    for ( uint32_t c = 0; c < s->ncomp; ++c )
+        s->comps[c]->results(out + (size_t)c * NRESULT);
+}
+
+// counters: [0] events delivered, [1] clock handler invocations, [2] end time, [3] trace length
+void
+oracle_counters(void* h, uint64_t* out)
+{
+    Sim* s = (Sim*)h;
+    out[0] = s->events_delivered;
+    out[1] = s->clock_ticks;
+    out[2] = s->end_time;
+    out[3] = s->trace.size();
+}
+
+// trace in global delivery order: time[], comp[], port[], payload[]
+void
+oracle_trace(void* h, uint64_t* time, uint32_t* comp, uint32_t* port, uint64_t* payload)
+{
+    Sim* s = (Sim*)h;
+    for ( size_t i = 0; i < s->trace.size(); ++i ) {
+        time[i]    = s->trace[i].time;
+        comp[i]    = s->trace[i].comp;
+        port[i]    = s->trace[i].port;
+        payload[i] = s->trace[i].payload;
+    }
+}
+
+// Raw generator stream: n draws of generateNextUInt32().  kind: 0 mersenne(seed=s1), 1 marsaglia(z=s1,w=s2),
+// 2 xorshift(seed=s1).  `skip` draws are discarded first.  out may be NULL (checksum only).
+// Returns the 64-bit checksum sum_i (i+1+skip)*draw_i mod 2^64 (position-sensitive).
+uint64_t
+oracle_rng_u32_stream(int kind, uint64_t s1, uint64_t s2, uint64_t skip, uint64_t n, uint32_t* out)
+{
+    Random* r = makeRng(kind, s1, s2);
+    for ( uint64_t i = 0; i < skip; ++i )
+        r->u32();
+    uint64_t cs = 0;
+    for ( uint64_t i = 0; i < n; ++i ) {
+        uint32_t v = r->u32();
+        if ( out ) out[i] = v;
+        cs += (i + 1 + skip) * (uint64_t)v;
+    }
+    delete r;
+    return cs;
+}
+
+// The coreTestRNGComponent tick sequence: per tick (nextUniform, u32, u64, i32, i64) -> 5 u64 words
+// (double bit pattern, zero-extended u32, u64, sign-extended i32, i64).  Writes ticks [first, first+n).
+void
+oracle_rng_ticks(int kind, uint64_t s1, uint64_t s2, uint64_t first, uint64_t n, uint64_t* out)
+{
+    Random* r = makeRng(kind, s1, s2);
+    for ( uint64_t t = 0; t < first + n; ++t ) {
+        double   nU  = r->uniform();
+        uint32_t U32 = r->u32();
+        uint64_t U64 = r->u64();
+        int32_t  I32 = r->i32();
+        int64_t  I64 = r->i64();
+        if ( t >= first ) {
+            uint64_t* o = out + (t - first) * 5;
+            memcpy(&o[0], &nU, 8);
+            o[1] = U32;
+            o[2] = U64;
+            o[3] = (uint64_t)(int64_t)I32;
+            o[4] = (uint64_t)I64;
+        }
+    }
+    delete r;
+}
+
+// ------------------------------------------------------------------------------------------------ distributions
+// kind of distribution: 0 discrete (rng/discrete.h:40-109), 1 exponential (expon.h:73-77), 2 gaussian
+// (gaussian.h:81-110), 3 poisson (poisson.h:73-85), 4 uniform (uniform.h), 5 constant (constant.h).
+// params: discrete: probs[np]; expon: lambda; gaussian: mean, stddev; poisson: lambda; uniform: bins; constant: v.
+// The base generator is given by (rng kind, s1, s2).
+void
+oracle_distribution(int dist, const double* params, int np, int rng_kind, uint64_t s1, uint64_t s2, uint64_t n,
+    double* out)
+{
+    Random* r = makeRng(rng_kind, s1, s2);
+    switch ( dist ) {
+    case 0:
+    {
+        // discrete.h:40-55: probabilities[i] = exclusive prefix sum; :96-109: first index with prob >= nextD wins,
+        // scanning from index 0 upward; result is the index (as double)
+        std::vector<double> prefix(np);
+        double              sum = 0;
+        for ( int i = 0; i < np; ++i ) {
+            prefix[i] = sum;
+            sum += params[i];
+        }
+        for ( uint64_t k = 0; k < n; ++k ) {
+            const double nextD = r->uniform();
+            uint32_t     index = 0;
+            for ( ; index < (uint32_t)np; index++ )
+                if ( prefix[index] >= nextD ) break;
+            out[k] = (double)index;
+        }
+        break;
+    }
+    case 1:
+        for ( uint64_t k = 0; k < n; ++k ) {
+            const double next = r->uniform();
+            out[k]            = log(1 - next) / (-1 * params[0]);
+        }
+        break;
+    case 2:
+    {
+        bool   usePair    = false; // gaussian.h ctor: no cached value at start
+        double unusedPair = 0;
+        for ( uint64_t k = 0; k < n; ++k ) {
+            if ( usePair ) {
+                usePair = false;
+                out[k]  = unusedPair;
+            }
+            else {
+                double gauss_u, gauss_v, sq_sum;
+                do {
+                    gauss_u = r->uniform();
+                    gauss_v = r->uniform();
+                    sq_sum  = (gauss_u * gauss_u) + (gauss_v * gauss_v);
+                } while ( sq_sum >= 1 || sq_sum == 0 );
+                if ( r->uniform() < 0.5 ) gauss_u *= -1.0;
+                if ( r->uniform() < 0.5 ) gauss_v *= -1.0;
+                double multiplier = sqrt(-2.0 * log(sq_sum) / sq_sum);
+                unusedPair        = params[0] + params[1] * gauss_v * multiplier;
+                usePair           = true;
+                out[k]            = params[0] + params[1] * gauss_u * multiplier;
+            }
+        }
+        break;
+    }
+    case 3:
+        for ( uint64_t k = 0; k < n; ++k ) {
+            const double L = exp(-params[0]);
+            double       p = 1.0;
+            int          kk = 0;
+            do {
+                kk++;
+                p *= r->uniform();
+            } while ( p > L );
+            out[k] = (double)(kk - 1);
+        }
+        break;
+    case 4:
+        for ( uint64_t k = 0; k < n; ++k ) {
+            // uniform.h: walks bins: probPerBin = 1/bins; first bin whose cumulative probability exceeds the draw
+            const uint32_t bins       = (uint32_t)params[0];
+            const double   probPerBin = 1.0 / (double)bins;
+            const double   nextD      = r->uniform();
+            uint32_t       current_bin = 1;
+            while ( nextD > ((double)current_bin * probPerBin) )
+                current_bin++;
+            out[k] = (double)(current_bin - 1);
+        }
+        break;
+    default:
+        for ( uint64_t k = 0; k < n; ++k )
+            out[k] = params[0];
+    }
+    delete r;
+}
+
+} // extern "C"

@@ -1,0 +1,363 @@
+"""The model-description surface: a stand-in for the reference's embedded-Python module ``sst``.
+
+Mirrors (names, argument meaning, error behaviour) the subset of
+``src/sst/core/model/python/pymodel.cc:990-1045`` (module functions),
+``pymodel_comp.cc:578-601,684-703`` (Component / SubComponent methods) and
+``pymodel_link.cc:38-120,188-192`` (Link) that GPU-eligible models use, and builds the same graph the reference's
+``ConfigGraph`` would (``model/configGraph.cc:320-455``): components numbered from 0 in creation order, links in
+``sst.Link()`` creation order, a link's endpoint 0/1 in attach order.
+
+A model script does ``import sst`` exactly as under the reference; :func:`install` puts this module into
+``sys.modules['sst']`` for the duration of the script (the reference does the same through
+``PyImport_AppendInittab("sst", ...)``, pymodel.cc:1144).
+"""
+from __future__ import annotations
+
+import sys
+import types
+from typing import Optional
+
+
+class ModelError(RuntimeError):
+    """Raised where the reference raises a Python exception or calls Output::fatal while building the graph."""
+
+
+class ConfigLink:
+    __slots__ = ("id", "name", "latency", "no_cut", "ends")
+
+    def __init__(self, lid: int, name: str, latency: Optional[str]):
+        self.id = lid
+        self.name = name
+        self.latency = latency
+        self.no_cut = False
+        self.ends = []  # [(ConfigComponent, port name, latency string)]
+
+
+class ConfigComponent:
+    """A component or subcomponent node of the graph (model/configComponent.h)."""
+
+    __slots__ = ("graph", "id", "name", "type", "params", "links", "subs", "parent", "slot", "slot_num",
+                 "rank", "thread", "weight", "stats_enabled", "stat_params", "stat_load_level")
+
+    def __init__(self, graph, cid, name, ctype, parent=None, slot=None, slot_num=0):
+        self.graph = graph
+        self.id = cid
+        self.name = name
+        self.type = ctype
+        self.params = {}
+        self.links = []  # [(port name, ConfigLink, endpoint index)]
+        self.subs = []  # ConfigComponent children, in creation order
+        self.parent = parent
+        self.slot = slot
+        self.slot_num = slot_num
+        self.rank = None
+        self.thread = None
+        self.weight = 1.0
+        self.stats_enabled = None  # None | "all" | [names]
+        self.stat_params = {}
+        self.stat_load_level = None
+
+    # full name rule: componentInfo.cc:125-144 -- parent:slot, with [n] only when the slot holds several
+    def full_name(self) -> str:
+        if self.parent is None:
+            return self.name
+        sibs = [s for s in self.parent.subs if s.slot == self.slot]
+        idx = f"[{self.slot_num}]" if len(sibs) > 1 else ""
+        return f"{self.parent.full_name()}:{self.slot}{idx}"
+
+    def top(self):
+        c = self
+        while c.parent is not None:
+            c = c.parent
+        return c
+
+    def sub_in_slot(self, slot):
+        return sorted((s for s in self.subs if s.slot == slot), key=lambda s: s.slot_num)
+
+
+class ConfigGraph:
+    def __init__(self):
+        self.components = []  # top-level, id order
+        self.links = []
+        self.link_by_name = {}
+        self.program_options = {}
+        self.stat_output = ("sst.statOutputConsole", {})
+        self.stat_load_level = 0
+        self.enable_all_stats = None  # None or params dict
+        self.name_prefix = []
+        self.comp_by_name = {}
+        self.n_ranks = 1
+        self.my_rank = 0
+        self.n_threads = 1
+
+
+_graph: Optional[ConfigGraph] = None
+
+
+def _g() -> ConfigGraph:
+    if _graph is None:
+        raise ModelError("sst module used outside of a model-building context")
+    return _graph
+
+
+# ------------------------------------------------------------------------------------------------ object types
+class _CompBase:
+    def __init__(self, cfg: ConfigComponent):
+        self._c = cfg
+
+    def addParam(self, name, value):
+        self._c.params[str(name)] = _param_str(value)
+
+    def addParams(self, d):
+        if not isinstance(d, dict):
+            raise TypeError("addParams requires a dict")
+        for k, v in d.items():
+            self._c.params[str(k)] = _param_str(v)
+
+    def addLink(self, link, port, latency=None):
+        if not isinstance(link, Link):
+            raise TypeError("addLink requires an sst.Link")
+        cl = link._l
+        lat = latency if latency is not None else cl.latency
+        if lat is None:
+            raise ModelError(f"no latency specified for link {cl.name} on port {port}")
+        if len(cl.ends) >= 2:
+            raise ModelError(f"Link {cl.name} already has two endpoints (configGraph.cc addLink)")
+        cl.ends.append((self._c, str(port), str(lat)))
+        self._c.links.append((str(port), cl, len(cl.ends) - 1))
+
+    def setSubComponent(self, slot, ctype, slot_num=0):
+        for s in self._c.subs:
+            if s.slot == slot and s.slot_num == slot_num:
+                raise ModelError(f"slot {slot}[{slot_num}] of {self._c.full_name()} already populated")
+        child = ConfigComponent(self._c.graph, None, None, str(ctype), parent=self._c, slot=str(slot),
+                                slot_num=int(slot_num))
+        self._c.subs.append(child)
+        return SubComponent(child)
+
+    def getFullName(self):
+        return self._c.full_name()
+
+    def getType(self):
+        return self._c.type
+
+    def enableAllStatistics(self, params=None, recursive=False):
+        self._c.stats_enabled = "all"
+        self._c.stat_params = dict(params or {})
+
+    def enableStatistics(self, names, params=None, recursive=False):
+        cur = self._c.stats_enabled if isinstance(self._c.stats_enabled, list) else []
+        self._c.stats_enabled = cur + list(names)
+        self._c.stat_params = dict(params or {})
+
+    def enableStatistic(self, name, params=None, recursive=False):
+        self.enableStatistics([name], params)
+
+    def setStatisticLoadLevel(self, level, recursive=False):
+        self._c.stat_load_level = int(level)
+
+    def setCoordinates(self, *a):
+        pass
+
+    def addSharedParamSet(self, name):
+        shared = _g().program_options.setdefault("__shared__", {}).get(name, {})
+        for k, v in shared.items():
+            self._c.params.setdefault(k, v)
+
+    addGlobalParamSet = addSharedParamSet
+
+
+class Component(_CompBase):
+    def __init__(self, name, ctype):
+        g = _g()
+        full = "".join(p + "." for p in g.name_prefix) + str(name)
+        if full in g.comp_by_name:
+            raise ModelError(f"ERROR: trying to add Component with name that already exists: {full}")
+        cfg = ConfigComponent(g, len(g.components), full, str(ctype))
+        g.components.append(cfg)
+        g.comp_by_name[full] = cfg
+        super().__init__(cfg)
+
+    def setRank(self, rank, thread=0):
+        self._c.rank = int(rank)
+        self._c.thread = int(thread)
+
+    def setWeight(self, w):
+        self._c.weight = float(w)
+
+
+class SubComponent(_CompBase):
+    pass
+
+
+class Link:
+    def __init__(self, name, latency=None):
+        g = _g()
+        full = "".join(p + "." for p in g.name_prefix) + str(name)
+        self._l = ConfigLink(len(g.links), full, None if latency is None else str(latency))
+        g.links.append(self._l)
+        g.link_by_name[full] = self._l
+
+    def connect(self, end0, end1):
+        for end in (end0, end1):
+            comp, port = end[0], end[1]
+            lat = end[2] if len(end) > 2 else None
+            comp.addLink(self, port, lat)
+
+    def setNoCut(self):
+        self._l.no_cut = True
+
+
+def _param_str(v) -> str:
+    if isinstance(v, bool):
+        return "1" if v else "0"
+    return str(v)
+
+
+# ------------------------------------------------------------------------------------------------ module functions
+def setProgramOption(name, value):
+    _g().program_options[str(name)] = str(value)
+
+
+def setProgramOptions(d):
+    for k, v in d.items():
+        setProgramOption(k, v)
+
+
+def getProgramOptions():
+    return {k: v for k, v in _g().program_options.items() if not k.startswith("__")}
+
+
+def pushNamePrefix(p):
+    _g().name_prefix.append(str(p))
+
+
+def popNamePrefix():
+    _g().name_prefix.pop()
+
+
+def getMPIRankCount():
+    return _g().n_ranks
+
+
+def getMyMPIRank():
+    return _g().my_rank
+
+
+def getThreadCount():
+    return _g().n_threads
+
+
+def setThreadCount(n):
+    _g().n_threads = int(n)
+
+
+def setStatisticOutput(name, params=None):
+    _g().stat_output = (str(name), dict(params or {}))
+
+
+def setStatisticOutputOption(k, v):
+    _g().stat_output[1][str(k)] = str(v)
+
+
+def setStatisticOutputOptions(d):
+    for k, v in d.items():
+        setStatisticOutputOption(k, v)
+
+
+def setStatisticLoadLevel(level):
+    _g().stat_load_level = int(level)
+
+
+def enableAllStatisticsForAllComponents(params=None):
+    _g().enable_all_stats = dict(params or {})
+
+
+def enableAllStatisticsForComponentName(name, params=None, recursive=False):
+    c = _g().comp_by_name.get(name)
+    if c is None:
+        raise ModelError(f"component name {name} not found")
+    c.stats_enabled = "all"
+    c.stat_params = dict(params or {})
+
+
+def enableAllStatisticsForComponentType(ctype, params=None, recursive=False):
+    for c in _g().components:
+        if c.type == ctype:
+            c.stats_enabled = "all"
+            c.stat_params = dict(params or {})
+
+
+def findComponentByName(name):
+    c = _g().comp_by_name.get(name)
+    if c is None:
+        return None
+    obj = Component.__new__(Component)
+    _CompBase.__init__(obj, c)
+    return obj
+
+
+def addSharedParam(set_name, key, value):
+    _g().program_options.setdefault("__shared__", {}).setdefault(set_name, {})[str(key)] = _param_str(value)
+
+
+def addSharedParams(set_name, d):
+    for k, v in d.items():
+        addSharedParam(set_name, k, v)
+
+
+addGlobalParam = addSharedParam
+addGlobalParams = addSharedParams
+
+
+def exit():
+    raise SystemExit(0)
+
+
+_API = [
+    "Component", "SubComponent", "Link", "setProgramOption", "setProgramOptions", "getProgramOptions",
+    "pushNamePrefix", "popNamePrefix", "getMPIRankCount", "getMyMPIRank", "getThreadCount", "setThreadCount",
+    "setStatisticOutput", "setStatisticOutputOption", "setStatisticOutputOptions", "setStatisticLoadLevel",
+    "enableAllStatisticsForAllComponents", "enableAllStatisticsForComponentName",
+    "enableAllStatisticsForComponentType", "findComponentByName", "addSharedParam", "addSharedParams",
+    "addGlobalParam", "addGlobalParams", "exit",
+]
+
+
+def make_module() -> types.ModuleType:
+    m = types.ModuleType("sst")
+    m.__doc__ = "sst_core_b200 stand-in for the reference's embedded `sst` module"
+    here = sys.modules[__name__]
+    for n in _API:
+        setattr(m, n, getattr(here, n))
+    return m
+
+
+def build_graph(script_path: str, model_options: str = "", n_ranks: int = 1, my_rank: int = 0) -> ConfigGraph:
+    """Run a model script with ``sst`` bound to this module and ``sys.argv`` set from ``--model-options``
+    (main.cc:311-386 start_graph_creation).  Returns the ConfigGraph it built."""
+    global _graph
+    import shlex
+
+    g = ConfigGraph()
+    g.n_ranks, g.my_rank = n_ranks, my_rank
+    prev_graph, prev_mod, prev_argv = _graph, sys.modules.get("sst"), sys.argv
+    _graph = g
+    sys.modules["sst"] = make_module()
+    sys.argv = [script_path] + shlex.split(model_options)
+    try:
+        with open(script_path) as f:
+            code = compile(f.read(), script_path, "exec")
+        exec(code, {"__name__": "__main__", "__file__": script_path})
+    finally:
+        sys.argv = prev_argv
+        _graph = prev_graph
+        if prev_mod is not None:
+            sys.modules["sst"] = prev_mod
+        else:
+            sys.modules.pop("sst", None)
+    for l in g.links:
+        if len(l.ends) == 1:
+            # the reference tolerates dangling links only with a warning at checkForStructuralErrors
+            pass
+    return g

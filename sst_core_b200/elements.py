@@ -1,0 +1,196 @@
+"""Host-side descriptors of the GPU-eligible element types (the ELI-facing half of each device component).
+
+In the reference a component library registers builders + metadata with static initialisers
+(``SST_ELI_REGISTER_COMPONENT`` component.h:93-95, ``SST_ELI_DOCUMENT_PARAMS/PORTS/STATISTICS``), and the
+constructor reads ``Params`` and calls ``configureLink`` / ``registerClock`` / ``registerStatistic``
+(baseComponent.cc:501-642).  A device component has the same two halves:
+
+* device half  -- POD state + ``__device__`` handler functors, compiled into libsstb200.so
+  (``sst_core_b200/csrc/components.cuh``; the native type table is queried through
+  ``sstb200_component_type_*`` and cross-checked against this file at import time);
+* host half    -- THIS file: for each ELI name, the rule that turns a ConfigComponent (params, subcomponent tree,
+  connected ports) into the wired record the engine consumes: type code, 8 int64 params, the ordered list of
+  ports exactly in the order the reference constructor would call ``configureLink`` (that order defines the
+  delivery order tags, baseComponent.cc:636), the clock period, and the statistics it registers.
+
+Errors mirror the reference constructors' ``Output::fatal`` calls (raised as ModelError).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Tuple
+
+from .config import ConfigComponent, ModelError
+from .timelord import TimeLord
+
+TYPE_MESH, TYPE_PHOLD, TYPE_CLOCKNODE, TYPE_RNGCOMP = 1, 2, 3, 4
+NPARAM = 8
+NRESULT = 32
+
+
+@dataclass
+class StatDesc:
+    owner_name: str  # full name of the (sub)component that registered it
+    name: str
+    subid: str
+    dtype: str  # "u64" | "i32"
+    offset: Optional[int]  # word offset of the 5-word accumulator in the result record; None = never updated
+
+
+@dataclass
+class Wired:
+    type_code: int
+    params: List[int]
+    ports: List[Tuple[ConfigComponent, str]]  # (owner (sub)component, port name) in configureLink order
+    clock_period: int = 0
+    stats: List[StatDesc] = field(default_factory=list)
+    finish: Optional[Callable] = None  # (result record) -> console line or None
+
+
+def _find_int(c: ConfigComponent, key: str, default=None, required_msg=None) -> int:
+    if key not in c.params:
+        if required_msg is not None:
+            raise ModelError(required_msg)
+        return default
+    v = c.params[key].strip()
+    try:
+        return int(v, 0)
+    except ValueError:
+        try:
+            return int(float(v))
+        except ValueError:
+            low = v.lower()
+            if low in ("true", "t", "yes"):
+                return 1
+            if low in ("false", "f", "no"):
+                return 0
+            raise ModelError(f"parameter {key}={v!r} of {c.full_name()} is not an integer")
+
+
+def _connected_numbered_ports(c: ConfigComponent, stem="port") -> List[str]:
+    """`while (isPortConnected("port%d"))` -- enclosingComponent.cc:129-137."""
+    have = {p for p, _, _ in c.links}
+    out, i = [], 0
+    while f"{stem}{i}" in have:
+        out.append(f"{stem}{i}")
+        i += 1
+    return out
+
+
+# ---- coreTestElement.message_mesh.enclosing_component (testElements/message_mesh/enclosingComponent.cc:29-69)
+def _wire_mesh(c: ConfigComponent, tl: TimeLord) -> Wired:
+    my_id = _find_int(c, "id", -1)
+    if my_id == -1:
+        raise ModelError("Must specify param 'id' in EnclosingComponent")
+    verbose = _find_int(c, "verbose", 1)
+    mod = _find_int(c, "mod", 1)
+    if mod < 1:
+        raise ModelError("Modulus must be at least 1")
+    nstats = _find_int(c, "stats", 0)
+    slots = c.sub_in_slot("ports")
+    if not slots:
+        raise ModelError("Must specify at least one PortInterface SubComponent for slot 'ports' in EnclosingComponent")
+    ports, counts = [], []
+    for s in slots:
+        mp = s
+        if s.type == "coreTestElement.message_mesh.port_slot":
+            inner = s.sub_in_slot("port")
+            if not inner:
+                raise ModelError(f"port_slot {s.full_name()} has no 'port' subcomponent")
+            mp = inner[0]
+        if mp.type != "coreTestElement.message_mesh.message_port":
+            raise ModelError(f"unsupported PortInterface type {mp.type}")
+        names = _connected_numbered_ports(mp)
+        counts.append(len(names))
+        ports += [(mp, n) for n in names]
+    route = c.sub_in_slot("route")
+    if not route or route[0].type != "coreTestElement.message_mesh.route_message":
+        raise ModelError("Must specify The RouteInterface SubComponent to use for slot 'route' in EnclosingComponent")
+    if len(counts) > 8 or any(k > 255 or k < 1 for k in counts):
+        raise ModelError("message_mesh on device supports up to 8 port groups of 1..255 links")
+    packed = 0
+    for g, k in enumerate(counts):
+        packed |= k << (8 * g)
+    stats = [StatDesc(route[0].full_name(), "msg_count", "", "u64", 1)]
+    stats += [StatDesc(c.full_name(), "stat", str(i), "u64", None) for i in range(nstats)]
+
+    def finish(r, _id=my_id, _v=verbose):
+        cnt = r[0] if r[0] < (1 << 31) else r[0] - (1 << 32)
+        return f"{_id} received {cnt} messages" if _v else None
+
+    return Wired(TYPE_MESH, [my_id, mod, verbose, nstats, len(counts), packed, 0, 0], ports, 0, stats, finish)
+
+
+# ---- pdes.phold (oracle/probe/pdes_elements.cc PholdNode)
+def _wire_phold(c: ConfigComponent, tl: TimeLord) -> Wired:
+    my_id = _find_int(c, "id", -1)
+    init = _find_int(c, "init_events", 16)
+    dmod = _find_int(c, "delay_mod", 8000)
+    verbose = _find_int(c, "verbose", 1)
+    if dmod < 1:
+        raise ModelError("delay_mod must be at least 1")
+    names = _connected_numbered_ports(c)
+    if not names:
+        raise ModelError(f"pdes.phold {c.name} has no connected port0")
+
+    def finish(r, _id=my_id, _v=verbose):
+        return f"phold {_id} recv {r[0]} hash {r[1]:016x}" if _v else None
+
+    return Wired(TYPE_PHOLD, [my_id, init, dmod, verbose, 0, 0, 0, 0], [(c, n) for n in names], 0,
+                 [StatDesc(c.full_name(), "delay", "", "u64", 2)], finish)
+
+
+# ---- pdes.clocknode (oracle/probe/pdes_elements.cc ClockNode; coreTest_Component.cc:25-173 style)
+def _wire_clocknode(c: ConfigComponent, tl: TimeLord) -> Wired:
+    my_id = _find_int(c, "id", -1)
+    comm = _find_int(c, "commFreq", 1000)
+    verbose = _find_int(c, "verbose", 1)
+    if comm == 0:
+        raise ModelError("commFreq must be non-zero")
+    period = tl.cycles(c.params.get("clock", "1GHz"))
+    have = {p for p, _, _ in c.links}
+    # the 4 ports are always "configured" in order; unconnected ones stay unwired (no tag is consumed for them)
+    ports = [(c, f"port{i}") if f"port{i}" in have else (c, None) for i in range(4)]
+    stats = [StatDesc(c.full_name(), n, "", "i32", 4 + 5 * i) for i, n in enumerate("NSEW")]
+
+    def finish(r, _id=my_id, _v=verbose):
+        return (f"clocknode {_id} ticks {r[0]} last_cycle {r[1]} recv {r[2]} hash {r[3]:016x}") if _v else None
+
+    return Wired(TYPE_CLOCKNODE, [my_id, comm, verbose, 0, 0, 0, 0, 0], ports, period, stats, finish)
+
+
+# ---- coreTestElement.coreTestRNGComponent (testElements/coreTest_RNGComponent.cc:26-74)
+def _wire_rngcomp(c: ConfigComponent, tl: TimeLord) -> Wired:
+    count = _find_int(c, "count", 1000)
+    verbose = _find_int(c, "verbose", 0)
+    kind_s = c.params.get("rng", "mersenne")
+    if kind_s == "mersenne":
+        kind, s1, s2 = 0, _find_int(c, "seed", 1447) & 0xFFFFFFFF, 0
+    elif kind_s == "marsaglia":
+        w = _find_int(c, "seed_w", 0) & 0xFFFFFFFF
+        z = _find_int(c, "seed_z", 0) & 0xFFFFFFFF
+        if w == 0 or z == 0:
+            raise ModelError("marsaglia generator without seeds is time-seeded in the reference; not reproducible")
+        kind, s1, s2 = 1, z, w
+    elif kind_s == "xorshift":
+        kind, s1, s2 = 2, _find_int(c, "seed", 57) & 0xFFFFFFFF, 0
+        if s1 == 0:
+            raise ModelError("XORShiftRNG seed must be non-zero (xorshift.cc:44-50 asserts)")
+    else:
+        kind, s1, s2 = 0, 1447, 0
+    return Wired(TYPE_RNGCOMP, [kind, s1, s2, count, verbose, 0, 0, 0], [], tl.cycles("1GHz"), [], None)
+
+
+ELEMENTS: Dict[str, Callable[[ConfigComponent, TimeLord], Wired]] = {
+    "coreTestElement.message_mesh.enclosing_component": _wire_mesh,
+    "pdes.phold": _wire_phold,
+    "pdes.clocknode": _wire_clocknode,
+    "coreTestElement.coreTestRNGComponent": _wire_rngcomp,
+}
+
+TYPE_NAMES = {
+    TYPE_MESH: "coreTestElement.message_mesh.enclosing_component",
+    TYPE_PHOLD: "pdes.phold",
+    TYPE_CLOCKNODE: "pdes.clocknode",
+    TYPE_RNGCOMP: "coreTestElement.coreTestRNGComponent",
+}

@@ -1,0 +1,137 @@
+"""ConfigGraph -> WiredModel: the flat arrays the engine's C-ABI consumes.
+
+Follows the reference's wire-up (``Simulation::prepareLinks`` simulation.cc:668-820, ``performWireUp`` :824-859,
+``BaseComponent::configureLink_impl`` baseComponent.cc:541-642): components are constructed in id order, every
+``configureLink`` call claims the next delivery-order tag, each link end sends with its OWN latency
+(``lp.getLeft()->setLatency(clink->latency_[0])``), and the lookahead is the minimum link latency
+(``ConfigGraph::getMinimumPartitionLatency`` configGraph.cc:711-730).
+
+WiredModel layout (all numpy, C-contiguous; this is what include/sstb200.h ``sstb200_engine_create`` takes):
+    comp_type   u32 [ncomp]        native type code
+    comp_param  i64 [ncomp, 8]     type-specific construction params
+    port_off    u32 [ncomp+1]      CSR over directed ports, ports in configureLink order
+    peer_port   u32 [nport]        directed port that receives what this port sends (0xFFFFFFFF = unconnected)
+    latency     u64 [nport]        cycles added when sending FROM this port
+    clock_period u64 [ncomp]       0 = no clock
+    rank        u32 [ncomp]        partition (GPU) owning the component; components are renumbered so that each
+                                   rank owns one contiguous id range (orig_id maps back)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from .config import ConfigGraph, ModelError
+from .elements import ELEMENTS, NPARAM, StatDesc
+from .timelord import TimeLord
+
+NO_PEER = np.uint32(0xFFFFFFFF)
+
+
+@dataclass
+class WiredModel:
+    comp_type: np.ndarray
+    comp_param: np.ndarray
+    port_off: np.ndarray
+    peer_port: np.ndarray
+    latency: np.ndarray
+    clock_period: np.ndarray
+    stop_at: int = 0
+    timebase: str = "1ps"
+    stats_enabled: bool = False
+    rank: Optional[np.ndarray] = None
+    n_ranks: int = 1
+    orig_id: Optional[np.ndarray] = None  # engine id -> id in the ConfigGraph
+    names: Optional[List[str]] = None
+    stats: Optional[List[List[StatDesc]]] = None
+    finish: Optional[list] = None
+    nocut_pairs: Optional[np.ndarray] = None  # [k,2] component pairs joined by no-cut links
+    stat_output: tuple = ("sst.statOutputConsole", {})
+
+    @property
+    def ncomp(self) -> int:
+        return int(self.comp_type.shape[0])
+
+    @property
+    def nport(self) -> int:
+        return int(self.port_off[-1])
+
+    def min_latency(self) -> int:
+        m = self.latency[self.peer_port != NO_PEER]
+        return int(m.min()) if m.size else 0
+
+    def validate(self):
+        assert self.comp_type.dtype == np.uint32 and self.comp_param.dtype == np.int64
+        assert self.comp_param.shape == (self.ncomp, NPARAM)
+        assert self.port_off.dtype == np.uint32 and self.port_off.shape == (self.ncomp + 1,)
+        assert self.peer_port.dtype == np.uint32 and self.latency.dtype == np.uint64
+        assert self.peer_port.shape == (self.nport,) and self.latency.shape == (self.nport,)
+        assert self.clock_period.dtype == np.uint64 and self.clock_period.shape == (self.ncomp,)
+        conn = self.peer_port != NO_PEER
+        if conn.any():
+            pp = self.peer_port[conn].astype(np.int64)
+            assert pp.max() < self.nport
+            # links are symmetric: my peer's peer is me
+            idx = np.nonzero(conn)[0]
+            assert np.array_equal(self.peer_port[pp].astype(np.int64), idx), "peer_port is not an involution"
+            if (self.latency[conn] == 0).any():
+                raise ModelError("zero-latency links are not allowed (link.cc / configGraph checks)")
+
+
+def wire(graph: ConfigGraph, stop_at_override: Optional[str] = None) -> WiredModel:
+    tl = TimeLord(graph.program_options.get("timebase", "1ps"))
+    wired = []
+    for c in graph.components:
+        fn = ELEMENTS.get(c.type)
+        if fn is None:
+            raise ModelError(
+                f"can't find requested component or subcomponent '{c.type}' among the GPU-eligible element types "
+                f"({', '.join(sorted(ELEMENTS))})")
+        wired.append(fn(c, tl))
+    ncomp = len(wired)
+    port_off = np.zeros(ncomp + 1, dtype=np.uint32)
+    for i, w in enumerate(wired):
+        port_off[i + 1] = port_off[i] + len(w.ports)
+    nport = int(port_off[-1])
+    peer_port = np.full(nport, NO_PEER, dtype=np.uint32)
+    latency = np.zeros(nport, dtype=np.uint64)
+    # (owner ConfigComponent id(), port name) -> directed port id
+    where = {}
+    for i, w in enumerate(wired):
+        for k, (owner, pname) in enumerate(w.ports):
+            if pname is not None:
+                where[(id(owner), pname)] = int(port_off[i]) + k
+    used_ends = 0
+    for l in graph.links:
+        if len(l.ends) != 2:
+            continue
+        pids = []
+        for owner, pname, lat in l.ends:
+            pid = where.get((id(owner), pname))
+            if pid is None:
+                raise ModelError(f"port {pname} of {owner.full_name()} (link {l.name}) is connected in the model "
+                                 f"but is not a port the element configures")
+            pids.append(pid)
+        for k in (0, 1):
+            peer_port[pids[k]] = pids[1 - k]
+            latency[pids[k]] = tl.cycles(l.ends[k][2])
+            used_ends += 1
+    stop = stop_at_override if stop_at_override is not None else graph.program_options.get("stop-at")
+    stop_at = tl.cycles(stop) if stop not in (None, "", "0 ns") else 0
+    nocut = [(l.ends[0][0].top().id, l.ends[1][0].top().id) for l in graph.links if l.no_cut and len(l.ends) == 2]
+    m = WiredModel(
+        comp_type=np.array([w.type_code for w in wired], dtype=np.uint32),
+        comp_param=np.array([w.params for w in wired], dtype=np.int64).reshape(ncomp, NPARAM),
+        port_off=port_off, peer_port=peer_port, latency=latency,
+        clock_period=np.array([w.clock_period for w in wired], dtype=np.uint64),
+        stop_at=stop_at, timebase=tl.timebase_string,
+        stats_enabled=graph.enable_all_stats is not None or any(c.stats_enabled for c in graph.components),
+        names=[c.name for c in graph.components],
+        stats=[w.stats for w in wired], finish=[w.finish for w in wired],
+        nocut_pairs=np.array(nocut, dtype=np.uint32).reshape(-1, 2),
+        stat_output=graph.stat_output,
+    )
+    m.validate()
+    return m

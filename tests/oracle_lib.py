@@ -1,0 +1,123 @@
+"""ctypes wrapper around oracle/liboracle.so (the CPU golden model) and runners for oracle/_ref (the reference
+binary built from /root/reference).  TEST INFRASTRUCTURE: imported only from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / reference arm."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+ORACLE_SO = ROOT / "oracle" / "liboracle.so"
+REF = ROOT / "oracle" / "_ref"
+SSTSIM = REF / "libexec" / "sstsim.x"
+REF_LIBDIR = REF / "lib" / "sst-elements-library"
+NRESULT = 32
+
+
+def build_oracle(force=False):
+    src = ROOT / "oracle" / "pdes_oracle.cc"
+    if force or not ORACLE_SO.exists() or ORACLE_SO.stat().st_mtime < src.stat().st_mtime:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(ORACLE_SO), str(src)])
+    return ORACLE_SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build_oracle()
+        L = C.CDLL(str(ORACLE_SO))
+        L.oracle_create.restype = C.c_void_p
+        L.oracle_create.argtypes = [C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint64, C.c_int, C.c_int]
+        L.oracle_destroy.argtypes = [C.c_void_p]
+        L.oracle_run.argtypes = [C.c_void_p]
+        L.oracle_results.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_counters.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_trace.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        L.oracle_rng_u32_stream.restype = C.c_uint64
+        L.oracle_rng_u32_stream.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.oracle_rng_ticks.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.oracle_distribution.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
+                                          C.c_uint64, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OracleRun:
+    def __init__(self, results, events, ticks, end_time, trace=None):
+        self.results, self.events, self.ticks, self.end_time, self.trace = results, events, ticks, end_time, trace
+
+
+def run_model(m, trace=False) -> OracleRun:
+    """Serial golden-model run of a WiredModel."""
+    L = lib()
+    arrs = [np.ascontiguousarray(a) for a in
+            (m.comp_type, m.comp_param, m.port_off, m.peer_port, m.latency, m.clock_period)]
+    h = L.oracle_create(m.ncomp, *[_p(a) for a in arrs], int(m.stop_at), int(bool(m.stats_enabled)), int(trace))
+    if not h:
+        raise RuntimeError("oracle_create failed (unknown component type)")
+    try:
+        L.oracle_run(h)
+        res = np.zeros((m.ncomp, NRESULT), dtype=np.uint64)
+        L.oracle_results(h, _p(res))
+        cnt = np.zeros(4, dtype=np.uint64)
+        L.oracle_counters(h, _p(cnt))
+        tr = None
+        if trace:
+            n = int(cnt[3])
+            tr = dict(time=np.zeros(n, np.uint64), comp=np.zeros(n, np.uint32), port=np.zeros(n, np.uint32),
+                      payload=np.zeros(n, np.uint64))
+            L.oracle_trace(h, _p(tr["time"]), _p(tr["comp"]), _p(tr["port"]), _p(tr["payload"]))
+        return OracleRun(res, int(cnt[0]), int(cnt[1]), int(cnt[2]), tr)
+    finally:
+        L.oracle_destroy(h)
+
+
+def rng_u32_stream(kind, s1, s2, n, skip=0, want=True):
+    out = np.zeros(n, dtype=np.uint32) if want else None
+    cs = lib().oracle_rng_u32_stream(kind, s1, s2, skip, n, _p(out) if want else None)
+    return out, cs
+
+
+def rng_ticks(kind, s1, s2, first, n):
+    out = np.zeros((n, 5), dtype=np.uint64)
+    lib().oracle_rng_ticks(kind, s1, s2, first, n, _p(out))
+    return out
+
+
+def distribution(dist, params, rng_kind, s1, s2, n):
+    p = np.asarray(params, dtype=np.float64)
+    out = np.zeros(n, dtype=np.float64)
+    lib().oracle_distribution(dist, _p(p), len(p), rng_kind, s1, s2, n, _p(out))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ reference binary
+def have_ref() -> bool:
+    return SSTSIM.exists() and (REF_LIBDIR / "libcoreTestElement.so").exists()
+
+
+def run_ref(script, model_options="", extra=(), cwd=None, threads=1, timeout=3600) -> str:
+    """Run the hand-built reference `sstsim.x` on a model script; returns stdout."""
+    cmd = [str(SSTSIM), "--lib-path", str(REF_LIBDIR)]
+    if threads > 1:
+        cmd += ["-n", str(threads)]
+    if model_options:
+        cmd += ["--model-options", model_options]
+    cmd += list(extra) + [str(script)]
+    env = dict(os.environ)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=cwd, env=env,
+                       timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError(f"reference run failed ({r.returncode}): {' '.join(cmd)}\n{r.stdout[-2000:]}")
+    return r.stdout
