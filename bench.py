@@ -1,0 +1,358 @@
+#!/usr/bin/env python3
+"""bench.py -- committed events/sec of the event-delivery hot path (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W              our engine, 1 GPU
+    torchrun ... bench.py --gpus N --steps K --warmup W        our engine, N GPUs (strong scaling of one mesh)
+    python bench.py --impl reference ...                       the reference's own CPU implementation of the path
+
+Workload (config.workload): MessageMesh (reference tests/test_MessageMesh.py semantics) scaled to X x Y components,
+default 4096 x 4096 = 16.7 M components, 67.1 M events per lookahead window -- the configuration BASELINE.json's
+metric is quoted on; it fits one B200 (42 GB of MT19937 state + 4.3 GB of event calendar).  A "step" is one lookahead
+window (1 ns of simulated time): every component receives its due events, draws its two MT19937 numbers per event
+and forwards each event over the CSR link table.
+
+  value    events delivered in the K timed windows / device time (CUDA events on the engine's stream, max over ranks);
+           the model lives in HBM when the timed region starts; inputs (67 M events, 42 GB RNG state) exceed L2 by far
+  e2e      the same metric through the public API from HOST arrays: engine create (H2D of the wired model), setup(),
+           W+K windows, results back to host (D2H) -- all inside the timed wall-clock region
+  roofline the dispatch kernel: algorithmic bytes/event (96 B mesh) x events per launch / its
+           mean launch duration (CUDA events around each dispatch launch), against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference binary (oracle/_ref/libexec/sstsim.x, unmodified sst-core) on the box's host cores on a
+           bounded sample of the same model; falls back to the oracle port (1 core) when the build is absent
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+ALGO_BYTES = {"mesh": 96, "phold": 192}  # SURVEY.md section 8(d) algorithmic bytes per committed event
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mesh", choices=["mesh", "phold"])
+    ap.add_argument("--x", type=int, default=0)
+    ap.add_argument("--y", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-size", type=int, default=256, help="reference sample: S x S mesh")
+    ap.add_argument("--cpu-ns", type=int, default=100, help="reference sample: simulated ns")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.stop_flag, self.index = [], threading.Event(), index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def start(self):
+        self.t.start()
+
+    def stop(self):
+        self.stop_flag.set()
+        self.t.join(timeout=6)
+        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU / reference arm
+def ref_paths():
+    ref = ROOT / "oracle" / "_ref"
+    return ref / "libexec" / "sstsim.x", ref / "lib" / "sst-elements-library"
+
+
+def run_reference_sample(size, ns, threads):
+    """One run of the UNMODIFIED reference core on an S x S MessageMesh for `ns` simulated ns.
+    Returns (events, execute-region seconds)."""
+    exe, libdir = ref_paths()
+    script = ROOT / "tests" / "models" / "mesh.py"
+    cmd = [str(exe), "--lib-path", str(libdir), "--timing-info=2", "--stop-at", f"{ns}ns",
+           "--model-options", f"{size} {size} 1 0", str(script)]
+    if threads > 1:
+        cmd[1:1] = ["-n", str(threads)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=3000, cwd="/tmp").stdout
+    m = re.search(r"execute\s*\n.*?Duration:\s*([0-9.eE+-]+)\s*(s|ms|us)", out, re.S)
+    if not m:
+        raise RuntimeError("could not parse the reference's --timing-info output:\n" + out[-1500:])
+    secs = float(m.group(1)) * {"s": 1.0, "ms": 1e-3, "us": 1e-6}[m.group(2)]
+    return size * size * 4 * (ns - 1), secs
+
+
+def cpu_baseline(size, ns):
+    exe, _ = ref_paths()
+    cores = os.cpu_count() or 1
+    if exe.exists():
+        ev, secs = run_reference_sample(size, ns, cores)
+        return {"value": ev / secs, "unit": "events/s", "cores": cores, "kind": "reference",
+                "sample": f"sstsim.x -n {cores} MessageMesh {size}x{size}, {ns} ns ({ev} events, execute region "
+                          f"{secs:.2f} s of --timing-info=2)"}
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_lib as O
+    from sst_core_b200 import models
+    m = models.mesh_model(size, size, stop_at=f"{ns}ns")
+    t0 = time.perf_counter()
+    r = O.run_model(m)
+    secs = time.perf_counter() - t0
+    return {"value": r.events / secs, "unit": "events/s", "cores": 1, "kind": "port",
+            "sample": f"oracle/pdes_oracle.cc serial MessageMesh {size}x{size}, {ns} ns ({r.events} events)"}
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    exe, _ = ref_paths()
+    vals = []
+    steps, warm = max(1, min(a.steps, 3)), min(a.warmup, 1)
+    t_all = time.perf_counter()
+    for i in range(warm + steps):
+        if exe.exists():
+            ev, secs = run_reference_sample(a.cpu_size, a.cpu_ns, cores)
+            kind = "reference"
+        else:
+            b = cpu_baseline(a.cpu_size, a.cpu_ns)
+            ev, secs, kind, cores = 1.0, 1.0 / b["value"], "port", 1
+        if i >= warm:
+            vals.append((ev, secs))
+    ev = sum(v[0] for v in vals)
+    secs = sum(v[1] for v in vals)
+    value = ev / secs
+    sample = (f"{'sstsim.x -n %d' % cores if kind == 'reference' else 'oracle port'} MessageMesh "
+              f"{a.cpu_size}x{a.cpu_size}, {a.cpu_ns} ns per step")
+    line = {
+        "impl": "reference", "metric": "committed events/sec", "value": value, "unit": "events/s",
+        "n_gpus": a.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * secs / steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"MessageMesh {a.cpu_size}x{a.cpu_size} torus (bounded sample of the 4096x4096 "
+                               f"config: the reference needs ~20 KB/component)", "stop_at_ns": a.cpu_ns},
+        "cpu_baseline": {"value": value, "unit": "events/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def build_model(a, windows):
+    from sst_core_b200 import models
+    x = a.x or 4096
+    y = a.y or 4096
+    stop_ns = windows + 2
+    if a.workload == "mesh":
+        m = models.mesh_model(x, y, stop_at=f"{stop_ns}ns", verbose=0, stats_enabled=True)
+        opts = dict(calendar_slots=2, bin_capacity=2048, smem_events=2048)
+        name = f"MessageMesh {x}x{y} torus, 1 ns links, MersenneRNG(id+100) per component, msg_count statistic on"
+    else:
+        m = models.phold_model(x, y, stop_at=f"{stop_ns}ns", verbose=0, stats_enabled=True)
+        opts = dict(calendar_slots=16, bin_capacity=2560, smem_events=2560)
+        name = f"PHOLD {x}x{y} torus, 16 events/component, delay u32%8000 ps, XORShiftRNG(id+1)"
+    return m, opts, name
+
+
+def ours(a):
+    import numpy as np
+    import torch
+
+    from sst_core_b200.engine import DistributedRunner, Engine, partition_model
+
+    n = a.gpus
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    W, K = max(a.warmup, 3), a.steps
+    m, opts, name = build_model(a, W + K + 1)
+    model_bytes = sum(arr.nbytes for arr in (m.comp_type, m.comp_param, m.port_off, m.peer_port, m.latency,
+                                             m.clock_period))
+    stream = torch.cuda.Stream(dev)
+    result = {}
+
+    def make_engine():
+        if world > 1:
+            pm = partition_model(m, world)
+            return Engine(pm, device=local_rank, rank=rank, n_ranks=world, stream=stream.cuda_stream, **opts)
+        return Engine(m, device=local_rank, stream=stream.cuda_stream, **opts)
+
+    # ---- e2e: host arrays -> engine -> W+K windows -> results on host, wall clock, everything inside
+    e2e = None
+    if not a.no_e2e:
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            e = make_engine()
+            e.setup()
+            if world > 1:
+                DistributedRunner(e).run(max_windows=W + K, check_every=W + K)
+            else:
+                e.run(max_windows=W + K, check_every=W + K)
+            res = e.results()
+            st = e.status()
+        torch.cuda.synchronize(dev)
+        secs = time.perf_counter() - t0
+        e.raise_on_error(st)
+        ev = torch.tensor([st.events_delivered, 0], dtype=torch.float64, device=dev)
+        tt = torch.tensor([secs], dtype=torch.float64, device=dev)
+        if dist:
+            dist.all_reduce(ev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": float(ev[0].item()) / float(tt[0].item()), "unit": "events/s",
+               "h2d_bytes_per_step": model_bytes // (W + K), "d2h_bytes_per_step": res.nbytes // (W + K),
+               "seconds": float(tt[0].item()), "windows": W + K,
+               "note": "engine create from host arrays + setup + windows + results to host, per rank slice"}
+        e.close()
+        del res
+
+    # ---- kernel-timed region: model resident in HBM, K windows
+    with torch.cuda.stream(stream):
+        e = make_engine()
+        e.setup()
+        runner = DistributedRunner(e) if world > 1 else None
+
+        def step(ev_pair=None):
+            if ev_pair:
+                ev_pair[0].record(stream)
+            if runner:
+                e.dispatch()
+                if ev_pair:
+                    ev_pair[1].record(stream)
+                dist.all_to_all_single(runner.inbox, runner.outbox)
+                e.ingest()
+                dist.all_gather_into_tensor(runner.gathered, runner.local)
+                e.advance()
+            else:
+                e.dispatch()
+                if ev_pair:
+                    ev_pair[1].record(stream)
+                e.advance()
+
+        for _ in range(W):
+            step()
+        torch.cuda.synchronize(dev)
+        st0 = e.status()
+        e.raise_on_error(st0)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_beg.record(stream)
+        for i in range(K):
+            step(pairs[i])
+        t_end.record(stream)
+        torch.cuda.synchronize(dev)
+        if dist:
+            dist.barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        st1 = e.status()
+        e.raise_on_error(st1)
+    ms_total = t_beg.elapsed_time(t_end)
+    ms_dispatch = sum(p[0].elapsed_time(p[1]) for p in pairs) / K
+    events = st1.events_delivered - st0.events_delivered
+    launches = st1.launches - st0.launches
+    tt = torch.tensor([ms_total, ms_dispatch], dtype=torch.float64, device=dev)
+    ee = torch.tensor([events, launches], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ee)
+    ms_total, ms_dispatch = float(tt[0].item()), float(tt[1].item())
+    events_all, launches_all = float(ee[0].item()), int(ee[1].item())
+    e.close()
+
+    if rank == 0:
+        peaks_path = ROOT / "MEASURED_PEAKS.json"
+        if peaks_path.exists():
+            peak, peak_src = json.loads(peaks_path.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured)"
+        else:
+            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        per_gpu_events_per_launch = events_all / K / world
+        achieved = ALGO_BYTES[a.workload] * per_gpu_events_per_launch / (ms_dispatch * 1e-3) / 1e9
+        traffic = None
+        tp = ROOT / "profiles" / "ncu_traffic.json"
+        if tp.exists():
+            traffic = json.loads(tp.read_text()).get(f"{a.workload}_dispatch_bytes_per_launch")
+        line = {
+            "metric": "committed events/sec", "value": events_all / (ms_total * 1e-3), "unit": "events/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": name, "components": int(m.ncomp), "events_per_step": events_all / K,
+                       "partition": f"sst.linear over {world} GPU(s)", "lookahead_window_ps": 1000,
+                       "l2": "inputs (event calendar + RNG state) far exceed the 126 MB L2; no flush needed",
+                       **{k: v for k, v in opts.items()}},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "dispatch_kernel", "ms_per_launch": ms_dispatch,
+                         "algorithmic_bytes_per_event": ALGO_BYTES[a.workload], "peak_source": peak_src},
+            "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks,
+        }
+        if not a.no_cpu_baseline and world == 1:
+            try:
+                line["cpu_baseline"] = cpu_baseline(a.cpu_size, a.cpu_ns)
+            except Exception as ex:  # the baseline must not take the bench line down
+                line["cpu_baseline"] = {"value": None, "unit": "events/s", "cores": 0, "kind": "unavailable",
+                                        "sample": repr(ex)[:200]}
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        return reference_arm(a)
+    return ours(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,151 @@
+/* sstb200.h -- C ABI of libsstb200.so, the B200-native event-delivery engine behind SST-core's plugin surface.
+ *
+ * The reference (sstsimulator/sst-core) has no C boundary for this path: the run loop, the TimeVortex, Link::send and
+ * the rank/thread sync are C++ objects inside one binary.  Each entry point below names the reference interface it
+ * replaces (paths relative to src/sst/core/).  A host driver -- sst_core_b200/engine.py here, or a C++ shim inside
+ * stock SST -- builds the wired-model arrays from its ConfigGraph and calls these.
+ * Plain pointers and sizes only; all arrays are caller-owned host memory unless a parameter is documented as a
+ * device pointer.  Every function returns 0 on success or a negative error code; sstb200_last_error() gives the text
+ * (the reference reports such errors through Output::fatal, output.cc:156-215).
+ * There is no CPU fallback: creating an engine without a CUDA device fails.
+ */
+#ifndef SSTB200_H
+#define SSTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSTB200_ABI_VERSION 1
+#define SSTB200_NPARAM 8    /* int64 construction params per component                        */
+#define SSTB200_NRESULT 32  /* u64 words in a component's result record                       */
+#define SSTB200_NO_PEER 0xFFFFFFFFu
+
+/* Result record (u64[32]) per component type, what finish() / the statistics engine would report
+ * (Accumulator words are Sum, SumSQ, Count, Min, Max -- statapi/stataccumulator.h:171-194):
+ *   1 coreTestElement.message_mesh.enclosing_component: [0] message_count (i32), [1..5] route "msg_count"
+ *   2 pdes.phold:      [0] recv, [1] delivery hash, [2..6] "delay"
+ *   3 pdes.clocknode:  [0] ticks, [1] last cycle, [2] recv, [3] delivery hash, [4+5i..] "N","S","E","W" (i32)
+ *   4 coreTestElement.coreTestRNGComponent: [0] rng_count, [1..5] last tick (double bits,u32,u64,i32,i64), [6] hash
+ */
+
+typedef struct sstb200_engine sstb200_engine;
+
+/* ---- library / ELI registry (eli/elibase.h:124-147 LoadedLibraries, factory.h:168-260; what sst-info prints) ---- */
+int         sstb200_abi_version(void);
+const char* sstb200_last_error(void);
+int         sstb200_num_component_types(void);
+/* idx in [0, num): ELI "lib.name", type code, POD state bytes, aux bytes per component, payload flag */
+int         sstb200_component_type_info(int idx, const char** eli_name, uint32_t* type_code, uint32_t* state_bytes,
+                                        uint32_t* aux_bytes, int* has_payload);
+int         sstb200_component_type_lookup(const char* eli_name); /* type code or -1 */
+
+/* ---- partitioning (impl/partitioners/linpart.cc:30-82 after ConfigGraph no-cut collapse, configGraph.cc:764-850)
+ * nocut_pairs: n_pairs x 2 component ids joined by no-cut links.  rank_out[ncomp] receives the owning partition. */
+int sstb200_partition_linear(uint32_t ncomp, const uint32_t* nocut_pairs, uint32_t n_pairs, uint32_t n_parts,
+                             uint32_t* rank_out);
+
+/* ---- engine (replaces Simulation::run simulation.cc:1072-1193, TimeVortexPQ impl/timevortex/timeVortexPQ.cc:62-95,
+ *      Link::send_impl link.cc:623-658, Clock::execute clock.cc:314-397, SyncManager::execute
+ *      sync/syncManager.cc:547-732 and RankSyncSerialSkip::exchange sync/rankSyncSerialSkip.cc:209-343) ---- */
+typedef struct sstb200_model {
+    uint32_t        ncomp;        /* GLOBAL number of components                                              */
+    const uint32_t* comp_type;    /* [ncomp]   type codes                                                     */
+    const int64_t*  comp_param;   /* [ncomp*8] construction params (host half of the element parses Params)   */
+    const uint32_t* port_off;     /* [ncomp+1] CSR over directed ports, in configureLink order                */
+    const uint32_t* peer_port;    /* [nport]   receiving directed port, SSTB200_NO_PEER if unconnected        */
+    const uint64_t* latency;      /* [nport]   cycles added when sending FROM this port (own-end latency,
+                                               simulation.cc:721-722)                                         */
+    const uint64_t* clock_period; /* [ncomp]   cycles, 0 = no clock (registerClock, clock.cc:400-420)         */
+    uint64_t        stop_at;      /* --stop-at in cycles, 0 = none (StopAction priority 30)                   */
+    int             stats_enabled;
+} sstb200_model;
+
+typedef struct sstb200_options {
+    int      device;          /* CUDA device ordinal                                                         */
+    uint32_t rank, n_ranks;   /* this engine's partition and the number of partitions (GPUs)                  */
+    uint32_t comp_begin, comp_end; /* components [begin,end) are owned by this rank (contiguous after wire-up)  */
+    const uint32_t* rank_comp_begin; /* [n_ranks+1] first component of every rank (NULL when n_ranks == 1)       */
+    uint32_t calendar_slots;  /* W: ring of lookahead windows events are binned into (>= 2)                   */
+    uint32_t bin_capacity;    /* events per (window slot, block of 256 components); 0 = default               */
+    uint32_t smem_events;     /* due events per block staged in shared memory; 0 = default                    */
+    uint32_t outbox_capacity; /* events per destination rank per window; 0 = default                          */
+    uint64_t window;          /* lookahead window in cycles; 0 = min link latency (configGraph.cc:711-730)    */
+    uint64_t trace_capacity;  /* delivery trace records to keep (0 = tracing off)                             */
+    void*    stream;          /* cudaStream_t to run on (NULL = engine-owned stream)                          */
+} sstb200_options;
+
+int  sstb200_engine_create(const sstb200_model* model, const sstb200_options* opt, sstb200_engine** out);
+void sstb200_engine_destroy(sstb200_engine* e);
+
+/* construct every component and run setup() (performWireUp simulation.cc:824-859, setup :969-987) */
+int sstb200_engine_setup(sstb200_engine* e);
+
+/* Run whole lookahead windows until the simulation ends or `max_windows` have been executed (0 = until the end).
+ * Single-rank only (an n_ranks > 1 engine is stepped with the three calls below).  Asynchronous on the engine's
+ * stream except for a completion check every `check_every` windows.  *finished is set to 1 when the simulation has
+ * ended (stop time reached, primary components done, or nothing left to run). */
+int sstb200_engine_run(sstb200_engine* e, uint64_t max_windows, uint32_t check_every, int* finished);
+
+/* Multi-rank stepping (one lookahead window = SyncManager::execute):
+ *   dispatch  : deliver this window's events and clock ticks; cross-rank sends land in per-destination outboxes
+ *   exchange buffers are DEVICE memory owned by the engine; the driver moves outbox -> peer inbox (NCCL all-to-all)
+ *   ingest    : bin received events into the local calendar
+ *   advance   : fold the (all-reduced) control words and move to the next window                            */
+int sstb200_engine_dispatch(sstb200_engine* e);
+int sstb200_engine_ingest(sstb200_engine* e);
+int sstb200_engine_advance(sstb200_engine* e);
+/* device pointers + geometry of the exchange buffers: words per rank slot = 1 + capacity*4 u64
+ * ([0] = count, then capacity x {time, dst_seq, payload, dst_comp}) */
+int sstb200_engine_exchange_buffers(sstb200_engine* e, void** outbox_dev, void** inbox_dev, uint64_t* words_per_rank);
+/* device pointer to the 8 x u64 control words that must be all-reduced (SUM) across ranks between ingest and advance:
+ * [0] pending events, [1] primary components still running, [2] active clocks, [3] error flag, [4] exit time (MAX is
+ * taken by the engine from [4..7] laid out as one-hot per rank is avoided: see DESIGN.md)                    */
+int sstb200_engine_control_words(sstb200_engine* e, void** local_dev, void** global_dev);
+
+/* ---- results (finish() simulation.cc:1286-1311, statistics dump statapi/statengine.cc:476-548) ---- */
+typedef struct sstb200_status {
+    uint64_t now;              /* start of the current window (cycles)                                        */
+    uint64_t end_time;         /* simulated end time once finished                                            */
+    uint64_t windows;          /* windows executed                                                            */
+    uint64_t events_delivered; /* committed events on this rank                                               */
+    uint64_t clock_ticks;      /* clock handler invocations on this rank                                      */
+    uint64_t events_sent;
+    uint64_t max_bin_fill;     /* high-water mark of any calendar bin (capacity tuning)                       */
+    uint64_t max_due;          /* high-water mark of due events in one block                                  */
+    uint32_t finished;
+    uint32_t error;            /* 0 ok; 1 calendar bin overflow; 2 shared-memory staging overflow; 3 time fault;
+                                  4 outbox overflow; 5 trace overflow                                         */
+    uint64_t error_info[4];
+    uint64_t launches;         /* kernels launched by the engine so far                                       */
+} sstb200_status;
+int sstb200_engine_status(sstb200_engine* e, sstb200_status* out);
+/* results[(comp_end-comp_begin) * 32] u64 for the components this rank owns */
+int sstb200_engine_results(sstb200_engine* e, uint64_t* results);
+/* delivery trace of this rank: per delivered event (time, component, port index within component, payload), in
+ * per-component delivery order; rows of one component are contiguous in `comp`-sorted order after this call.   */
+int sstb200_engine_trace(sstb200_engine* e, uint64_t* n_inout, uint64_t* time, uint32_t* comp, uint32_t* port,
+                         uint64_t* payload);
+
+/* ---- SST::RNG streams on the device (rng/mersenne.cc, marsaglia.cc, xorshift.cc; BASELINE config 2) ----
+ * kind: 0 mersenne(seed=s1), 1 marsaglia(z=s1,w=s2), 2 xorshift(seed=s1).
+ * n_streams independent generators, stream j seeded with (s1 + j*stride1, s2 + j*stride2), each producing
+ * draws_per_stream u32 draws.  out_dev (DEVICE pointer, may be NULL) receives them stream-major
+ * [n_streams][draws_per_stream]; checksum_dev (DEVICE, u64[n_streams]) receives sum_i (i+1)*draw_i per stream.   */
+int sstb200_rng_streams(int device, void* stream, int kind, uint64_t s1, uint64_t s2, uint64_t stride1,
+                        uint64_t stride2, uint64_t n_streams, uint64_t draws_per_stream, void* out_dev,
+                        void* checksum_dev);
+/* coreTestRNGComponent tick tuples: ticks [first, first+n) of one generator -> out_host[n*5] u64 */
+int sstb200_rng_ticks(int device, int kind, uint64_t s1, uint64_t s2, uint64_t first, uint64_t n, uint64_t* out_host);
+/* distributions (rng/discrete.h, expon.h, gaussian.h, poisson.h, uniform.h, constant.h): dist 0..5 as in
+ * oracle_distribution; n values of one generator -> out_host[n] doubles */
+int sstb200_rng_distribution(int device, int dist, const double* params, int n_params, int rng_kind, uint64_t s1,
+                             uint64_t s2, uint64_t n, double* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSTB200_H */

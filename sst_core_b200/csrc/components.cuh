@@ -1,0 +1,377 @@
+// GPU-eligible element types: POD state + device handler functors, registered in a compile-time table.
+//
+// This is the device half of the reference's component plugin API:
+//   SST_ELI_REGISTER_COMPONENT(cls, "lib", "name", ...)   component.h:93-95  ->  SSTB200_ELI_DEVICE_COMPONENT below:
+//                                                         the type appears in DeviceElements with its ELI name
+//   Component(ComponentId_t, Params&)                     ->  static construct(Ctx&, State&, const int64_t params[8])
+//                                                         (the host half, sst_core_b200/elements.py, has already
+//                                                         parsed Params and fixed the configureLink order)
+//   setup()                                               ->  static setup(Ctx&, State&)
+//   Event::Handler<cls,&cls::fn,int>(this, port)          ->  static handleEvent(Ctx&, State&, int port, uint64_t& payload)
+//   Clock::Handler<cls,&cls::fn>  (bool = unregister)     ->  static clockTick(Ctx&, State&, uint64_t cycle)
+//   Link::send(delay, ev) / send(ev)   link.h:202-220     ->  ctx.send(port, delay, payload)
+//   Statistic<T>::addData              statbase.h:393-401 ->  Accumulator<T>::add   (stataccumulator.h:89-95)
+//   primaryComponentOKToEndSim         baseComponent.cc:869-920 -> ctx.primaryComponentOKToEndSim()
+//   getCurrentSimCycle                                    ->  ctx.now
+//   finish()                                              ->  static results(const State&, uint64_t r[32]); the host
+//                                                         half formats the console line / statistic rows from r.
+//
+// A handler runs on exactly one thread and is never concurrent with another handler of the same component -- the
+// reference's threading contract.  Components touch no memory but their own State, their aux
+// block and what ctx hands them.
+#pragma once
+#include "rng.cuh"
+
+#include <cstdint>
+#include <limits>
+
+namespace sstb200 {
+
+enum : uint32_t { TYPE_MESH = 1, TYPE_PHOLD = 2, TYPE_CLOCKNODE = 3, TYPE_RNGCOMP = 4, TYPE_MAX = 5 };
+constexpr int NPARAM  = 8;
+constexpr int NRESULT = 32;
+
+// statapi/stataccumulator.h:44-209 -- fields Sum, SumSQ, Count, Min, Max
+template <typename T>
+struct Accumulator
+{
+    T        sum, sumsq, mn, mx;
+    uint64_t count;
+    SSTB_HD void init()
+    {
+        sum   = 0;
+        sumsq = 0;
+        mn    = std::numeric_limits<T>::max();
+        mx    = std::numeric_limits<T>::min();
+        count = 0;
+    }
+    SSTB_HD void add(T v)
+    {
+        sum += v;
+        sumsq += v * v;
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+        count++;
+    }
+    SSTB_HD void out(uint64_t* r) const
+    {
+        r[0] = (uint64_t)(int64_t)sum;
+        r[1] = (uint64_t)(int64_t)sumsq;
+        r[2] = count;
+        r[3] = count ? (uint64_t)(int64_t)mn : 0;
+        r[4] = count ? (uint64_t)(int64_t)mx : 0;
+    }
+};
+
+// oracle/probe/pdes_elements.cc mixDelivery (order-sensitive per-component delivery hash)
+SSTB_HD uint64_t
+mixDelivery(uint64_t h, uint64_t time, uint64_t port, uint64_t payload)
+{
+    uint64_t v = time * 0x9E3779B97F4A7C15ull + (port + 1) * 0xC2B2AE3D27D4EB4Full + payload;
+    h ^= v;
+    h *= 0x100000001B3ull;
+    h ^= h >> 29;
+    return h;
+}
+
+#if defined(__CUDACC__)
+
+// ------------------------------------------------------------------------------------------------------------------
+// coreTestElement.message_mesh.enclosing_component (+ message_port / port_slot / route_message subcomponents,
+// flattened).  Reference: testElements/message_mesh/enclosingComponent.cc:29-69 (ctor), :72-81 (setup), :92-99
+// (handleEvent), :164-199 (RouteMessage).
+struct MeshElement
+{
+    static constexpr uint32_t    TYPE         = TYPE_MESH;
+    static constexpr const char* ELI_NAME     = "coreTestElement.message_mesh.enclosing_component";
+    static constexpr uint32_t    AUX_BYTES    = MT_N * 4;
+    static constexpr bool        HAS_PAYLOAD  = false;
+    struct State
+    {
+        int32_t               message_count;
+        uint32_t              mt_idx;
+        uint32_t              ngroups;
+        uint32_t              mod;
+        uint64_t              counts; // links per port group, 8 bits each
+        Accumulator<uint64_t> mcnt;   // RouteMessage "msg_count"
+    };
+    template <class Ctx>
+    __device__ static void construct(Ctx& ctx, State& s, const int64_t* p)
+    {
+        s.message_count = 0;
+        s.mt_idx        = 0;
+        s.mod           = (uint32_t)p[1];
+        s.ngroups       = (uint32_t)p[4];
+        s.counts        = (uint64_t)p[5];
+        s.mcnt.init();
+        mt_seed((uint32_t*)ctx.aux, (uint32_t)(p[0] + 100)); // RouteMessage ctor: MersenneRNG(my_id + 100)
+    }
+    template <class Ctx>
+    __device__ static void setup(Ctx& ctx, State& s)
+    {
+        // RouteMessage::sendInitialEvents :188-199
+        MersenneDev rng { (uint32_t*)ctx.aux, s.mt_idx };
+        uint32_t    flat = 0;
+        for ( uint32_t i = 0; i < s.ngroups; i++ ) {
+            uint32_t cnt = (uint32_t)((s.counts >> (8 * i)) & 0xFF);
+            for ( uint32_t j = 0; j < cnt; j++, flat++ )
+                if ( (rng.u32() % s.mod) == 0 ) ctx.send((int)flat, 0, 0);
+        }
+        s.mt_idx = rng.idx;
+    }
+    template <class Ctx>
+    __device__ static void handleEvent(Ctx& ctx, State& s, int /*port*/, uint64_t& payload)
+    {
+        s.message_count++;
+        MersenneDev rng { (uint32_t*)ctx.aux, s.mt_idx };
+        uint32_t    nextport = rng.u32() % s.ngroups;
+        uint32_t    cnt      = (uint32_t)((s.counts >> (8 * nextport)) & 0xFF);
+        uint32_t    portnum  = rng.u32() % cnt;
+        s.mt_idx             = rng.idx;
+        uint32_t base        = 0;
+        for ( uint32_t g = 0; g < nextport; ++g )
+            base += (uint32_t)((s.counts >> (8 * g)) & 0xFF);
+        ctx.send((int)(base + portnum), 0, payload);
+        if ( ctx.stats_on ) s.mcnt.add(1);
+    }
+    template <class Ctx>
+    __device__ static bool clockTick(Ctx&, State&, uint64_t)
+    {
+        return true;
+    }
+    __device__ static void results(const State& s, uint64_t* r)
+    {
+        r[0] = (uint64_t)(int64_t)s.message_count;
+        s.mcnt.out(r + 1);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// pdes.phold (oracle/probe/pdes_elements.cc PholdNode)
+struct PholdElement
+{
+    static constexpr uint32_t    TYPE        = TYPE_PHOLD;
+    static constexpr const char* ELI_NAME    = "pdes.phold";
+    static constexpr uint32_t    AUX_BYTES   = 0;
+    static constexpr bool        HAS_PAYLOAD = true;
+    struct State
+    {
+        uint64_t              recv, hash;
+        XorShiftDev           rng;
+        uint32_t              dmod, init;
+        Accumulator<uint64_t> delay;
+    };
+    template <class Ctx>
+    __device__ static void construct(Ctx&, State& s, const int64_t* p)
+    {
+        s.recv = 0;
+        s.hash = 0;
+        s.rng.seed((uint32_t)(p[0] + 1));
+        s.init = (uint32_t)p[1];
+        s.dmod = (uint32_t)p[2];
+        s.delay.init();
+    }
+    template <class Ctx>
+    __device__ static void setup(Ctx& ctx, State& s)
+    {
+        for ( uint32_t i = 0; i < s.init; ++i ) {
+            uint32_t pp = s.rng.u32() % ctx.nports;
+            uint64_t d  = s.rng.u32() % s.dmod;
+            ctx.send((int)pp, d, d);
+        }
+    }
+    template <class Ctx>
+    __device__ static void handleEvent(Ctx& ctx, State& s, int port, uint64_t& payload)
+    {
+        s.recv++;
+        if ( ctx.stats_on ) s.delay.add(payload);
+        s.hash      = mixDelivery(s.hash, ctx.now, (uint64_t)port, payload);
+        uint32_t pp = s.rng.u32() % ctx.nports;
+        uint64_t d  = s.rng.u32() % s.dmod;
+        ctx.send((int)pp, d, d);
+    }
+    template <class Ctx>
+    __device__ static bool clockTick(Ctx&, State&, uint64_t)
+    {
+        return true;
+    }
+    __device__ static void results(const State& s, uint64_t* r)
+    {
+        r[0] = s.recv;
+        r[1] = s.hash;
+        s.delay.out(r + 2);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// pdes.clocknode (oracle/probe/pdes_elements.cc ClockNode; testElements/coreTest_Component.cc:25-173 style)
+struct ClockNodeElement
+{
+    static constexpr uint32_t    TYPE        = TYPE_CLOCKNODE;
+    static constexpr const char* ELI_NAME    = "pdes.clocknode";
+    static constexpr uint32_t    AUX_BYTES   = 0;
+    static constexpr bool        HAS_PAYLOAD = false;
+    struct State
+    {
+        uint64_t             ticks, last_cycle, recv, hash;
+        MarsagliaDev         rng;
+        uint32_t             neighbor;
+        int32_t              commFreq;
+        Accumulator<int32_t> count[4];
+    };
+    template <class Ctx>
+    __device__ static void construct(Ctx&, State& s, const int64_t* p)
+    {
+        s.ticks = s.last_cycle = s.recv = s.hash = 0;
+        s.rng.z    = (uint32_t)(11 + p[0]);
+        s.rng.w    = 272727u;
+        s.commFreq = (int32_t)p[1];
+        s.neighbor = s.rng.u32() % 4;
+        for ( int i = 0; i < 4; ++i )
+            s.count[i].init();
+    }
+    template <class Ctx>
+    __device__ static void setup(Ctx&, State&)
+    {}
+    template <class Ctx>
+    __device__ static void handleEvent(Ctx& ctx, State& s, int port, uint64_t&)
+    {
+        s.recv++;
+        s.hash = mixDelivery(s.hash, ctx.now, (uint64_t)port, s.ticks);
+    }
+    template <class Ctx>
+    __device__ static bool clockTick(Ctx& ctx, State& s, uint64_t cycle)
+    {
+        s.ticks++;
+        s.last_cycle = cycle;
+        if ( (rng_i32(s.rng) % s.commFreq) == 0 ) {
+            s.neighbor = (s.neighbor + 1) % 4;
+            if ( s.neighbor < ctx.nports && ctx.connected((int)s.neighbor) ) {
+                ctx.send((int)s.neighbor, 0, 0);
+                if ( ctx.stats_on ) s.count[s.neighbor].add(1);
+            }
+        }
+        return false;
+    }
+    __device__ static void results(const State& s, uint64_t* r)
+    {
+        r[0] = s.ticks;
+        r[1] = s.last_cycle;
+        r[2] = s.recv;
+        r[3] = s.hash;
+        for ( int i = 0; i < 4; ++i )
+            s.count[i].out(r + 4 + 5 * i);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// coreTestElement.coreTestRNGComponent (testElements/coreTest_RNGComponent.cc:26-74 ctor, :87-109 tick)
+struct RngElement
+{
+    static constexpr uint32_t    TYPE        = TYPE_RNGCOMP;
+    static constexpr const char* ELI_NAME    = "coreTestElement.coreTestRNGComponent";
+    static constexpr uint32_t    AUX_BYTES   = MT_N * 4;
+    static constexpr bool        HAS_PAYLOAD = false;
+    struct State
+    {
+        int64_t  rng_count, max_count;
+        uint64_t last[5];
+        uint64_t hash;
+        uint32_t kind, a, b, c, d; // generator state: mersenne idx in a; marsaglia z,w in a,b; xorshift x,y,z,w
+    };
+    template <class Ctx>
+    __device__ static void construct(Ctx& ctx, State& s, const int64_t* p)
+    {
+        s.rng_count = 0;
+        s.max_count = p[3];
+        s.hash      = 0;
+        for ( int i = 0; i < 5; ++i )
+            s.last[i] = 0;
+        s.kind = (uint32_t)p[0];
+        s.a = s.b = s.c = s.d = 0;
+        if ( s.kind == 0 ) {
+            mt_seed((uint32_t*)ctx.aux, (uint32_t)p[1]);
+        }
+        else if ( s.kind == 1 ) {
+            s.a = (uint32_t)p[1];
+            s.b = (uint32_t)p[2];
+        }
+        else {
+            s.a = (uint32_t)p[1];
+        }
+    }
+    template <class Ctx>
+    __device__ static void setup(Ctx&, State&)
+    {}
+    template <class Ctx>
+    __device__ static void handleEvent(Ctx&, State&, int, uint64_t&)
+    {}
+    template <class G>
+    __device__ static void draw(G& g, State& s)
+    {
+        double   nU  = g.uniform();
+        uint32_t U32 = g.u32();
+        uint64_t U64 = rng_u64(g);
+        int32_t  I32 = rng_i32(g);
+        int64_t  I64 = rng_i64(g);
+        s.last[0]    = (uint64_t)__double_as_longlong(nU);
+        s.last[1]    = U32;
+        s.last[2]    = U64;
+        s.last[3]    = (uint64_t)(int64_t)I32;
+        s.last[4]    = (uint64_t)I64;
+    }
+    template <class Ctx>
+    __device__ static bool clockTick(Ctx& ctx, State& s, uint64_t)
+    {
+        if ( s.kind == 0 ) {
+            MersenneDev g { (uint32_t*)ctx.aux, s.a };
+            draw(g, s);
+            s.a = g.idx;
+        }
+        else if ( s.kind == 1 ) {
+            MarsagliaDev g { s.a, s.b };
+            draw(g, s);
+            s.a = g.z;
+            s.b = g.w;
+        }
+        else {
+            XorShiftDev g { s.a, s.b, s.c, s.d };
+            draw(g, s);
+            s.a = g.x;
+            s.b = g.y;
+            s.c = g.z;
+            s.d = g.w;
+        }
+        s.rng_count++;
+        for ( int i = 0; i < 5; ++i )
+            s.hash = mixDelivery(s.hash, (uint64_t)s.rng_count, (uint64_t)i, s.last[i]);
+        if ( s.rng_count == s.max_count ) {
+            ctx.primaryComponentOKToEndSim();
+            return true;
+        }
+        return false;
+    }
+    __device__ static void results(const State& s, uint64_t* r)
+    {
+        r[0] = (uint64_t)s.rng_count;
+        for ( int i = 0; i < 5; ++i )
+            r[1 + i] = s.last[i];
+        r[6] = s.hash;
+    }
+};
+
+#endif // __CUDACC__
+
+// ---- the registry: what SST_ELI_REGISTER_COMPONENT's static initialisers build in the reference
+// (eli/elibase.h:124-147 LoadedLibraries); here a constexpr table, queried through sstb200_component_type_*.
+struct ElementInfo
+{
+    uint32_t    type;
+    const char* eli_name;
+    uint32_t    state_bytes;
+    uint32_t    aux_bytes;
+    int         has_payload;
+    const char* description;
+};
+
+} // namespace sstb200

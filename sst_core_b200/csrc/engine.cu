@@ -1,0 +1,1345 @@
+// libsstb200: B200-native conservative parallel discrete-event engine (sm_100a) for SST-core's event-delivery path.
+// See DESIGN.md for the data layout and the roofline of each kernel; include/sstb200.h for the C ABI.
+//
+// What replaces what (reference paths relative to src/sst/core/):
+//   TimeVortexPQ (impl/timevortex/timeVortexPQ.cc:62-95) + Link::send_impl (link.cc:623-658)
+//       -> a calendar of W lookahead-window slots x blocks of 256 components, structure-of-arrays in HBM.  A send is
+//          the most-significant-digit pass of a radix sort on the 64-bit delivery key
+//          (destination block | window slot) fused into the producing handler: one reservation + one record write.
+//   Simulation::run pop/execute loop (simulation.cc:1099-1153) + Clock::execute (clock.cc:314-397)
+//       -> dispatch_kernel: one CTA per block of 256 components loads the block's bin for the current window,
+//          finishes the sort in shared memory (counting sort by component with warp-level scans, then the
+//          (time, port order, sequence) order inside each component's segment -- the reference's
+//          (delivery_time, priority<<32|order_tag, queue_order) order, activity.h:64-73), and every thread walks its
+//          component's segment in order, merged with that component's clock ticks (clock priority 40 before event
+//          priority 50 at equal time, activity.h:29-40), calling the device handler functors (components.cuh).
+//   SyncManager::execute / RankSyncSerialSkip::exchange (sync/syncManager.cc:547-732, sync/rankSyncSerialSkip.cc:209-343)
+//       -> per window: cross-rank sends go to per-destination outboxes, the driver moves them over NVLink (NCCL),
+//          ingest_kernel bins them, advance_kernel folds the all-gathered control words (pending events, primary
+//          components, active clocks, error, exit time) and opens the next window.
+//   Exit / StopAction (exit.cc:53-132, stopAction.h:27-57) -> advance_kernel; the window is clipped at stop_at so that
+//          nothing AT the stop time runs (StopAction priority 30 < clock 40 < event 50).
+#include "../../include/sstb200.h"
+#include "components.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace sstb200 {
+
+static thread_local std::string g_error;
+void
+set_error(const std::string& s)
+{
+    g_error = s;
+}
+
+#define CUDA_OK(expr)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if ( _e != cudaSuccess ) {                                                                         \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" +             \
+                      std::to_string(__LINE__) + ")");                                                     \
+            return -2;                                                                                     \
+        }                                                                                                  \
+    } while ( 0 )
+
+constexpr int      BLOCK      = 256; // components per CTA == threads per CTA
+constexpr uint64_t TIME_NEVER = ~0ull;
+
+enum : uint32_t { ERR_BIN_OVERFLOW = 1, ERR_SMEM_OVERFLOW = 2, ERR_TIME_FAULT = 3, ERR_OUTBOX_OVERFLOW = 4, ERR_TRACE_OVERFLOW = 5 };
+enum { CW_PENDING = 0, CW_PRIMARY = 1, CW_CLOCKS = 2, CW_ERROR = 3, CW_EXIT_TIME = 4, CW_WORDS = 8 };
+
+struct Ctrl
+{
+    uint64_t           k;     // window index; the window is [k*w, min((k+1)*w, stop_at))
+    uint64_t           T, T_end;
+    uint64_t           stop_at, w;
+    unsigned long long events_delivered, clock_ticks, events_sent;
+    unsigned long long max_bin_fill, max_due;
+    uint64_t           end_time;
+    uint32_t           done, error;
+    unsigned long long error_info[4];
+    long long          local[CW_WORDS]; // control words folded across ranks by advance_kernel
+    unsigned long long trace_n;
+    uint64_t           windows;
+    uint32_t           had_primary, pad;
+};
+
+struct Dev
+{
+    Ctrl*           ctrl;
+    uint32_t        n_local, c0, nbins, W, cap, emax;
+    uint32_t        P0, nport_local;
+    uint32_t        rank, n_ranks;
+    const uint32_t* rank_comp_begin; // [n_ranks+1] (device)
+    const uint32_t* comp_type;
+    const int64_t*  comp_param;
+    const uint32_t* port_off; // [n_local+1] GLOBAL directed-port ids
+    const uint4*    link;     // [nport_local] {dst_port, dst_comp, latency lo, latency hi}
+    const uint64_t* clock_period;
+    uint64_t*       next_tick;
+    uint32_t*       send_seq;
+    uint8_t*        state;
+    uint32_t        state_stride;
+    uint8_t*        aux;
+    uint32_t        aux_stride;
+    uint64_t*       ev_time;
+    uint64_t*       ev_dst_seq;
+    uint64_t*       ev_payload;
+    uint32_t*       bin_count; // [W*nbins]
+    unsigned long long* outbox;    // [n_ranks][1 + outbox_cap*4]
+    unsigned long long* inbox;     // same shape, filled by the driver's exchange
+    uint64_t        xwords;    // words per rank slot
+    uint32_t        outbox_cap;
+    long long*      gathered;  // [n_ranks][CW_WORDS]
+    uint64_t*       tr_time;
+    uint32_t*       tr_comp;
+    uint32_t*       tr_port;
+    uint32_t*       tr_idx;
+    uint64_t*       tr_payload;
+    uint32_t*       deliv_seq;
+    uint64_t        trace_cap;
+    int             stats_on, has_payload;
+};
+
+// ================================================================================================ device side
+__device__ __forceinline__ void
+raise_error(const Dev& d, uint32_t code, uint64_t a, uint64_t b, uint64_t c)
+{
+    if ( atomicCAS(&d.ctrl->error, 0u, code) == 0u ) {
+        d.ctrl->error_info[0] = a;
+        d.ctrl->error_info[1] = b;
+        d.ctrl->error_info[2] = c;
+        d.ctrl->error_info[3] = d.ctrl->k;
+    }
+}
+
+// The fused "send": most-significant-digit scatter of the delivery key.  Local destination -> calendar bin of the
+// (window slot, destination block); remote destination -> outbox of the owning rank.
+__device__ __forceinline__ void
+emit(const Dev& d, uint64_t k, uint64_t time, uint32_t dst_port, uint32_t dst_comp, uint32_t seq, uint64_t payload)
+{
+    if ( d.n_ranks > 1 && (dst_comp < d.c0 || dst_comp >= d.c0 + d.n_local) ) {
+        uint32_t r = 0;
+        while ( r + 1 < d.n_ranks && dst_comp >= d.rank_comp_begin[r + 1] )
+            ++r;
+        unsigned long long* box = d.outbox + (uint64_t)r * d.xwords;
+        unsigned long long  pos = atomicAdd(&box[0], 1ull);
+        if ( pos >= d.outbox_cap ) {
+            raise_error(d, ERR_OUTBOX_OVERFLOW, r, pos, d.outbox_cap);
+            return;
+        }
+        unsigned long long* rec = box + 1 + pos * 4;
+        rec[0]                  = time;
+        rec[1]                  = ((unsigned long long)dst_port << 32) | seq;
+        rec[2]                  = payload;
+        rec[3]                  = dst_comp;
+        return;
+    }
+    const uint32_t lc   = dst_comp - d.c0;
+    const uint32_t bin  = lc / BLOCK;
+    const uint64_t base = k * d.ctrl->w;
+    uint64_t       dk;
+    const uint64_t dt = time - base;
+    if ( time < base + d.ctrl->w ) {
+        // would have to be delivered in the window that is being drained: violates the lookahead
+        raise_error(d, ERR_TIME_FAULT, time, base, dst_comp);
+        return;
+    }
+    if ( (dt >> 32) == 0 && (d.ctrl->w >> 32) == 0 )
+        dk = (uint32_t)dt / (uint32_t)d.ctrl->w;
+    else
+        dk = dt / d.ctrl->w;
+    if ( dk > d.W - 1 ) dk = d.W - 1; // beyond the calendar horizon: parked in the farthest slot, re-binned there
+    const uint32_t slot = (uint32_t)((k + dk) % d.W);
+    const uint32_t idx  = slot * d.nbins + bin;
+    const uint32_t pos  = atomicAdd(&d.bin_count[idx], 1u);
+    if ( pos >= d.cap ) {
+        raise_error(d, ERR_BIN_OVERFLOW, slot, bin, pos);
+        return;
+    }
+    const uint64_t off = (uint64_t)idx * d.cap + pos;
+    d.ev_time[off]     = time;
+    d.ev_dst_seq[off]  = ((uint64_t)dst_port << 32) | seq;
+    if ( d.has_payload ) d.ev_payload[off] = payload;
+}
+
+// What a handler sees of the core (BaseComponent / Link API subset)
+struct Ctx
+{
+    const Dev& d;
+    uint64_t   now;    // getCurrentSimCycle()
+    uint64_t   k;      // current window
+    uint32_t   comp;   // global component id
+    uint32_t   port0;  // global id of this component's first directed port
+    uint32_t   nports;
+    uint8_t*   aux;
+    uint32_t   seq;    // per-component send sequence: the FIFO tie-break the reference gets from queue_order
+    uint32_t   sent;
+    int        stats_on;
+
+    __device__ __forceinline__ bool connected(int port) const
+    {
+        return __ldg(&d.link[port0 - d.P0 + (uint32_t)port]).x != SSTB200_NO_PEER;
+    }
+    // Link::send(delay, ev): delivery time = now + delay + latency of the sending end (link.cc:636)
+    __device__ __forceinline__ void send(int port, uint64_t delay, uint64_t payload)
+    {
+        const uint4 l = __ldg(&d.link[port0 - d.P0 + (uint32_t)port]);
+        if ( l.x == SSTB200_NO_PEER ) return;
+        const uint64_t lat = ((uint64_t)l.w << 32) | l.z;
+        emit(d, k, now + delay + lat, l.x, l.y, seq++, payload);
+        sent++;
+    }
+    __device__ __forceinline__ void primaryComponentOKToEndSim()
+    {
+        atomicAdd((unsigned long long*)&d.ctrl->local[CW_PRIMARY], (unsigned long long)(-1ll));
+        atomicMax((unsigned long long*)&d.ctrl->local[CW_EXIT_TIME], (unsigned long long)now);
+    }
+};
+
+template <class F>
+__device__ __forceinline__ void
+with_element(uint32_t type, F&& f)
+{
+    switch ( type ) {
+    case TYPE_MESH:
+        f(MeshElement {});
+        break;
+    case TYPE_PHOLD:
+        f(PholdElement {});
+        break;
+    case TYPE_CLOCKNODE:
+        f(ClockNodeElement {});
+        break;
+    case TYPE_RNGCOMP:
+        f(RngElement {});
+        break;
+    default:
+        break;
+    }
+}
+
+template <class S>
+__device__ __forceinline__ void
+load_state(S& s, const uint8_t* p)
+{
+    static_assert(sizeof(S) % 8 == 0, "element State must be a multiple of 8 bytes");
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(p);
+    uint64_t*       dst = reinterpret_cast<uint64_t*>(&s);
+#pragma unroll
+    for ( int i = 0; i < (int)(sizeof(S) / 8); ++i )
+        dst[i] = src[i];
+}
+template <class S>
+__device__ __forceinline__ void
+store_state(const S& s, uint8_t* p)
+{
+    uint64_t*       dst = reinterpret_cast<uint64_t*>(p);
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(&s);
+#pragma unroll
+    for ( int i = 0; i < (int)(sizeof(S) / 8); ++i )
+        dst[i] = src[i];
+}
+
+// ---- construct + setup(): performWireUp (simulation.cc:824-859) and setup() (simulation.cc:969-987)
+__global__ void __launch_bounds__(BLOCK)
+setup_kernel(Dev d)
+{
+    const uint32_t lc = blockIdx.x * BLOCK + threadIdx.x;
+    if ( lc >= d.n_local ) return;
+    const uint32_t type = d.comp_type[lc];
+    Ctx            ctx { d, 0, 0, d.c0 + lc, d.port_off[lc], d.port_off[lc + 1] - d.port_off[lc],
+                         d.aux + (uint64_t)lc * d.aux_stride, 0, 0, d.stats_on };
+    const uint64_t period = d.clock_period[lc];
+    d.next_tick[lc]       = period ? period : TIME_NEVER; // first tick at `period`, never at 0 (clock.cc:400-420)
+    with_element(type, [&](auto el) {
+        using E = decltype(el);
+        typename E::State s;
+        E::construct(ctx, s, d.comp_param + (uint64_t)lc * NPARAM);
+        E::setup(ctx, s);
+        store_state(s, d.state + (uint64_t)lc * d.state_stride);
+    });
+    d.send_seq[lc] = ctx.seq;
+    if ( d.deliv_seq ) d.deliv_seq[lc] = 0;
+    if ( ctx.sent ) {
+        atomicAdd(&d.ctrl->events_sent, (unsigned long long)ctx.sent);
+        atomicAdd((unsigned long long*)&d.ctrl->local[CW_PENDING], (unsigned long long)ctx.sent);
+    }
+    if ( period ) atomicAdd((unsigned long long*)&d.ctrl->local[CW_CLOCKS], 1ull);
+    atomicAdd((unsigned long long*)&d.ctrl->local[CW_PRIMARY], 1ull); // every in-scope element is a primary component
+}
+
+// Exclusive scan of one u32 per thread over the CTA (warp shuffles + one shared round).
+__device__ __forceinline__ uint32_t
+block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& total)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t       inc = v;
+#pragma unroll
+    for ( int o = 1; o < 32; o <<= 1 ) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ( lane >= (uint32_t)o ) inc += t;
+    }
+    if ( lane == 31 ) s_warp[warp] = inc;
+    __syncthreads();
+    if ( warp == 0 ) {
+        uint32_t wv = (lane < BLOCK / 32) ? s_warp[lane] : 0;
+        uint32_t wi = wv;
+#pragma unroll
+        for ( int o = 1; o < BLOCK / 32; o <<= 1 ) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if ( lane >= (uint32_t)o ) wi += t;
+        }
+        if ( lane < BLOCK / 32 ) s_warp[lane] = wi - wv; // exclusive warp offsets
+        if ( lane == BLOCK / 32 - 1 ) s_warp[BLOCK / 32] = wi;
+    }
+    __syncthreads();
+    total = s_warp[BLOCK / 32];
+    return s_warp[warp] + inc - v;
+}
+
+// ---- one lookahead window for one block of 256 components
+template <bool PAYLOAD>
+__global__ void __launch_bounds__(BLOCK)
+dispatch_kernel(Dev d)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    Ctrl* const    ctrl = d.ctrl;
+    if ( ctrl->done ) return;
+    const uint64_t k     = ctrl->k;
+    const uint64_t T     = ctrl->T;
+    const uint64_t T_end = ctrl->T_end;
+    const uint64_t w     = ctrl->w;
+    const uint32_t bin   = blockIdx.x;
+    const uint32_t slot  = (uint32_t)(k % d.W);
+    const uint32_t tid   = threadIdx.x;
+    const uint32_t lc    = bin * BLOCK + tid;
+    const bool     valid = lc < d.n_local;
+
+    // shared-memory carve-up
+    uint64_t* s_pay      = reinterpret_cast<uint64_t*>(smem_raw); // [emax] (PAYLOAD only)
+    uint8_t*  p          = smem_raw + (PAYLOAD ? (size_t)d.emax * 8 : 0);
+    uint32_t* s_time     = reinterpret_cast<uint32_t*>(p);
+    uint32_t* s_dst      = s_time + d.emax;
+    uint32_t* s_seq      = s_dst + d.emax;
+    uint32_t* s_cr       = s_seq + d.emax;                  // comp<<16 | rank within comp
+    uint32_t* s_port_off = s_cr + d.emax;                   // [BLOCK+1]
+    uint32_t* s_cnt      = s_port_off + BLOCK + 1;          // [BLOCK]
+    uint32_t* s_off      = s_cnt + BLOCK;                   // [BLOCK]
+    uint32_t* s_warp     = s_off + BLOCK;                   // [BLOCK/32+1]
+    uint32_t* s_misc     = s_warp + BLOCK / 32 + 1;         // [4]
+    uint16_t* s_perm     = reinterpret_cast<uint16_t*>(s_misc + 4); // [emax]
+
+    const uint32_t n_in = d.bin_count[slot * d.nbins + bin];
+    {
+        const uint32_t j = bin * BLOCK + tid;
+        s_port_off[tid]  = d.port_off[j <= d.n_local ? j : d.n_local];
+        if ( tid == 0 ) {
+            const uint32_t e  = (bin + 1) * BLOCK;
+            s_port_off[BLOCK] = d.port_off[e <= d.n_local ? e : d.n_local];
+            s_misc[0]         = 0;
+        }
+        s_cnt[tid] = 0;
+    }
+    __syncthreads();
+
+    // ---- phase 1: load the bin; stage due events in shared memory, re-bin the ones that are not due yet
+    uint32_t       carried = 0, dropped = 0;
+    const uint64_t bin_base = (uint64_t)(slot * d.nbins + bin) * d.cap;
+    for ( uint32_t i = tid; i < n_in; i += BLOCK ) {
+        const uint64_t t  = d.ev_time[bin_base + i];
+        const uint64_t ds = d.ev_dst_seq[bin_base + i];
+        uint64_t       pl = 0;
+        if ( PAYLOAD ) pl = d.ev_payload[bin_base + i];
+        const uint32_t dst = (uint32_t)(ds >> 32);
+        // component of the receiving port: largest j with s_port_off[j] <= dst
+        uint32_t lo = 0, hi = BLOCK;
+        while ( hi - lo > 1 ) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if ( s_port_off[mid] <= dst )
+                lo = mid;
+            else
+                hi = mid;
+        }
+        if ( t < T ) {
+            raise_error(d, ERR_TIME_FAULT, t, T, bin * BLOCK + lo + d.c0);
+        }
+        else if ( t >= T_end ) {
+            if ( t < (k + 1) * w ) {
+                dropped++; // at or after a stop time inside this window: never delivered (StopAction priority 30)
+            }
+            else {
+                emit(d, k, t, dst, d.c0 + bin * BLOCK + lo, (uint32_t)ds, pl);
+                carried++;
+            }
+        }
+        else {
+            const uint32_t e = atomicAdd(&s_misc[0], 1u);
+            if ( e < d.emax ) {
+                const uint32_t r = atomicAdd(&s_cnt[lo], 1u);
+                s_time[e]        = (uint32_t)(t - T);
+                s_dst[e]         = dst;
+                s_seq[e]         = (uint32_t)ds;
+                s_cr[e]          = (lo << 16) | (r & 0xFFFFu);
+                if ( PAYLOAD ) s_pay[e] = pl;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t n_due = s_misc[0];
+    if ( n_due > d.emax ) {
+        if ( tid == 0 ) raise_error(d, ERR_SMEM_OVERFLOW, bin, n_due, d.emax);
+        return; // uniform across the CTA
+    }
+
+    // ---- phase 2: counting sort by component (warp-level scans), permutation into per-component segments
+    const uint32_t my_cnt = s_cnt[tid];
+    uint32_t       total;
+    const uint32_t my_off = block_exclusive_scan(my_cnt, s_warp, total);
+    s_off[tid]            = my_off;
+    __syncthreads();
+    for ( uint32_t e = tid; e < n_due; e += BLOCK ) {
+        const uint32_t cr          = s_cr[e];
+        s_perm[s_off[cr >> 16] + (cr & 0xFFFFu)] = (uint16_t)e;
+    }
+    __syncthreads();
+
+    // ---- phase 3: every thread orders its component's segment by (time, port, sequence) and runs the handlers,
+    // merged with the component's clock ticks
+    uint32_t delivered = 0, ticks = 0, sent = 0, clocks_stopped = 0;
+    if ( valid ) {
+        uint16_t* seg = s_perm + my_off;
+        for ( uint32_t a = 1; a < my_cnt; ++a ) { // insertion sort; segments are a handful of events
+            const uint16_t ea = seg[a];
+            const uint32_t ta = s_time[ea], da = s_dst[ea], qa = s_seq[ea];
+            uint32_t       b  = a;
+            while ( b > 0 ) {
+                const uint16_t eb = seg[b - 1];
+                const uint32_t tb = s_time[eb], db = s_dst[eb], qb = s_seq[eb];
+                const bool     gt = (tb > ta) || (tb == ta && (db > da || (db == da && (int32_t)(qb - qa) > 0)));
+                if ( !gt ) break;
+                seg[b] = eb;
+                --b;
+            }
+            seg[b] = ea;
+        }
+
+        const uint64_t period    = d.clock_period[lc];
+        uint64_t       next_tick = d.next_tick[lc];
+        const bool     has_work  = my_cnt > 0 || next_tick < T_end;
+        if ( has_work ) {
+            const uint32_t type = d.comp_type[lc];
+            Ctx            ctx { d, T, k, d.c0 + lc, s_port_off[tid], s_port_off[tid + 1] - s_port_off[tid],
+                                 d.aux + (uint64_t)lc * d.aux_stride, d.send_seq[lc], 0, d.stats_on };
+            uint32_t       dseq = d.deliv_seq ? d.deliv_seq[lc] : 0;
+            with_element(type, [&](auto el) {
+                using E = decltype(el);
+                typename E::State s;
+                load_state(s, d.state + (uint64_t)lc * d.state_stride);
+                uint64_t cycle = (next_tick != TIME_NEVER && period) ? next_tick / period : 0;
+                uint32_t i     = 0;
+                for ( ;; ) {
+                    const uint64_t ev_t = (i < my_cnt) ? T + s_time[seg[i]] : TIME_NEVER;
+                    if ( next_tick < T_end && next_tick <= ev_t ) {
+                        ctx.now         = next_tick;
+                        const bool stop = E::clockTick(ctx, s, cycle);
+                        ticks++;
+                        cycle++;
+                        if ( stop ) {
+                            next_tick = TIME_NEVER; // handler unregistered itself (clock.cc:324-367)
+                            clocks_stopped++;
+                        }
+                        else
+                            next_tick += period;
+                        continue;
+                    }
+                    if ( i >= my_cnt ) break;
+                    const uint32_t e    = seg[i++];
+                    const uint32_t port = s_dst[e] - ctx.port0;
+                    uint64_t       pl   = PAYLOAD ? s_pay[e] : 0;
+                    ctx.now             = ev_t;
+                    if ( d.trace_cap ) {
+                        const unsigned long long tp = atomicAdd(&ctrl->trace_n, 1ull);
+                        if ( tp < d.trace_cap ) {
+                            d.tr_time[tp]    = ev_t;
+                            d.tr_comp[tp]    = ctx.comp;
+                            d.tr_port[tp]    = port;
+                            d.tr_idx[tp]     = dseq;
+                            d.tr_payload[tp] = pl;
+                        }
+                        dseq++;
+                    }
+                    E::handleEvent(ctx, s, (int)port, pl);
+                    delivered++;
+                }
+                store_state(s, d.state + (uint64_t)lc * d.state_stride);
+            });
+            d.send_seq[lc]  = ctx.seq;
+            d.next_tick[lc] = next_tick;
+            if ( d.deliv_seq ) d.deliv_seq[lc] = dseq;
+            sent = ctx.sent;
+        }
+    }
+
+    // ---- phase 4: fold counters (one atomic per warp), recycle the bin
+    {
+        uint32_t v0 = delivered, v1 = ticks, v2 = sent, v3 = clocks_stopped, v4 = dropped;
+#pragma unroll
+        for ( int o = 16; o > 0; o >>= 1 ) {
+            v0 += __shfl_down_sync(0xffffffffu, v0, o);
+            v1 += __shfl_down_sync(0xffffffffu, v1, o);
+            v2 += __shfl_down_sync(0xffffffffu, v2, o);
+            v3 += __shfl_down_sync(0xffffffffu, v3, o);
+            v4 += __shfl_down_sync(0xffffffffu, v4, o);
+        }
+        if ( (tid & 31) == 0 ) {
+            if ( v0 ) atomicAdd(&ctrl->events_delivered, (unsigned long long)v0);
+            if ( v1 ) atomicAdd(&ctrl->clock_ticks, (unsigned long long)v1);
+            if ( v2 ) atomicAdd(&ctrl->events_sent, (unsigned long long)v2);
+            const long long dp = (long long)v2 - (long long)v0 - (long long)v4;
+            if ( dp ) atomicAdd((unsigned long long*)&ctrl->local[CW_PENDING], (unsigned long long)dp);
+            if ( v3 ) atomicAdd((unsigned long long*)&ctrl->local[CW_CLOCKS], (unsigned long long)(-(long long)v3));
+        }
+    }
+    if ( tid == 0 ) {
+        d.bin_count[slot * d.nbins + bin] = 0;
+        if ( n_in > ctrl->max_bin_fill ) atomicMax(&ctrl->max_bin_fill, (unsigned long long)n_in);
+        if ( n_due > ctrl->max_due ) atomicMax(&ctrl->max_due, (unsigned long long)n_due);
+    }
+}
+
+// ---- bin the events received from other ranks (RankSyncSerialSkip::exchange re-send, rankSyncSerialSkip.cc:291-295)
+__global__ void __launch_bounds__(BLOCK)
+ingest_kernel(Dev d)
+{
+    if ( d.ctrl->done ) return;
+    const uint64_t k = d.ctrl->k;
+    for ( uint32_t r = 0; r < d.n_ranks; ++r ) {
+        if ( r == d.rank ) continue;
+        const unsigned long long* box = d.inbox + (uint64_t)r * d.xwords;
+        const uint64_t            n   = box[0] < d.outbox_cap ? box[0] : d.outbox_cap;
+        for ( uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (uint64_t)gridDim.x * BLOCK ) {
+            const unsigned long long* rec = box + 1 + i * 4;
+            emit(d, k, rec[0], (uint32_t)(rec[1] >> 32), (uint32_t)rec[3], (uint32_t)rec[1], rec[2]);
+        }
+    }
+}
+
+// ---- open the next window (SyncManager::computeNextInsert syncManager.cc:772-798; Exit::check exit.cc:111-132)
+__global__ void
+advance_kernel(Dev d)
+{
+    if ( threadIdx.x != 0 || blockIdx.x != 0 ) return;
+    Ctrl* c = d.ctrl;
+    if ( c->done ) return;
+    long long pending = 0, primary = 0, clocks = 0, err = 0;
+    uint64_t  exit_time = 0;
+    if ( d.n_ranks > 1 ) {
+        for ( uint32_t r = 0; r < d.n_ranks; ++r ) {
+            const long long* g = d.gathered + (uint64_t)r * CW_WORDS;
+            pending += g[CW_PENDING];
+            primary += g[CW_PRIMARY];
+            clocks += g[CW_CLOCKS];
+            err += g[CW_ERROR];
+            if ( (uint64_t)g[CW_EXIT_TIME] > exit_time ) exit_time = (uint64_t)g[CW_EXIT_TIME];
+        }
+        for ( uint32_t r = 0; r < d.n_ranks; ++r )
+            d.outbox[(uint64_t)r * d.xwords] = 0; // outboxes have been shipped
+    }
+    else {
+        pending   = c->local[CW_PENDING];
+        primary   = c->local[CW_PRIMARY];
+        clocks    = c->local[CW_CLOCKS];
+        exit_time = (uint64_t)c->local[CW_EXIT_TIME];
+    }
+    c->windows++;
+    if ( c->error || err ) {
+        if ( !c->error ) c->error = (uint32_t)0x80000000u; // another rank failed
+        c->done = 1;
+        return;
+    }
+    if ( c->had_primary && primary <= 0 ) { // Exit: last primary component said OKToEndSim (exit.cc:53-68)
+        c->done     = 1;
+        c->end_time = exit_time;
+        return;
+    }
+    const uint64_t next_T = (c->k + 1) * c->w;
+    if ( c->stop_at && next_T >= c->stop_at ) { // StopAction
+        c->done     = 1;
+        c->end_time = c->stop_at;
+        return;
+    }
+    if ( pending <= 0 && clocks <= 0 ) { // nothing left in the (virtual) TimeVortex
+        c->done     = 1;
+        c->end_time = c->T_end;
+        return;
+    }
+    c->k     = c->k + 1;
+    c->T     = next_T;
+    c->T_end = (c->stop_at && next_T + c->w > c->stop_at) ? c->stop_at : next_T + c->w;
+}
+
+__global__ void
+publish_control_kernel(Dev d)
+{
+    // snapshot of the error flag into the control words that get all-gathered
+    if ( threadIdx.x == 0 && blockIdx.x == 0 ) d.ctrl->local[CW_ERROR] = d.ctrl->error ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(BLOCK)
+results_kernel(Dev d, uint64_t* out)
+{
+    const uint32_t lc = blockIdx.x * BLOCK + threadIdx.x;
+    if ( lc >= d.n_local ) return;
+    uint64_t r[NRESULT];
+#pragma unroll
+    for ( int i = 0; i < NRESULT; ++i )
+        r[i] = 0;
+    with_element(d.comp_type[lc], [&](auto el) {
+        using E = decltype(el);
+        typename E::State s;
+        load_state(s, d.state + (uint64_t)lc * d.state_stride);
+        E::results(s, r);
+    });
+#pragma unroll
+    for ( int i = 0; i < NRESULT; ++i )
+        out[(uint64_t)lc * NRESULT + i] = r[i];
+}
+
+// ================================================================================================ RNG stream kernels
+template <class G>
+__device__ __forceinline__ void
+stream_body(G& g, uint64_t n, uint32_t* out, unsigned long long* checksum)
+{
+    unsigned long long cs = 0;
+    for ( uint64_t i = 0; i < n; ++i ) {
+        const uint32_t v = g.u32();
+        if ( out ) out[i] = v;
+        cs += (i + 1) * (unsigned long long)v;
+    }
+    *checksum = cs;
+}
+
+__global__ void __launch_bounds__(128)
+rng_stream_kernel(int kind, uint64_t s1, uint64_t s2, uint64_t stride1, uint64_t stride2, uint64_t n_streams,
+    uint64_t draws, uint32_t* out, unsigned long long* checksum, uint32_t* mt_scratch)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ( j >= n_streams ) return;
+    uint32_t* o = out ? out + j * draws : nullptr;
+    const uint64_t a = s1 + j * stride1, b = s2 + j * stride2;
+    if ( kind == 0 ) {
+        uint32_t* mt = mt_scratch + j * MT_N;
+        mt_seed(mt, (uint32_t)a);
+        MersenneDev g { mt, 0 };
+        stream_body(g, draws, o, checksum + j);
+    }
+    else if ( kind == 1 ) {
+        MarsagliaDev g { (uint32_t)a, (uint32_t)b };
+        stream_body(g, draws, o, checksum + j);
+    }
+    else {
+        XorShiftDev g;
+        g.seed((uint32_t)a);
+        stream_body(g, draws, o, checksum + j);
+    }
+}
+
+template <class G>
+__device__ void
+ticks_body(G& g, uint64_t first, uint64_t n, uint64_t* out)
+{
+    for ( uint64_t t = 0; t < first + n; ++t ) {
+        double   nU  = g.uniform();
+        uint32_t U32 = g.u32();
+        uint64_t U64 = rng_u64(g);
+        int32_t  I32 = rng_i32(g);
+        int64_t  I64 = rng_i64(g);
+        if ( t >= first ) {
+            uint64_t* o = out + (t - first) * 5;
+            o[0]        = (uint64_t)__double_as_longlong(nU);
+            o[1]        = U32;
+            o[2]        = U64;
+            o[3]        = (uint64_t)(int64_t)I32;
+            o[4]        = (uint64_t)I64;
+        }
+    }
+}
+
+__global__ void
+rng_ticks_kernel(int kind, uint64_t s1, uint64_t s2, uint64_t first, uint64_t n, uint64_t* out, uint32_t* mt)
+{
+    if ( threadIdx.x || blockIdx.x ) return;
+    if ( kind == 0 ) {
+        mt_seed(mt, (uint32_t)s1);
+        MersenneDev g { mt, 0 };
+        ticks_body(g, first, n, out);
+    }
+    else if ( kind == 1 ) {
+        MarsagliaDev g { (uint32_t)s1, (uint32_t)s2 };
+        ticks_body(g, first, n, out);
+    }
+    else {
+        XorShiftDev g;
+        g.seed((uint32_t)s1);
+        ticks_body(g, first, n, out);
+    }
+}
+
+template <class G>
+__device__ void
+dist_body(G& g, int dist, const double* params, int np, uint64_t n, double* out)
+{
+    GaussianDev gs { np > 0 ? params[0] : 0.0, np > 1 ? params[1] : 1.0, 0.0, false };
+    for ( uint64_t i = 0; i < n; ++i ) {
+        double v;
+        switch ( dist ) {
+        case 0:
+            v = dist_discrete(g, params, (uint32_t)np); // params = exclusive prefix sums (host-prepared)
+            break;
+        case 1:
+            v = dist_exponential(g, params[0]);
+            break;
+        case 2:
+            v = gs.next(g);
+            break;
+        case 3:
+            v = dist_poisson(g, params[1]); // params[1] = exp(-lambda) from the host
+            break;
+        case 4:
+            v = dist_uniform_bins(g, (uint32_t)params[0]);
+            break;
+        default:
+            v = params[0];
+        }
+        out[i] = v;
+    }
+}
+
+__global__ void
+rng_dist_kernel(int dist, const double* params, int np, int kind, uint64_t s1, uint64_t s2, uint64_t n, double* out,
+    uint32_t* mt)
+{
+    if ( threadIdx.x || blockIdx.x ) return;
+    if ( kind == 0 ) {
+        mt_seed(mt, (uint32_t)s1);
+        MersenneDev g { mt, 0 };
+        dist_body(g, dist, params, np, n, out);
+    }
+    else if ( kind == 1 ) {
+        MarsagliaDev g { (uint32_t)s1, (uint32_t)s2 };
+        dist_body(g, dist, params, np, n, out);
+    }
+    else {
+        XorShiftDev g;
+        g.seed((uint32_t)s1);
+        dist_body(g, dist, params, np, n, out);
+    }
+}
+
+// ================================================================================================ host side
+static const ElementInfo kElements[] = {
+    { TYPE_MESH, MeshElement::ELI_NAME, (uint32_t)sizeof(MeshElement::State), MeshElement::AUX_BYTES,
+        MeshElement::HAS_PAYLOAD, "message_mesh enclosing component with message_port/port_slot/route_message" },
+    { TYPE_PHOLD, PholdElement::ELI_NAME, (uint32_t)sizeof(PholdElement::State), PholdElement::AUX_BYTES,
+        PholdElement::HAS_PAYLOAD, "PHOLD-style node, integer delays, 8-byte payload" },
+    { TYPE_CLOCKNODE, ClockNodeElement::ELI_NAME, (uint32_t)sizeof(ClockNodeElement::State),
+        ClockNodeElement::AUX_BYTES, ClockNodeElement::HAS_PAYLOAD, "clock-driven node (coreTestComponent style)" },
+    { TYPE_RNGCOMP, RngElement::ELI_NAME, (uint32_t)sizeof(RngElement::State), RngElement::AUX_BYTES,
+        RngElement::HAS_PAYLOAD, "coreTestRNGComponent: 1 GHz clock drawing from an SST::RNG generator" },
+};
+constexpr int kNumElements = (int)(sizeof(kElements) / sizeof(kElements[0]));
+
+static const ElementInfo*
+element_by_type(uint32_t t)
+{
+    for ( int i = 0; i < kNumElements; ++i )
+        if ( kElements[i].type == t ) return &kElements[i];
+    return nullptr;
+}
+
+} // namespace sstb200
+
+using namespace sstb200;
+
+struct sstb200_engine
+{
+    Dev                d {};
+    int                device      = 0;
+    cudaStream_t       stream      = nullptr;
+    bool               own_stream  = false;
+    std::vector<void*> allocs;
+    Ctrl*              h_ctrl      = nullptr; // pinned mirror
+    uint64_t*          d_results   = nullptr;
+    size_t             smem_bytes  = 0;
+    uint64_t           launches    = 0;
+    bool               is_setup    = false;
+    uint32_t           n_ranks     = 1;
+
+    template <class T>
+    int alloc(T** p, size_t count, bool zero = true)
+    {
+        void*  q     = nullptr;
+        size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+        CUDA_OK(cudaMalloc(&q, bytes));
+        if ( zero ) CUDA_OK(cudaMemsetAsync(q, 0, bytes, stream));
+        allocs.push_back(q);
+        *p = (T*)q;
+        return 0;
+    }
+    template <class T>
+    int upload(const T** p, const T* host, size_t count)
+    {
+        T* q = nullptr;
+        if ( int rc = alloc(&q, count, false) ) return rc;
+        if ( count ) CUDA_OK(cudaMemcpyAsync(q, host, count * sizeof(T), cudaMemcpyHostToDevice, stream));
+        *p = q;
+        return 0;
+    }
+    int fetch_ctrl()
+    {
+        CUDA_OK(cudaMemcpyAsync(h_ctrl, d.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        return 0;
+    }
+    int launch_dispatch()
+    {
+        if ( d.has_payload )
+            dispatch_kernel<true><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
+        else
+            dispatch_kernel<false><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
+        launches++;
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    int launch_advance()
+    {
+        advance_kernel<<<1, 32, 0, stream>>>(d);
+        launches++;
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+};
+
+extern "C" {
+
+int
+sstb200_abi_version(void)
+{
+    return SSTB200_ABI_VERSION;
+}
+
+const char*
+sstb200_last_error(void)
+{
+    return g_error.c_str();
+}
+
+int
+sstb200_num_component_types(void)
+{
+    return kNumElements;
+}
+
+int
+sstb200_component_type_info(int idx, const char** eli_name, uint32_t* type_code, uint32_t* state_bytes,
+    uint32_t* aux_bytes, int* has_payload)
+{
+    if ( idx < 0 || idx >= kNumElements ) {
+        set_error("component type index out of range");
+        return -1;
+    }
+    if ( eli_name ) *eli_name = kElements[idx].eli_name;
+    if ( type_code ) *type_code = kElements[idx].type;
+    if ( state_bytes ) *state_bytes = kElements[idx].state_bytes;
+    if ( aux_bytes ) *aux_bytes = kElements[idx].aux_bytes;
+    if ( has_payload ) *has_payload = kElements[idx].has_payload;
+    return 0;
+}
+
+int
+sstb200_component_type_lookup(const char* eli_name)
+{
+    for ( int i = 0; i < kNumElements; ++i )
+        if ( eli_name && !strcmp(eli_name, kElements[i].eli_name) ) return (int)kElements[i].type;
+    return -1;
+}
+
+int
+sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_engine** out)
+{
+    if ( !m || !o || !out ) {
+        set_error("engine_create: null argument");
+        return -1;
+    }
+    int ndev = 0;
+    if ( cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 ) {
+        set_error("engine_create: no CUDA device available (libsstb200 has no CPU fallback)");
+        return -3;
+    }
+    if ( o->device < 0 || o->device >= ndev ) {
+        set_error("engine_create: bad device ordinal");
+        return -1;
+    }
+    const uint32_t n_ranks = o->n_ranks ? o->n_ranks : 1;
+    const uint32_t c0      = n_ranks > 1 ? o->comp_begin : 0;
+    const uint32_t c1      = n_ranks > 1 ? o->comp_end : m->ncomp;
+    if ( c1 < c0 || c1 > m->ncomp || (n_ranks > 1 && !o->rank_comp_begin) ) {
+        set_error("engine_create: bad component range");
+        return -1;
+    }
+    CUDA_OK(cudaSetDevice(o->device));
+    sstb200_engine* e = new sstb200_engine();
+    e->device         = o->device;
+    e->n_ranks        = n_ranks;
+    if ( o->stream ) {
+        e->stream = (cudaStream_t)o->stream;
+    }
+    else {
+        CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+        e->own_stream = true;
+    }
+    Dev& d    = e->d;
+    d.n_local = c1 - c0;
+    d.c0      = c0;
+    d.rank    = o->rank;
+    d.n_ranks = n_ranks;
+    d.nbins   = (d.n_local + BLOCK - 1) / BLOCK;
+    if ( d.nbins == 0 ) d.nbins = 1;
+    d.W       = o->calendar_slots >= 2 ? o->calendar_slots : 2;
+    d.cap     = o->bin_capacity ? o->bin_capacity : 8 * BLOCK;
+    d.emax    = o->smem_events ? o->smem_events : 8 * BLOCK;
+    if ( d.emax > 32768 ) d.emax = 32768;
+    d.stats_on = m->stats_enabled;
+
+    // lookahead window = minimum latency over every connected link (cut or not: a window is processed as one batch
+    // per component, so nothing sent inside it may be due inside it)
+    uint64_t       w     = o->window;
+    const uint32_t nport = m->port_off[m->ncomp];
+    if ( !w ) {
+        uint64_t mn = TIME_NEVER;
+        for ( uint32_t p = 0; p < nport; ++p )
+            if ( m->peer_port[p] != SSTB200_NO_PEER && m->latency[p] < mn ) mn = m->latency[p];
+        w = (mn == TIME_NEVER) ? 1000000ull : mn;
+    }
+    if ( w == 0 || w > 0x7fffffffull ) {
+        set_error("engine_create: lookahead window must be in [1, 2^31) cycles (zero-latency links are not allowed)");
+        delete e;
+        return -1;
+    }
+    for ( uint32_t p = 0; p < nport; ++p )
+        if ( m->peer_port[p] != SSTB200_NO_PEER && m->latency[p] < w ) {
+            set_error("engine_create: window larger than a link latency");
+            delete e;
+            return -1;
+        }
+
+    // per-rank slices
+    d.P0          = m->port_off[c0];
+    d.nport_local = m->port_off[c1] - d.P0;
+    std::vector<uint32_t> port_comp(nport);
+    for ( uint32_t c = 0; c < m->ncomp; ++c )
+        for ( uint32_t p = m->port_off[c]; p < m->port_off[c + 1]; ++p )
+            port_comp[p] = c;
+    std::vector<uint4> link(d.nport_local);
+    for ( uint32_t p = 0; p < d.nport_local; ++p ) {
+        const uint32_t gp   = d.P0 + p;
+        const uint32_t peer = m->peer_port[gp];
+        link[p].x           = peer;
+        link[p].y           = peer == SSTB200_NO_PEER ? 0 : port_comp[peer];
+        link[p].z           = (uint32_t)(m->latency[gp] & 0xFFFFFFFFull);
+        link[p].w           = (uint32_t)(m->latency[gp] >> 32);
+    }
+    uint32_t state_stride = 8, aux_stride = 0;
+    int      has_payload  = 0;
+    for ( uint32_t c = c0; c < c1; ++c ) {
+        const ElementInfo* ei = element_by_type(m->comp_type[c]);
+        if ( !ei ) {
+            set_error("engine_create: component " + std::to_string(c) + " has unknown type code " +
+                      std::to_string(m->comp_type[c]));
+            delete e;
+            return -1;
+        }
+        state_stride = std::max(state_stride, ei->state_bytes);
+        aux_stride   = std::max(aux_stride, ei->aux_bytes);
+    }
+    // payload arrays are needed if ANY component of the model (any rank) carries payloads
+    for ( uint32_t c = 0; c < m->ncomp; ++c ) {
+        const ElementInfo* ei = element_by_type(m->comp_type[c]);
+        if ( ei && ei->has_payload ) has_payload = 1;
+    }
+    d.state_stride = (state_stride + 15u) & ~15u;
+    d.aux_stride   = (aux_stride + 31u) & ~31u;
+    d.has_payload  = has_payload;
+
+    int rc = 0;
+    rc |= e->upload(&d.comp_type, m->comp_type + c0, d.n_local);
+    rc |= e->upload(&d.comp_param, m->comp_param + (size_t)c0 * NPARAM, (size_t)d.n_local * NPARAM);
+    rc |= e->upload(&d.port_off, m->port_off + c0, (size_t)d.n_local + 1);
+    rc |= e->upload(&d.link, link.data(), link.size());
+    rc |= e->upload(&d.clock_period, m->clock_period + c0, d.n_local);
+    if ( n_ranks > 1 ) rc |= e->upload(&d.rank_comp_begin, o->rank_comp_begin, (size_t)n_ranks + 1);
+    rc |= e->alloc(&d.next_tick, d.n_local);
+    rc |= e->alloc(&d.send_seq, d.n_local);
+    rc |= e->alloc(&d.state, (size_t)d.n_local * d.state_stride);
+    rc |= e->alloc(&d.aux, (size_t)d.n_local * d.aux_stride, false);
+    const size_t nev = (size_t)d.W * d.nbins * d.cap;
+    rc |= e->alloc(&d.ev_time, nev, false);
+    rc |= e->alloc(&d.ev_dst_seq, nev, false);
+    if ( has_payload ) rc |= e->alloc(&d.ev_payload, nev, false);
+    rc |= e->alloc(&d.bin_count, (size_t)d.W * d.nbins);
+    rc |= e->alloc(&d.ctrl, 1);
+    d.outbox_cap = o->outbox_capacity ? o->outbox_capacity : 65536;
+    d.xwords     = 1 + (uint64_t)d.outbox_cap * 4;
+    if ( n_ranks > 1 ) {
+        rc |= e->alloc(&d.outbox, (size_t)n_ranks * d.xwords);
+        rc |= e->alloc(&d.inbox, (size_t)n_ranks * d.xwords);
+        rc |= e->alloc(&d.gathered, (size_t)n_ranks * CW_WORDS);
+    }
+    d.trace_cap = o->trace_capacity;
+    if ( d.trace_cap ) {
+        rc |= e->alloc(&d.tr_time, d.trace_cap);
+        rc |= e->alloc(&d.tr_comp, d.trace_cap);
+        rc |= e->alloc(&d.tr_port, d.trace_cap);
+        rc |= e->alloc(&d.tr_idx, d.trace_cap);
+        rc |= e->alloc(&d.tr_payload, d.trace_cap);
+        rc |= e->alloc(&d.deliv_seq, d.n_local);
+    }
+    rc |= e->alloc(&e->d_results, (size_t)d.n_local * NRESULT);
+    if ( rc ) {
+        sstb200_engine_destroy(e);
+        return -2;
+    }
+    CUDA_OK(cudaMallocHost((void**)&e->h_ctrl, sizeof(Ctrl)));
+    memset(e->h_ctrl, 0, sizeof(Ctrl));
+    e->h_ctrl->w       = w;
+    e->h_ctrl->stop_at = m->stop_at;
+    e->h_ctrl->k       = 0;
+    e->h_ctrl->T       = 0;
+    e->h_ctrl->T_end   = (m->stop_at && w > m->stop_at) ? m->stop_at : w;
+    e->h_ctrl->had_primary = 1;
+    CUDA_OK(cudaMemcpyAsync(d.ctrl, e->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, e->stream));
+
+    e->smem_bytes = (size_t)d.emax * (has_payload ? 8 : 0) + (size_t)d.emax * 16 +
+                    (size_t)(BLOCK + 1 + BLOCK + BLOCK + BLOCK / 32 + 1 + 4) * 4 + (size_t)d.emax * 2 + 16;
+    if ( e->smem_bytes > 227 * 1024 ) {
+        set_error("engine_create: smem_events too large for 227 KB of shared memory");
+        sstb200_engine_destroy(e);
+        return -1;
+    }
+    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    *out = e;
+    return 0;
+}
+
+void
+sstb200_engine_destroy(sstb200_engine* e)
+{
+    if ( !e ) return;
+    cudaSetDevice(e->device);
+    if ( e->stream ) cudaStreamSynchronize(e->stream);
+    for ( void* p : e->allocs )
+        cudaFree(p);
+    if ( e->h_ctrl ) cudaFreeHost(e->h_ctrl);
+    if ( e->own_stream && e->stream ) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int
+sstb200_engine_setup(sstb200_engine* e)
+{
+    if ( !e ) return -1;
+    CUDA_OK(cudaSetDevice(e->device));
+    if ( e->is_setup ) {
+        set_error("engine_setup called twice");
+        return -1;
+    }
+    setup_kernel<<<e->d.nbins, BLOCK, 0, e->stream>>>(e->d);
+    e->launches++;
+    CUDA_OK(cudaGetLastError());
+    e->is_setup = true;
+    return 0;
+}
+
+int
+sstb200_engine_run(sstb200_engine* e, uint64_t max_windows, uint32_t check_every, int* finished)
+{
+    if ( !e ) return -1;
+    CUDA_OK(cudaSetDevice(e->device));
+    if ( !e->is_setup ) {
+        set_error("engine_run before engine_setup");
+        return -1;
+    }
+    if ( e->n_ranks > 1 ) {
+        set_error("engine_run is single-rank; step a multi-rank engine with dispatch/ingest/advance");
+        return -1;
+    }
+    if ( !check_every ) check_every = 64;
+    uint64_t done_windows = 0;
+    if ( finished ) *finished = 0;
+    for ( ;; ) {
+        uint32_t chunk = check_every;
+        if ( max_windows && max_windows - done_windows < chunk ) chunk = (uint32_t)(max_windows - done_windows);
+        for ( uint32_t i = 0; i < chunk; ++i ) {
+            if ( int rc = e->launch_dispatch() ) return rc;
+            if ( int rc = e->launch_advance() ) return rc;
+        }
+        done_windows += chunk;
+        if ( int rc = e->fetch_ctrl() ) return rc;
+        if ( e->h_ctrl->error ) {
+            char buf[256];
+            snprintf(buf, sizeof buf, "engine error %u at window %llu (info %llu %llu %llu)", e->h_ctrl->error,
+                (unsigned long long)e->h_ctrl->error_info[3], (unsigned long long)e->h_ctrl->error_info[0],
+                (unsigned long long)e->h_ctrl->error_info[1], (unsigned long long)e->h_ctrl->error_info[2]);
+            set_error(buf);
+            if ( finished ) *finished = 1;
+            return -4;
+        }
+        if ( e->h_ctrl->done ) {
+            if ( finished ) *finished = 1;
+            return 0;
+        }
+        if ( max_windows && done_windows >= max_windows ) return 0;
+    }
+}
+
+int
+sstb200_engine_dispatch(sstb200_engine* e)
+{
+    if ( !e || !e->is_setup ) return -1;
+    CUDA_OK(cudaSetDevice(e->device));
+    if ( int rc = e->launch_dispatch() ) return rc;
+    publish_control_kernel<<<1, 32, 0, e->stream>>>(e->d);
+    e->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int
+sstb200_engine_ingest(sstb200_engine* e)
+{
+    if ( !e || !e->is_setup ) return -1;
+    CUDA_OK(cudaSetDevice(e->device));
+    if ( e->n_ranks > 1 ) {
+        ingest_kernel<<<64, BLOCK, 0, e->stream>>>(e->d);
+        e->launches++;
+        CUDA_OK(cudaGetLastError());
+        publish_control_kernel<<<1, 32, 0, e->stream>>>(e->d);
+        e->launches++;
+        CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+
+int
+sstb200_engine_advance(sstb200_engine* e)
+{
+    if ( !e || !e->is_setup ) return -1;
+    CUDA_OK(cudaSetDevice(e->device));
+    return e->launch_advance();
+}
+
+int
+sstb200_engine_exchange_buffers(sstb200_engine* e, void** outbox_dev, void** inbox_dev, uint64_t* words_per_rank)
+{
+    if ( !e ) return -1;
+    if ( outbox_dev ) *outbox_dev = e->d.outbox;
+    if ( inbox_dev ) *inbox_dev = e->d.inbox;
+    if ( words_per_rank ) *words_per_rank = e->d.xwords;
+    return 0;
+}
+
+int
+sstb200_engine_control_words(sstb200_engine* e, void** local_dev, void** global_dev)
+{
+    if ( !e ) return -1;
+    if ( local_dev ) *local_dev = (void*)&e->d.ctrl->local[0];
+    if ( global_dev ) *global_dev = (void*)e->d.gathered;
+    return 0;
+}
+
+int
+sstb200_engine_status(sstb200_engine* e, sstb200_status* s)
+{
+    if ( !e || !s ) return -1;
+    CUDA_OK(cudaSetDevice(e->device));
+    if ( int rc = e->fetch_ctrl() ) return rc;
+    const Ctrl& c       = *e->h_ctrl;
+    s->now              = c.T;
+    s->end_time         = c.end_time;
+    s->windows          = c.windows;
+    s->events_delivered = c.events_delivered;
+    s->clock_ticks      = c.clock_ticks;
+    s->events_sent      = c.events_sent;
+    s->max_bin_fill     = c.max_bin_fill;
+    s->max_due          = c.max_due;
+    s->finished         = c.done;
+    s->error            = c.error;
+    for ( int i = 0; i < 4; ++i )
+        s->error_info[i] = c.error_info[i];
+    s->launches = e->launches;
+    return 0;
+}
+
+int
+sstb200_engine_results(sstb200_engine* e, uint64_t* results)
+{
+    if ( !e || !results ) return -1;
+    CUDA_OK(cudaSetDevice(e->device));
+    results_kernel<<<e->d.nbins, BLOCK, 0, e->stream>>>(e->d, e->d_results);
+    e->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(results, e->d_results, (size_t)e->d.n_local * NRESULT * 8, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int
+sstb200_engine_trace(sstb200_engine* e, uint64_t* n_inout, uint64_t* time, uint32_t* comp, uint32_t* port,
+    uint64_t* payload)
+{
+    if ( !e || !n_inout ) return -1;
+    CUDA_OK(cudaSetDevice(e->device));
+    if ( int rc = e->fetch_ctrl() ) return rc;
+    uint64_t n = e->h_ctrl->trace_n;
+    if ( n > e->d.trace_cap ) {
+        set_error("trace overflow: " + std::to_string(n) + " deliveries, capacity " + std::to_string(e->d.trace_cap));
+        return -4;
+    }
+    if ( !time ) {
+        *n_inout = n;
+        return 0;
+    }
+    if ( *n_inout < n ) {
+        set_error("trace buffer too small");
+        return -1;
+    }
+    std::vector<uint64_t> t(n), pl(n);
+    std::vector<uint32_t> c(n), p(n), ix(n);
+    if ( n ) {
+        CUDA_OK(cudaMemcpy(t.data(), e->d.tr_time, n * 8, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(pl.data(), e->d.tr_payload, n * 8, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(c.data(), e->d.tr_comp, n * 4, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(p.data(), e->d.tr_port, n * 4, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(ix.data(), e->d.tr_idx, n * 4, cudaMemcpyDeviceToHost));
+    }
+    std::vector<uint64_t> order(n);
+    for ( uint64_t i = 0; i < n; ++i )
+        order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) {
+        if ( c[a] != c[b] ) return c[a] < c[b];
+        return ix[a] < ix[b];
+    });
+    for ( uint64_t i = 0; i < n; ++i ) {
+        time[i]    = t[order[i]];
+        comp[i]    = c[order[i]];
+        port[i]    = p[order[i]];
+        payload[i] = pl[order[i]];
+    }
+    *n_inout = n;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ RNG entry points
+int
+sstb200_rng_streams(int device, void* stream, int kind, uint64_t s1, uint64_t s2, uint64_t stride1, uint64_t stride2,
+    uint64_t n_streams, uint64_t draws, void* out_dev, void* checksum_dev)
+{
+    int ndev = 0;
+    if ( cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 ) {
+        set_error("rng_streams: no CUDA device available (no CPU fallback)");
+        return -3;
+    }
+    if ( kind < 0 || kind > 2 || !checksum_dev || n_streams == 0 ) {
+        set_error("rng_streams: bad arguments");
+        return -1;
+    }
+    CUDA_OK(cudaSetDevice(device));
+    uint32_t* mt = nullptr;
+    if ( kind == 0 ) CUDA_OK(cudaMallocAsync((void**)&mt, n_streams * MT_N * 4, (cudaStream_t)stream));
+    const uint32_t threads = 128;
+    const uint64_t blocks  = (n_streams + threads - 1) / threads;
+    rng_stream_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(kind, s1, s2, stride1, stride2, n_streams,
+        draws, (uint32_t*)out_dev, (unsigned long long*)checksum_dev, mt);
+    CUDA_OK(cudaGetLastError());
+    if ( mt ) CUDA_OK(cudaFreeAsync(mt, (cudaStream_t)stream));
+    return 0;
+}
+
+int
+sstb200_rng_ticks(int device, int kind, uint64_t s1, uint64_t s2, uint64_t first, uint64_t n, uint64_t* out_host)
+{
+    int ndev = 0;
+    if ( cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 ) {
+        set_error("rng_ticks: no CUDA device available (no CPU fallback)");
+        return -3;
+    }
+    CUDA_OK(cudaSetDevice(device));
+    uint64_t* out = nullptr;
+    uint32_t* mt  = nullptr;
+    CUDA_OK(cudaMalloc((void**)&out, std::max<uint64_t>(n, 1) * 5 * 8));
+    CUDA_OK(cudaMalloc((void**)&mt, MT_N * 4));
+    rng_ticks_kernel<<<1, 32>>>(kind, s1, s2, first, n, out, mt);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpy(out_host, out, n * 5 * 8, cudaMemcpyDeviceToHost));
+    cudaFree(out);
+    cudaFree(mt);
+    return 0;
+}
+
+int
+sstb200_rng_distribution(int device, int dist, const double* params, int n_params, int rng_kind, uint64_t s1,
+    uint64_t s2, uint64_t n, double* out_host)
+{
+    int ndev = 0;
+    if ( cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 ) {
+        set_error("rng_distribution: no CUDA device available (no CPU fallback)");
+        return -3;
+    }
+    if ( dist < 0 || dist > 5 || n_params < 1 || !params ) {
+        set_error("rng_distribution: bad arguments");
+        return -1;
+    }
+    CUDA_OK(cudaSetDevice(device));
+    // host-side preparation mirrors the reference constructors: discrete.h:40-55 exclusive prefix sums;
+    // poisson L = exp(-lambda) (poisson.h:75) computed with the host libm so the device does no transcendental.
+    std::vector<double> hp(params, params + n_params);
+    if ( dist == 0 ) {
+        double sum = 0;
+        for ( int i = 0; i < n_params; ++i ) {
+            hp[i] = sum;
+            sum += params[i];
+        }
+    }
+    if ( dist == 3 ) {
+        hp.resize(2);
+        hp[1] = exp(-params[0]);
+    }
+    double*   dp  = nullptr;
+    double*   out = nullptr;
+    uint32_t* mt  = nullptr;
+    CUDA_OK(cudaMalloc((void**)&dp, hp.size() * 8));
+    CUDA_OK(cudaMalloc((void**)&out, std::max<uint64_t>(n, 1) * 8));
+    CUDA_OK(cudaMalloc((void**)&mt, MT_N * 4));
+    CUDA_OK(cudaMemcpy(dp, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice));
+    rng_dist_kernel<<<1, 32>>>(dist, dp, (int)hp.size(), rng_kind, s1, s2, n, out, mt);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpy(out_host, out, n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(dp);
+    cudaFree(out);
+    cudaFree(mt);
+    return 0;
+}
+
+} // extern "C"

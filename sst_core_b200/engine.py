@@ -1,0 +1,386 @@
+"""Host driver of the CUDA engine through the C ABI (include/sstb200.h).
+
+`Engine` is what replaces ``Simulation::run`` (simulation.cc:1072-1193) for a wired model.  One process drives one
+GPU.  With ``torch.distributed`` initialised and world_size > 1 the same class steps a partition of the model and
+exchanges boundary events over NCCL once per lookahead window (SyncManager::execute, sync/syncManager.cc:547-732).
+
+There is NO CPU fallback: if libsstb200.so is missing this module raises at import; if no CUDA device is visible,
+engine creation fails with the library's error text.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Optional
+
+import numpy as np
+
+from .elements import NRESULT, TYPE_NAMES
+from .wireup import WiredModel
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libsstb200.so"
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class _Model(C.Structure):
+    _fields_ = [("ncomp", C.c_uint32), ("comp_type", C.c_void_p), ("comp_param", C.c_void_p),
+                ("port_off", C.c_void_p), ("peer_port", C.c_void_p), ("latency", C.c_void_p),
+                ("clock_period", C.c_void_p), ("stop_at", C.c_uint64), ("stats_enabled", C.c_int)]
+
+
+class _Options(C.Structure):
+    _fields_ = [("device", C.c_int), ("rank", C.c_uint32), ("n_ranks", C.c_uint32), ("comp_begin", C.c_uint32),
+                ("comp_end", C.c_uint32), ("rank_comp_begin", C.c_void_p), ("calendar_slots", C.c_uint32),
+                ("bin_capacity", C.c_uint32), ("smem_events", C.c_uint32), ("outbox_capacity", C.c_uint32),
+                ("window", C.c_uint64), ("trace_capacity", C.c_uint64), ("stream", C.c_void_p)]
+
+
+class _Status(C.Structure):
+    _fields_ = [("now", C.c_uint64), ("end_time", C.c_uint64), ("windows", C.c_uint64),
+                ("events_delivered", C.c_uint64), ("clock_ticks", C.c_uint64), ("events_sent", C.c_uint64),
+                ("max_bin_fill", C.c_uint64), ("max_due", C.c_uint64), ("finished", C.c_uint32),
+                ("error", C.c_uint32), ("error_info", C.c_uint64 * 4), ("launches", C.c_uint64)]
+
+
+EXPORTS = [
+    "sstb200_abi_version", "sstb200_last_error", "sstb200_num_component_types", "sstb200_component_type_info",
+    "sstb200_component_type_lookup", "sstb200_partition_linear", "sstb200_engine_create", "sstb200_engine_destroy",
+    "sstb200_engine_setup", "sstb200_engine_run", "sstb200_engine_dispatch", "sstb200_engine_ingest",
+    "sstb200_engine_advance", "sstb200_engine_exchange_buffers", "sstb200_engine_control_words",
+    "sstb200_engine_status", "sstb200_engine_results", "sstb200_engine_trace", "sstb200_rng_streams",
+    "sstb200_rng_ticks", "sstb200_rng_distribution",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libsstb200.so; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise EngineError(f"{LIB_PATH} is missing: build it with `python -m sst_core_b200.build` "
+                          f"(the CUDA engine is the only execution path)")
+    L = C.CDLL(str(LIB_PATH))
+    L.sstb200_last_error.restype = C.c_char_p
+    L.sstb200_component_type_info.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint32),
+                                              C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
+    L.sstb200_component_type_lookup.argtypes = [C.c_char_p]
+    L.sstb200_partition_linear.argtypes = [C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.sstb200_engine_create.argtypes = [C.POINTER(_Model), C.POINTER(_Options), C.POINTER(C.c_void_p)]
+    L.sstb200_engine_destroy.argtypes = [C.c_void_p]
+    L.sstb200_engine_destroy.restype = None
+    L.sstb200_engine_setup.argtypes = [C.c_void_p]
+    L.sstb200_engine_run.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_int)]
+    for f in ("dispatch", "ingest", "advance"):
+        getattr(L, f"sstb200_engine_{f}").argtypes = [C.c_void_p]
+    L.sstb200_engine_exchange_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                                  C.POINTER(C.c_uint64)]
+    L.sstb200_engine_control_words.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.sstb200_engine_status.argtypes = [C.c_void_p, C.POINTER(_Status)]
+    L.sstb200_engine_results.argtypes = [C.c_void_p, C.c_void_p]
+    L.sstb200_engine_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]
+    L.sstb200_rng_streams.argtypes = [C.c_int, C.c_void_p, C.c_int] + [C.c_uint64] * 6 + [C.c_void_p, C.c_void_p]
+    L.sstb200_rng_ticks.argtypes = [C.c_int, C.c_int] + [C.c_uint64] * 4 + [C.c_void_p]
+    L.sstb200_rng_distribution.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
+                                           C.c_uint64, C.c_void_p]
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    return lib().sstb200_last_error().decode()
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise EngineError(f"{what} failed ({rc}): {last_error()}")
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def component_types():
+    """The native ELI table: [(eli name, type code, state bytes, aux bytes, has payload)]."""
+    L = lib()
+    out = []
+    for i in range(L.sstb200_num_component_types()):
+        name, code, sb, ab, hp = C.c_char_p(), C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_int()
+        _check(L.sstb200_component_type_info(i, C.byref(name), C.byref(code), C.byref(sb), C.byref(ab),
+                                             C.byref(hp)), "component_type_info")
+        out.append((name.value.decode(), code.value, sb.value, ab.value, bool(hp.value)))
+    return out
+
+
+def check_registry():
+    """The Python element descriptors and the native type table must agree (names and codes)."""
+    native = {code: name for name, code, *_ in component_types()}
+    if native != TYPE_NAMES:
+        raise EngineError(f"element registry mismatch: native {native} vs host {TYPE_NAMES}")
+
+
+def partition_linear(ncomp: int, nocut_pairs: Optional[np.ndarray], n_parts: int) -> np.ndarray:
+    """sst.linear over no-cut groups (linpart.cc:30-82, configGraph.cc:764-850) -- native host C++."""
+    pairs = np.ascontiguousarray(nocut_pairs if nocut_pairs is not None else np.zeros((0, 2)), dtype=np.uint32)
+    out = np.zeros(ncomp, dtype=np.uint32)
+    _check(lib().sstb200_partition_linear(ncomp, _p(pairs), pairs.shape[0], n_parts, _p(out)), "partition_linear")
+    return out
+
+
+def partition_model(m: WiredModel, n_ranks: int) -> WiredModel:
+    """Assign ranks with the linear partitioner and renumber components so that every rank owns one contiguous id
+    range (the engine's layout); per-component port order -- hence delivery order -- is unchanged."""
+    rank = partition_linear(m.ncomp, m.nocut_pairs, n_ranks)
+    order = np.argsort(rank, kind="stable")  # new id -> old id
+    if np.array_equal(order, np.arange(m.ncomp)):
+        m.rank, m.n_ranks = rank, n_ranks
+        m.orig_id = np.arange(m.ncomp, dtype=np.uint32)
+        return m
+    nports = np.diff(m.port_off.astype(np.int64))
+    new_nports = nports[order]
+    new_port_off = np.zeros(m.ncomp + 1, dtype=np.int64)
+    np.cumsum(new_nports, out=new_port_off[1:])
+    # old directed port id -> new id
+    old_first = m.port_off.astype(np.int64)[order]
+    port_map = np.empty(m.nport, dtype=np.int64)
+    idx_new = np.arange(m.nport, dtype=np.int64)
+    comp_of_new = np.repeat(np.arange(m.ncomp), new_nports)
+    old_ids = old_first[comp_of_new] + (idx_new - new_port_off[comp_of_new])
+    port_map[old_ids] = idx_new
+    peer_old = m.peer_port[old_ids]
+    conn = peer_old != 0xFFFFFFFF
+    new_peer = np.full(m.nport, 0xFFFFFFFF, dtype=np.uint32)
+    new_peer[conn] = port_map[peer_old[conn].astype(np.int64)].astype(np.uint32)
+    out = WiredModel(
+        comp_type=np.ascontiguousarray(m.comp_type[order]), comp_param=np.ascontiguousarray(m.comp_param[order]),
+        port_off=new_port_off.astype(np.uint32), peer_port=new_peer, latency=np.ascontiguousarray(m.latency[old_ids]),
+        clock_period=np.ascontiguousarray(m.clock_period[order]), stop_at=m.stop_at, timebase=m.timebase,
+        stats_enabled=m.stats_enabled, rank=rank[order], n_ranks=n_ranks, orig_id=order.astype(np.uint32),
+        names=[m.names[i] for i in order] if m.names else None,
+        stats=[m.stats[i] for i in order] if m.stats else None,
+        finish=[m.finish[i] for i in order] if m.finish else None, nocut_pairs=None, stat_output=m.stat_output)
+    out.validate()
+    return out
+
+
+@dataclass
+class Status:
+    now: int
+    end_time: int
+    windows: int
+    events_delivered: int
+    clock_ticks: int
+    events_sent: int
+    max_bin_fill: int
+    max_due: int
+    finished: bool
+    error: int
+    error_info: tuple
+    launches: int
+
+
+_ERRORS = {
+    1: "calendar bin overflow (raise bin_capacity or calendar_slots): slot {0}, block {1}, fill {2}",
+    2: "shared-memory staging overflow (raise smem_events): block {0} had {1} due events, capacity {2}",
+    3: "time fault: event for time {0} while the window starts at {1} (component {2}); a send violated the lookahead",
+    4: "outbox overflow (raise outbox_capacity): to rank {0}, fill {1}, capacity {2}",
+    5: "trace overflow",
+    0x80000000: "another rank reported an error",
+}
+
+
+class Engine:
+    """One rank's engine.  ``Engine(model).run()`` for a single GPU; see :func:`run_distributed` for N GPUs."""
+
+    def __init__(self, model: WiredModel, device: int = 0, rank: int = 0, n_ranks: int = 1, calendar_slots: int = 2,
+                 bin_capacity: int = 0, smem_events: int = 0, outbox_capacity: int = 0, window: int = 0,
+                 trace_capacity: int = 0, stream: int = 0):
+        L = lib()
+        check_registry()
+        self.model = model
+        self.rank, self.n_ranks = rank, n_ranks
+        self._keep = [np.ascontiguousarray(a) for a in (model.comp_type, model.comp_param, model.port_off,
+                                                        model.peer_port, model.latency, model.clock_period)]
+        cm = _Model(model.ncomp, *[_p(a) for a in self._keep], int(model.stop_at), int(bool(model.stats_enabled)))
+        if n_ranks > 1:
+            if model.rank is None or model.n_ranks != n_ranks:
+                raise EngineError("multi-rank engine needs a model prepared by partition_model(model, n_ranks)")
+            counts = np.bincount(model.rank, minlength=n_ranks)
+            begins = np.zeros(n_ranks + 1, dtype=np.uint32)
+            begins[1:] = np.cumsum(counts)
+            self._begins = begins
+            c0, c1 = int(begins[rank]), int(begins[rank + 1])
+        else:
+            self._begins = np.array([0, model.ncomp], dtype=np.uint32)
+            c0, c1 = 0, model.ncomp
+        self.comp_begin, self.comp_end = c0, c1
+        opt = _Options(device, rank, n_ranks, c0, c1, _p(self._begins), calendar_slots, bin_capacity, smem_events,
+                       outbox_capacity, window, trace_capacity, stream)
+        h = C.c_void_p()
+        _check(L.sstb200_engine_create(C.byref(cm), C.byref(opt), C.byref(h)), "engine_create")
+        self._h = h
+        self._L = L
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sstb200_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setup(self):
+        _check(self._L.sstb200_engine_setup(self._h), "engine_setup")
+
+    def status(self) -> Status:
+        s = _Status()
+        _check(self._L.sstb200_engine_status(self._h, C.byref(s)), "engine_status")
+        return Status(s.now, s.end_time, s.windows, s.events_delivered, s.clock_ticks, s.events_sent,
+                      s.max_bin_fill, s.max_due, bool(s.finished), s.error, tuple(s.error_info), s.launches)
+
+    def raise_on_error(self, st: Optional[Status] = None):
+        st = st or self.status()
+        if st.error:
+            msg = _ERRORS.get(st.error, f"error code {st.error}").format(*st.error_info)
+            raise EngineError(f"engine error at window {st.error_info[3]}: {msg}")
+
+    def run(self, max_windows: int = 0, check_every: int = 64) -> bool:
+        """Run to the end (or for max_windows lookahead windows).  Returns True when the simulation has ended."""
+        fin = C.c_int(0)
+        rc = self._L.sstb200_engine_run(self._h, max_windows, check_every, C.byref(fin))
+        if rc == -4:
+            self.raise_on_error()
+        _check(rc, "engine_run")
+        return bool(fin.value)
+
+    def dispatch(self):
+        _check(self._L.sstb200_engine_dispatch(self._h), "engine_dispatch")
+
+    def ingest(self):
+        _check(self._L.sstb200_engine_ingest(self._h), "engine_ingest")
+
+    def advance(self):
+        _check(self._L.sstb200_engine_advance(self._h), "engine_advance")
+
+    def exchange_buffers(self):
+        ob, ib, w = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        _check(self._L.sstb200_engine_exchange_buffers(self._h, C.byref(ob), C.byref(ib), C.byref(w)), "exchange")
+        return ob.value, ib.value, w.value
+
+    def control_words(self):
+        a, b = C.c_void_p(), C.c_void_p()
+        _check(self._L.sstb200_engine_control_words(self._h, C.byref(a), C.byref(b)), "control_words")
+        return a.value, b.value
+
+    def results(self) -> np.ndarray:
+        out = np.zeros((self.comp_end - self.comp_begin, NRESULT), dtype=np.uint64)
+        _check(self._L.sstb200_engine_results(self._h, _p(out)), "engine_results")
+        return out
+
+    def trace(self):
+        n = C.c_uint64(0)
+        _check(self._L.sstb200_engine_trace(self._h, C.byref(n), None, None, None, None), "engine_trace")
+        k = n.value
+        t = dict(time=np.zeros(k, np.uint64), comp=np.zeros(k, np.uint32), port=np.zeros(k, np.uint32),
+                 payload=np.zeros(k, np.uint64))
+        n = C.c_uint64(k)
+        _check(self._L.sstb200_engine_trace(self._h, C.byref(n), _p(t["time"]), _p(t["comp"]), _p(t["port"]),
+                                            _p(t["payload"])), "engine_trace")
+        return t
+
+
+# ------------------------------------------------------------------------------------------------ multi-GPU stepping
+class DistributedRunner:
+    """One lookahead window per step across all ranks: dispatch -> all-to-all of the outboxes over NVLink (NCCL) ->
+    ingest -> all-gather of the control words -> advance.  Replaces SyncManager::execute +
+    RankSyncSerialSkip::exchange (+ its MPI_Allreduce calls, rankSyncSerialSkip.cc:318-335)."""
+
+    def __init__(self, engine: Engine):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.e = torch, dist, engine
+        ob, ib, words = engine.exchange_buffers()
+        n = engine.n_ranks
+        dev = torch.device("cuda", engine.device)
+        self.outbox = _as_tensor(torch, ob, n * words, dev).view(n, words)
+        self.inbox = _as_tensor(torch, ib, n * words, dev).view(n, words)
+        lw, gw = engine.control_words()
+        self.local = _as_tensor(torch, lw, 8, dev)
+        self.gathered = _as_tensor(torch, gw, 8 * n, dev)
+
+    def step(self):
+        e = self.e
+        e.dispatch()
+        self.dist.all_to_all_single(self.inbox, self.outbox)
+        e.ingest()
+        self.dist.all_gather_into_tensor(self.gathered, self.local)
+        e.advance()
+
+    def run(self, max_windows: int = 0, check_every: int = 32) -> bool:
+        done_windows = 0
+        while True:
+            chunk = check_every if not max_windows else min(check_every, max_windows - done_windows)
+            for _ in range(chunk):
+                self.step()
+            done_windows += chunk
+            st = self.e.status()
+            self.e.raise_on_error(st)
+            if st.finished:
+                return True
+            if max_windows and done_windows >= max_windows:
+                return False
+
+
+def _as_tensor(torch, ptr: int, n_words: int, device):
+    """Zero-copy int64 view of engine-owned device memory (``__cuda_array_interface__``)."""
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+    return torch.as_tensor(h, device=device)
+
+
+# ------------------------------------------------------------------------------------------------ RNG streams
+def rng_streams(kind: int, s1: int, s2: int, n_streams: int, draws: int, stride1: int = 0, stride2: int = 0,
+                want_output: bool = True, device: int = 0):
+    """SST::RNG streams on the device (BASELINE config 2).  Returns (draws [n_streams, draws] u32 or None,
+    checksums [n_streams] u64) as numpy arrays."""
+    import torch
+
+    dev = torch.device("cuda", device)
+    out = torch.empty((n_streams, draws), dtype=torch.int32, device=dev) if want_output else None
+    cs = torch.zeros(n_streams, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _check(lib().sstb200_rng_streams(device, stream, kind, s1, s2, stride1, stride2, n_streams, draws,
+                                     out.data_ptr() if want_output else None, cs.data_ptr()), "rng_streams")
+    torch.cuda.synchronize(dev)
+    o = out.cpu().numpy().view(np.uint32) if want_output else None
+    return o, cs.cpu().numpy().view(np.uint64)
+
+
+def rng_ticks(kind: int, s1: int, s2: int, first: int, n: int, device: int = 0) -> np.ndarray:
+    out = np.zeros((n, 5), dtype=np.uint64)
+    _check(lib().sstb200_rng_ticks(device, kind, s1, s2, first, n, _p(out)), "rng_ticks")
+    return out
+
+
+def rng_distribution(dist: int, params, rng_kind: int, s1: int, s2: int, n: int, device: int = 0) -> np.ndarray:
+    p = np.ascontiguousarray(params, dtype=np.float64)
+    out = np.zeros(n, dtype=np.float64)
+    _check(lib().sstb200_rng_distribution(device, dist, _p(p), len(p), rng_kind, s1, s2, n, _p(out)), "rng_dist")
+    return out

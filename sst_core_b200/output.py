@@ -1,0 +1,62 @@
+"""finish() console lines and end-of-simulation statistic output.
+
+Formats follow the reference so its testsuites' sorted-diff comparison can be pointed at this engine:
+* per-component finish() lines come from the element descriptors (e.g. ``"%d received %d messages"``,
+  enclosingComponent.cc:84-89), then ``Simulation is complete, simulated time: <best SI>`` (main.cc);
+* ``StatisticOutput.csv`` rows (statapi/statoutputcsv.cc, statengine.cc:476-548): header
+  ``ComponentName, StatisticName, StatisticSubId, StatisticType, SimTime, Rank, Sum.<t>, SumSQ.<t>, Count.u64,
+  Min.<t>, Max.<t>``; one row per registered statistic, components in id order, statistics in registration order.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import numpy as np
+
+from .timelord import TimeLord
+from .wireup import WiredModel
+
+
+def _signed(v: int, bits: int) -> int:
+    v &= (1 << bits) - 1
+    return v - (1 << bits) if v >> (bits - 1) else v
+
+
+def finish_lines(m: WiredModel, results: np.ndarray, end_time: int) -> List[str]:
+    """results are indexed by engine id; lines are returned in ConfigGraph id order."""
+    order = np.argsort(m.orig_id) if m.orig_id is not None else np.arange(m.ncomp)
+    lines = []
+    if m.finish:
+        for i in order:
+            fn = m.finish[i]
+            if fn is not None:
+                s = fn([int(x) for x in results[i]])
+                if s is not None:
+                    lines.append(s)
+    lines.append(f"Simulation is complete, simulated time: {TimeLord(m.timebase).best_si(end_time)}")
+    return lines
+
+
+def stat_rows_csv(m: WiredModel, results: np.ndarray, end_time: int, rank_of=None) -> List[str]:
+    if not m.stats_enabled or not m.stats:
+        return []
+    order = np.argsort(m.orig_id) if m.orig_id is not None else np.arange(m.ncomp)
+    dtypes = {s.dtype for sl in m.stats for s in sl}
+    t = "u64" if dtypes <= {"u64"} else "i32" if dtypes <= {"i32"} else None
+    if t is None:
+        raise NotImplementedError("mixed statistic field types in one CSV are out of scope (statoutputcsv.cc)")
+    rows = [f"ComponentName, StatisticName, StatisticSubId, StatisticType, SimTime, Rank, "
+            f"Sum.{t}, SumSQ.{t}, Count.u64, Min.{t}, Max.{t}"]
+    for i in order:
+        rk = int(m.rank[i]) if m.rank is not None else 0
+        for s in m.stats[i]:
+            if s.offset is None:
+                vals = [0, 0, 0, 0, 0]
+            else:
+                vals = [int(x) for x in results[i, s.offset:s.offset + 5]]
+                if s.dtype == "i32":
+                    vals = [_signed(vals[0], 32), _signed(vals[1], 32), vals[2], _signed(vals[3], 32),
+                            _signed(vals[4], 32)]
+            rows.append(f"{s.owner_name}, {s.name}, {s.subid}, Accumulator, {end_time}, {rk}, "
+                        f"{vals[0]}, {vals[1]}, {vals[2]}, {vals[3]}, {vals[4]}")
+    return rows

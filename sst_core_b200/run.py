@@ -1,0 +1,99 @@
+"""`sst`-like front end: python -m sst_core_b200 [options] model.py
+
+Mirrors the reference command line for the options the hot path needs (config.cc:412-504): --model-options,
+--stop-at, --num-threads/-n (accepted; partitions are GPUs here), --partitioner (only sst.linear), --timebase,
+--lib-path (accepted, ignored: device elements are compiled into libsstb200.so), --output-directory.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+from typing import Optional
+
+import numpy as np
+
+from . import config, output, wireup
+
+
+def simulate_model(m: wireup.WiredModel, device: int = 0, **engine_opts):
+    """Run a WiredModel on one GPU.  Returns (results [ncomp,32] u64, Status)."""
+    from .engine import Engine
+
+    e = Engine(m, device=device, **engine_opts)
+    try:
+        e.setup()
+        e.run()
+        st = e.status()
+        e.raise_on_error(st)
+        return e.results(), st
+    finally:
+        e.close()
+
+
+def simulate_distributed(m: wireup.WiredModel, **engine_opts):
+    """Run a WiredModel partitioned over the ranks of the initialised torch.distributed world (one GPU per rank).
+    Returns (results of THIS rank's components, Status, partitioned model)."""
+    import torch
+    import torch.distributed as dist
+
+    from .engine import DistributedRunner, Engine, partition_model
+
+    n, r = dist.get_world_size(), dist.get_rank()
+    pm = partition_model(m, n)
+    dev = torch.cuda.current_device()
+    stream = torch.cuda.current_stream().cuda_stream
+    e = Engine(pm, device=dev, rank=r, n_ranks=n, stream=stream, **engine_opts)
+    try:
+        e.setup()
+        DistributedRunner(e).run()
+        st = e.status()
+        e.raise_on_error(st)
+        return e.results(), st, pm
+    finally:
+        e.close()
+
+
+def main(argv: Optional[list] = None) -> int:
+    ap = argparse.ArgumentParser(prog="sst_core_b200", description="B200 engine behind SST-core's model surface")
+    ap.add_argument("script")
+    ap.add_argument("--model-options", default="")
+    ap.add_argument("--stop-at", default=None)
+    ap.add_argument("-n", "--num-threads", type=int, default=1)
+    ap.add_argument("--partitioner", default="sst.linear")
+    ap.add_argument("--timebase", default=None)
+    ap.add_argument("--lib-path", default=None)
+    ap.add_argument("--output-directory", default=".")
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--calendar-slots", type=int, default=0)
+    ap.add_argument("--bin-capacity", type=int, default=0)
+    a = ap.parse_args(argv)
+    if a.partitioner not in ("sst.linear", "linear"):
+        print(f"FATAL: partitioner {a.partitioner} is not supported (only sst.linear)", file=sys.stderr)
+        return 1
+    try:
+        g = config.build_graph(a.script, a.model_options)
+        if a.timebase:
+            g.program_options["timebase"] = a.timebase
+        m = wireup.wire(g, stop_at_override=a.stop_at)
+    except config.ModelError as ex:
+        print(f"FATAL: {ex}", file=sys.stderr)
+        return 1
+    opts = {}
+    if a.calendar_slots:
+        opts["calendar_slots"] = a.calendar_slots
+    if a.bin_capacity:
+        opts["bin_capacity"] = a.bin_capacity
+    res, st = simulate_model(m, device=a.device, **opts)
+    for line in output.finish_lines(m, res, st.end_time):
+        print(line)
+    rows = output.stat_rows_csv(m, res, st.end_time)
+    if rows and m.stat_output[0] == "sst.statOutputCSV":
+        path = os.path.join(a.output_directory, m.stat_output[1].get("filepath", "StatisticOutput.csv"))
+        with open(path, "w") as f:
+            f.write("\n".join(rows) + "\n")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,101 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.json from (a) the reference's own golden files under /root/reference/tests/refFiles and
+(b) runs of the UNMODIFIED reference core built by oracle/build_ref.py (oracle/_ref/libexec/sstsim.x), including our
+out-of-tree probe elements (oracle/probe).  Run in the build container (the GPU box has no /root/reference):
+
+    python oracle/build_ref.py && python tests/golden/make_golden.py
+"""
+import json
+import re
+import sys
+import tempfile
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, str(ROOT / "tests"))
+import oracle_lib as O  # noqa: E402
+
+REF_TESTS = Path("/root/reference/tests")
+MODELS = ROOT / "tests" / "models"
+
+
+def mesh_counts(text):
+    return {int(m.group(1)): int(m.group(2)) for m in re.finditer(r"^(\d+) received (-?\d+) messages", text, re.M)}
+
+
+def main():
+    out = {}
+    # (a) reference golden vectors -------------------------------------------------------------------------------
+    out["mesh_6x6_10us"] = {"source": "tests/refFiles/test_MessageMesh.out",
+                            "counts": mesh_counts((REF_TESTS / "refFiles/test_MessageMesh.out").read_text())}
+    for g in ("mersenne", "marsaglia", "xorshift"):
+        lines = (REF_TESTS / f"refFiles/test_RNGComponent_{g}.out").read_text().strip().splitlines()
+        out[f"rng_{g}_last5"] = {"source": f"tests/refFiles/test_RNGComponent_{g}.out", "lines": lines[-5:]}
+    prof = (REF_TESTS / "refFiles/test_Profiling_event_global.out").read_text()
+    out["profiling_4x4_recv_count"] = {"source": "tests/refFiles/test_Profiling_event_global.out",
+                                       "recv_count": int(re.search(r"recv_count\D+(\d+)", prof).group(1))}
+    disc = (REF_TESTS / "refFiles/test_DistribComponent_discrete.out").read_text()
+    out["distrib_discrete"] = {"source": "tests/refFiles/test_DistribComponent_discrete.out (unwired by the "
+                                         "reference's testsuites, SURVEY.md section 4)", "text": disc.strip().splitlines()}
+    # (b) reference binary runs ----------------------------------------------------------------------------------
+    if not O.have_ref():
+        raise SystemExit("oracle/_ref is not built; run python oracle/build_ref.py")
+    txt = O.run_ref(REF_TESTS / "test_MessageMesh.py", "4 4")
+    out["mesh_4x4_10us"] = {"source": "sstsim.x tests/test_MessageMesh.py '4 4'", "counts": mesh_counts(txt)}
+    txt = O.run_ref(REF_TESTS / "test_MessageMesh.py", "5 3 3", extra=["--stop-at", "500ns"])
+    out["mesh_5x3_mod3_500ns"] = {"source": "sstsim.x test_MessageMesh.py '5 3 3' --stop-at 500ns",
+                                  "counts": mesh_counts(txt)}
+    txt = O.run_ref(REF_TESTS / "test_MessageMesh.py", "1 2", extra=["--stop-at", "300ns"])
+    out["mesh_1x2_300ns"] = {"source": "sstsim.x test_MessageMesh.py '1 2' --stop-at 300ns (x links are loops "
+                                       "between two ports of the same component)", "counts": mesh_counts(txt)}
+    txt = O.run_ref(REF_TESTS / "test_MessageMesh.py", "2 2", extra=["--stop-at", "300ns"])
+    out["mesh_2x2_300ns"] = {"source": "sstsim.x test_MessageMesh.py '2 2' --stop-at 300ns",
+                             "counts": mesh_counts(txt)}
+    txt = O.run_ref(REF_TESTS / "test_MessageMesh.py", "16 16", extra=["--stop-at", "200ns"], threads=4)
+    out["mesh_16x16_200ns_n4"] = {"source": "sstsim.x -n 4 test_MessageMesh.py '16 16' --stop-at 200ns",
+                                  "counts": mesh_counts(txt)}
+    txt = O.run_ref(MODELS / "phold.py", "8 8 200ns")
+    out["phold_8x8_200ns"] = {
+        "source": "sstsim.x tests/models/phold.py '8 8 200ns' (pdes.phold probe element)",
+        "nodes": {int(m.group(1)): [int(m.group(2)), m.group(3)]
+                  for m in re.finditer(r"^phold (\d+) recv (\d+) hash ([0-9a-f]+)", txt, re.M)}}
+    txt = O.run_ref(MODELS / "phold.py", "5 4 300ns 7 3000", threads=2)
+    out["phold_5x4_300ns_n2"] = {
+        "source": "sstsim.x -n 2 tests/models/phold.py '5 4 300ns 7 3000'",
+        "nodes": {int(m.group(1)): [int(m.group(2)), m.group(3)]
+                  for m in re.finditer(r"^phold (\d+) recv (\d+) hash ([0-9a-f]+)", txt, re.M)}}
+    txt = O.run_ref(MODELS / "clockpop.py", "6 5 2us 10")
+    out["clockpop_6x5_2us_f10"] = {
+        "source": "sstsim.x tests/models/clockpop.py '6 5 2us 10' (pdes.clocknode probe element)",
+        "nodes": {int(m.group(1)): [int(m.group(2)), int(m.group(3)), int(m.group(4)), m.group(5)]
+                  for m in re.finditer(r"^clocknode (\d+) ticks (\d+) last_cycle (\d+) recv (\d+) hash ([0-9a-f]+)",
+                                       txt, re.M)}}
+    with tempfile.TemporaryDirectory() as td:
+        O.run_ref(MODELS / "phold.py", "3 3 100ns 16 8000 1 1", cwd=td)
+        out["phold_3x3_100ns_csv"] = {"source": "sstsim.x phold.py '3 3 100ns 16 8000 1 1' StatisticOutput.csv",
+                                      "rows": (Path(td) / "StatisticOutput.csv").read_text().strip().splitlines()}
+        O.run_ref(REF_TESTS / "test_MessageMesh.py", "3 3 1 1 2 1", extra=["--stop-at", "100ns"], cwd=td)
+        out["mesh_3x3_100ns_csv"] = {"source": "sstsim.x test_MessageMesh.py '3 3 1 1 2 1' --stop-at 100ns",
+                                     "rows": (Path(td) / "StatisticOutput.csv").read_text().strip().splitlines()}
+        O.run_ref(MODELS / "clockpop.py", "3 3 1us 10 1 1", cwd=td)
+        out["clockpop_3x3_1us_csv"] = {"source": "sstsim.x clockpop.py '3 3 1us 10 1 1' StatisticOutput.csv",
+                                       "rows": (Path(td) / "StatisticOutput.csv").read_text().strip().splitlines()}
+        # per-component delivery order (time, port) captured with the pdes.trace profile tool
+        tr = Path(td) / "tr.txt"
+        O.run_ref(MODELS / "phold.py", "3 2 40ns 4 3000 0",
+                  extra=[f"--enable-profiling=tr:pdes.trace(level=component,track_ports=true,file={tr})[event]"])
+        seq = {}
+        for line in tr.read_text().splitlines():
+            t, prio, tag, q, key = line.split()
+            comp, port = key.split(":")
+            seq.setdefault(comp, []).append([int(t), int(port.replace("port", ""))])
+        out["phold_3x2_40ns_trace"] = {
+            "source": "sstsim.x phold.py '3 2 40ns 4 3000 0' + pdes.trace: per-component [time, port] sequences",
+            "seq": seq}
+    (HERE / "reference_golden.json").write_text(json.dumps(out, indent=1, sort_keys=True))
+    print("wrote", HERE / "reference_golden.json", (HERE / "reference_golden.json").stat().st_size, "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,178 @@
+"""Parity of the CUDA engine (through the C ABI) with the oracle, the reference's golden vectors and the fixtures
+generated from the reference core.  Bit-exact: every result word, event counts, end time, per-component order."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from sst_core_b200 import config, models, output, wireup
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = json.loads((ROOT / "tests" / "golden" / "reference_golden.json").read_text())
+
+
+def run_gpu(m, **opts):
+    from sst_core_b200.run import simulate_model
+    return simulate_model(m, **opts)
+
+
+def assert_same_as_oracle(m, **opts):
+    res, st = run_gpu(m, **opts)
+    ref = O.run_model(m)
+    bad = np.nonzero((res != ref.results).any(axis=1))[0]
+    assert bad.size == 0, f"{bad.size} components differ, first {bad[:5]}: gpu {res[bad[0]][:8]} oracle {ref.results[bad[0]][:8]}"
+    assert st.events_delivered == ref.events
+    assert st.clock_ticks == ref.ticks
+    assert st.end_time == ref.end_time
+    return res, st, ref
+
+
+def _counts(res):
+    return {str(i): int(np.int32(np.uint32(res[i, 0] & 0xFFFFFFFF))) for i in range(res.shape[0])}
+
+
+# ---- BASELINE config 1: MessageMesh reference check -----------------------------------------------------------------
+def test_mesh_6x6_matches_reference_golden_file():
+    res, st = run_gpu(models.mesh_model(6, 6))
+    assert _counts(res) == GOLD["mesh_6x6_10us"]["counts"]
+    assert st.events_delivered == 36 * 4 * 9999 and st.end_time == 10_000_000 and st.windows == 10_000
+
+
+def test_mesh_4x4_matches_reference_and_profiling_count():
+    res, st = run_gpu(models.mesh_model(4, 4))
+    assert _counts(res) == GOLD["mesh_4x4_10us"]["counts"]
+    assert st.events_delivered == GOLD["profiling_4x4_recv_count"]["recv_count"]
+
+
+@pytest.mark.parametrize("key,args", [
+    ("mesh_5x3_mod3_500ns", dict(x=5, y=3, mod=3, stop_at="500ns")),
+    ("mesh_1x2_300ns", dict(x=1, y=2, stop_at="300ns")),
+    ("mesh_2x2_300ns", dict(x=2, y=2, stop_at="300ns")),
+    ("mesh_16x16_200ns_n4", dict(x=16, y=16, stop_at="200ns")),
+])
+def test_mesh_edge_cases_match_reference_core(key, args):
+    res, _ = run_gpu(models.mesh_model(**args))
+    assert _counts(res) == GOLD[key]["counts"]
+
+
+@pytest.mark.parametrize("x,y,stop", [(64, 64, "100ns"), (256, 100, "30ns"), (37, 19, "77ns"), (300, 1, "50ns")])
+def test_mesh_larger_vs_oracle(x, y, stop):
+    assert_same_as_oracle(models.mesh_model(x, y, stop_at=stop, stats_enabled=True))
+
+
+def test_mesh_stats_disabled_leave_accumulators_empty():
+    res, _ = run_gpu(models.mesh_model(8, 8, stop_at="50ns", stats_enabled=False))
+    assert (res[:, 1:6] == 0).all() and res[:, 0].sum() == 64 * 4 * 49
+
+
+def test_mesh_through_the_sst_script_surface(tmp_path):
+    from test_host import _mesh_script
+    w = wireup.wire(config.build_graph(str(_mesh_script(tmp_path)), "6 6"))
+    res, st = run_gpu(w)
+    lines = output.finish_lines(w, res, st.end_time)
+    want = [f"{i} received {c} messages" for i, c in sorted((int(k), v) for k, v in GOLD["mesh_6x6_10us"]["counts"].items())]
+    assert lines[:-1] == want and lines[-1] == "Simulation is complete, simulated time: 10 us"
+
+
+# ---- BASELINE config 3: PHOLD (event order matters) -----------------------------------------------------------------
+@pytest.mark.parametrize("key,args", [
+    ("phold_8x8_200ns", dict(x=8, y=8, stop_at="200ns")),
+    ("phold_5x4_300ns_n2", dict(x=5, y=4, stop_at="300ns", init_events=7, delay_mod=3000)),
+])
+def test_phold_matches_reference_core(key, args):
+    res, _ = run_gpu(models.phold_model(**args), calendar_slots=16)
+    for i, (recv, h) in GOLD[key]["nodes"].items():
+        assert int(res[int(i), 0]) == recv and int(res[int(i), 1]) == int(h, 16), i
+
+
+@pytest.mark.parametrize("slots", [2, 3, 16])
+def test_phold_any_calendar_depth_same_result(slots):
+    # events beyond the calendar horizon are parked and re-binned: the result must not depend on W
+    assert_same_as_oracle(models.phold_model(24, 24, stop_at="120ns", stats_enabled=True), calendar_slots=slots,
+                          bin_capacity=8192, smem_events=4096)
+
+
+def test_phold_zero_extra_delay_bursts_keep_link_fifo():
+    # delay_mod=1: every event arrives exactly one latency later; many ties on (time, port) -> FIFO by sender order
+    assert_same_as_oracle(models.phold_model(16, 16, stop_at="60ns", delay_mod=1, stats_enabled=True),
+                          bin_capacity=8192, smem_events=6144)
+
+
+def test_phold_large_vs_oracle():
+    assert_same_as_oracle(models.phold_model(128, 128, stop_at="40ns", stats_enabled=True), calendar_slots=16)
+
+
+def test_phold_trace_matches_reference_trace():
+    m = models.phold_model(3, 2, stop_at="40ns", init_events=4, delay_mod=3000, verbose=0)
+    from sst_core_b200.engine import Engine
+    e = Engine(m, calendar_slots=8, trace_capacity=1 << 16)
+    e.setup()
+    e.run()
+    tr = e.trace()
+    e.close()
+    for name, seq in GOLD["phold_3x2_40ns_trace"]["seq"].items():
+        c = int(name.replace("node", ""))
+        sel = tr["comp"] == c
+        assert [[int(t), int(p)] for t, p in zip(tr["time"][sel], tr["port"][sel])] == seq
+
+
+def test_phold_csv_rows_match_reference(tmp_path):
+    w = wireup.wire(config.build_graph(str(ROOT / "tests/models/phold.py"), "3 3 100ns 16 8000 1 1"))
+    res, st = run_gpu(w, calendar_slots=16)
+    assert output.stat_rows_csv(w, res, st.end_time) == GOLD["phold_3x3_100ns_csv"]["rows"]
+
+
+# ---- BASELINE config 5: clock-driven population ---------------------------------------------------------------------
+def test_clockpop_matches_reference_core():
+    res, _ = run_gpu(models.clockpop_model(6, 5, stop_at="2us", comm_freq=10))
+    for i, (ticks, last, recv, h) in GOLD["clockpop_6x5_2us_f10"]["nodes"].items():
+        assert [int(v) for v in res[int(i), :4]] == [ticks, last, recv, int(h, 16)], i
+
+
+@pytest.mark.parametrize("x,y,stop,f", [(64, 64, "300ns", 5), (100, 7, "1us", 1000), (33, 33, "100ns", 1)])
+def test_clockpop_vs_oracle(x, y, stop, f):
+    assert_same_as_oracle(models.clockpop_model(x, y, stop_at=stop, comm_freq=f, stats_enabled=True))
+
+
+def test_clockpop_csv_rows_match_reference():
+    w = wireup.wire(config.build_graph(str(ROOT / "tests/models/clockpop.py"), "3 3 1us 10 1 1"))
+    res, st = run_gpu(w)
+    assert output.stat_rows_csv(w, res, st.end_time) == GOLD["clockpop_3x3_1us_csv"]["rows"]
+
+
+# ---- termination / error behaviour ----------------------------------------------------------------------------------
+def test_stop_before_first_delivery():
+    res, st = run_gpu(models.mesh_model(4, 4, stop_at="1ns"))
+    assert st.events_delivered == 0 and st.end_time == 1000 and (res[:, 0] == 0).all()
+
+
+def test_stop_inside_a_window_clips_it():
+    m = models.phold_model(8, 8, stop_at="1ns")
+    m.stop_at = 12_345  # not a multiple of the 1000-cycle lookahead
+    assert_same_as_oracle(m, calendar_slots=16)
+
+
+def test_bin_overflow_is_reported_not_silent():
+    from sst_core_b200.engine import EngineError
+    with pytest.raises(EngineError, match="bin overflow"):
+        run_gpu(models.phold_model(16, 16, stop_at="50ns", init_events=64), calendar_slots=2, bin_capacity=512)
+
+
+def test_rng_component_model_ends_by_primary_component_exit():
+    # tests/test_RNGComponent_mersenne.py: one component, 1 GHz clock, ends after `count` ticks
+    from sst_core_b200.elements import TYPE_RNGCOMP
+    from sst_core_b200.wireup import WiredModel
+    for kind, s1, s2 in [(0, 1447, 0), (1, 1053, 1447), (2, 1447, 0)]:
+        p = np.zeros((1, 8), dtype=np.int64)
+        p[0, :5] = [kind, s1, s2, 100000, 1]
+        m = WiredModel(np.array([TYPE_RNGCOMP], np.uint32), p, np.zeros(2, np.uint32), np.zeros(0, np.uint32),
+                       np.zeros(0, np.uint64), np.array([1000], np.uint64), stop_at=10**16)
+        res, st = run_gpu(m)
+        ref = O.run_model(m)
+        assert np.array_equal(res, ref.results)
+        assert st.end_time == ref.end_time == 100_000_000 and st.clock_ticks == 100000
+        t = O.rng_ticks(kind, s1, s2, 99999, 1)[0]
+        assert [int(v) for v in res[0, 1:6]] == [int(v) for v in t]
