@@ -13,6 +13,8 @@
 //   Statistic<T>::addData              statbase.h:393-401 ->  Accumulator<T>::add   (stataccumulator.h:89-95)
 //   primaryComponentOKToEndSim         baseComponent.cc:869-920 -> ctx.primaryComponentOKToEndSim()
 //   getCurrentSimCycle                                    ->  ctx.now
+//   (none: engine-side latency hiding)                    ->  static prefetch(state*, aux*): issue L2 prefetches for what
+//                                                         the handlers will read this window
 //   finish()                                              ->  static results(const State&, uint64_t r[32]); the host
 //                                                         half formats the console line / statistic rows from r.
 //
@@ -76,6 +78,12 @@ mixDelivery(uint64_t h, uint64_t time, uint64_t port, uint64_t payload)
 
 #if defined(__CUDACC__)
 
+__device__ __forceinline__ void
+prefetch_l2(const void* p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // coreTestElement.message_mesh.enclosing_component (+ message_port / port_slot / route_message subcomponents,
 // flattened).  Reference: testElements/message_mesh/enclosingComponent.cc:29-69 (ctor), :72-81 (setup), :92-99
@@ -95,6 +103,18 @@ struct MeshElement
         uint64_t              counts; // links per port group, 8 bits each
         Accumulator<uint64_t> mcnt;   // RouteMessage "msg_count"
     };
+    // dispatch prologue hook: pull towards L2 the MT19937 words the next handful of draws will read
+    // (words idx.. and idx+397.. mod 624), so that the per-event draws hit L2 instead of paying an HBM round trip each
+    __device__ static void prefetch(const uint8_t* state, const uint8_t* aux)
+    {
+        const uint32_t  idx = reinterpret_cast<const State*>(state)->mt_idx;
+        const uint32_t  im  = (idx + MT_M >= MT_N) ? idx + MT_M - MT_N : idx + MT_M;
+        const uint32_t* mt  = reinterpret_cast<const uint32_t*>(aux);
+        prefetch_l2(mt + idx);
+        prefetch_l2(mt + (idx + 16 >= MT_N ? idx + 16 - MT_N : idx + 16));
+        prefetch_l2(mt + im);
+        prefetch_l2(mt + (im + 16 >= MT_N ? im + 16 - MT_N : im + 16));
+    }
     template <class Ctx>
     __device__ static void construct(Ctx& ctx, State& s, const int64_t* p)
     {
@@ -124,10 +144,12 @@ struct MeshElement
     {
         s.message_count++;
         MersenneDev rng { (uint32_t*)ctx.aux, s.mt_idx };
-        uint32_t    nextport = rng.u32() % s.ngroups;
-        uint32_t    cnt      = (uint32_t)((s.counts >> (8 * nextport)) & 0xFF);
-        uint32_t    portnum  = rng.u32() % cnt;
-        s.mt_idx             = rng.idx;
+        uint32_t    r0, r1;
+        rng.u32x2(r0, r1); // the two draws of RouteMessage::send, loads overlapped
+        uint32_t nextport = r0 % s.ngroups;
+        uint32_t cnt      = (uint32_t)((s.counts >> (8 * nextport)) & 0xFF);
+        uint32_t portnum  = r1 % cnt;
+        s.mt_idx          = rng.idx;
         uint32_t base        = 0;
         for ( uint32_t g = 0; g < nextport; ++g )
             base += (uint32_t)((s.counts >> (8 * g)) & 0xFF);
@@ -161,6 +183,7 @@ struct PholdElement
         uint32_t              dmod, init;
         Accumulator<uint64_t> delay;
     };
+    __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
     template <class Ctx>
     __device__ static void construct(Ctx&, State& s, const int64_t* p)
     {
@@ -219,6 +242,7 @@ struct ClockNodeElement
         int32_t              commFreq;
         Accumulator<int32_t> count[4];
     };
+    __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
     template <class Ctx>
     __device__ static void construct(Ctx&, State& s, const int64_t* p)
     {
@@ -279,6 +303,7 @@ struct RngElement
         uint64_t hash;
         uint32_t kind, a, b, c, d; // generator state: mersenne idx in a; marsaglia z,w in a,b; xorshift x,y,z,w
     };
+    __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
     template <class Ctx>
     __device__ static void construct(Ctx& ctx, State& s, const int64_t* p)
     {

@@ -77,6 +77,7 @@ struct Dev
 {
     Ctrl*           ctrl;
     uint32_t        n_local, c0, nbins, W, cap, emax;
+    uint32_t        lmax, uniform_nports; // link rows staged per block; ports per component when uniform (else 0)
     uint32_t        P0, nport_local;
     uint32_t        rank, n_ranks;
     const uint32_t* rank_comp_begin; // [n_ranks+1] (device)
@@ -172,32 +173,72 @@ emit(const Dev& d, uint64_t k, uint64_t time, uint32_t dst_port, uint32_t dst_co
     if ( d.has_payload ) d.ev_payload[off] = payload;
 }
 
-// What a handler sees of the core (BaseComponent / Link API subset, SURVEY.md section 8b.3)
-struct Ctx
+// Shared-memory view of one block's staged events.  Due events are staged here by phase 1; as a component consumes
+// its events the slots are recycled for the events it sends (out-staging), and phase 4 flushes them with
+// warp-aggregated reservations.  Record layout per slot (4 x u32 [+ u64 payload]):
+//   staged-in : t = time - T, a = receiving port, b = sequence, c = comp<<16 | rank (sorting scratch)
+//   staged-out: t = arrival - T, a = receiving port, b = sequence, c = destination component
+struct Stage
 {
-    const Dev& d;
-    uint64_t   now;    // getCurrentSimCycle()
-    uint64_t   k;      // current window
-    uint32_t   comp;   // global component id
-    uint32_t   port0;  // global id of this component's first directed port
-    uint32_t   nports;
-    uint8_t*   aux;
-    uint32_t   seq;    // per-component send sequence: the FIFO tie-break the reference gets from queue_order
-    uint32_t   sent;
-    int        stats_on;
+    uint32_t* t;
+    uint32_t* a;
+    uint32_t* b;
+    uint32_t* c;
+    uint64_t* pay;
+    uint32_t* overflow_ctr; // slots handed out beyond n_due
+    uint32_t  n_due, emax;
+};
 
-    __device__ __forceinline__ bool connected(int port) const
-    {
-        return __ldg(&d.link[port0 - d.P0 + (uint32_t)port]).x != SSTB200_NO_PEER;
-    }
+// What a handler sees of the core (BaseComponent / Link API subset, SURVEY.md section 8b.3)
+template <bool STAGED>
+struct CtxT
+{
+    const Dev&   d;
+    uint64_t     now;   // getCurrentSimCycle()
+    uint64_t     k;     // current window
+    uint64_t     T;     // start of the current window
+    uint32_t     comp;  // global component id
+    uint32_t     port0; // global id of this component's first directed port
+    uint32_t     nports;
+    uint8_t*     aux;
+    uint32_t     seq;   // per-component send sequence: the FIFO tie-break the reference gets from queue_order
+    uint32_t     sent;
+    int          stats_on;
+    const uint4* links; // this component's link row (shared memory when the block's rows were staged, else global)
+    // out-staging (STAGED only)
+    Stage           st;
+    const uint16_t* seg;       // this component's consumed slots are seg[free_head .. free_tail)
+    uint32_t        free_head, free_tail;
+
+    __device__ __forceinline__ bool connected(int port) const { return links[port].x != SSTB200_NO_PEER; }
     // Link::send(delay, ev): delivery time = now + delay + latency of the sending end (link.cc:636)
     __device__ __forceinline__ void send(int port, uint64_t delay, uint64_t payload)
     {
-        const uint4 l = __ldg(&d.link[port0 - d.P0 + (uint32_t)port]);
+        const uint4 l = links[port];
         if ( l.x == SSTB200_NO_PEER ) return;
-        const uint64_t lat = ((uint64_t)l.w << 32) | l.z;
-        emit(d, k, now + delay + lat, l.x, l.y, seq++, payload);
+        const uint64_t lat  = ((uint64_t)l.w << 32) | l.z;
+        const uint64_t when = now + delay + lat;
+        const uint32_t sq   = seq++;
         sent++;
+        if ( STAGED ) {
+            const uint64_t off = when - T;
+            if ( (off >> 32) == 0 ) {
+                uint32_t slot;
+                if ( free_head < free_tail )
+                    slot = seg[free_head++];
+                else
+                    slot = st.n_due + atomicAdd(st.overflow_ctr, 1u);
+                if ( slot < st.emax ) {
+                    st.t[slot] = (uint32_t)off;
+                    st.a[slot] = l.x;
+                    st.b[slot] = sq;
+                    st.c[slot] = l.y;
+                    if ( st.pay ) st.pay[slot] = payload;
+                    return;
+                }
+            }
+        }
+        emit(d, k, when, l.x, l.y, sq, payload);
     }
     __device__ __forceinline__ void primaryComponentOKToEndSim()
     {
@@ -257,8 +298,9 @@ setup_kernel(Dev d)
     const uint32_t lc = blockIdx.x * BLOCK + threadIdx.x;
     if ( lc >= d.n_local ) return;
     const uint32_t type = d.comp_type[lc];
-    Ctx            ctx { d, 0, 0, d.c0 + lc, d.port_off[lc], d.port_off[lc + 1] - d.port_off[lc],
-                         d.aux + (uint64_t)lc * d.aux_stride, 0, 0, d.stats_on };
+    const uint32_t p0   = d.port_off[lc];
+    CtxT<false>    ctx { d, 0, 0, 0, d.c0 + lc, p0, d.port_off[lc + 1] - p0, d.aux + (uint64_t)lc * d.aux_stride,
+                         0, 0, d.stats_on, d.link + (p0 - d.P0), Stage {}, nullptr, 0, 0 };
     const uint64_t period = d.clock_period[lc];
     d.next_tick[lc]       = period ? period : TIME_NEVER; // first tick at `period`, never at 0 (clock.cc:400-420)
     with_element(type, [&](auto el) {
@@ -309,7 +351,7 @@ block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& total)
 
 // ---- one lookahead window for one block of 256 components
 template <bool PAYLOAD>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, 4)
 dispatch_kernel(Dev d)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -318,42 +360,61 @@ dispatch_kernel(Dev d)
     const uint64_t k     = ctrl->k;
     const uint64_t T     = ctrl->T;
     const uint64_t T_end = ctrl->T_end;
-    const uint64_t w     = ctrl->w;
+    const uint32_t w     = (uint32_t)ctrl->w; // < 2^31 (checked by the host)
     const uint32_t bin   = blockIdx.x;
     const uint32_t slot  = (uint32_t)(k % d.W);
     const uint32_t tid   = threadIdx.x;
     const uint32_t lc    = bin * BLOCK + tid;
     const bool     valid = lc < d.n_local;
 
-    // shared-memory carve-up
-    uint64_t* s_pay      = reinterpret_cast<uint64_t*>(smem_raw); // [emax] (PAYLOAD only)
-    uint8_t*  p          = smem_raw + (PAYLOAD ? (size_t)d.emax * 8 : 0);
+    // shared-memory carve-up (host: engine_create computes the same sizes)
+    uint4*    s_link     = reinterpret_cast<uint4*>(smem_raw);                       // [lmax]
+    uint64_t* s_pay      = reinterpret_cast<uint64_t*>(smem_raw + (size_t)d.lmax * 16); // [emax] (PAYLOAD only)
+    uint8_t*  p          = reinterpret_cast<uint8_t*>(s_pay) + (PAYLOAD ? (size_t)d.emax * 8 : 0);
     uint32_t* s_time     = reinterpret_cast<uint32_t*>(p);
     uint32_t* s_dst      = s_time + d.emax;
     uint32_t* s_seq      = s_dst + d.emax;
-    uint32_t* s_cr       = s_seq + d.emax;                  // comp<<16 | rank within comp
+    uint32_t* s_cr       = s_seq + d.emax;
     uint32_t* s_port_off = s_cr + d.emax;                   // [BLOCK+1]
     uint32_t* s_cnt      = s_port_off + BLOCK + 1;          // [BLOCK]
     uint32_t* s_off      = s_cnt + BLOCK;                   // [BLOCK]
     uint32_t* s_warp     = s_off + BLOCK;                   // [BLOCK/32+1]
-    uint32_t* s_misc     = s_warp + BLOCK / 32 + 1;         // [4]
+    uint32_t* s_misc     = s_warp + BLOCK / 32 + 1;         // [4]: 0 due events, 1 out-staging overflow slots
     uint16_t* s_perm     = reinterpret_cast<uint16_t*>(s_misc + 4); // [emax]
 
+    // ---- prologue: everything here is independent global traffic issued back to back
     const uint32_t n_in = d.bin_count[slot * d.nbins + bin];
     {
-        const uint32_t j = bin * BLOCK + tid;
-        s_port_off[tid]  = d.port_off[j <= d.n_local ? j : d.n_local];
+        s_port_off[tid] = d.port_off[lc <= d.n_local ? lc : d.n_local];
         if ( tid == 0 ) {
             const uint32_t e  = (bin + 1) * BLOCK;
             s_port_off[BLOCK] = d.port_off[e <= d.n_local ? e : d.n_local];
             s_misc[0]         = 0;
+            s_misc[1]         = 0;
         }
         s_cnt[tid] = 0;
     }
+    uint32_t my_type = 0;
+    if ( valid ) {
+        my_type = d.comp_type[lc];
+        // element hook: start pulling the state line and the aux words the handlers will touch towards L2
+        with_element(my_type, [&](auto el) {
+            using E = decltype(el);
+            E::prefetch(d.state + (uint64_t)lc * d.state_stride, d.aux + (uint64_t)lc * d.aux_stride);
+        });
+    }
     __syncthreads();
+    const uint32_t blk_port0  = s_port_off[0];
+    const uint32_t blk_nports = s_port_off[BLOCK] - blk_port0;
+    const bool     links_in_smem = blk_nports <= d.lmax;
+    if ( links_in_smem ) {
+        const uint4* src = d.link + (blk_port0 - d.P0);
+        for ( uint32_t i = tid; i < blk_nports; i += BLOCK )
+            s_link[i] = __ldg(&src[i]);
+    }
 
     // ---- phase 1: load the bin; stage due events in shared memory, re-bin the ones that are not due yet
-    uint32_t       carried = 0, dropped = 0;
+    uint32_t       dropped  = 0;
     const uint64_t bin_base = (uint64_t)(slot * d.nbins + bin) * d.cap;
     for ( uint32_t i = tid; i < n_in; i += BLOCK ) {
         const uint64_t t  = d.ev_time[bin_base + i];
@@ -362,24 +423,30 @@ dispatch_kernel(Dev d)
         if ( PAYLOAD ) pl = d.ev_payload[bin_base + i];
         const uint32_t dst = (uint32_t)(ds >> 32);
         // component of the receiving port: largest j with s_port_off[j] <= dst
-        uint32_t lo = 0, hi = BLOCK;
-        while ( hi - lo > 1 ) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if ( s_port_off[mid] <= dst )
-                lo = mid;
-            else
-                hi = mid;
+        uint32_t lo;
+        if ( d.uniform_nports ) {
+            lo = (dst - blk_port0) / d.uniform_nports;
+        }
+        else {
+            lo          = 0;
+            uint32_t hi = BLOCK;
+            while ( hi - lo > 1 ) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if ( s_port_off[mid] <= dst )
+                    lo = mid;
+                else
+                    hi = mid;
+            }
         }
         if ( t < T ) {
             raise_error(d, ERR_TIME_FAULT, t, T, bin * BLOCK + lo + d.c0);
         }
         else if ( t >= T_end ) {
-            if ( t < (k + 1) * w ) {
+            if ( t < T + w ) {
                 dropped++; // at or after a stop time inside this window: never delivered (StopAction priority 30)
             }
             else {
                 emit(d, k, t, dst, d.c0 + bin * BLOCK + lo, (uint32_t)ds, pl);
-                carried++;
             }
         }
         else {
@@ -414,7 +481,7 @@ dispatch_kernel(Dev d)
     __syncthreads();
 
     // ---- phase 3: every thread orders its component's segment by (time, port, sequence) and runs the handlers,
-    // merged with the component's clock ticks
+    // merged with the component's clock ticks; sends are staged in the slots the component has already consumed
     uint32_t delivered = 0, ticks = 0, sent = 0, clocks_stopped = 0;
     if ( valid ) {
         uint16_t* seg = s_perm + my_off;
@@ -437,11 +504,14 @@ dispatch_kernel(Dev d)
         uint64_t       next_tick = d.next_tick[lc];
         const bool     has_work  = my_cnt > 0 || next_tick < T_end;
         if ( has_work ) {
-            const uint32_t type = d.comp_type[lc];
-            Ctx            ctx { d, T, k, d.c0 + lc, s_port_off[tid], s_port_off[tid + 1] - s_port_off[tid],
-                                 d.aux + (uint64_t)lc * d.aux_stride, d.send_seq[lc], 0, d.stats_on };
+            const uint32_t p0 = s_port_off[tid];
+            CtxT<true>     ctx { d, T, k, T, d.c0 + lc, p0, s_port_off[tid + 1] - p0,
+                                 d.aux + (uint64_t)lc * d.aux_stride, d.send_seq[lc], 0, d.stats_on,
+                                 links_in_smem ? (const uint4*)(s_link + (p0 - blk_port0)) : d.link + (p0 - d.P0),
+                                 Stage { s_time, s_dst, s_seq, s_cr, PAYLOAD ? s_pay : nullptr, &s_misc[1], n_due, d.emax },
+                                 seg, 0, 0 };
             uint32_t       dseq = d.deliv_seq ? d.deliv_seq[lc] : 0;
-            with_element(type, [&](auto el) {
+            with_element(my_type, [&](auto el) {
                 using E = decltype(el);
                 typename E::State s;
                 load_state(s, d.state + (uint64_t)lc * d.state_stride);
@@ -466,6 +536,8 @@ dispatch_kernel(Dev d)
                     const uint32_t e    = seg[i++];
                     const uint32_t port = s_dst[e] - ctx.port0;
                     uint64_t       pl   = PAYLOAD ? s_pay[e] : 0;
+                    s_dst[e]            = SSTB200_NO_PEER; // slot consumed: free for out-staging
+                    ctx.free_tail       = i;
                     ctx.now             = ev_t;
                     if ( d.trace_cap ) {
                         const unsigned long long tp = atomicAdd(&ctrl->trace_n, 1ull);
@@ -489,8 +561,80 @@ dispatch_kernel(Dev d)
             sent = ctx.sent;
         }
     }
+    __syncthreads();
 
-    // ---- phase 4: fold counters (one atomic per warp), recycle the bin
+    // ---- phase 4: flush the staged sends.  Lanes of a warp that target the same (window slot, destination block)
+    // reserve their calendar slots with ONE atomic (match.any), then write their records side by side.
+    {
+        uint32_t n_stage = n_due + s_misc[1];
+        if ( n_stage > d.emax ) n_stage = d.emax;
+        const uint32_t lane = tid & 31;
+        for ( uint32_t base = 0; base < n_stage; base += BLOCK ) {
+            const uint32_t e      = base + tid;
+            const bool     active = e < n_stage && s_dst[e] != SSTB200_NO_PEER;
+            uint32_t       key = 0xFFFFFFFFu, dcomp = 0, dt = 0;
+            bool           remote = false;
+            if ( active ) {
+                dcomp = s_cr[e];
+                dt    = s_time[e];
+                if ( d.n_ranks > 1 && (dcomp < d.c0 || dcomp >= d.c0 + d.n_local) ) {
+                    remote = true;
+                    uint32_t r = 0;
+                    while ( r + 1 < d.n_ranks && dcomp >= d.rank_comp_begin[r + 1] )
+                        ++r;
+                    key = 0x80000000u | r;
+                }
+                else if ( dt < w ) {
+                    raise_error(d, ERR_TIME_FAULT, T + dt, T, dcomp); // a send violated the lookahead
+                    key = 0xFFFFFFFEu;
+                }
+                else {
+                    uint32_t dk = dt < 2 * w ? 1u : dt / w;
+                    if ( dk > d.W - 1 ) dk = d.W - 1;
+                    key = (uint32_t)((k + dk) % d.W) * d.nbins + (dcomp - d.c0) / BLOCK;
+                }
+            }
+            const uint32_t peers  = __match_any_sync(0xffffffffu, key);
+            const uint32_t leader = __ffs(peers) - 1;
+            const uint32_t rank   = __popc(peers & ((1u << lane) - 1));
+            unsigned long long pos0 = 0;
+            if ( active && key < 0xFFFFFFFEu && lane == leader ) {
+                if ( remote )
+                    pos0 = atomicAdd(&d.outbox[(uint64_t)(key & 0x7FFFFFFFu) * d.xwords], (unsigned long long)__popc(peers));
+                else
+                    pos0 = atomicAdd(&d.bin_count[key], (uint32_t)__popc(peers));
+            }
+            pos0 = __shfl_sync(0xffffffffu, pos0, leader);
+            if ( active && key < 0xFFFFFFFEu ) {
+                const unsigned long long pos = pos0 + rank;
+                const uint64_t           tm  = T + dt;
+                const uint64_t           ds  = ((uint64_t)s_dst[e] << 32) | s_seq[e];
+                if ( remote ) {
+                    if ( pos >= d.outbox_cap ) {
+                        raise_error(d, ERR_OUTBOX_OVERFLOW, key & 0x7FFFFFFFu, pos, d.outbox_cap);
+                    }
+                    else {
+                        unsigned long long* rec = d.outbox + (uint64_t)(key & 0x7FFFFFFFu) * d.xwords + 1 + pos * 4;
+                        rec[0]                  = tm;
+                        rec[1]                  = ds;
+                        rec[2]                  = PAYLOAD ? s_pay[e] : 0;
+                        rec[3]                  = dcomp;
+                    }
+                }
+                else if ( pos >= d.cap ) {
+                    raise_error(d, ERR_BIN_OVERFLOW, key / d.nbins, key % d.nbins, pos);
+                }
+                else {
+                    const uint64_t off = (uint64_t)key * d.cap + pos;
+                    d.ev_time[off]     = tm;
+                    d.ev_dst_seq[off]  = ds;
+                    if ( PAYLOAD ) d.ev_payload[off] = s_pay[e];
+                }
+            }
+        }
+    }
+
+    // ---- phase 5: fold counters (one atomic per warp), recycle the bin
     {
         uint32_t v0 = delivered, v1 = ticks, v2 = sent, v3 = clocks_stopped, v4 = dropped;
 #pragma unroll
@@ -977,6 +1121,19 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         const ElementInfo* ei = element_by_type(m->comp_type[c]);
         if ( ei && ei->has_payload ) has_payload = 1;
     }
+    // link rows of a block are staged in shared memory when they fit (2048 rows = 32 KB); a uniform port count lets
+    // the kernel find an event's component with one division instead of a binary search
+    {
+        uint32_t max_blk = 0, uni = m->port_off[c0 + (d.n_local ? 1 : 0)] - m->port_off[c0];
+        for ( uint32_t b = 0; b < d.nbins; ++b ) {
+            const uint32_t lo = c0 + b * BLOCK, hi = std::min<uint32_t>(c1, lo + BLOCK);
+            max_blk           = std::max(max_blk, m->port_off[hi] - m->port_off[lo]);
+        }
+        for ( uint32_t c = c0; c < c1 && uni; ++c )
+            if ( m->port_off[c + 1] - m->port_off[c] != uni ) uni = 0;
+        d.lmax           = max_blk <= 2048 ? max_blk : 0;
+        d.uniform_nports = uni;
+    }
     d.state_stride = (state_stride + 15u) & ~15u;
     d.aux_stride   = (aux_stride + 31u) & ~31u;
     d.has_payload  = has_payload;
@@ -1029,7 +1186,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     e->h_ctrl->had_primary = 1;
     CUDA_OK(cudaMemcpyAsync(d.ctrl, e->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, e->stream));
 
-    e->smem_bytes = (size_t)d.emax * (has_payload ? 8 : 0) + (size_t)d.emax * 16 +
+    e->smem_bytes = (size_t)d.lmax * 16 + (size_t)d.emax * (has_payload ? 8 : 0) + (size_t)d.emax * 16 +
                     (size_t)(BLOCK + 1 + BLOCK + BLOCK + BLOCK / 32 + 1 + 4) * 4 + (size_t)d.emax * 2 + 16;
     if ( e->smem_bytes > 227 * 1024 ) {
         set_error("engine_create: smem_events too large for 227 KB of shared memory");

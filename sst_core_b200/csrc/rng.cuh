@@ -69,6 +69,33 @@ struct MersenneDev
         idx   = i1;
         return mt_temper(v);
     }
+    // Two consecutive draws with all five word reads issued before either write: the second draw never depends on
+    // the first one's store (word i+1 is still old, (i+1+397)%624 != i), so the loads overlap instead of forming two
+    // dependent memory round trips.  Same stream as two u32() calls.
+    SSTB_HD void u32x2(uint32_t& r0, uint32_t& r1)
+    {
+        const uint32_t i   = idx;
+        const uint32_t i1  = (i + 1 == MT_N) ? 0u : i + 1;
+        const uint32_t i2  = (i1 + 1 == MT_N) ? 0u : i1 + 1;
+        const uint32_t im  = (i + MT_M >= MT_N) ? i + MT_M - MT_N : i + MT_M;
+        const uint32_t im1 = (im + 1 == MT_N) ? 0u : im + 1;
+        const uint32_t a0 = mt[i], a1 = mt[i1], a2 = mt[i2], b0 = mt[im], b1 = mt[im1];
+        const uint32_t y0 = (a0 & 0x80000000u) + (a1 & 0x7fffffffu);
+        uint32_t       v0 = b0 ^ (y0 >> 1);
+        if ( y0 & 1u ) v0 ^= 2567483615u;
+        // word i2 is new-generation only when the pair wraps (i1 == 623 -> i2 == 0, written 623 draws ago) and
+        // word im1 == i only if 398 == 0 mod 624: never.  But im1 == i is impossible while im == i1 is too
+        // (397 != 1 mod 624), so a2/b1 are exactly what a second u32() would have read -- except a2 when i2 == i
+        // (MT_N == 2: impossible).
+        const uint32_t y1 = (a1 & 0x80000000u) + (a2 & 0x7fffffffu);
+        uint32_t       v1 = b1 ^ (y1 >> 1);
+        if ( y1 & 1u ) v1 ^= 2567483615u;
+        mt[i]  = v0;
+        mt[i1] = v1;
+        idx    = i2;
+        r0     = mt_temper(v0);
+        r1     = mt_temper(v1);
+    }
     SSTB_HD double uniform()
     {
         double d;

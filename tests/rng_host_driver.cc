@@ -1,0 +1,50 @@
+// Host compile of the DEVICE RNG header (sst_core_b200/csrc/rng.cuh is host/device code): lets the CPU-only test
+// tier check the incremental MT19937 twist and the paired draw against the oracle without a GPU.
+#include "../sst_core_b200/csrc/rng.cuh"
+
+#include <cstdint>
+using namespace sstb200;
+
+extern "C" {
+// mode 0: u32() only; mode 1: u32x2() pairs; mode 2: `lead` single draws then pairs (exercises every alignment of
+// the pair against the 624-word wrap)
+void
+dev_mt_stream(uint32_t seed, int mode, uint32_t lead, uint64_t n, uint32_t* out)
+{
+    static uint32_t mt[MT_N];
+    mt_seed(mt, seed);
+    MersenneDev g { mt, 0 };
+    uint64_t    i = 0;
+    if ( mode == 2 )
+        for ( ; i < lead && i < n; ++i )
+            out[i] = g.u32();
+    if ( mode == 0 ) {
+        for ( ; i < n; ++i )
+            out[i] = g.u32();
+    }
+    else {
+        for ( ; i + 1 < n; i += 2 )
+            g.u32x2(out[i], out[i + 1]);
+        for ( ; i < n; ++i )
+            out[i] = g.u32();
+    }
+}
+void
+dev_marsaglia_stream(uint32_t z, uint32_t w, uint64_t n, uint32_t* out, double* uni)
+{
+    MarsagliaDev g { z, w };
+    for ( uint64_t i = 0; i < n; ++i )
+        out[i] = g.u32();
+    MarsagliaDev h { z, w };
+    for ( uint64_t i = 0; i < n; ++i )
+        uni[i] = h.uniform();
+}
+void
+dev_xorshift_stream(uint32_t seed, uint64_t n, uint32_t* out)
+{
+    XorShiftDev g;
+    g.seed(seed);
+    for ( uint64_t i = 0; i < n; ++i )
+        out[i] = g.u32();
+}
+}

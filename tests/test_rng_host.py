@@ -1,0 +1,53 @@
+"""The device RNG header compiled for the host (it is __host__ __device__ code) against the oracle: the incremental
+MT19937 twist and the paired draw reproduce the reference's batch generator for every alignment of the 624-word wrap."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+HERE = Path(__file__).resolve().parent
+
+
+@pytest.fixture(scope="module")
+def drv(tmp_path_factory):
+    so = tmp_path_factory.mktemp("rngdrv") / "librngdrv.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", str(so),
+                           str(HERE / "rng_host_driver.cc")])
+    L = C.CDLL(str(so))
+    L.dev_mt_stream.argtypes = [C.c_uint32, C.c_int, C.c_uint32, C.c_uint64, C.c_void_p]
+    L.dev_marsaglia_stream.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.dev_xorshift_stream.argtypes = [C.c_uint32, C.c_uint64, C.c_void_p]
+    return L
+
+
+def test_incremental_twist_equals_batch_generator(drv):
+    n = 624 * 7 + 13
+    ref, _ = O.rng_u32_stream(0, 1447, 0, n)
+    out = np.zeros(n, dtype=np.uint32)
+    drv.dev_mt_stream(1447, 0, 0, n, out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("lead", [0, 1, 2, 3, 226, 227, 228, 621, 622, 623, 624, 625])
+def test_paired_draw_equals_two_single_draws(drv, lead):
+    n = 624 * 5 + 7
+    ref, _ = O.rng_u32_stream(0, 100 + lead, 0, n)
+    out = np.zeros(n, dtype=np.uint32)
+    drv.dev_mt_stream(100 + lead, 2, lead, n, out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out, ref)
+
+
+def test_marsaglia_and_xorshift(drv):
+    n = 5000
+    ref, _ = O.rng_u32_stream(1, 1053, 1447, n)
+    out = np.zeros(n, dtype=np.uint32)
+    uni = np.zeros(n, dtype=np.float64)
+    drv.dev_marsaglia_stream(1053, 1447, n, out.ctypes.data_as(C.c_void_p), uni.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out, ref)
+    ref, _ = O.rng_u32_stream(2, 1447, 0, n)
+    drv.dev_xorshift_stream(1447, n, out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out, ref)
