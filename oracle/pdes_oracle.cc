@@ -273,6 +273,12 @@ struct Sim
     int64_t                  primary = 0;
     bool                     end_sim = false, in_run = false, stats_on = true, tracing = false;
     std::vector<TraceRec>    trace;
+    // partitioned stepping (RankSyncSerialSkip contract): this Sim owns components [own_lo, own_hi); events for other
+    // components are collected in `outbox` as {time, dst_port<<32|seq, payload, dst_comp} and handed to the owner
+    // at the next sync, which re-inserts them (rankSyncSerialSkip.cc:291-295)
+    uint32_t                 own_lo = 0, own_hi = 0xFFFFFFFFu;
+    std::vector<uint64_t>    outbox;
+    std::vector<uint32_t>    send_seq;
 
     ~Sim()
     {
@@ -360,7 +366,13 @@ Component::send(int port, uint64_t delay, uint64_t payload)
     uint32_t p    = port0 + (uint32_t)port;
     uint32_t peer = sim->peer_port[p];
     if ( peer == NO_PEER ) return;
-    uint64_t t = sim->now + delay + sim->latency[p];
+    uint64_t t  = sim->now + delay + sim->latency[p];
+    uint32_t dc = sim->port_comp[peer];
+    uint32_t sq = sim->send_seq[id]++;
+    if ( dc < sim->own_lo || dc >= sim->own_hi ) {
+        sim->outbox.insert(sim->outbox.end(), { t, ((uint64_t)peer << 32) | sq, payload, (uint64_t)dc });
+        return;
+    }
     sim->insert({ t, (PRIO_EVENT << 32) | sim->port_tag[peer], 0, KIND_EVENT, peer, payload });
 }
 
@@ -546,6 +558,7 @@ oracle_create(uint32_t ncomp, const uint32_t* comp_type, const int64_t* comp_par
     s->latency.assign(latency, latency + nport);
     s->port_comp.resize(nport);
     s->port_tag.resize(nport);
+    s->send_seq.assign(ncomp, 0);
     uint32_t next_tag = 1; // simulation.h:566-572
     for ( uint32_t c = 0; c < ncomp; ++c ) {
         const int64_t* p = comp_param + (size_t)c * NPARAM;
@@ -584,6 +597,120 @@ oracle_create(uint32_t ncomp, const uint32_t* comp_type, const int64_t* comp_par
         if ( clock_period[c] ) s->registerClock(c, clock_period[c]);
     }
     return s;
+}
+
+// ---- partitioned stepping: the reference's conservative window protocol (SyncManager::execute +
+// RankSyncSerialSkip::exchange) restated for one partition.  Components outside [own_lo, own_hi) are constructed but
+// never run (their setup() is skipped and nothing is delivered to them).
+void
+oracle_set_ownership(void* h, uint32_t own_lo, uint32_t own_hi)
+{
+    Sim* s    = (Sim*)h;
+    s->own_lo = own_lo;
+    s->own_hi = own_hi;
+}
+
+void
+oracle_setup_owned(void* h)
+{
+    Sim* s = (Sim*)h;
+    // non-owned components: remove their clock registrations and primary counts
+    for ( auto& ck : s->clocks ) {
+        std::vector<uint32_t> keep;
+        for ( uint32_t c : ck.handlers )
+            if ( c >= s->own_lo && c < s->own_hi ) keep.push_back(c);
+        ck.handlers = keep;
+    }
+    s->primary = 0;
+    for ( uint32_t c = s->own_lo; c < s->own_hi && c < s->ncomp; ++c )
+        s->primary++;
+    s->in_run = true;
+    for ( uint32_t c = s->own_lo; c < s->own_hi && c < s->ncomp; ++c )
+        s->comps[c]->setup();
+}
+
+// deliver every local activity with time < t_end (and, like StopAction, nothing at or after stop_at); returns the
+// number of 4-word records now in the outbox
+uint64_t
+oracle_run_until(void* h, uint64_t t_end)
+{
+    Sim* s = (Sim*)h;
+    while ( !s->pq.empty() ) {
+        Activity a = s->pq.top();
+        if ( a.time >= t_end ) break;
+        s->pq.pop();
+        s->now = a.time;
+        if ( a.kind == KIND_EVENT ) {
+            uint32_t   c = s->port_comp[a.target];
+            Component* k = s->comps[c];
+            s->events_delivered++;
+            if ( s->tracing ) s->trace.push_back({ s->now, c, a.target - k->port0, a.payload });
+            k->handleEvent((int)(a.target - k->port0), a.payload);
+        }
+        else if ( a.kind == KIND_CLOCK ) {
+            ClockObj& ck = s->clocks[a.target];
+            if ( ck.handlers.empty() ) continue;
+            ck.cycle++;
+            size_t keep = 0;
+            for ( size_t i = 0; i < ck.handlers.size(); ++i ) {
+                s->clock_ticks++;
+                if ( !s->comps[ck.handlers[i]]->tick(ck.cycle) ) ck.handlers[keep++] = ck.handlers[i];
+            }
+            ck.handlers.resize(keep);
+            s->insert({ s->now + ck.period, PRIO_CLOCK << 32, 0, KIND_CLOCK, a.target, 0 });
+        }
+    }
+    return s->outbox.size() / 4;
+}
+
+void
+oracle_take_outbox(void* h, uint64_t* out)
+{
+    Sim* s = (Sim*)h;
+    memcpy(out, s->outbox.data(), s->outbox.size() * 8);
+    s->outbox.clear();
+}
+
+// re-insert events received from other partitions.  The tie-break among events with equal (time, tag) must be the
+// sender's order: the records carry the sender's per-component sequence number, so insert them sorted by it.
+void
+oracle_ingest(void* h, const uint64_t* rec, uint64_t n)
+{
+    Sim*                  s = (Sim*)h;
+    std::vector<uint64_t> idx(n);
+    for ( uint64_t i = 0; i < n; ++i )
+        idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) {
+        return (int32_t)((uint32_t)rec[4 * a + 1] - (uint32_t)rec[4 * b + 1]) < 0;
+    });
+    for ( uint64_t j = 0; j < n; ++j ) {
+        const uint64_t* r    = rec + 4 * idx[j];
+        uint32_t        peer = (uint32_t)(r[1] >> 32);
+        s->insert({ r[0], (PRIO_EVENT << 32) | s->port_tag[peer], 0, KIND_EVENT, peer, r[2] });
+    }
+}
+
+// control words of this partition: [0] pending events, [1] primary components still running, [2] active clock
+// handlers, [3] error, [4] exit time
+void
+oracle_control_words(void* h, int64_t* out)
+{
+    Sim*    s       = (Sim*)h;
+    int64_t pending = 0, clocks = 0;
+    // count queued events / active handlers
+    auto copy = s->pq;
+    while ( !copy.empty() ) {
+        if ( copy.top().kind == KIND_EVENT ) pending++;
+        copy.pop();
+    }
+    for ( auto& ck : s->clocks )
+        clocks += (int64_t)ck.handlers.size();
+    out[0] = pending + (int64_t)(s->outbox.size() / 4);
+    out[1] = s->primary;
+    out[2] = clocks;
+    out[3] = 0;
+    out[4] = (int64_t)s->end_time;
+    out[5] = out[6] = out[7] = 0;
 }
 
 void

@@ -284,6 +284,25 @@ class Engine:
         _check(self._L.sstb200_engine_control_words(self._h, C.byref(a), C.byref(b)), "control_words")
         return a.value, b.value
 
+    def exchange_tensors(self):
+        """(outbox, inbox) as zero-copy int64 torch tensors [n_ranks, words] over engine-owned device memory."""
+        import torch
+        ob, ib, words = self.exchange_buffers()
+        dev = torch.device("cuda", self.device)
+        n = self.n_ranks
+        return (_as_tensor(torch, ob, n * words, dev).view(n, words), _as_tensor(torch, ib, n * words, dev).view(n, words))
+
+    def control_tensors(self):
+        """(local [8], gathered [n_ranks*8]) control words as zero-copy int64 torch tensors."""
+        import torch
+        lw, gw = self.control_words()
+        dev = torch.device("cuda", self.device)
+        return _as_tensor(torch, lw, 8, dev), _as_tensor(torch, gw, 8 * self.n_ranks, dev)
+
+    def sync(self):
+        """Wait for the engine's stream (status() does a device->host read on it)."""
+        self.status()
+
     def results(self) -> np.ndarray:
         out = np.zeros((self.comp_end - self.comp_begin, NRESULT), dtype=np.uint64)
         _check(self._L.sstb200_engine_results(self._h, _p(out)), "engine_results")
@@ -303,23 +322,20 @@ class Engine:
 
 # ------------------------------------------------------------------------------------------------ multi-GPU stepping
 class DistributedRunner:
-    """One lookahead window per step across all ranks: dispatch -> all-to-all of the outboxes over NVLink (NCCL) ->
-    ingest -> all-gather of the control words -> advance.  Replaces SyncManager::execute +
-    RankSyncSerialSkip::exchange (+ its MPI_Allreduce calls, rankSyncSerialSkip.cc:318-335)."""
+    """One lookahead window per step across all ranks of the torch.distributed world:
 
-    def __init__(self, engine: Engine):
-        import torch
+        dispatch -> all-to-all of the outboxes (NVLink / NCCL) -> ingest -> all-gather of the control words -> advance
+
+    Replaces SyncManager::execute + RankSyncSerialSkip::exchange and its MPI_Allreduce calls
+    (sync/syncManager.cc:547-732, sync/rankSyncSerialSkip.cc:209-343).  The engine may be the CUDA `Engine` or any
+    object with the same stepping interface (the CPU tests drive the oracle through this class over gloo)."""
+
+    def __init__(self, engine):
         import torch.distributed as dist
 
-        self.torch, self.dist, self.e = torch, dist, engine
-        ob, ib, words = engine.exchange_buffers()
-        n = engine.n_ranks
-        dev = torch.device("cuda", engine.device)
-        self.outbox = _as_tensor(torch, ob, n * words, dev).view(n, words)
-        self.inbox = _as_tensor(torch, ib, n * words, dev).view(n, words)
-        lw, gw = engine.control_words()
-        self.local = _as_tensor(torch, lw, 8, dev)
-        self.gathered = _as_tensor(torch, gw, 8 * n, dev)
+        self.dist, self.e = dist, engine
+        self.outbox, self.inbox = engine.exchange_tensors()
+        self.local, self.gathered = engine.control_tensors()
 
     def step(self):
         e = self.e
@@ -342,6 +358,75 @@ class DistributedRunner:
                 return True
             if max_windows and done_windows >= max_windows:
                 return False
+
+
+class LocalMultiRankRunner:
+    """All partitions of a model stepped by ONE process on ONE GPU: the same device code path as a multi-GPU run
+    (outbox emission, ingest kernel, gathered control words) with the exchange done by device-to-device copies.
+    Used to validate the multi-rank path where fewer GPUs than ranks are available, and usable as a way to run more
+    partitions than GPUs.  Kernels of different ranks never wait on each other, so running them back to back on one
+    stream is safe."""
+
+    def __init__(self, model: WiredModel, n_ranks: int, device: int = 0, **engine_opts):
+        import torch
+
+        self.torch = torch
+        self.pm = partition_model(model, n_ranks)
+        self.engines = [Engine(self.pm, device=device, rank=r, n_ranks=n_ranks, **engine_opts) for r in range(n_ranks)]
+        self.n = n_ranks
+        self.xt = [e.exchange_tensors() for e in self.engines]
+        self.ct = [e.control_tensors() for e in self.engines]
+
+    def setup(self):
+        for e in self.engines:
+            e.setup()
+
+    def step(self):
+        t = self.torch
+        for e in self.engines:
+            e.dispatch()
+        for e in self.engines:
+            e.sync()
+        for r in range(self.n):  # inbox[r][src] = outbox[src][r]
+            for src in range(self.n):
+                self.xt[r][1][src].copy_(self.xt[src][0][r])
+        t.cuda.synchronize()
+        for e in self.engines:
+            e.ingest()
+        for e in self.engines:
+            e.sync()
+        allw = t.cat([c[0] for c in self.ct])
+        for c in self.ct:
+            c[1].copy_(allw)
+        t.cuda.synchronize()
+        for e in self.engines:
+            e.advance()
+        for e in self.engines:
+            e.sync()
+
+    def run(self, max_windows: int = 0, check_every: int = 16) -> bool:
+        done = 0
+        while True:
+            for _ in range(check_every):
+                self.step()
+                done += 1
+                if max_windows and done >= max_windows:
+                    break
+            sts = [e.status() for e in self.engines]
+            for e, st in zip(self.engines, sts):
+                e.raise_on_error(st)
+            if all(st.finished for st in sts):
+                return True
+            if max_windows and done >= max_windows:
+                return False
+
+    def results(self) -> np.ndarray:
+        """Results of all components in ENGINE id order (use self.pm.orig_id to map back)."""
+        return np.concatenate([e.results() for e in self.engines], axis=0)
+
+    def close(self):
+        for e in self.engines:
+            e.close()
 
 
 def _as_tensor(torch, ptr: int, n_words: int, device):

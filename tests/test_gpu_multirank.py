@@ -1,0 +1,66 @@
+"""The multi-rank device path: partitions of a model stepped through outbox emission / ingest / gathered control words.
+On one GPU all ranks are stepped by one process (LocalMultiRankRunner); with >= 2 GPUs the same check runs as real
+NCCL ranks under torchrun (tests/multi_gpu_check.py)."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from sst_core_b200 import models
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _check_local(m, n_ranks, **opts):
+    from sst_core_b200.engine import LocalMultiRankRunner
+    ref = O.run_model(m)
+    r = LocalMultiRankRunner(m, n_ranks, **opts)
+    try:
+        r.setup()
+        assert r.run()
+        res = r.results()
+        sts = [e.status() for e in r.engines]
+    finally:
+        r.close()
+    got = np.zeros_like(res)
+    got[r.pm.orig_id] = res
+    bad = np.nonzero((got != ref.results).any(axis=1))[0]
+    assert bad.size == 0, f"{bad.size} components differ, first {bad[:5]}"
+    assert sum(s.events_delivered for s in sts) == ref.events
+    assert sum(s.clock_ticks for s in sts) == ref.ticks
+    assert all(s.end_time == ref.end_time for s in sts)
+
+
+@pytest.mark.parametrize("n_ranks", [2, 3, 8])
+def test_mesh_partitions_on_one_gpu(n_ranks):
+    _check_local(models.mesh_model(32, 24, stop_at="80ns", stats_enabled=True), n_ranks)
+
+
+@pytest.mark.parametrize("n_ranks", [2, 4])
+def test_phold_partitions_on_one_gpu(n_ranks):
+    m = models.phold_model(20, 20, stop_at="100ns", stats_enabled=True)
+    m.nocut_pairs = np.array([[0, 399], [5, 200]], dtype=np.uint32)  # non-contiguous no-cut groups: renumbering
+    _check_local(m, n_ranks, calendar_slots=16)
+
+
+def test_clockpop_partitions_on_one_gpu():
+    _check_local(models.clockpop_model(16, 16, stop_at="500ns", comm_freq=3, stats_enabled=True), 4)
+
+
+def test_real_multi_gpu_nccl_ranks():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (covered on one GPU by the LocalMultiRankRunner tests)")
+    n = 2 if n < 4 else 4
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29617", str(ROOT / "tests" / "multi_gpu_check.py")],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MULTI_GPU_OK" in r.stdout
