@@ -1193,8 +1193,8 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         sstb200_engine_destroy(e);
         return -1;
     }
-    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
-    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaStreamSynchronize(e->stream));
     *out = e;
     return 0;

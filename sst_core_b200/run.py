@@ -42,16 +42,19 @@ def simulate_distributed(m: wireup.WiredModel, **engine_opts):
     n, r = dist.get_world_size(), dist.get_rank()
     pm = partition_model(m, n)
     dev = torch.cuda.current_device()
-    stream = torch.cuda.current_stream().cuda_stream
-    e = Engine(pm, device=dev, rank=r, n_ranks=n, stream=stream, **engine_opts)
-    try:
-        e.setup()
-        DistributedRunner(e).run()
-        st = e.status()
-        e.raise_on_error(st)
-        return e.results(), st, pm
-    finally:
-        e.close()
+    # the engine's kernels and the NCCL collectives must be ordered on ONE stream: torch orders its collectives after
+    # the *current* stream, so make a dedicated stream current and hand the same stream to the engine
+    stream = torch.cuda.Stream(dev)
+    with torch.cuda.stream(stream):
+        e = Engine(pm, device=dev, rank=r, n_ranks=n, stream=stream.cuda_stream, **engine_opts)
+        try:
+            e.setup()
+            DistributedRunner(e).run()
+            st = e.status()
+            e.raise_on_error(st)
+            return e.results(), st, pm
+        finally:
+            e.close()
 
 
 def main(argv: Optional[list] = None) -> int:
