@@ -146,13 +146,18 @@ struct MeshElement
         MersenneDev rng { (uint32_t*)ctx.aux, s.mt_idx };
         uint32_t    r0, r1;
         rng.u32x2(r0, r1); // the two draws of RouteMessage::send, loads overlapped
-        uint32_t nextport = r0 % s.ngroups;
-        uint32_t cnt      = (uint32_t)((s.counts >> (8 * nextport)) & 0xFF);
-        uint32_t portnum  = r1 % cnt;
-        s.mt_idx          = rng.idx;
-        uint32_t base        = 0;
-        for ( uint32_t g = 0; g < nextport; ++g )
-            base += (uint32_t)((s.counts >> (8 * g)) & 0xFF);
+        // nextport = r0 % ports.size(); portnum = r1 % counts[nextport] (both draws are always made)
+        const uint32_t ng       = s.ngroups;
+        const uint32_t nextport = (ng & (ng - 1)) == 0 ? (r0 & (ng - 1)) : r0 % ng;
+        uint32_t       portnum = 0, base = nextport;
+        if ( s.counts != (0x0101010101010101ull >> (8 * (8 - ng))) ) { // not the one-link-per-port-group case
+            const uint32_t cnt = (uint32_t)((s.counts >> (8 * nextport)) & 0xFF);
+            portnum            = r1 % cnt;
+            base               = 0;
+            for ( uint32_t g = 0; g < nextport; ++g )
+                base += (uint32_t)((s.counts >> (8 * g)) & 0xFF);
+        }
+        s.mt_idx = rng.idx;
         ctx.send((int)(base + portnum), 0, payload);
         if ( ctx.stats_on ) s.mcnt.add(1);
     }

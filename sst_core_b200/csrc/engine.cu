@@ -78,6 +78,7 @@ struct Dev
     Ctrl*           ctrl;
     uint32_t        n_local, c0, nbins, W, cap, emax;
     uint32_t        lmax, uniform_nports; // link rows staged per block; ports per component when uniform (else 0)
+    uint32_t        uniform_shift;        // log2(uniform_nports) when it is a power of two, else 32
     uint32_t        P0, nport_local;
     uint32_t        rank, n_ranks;
     const uint32_t* rank_comp_begin; // [n_ranks+1] (device)
@@ -174,7 +175,7 @@ emit(const Dev& d, uint64_t k, uint64_t time, uint32_t dst_port, uint32_t dst_co
 }
 
 // Shared-memory view of one block's staged events.  Due events are staged here by phase 1; as a component consumes
-// its events the slots are recycled for the events it sends (out-staging), and phase 4 flushes them with
+// its events the slots are recycled for the events it sends (out-staging), and the owning warp flushes them with
 // warp-aggregated reservations.  Record layout per slot (4 x u32 [+ u64 payload]):
 //   staged-in : t = time - T, a = receiving port, b = sequence, c = comp<<16 | rank (sorting scratch)
 //   staged-out: t = arrival - T, a = receiving port, b = sequence, c = destination component
@@ -185,8 +186,6 @@ struct Stage
     uint32_t* b;
     uint32_t* c;
     uint64_t* pay;
-    uint32_t* overflow_ctr; // slots handed out beyond n_due
-    uint32_t  n_due, emax;
 };
 
 // What a handler sees of the core (BaseComponent / Link API subset)
@@ -205,9 +204,9 @@ struct CtxT
     uint32_t     sent;
     int          stats_on;
     const uint4* links; // this component's link row (shared memory when the block's rows were staged, else global)
-    // out-staging (STAGED only)
+    // out-staging (STAGED only): this component's consumed slots are seg[free_head .. free_tail)
     Stage           st;
-    const uint16_t* seg;       // this component's consumed slots are seg[free_head .. free_tail)
+    const uint16_t* seg;
     uint32_t        free_head, free_tail;
 
     __device__ __forceinline__ bool connected(int port) const { return links[port].x != SSTB200_NO_PEER; }
@@ -222,20 +221,14 @@ struct CtxT
         sent++;
         if ( STAGED ) {
             const uint64_t off = when - T;
-            if ( (off >> 32) == 0 ) {
-                uint32_t slot;
-                if ( free_head < free_tail )
-                    slot = seg[free_head++];
-                else
-                    slot = st.n_due + atomicAdd(st.overflow_ctr, 1u);
-                if ( slot < st.emax ) {
-                    st.t[slot] = (uint32_t)off;
-                    st.a[slot] = l.x;
-                    st.b[slot] = sq;
-                    st.c[slot] = l.y;
-                    if ( st.pay ) st.pay[slot] = payload;
-                    return;
-                }
+            if ( free_head < free_tail && (off >> 32) == 0 ) {
+                const uint32_t slot = seg[free_head++];
+                st.t[slot]          = (uint32_t)off;
+                st.a[slot]          = l.x;
+                st.b[slot]          = sq;
+                st.c[slot]          = l.y;
+                if ( st.pay ) st.pay[slot] = payload;
+                return;
             }
         }
         emit(d, k, when, l.x, l.y, sq, payload);
@@ -349,6 +342,13 @@ block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& total)
     return s_warp[warp] + inc - v;
 }
 
+// wrap-safe "key of a < key of b" for two staged events of one component: (time, port, sequence)
+__device__ __forceinline__ bool
+key_less(uint32_t ta, uint32_t da, uint32_t qa, uint32_t tb, uint32_t db, uint32_t qb)
+{
+    return (ta < tb) || (ta == tb && (da < db || (da == db && (int32_t)(qa - qb) < 0)));
+}
+
 // ---- one lookahead window for one block of 256 components
 template <bool PAYLOAD>
 __global__ void __launch_bounds__(BLOCK, 4)
@@ -363,49 +363,51 @@ dispatch_kernel(Dev d)
     const uint32_t w     = (uint32_t)ctrl->w; // < 2^31 (checked by the host)
     const uint32_t bin   = blockIdx.x;
     const uint32_t slot  = (uint32_t)(k % d.W);
+    const uint32_t slot1 = slot + 1 == d.W ? 0 : slot + 1; // where events due in the next window go
     const uint32_t tid   = threadIdx.x;
-    const uint32_t lc    = bin * BLOCK + tid;
-    const bool     valid = lc < d.n_local;
+    const uint32_t lane  = tid & 31;
 
     // shared-memory carve-up (host: engine_create computes the same sizes)
-    uint4*    s_link     = reinterpret_cast<uint4*>(smem_raw);                       // [lmax]
+    uint4*    s_link     = reinterpret_cast<uint4*>(smem_raw);                          // [lmax]
     uint64_t* s_pay      = reinterpret_cast<uint64_t*>(smem_raw + (size_t)d.lmax * 16); // [emax] (PAYLOAD only)
     uint8_t*  p          = reinterpret_cast<uint8_t*>(s_pay) + (PAYLOAD ? (size_t)d.emax * 8 : 0);
     uint32_t* s_time     = reinterpret_cast<uint32_t*>(p);
     uint32_t* s_dst      = s_time + d.emax;
     uint32_t* s_seq      = s_dst + d.emax;
     uint32_t* s_cr       = s_seq + d.emax;
-    uint32_t* s_port_off = s_cr + d.emax;                   // [BLOCK+1]
-    uint32_t* s_cnt      = s_port_off + BLOCK + 1;          // [BLOCK]
-    uint32_t* s_off      = s_cnt + BLOCK;                   // [BLOCK]
-    uint32_t* s_warp     = s_off + BLOCK;                   // [BLOCK/32+1]
-    uint32_t* s_misc     = s_warp + BLOCK / 32 + 1;         // [4]: 0 due events, 1 out-staging overflow slots
-    uint16_t* s_perm     = reinterpret_cast<uint16_t*>(s_misc + 4); // [emax]
+    uint32_t* s_port_off = s_cr + d.emax;           // [BLOCK+1]
+    uint32_t* s_cnt      = s_port_off + BLOCK + 1;  // [BLOCK]
+    uint32_t* s_off      = s_cnt + BLOCK;           // [BLOCK]
+    uint32_t* s_warp     = s_off + BLOCK;           // [BLOCK/32+1]
+    uint32_t* s_misc     = s_warp + BLOCK / 32 + 1; // [4]: 0 due events
+    uint32_t* s_hist     = s_misc + 4;              // [32] components per event-count bucket, then bucket fill
+    uint32_t* s_hbase    = s_hist + 32;             // [32]
+    uint16_t* s_perm     = reinterpret_cast<uint16_t*>(s_hbase + 32); // [emax] per-component segments
+    uint16_t* s_order    = s_perm + d.emax;                           // [BLOCK] thread -> component of the block
 
     // ---- prologue: everything here is independent global traffic issued back to back
     const uint32_t n_in = d.bin_count[slot * d.nbins + bin];
     {
-        s_port_off[tid] = d.port_off[lc <= d.n_local ? lc : d.n_local];
+        const uint32_t lc0 = bin * BLOCK + tid;
+        s_port_off[tid]    = d.port_off[lc0 <= d.n_local ? lc0 : d.n_local];
         if ( tid == 0 ) {
             const uint32_t e  = (bin + 1) * BLOCK;
             s_port_off[BLOCK] = d.port_off[e <= d.n_local ? e : d.n_local];
             s_misc[0]         = 0;
-            s_misc[1]         = 0;
         }
         s_cnt[tid] = 0;
-    }
-    uint32_t my_type = 0;
-    if ( valid ) {
-        my_type = d.comp_type[lc];
-        // element hook: start pulling the state line and the aux words the handlers will touch towards L2
-        with_element(my_type, [&](auto el) {
-            using E = decltype(el);
-            E::prefetch(d.state + (uint64_t)lc * d.state_stride, d.aux + (uint64_t)lc * d.aux_stride);
-        });
+        if ( tid < 32 ) s_hist[tid] = 0;
+        if ( lc0 < d.n_local ) {
+            // element hook: start pulling the state line and the aux words the handlers will touch towards L2
+            with_element(d.comp_type[lc0], [&](auto el) {
+                using E = decltype(el);
+                E::prefetch(d.state + (uint64_t)lc0 * d.state_stride, d.aux + (uint64_t)lc0 * d.aux_stride);
+            });
+        }
     }
     __syncthreads();
-    const uint32_t blk_port0  = s_port_off[0];
-    const uint32_t blk_nports = s_port_off[BLOCK] - blk_port0;
+    const uint32_t blk_port0     = s_port_off[0];
+    const uint32_t blk_nports    = s_port_off[BLOCK] - blk_port0;
     const bool     links_in_smem = blk_nports <= d.lmax;
     if ( links_in_smem ) {
         const uint4* src = d.link + (blk_port0 - d.P0);
@@ -424,7 +426,10 @@ dispatch_kernel(Dev d)
         const uint32_t dst = (uint32_t)(ds >> 32);
         // component of the receiving port: largest j with s_port_off[j] <= dst
         uint32_t lo;
-        if ( d.uniform_nports ) {
+        if ( d.uniform_shift < 32 ) {
+            lo = (dst - blk_port0) >> d.uniform_shift;
+        }
+        else if ( d.uniform_nports ) {
             lo = (dst - blk_port0) / d.uniform_nports;
         }
         else {
@@ -468,50 +473,75 @@ dispatch_kernel(Dev d)
         return; // uniform across the CTA
     }
 
-    // ---- phase 2: counting sort by component (warp-level scans), permutation into per-component segments
-    const uint32_t my_cnt = s_cnt[tid];
-    uint32_t       total;
-    const uint32_t my_off = block_exclusive_scan(my_cnt, s_warp, total);
-    s_off[tid]            = my_off;
+    // ---- phase 2: finish the sort in shared memory
+    // (a) counting sort by component: exclusive scan of the per-component counts (warp shuffles), scatter
+    {
+        const uint32_t cnt_c = s_cnt[tid];
+        uint32_t       total;
+        s_off[tid] = block_exclusive_scan(cnt_c, s_warp, total);
+        // (c, first half) bucket the block's components by how many events they got, busiest first, so that the
+        // 32 components a warp runs in phase 3 have (nearly) the same trip count
+        atomicAdd(&s_hist[31 - (cnt_c < 31 ? cnt_c : 31)], 1u);
+    }
     __syncthreads();
     for ( uint32_t e = tid; e < n_due; e += BLOCK ) {
-        const uint32_t cr          = s_cr[e];
+        const uint32_t cr                        = s_cr[e];
         s_perm[s_off[cr >> 16] + (cr & 0xFFFFu)] = (uint16_t)e;
+    }
+    if ( tid < 32 ) { // exclusive scan of the 32 buckets by one warp
+        const uint32_t v   = s_hist[tid];
+        uint32_t       inc = v;
+#pragma unroll
+        for ( int o = 1; o < 32; o <<= 1 ) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if ( lane >= (uint32_t)o ) inc += t;
+        }
+        s_hbase[tid] = inc - v;
+        s_hist[tid]  = 0; // reused as the bucket fill counter
+    }
+    __syncthreads();
+    // (c, second half) thread -> component assignment
+    {
+        const uint32_t cnt_c  = s_cnt[tid];
+        const uint32_t bucket = 31 - (cnt_c < 31 ? cnt_c : 31);
+        s_order[s_hbase[bucket] + atomicAdd(&s_hist[bucket], 1u)] = (uint16_t)tid;
     }
     __syncthreads();
 
-    // ---- phase 3: every thread orders its component's segment by (time, port, sequence) and runs the handlers,
-    // merged with the component's clock ticks; sends are staged in the slots the component has already consumed
-    uint32_t delivered = 0, ticks = 0, sent = 0, clocks_stopped = 0;
+    // ---- phase 3: thread t runs component s_order[t]: walks its segment in delivery order, merged with the
+    // component's clock ticks; sends are staged in the slots the component has already consumed
+    const uint32_t  c      = s_order[tid];
+    const uint32_t  lc     = bin * BLOCK + c;
+    const bool      valid  = lc < d.n_local;
+    const uint32_t  my_cnt = s_cnt[c];
+    uint16_t*       seg    = s_perm + s_off[c];
+    uint32_t        delivered = 0, ticks = 0, sent = 0, clocks_stopped = 0, n_staged = 0;
     if ( valid ) {
-        uint16_t* seg = s_perm + my_off;
-        for ( uint32_t a = 1; a < my_cnt; ++a ) { // insertion sort; segments are a handful of events
+        // (b) order inside the segment: (time, port, sequence).  Insertion sort by the owning thread; the lanes of a
+        // warp own components with (nearly) equal event counts, so the loops stay converged.
+        for ( uint32_t a = 1; a < my_cnt; ++a ) {
             const uint16_t ea = seg[a];
             const uint32_t ta = s_time[ea], da = s_dst[ea], qa = s_seq[ea];
             uint32_t       b  = a;
             while ( b > 0 ) {
                 const uint16_t eb = seg[b - 1];
-                const uint32_t tb = s_time[eb], db = s_dst[eb], qb = s_seq[eb];
-                const bool     gt = (tb > ta) || (tb == ta && (db > da || (db == da && (int32_t)(qb - qa) > 0)));
-                if ( !gt ) break;
+                if ( !key_less(ta, da, qa, s_time[eb], s_dst[eb], s_seq[eb]) ) break;
                 seg[b] = eb;
                 --b;
             }
             seg[b] = ea;
         }
-
         const uint64_t period    = d.clock_period[lc];
         uint64_t       next_tick = d.next_tick[lc];
         const bool     has_work  = my_cnt > 0 || next_tick < T_end;
         if ( has_work ) {
-            const uint32_t p0 = s_port_off[tid];
-            CtxT<true>     ctx { d, T, k, T, d.c0 + lc, p0, s_port_off[tid + 1] - p0,
+            const uint32_t p0 = s_port_off[c];
+            CtxT<true>     ctx { d, T, k, T, d.c0 + lc, p0, s_port_off[c + 1] - p0,
                                  d.aux + (uint64_t)lc * d.aux_stride, d.send_seq[lc], 0, d.stats_on,
                                  links_in_smem ? (const uint4*)(s_link + (p0 - blk_port0)) : d.link + (p0 - d.P0),
-                                 Stage { s_time, s_dst, s_seq, s_cr, PAYLOAD ? s_pay : nullptr, &s_misc[1], n_due, d.emax },
-                                 seg, 0, 0 };
+                                 Stage { s_time, s_dst, s_seq, s_cr, PAYLOAD ? s_pay : nullptr }, seg, 0, 0 };
             uint32_t       dseq = d.deliv_seq ? d.deliv_seq[lc] : 0;
-            with_element(my_type, [&](auto el) {
+            with_element(d.comp_type[lc], [&](auto el) {
                 using E = decltype(el);
                 typename E::State s;
                 load_state(s, d.state + (uint64_t)lc * d.state_stride);
@@ -536,8 +566,7 @@ dispatch_kernel(Dev d)
                     const uint32_t e    = seg[i++];
                     const uint32_t port = s_dst[e] - ctx.port0;
                     uint64_t       pl   = PAYLOAD ? s_pay[e] : 0;
-                    s_dst[e]            = SSTB200_NO_PEER; // slot consumed: free for out-staging
-                    ctx.free_tail       = i;
+                    ctx.free_tail       = i; // slot e is consumed: free for out-staging
                     ctx.now             = ev_t;
                     if ( d.trace_cap ) {
                         const unsigned long long tp = atomicAdd(&ctrl->trace_n, 1ull);
@@ -558,74 +587,97 @@ dispatch_kernel(Dev d)
             d.send_seq[lc]  = ctx.seq;
             d.next_tick[lc] = next_tick;
             if ( d.deliv_seq ) d.deliv_seq[lc] = dseq;
-            sent = ctx.sent;
+            sent     = ctx.sent;
+            n_staged = ctx.free_head;
         }
     }
-    __syncthreads();
+    __syncwarp();
 
-    // ---- phase 4: flush the staged sends.  Lanes of a warp that target the same (window slot, destination block)
-    // reserve their calendar slots with ONE atomic (match.any), then write their records side by side.
+    // ---- phase 4: each warp flushes what its 32 components staged (slots seg[0 .. n_staged)).  Lanes that target
+    // the same (window slot, destination block) reserve their calendar slots with ONE atomic (match.any) and write
+    // their records side by side.  No CTA-wide barrier: a warp that is done leaves.
     {
-        uint32_t n_stage = n_due + s_misc[1];
-        if ( n_stage > d.emax ) n_stage = d.emax;
-        const uint32_t lane = tid & 31;
-        for ( uint32_t base = 0; base < n_stage; base += BLOCK ) {
-            const uint32_t e      = base + tid;
-            const bool     active = e < n_stage && s_dst[e] != SSTB200_NO_PEER;
-            uint32_t       key = 0xFFFFFFFFu, dcomp = 0, dt = 0;
-            bool           remote = false;
-            if ( active ) {
-                dcomp = s_cr[e];
-                dt    = s_time[e];
-                if ( d.n_ranks > 1 && (dcomp < d.c0 || dcomp >= d.c0 + d.n_local) ) {
-                    remote = true;
-                    uint32_t r = 0;
-                    while ( r + 1 < d.n_ranks && dcomp >= d.rank_comp_begin[r + 1] )
-                        ++r;
-                    key = 0x80000000u | r;
-                }
-                else if ( dt < w ) {
-                    raise_error(d, ERR_TIME_FAULT, T + dt, T, dcomp); // a send violated the lookahead
-                    key = 0xFFFFFFFEu;
-                }
-                else {
-                    uint32_t dk = dt < 2 * w ? 1u : dt / w;
-                    if ( dk > d.W - 1 ) dk = d.W - 1;
-                    key = (uint32_t)((k + dk) % d.W) * d.nbins + (dcomp - d.c0) / BLOCK;
-                }
-            }
-            const uint32_t peers  = __match_any_sync(0xffffffffu, key);
-            const uint32_t leader = __ffs(peers) - 1;
-            const uint32_t rank   = __popc(peers & ((1u << lane) - 1));
-            unsigned long long pos0 = 0;
-            if ( active && key < 0xFFFFFFFEu && lane == leader ) {
-                if ( remote )
-                    pos0 = atomicAdd(&d.outbox[(uint64_t)(key & 0x7FFFFFFFu) * d.xwords], (unsigned long long)__popc(peers));
-                else
-                    pos0 = atomicAdd(&d.bin_count[key], (uint32_t)__popc(peers));
-            }
-            pos0 = __shfl_sync(0xffffffffu, pos0, leader);
-            if ( active && key < 0xFFFFFFFEu ) {
-                const unsigned long long pos = pos0 + rank;
-                const uint64_t           tm  = T + dt;
-                const uint64_t           ds  = ((uint64_t)s_dst[e] << 32) | s_seq[e];
-                if ( remote ) {
-                    if ( pos >= d.outbox_cap ) {
-                        raise_error(d, ERR_OUTBOX_OVERFLOW, key & 0x7FFFFFFFu, pos, d.outbox_cap);
+        uint32_t max_staged = n_staged;
+#pragma unroll
+        for ( int o = 16; o > 0; o >>= 1 )
+            max_staged = max(max_staged, __shfl_xor_sync(0xffffffffu, max_staged, o));
+        constexpr int FL = 4; // records in flight per lane: the FL reservations are issued before any is consumed
+        for ( uint32_t j0 = 0; j0 < max_staged; j0 += FL ) {
+            uint32_t           ev[FL], key[FL], rank[FL], dtv[FL];
+            unsigned long long pos0[FL];
+            uint32_t           leaderv[FL];
+#pragma unroll
+            for ( int u = 0; u < FL; ++u ) {
+                const uint32_t j      = j0 + u;
+                const bool     active = j < n_staged;
+                const uint32_t e      = active ? seg[j] : 0;
+                uint32_t       ky     = 0xFFFFFFFFu;
+                uint32_t       dt     = 0;
+                if ( active ) {
+                    const uint32_t dcomp = s_cr[e];
+                    dt                   = s_time[e];
+                    if ( d.n_ranks > 1 && (dcomp < d.c0 || dcomp >= d.c0 + d.n_local) ) {
+                        uint32_t r = 0;
+                        while ( r + 1 < d.n_ranks && dcomp >= d.rank_comp_begin[r + 1] )
+                            ++r;
+                        ky = 0x80000000u | r;
+                    }
+                    else if ( dt < w ) {
+                        raise_error(d, ERR_TIME_FAULT, T + dt, T, dcomp); // a send violated the lookahead
+                        ky = 0xFFFFFFFEu;
                     }
                     else {
-                        unsigned long long* rec = d.outbox + (uint64_t)(key & 0x7FFFFFFFu) * d.xwords + 1 + pos * 4;
+                        uint32_t sl = slot1;
+                        if ( dt >= 2 * w ) {
+                            uint32_t dk = dt / w;
+                            if ( dk > d.W - 1 ) dk = d.W - 1; // beyond the horizon: parked in the farthest slot
+                            sl = (uint32_t)((slot + dk) % d.W);
+                        }
+                        ky = sl * d.nbins + ((dcomp - d.c0) >> 8);
+                    }
+                }
+                const uint32_t peers = __match_any_sync(0xffffffffu, ky);
+                leaderv[u]           = __ffs(peers) - 1;
+                rank[u]              = __popc(peers & ((1u << lane) - 1));
+                ev[u]                = e;
+                key[u]               = ky;
+                dtv[u]               = dt;
+                pos0[u]              = 0;
+                if ( ky < 0xFFFFFFFEu && lane == leaderv[u] ) {
+                    if ( ky & 0x80000000u )
+                        pos0[u] = atomicAdd(&d.outbox[(uint64_t)(ky & 0x7FFFFFFFu) * d.xwords],
+                            (unsigned long long)__popc(peers));
+                    else
+                        pos0[u] = atomicAdd(&d.bin_count[ky], (uint32_t)__popc(peers));
+                }
+            }
+#pragma unroll
+            for ( int u = 0; u < FL; ++u ) {
+                const unsigned long long base = __shfl_sync(0xffffffffu, pos0[u], leaderv[u]);
+                const uint32_t           ky   = key[u];
+                if ( ky >= 0xFFFFFFFEu ) continue;
+                const uint32_t           e   = ev[u];
+                const unsigned long long pos = base + rank[u];
+                const uint64_t           tm  = T + dtv[u];
+                const uint64_t           ds  = ((uint64_t)s_dst[e] << 32) | s_seq[e];
+                if ( ky & 0x80000000u ) {
+                    const uint32_t r = ky & 0x7FFFFFFFu;
+                    if ( pos >= d.outbox_cap ) {
+                        raise_error(d, ERR_OUTBOX_OVERFLOW, r, pos, d.outbox_cap);
+                    }
+                    else {
+                        unsigned long long* rec = d.outbox + (uint64_t)r * d.xwords + 1 + pos * 4;
                         rec[0]                  = tm;
                         rec[1]                  = ds;
                         rec[2]                  = PAYLOAD ? s_pay[e] : 0;
-                        rec[3]                  = dcomp;
+                        rec[3]                  = s_cr[e];
                     }
                 }
                 else if ( pos >= d.cap ) {
-                    raise_error(d, ERR_BIN_OVERFLOW, key / d.nbins, key % d.nbins, pos);
+                    raise_error(d, ERR_BIN_OVERFLOW, ky / d.nbins, ky % d.nbins, pos);
                 }
                 else {
-                    const uint64_t off = (uint64_t)key * d.cap + pos;
+                    const uint64_t off = (uint64_t)ky * d.cap + pos;
                     d.ev_time[off]     = tm;
                     d.ev_dst_seq[off]  = ds;
                     if ( PAYLOAD ) d.ev_payload[off] = s_pay[e];
@@ -645,7 +697,7 @@ dispatch_kernel(Dev d)
             v3 += __shfl_down_sync(0xffffffffu, v3, o);
             v4 += __shfl_down_sync(0xffffffffu, v4, o);
         }
-        if ( (tid & 31) == 0 ) {
+        if ( lane == 0 ) {
             if ( v0 ) atomicAdd(&ctrl->events_delivered, (unsigned long long)v0);
             if ( v1 ) atomicAdd(&ctrl->clock_ticks, (unsigned long long)v1);
             if ( v2 ) atomicAdd(&ctrl->events_sent, (unsigned long long)v2);
@@ -655,6 +707,7 @@ dispatch_kernel(Dev d)
         }
     }
     if ( tid == 0 ) {
+        // every thread of the CTA finished reading this bin before the phase-1 barrier
         d.bin_count[slot * d.nbins + bin] = 0;
         if ( n_in > ctrl->max_bin_fill ) atomicMax(&ctrl->max_bin_fill, (unsigned long long)n_in);
         if ( n_due > ctrl->max_due ) atomicMax(&ctrl->max_due, (unsigned long long)n_due);
@@ -1133,6 +1186,12 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
             if ( m->port_off[c + 1] - m->port_off[c] != uni ) uni = 0;
         d.lmax           = max_blk <= 2048 ? max_blk : 0;
         d.uniform_nports = uni;
+        d.uniform_shift  = 32;
+        if ( uni && (uni & (uni - 1)) == 0 ) {
+            d.uniform_shift = 0;
+            while ( (1u << d.uniform_shift) < uni )
+                ++d.uniform_shift;
+        }
     }
     d.state_stride = (state_stride + 15u) & ~15u;
     d.aux_stride   = (aux_stride + 31u) & ~31u;
@@ -1187,7 +1246,8 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     CUDA_OK(cudaMemcpyAsync(d.ctrl, e->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, e->stream));
 
     e->smem_bytes = (size_t)d.lmax * 16 + (size_t)d.emax * (has_payload ? 8 : 0) + (size_t)d.emax * 16 +
-                    (size_t)(BLOCK + 1 + BLOCK + BLOCK + BLOCK / 32 + 1 + 4) * 4 + (size_t)d.emax * 2 + 16;
+                    (size_t)(BLOCK + 1 + BLOCK + BLOCK + BLOCK / 32 + 1 + 4 + 32 + 32) * 4 + (size_t)d.emax * 2 +
+                    (size_t)BLOCK * 2 + 16;
     if ( e->smem_bytes > 227 * 1024 ) {
         set_error("engine_create: smem_events too large for 227 KB of shared memory");
         sstb200_engine_destroy(e);
