@@ -96,13 +96,24 @@ struct MeshElement
     static constexpr bool        HAS_PAYLOAD  = false;
     struct State
     {
+        // stored part (STORED_BYTES): what changes while the simulation runs
         int32_t               message_count;
         uint32_t              mt_idx;
+        Accumulator<uint64_t> mcnt; // RouteMessage "msg_count"
+        // construction constants (written once by construct())
         uint32_t              ngroups;
         uint32_t              mod;
         uint64_t              counts; // links per port group, 8 bits each
-        Accumulator<uint64_t> mcnt;   // RouteMessage "msg_count"
+        // register-only scratch, valid inside one window (never read from / needed in memory)
+        MtPairCache           cache;
     };
+    static constexpr uint32_t STORED_BYTES  = 48; // written back every window
+    static constexpr uint32_t PERSIST_BYTES = 64; // lives in HBM (stored part + construction constants)
+    template <class Ctx>
+    __device__ static void beginWindow(Ctx&, State& s)
+    {
+        s.cache.valid = 0;
+    }
     // dispatch prologue hook: pull towards L2 the MT19937 words the next handful of draws will read
     // (words idx.. and idx+397.. mod 624), so that the per-event draws hit L2 instead of paying an HBM round trip each
     __device__ static void prefetch(const uint8_t* state, const uint8_t* aux)
@@ -143,9 +154,8 @@ struct MeshElement
     __device__ static void handleEvent(Ctx& ctx, State& s, int /*port*/, uint64_t& payload)
     {
         s.message_count++;
-        MersenneDev rng { (uint32_t*)ctx.aux, s.mt_idx };
-        uint32_t    r0, r1;
-        rng.u32x2(r0, r1); // the two draws of RouteMessage::send, loads overlapped
+        uint32_t r0, r1; // the two draws of RouteMessage::send
+        mt_u32x2_cached((uint32_t*)ctx.aux, s.mt_idx, s.cache, r0, r1);
         // nextport = r0 % ports.size(); portnum = r1 % counts[nextport] (both draws are always made)
         const uint32_t ng       = s.ngroups;
         const uint32_t nextport = (ng & (ng - 1)) == 0 ? (r0 & (ng - 1)) : r0 % ng;
@@ -157,7 +167,6 @@ struct MeshElement
             for ( uint32_t g = 0; g < nextport; ++g )
                 base += (uint32_t)((s.counts >> (8 * g)) & 0xFF);
         }
-        s.mt_idx = rng.idx;
         ctx.send((int)(base + portnum), 0, payload);
         if ( ctx.stats_on ) s.mcnt.add(1);
     }
@@ -188,6 +197,11 @@ struct PholdElement
         uint32_t              dmod, init;
         Accumulator<uint64_t> delay;
     };
+    static constexpr uint32_t STORED_BYTES  = sizeof(State);
+    static constexpr uint32_t PERSIST_BYTES = sizeof(State);
+    template <class Ctx>
+    __device__ static void beginWindow(Ctx&, State&)
+    {}
     __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
     template <class Ctx>
     __device__ static void construct(Ctx&, State& s, const int64_t* p)
@@ -247,6 +261,11 @@ struct ClockNodeElement
         int32_t              commFreq;
         Accumulator<int32_t> count[4];
     };
+    static constexpr uint32_t STORED_BYTES  = sizeof(State);
+    static constexpr uint32_t PERSIST_BYTES = sizeof(State);
+    template <class Ctx>
+    __device__ static void beginWindow(Ctx&, State&)
+    {}
     __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
     template <class Ctx>
     __device__ static void construct(Ctx&, State& s, const int64_t* p)
@@ -308,6 +327,11 @@ struct RngElement
         uint64_t hash;
         uint32_t kind, a, b, c, d; // generator state: mersenne idx in a; marsaglia z,w in a,b; xorshift x,y,z,w
     };
+    static constexpr uint32_t STORED_BYTES  = sizeof(State);
+    static constexpr uint32_t PERSIST_BYTES = sizeof(State);
+    template <class Ctx>
+    __device__ static void beginWindow(Ctx&, State&)
+    {}
     __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
     template <class Ctx>
     __device__ static void construct(Ctx& ctx, State& s, const int64_t* p)

@@ -262,26 +262,31 @@ with_element(uint32_t type, F&& f)
     }
 }
 
+// Element state moves between HBM and registers in 16-byte pieces (state_stride is a multiple of 16).  `bytes` may be
+// a prefix of the struct: construction constants are loaded but never written back, register-only scratch at the end
+// of a State is neither loaded nor stored.
 template <class S>
 __device__ __forceinline__ void
-load_state(S& s, const uint8_t* p)
+load_state(S& s, const uint8_t* p, uint32_t bytes)
 {
     static_assert(sizeof(S) % 8 == 0, "element State must be a multiple of 8 bytes");
-    const uint64_t* src = reinterpret_cast<const uint64_t*>(p);
-    uint64_t*       dst = reinterpret_cast<uint64_t*>(&s);
+    const uint4* src = reinterpret_cast<const uint4*>(p);
+    uint4        tmp[(sizeof(S) + 15) / 16];
 #pragma unroll
-    for ( int i = 0; i < (int)(sizeof(S) / 8); ++i )
-        dst[i] = src[i];
+    for ( int i = 0; i < (int)((sizeof(S) + 15) / 16); ++i )
+        if ( (uint32_t)i * 16 < bytes ) tmp[i] = src[i];
+    memcpy(&s, tmp, sizeof(S));
 }
 template <class S>
 __device__ __forceinline__ void
-store_state(const S& s, uint8_t* p)
+store_state(const S& s, uint8_t* p, uint32_t bytes)
 {
-    uint64_t*       dst = reinterpret_cast<uint64_t*>(p);
-    const uint64_t* src = reinterpret_cast<const uint64_t*>(&s);
+    uint4* dst = reinterpret_cast<uint4*>(p);
+    uint4  tmp[(sizeof(S) + 15) / 16];
+    memcpy(tmp, &s, sizeof(S));
 #pragma unroll
-    for ( int i = 0; i < (int)(sizeof(S) / 8); ++i )
-        dst[i] = src[i];
+    for ( int i = 0; i < (int)((sizeof(S) + 15) / 16); ++i )
+        if ( (uint32_t)i * 16 < bytes ) dst[i] = tmp[i];
 }
 
 // ---- construct + setup(): performWireUp (simulation.cc:824-859) and setup() (simulation.cc:969-987)
@@ -301,7 +306,7 @@ setup_kernel(Dev d)
         typename E::State s;
         E::construct(ctx, s, d.comp_param + (uint64_t)lc * NPARAM);
         E::setup(ctx, s);
-        store_state(s, d.state + (uint64_t)lc * d.state_stride);
+        store_state(s, d.state + (uint64_t)lc * d.state_stride, E::PERSIST_BYTES);
     });
     d.send_seq[lc] = ctx.seq;
     if ( d.deliv_seq ) d.deliv_seq[lc] = 0;
@@ -544,7 +549,8 @@ dispatch_kernel(Dev d)
             with_element(d.comp_type[lc], [&](auto el) {
                 using E = decltype(el);
                 typename E::State s;
-                load_state(s, d.state + (uint64_t)lc * d.state_stride);
+                load_state(s, d.state + (uint64_t)lc * d.state_stride, E::PERSIST_BYTES);
+                E::beginWindow(ctx, s);
                 uint64_t cycle = (next_tick != TIME_NEVER && period) ? next_tick / period : 0;
                 uint32_t i     = 0;
                 for ( ;; ) {
@@ -582,7 +588,7 @@ dispatch_kernel(Dev d)
                     E::handleEvent(ctx, s, (int)port, pl);
                     delivered++;
                 }
-                store_state(s, d.state + (uint64_t)lc * d.state_stride);
+                store_state(s, d.state + (uint64_t)lc * d.state_stride, E::STORED_BYTES);
             });
             d.send_seq[lc]  = ctx.seq;
             d.next_tick[lc] = next_tick;
@@ -804,7 +810,7 @@ results_kernel(Dev d, uint64_t* out)
     with_element(d.comp_type[lc], [&](auto el) {
         using E = decltype(el);
         typename E::State s;
-        load_state(s, d.state + (uint64_t)lc * d.state_stride);
+        load_state(s, d.state + (uint64_t)lc * d.state_stride, E::PERSIST_BYTES);
         E::results(s, r);
     });
 #pragma unroll
@@ -945,13 +951,13 @@ rng_dist_kernel(int dist, const double* params, int np, int kind, uint64_t s1, u
 
 // ================================================================================================ host side
 static const ElementInfo kElements[] = {
-    { TYPE_MESH, MeshElement::ELI_NAME, (uint32_t)sizeof(MeshElement::State), MeshElement::AUX_BYTES,
+    { TYPE_MESH, MeshElement::ELI_NAME, MeshElement::PERSIST_BYTES, MeshElement::AUX_BYTES,
         MeshElement::HAS_PAYLOAD, "message_mesh enclosing component with message_port/port_slot/route_message" },
-    { TYPE_PHOLD, PholdElement::ELI_NAME, (uint32_t)sizeof(PholdElement::State), PholdElement::AUX_BYTES,
+    { TYPE_PHOLD, PholdElement::ELI_NAME, PholdElement::PERSIST_BYTES, PholdElement::AUX_BYTES,
         PholdElement::HAS_PAYLOAD, "PHOLD-style node, integer delays, 8-byte payload" },
-    { TYPE_CLOCKNODE, ClockNodeElement::ELI_NAME, (uint32_t)sizeof(ClockNodeElement::State),
+    { TYPE_CLOCKNODE, ClockNodeElement::ELI_NAME, ClockNodeElement::PERSIST_BYTES,
         ClockNodeElement::AUX_BYTES, ClockNodeElement::HAS_PAYLOAD, "clock-driven node (coreTestComponent style)" },
-    { TYPE_RNGCOMP, RngElement::ELI_NAME, (uint32_t)sizeof(RngElement::State), RngElement::AUX_BYTES,
+    { TYPE_RNGCOMP, RngElement::ELI_NAME, RngElement::PERSIST_BYTES, RngElement::AUX_BYTES,
         RngElement::HAS_PAYLOAD, "coreTestRNGComponent: 1 GHz clock drawing from an SST::RNG generator" },
 };
 constexpr int kNumElements = (int)(sizeof(kElements) / sizeof(kElements[0]));

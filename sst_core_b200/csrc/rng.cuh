@@ -19,6 +19,14 @@
 //                 glibc within 1e-9 relative, not bit-exact -- SURVEY.md section 7 "libm parity").
 #pragma once
 #include <cstdint>
+#if !defined(__CUDACC__)
+struct uint2
+{
+    uint32_t x, y;
+};
+#else
+#include <vector_types.h>
+#endif
 
 namespace sstb200 {
 
@@ -105,6 +113,55 @@ struct MersenneDev
         return d;
     }
 };
+
+// Register-resident read-ahead for a run of paired draws at EVEN index (624 is even, so parity never changes while a
+// component only draws in pairs).  The words a pair needs are mt[i], mt[i+1], mt[i+2] and mt[i+397], mt[i+398]; with
+// 8-byte-aligned chunks C_j = (mt[2j], mt[2j+1]) that is C_j + first word of C_j+1, and second word of C_j+198 +
+// first word of C_j+199.  Keeping C_j and the second word of the last b-chunk from the previous pair, one pair costs
+// two 8-byte loads and one 8-byte store instead of five 4-byte loads and two 4-byte stores.  Reading one pair early is
+// safe: a pair writes only mt[i], mt[i+1], and i+2, i+3, i+399 are never congruent to i or i+1 mod 624.
+struct MtPairCache
+{
+    uint32_t a0, a1, b0, valid;
+};
+
+SSTB_HD void
+mt_u32x2_cached(uint32_t* mt, uint32_t& idx, MtPairCache& c, uint32_t& r0, uint32_t& r1)
+{
+    const uint32_t i = idx;
+    if ( (i & 1u) != 0 ) { // odd position: plain path
+        c.valid = 0;
+        MersenneDev g { mt, i };
+        g.u32x2(r0, r1);
+        idx = g.idx;
+        return;
+    }
+    const uint32_t i2  = (i + 2 == MT_N) ? 0u : i + 2;                    // even
+    const uint32_t im  = (i + MT_M >= MT_N) ? i + MT_M - MT_N : i + MT_M; // odd
+    const uint32_t im1 = (im + 1 == MT_N) ? 0u : im + 1;                  // even
+    if ( !c.valid ) {
+        const uint2 ca = *reinterpret_cast<const uint2*>(mt + i);
+        c.a0           = ca.x;
+        c.a1           = ca.y;
+        c.b0           = mt[im];
+    }
+    const uint2    na = *reinterpret_cast<const uint2*>(mt + i2);  // (mt[i+2], mt[i+3])
+    const uint2    nb = *reinterpret_cast<const uint2*>(mt + im1); // (mt[im+1], mt[im+2])
+    const uint32_t y0 = (c.a0 & 0x80000000u) + (c.a1 & 0x7fffffffu);
+    uint32_t       v0 = c.b0 ^ (y0 >> 1);
+    if ( y0 & 1u ) v0 ^= 2567483615u;
+    const uint32_t y1 = (c.a1 & 0x80000000u) + (na.x & 0x7fffffffu);
+    uint32_t       v1 = nb.x ^ (y1 >> 1);
+    if ( y1 & 1u ) v1 ^= 2567483615u;
+    *reinterpret_cast<uint2*>(mt + i) = uint2 { v0, v1 };
+    c.a0    = na.x;
+    c.a1    = na.y;
+    c.b0    = nb.y;
+    c.valid = 1;
+    idx     = i2;
+    r0      = mt_temper(v0);
+    r1      = mt_temper(v1);
+}
 
 struct MarsagliaDev
 {

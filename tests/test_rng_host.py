@@ -41,6 +41,15 @@ def test_paired_draw_equals_two_single_draws(drv, lead):
     assert np.array_equal(out, ref)
 
 
+@pytest.mark.parametrize("lead", [0, 1, 2, 4, 226, 227, 620, 622, 623, 624])
+def test_cached_paired_draw_equals_reference_stream(drv, lead):
+    n = 624 * 6 + 11
+    ref, _ = O.rng_u32_stream(0, 7000 + lead, 0, n)
+    out = np.zeros(n, dtype=np.uint32)
+    drv.dev_mt_stream(7000 + lead, 3, lead, n, out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out, ref)
+
+
 def test_marsaglia_and_xorshift(drv):
     n = 5000
     ref, _ = O.rng_u32_stream(1, 1053, 1447, n)
