@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--x", type=int, default=0)
     ap.add_argument("--y", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--smem-events", type=int, default=0, help="override the staging capacity (tuning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-size", type=int, default=256, help="reference sample: S x S mesh")
     ap.add_argument("--cpu-ns", type=int, default=100, help="reference sample: simulated ns")
@@ -186,6 +187,8 @@ def build_model(a, windows):
         m = models.phold_model(x, y, stop_at=f"{stop_ns}ns", verbose=0, stats_enabled=True)
         opts = dict(calendar_slots=16, bin_capacity=2560, smem_events=2560)
         name = f"PHOLD {x}x{y} torus, 16 events/component, delay u32%8000 ps, XORShiftRNG(id+1)"
+    if a.smem_events:
+        opts["smem_events"] = a.smem_events
     return m, opts, name
 
 

@@ -1,6 +1,7 @@
 """Build libsstb200.so (sm_100a) in-tree with nvcc.  `python -m sst_core_b200.build [--force]`."""
 from __future__ import annotations
 
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -20,7 +21,8 @@ NVCC_FLAGS = [
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and LIB.exists() and all(LIB.stat().st_mtime >= d.stat().st_mtime for d in DEPS):
         return LIB
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", str(LIB), *map(str, SOURCES)]
+    extra = os.environ.get("SSTB200_NVCC_EXTRA", "").split()  # experiments, e.g. -DSSTB200_MIN_BLOCKS=5
+    cmd = ["nvcc", *NVCC_FLAGS, *extra, "-o", str(LIB), *map(str, SOURCES)]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

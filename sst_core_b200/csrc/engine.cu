@@ -22,6 +22,7 @@
 #include "../../include/sstb200.h"
 #include "components.cuh"
 
+#include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -356,7 +357,10 @@ key_less(uint32_t ta, uint32_t da, uint32_t qa, uint32_t tb, uint32_t db, uint32
 
 // ---- one lookahead window for one block of 256 components
 template <bool PAYLOAD>
-__global__ void __launch_bounds__(BLOCK, 4)
+#ifndef SSTB200_MIN_BLOCKS
+#define SSTB200_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(BLOCK, SSTB200_MIN_BLOCKS)
 dispatch_kernel(Dev d)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -390,8 +394,13 @@ dispatch_kernel(Dev d)
     uint16_t* s_perm     = reinterpret_cast<uint16_t*>(s_hbase + 32); // [emax] per-component segments
     uint16_t* s_order    = s_perm + d.emax;                           // [BLOCK] thread -> component of the block
 
-    // ---- prologue: everything here is independent global traffic issued back to back
-    const uint32_t n_in = d.bin_count[slot * d.nbins + bin];
+    // ---- prologue: everything here is independent global traffic issued back to back.  The first 256 records of the
+    // bin are loaded before its fill count is known (the slots exist; what is past the count is ignored).
+    const uint32_t n_in     = d.bin_count[slot * d.nbins + bin];
+    const uint64_t t_first  = d.ev_time[(uint64_t)(slot * d.nbins + bin) * d.cap + tid];
+    const uint64_t ds_first = d.ev_dst_seq[(uint64_t)(slot * d.nbins + bin) * d.cap + tid];
+    uint64_t       pl_first = 0;
+    if ( PAYLOAD ) pl_first = d.ev_payload[(uint64_t)(slot * d.nbins + bin) * d.cap + tid];
     {
         const uint32_t lc0 = bin * BLOCK + tid;
         s_port_off[tid]    = d.port_off[lc0 <= d.n_local ? lc0 : d.n_local];
@@ -414,20 +423,17 @@ dispatch_kernel(Dev d)
     const uint32_t blk_port0     = s_port_off[0];
     const uint32_t blk_nports    = s_port_off[BLOCK] - blk_port0;
     const bool     links_in_smem = blk_nports <= d.lmax;
-    if ( links_in_smem ) {
+    if ( links_in_smem ) { // asynchronous copy (LDGSTS): nobody waits for the rows until phase 3
         const uint4* src = d.link + (blk_port0 - d.P0);
         for ( uint32_t i = tid; i < blk_nports; i += BLOCK )
-            s_link[i] = __ldg(&src[i]);
+            __pipeline_memcpy_async(&s_link[i], &src[i], 16);
     }
+    __pipeline_commit();
 
     // ---- phase 1: load the bin; stage due events in shared memory, re-bin the ones that are not due yet
     uint32_t       dropped  = 0;
     const uint64_t bin_base = (uint64_t)(slot * d.nbins + bin) * d.cap;
-    for ( uint32_t i = tid; i < n_in; i += BLOCK ) {
-        const uint64_t t  = d.ev_time[bin_base + i];
-        const uint64_t ds = d.ev_dst_seq[bin_base + i];
-        uint64_t       pl = 0;
-        if ( PAYLOAD ) pl = d.ev_payload[bin_base + i];
+    auto           classify = [&](uint64_t t, uint64_t ds, uint64_t pl) {
         const uint32_t dst = (uint32_t)(ds >> 32);
         // component of the receiving port: largest j with s_port_off[j] <= dst
         uint32_t lo;
@@ -470,7 +476,16 @@ dispatch_kernel(Dev d)
                 if ( PAYLOAD ) s_pay[e] = pl;
             }
         }
+    };
+    if ( tid < n_in ) classify(t_first, ds_first, pl_first);
+    for ( uint32_t i = tid + BLOCK; i < n_in; i += BLOCK ) {
+        const uint64_t t  = d.ev_time[bin_base + i];
+        const uint64_t ds = d.ev_dst_seq[bin_base + i];
+        uint64_t       pl = 0;
+        if ( PAYLOAD ) pl = d.ev_payload[bin_base + i];
+        classify(t, ds, pl);
     }
+    __pipeline_wait_prior(0);
     __syncthreads();
     const uint32_t n_due = s_misc[0];
     if ( n_due > d.emax ) {
@@ -1120,6 +1135,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     if ( d.nbins == 0 ) d.nbins = 1;
     d.W       = o->calendar_slots >= 2 ? o->calendar_slots : 2;
     d.cap     = o->bin_capacity ? o->bin_capacity : 8 * BLOCK;
+    if ( d.cap < BLOCK ) d.cap = BLOCK; // the dispatch prologue reads the first BLOCK slots of a bin unconditionally
     d.emax    = o->smem_events ? o->smem_events : 8 * BLOCK;
     if ( d.emax > 32768 ) d.emax = 32768;
     d.stats_on = m->stats_enabled;

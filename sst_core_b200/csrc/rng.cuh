@@ -116,14 +116,25 @@ struct MersenneDev
 
 // Register-resident read-ahead for a run of paired draws at EVEN index (624 is even, so parity never changes while a
 // component only draws in pairs).  The words a pair needs are mt[i], mt[i+1], mt[i+2] and mt[i+397], mt[i+398]; with
-// 8-byte-aligned chunks C_j = (mt[2j], mt[2j+1]) that is C_j + first word of C_j+1, and second word of C_j+198 +
-// first word of C_j+199.  Keeping C_j and the second word of the last b-chunk from the previous pair, one pair costs
-// two 8-byte loads and one 8-byte store instead of five 4-byte loads and two 4-byte stores.  Reading one pair early is
-// safe: a pair writes only mt[i], mt[i+1], and i+2, i+3, i+399 are never congruent to i or i+1 mod 624.
+// 8-byte-aligned chunks C_j = (mt[2j], mt[2j+1]) that is C_j + first word of C_j+1, and second word of the chunk
+// holding mt[i+397] + first word of E_j = (mt[i+398], mt[i+399]).  The cache holds C_j, C_j+1, that second word and
+// E_j, all loaded during EARLIER pairs: a pair is computed from registers only, then the two 8-byte loads for the
+// pair after next are issued and are not waited for until they are needed -- one iteration of the handler loop later.
+// Per pair: two 8-byte loads + one 8-byte store (instead of five 4-byte loads + two 4-byte stores), off the
+// critical path.  Reading up to two pairs early is safe: pairs j and j+1 write only mt[i..i+3], and the words read
+// early (mt[i+4], mt[i+5], mt[i+400], mt[i+401]) are never congruent to those mod 624.
 struct MtPairCache
 {
-    uint32_t a0, a1, b0, valid;
+    uint32_t a0, a1, a2, a3; // C_j, C_j+1
+    uint32_t b0, b1, b2;     // mt[i+397]; E_j = (mt[i+398], mt[i+399])
+    uint32_t valid;
 };
+
+SSTB_HD uint32_t
+mt_wrap(uint32_t i)
+{
+    return i >= MT_N ? i - MT_N : i;
+}
 
 SSTB_HD void
 mt_u32x2_cached(uint32_t* mt, uint32_t& idx, MtPairCache& c, uint32_t& r0, uint32_t& r1)
@@ -136,29 +147,37 @@ mt_u32x2_cached(uint32_t* mt, uint32_t& idx, MtPairCache& c, uint32_t& r0, uint3
         idx = g.idx;
         return;
     }
-    const uint32_t i2  = (i + 2 == MT_N) ? 0u : i + 2;                    // even
-    const uint32_t im  = (i + MT_M >= MT_N) ? i + MT_M - MT_N : i + MT_M; // odd
-    const uint32_t im1 = (im + 1 == MT_N) ? 0u : im + 1;                  // even
     if ( !c.valid ) {
         const uint2 ca = *reinterpret_cast<const uint2*>(mt + i);
+        const uint2 cb = *reinterpret_cast<const uint2*>(mt + mt_wrap(i + 2));
+        const uint2 ce = *reinterpret_cast<const uint2*>(mt + mt_wrap(i + MT_M + 1));
+        c.b0           = mt[mt_wrap(i + MT_M)];
         c.a0           = ca.x;
         c.a1           = ca.y;
-        c.b0           = mt[im];
+        c.a2           = cb.x;
+        c.a3           = cb.y;
+        c.b1           = ce.x;
+        c.b2           = ce.y;
     }
-    const uint2    na = *reinterpret_cast<const uint2*>(mt + i2);  // (mt[i+2], mt[i+3])
-    const uint2    nb = *reinterpret_cast<const uint2*>(mt + im1); // (mt[im+1], mt[im+2])
     const uint32_t y0 = (c.a0 & 0x80000000u) + (c.a1 & 0x7fffffffu);
     uint32_t       v0 = c.b0 ^ (y0 >> 1);
     if ( y0 & 1u ) v0 ^= 2567483615u;
-    const uint32_t y1 = (c.a1 & 0x80000000u) + (na.x & 0x7fffffffu);
-    uint32_t       v1 = nb.x ^ (y1 >> 1);
+    const uint32_t y1 = (c.a1 & 0x80000000u) + (c.a2 & 0x7fffffffu);
+    uint32_t       v1 = c.b1 ^ (y1 >> 1);
     if ( y1 & 1u ) v1 ^= 2567483615u;
     *reinterpret_cast<uint2*>(mt + i) = uint2 { v0, v1 };
-    c.a0    = na.x;
-    c.a1    = na.y;
-    c.b0    = nb.y;
+    // read-ahead for the pair after next
+    const uint2 na = *reinterpret_cast<const uint2*>(mt + mt_wrap(i + 4));        // C_j+2
+    const uint2 ne = *reinterpret_cast<const uint2*>(mt + mt_wrap(i + MT_M + 3)); // E_j+1
+    c.a0    = c.a2;
+    c.a1    = c.a3;
+    c.b0    = c.b2;
+    c.a2    = na.x;
+    c.a3    = na.y;
+    c.b1    = ne.x;
+    c.b2    = ne.y;
     c.valid = 1;
-    idx     = i2;
+    idx     = mt_wrap(i + 2);
     r0      = mt_temper(v0);
     r1      = mt_temper(v1);
 }

@@ -21,7 +21,7 @@ dev_mt_stream(uint32_t seed, int mode, uint32_t lead, uint64_t n, uint32_t* out)
     if ( mode == 3 ) { // `lead` single draws, then cached pairs; the cache is dropped every `lead+3` pairs (window end)
         for ( ; i < lead && i < n; ++i )
             out[i] = g.u32();
-        MtPairCache c { 0, 0, 0, 0 };
+        MtPairCache c {};
         uint32_t    idx = g.idx, pairs = 0;
         for ( ; i + 1 < n; i += 2 ) {
             mt_u32x2_cached(mt, idx, c, out[i], out[i + 1]);
