@@ -101,9 +101,10 @@ int sstb200_engine_advance(sstb200_engine* e);
 /* device pointers + geometry of the exchange buffers: words per rank slot = 1 + capacity*4 u64
  * ([0] = count, then capacity x {time, dst_seq, payload, dst_comp}) */
 int sstb200_engine_exchange_buffers(sstb200_engine* e, void** outbox_dev, void** inbox_dev, uint64_t* words_per_rank);
-/* device pointer to the 8 x u64 control words that must be all-reduced (SUM) across ranks between ingest and advance:
- * [0] pending events, [1] primary components still running, [2] active clocks, [3] error flag, [4] exit time (MAX is
- * taken by the engine from [4..7] laid out as one-hot per rank is avoided: see DESIGN.md)                    */
+/* device pointers to this rank's 8 x i64 control words and to the n_ranks x 8 buffer the driver must fill with every
+ * rank's words (all-gather) between ingest and advance: [0] pending events (sent - delivered, may be negative on one
+ * rank), [1] primary components still running, [2] active clocks, [3] error flag, [4] exit time, [5..7] reserved.
+ * advance folds them: sums of 0..3, max of 4. */
 int sstb200_engine_control_words(sstb200_engine* e, void** local_dev, void** global_dev);
 
 /* ---- results (finish() simulation.cc:1286-1311, statistics dump statapi/statengine.cc:476-548) ---- */
@@ -123,8 +124,9 @@ typedef struct sstb200_status {
     uint64_t launches;         /* kernels launched by the engine so far                                       */
 } sstb200_status;
 int sstb200_engine_status(sstb200_engine* e, sstb200_status* out);
-/* results[(comp_end-comp_begin) * 32] u64 for the components this rank owns */
-int sstb200_engine_results(sstb200_engine* e, uint64_t* results);
+/* results[(comp_end-comp_begin) * words] u64 for the components this rank owns: the first `words_per_component` words
+ * of each result record (0 = all 32) */
+int sstb200_engine_results(sstb200_engine* e, uint64_t* results, uint32_t words_per_component);
 /* delivery trace of this rank: per delivered event (time, component, port index within component, payload), in
  * per-component delivery order; rows of one component are contiguous in `comp`-sorted order after this call.   */
 int sstb200_engine_trace(sstb200_engine* e, uint64_t* n_inout, uint64_t* time, uint32_t* comp, uint32_t* port,

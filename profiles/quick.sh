@@ -8,3 +8,13 @@ import json;d=json.loads(open('gpurun_out/bench_4096.log').read().strip().splitl
 timeout 600 python bench.py --workload phold --x 1024 --y 1024 --steps 20 --warmup 10 --no-cpu-baseline --no-e2e > gpurun_out/bench_phold.log 2>&1
 python -c "
 import json;d=json.loads(open('gpurun_out/bench_phold.log').read().strip().splitlines()[-1]);print('phold1024',d['value'],d['ms_per_step'],d['roofline']['frac'])"
+python - <<'PY'
+import time, sys
+sys.path.insert(0, '.')
+from sst_core_b200 import models
+from sst_core_b200.run import simulate_model
+m = models.mesh_model(6, 6)
+simulate_model(m)
+t0 = time.perf_counter(); res, st = simulate_model(m); dt = time.perf_counter() - t0
+print(f"mesh 6x6 10us end-to-end {dt*1e3:.1f} ms, {st.events_delivered/dt/1e6:.2f} M ev/s, windows {st.windows}")
+PY

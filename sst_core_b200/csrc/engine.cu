@@ -735,6 +735,31 @@ dispatch_kernel(Dev d)
     }
 }
 
+// ---- wire-up on the device: link row of every local directed port = {peer port, component owning the peer (binary
+// search in the GLOBAL port CSR), send latency}.  Replaces the per-Link object setup of Simulation::prepareLinks
+// (simulation.cc:668-820) for 67 M ports without a host loop.
+__global__ void __launch_bounds__(BLOCK)
+build_links_kernel(uint4* link, const uint32_t* peer, const uint64_t* latency, const uint32_t* port_off_global,
+    uint32_t ncomp_global, uint32_t nport_local)
+{
+    for ( uint32_t p = blockIdx.x * BLOCK + threadIdx.x; p < nport_local; p += gridDim.x * BLOCK ) {
+        const uint32_t pr = peer[p];
+        uint32_t       lo = 0;
+        if ( pr != SSTB200_NO_PEER ) {
+            uint32_t hi = ncomp_global; // largest c with port_off[c] <= pr
+            while ( hi - lo > 1 ) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                if ( port_off_global[mid] <= pr )
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+        }
+        const uint64_t lat = latency[p];
+        link[p]            = make_uint4(pr, lo, (uint32_t)(lat & 0xFFFFFFFFull), (uint32_t)(lat >> 32));
+    }
+}
+
 // ---- bin the events received from other ranks (RankSyncSerialSkip::exchange re-send, rankSyncSerialSkip.cc:291-295)
 __global__ void __launch_bounds__(BLOCK)
 ingest_kernel(Dev d)
@@ -814,7 +839,7 @@ publish_control_kernel(Dev d)
 }
 
 __global__ void __launch_bounds__(BLOCK)
-results_kernel(Dev d, uint64_t* out)
+results_kernel(Dev d, uint64_t* out, uint32_t words)
 {
     const uint32_t lc = blockIdx.x * BLOCK + threadIdx.x;
     if ( lc >= d.n_local ) return;
@@ -830,7 +855,7 @@ results_kernel(Dev d, uint64_t* out)
     });
 #pragma unroll
     for ( int i = 0; i < NRESULT; ++i )
-        out[(uint64_t)lc * NRESULT + i] = r[i];
+        if ( (uint32_t)i < words ) out[(uint64_t)lc * words + i] = r[i];
 }
 
 // ================================================================================================ RNG stream kernels
@@ -1039,6 +1064,48 @@ struct sstb200_engine
         CUDA_OK(cudaGetLastError());
         return 0;
     }
+    // `n` windows (dispatch + advance each).  The kernels take the same arguments every window -- the window state
+    // lives in device memory -- so a chunk is captured once into a CUDA graph and replayed: small models are bound by
+    // launch overhead, not by the kernels.
+    cudaGraphExec_t graph_exec  = nullptr;
+    uint32_t        graph_chunk = 0;
+    bool            graph_failed = false;
+    int launch_windows(uint32_t n)
+    {
+        if ( !graph_failed && n >= 8 && (graph_exec == nullptr || graph_chunk == n) ) {
+            if ( graph_exec == nullptr ) {
+                cudaGraph_t g = nullptr;
+                if ( cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed) == cudaSuccess ) {
+                    const uint64_t before = launches;
+                    int            rc     = 0;
+                    for ( uint32_t i = 0; i < n && !rc; ++i ) {
+                        rc = launch_dispatch();
+                        if ( !rc ) rc = launch_advance();
+                    }
+                    launches = before; // counted per replay below
+                    cudaError_t ce = cudaStreamEndCapture(stream, &g);
+                    if ( rc == 0 && ce == cudaSuccess && cudaGraphInstantiate(&graph_exec, g, 0) == cudaSuccess )
+                        graph_chunk = n;
+                    else
+                        graph_failed = true;
+                    if ( g ) cudaGraphDestroy(g);
+                }
+                else
+                    graph_failed = true;
+                (void)cudaGetLastError();
+            }
+            if ( graph_exec && graph_chunk == n ) {
+                CUDA_OK(cudaGraphLaunch(graph_exec, stream));
+                launches += 2ull * n;
+                return 0;
+            }
+        }
+        for ( uint32_t i = 0; i < n; ++i ) {
+            if ( int rc = launch_dispatch() ) return rc;
+            if ( int rc = launch_advance() ) return rc;
+        }
+        return 0;
+    }
     int launch_advance()
     {
         advance_kernel<<<1, 32, 0, stream>>>(d);
@@ -1165,19 +1232,6 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     // per-rank slices
     d.P0          = m->port_off[c0];
     d.nport_local = m->port_off[c1] - d.P0;
-    std::vector<uint32_t> port_comp(nport);
-    for ( uint32_t c = 0; c < m->ncomp; ++c )
-        for ( uint32_t p = m->port_off[c]; p < m->port_off[c + 1]; ++p )
-            port_comp[p] = c;
-    std::vector<uint4> link(d.nport_local);
-    for ( uint32_t p = 0; p < d.nport_local; ++p ) {
-        const uint32_t gp   = d.P0 + p;
-        const uint32_t peer = m->peer_port[gp];
-        link[p].x           = peer;
-        link[p].y           = peer == SSTB200_NO_PEER ? 0 : port_comp[peer];
-        link[p].z           = (uint32_t)(m->latency[gp] & 0xFFFFFFFFull);
-        link[p].w           = (uint32_t)(m->latency[gp] >> 32);
-    }
     uint32_t state_stride = 8, aux_stride = 0;
     int      has_payload  = 0;
     for ( uint32_t c = c0; c < c1; ++c ) {
@@ -1223,7 +1277,23 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     rc |= e->upload(&d.comp_type, m->comp_type + c0, d.n_local);
     rc |= e->upload(&d.comp_param, m->comp_param + (size_t)c0 * NPARAM, (size_t)d.n_local * NPARAM);
     rc |= e->upload(&d.port_off, m->port_off + c0, (size_t)d.n_local + 1);
-    rc |= e->upload(&d.link, link.data(), link.size());
+    {
+        // link rows are built on the device from the rank's slice of peer_port / latency and the global port CSR
+        uint4*          link_dev = nullptr;
+        const uint32_t* peer_dev = nullptr;
+        const uint64_t* lat_dev  = nullptr;
+        const uint32_t* poff_dev = nullptr;
+        rc |= e->alloc(&link_dev, d.nport_local, false);
+        rc |= e->upload(&peer_dev, m->peer_port + d.P0, d.nport_local);
+        rc |= e->upload(&lat_dev, m->latency + d.P0, d.nport_local);
+        rc |= e->upload(&poff_dev, m->port_off, (size_t)m->ncomp + 1);
+        if ( !rc && d.nport_local ) {
+            build_links_kernel<<<148 * 8, BLOCK, 0, e->stream>>>(link_dev, peer_dev, lat_dev, poff_dev, m->ncomp,
+                d.nport_local);
+            e->launches++;
+        }
+        d.link = link_dev;
+    }
     rc |= e->upload(&d.clock_period, m->clock_period + c0, d.n_local);
     if ( n_ranks > 1 ) rc |= e->upload(&d.rank_comp_begin, o->rank_comp_begin, (size_t)n_ranks + 1);
     rc |= e->alloc(&d.next_tick, d.n_local);
@@ -1290,6 +1360,7 @@ sstb200_engine_destroy(sstb200_engine* e)
     if ( e->stream ) cudaStreamSynchronize(e->stream);
     for ( void* p : e->allocs )
         cudaFree(p);
+    if ( e->graph_exec ) cudaGraphExecDestroy(e->graph_exec);
     if ( e->h_ctrl ) cudaFreeHost(e->h_ctrl);
     if ( e->own_stream && e->stream ) cudaStreamDestroy(e->stream);
     delete e;
@@ -1330,10 +1401,7 @@ sstb200_engine_run(sstb200_engine* e, uint64_t max_windows, uint32_t check_every
     for ( ;; ) {
         uint32_t chunk = check_every;
         if ( max_windows && max_windows - done_windows < chunk ) chunk = (uint32_t)(max_windows - done_windows);
-        for ( uint32_t i = 0; i < chunk; ++i ) {
-            if ( int rc = e->launch_dispatch() ) return rc;
-            if ( int rc = e->launch_advance() ) return rc;
-        }
+        if ( int rc = e->launch_windows(chunk) ) return rc;
         done_windows += chunk;
         if ( int rc = e->fetch_ctrl() ) return rc;
         if ( e->h_ctrl->error ) {
@@ -1432,14 +1500,15 @@ sstb200_engine_status(sstb200_engine* e, sstb200_status* s)
 }
 
 int
-sstb200_engine_results(sstb200_engine* e, uint64_t* results)
+sstb200_engine_results(sstb200_engine* e, uint64_t* results, uint32_t words_per_component)
 {
     if ( !e || !results ) return -1;
+    const uint32_t words = (words_per_component == 0 || words_per_component > NRESULT) ? NRESULT : words_per_component;
     CUDA_OK(cudaSetDevice(e->device));
-    results_kernel<<<e->d.nbins, BLOCK, 0, e->stream>>>(e->d, e->d_results);
+    results_kernel<<<e->d.nbins, BLOCK, 0, e->stream>>>(e->d, e->d_results, words);
     e->launches++;
     CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaMemcpyAsync(results, e->d_results, (size_t)e->d.n_local * NRESULT * 8, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaMemcpyAsync(results, e->d_results, (size_t)e->d.n_local * words * 8, cudaMemcpyDeviceToHost, e->stream));
     CUDA_OK(cudaStreamSynchronize(e->stream));
     return 0;
 }

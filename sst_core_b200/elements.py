@@ -26,6 +26,8 @@ from .timelord import TimeLord
 TYPE_MESH, TYPE_PHOLD, TYPE_CLOCKNODE, TYPE_RNGCOMP = 1, 2, 3, 4
 NPARAM = 8
 NRESULT = 32
+# words of the result record each element actually fills (the download can stop there)
+RESULT_WORDS = {1: 6, 2: 7, 3: 24, 4: 7}
 
 
 @dataclass

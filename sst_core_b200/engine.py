@@ -84,7 +84,7 @@ def lib():
                                                   C.POINTER(C.c_uint64)]
     L.sstb200_engine_control_words.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.sstb200_engine_status.argtypes = [C.c_void_p, C.POINTER(_Status)]
-    L.sstb200_engine_results.argtypes = [C.c_void_p, C.c_void_p]
+    L.sstb200_engine_results.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.sstb200_engine_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p]
     L.sstb200_rng_streams.argtypes = [C.c_int, C.c_void_p, C.c_int] + [C.c_uint64] * 6 + [C.c_void_p, C.c_void_p]
@@ -303,9 +303,18 @@ class Engine:
         """Wait for the engine's stream (status() does a device->host read on it)."""
         self.status()
 
-    def results(self) -> np.ndarray:
-        out = np.zeros((self.comp_end - self.comp_begin, NRESULT), dtype=np.uint64)
-        _check(self._L.sstb200_engine_results(self._h, _p(out)), "engine_results")
+    def results(self, words: int = 0) -> np.ndarray:
+        """Result records of this rank's components; `words` > 0 downloads only the first `words` of the 32 words
+        (the rest of the returned [n, 32] array is zero)."""
+        n = self.comp_end - self.comp_begin
+        if not words or words >= NRESULT:
+            out = np.empty((n, NRESULT), dtype=np.uint64)
+            _check(self._L.sstb200_engine_results(self._h, _p(out), 0), "engine_results")
+            return out
+        part = np.empty((n, words), dtype=np.uint64)
+        _check(self._L.sstb200_engine_results(self._h, _p(part), words), "engine_results")
+        out = np.zeros((n, NRESULT), dtype=np.uint64)
+        out[:, :words] = part
         return out
 
     def trace(self):

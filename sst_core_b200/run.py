@@ -14,6 +14,12 @@ from typing import Optional
 import numpy as np
 
 from . import config, output, wireup
+from .elements import NRESULT, RESULT_WORDS
+
+
+def result_words(m) -> int:
+    """How many words of the 32-word result record the model's elements fill."""
+    return max((RESULT_WORDS.get(int(t), NRESULT) for t in np.unique(m.comp_type)), default=NRESULT)
 
 
 def simulate_model(m: wireup.WiredModel, device: int = 0, **engine_opts):
@@ -26,7 +32,7 @@ def simulate_model(m: wireup.WiredModel, device: int = 0, **engine_opts):
         e.run()
         st = e.status()
         e.raise_on_error(st)
-        return e.results(), st
+        return e.results(result_words(m)), st
     finally:
         e.close()
 
@@ -52,7 +58,7 @@ def simulate_distributed(m: wireup.WiredModel, **engine_opts):
             DistributedRunner(e).run()
             st = e.status()
             e.raise_on_error(st)
-            return e.results(), st, pm
+            return e.results(result_words(pm)), st, pm
         finally:
             e.close()
 
