@@ -181,11 +181,11 @@ def build_model(a, windows):
     stop_ns = windows + 2
     if a.workload == "mesh":
         m = models.mesh_model(x, y, stop_at=f"{stop_ns}ns", verbose=0, stats_enabled=True)
-        opts = dict(calendar_slots=2, bin_capacity=2048, smem_events=1536)
+        opts = dict(calendar_slots=2, bin_capacity=2048, smem_events=1536, outbox_capacity=16384)
         name = f"MessageMesh {x}x{y} torus, 1 ns links, MersenneRNG(id+100) per component, msg_count statistic on"
     else:
         m = models.phold_model(x, y, stop_at=f"{stop_ns}ns", verbose=0, stats_enabled=True)
-        opts = dict(calendar_slots=16, bin_capacity=2560, smem_events=2560)
+        opts = dict(calendar_slots=16, bin_capacity=2560, smem_events=2560, outbox_capacity=16384)
         name = f"PHOLD {x}x{y} torus, 16 events/component, delay u32%8000 ps, XORShiftRNG(id+1)"
     if a.smem_events:
         opts["smem_events"] = a.smem_events
