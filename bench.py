@@ -35,7 +35,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-ALGO_BYTES = {"mesh": 96, "phold": 192}  # SURVEY.md section 8(d) algorithmic bytes per committed event
+ALGO_BYTES = {"mesh": 96, "phold": 192, "clockpop": 24}  # clockpop: per clock tick  # SURVEY.md section 8(d) algorithmic bytes per committed event
 
 
 def parse_args():
@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mesh", choices=["mesh", "phold"])
+    ap.add_argument("--workload", default="mesh", choices=["mesh", "phold", "clockpop"])
     ap.add_argument("--x", type=int, default=0)
     ap.add_argument("--y", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
@@ -183,6 +183,11 @@ def build_model(a, windows):
         m = models.mesh_model(x, y, stop_at=f"{stop_ns}ns", verbose=0, stats_enabled=True)
         opts = dict(calendar_slots=2, bin_capacity=2048, smem_events=1536, outbox_capacity=16384)
         name = f"MessageMesh {x}x{y} torus, 1 ns links, MersenneRNG(id+100) per component, msg_count statistic on"
+    elif a.workload == "clockpop":
+        m = models.clockpop_model(x, y, stop_at=f"{stop_ns}ns", verbose=0, stats_enabled=True)
+        opts = dict(calendar_slots=2, bin_capacity=512, smem_events=512, outbox_capacity=16384)
+        name = (f"clock population {x}x{y} torus, periods 1/0.5/0.25/2 GHz by id%4, MarsagliaRNG(11+id,272727), "
+                f"commFreq 1000 (metric counts clock ticks + delivered events)")
     else:
         m = models.phold_model(x, y, stop_at=f"{stop_ns}ns", verbose=0, stats_enabled=True)
         opts = dict(calendar_slots=16, bin_capacity=2560, smem_events=2560, outbox_capacity=16384)
@@ -302,7 +307,7 @@ def ours(a):
         e.raise_on_error(st1)
     ms_total = t_beg.elapsed_time(t_end)
     ms_dispatch = sum(p[0].elapsed_time(p[1]) for p in pairs) / K
-    events = st1.events_delivered - st0.events_delivered
+    events = (st1.events_delivered - st0.events_delivered) + (st1.clock_ticks - st0.clock_ticks)
     launches = st1.launches - st0.launches
     tt = torch.tensor([ms_total, ms_dispatch], dtype=torch.float64, device=dev)
     ee = torch.tensor([events, launches], dtype=torch.float64, device=dev)
