@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--y", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--smem-events", type=int, default=0, help="override the staging capacity (tuning)")
+    ap.add_argument("--bin-capacity", type=int, default=0, help="override the calendar bin capacity (tuning)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-size", type=int, default=256, help="reference sample: S x S mesh")
     ap.add_argument("--cpu-ns", type=int, default=100, help="reference sample: simulated ns")
@@ -194,6 +195,8 @@ def build_model(a, windows):
         name = f"PHOLD {x}x{y} torus, 16 events/component, delay u32%8000 ps, XORShiftRNG(id+1)"
     if a.smem_events:
         opts["smem_events"] = a.smem_events
+    if a.bin_capacity:
+        opts["bin_capacity"] = a.bin_capacity
     return m, opts, name
 
 

@@ -109,10 +109,13 @@ struct MeshElement
     };
     static constexpr uint32_t STORED_BYTES  = 48; // written back every window
     static constexpr uint32_t PERSIST_BYTES = 64; // lives in HBM (stored part + construction constants)
+    // start of a window in which this component has `n_events` events: issue the MT19937 read-ahead now, so that
+    // it is in flight while the engine orders the component's events
     template <class Ctx>
-    __device__ static void beginWindow(Ctx&, State& s)
+    __device__ static void beginWindow(Ctx& ctx, State& s, uint32_t n_events)
     {
         s.cache.valid = 0;
+        if ( n_events && (s.mt_idx & 1u) == 0 ) mt_cache_fill((const uint32_t*)ctx.aux, s.mt_idx, s.cache);
     }
     // dispatch prologue hook: pull towards L2 the MT19937 words the next handful of draws will read
     // (words idx.. and idx+397.. mod 624), so that the per-event draws hit L2 instead of paying an HBM round trip each
@@ -200,7 +203,7 @@ struct PholdElement
     static constexpr uint32_t STORED_BYTES  = sizeof(State);
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>
-    __device__ static void beginWindow(Ctx&, State&)
+    __device__ static void beginWindow(Ctx&, State&, uint32_t)
     {}
     __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
     template <class Ctx>
@@ -264,7 +267,7 @@ struct ClockNodeElement
     static constexpr uint32_t STORED_BYTES  = sizeof(State);
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>
-    __device__ static void beginWindow(Ctx&, State&)
+    __device__ static void beginWindow(Ctx&, State&, uint32_t)
     {}
     __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
     template <class Ctx>
@@ -330,7 +333,7 @@ struct RngElement
     static constexpr uint32_t STORED_BYTES  = sizeof(State);
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>
-    __device__ static void beginWindow(Ctx&, State&)
+    __device__ static void beginWindow(Ctx&, State&, uint32_t)
     {}
     __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
     template <class Ctx>

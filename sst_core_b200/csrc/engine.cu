@@ -52,7 +52,10 @@ set_error(const std::string& s)
         }                                                                                                  \
     } while ( 0 )
 
-constexpr int      BLOCK      = 256; // components per CTA == threads per CTA
+#ifndef SSTB200_BLOCK
+#define SSTB200_BLOCK 256
+#endif
+constexpr int      BLOCK      = SSTB200_BLOCK; // components per CTA == threads per CTA
 constexpr uint64_t TIME_NEVER = ~0ull;
 
 enum : uint32_t { ERR_BIN_OVERFLOW = 1, ERR_SMEM_OVERFLOW = 2, ERR_TIME_FAULT = 3, ERR_OUTBOX_OVERFLOW = 4, ERR_TRACE_OVERFLOW = 5 };
@@ -535,22 +538,8 @@ dispatch_kernel(Dev d)
     const bool      valid  = lc < d.n_local;
     const uint32_t  my_cnt = s_cnt[c];
     uint16_t*       seg    = s_perm + s_off[c];
-    uint32_t        delivered = 0, ticks = 0, sent = 0, clocks_stopped = 0, n_staged = 0;
+    uint32_t        delivered = 0, ticks = 0, sent = 0, clocks_stopped = 0;
     if ( valid ) {
-        // (b) order inside the segment: (time, port, sequence).  Insertion sort by the owning thread; the lanes of a
-        // warp own components with (nearly) equal event counts, so the loops stay converged.
-        for ( uint32_t a = 1; a < my_cnt; ++a ) {
-            const uint16_t ea = seg[a];
-            const uint32_t ta = s_time[ea], da = s_dst[ea], qa = s_seq[ea];
-            uint32_t       b  = a;
-            while ( b > 0 ) {
-                const uint16_t eb = seg[b - 1];
-                if ( !key_less(ta, da, qa, s_time[eb], s_dst[eb], s_seq[eb]) ) break;
-                seg[b] = eb;
-                --b;
-            }
-            seg[b] = ea;
-        }
         const uint64_t period    = d.clock_period[lc];
         uint64_t       next_tick = d.next_tick[lc];
         const bool     has_work  = my_cnt > 0 || next_tick < T_end;
@@ -565,7 +554,21 @@ dispatch_kernel(Dev d)
                 using E = decltype(el);
                 typename E::State s;
                 load_state(s, d.state + (uint64_t)lc * d.state_stride, E::PERSIST_BYTES);
-                E::beginWindow(ctx, s);
+                E::beginWindow(ctx, s, my_cnt); // issues the element's first loads (MT19937 read-ahead) ...
+                // ... which the sort below overlaps.  (b) order inside the segment: (time, port, sequence).  Insertion sort by the owning thread; the lanes of a
+                // warp own components with (nearly) equal event counts, so the loops stay converged.
+                for ( uint32_t a = 1; a < my_cnt; ++a ) {
+                    const uint16_t ea = seg[a];
+                    const uint32_t ta = s_time[ea], da = s_dst[ea], qa = s_seq[ea];
+                    uint32_t       b  = a;
+                    while ( b > 0 ) {
+                        const uint16_t eb = seg[b - 1];
+                        if ( !key_less(ta, da, qa, s_time[eb], s_dst[eb], s_seq[eb]) ) break;
+                        seg[b] = eb;
+                        --b;
+                    }
+                    seg[b] = ea;
+                }
                 uint64_t cycle = (next_tick != TIME_NEVER && period) ? next_tick / period : 0;
                 uint32_t i     = 0;
                 for ( ;; ) {
@@ -587,7 +590,8 @@ dispatch_kernel(Dev d)
                     const uint32_t e    = seg[i++];
                     const uint32_t port = s_dst[e] - ctx.port0;
                     uint64_t       pl   = PAYLOAD ? s_pay[e] : 0;
-                    ctx.free_tail       = i; // slot e is consumed: free for out-staging
+                    s_dst[e]            = SSTB200_NO_PEER; // slot e is consumed: free for out-staging
+                    ctx.free_tail       = i;
                     ctx.now             = ev_t;
                     if ( d.trace_cap ) {
                         const unsigned long long tp = atomicAdd(&ctrl->trace_n, 1ull);
@@ -608,101 +612,118 @@ dispatch_kernel(Dev d)
             d.send_seq[lc]  = ctx.seq;
             d.next_tick[lc] = next_tick;
             if ( d.deliv_seq ) d.deliv_seq[lc] = dseq;
-            sent     = ctx.sent;
-            n_staged = ctx.free_head;
+            sent = ctx.sent;
         }
     }
-    __syncwarp();
+    __syncthreads();
 
-    // ---- phase 4: each warp flushes what its 32 components staged (slots seg[0 .. n_staged)).  Lanes that target
-    // the same (window slot, destination block) reserve their calendar slots with ONE atomic (match.any) and write
-    // their records side by side.  No CTA-wide barrier: a warp that is done leaves.
+    // ---- phase 4: flush the staged sends, the whole CTA over all slots (balanced: ~4 records per thread however the
+    // events were distributed over components).  Destination bins are counted in a small shared hash table
+    // (key = window slot x destination block, or the destination rank): a record's rank inside its bin comes from a
+    // shared-memory atomic, ONE global atomic per distinct bin reserves the calendar slots, then the records are
+    // written side by side.  Records that find no table entry (more than HT distinct bins per CTA: irregular graphs)
+    // reserve their slot directly.
     {
-        uint32_t max_staged = n_staged;
-#pragma unroll
-        for ( int o = 16; o > 0; o >>= 1 )
-            max_staged = max(max_staged, __shfl_xor_sync(0xffffffffu, max_staged, o));
-        constexpr int FL = 4; // records in flight per lane: the FL reservations are issued before any is consumed
-        for ( uint32_t j0 = 0; j0 < max_staged; j0 += FL ) {
-            uint32_t           ev[FL], key[FL], rank[FL], dtv[FL];
-            unsigned long long pos0[FL];
-            uint32_t           leaderv[FL];
-#pragma unroll
-            for ( int u = 0; u < FL; ++u ) {
-                const uint32_t j      = j0 + u;
-                const bool     active = j < n_staged;
-                const uint32_t e      = active ? seg[j] : 0;
-                uint32_t       ky     = 0xFFFFFFFFu;
-                uint32_t       dt     = 0;
-                if ( active ) {
-                    const uint32_t dcomp = s_cr[e];
-                    dt                   = s_time[e];
-                    if ( d.n_ranks > 1 && (dcomp < d.c0 || dcomp >= d.c0 + d.n_local) ) {
-                        uint32_t r = 0;
-                        while ( r + 1 < d.n_ranks && dcomp >= d.rank_comp_begin[r + 1] )
-                            ++r;
-                        ky = 0x80000000u | r;
-                    }
-                    else if ( dt < w ) {
-                        raise_error(d, ERR_TIME_FAULT, T + dt, T, dcomp); // a send violated the lookahead
-                        ky = 0xFFFFFFFEu;
-                    }
-                    else {
-                        uint32_t sl = slot1;
-                        if ( dt >= 2 * w ) {
-                            uint32_t dk = dt / w;
-                            if ( dk > d.W - 1 ) dk = d.W - 1; // beyond the horizon: parked in the farthest slot
-                            sl = (uint32_t)((slot + dk) % d.W);
-                        }
-                        ky = sl * d.nbins + ((dcomp - d.c0) >> 8);
-                    }
-                }
-                const uint32_t peers = __match_any_sync(0xffffffffu, ky);
-                leaderv[u]           = __ffs(peers) - 1;
-                rank[u]              = __popc(peers & ((1u << lane) - 1));
-                ev[u]                = e;
-                key[u]               = ky;
-                dtv[u]               = dt;
-                pos0[u]              = 0;
-                if ( ky < 0xFFFFFFFEu && lane == leaderv[u] ) {
-                    if ( ky & 0x80000000u )
-                        pos0[u] = atomicAdd(&d.outbox[(uint64_t)(ky & 0x7FFFFFFFu) * d.xwords],
-                            (unsigned long long)__popc(peers));
-                    else
-                        pos0[u] = atomicAdd(&d.bin_count[ky], (uint32_t)__popc(peers));
-                }
+        constexpr uint32_t HT = 64;
+        uint32_t* ht_key  = s_cnt;      // [HT] phase-2 scratch is dead by now
+        uint32_t* ht_cnt  = s_cnt + HT; // [HT]
+        uint32_t* ht_base = s_off;      // [HT] (low 32 bits of the reserved base)
+        if ( tid < HT ) {
+            ht_key[tid] = 0xFFFFFFFFu;
+            ht_cnt[tid] = 0;
+        }
+        __syncthreads();
+        constexpr int MAXR = 8; // slots tid, tid+256, ... per thread in registers between the passes (2048 slots)
+        uint32_t      r_key[MAXR], r_rank[MAXR], r_ent[MAXR];
+        auto          classify_out = [&](uint32_t e, uint32_t& ky_out, uint32_t& ent_out, uint32_t& rank_out) {
+            ent_out = 0xFFFFFFFFu;
+            if ( e >= n_due || s_dst[e] == SSTB200_NO_PEER ) return;
+            const uint32_t dcomp = s_cr[e];
+            const uint32_t dt    = s_time[e];
+            uint32_t       ky;
+            if ( d.n_ranks > 1 && (dcomp < d.c0 || dcomp >= d.c0 + d.n_local) ) {
+                uint32_t r = 0;
+                while ( r + 1 < d.n_ranks && dcomp >= d.rank_comp_begin[r + 1] )
+                    ++r;
+                ky = 0x80000000u | r;
             }
-#pragma unroll
-            for ( int u = 0; u < FL; ++u ) {
-                const unsigned long long base = __shfl_sync(0xffffffffu, pos0[u], leaderv[u]);
-                const uint32_t           ky   = key[u];
-                if ( ky >= 0xFFFFFFFEu ) continue;
-                const uint32_t           e   = ev[u];
-                const unsigned long long pos = base + rank[u];
-                const uint64_t           tm  = T + dtv[u];
-                const uint64_t           ds  = ((uint64_t)s_dst[e] << 32) | s_seq[e];
-                if ( ky & 0x80000000u ) {
-                    const uint32_t r = ky & 0x7FFFFFFFu;
-                    if ( pos >= d.outbox_cap ) {
-                        raise_error(d, ERR_OUTBOX_OVERFLOW, r, pos, d.outbox_cap);
-                    }
-                    else {
-                        unsigned long long* rec = d.outbox + (uint64_t)r * d.xwords + 1 + pos * 4;
-                        rec[0]                  = tm;
-                        rec[1]                  = ds;
-                        rec[2]                  = PAYLOAD ? s_pay[e] : 0;
-                        rec[3]                  = s_cr[e];
-                    }
+            else if ( dt < w ) {
+                raise_error(d, ERR_TIME_FAULT, T + dt, T, dcomp); // a send violated the lookahead
+                return;
+            }
+            else {
+                uint32_t sl = slot1;
+                if ( dt >= 2 * w ) {
+                    uint32_t dk = dt / w;
+                    if ( dk > d.W - 1 ) dk = d.W - 1; // beyond the horizon: parked in the farthest slot
+                    sl = (uint32_t)((slot + dk) % d.W);
                 }
-                else if ( pos >= d.cap ) {
-                    raise_error(d, ERR_BIN_OVERFLOW, ky / d.nbins, ky % d.nbins, pos);
+                ky = sl * d.nbins + (dcomp - d.c0) / BLOCK;
+            }
+            // find / claim the table entry of this bin (open addressing, 4 probes)
+            uint32_t h = (ky * 2654435761u) >> 26;
+#pragma unroll
+            for ( int pr = 0; pr < 4; ++pr ) {
+                const uint32_t old = atomicCAS(&ht_key[h], 0xFFFFFFFFu, ky);
+                if ( old == 0xFFFFFFFFu || old == ky ) {
+                    ent_out = h;
+                    break;
+                }
+                h = (h + 1) & (HT - 1);
+            }
+            if ( ent_out != 0xFFFFFFFFu ) {
+                ky_out   = ky;
+                rank_out = atomicAdd(&ht_cnt[ent_out], 1u);
+            }
+            else { // table full: reserve directly
+                emit(d, k, T + dt, s_dst[e], dcomp, s_seq[e], PAYLOAD ? s_pay[e] : 0);
+            }
+        };
+#pragma unroll
+        for ( int j = 0; j < MAXR; ++j )
+            classify_out(tid + j * BLOCK, r_key[j], r_ent[j], r_rank[j]);
+        for ( uint32_t e = tid + MAXR * BLOCK; e < n_due; e += BLOCK ) // beyond the register window: direct
+            if ( s_dst[e] != SSTB200_NO_PEER )
+                emit(d, k, T + s_time[e], s_dst[e], s_cr[e], s_seq[e], PAYLOAD ? s_pay[e] : 0);
+        __syncthreads();
+        if ( tid < HT && ht_key[tid] != 0xFFFFFFFFu && ht_cnt[tid] ) {
+            const uint32_t ky = ht_key[tid];
+            if ( ky & 0x80000000u )
+                ht_base[tid] = (uint32_t)atomicAdd(&d.outbox[(uint64_t)(ky & 0x7FFFFFFFu) * d.xwords],
+                    (unsigned long long)ht_cnt[tid]);
+            else
+                ht_base[tid] = atomicAdd(&d.bin_count[ky], ht_cnt[tid]);
+        }
+        __syncthreads();
+#pragma unroll
+        for ( int j = 0; j < MAXR; ++j ) {
+            if ( r_ent[j] == 0xFFFFFFFFu ) continue;
+            const uint32_t e   = tid + j * BLOCK;
+            const uint32_t ky  = r_key[j];
+            const uint32_t pos = ht_base[r_ent[j]] + r_rank[j];
+            const uint64_t tm  = T + s_time[e];
+            const uint64_t ds  = ((uint64_t)s_dst[e] << 32) | s_seq[e];
+            if ( ky & 0x80000000u ) {
+                const uint32_t r = ky & 0x7FFFFFFFu;
+                if ( pos >= d.outbox_cap ) {
+                    raise_error(d, ERR_OUTBOX_OVERFLOW, r, pos, d.outbox_cap);
                 }
                 else {
-                    const uint64_t off = (uint64_t)ky * d.cap + pos;
-                    d.ev_time[off]     = tm;
-                    d.ev_dst_seq[off]  = ds;
-                    if ( PAYLOAD ) d.ev_payload[off] = s_pay[e];
+                    unsigned long long* rec = d.outbox + (uint64_t)r * d.xwords + 1 + (uint64_t)pos * 4;
+                    rec[0]                  = tm;
+                    rec[1]                  = ds;
+                    rec[2]                  = PAYLOAD ? s_pay[e] : 0;
+                    rec[3]                  = s_cr[e];
                 }
+            }
+            else if ( pos >= d.cap ) {
+                raise_error(d, ERR_BIN_OVERFLOW, ky / d.nbins, ky % d.nbins, pos);
+            }
+            else {
+                const uint64_t off = (uint64_t)ky * d.cap + pos;
+                d.ev_time[off]     = tm;
+                d.ev_dst_seq[off]  = ds;
+                if ( PAYLOAD ) d.ev_payload[off] = s_pay[e];
             }
         }
     }

@@ -136,6 +136,23 @@ mt_wrap(uint32_t i)
     return i >= MT_N ? i - MT_N : i;
 }
 
+// loads the cache for a pair at even index i (C_j, C_j+1, mt[i+397], E_j)
+SSTB_HD void
+mt_cache_fill(const uint32_t* mt, uint32_t i, MtPairCache& c)
+{
+    const uint2 ca = *reinterpret_cast<const uint2*>(mt + i);
+    const uint2 cb = *reinterpret_cast<const uint2*>(mt + mt_wrap(i + 2));
+    const uint2 ce = *reinterpret_cast<const uint2*>(mt + mt_wrap(i + MT_M + 1));
+    c.b0           = mt[mt_wrap(i + MT_M)];
+    c.a0           = ca.x;
+    c.a1           = ca.y;
+    c.a2           = cb.x;
+    c.a3           = cb.y;
+    c.b1           = ce.x;
+    c.b2           = ce.y;
+    c.valid        = 1;
+}
+
 SSTB_HD void
 mt_u32x2_cached(uint32_t* mt, uint32_t& idx, MtPairCache& c, uint32_t& r0, uint32_t& r1)
 {
@@ -147,18 +164,7 @@ mt_u32x2_cached(uint32_t* mt, uint32_t& idx, MtPairCache& c, uint32_t& r0, uint3
         idx = g.idx;
         return;
     }
-    if ( !c.valid ) {
-        const uint2 ca = *reinterpret_cast<const uint2*>(mt + i);
-        const uint2 cb = *reinterpret_cast<const uint2*>(mt + mt_wrap(i + 2));
-        const uint2 ce = *reinterpret_cast<const uint2*>(mt + mt_wrap(i + MT_M + 1));
-        c.b0           = mt[mt_wrap(i + MT_M)];
-        c.a0           = ca.x;
-        c.a1           = ca.y;
-        c.a2           = cb.x;
-        c.a3           = cb.y;
-        c.b1           = ce.x;
-        c.b2           = ce.y;
-    }
+    if ( !c.valid ) mt_cache_fill(mt, i, c);
     const uint32_t y0 = (c.a0 & 0x80000000u) + (c.a1 & 0x7fffffffu);
     uint32_t       v0 = c.b0 ^ (y0 >> 1);
     if ( y0 & 1u ) v0 ^= 2567483615u;
