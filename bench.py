@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--smem-events", type=int, default=0, help="override the staging capacity (tuning)")
     ap.add_argument("--bin-capacity", type=int, default=0, help="override the calendar bin capacity (tuning)")
+    ap.add_argument("--stats", type=int, default=1, help="1: statistics enabled (accumulators updated), 0: disabled")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-size", type=int, default=256, help="reference sample: S x S mesh")
     ap.add_argument("--cpu-ns", type=int, default=100, help="reference sample: simulated ns")
@@ -181,9 +182,9 @@ def build_model(a, windows):
     y = a.y or 4096
     stop_ns = windows + 2
     if a.workload == "mesh":
-        m = models.mesh_model(x, y, stop_at=f"{stop_ns}ns", verbose=0, stats_enabled=True)
+        m = models.mesh_model(x, y, stop_at=f"{stop_ns}ns", verbose=0, stats_enabled=bool(a.stats))
         opts = dict(calendar_slots=2, bin_capacity=2048, smem_events=1536, outbox_capacity=16384)
-        name = f"MessageMesh {x}x{y} torus, 1 ns links, MersenneRNG(id+100) per component, msg_count statistic on"
+        name = f"MessageMesh {x}x{y} torus, 1 ns links, MersenneRNG(id+100) per component, msg_count statistic {'on' if a.stats else 'off'}"
     elif a.workload == "clockpop":
         m = models.clockpop_model(x, y, stop_at=f"{stop_ns}ns", verbose=0, stats_enabled=True)
         opts = dict(calendar_slots=2, bin_capacity=512, smem_events=512, outbox_capacity=16384)

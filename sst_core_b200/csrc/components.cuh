@@ -96,19 +96,21 @@ struct MeshElement
     static constexpr bool        HAS_PAYLOAD  = false;
     struct State
     {
-        // stored part (STORED_BYTES): what changes while the simulation runs
-        int32_t               message_count;
-        uint32_t              mt_idx;
+        // [0,16) mutable core
+        int32_t  message_count;
+        uint32_t mt_idx;
+        uint32_t pad0, pad1;
+        // [16,32) construction constants
+        uint32_t ngroups;
+        uint32_t mod;
+        uint64_t counts; // links per port group, 8 bits each
+        // [32,80) statistics
         Accumulator<uint64_t> mcnt; // RouteMessage "msg_count"
-        // construction constants (written once by construct())
-        uint32_t              ngroups;
-        uint32_t              mod;
-        uint64_t              counts; // links per port group, 8 bits each
-        // register-only scratch, valid inside one window (never read from / needed in memory)
-        MtPairCache           cache;
+        uint64_t              pad2;
+        // register-only scratch, valid inside one window
+        MtPairCache cache;
     };
-    static constexpr uint32_t STORED_BYTES  = 48; // written back every window
-    static constexpr uint32_t PERSIST_BYTES = 64; // lives in HBM (stored part + construction constants)
+    static constexpr uint32_t STORE_END = 16, CONST_END = 32, STATS_END = 80, PERSIST_BYTES = 80;
     // start of a window in which this component has `n_events` events: issue the MT19937 read-ahead now, so that
     // it is in flight while the engine orders the component's events
     template <class Ctx>
@@ -134,6 +136,8 @@ struct MeshElement
     {
         s.message_count = 0;
         s.mt_idx        = 0;
+        s.pad0 = s.pad1 = 0;
+        s.pad2          = 0;
         s.mod           = (uint32_t)p[1];
         s.ngroups       = (uint32_t)p[4];
         s.counts        = (uint64_t)p[5];
@@ -195,12 +199,17 @@ struct PholdElement
     static constexpr bool        HAS_PAYLOAD = true;
     struct State
     {
-        uint64_t              recv, hash;
-        XorShiftDev           rng;
-        uint32_t              dmod, init;
+        // [0,32) mutable core
+        uint64_t    recv, hash;
+        XorShiftDev rng;
+        // [32,48) construction constants
+        uint32_t dmod, init;
+        uint64_t pad0;
+        // [48,96) statistics
         Accumulator<uint64_t> delay;
+        uint64_t              pad1;
     };
-    static constexpr uint32_t STORED_BYTES  = sizeof(State);
+    static constexpr uint32_t STORE_END = 32, CONST_END = 48, STATS_END = 96;
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
@@ -258,13 +267,19 @@ struct ClockNodeElement
     static constexpr bool        HAS_PAYLOAD = false;
     struct State
     {
-        uint64_t             ticks, last_cycle, recv, hash;
-        MarsagliaDev         rng;
-        uint32_t             neighbor;
-        int32_t              commFreq;
+        // [0,48) mutable core
+        uint64_t     ticks, last_cycle, recv, hash;
+        MarsagliaDev rng;
+        uint32_t     neighbor;
+        uint32_t     pad0;
+        // [48,64) construction constants
+        int32_t  commFreq;
+        uint32_t pad1;
+        uint64_t pad2;
+        // [64,160) statistics
         Accumulator<int32_t> count[4];
     };
-    static constexpr uint32_t STORED_BYTES  = sizeof(State);
+    static constexpr uint32_t STORE_END = 48, CONST_END = 64, STATS_END = 160;
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
@@ -329,8 +344,10 @@ struct RngElement
         uint64_t last[5];
         uint64_t hash;
         uint32_t kind, a, b, c, d; // generator state: mersenne idx in a; marsaglia z,w in a,b; xorshift x,y,z,w
+        uint32_t pad0;
+        uint64_t pad1;
     };
-    static constexpr uint32_t STORED_BYTES  = sizeof(State);
+    static constexpr uint32_t STORE_END = 96, CONST_END = 96, STATS_END = 96;
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)

@@ -77,6 +77,19 @@ struct Ctrl
     uint32_t           had_primary, pad;
 };
 
+// Per-component engine control block: everything the dispatch kernel needs about a component besides its element
+// state, in one 32-byte record (two 16-byte loads; only the first half is ever written back).
+struct CompCtl
+{
+    uint64_t next_tick; // next clock tick time, TIME_NEVER when the component has no (active) clock
+    uint32_t send_seq;  // per-component send sequence (link-FIFO tie-break)
+    uint32_t deliv_seq; // deliveries so far (trace index)
+    uint64_t period;    // clock period in cycles, 0 = none          -- constant
+    uint32_t type;      // element type code                        -- constant
+    uint32_t pad;
+};
+static_assert(sizeof(CompCtl) == 32, "CompCtl must be 32 bytes");
+
 struct Dev
 {
     Ctrl*           ctrl;
@@ -86,20 +99,18 @@ struct Dev
     uint32_t        P0, nport_local;
     uint32_t        rank, n_ranks;
     const uint32_t* rank_comp_begin; // [n_ranks+1] (device)
-    const uint32_t* comp_type;
+    const uint32_t* comp_type; // [n_local] (setup / hooks; the hot path reads CompCtl)
     const int64_t*  comp_param;
     const uint32_t* port_off; // [n_local+1] GLOBAL directed-port ids
     const uint4*    link;     // [nport_local] {dst_port, dst_comp, latency lo, latency hi}
-    const uint64_t* clock_period;
-    uint64_t*       next_tick;
-    uint32_t*       send_seq;
+    const uint64_t* clock_period; // [n_local] (setup only)
+    CompCtl*        ctl;          // [n_local] per-component engine control block, 32 B
     uint8_t*        state;
     uint32_t        state_stride;
     uint8_t*        aux;
     uint32_t        aux_stride;
-    uint64_t*       ev_time;
-    uint64_t*       ev_dst_seq;
-    uint64_t*       ev_payload;
+    ulonglong2*     ev;         // calendar records {time, dst_port<<32 | seq}, 16 B each
+    uint64_t*       ev_payload; // only when an element of the model carries a payload
     uint32_t*       bin_count; // [W*nbins]
     unsigned long long* outbox;    // [n_ranks][1 + outbox_cap*4]
     unsigned long long* inbox;     // same shape, filled by the driver's exchange
@@ -111,7 +122,6 @@ struct Dev
     uint32_t*       tr_port;
     uint32_t*       tr_idx;
     uint64_t*       tr_payload;
-    uint32_t*       deliv_seq;
     uint64_t        trace_cap;
     int             stats_on, has_payload;
 };
@@ -173,8 +183,7 @@ emit(const Dev& d, uint64_t k, uint64_t time, uint32_t dst_port, uint32_t dst_co
         return;
     }
     const uint64_t off = (uint64_t)idx * d.cap + pos;
-    d.ev_time[off]     = time;
-    d.ev_dst_seq[off]  = ((uint64_t)dst_port << 32) | seq;
+    d.ev[off] = make_ulonglong2(time, ((unsigned long long)dst_port << 32) | seq);
     if ( d.has_payload ) d.ev_payload[off] = payload;
 }
 
@@ -267,30 +276,31 @@ with_element(uint32_t type, F&& f)
 }
 
 // Element state moves between HBM and registers in 16-byte pieces (state_stride is a multiple of 16).  `bytes` may be
-// a prefix of the struct: construction constants are loaded but never written back, register-only scratch at the end
-// of a State is neither loaded nor stored.
+// State layout convention: [0, STORE_END) mutable core (always loaded and stored), [STORE_END, CONST_END) construction
+// constants (loaded, never stored), [CONST_END, STATS_END) statistics (loaded and stored only when statistics are
+// enabled), then register-only scratch (neither).  All boundaries are multiples of 16.
 template <class S>
 __device__ __forceinline__ void
-load_state(S& s, const uint8_t* p, uint32_t bytes)
+load_state(S& s, const uint8_t* p, uint32_t from, uint32_t to)
 {
     static_assert(sizeof(S) % 8 == 0, "element State must be a multiple of 8 bytes");
     const uint4* src = reinterpret_cast<const uint4*>(p);
     uint4        tmp[(sizeof(S) + 15) / 16];
 #pragma unroll
     for ( int i = 0; i < (int)((sizeof(S) + 15) / 16); ++i )
-        if ( (uint32_t)i * 16 < bytes ) tmp[i] = src[i];
+        if ( (uint32_t)i * 16 >= from && (uint32_t)i * 16 < to ) tmp[i] = src[i];
     memcpy(&s, tmp, sizeof(S));
 }
 template <class S>
 __device__ __forceinline__ void
-store_state(const S& s, uint8_t* p, uint32_t bytes)
+store_state(const S& s, uint8_t* p, uint32_t from, uint32_t to)
 {
     uint4* dst = reinterpret_cast<uint4*>(p);
     uint4  tmp[(sizeof(S) + 15) / 16];
     memcpy(tmp, &s, sizeof(S));
 #pragma unroll
     for ( int i = 0; i < (int)((sizeof(S) + 15) / 16); ++i )
-        if ( (uint32_t)i * 16 < bytes ) dst[i] = tmp[i];
+        if ( (uint32_t)i * 16 >= from && (uint32_t)i * 16 < to ) dst[i] = tmp[i];
 }
 
 // ---- construct + setup(): performWireUp (simulation.cc:824-859) and setup() (simulation.cc:969-987)
@@ -304,16 +314,15 @@ setup_kernel(Dev d)
     CtxT<false>    ctx { d, 0, 0, 0, d.c0 + lc, p0, d.port_off[lc + 1] - p0, d.aux + (uint64_t)lc * d.aux_stride,
                          0, 0, d.stats_on, d.link + (p0 - d.P0), Stage {}, nullptr, 0, 0 };
     const uint64_t period = d.clock_period[lc];
-    d.next_tick[lc]       = period ? period : TIME_NEVER; // first tick at `period`, never at 0 (clock.cc:400-420)
     with_element(type, [&](auto el) {
         using E = decltype(el);
         typename E::State s;
         E::construct(ctx, s, d.comp_param + (uint64_t)lc * NPARAM);
         E::setup(ctx, s);
-        store_state(s, d.state + (uint64_t)lc * d.state_stride, E::PERSIST_BYTES);
+        store_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::PERSIST_BYTES);
     });
-    d.send_seq[lc] = ctx.seq;
-    if ( d.deliv_seq ) d.deliv_seq[lc] = 0;
+    // first tick at `period`, never at 0 (clock.cc:400-420)
+    d.ctl[lc] = CompCtl { period ? period : TIME_NEVER, ctx.seq, 0, period, type, 0 };
     if ( ctx.sent ) {
         atomicAdd(&d.ctrl->events_sent, (unsigned long long)ctx.sent);
         atomicAdd((unsigned long long*)&d.ctrl->local[CW_PENDING], (unsigned long long)ctx.sent);
@@ -358,6 +367,24 @@ key_less(uint32_t ta, uint32_t da, uint32_t qa, uint32_t tb, uint32_t db, uint32
     return (ta < tb) || (ta == tb && (da < db || (da == db && (int32_t)(qa - qb) < 0)));
 }
 
+#ifdef SSTB200_TIMING
+// phase timestamps (globaltimer, ns) of every CTA of the LAST window: [nbins][8]; profiles/phase_times.py reads them
+__device__ unsigned long long g_phase_times[1 << 20];
+__device__ __forceinline__ unsigned long long
+gtimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define PHASE_MARK(i)                                                                    \
+    do {                                                                                 \
+        if ( threadIdx.x == 0 && blockIdx.x < (1 << 17) ) g_phase_times[blockIdx.x * 8 + (i)] = gtimer(); \
+    } while ( 0 )
+#else
+#define PHASE_MARK(i)
+#endif
+
 // ---- one lookahead window for one block of 256 components
 template <bool PAYLOAD>
 #ifndef SSTB200_MIN_BLOCKS
@@ -379,6 +406,7 @@ dispatch_kernel(Dev d)
     const uint32_t tid   = threadIdx.x;
     const uint32_t lane  = tid & 31;
 
+    PHASE_MARK(0);
     // shared-memory carve-up (host: engine_create computes the same sizes)
     uint4*    s_link     = reinterpret_cast<uint4*>(smem_raw);                          // [lmax]
     uint64_t* s_pay      = reinterpret_cast<uint64_t*>(smem_raw + (size_t)d.lmax * 16); // [emax] (PAYLOAD only)
@@ -400,8 +428,7 @@ dispatch_kernel(Dev d)
     // ---- prologue: everything here is independent global traffic issued back to back.  The first 256 records of the
     // bin are loaded before its fill count is known (the slots exist; what is past the count is ignored).
     const uint32_t n_in     = d.bin_count[slot * d.nbins + bin];
-    const uint64_t t_first  = d.ev_time[(uint64_t)(slot * d.nbins + bin) * d.cap + tid];
-    const uint64_t ds_first = d.ev_dst_seq[(uint64_t)(slot * d.nbins + bin) * d.cap + tid];
+    const ulonglong2 ev_first = d.ev[(uint64_t)(slot * d.nbins + bin) * d.cap + tid];
     uint64_t       pl_first = 0;
     if ( PAYLOAD ) pl_first = d.ev_payload[(uint64_t)(slot * d.nbins + bin) * d.cap + tid];
     {
@@ -420,9 +447,11 @@ dispatch_kernel(Dev d)
                 using E = decltype(el);
                 E::prefetch(d.state + (uint64_t)lc0 * d.state_stride, d.aux + (uint64_t)lc0 * d.aux_stride);
             });
+            prefetch_l2(&d.ctl[lc0]);
         }
     }
     __syncthreads();
+    PHASE_MARK(1);
     const uint32_t blk_port0     = s_port_off[0];
     const uint32_t blk_nports    = s_port_off[BLOCK] - blk_port0;
     const bool     links_in_smem = blk_nports <= d.lmax;
@@ -480,16 +509,16 @@ dispatch_kernel(Dev d)
             }
         }
     };
-    if ( tid < n_in ) classify(t_first, ds_first, pl_first);
+    if ( tid < n_in ) classify(ev_first.x, ev_first.y, pl_first);
     for ( uint32_t i = tid + BLOCK; i < n_in; i += BLOCK ) {
-        const uint64_t t  = d.ev_time[bin_base + i];
-        const uint64_t ds = d.ev_dst_seq[bin_base + i];
-        uint64_t       pl = 0;
+        const ulonglong2 ev = d.ev[bin_base + i];
+        uint64_t         pl = 0;
         if ( PAYLOAD ) pl = d.ev_payload[bin_base + i];
-        classify(t, ds, pl);
+        classify(ev.x, ev.y, pl);
     }
     __pipeline_wait_prior(0);
     __syncthreads();
+    PHASE_MARK(2);
     const uint32_t n_due = s_misc[0];
     if ( n_due > d.emax ) {
         if ( tid == 0 ) raise_error(d, ERR_SMEM_OVERFLOW, bin, n_due, d.emax);
@@ -531,6 +560,7 @@ dispatch_kernel(Dev d)
     }
     __syncthreads();
 
+    PHASE_MARK(3);
     // ---- phase 3: thread t runs component s_order[t]: walks its segment in delivery order, merged with the
     // component's clock ticks; sends are staged in the slots the component has already consumed
     const uint32_t  c      = s_order[tid];
@@ -540,20 +570,22 @@ dispatch_kernel(Dev d)
     uint16_t*       seg    = s_perm + s_off[c];
     uint32_t        delivered = 0, ticks = 0, sent = 0, clocks_stopped = 0;
     if ( valid ) {
-        const uint64_t period    = d.clock_period[lc];
-        uint64_t       next_tick = d.next_tick[lc];
+        const uint4*   ctlp      = reinterpret_cast<const uint4*>(&d.ctl[lc]);
+        const uint4    c_lo = ctlp[0], c_hi = ctlp[1];
+        uint64_t       next_tick = ((uint64_t)c_lo.y << 32) | c_lo.x;
+        const uint64_t period    = ((uint64_t)c_hi.y << 32) | c_hi.x;
         const bool     has_work  = my_cnt > 0 || next_tick < T_end;
         if ( has_work ) {
             const uint32_t p0 = s_port_off[c];
             CtxT<true>     ctx { d, T, k, T, d.c0 + lc, p0, s_port_off[c + 1] - p0,
-                                 d.aux + (uint64_t)lc * d.aux_stride, d.send_seq[lc], 0, d.stats_on,
+                                 d.aux + (uint64_t)lc * d.aux_stride, c_lo.z, 0, d.stats_on,
                                  links_in_smem ? (const uint4*)(s_link + (p0 - blk_port0)) : d.link + (p0 - d.P0),
                                  Stage { s_time, s_dst, s_seq, s_cr, PAYLOAD ? s_pay : nullptr }, seg, 0, 0 };
-            uint32_t       dseq = d.deliv_seq ? d.deliv_seq[lc] : 0;
-            with_element(d.comp_type[lc], [&](auto el) {
+            uint32_t       dseq = c_lo.w;
+            with_element(c_hi.z, [&](auto el) {
                 using E = decltype(el);
                 typename E::State s;
-                load_state(s, d.state + (uint64_t)lc * d.state_stride, E::PERSIST_BYTES);
+                load_state(s, d.state + (uint64_t)lc * d.state_stride, 0, d.stats_on ? E::STATS_END : E::CONST_END);
                 E::beginWindow(ctx, s, my_cnt); // issues the element's first loads (MT19937 read-ahead) ...
                 // ... which the sort below overlaps.  (b) order inside the segment: (time, port, sequence).  Insertion sort by the owning thread; the lanes of a
                 // warp own components with (nearly) equal event counts, so the loops stay converged.
@@ -607,15 +639,21 @@ dispatch_kernel(Dev d)
                     E::handleEvent(ctx, s, (int)port, pl);
                     delivered++;
                 }
-                store_state(s, d.state + (uint64_t)lc * d.state_stride, E::STORED_BYTES);
+                store_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::STORE_END);
+                if ( d.stats_on ) store_state(s, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
             });
-            d.send_seq[lc]  = ctx.seq;
-            d.next_tick[lc] = next_tick;
-            if ( d.deliv_seq ) d.deliv_seq[lc] = dseq;
+            *reinterpret_cast<uint4*>(&d.ctl[lc]) =
+                make_uint4((uint32_t)next_tick, (uint32_t)(next_tick >> 32), ctx.seq, dseq);
             sent = ctx.sent;
         }
     }
+    if ( threadIdx.x == 255 ) {
+#ifdef SSTB200_TIMING
+        if ( blockIdx.x < (1 << 17) ) g_phase_times[blockIdx.x * 8 + 7] = gtimer(); // lightest warp done with phase 3
+#endif
+    }
     __syncthreads();
+    PHASE_MARK(4);
 
     // ---- phase 4: flush the staged sends, the whole CTA over all slots (balanced: ~4 records per thread however the
     // events were distributed over components).  Destination bins are counted in a small shared hash table
@@ -721,13 +759,13 @@ dispatch_kernel(Dev d)
             }
             else {
                 const uint64_t off = (uint64_t)ky * d.cap + pos;
-                d.ev_time[off]     = tm;
-                d.ev_dst_seq[off]  = ds;
+                d.ev[off]          = make_ulonglong2(tm, ds);
                 if ( PAYLOAD ) d.ev_payload[off] = s_pay[e];
             }
         }
     }
 
+    PHASE_MARK(5);
     // ---- phase 5: fold counters (one atomic per warp), recycle the bin
     {
         uint32_t v0 = delivered, v1 = ticks, v2 = sent, v3 = clocks_stopped, v4 = dropped;
@@ -868,10 +906,10 @@ results_kernel(Dev d, uint64_t* out, uint32_t words)
 #pragma unroll
     for ( int i = 0; i < NRESULT; ++i )
         r[i] = 0;
-    with_element(d.comp_type[lc], [&](auto el) {
+    with_element(d.ctl[lc].type, [&](auto el) {
         using E = decltype(el);
         typename E::State s;
-        load_state(s, d.state + (uint64_t)lc * d.state_stride, E::PERSIST_BYTES);
+        load_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::PERSIST_BYTES);
         E::results(s, r);
     });
 #pragma unroll
@@ -1136,6 +1174,14 @@ struct sstb200_engine
     }
 };
 
+#ifdef SSTB200_TIMING
+extern "C" int
+sstb200_debug_phase_times(unsigned long long* out, uint32_t n_words)
+{
+    return cudaMemcpyFromSymbol(out, g_phase_times, (size_t)n_words * 8) == cudaSuccess ? 0 : -2;
+}
+#endif
+
 extern "C" {
 
 int
@@ -1317,13 +1363,11 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     }
     rc |= e->upload(&d.clock_period, m->clock_period + c0, d.n_local);
     if ( n_ranks > 1 ) rc |= e->upload(&d.rank_comp_begin, o->rank_comp_begin, (size_t)n_ranks + 1);
-    rc |= e->alloc(&d.next_tick, d.n_local);
-    rc |= e->alloc(&d.send_seq, d.n_local);
+    rc |= e->alloc(&d.ctl, d.n_local);
     rc |= e->alloc(&d.state, (size_t)d.n_local * d.state_stride);
     rc |= e->alloc(&d.aux, (size_t)d.n_local * d.aux_stride, false);
     const size_t nev = (size_t)d.W * d.nbins * d.cap;
-    rc |= e->alloc(&d.ev_time, nev, false);
-    rc |= e->alloc(&d.ev_dst_seq, nev, false);
+    rc |= e->alloc(&d.ev, nev, false);
     if ( has_payload ) rc |= e->alloc(&d.ev_payload, nev, false);
     rc |= e->alloc(&d.bin_count, (size_t)d.W * d.nbins);
     rc |= e->alloc(&d.ctrl, 1);
@@ -1341,7 +1385,6 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         rc |= e->alloc(&d.tr_port, d.trace_cap);
         rc |= e->alloc(&d.tr_idx, d.trace_cap);
         rc |= e->alloc(&d.tr_payload, d.trace_cap);
-        rc |= e->alloc(&d.deliv_seq, d.n_local);
     }
     rc |= e->alloc(&e->d_results, (size_t)d.n_local * NRESULT);
     if ( rc ) {
