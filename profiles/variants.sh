@@ -1,19 +1,28 @@
 #!/bin/bash
-# build variants on the GPU box and time mesh 4096^2 (kernel only)
+# build variants on the GPU box and time mesh 4096^2 / PHOLD 1024^2 (kernel only)
 run() { python - <<PY
 import json,subprocess,sys
-out=subprocess.run([sys.executable,"bench.py","--steps","20","--warmup","5","--no-cpu-baseline","--no-e2e","--smem-events","$2","--bin-capacity","$3"],capture_output=True,text=True)
-try:
-    d=json.loads(out.stdout.strip().splitlines()[-1]); print("$1 smem_events $2 cap $3 mesh4096",round(d["value"]/1e9,2),"G ev/s",round(d["ms_per_step"],3),"ms")
-except Exception as e:
-    print("FAILED",out.stdout[-300:],out.stderr[-600:])
+for wl,extra in (("mesh",[]),("phold",["--x","1024","--y","1024","--warmup","10"])):
+    out=subprocess.run([sys.executable,"bench.py","--workload",wl,"--steps","20","--warmup","5","--no-cpu-baseline","--no-e2e"]+extra,capture_output=True,text=True)
+    try:
+        d=json.loads(out.stdout.strip().splitlines()[-1]); print("$1",wl,round(d["value"]/1e9,2),"G ev/s",round(d["ms_per_step"],3),"ms")
+    except Exception as e:
+        print("FAILED",out.stdout[-300:],out.stderr[-600:])
 PY
 }
-SSTB200_NVCC_EXTRA="-DSSTB200_BLOCK=128 -DSSTB200_MIN_BLOCKS=8" python -m sst_core_b200.build --force > gpurun_out/build_a.log 2>&1; grep -A2 "dispatch_kernelILb0" gpurun_out/build_a.log | grep -E "registers"
-run "block128/min8" 768 1024
-run "block128/min8" 1024 1024
-SSTB200_NVCC_EXTRA="-DSSTB200_BLOCK=128 -DSSTB200_MIN_BLOCKS=6" python -m sst_core_b200.build --force > gpurun_out/build_b.log 2>&1; grep -A2 "dispatch_kernelILb0" gpurun_out/build_b.log | grep -E "registers"
-run "block128/min6" 768 1024
-SSTB200_NVCC_EXTRA="-DSSTB200_BLOCK=512 -DSSTB200_MIN_BLOCKS=2" python -m sst_core_b200.build --force > gpurun_out/build_c.log 2>&1; grep -A2 "dispatch_kernelILb0" gpurun_out/build_c.log | grep -E "registers"
-run "block512/min2" 3072 4096
+for v in "-DSSTB200_SPEC=1" "-DSSTB200_SPEC=2" "-DSSTB200_SPEC=4"; do
+  SSTB200_NVCC_EXTRA="$v" python -m sst_core_b200.build --force > gpurun_out/build_v.log 2>&1; grep -A2 "dispatch_kernelILb0" gpurun_out/build_v.log | grep -E "spill" 
+  run "$v"
+done
 python -m sst_core_b200.build --force > /dev/null 2>&1
+python - <<'PY'
+import time, sys
+sys.path.insert(0, '.')
+from sst_core_b200 import models
+from sst_core_b200.run import simulate_model
+m = models.mesh_model(6, 6)
+simulate_model(m)
+for i in range(3):
+    t0 = time.perf_counter(); res, st = simulate_model(m); dt = time.perf_counter() - t0
+    print(f"mesh 6x6 10us end-to-end {dt*1e3:.1f} ms")
+PY

@@ -24,6 +24,10 @@
 #pragma once
 #include "rng.cuh"
 
+#if defined(__CUDACC__)
+#include <cuda_pipeline.h>
+#endif
+
 #include <cstdint>
 #include <limits>
 
@@ -108,17 +112,58 @@ struct MeshElement
         Accumulator<uint64_t> mcnt; // RouteMessage "msg_count"
         uint64_t              pad2;
         // register-only scratch, valid inside one window
-        MtPairCache cache;
+#ifdef SSTB200_MESH_STAGE_MT
+        uint32_t win_pair, win_n; // pairs drawn from the staged words so far / pairs staged (0 = nothing staged)
+#endif
+        MtPairCache cache; // read-ahead of the MT19937 words the next two pairs need
     };
     static constexpr uint32_t STORE_END = 16, CONST_END = 32, STATS_END = 80, PERSIST_BYTES = 80;
-    // start of a window in which this component has `n_events` events: issue the MT19937 read-ahead now, so that
-    // it is in flight while the engine orders the component's events
+    // shared-memory scratch: the MT19937 words this window's draws will read, 4 per event (+3 per component)
+#ifdef SSTB200_MESH_STAGE_MT
+    static constexpr uint32_t SCRATCH_PER_EVENT = 4, SCRATCH_FIXED = 4;
+#else
+    // measured (profiles/r01_notes.md): staging costs 28 KB of shared memory per CTA (3 instead of 4 CTAs per SM) and
+    // the heavy warp of a block is bound by its instruction chain, not by the MT19937 loads -- the register
+    // read-ahead (MtPairCache) wins.  The staged path stays available for elements whose draws are load-bound.
+    static constexpr uint32_t SCRATCH_PER_EVENT = 0, SCRATCH_FIXED = 0;
+#endif
+    // Start of a window in which this component has `n_events` events.  Every event draws one PAIR; pair k (index
+    // i + 2k, even) reads mt[i+2k .. i+2k+2] and mt[i+2k+397], mt[i+2k+398]: two contiguous runs of 2n+1 words.
+    // Copy both runs into shared memory now with ALL loads in flight at once (one memory round trip for the whole
+    // window instead of one per event), as 8-byte chunks.  Pairs never read what an earlier pair of the same window
+    // wrote (those are words i .. i+2n-1; a pair's reads start at its own index and at +397), provided the a-run does
+    // window is short enough: pair k reads mt[i+2k+398], which pair k-114 wrote (2*114+396 = 624), so at most
+    // MT_STAGE_MAX_PAIRS = 100 pairs are staged; busier components fall back to direct draws.
+#ifdef SSTB200_MESH_STAGE_MT
+    template <class Ctx>
+    __device__ static void beginWindow(Ctx& ctx, State& s, uint32_t n_events)
+    {
+        s.win_pair    = 0;
+        s.win_n       = 0;
+        s.cache.valid = 0;
+        const uint32_t i = s.mt_idx;
+        if ( n_events && (i & 1u) == 0 && ctx.scratch == nullptr ) mt_cache_fill((const uint32_t*)ctx.aux, i, s.cache);
+        if ( n_events == 0 || (i & 1u) || n_events > MT_STAGE_MAX_PAIRS || ctx.scratch == nullptr ) return;
+        // asynchronous copies (LDGSTS): nothing waits until the first draw, see mesh_words_ready()
+        const uint32_t* mt  = (const uint32_t*)ctx.aux;
+        uint32_t*       scr = ctx.scratch; // a-run: scr[0 .. 2n+1]; b-run: mt[i+397+j] at scr[2n+3+j], j = 0 .. 2n
+        for ( uint32_t c = 0; c <= n_events; ++c )
+            __pipeline_memcpy_async(scr + 2 * c, mt + mt_wrap(mt_wrap(i + 2 * c)), 8);
+        __pipeline_memcpy_async(scr + 2 * n_events + 3, mt + mt_wrap(i + MT_M), 4);
+        for ( uint32_t c = 0; c < n_events; ++c )
+            __pipeline_memcpy_async(scr + 2 * n_events + 4 + 2 * c, mt + mt_wrap(mt_wrap(i + MT_M + 1 + 2 * c)), 8);
+        __pipeline_commit();
+        s.win_n = n_events;
+    }
+#else
+    // issue the read-ahead loads now: they are in flight while the engine orders the component's events
     template <class Ctx>
     __device__ static void beginWindow(Ctx& ctx, State& s, uint32_t n_events)
     {
         s.cache.valid = 0;
         if ( n_events && (s.mt_idx & 1u) == 0 ) mt_cache_fill((const uint32_t*)ctx.aux, s.mt_idx, s.cache);
     }
+#endif
     // dispatch prologue hook: pull towards L2 the MT19937 words the next handful of draws will read
     // (words idx.. and idx+397.. mod 624), so that the per-event draws hit L2 instead of paying an HBM round trip each
     __device__ static void prefetch(const uint8_t* state, const uint8_t* aux)
@@ -162,7 +207,17 @@ struct MeshElement
     {
         s.message_count++;
         uint32_t r0, r1; // the two draws of RouteMessage::send
-        mt_u32x2_cached((uint32_t*)ctx.aux, s.mt_idx, s.cache, r0, r1);
+#ifdef SSTB200_MESH_STAGE_MT
+        if ( s.win_pair < s.win_n ) { // from the words staged by beginWindow
+            const uint32_t  n = s.win_n, kq = s.win_pair++;
+            if ( kq == 0 ) __pipeline_wait_prior(0); // the staged words have landed
+            const uint32_t* a = ctx.scratch + 2 * kq;
+            const uint32_t* b = ctx.scratch + 2 * n + 3 + 2 * kq;
+            mt_pair_from_words((uint32_t*)ctx.aux, s.mt_idx, a[0], a[1], a[2], b[0], b[1], r0, r1);
+        }
+        else
+#endif
+            mt_u32x2_cached((uint32_t*)ctx.aux, s.mt_idx, s.cache, r0, r1);
         // nextport = r0 % ports.size(); portnum = r1 % counts[nextport] (both draws are always made)
         const uint32_t ng       = s.ngroups;
         const uint32_t nextport = (ng & (ng - 1)) == 0 ? (r0 & (ng - 1)) : r0 % ng;
@@ -210,6 +265,7 @@ struct PholdElement
         uint64_t              pad1;
     };
     static constexpr uint32_t STORE_END = 32, CONST_END = 48, STATS_END = 96;
+    static constexpr uint32_t SCRATCH_PER_EVENT = 0, SCRATCH_FIXED = 0;
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
@@ -280,6 +336,7 @@ struct ClockNodeElement
         Accumulator<int32_t> count[4];
     };
     static constexpr uint32_t STORE_END = 48, CONST_END = 64, STATS_END = 160;
+    static constexpr uint32_t SCRATCH_PER_EVENT = 0, SCRATCH_FIXED = 0;
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
@@ -348,6 +405,7 @@ struct RngElement
         uint64_t pad1;
     };
     static constexpr uint32_t STORE_END = 96, CONST_END = 96, STATS_END = 96;
+    static constexpr uint32_t SCRATCH_PER_EVENT = 0, SCRATCH_FIXED = 0;
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
@@ -445,6 +503,7 @@ struct ElementInfo
     uint32_t    state_bytes;
     uint32_t    aux_bytes;
     int         has_payload;
+    uint32_t    scratch_per_event, scratch_fixed; // shared-memory scratch words per due event / per component
     const char* description;
 };
 

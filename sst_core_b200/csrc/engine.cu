@@ -96,6 +96,8 @@ struct Dev
     uint32_t        n_local, c0, nbins, W, cap, emax;
     uint32_t        lmax, uniform_nports; // link rows staged per block; ports per component when uniform (else 0)
     uint32_t        uniform_shift;        // log2(uniform_nports) when it is a power of two, else 32
+    uint32_t        uniform_type;         // the element type when every local component has the same one, else 0
+    uint32_t        scr_per_event, scr_fixed; // shared-memory scratch words an element gets per due event / per component
     uint32_t        P0, nport_local;
     uint32_t        rank, n_ranks;
     const uint32_t* rank_comp_begin; // [n_ranks+1] (device)
@@ -217,6 +219,7 @@ struct CtxT
     uint32_t     sent;
     int          stats_on;
     const uint4* links; // this component's link row (shared memory when the block's rows were staged, else global)
+    uint32_t*    scratch; // shared memory, scr_per_event * (events this window) + scr_fixed words (nullptr if none)
     // out-staging (STAGED only): this component's consumed slots are seg[free_head .. free_tail)
     Stage           st;
     const uint16_t* seg;
@@ -312,7 +315,7 @@ setup_kernel(Dev d)
     const uint32_t type = d.comp_type[lc];
     const uint32_t p0   = d.port_off[lc];
     CtxT<false>    ctx { d, 0, 0, 0, d.c0 + lc, p0, d.port_off[lc + 1] - p0, d.aux + (uint64_t)lc * d.aux_stride,
-                         0, 0, d.stats_on, d.link + (p0 - d.P0), Stage {}, nullptr, 0, 0 };
+                         0, 0, d.stats_on, d.link + (p0 - d.P0), nullptr, Stage {}, nullptr, 0, 0 };
     const uint64_t period = d.clock_period[lc];
     with_element(type, [&](auto el) {
         using E = decltype(el);
@@ -424,13 +427,27 @@ dispatch_kernel(Dev d)
     uint32_t* s_hbase    = s_hist + 32;             // [32]
     uint16_t* s_perm     = reinterpret_cast<uint16_t*>(s_hbase + 32); // [emax] per-component segments
     uint16_t* s_order    = s_perm + d.emax;                           // [BLOCK] thread -> component of the block
+    uint32_t* s_scratch  = reinterpret_cast<uint32_t*>( // [scr_per_event*emax + scr_fixed*BLOCK], 16-byte aligned
+        (reinterpret_cast<uintptr_t>(s_order + BLOCK) + 15) & ~(uintptr_t)15);
 
-    // ---- prologue: everything here is independent global traffic issued back to back.  The first 256 records of the
-    // bin are loaded before its fill count is known (the slots exist; what is past the count is ignored).
+    // ---- prologue: everything here is independent global traffic issued back to back.  The first 1024 records of
+    // the bin are loaded before its fill count is known (the slots exist; what is past the count is ignored).
     const uint32_t n_in     = d.bin_count[slot * d.nbins + bin];
-    const ulonglong2 ev_first = d.ev[(uint64_t)(slot * d.nbins + bin) * d.cap + tid];
-    uint64_t       pl_first = 0;
-    if ( PAYLOAD ) pl_first = d.ev_payload[(uint64_t)(slot * d.nbins + bin) * d.cap + tid];
+#ifndef SSTB200_SPEC
+#define SSTB200_SPEC 4
+#endif
+    constexpr int SPEC = SSTB200_SPEC;
+    ulonglong2    ev_spec[SPEC];
+    uint64_t      pl_spec[SPEC];
+#pragma unroll
+    for ( int b = 0; b < SPEC; ++b ) {
+        const uint32_t i = tid + b * BLOCK;
+        pl_spec[b]       = 0;
+        if ( i < d.cap ) {
+            ev_spec[b] = d.ev[(uint64_t)(slot * d.nbins + bin) * d.cap + i];
+            if ( PAYLOAD ) pl_spec[b] = d.ev_payload[(uint64_t)(slot * d.nbins + bin) * d.cap + i];
+        }
+    }
     {
         const uint32_t lc0 = bin * BLOCK + tid;
         s_port_off[tid]    = d.port_off[lc0 <= d.n_local ? lc0 : d.n_local];
@@ -443,7 +460,7 @@ dispatch_kernel(Dev d)
         if ( tid < 32 ) s_hist[tid] = 0;
         if ( lc0 < d.n_local ) {
             // element hook: start pulling the state line and the aux words the handlers will touch towards L2
-            with_element(d.comp_type[lc0], [&](auto el) {
+            with_element(d.uniform_type ? d.uniform_type : d.comp_type[lc0], [&](auto el) {
                 using E = decltype(el);
                 E::prefetch(d.state + (uint64_t)lc0 * d.state_stride, d.aux + (uint64_t)lc0 * d.aux_stride);
             });
@@ -509,8 +526,10 @@ dispatch_kernel(Dev d)
             }
         }
     };
-    if ( tid < n_in ) classify(ev_first.x, ev_first.y, pl_first);
-    for ( uint32_t i = tid + BLOCK; i < n_in; i += BLOCK ) {
+#pragma unroll
+    for ( int b = 0; b < SPEC; ++b )
+        if ( tid + b * BLOCK < n_in ) classify(ev_spec[b].x, ev_spec[b].y, pl_spec[b]);
+    for ( uint32_t i = tid + SPEC * BLOCK; i < n_in; i += BLOCK ) {
         const ulonglong2 ev = d.ev[bin_base + i];
         uint64_t         pl = 0;
         if ( PAYLOAD ) pl = d.ev_payload[bin_base + i];
@@ -580,9 +599,10 @@ dispatch_kernel(Dev d)
             CtxT<true>     ctx { d, T, k, T, d.c0 + lc, p0, s_port_off[c + 1] - p0,
                                  d.aux + (uint64_t)lc * d.aux_stride, c_lo.z, 0, d.stats_on,
                                  links_in_smem ? (const uint4*)(s_link + (p0 - blk_port0)) : d.link + (p0 - d.P0),
+                                 d.scr_per_event | d.scr_fixed ? s_scratch + d.scr_per_event * s_off[c] + d.scr_fixed * c : nullptr,
                                  Stage { s_time, s_dst, s_seq, s_cr, PAYLOAD ? s_pay : nullptr }, seg, 0, 0 };
             uint32_t       dseq = c_lo.w;
-            with_element(c_hi.z, [&](auto el) {
+            with_element(d.uniform_type ? d.uniform_type : c_hi.z, [&](auto el) {
                 using E = decltype(el);
                 typename E::State s;
                 load_state(s, d.state + (uint64_t)lc * d.state_stride, 0, d.stats_on ? E::STATS_END : E::CONST_END);
@@ -671,7 +691,7 @@ dispatch_kernel(Dev d)
             ht_cnt[tid] = 0;
         }
         __syncthreads();
-        constexpr int MAXR = 8; // slots tid, tid+256, ... per thread in registers between the passes (2048 slots)
+        constexpr int MAXR = 6; // slots tid, tid+256, ... per thread in registers between the passes (1536 slots)
         uint32_t      r_key[MAXR], r_rank[MAXR], r_ent[MAXR];
         auto          classify_out = [&](uint32_t e, uint32_t& ky_out, uint32_t& ent_out, uint32_t& rank_out) {
             ent_out = 0xFFFFFFFFu;
@@ -1051,13 +1071,13 @@ rng_dist_kernel(int dist, const double* params, int np, int kind, uint64_t s1, u
 // ================================================================================================ host side
 static const ElementInfo kElements[] = {
     { TYPE_MESH, MeshElement::ELI_NAME, MeshElement::PERSIST_BYTES, MeshElement::AUX_BYTES,
-        MeshElement::HAS_PAYLOAD, "message_mesh enclosing component with message_port/port_slot/route_message" },
+        MeshElement::HAS_PAYLOAD, MeshElement::SCRATCH_PER_EVENT, MeshElement::SCRATCH_FIXED, "message_mesh enclosing component with message_port/port_slot/route_message" },
     { TYPE_PHOLD, PholdElement::ELI_NAME, PholdElement::PERSIST_BYTES, PholdElement::AUX_BYTES,
-        PholdElement::HAS_PAYLOAD, "PHOLD-style node, integer delays, 8-byte payload" },
+        PholdElement::HAS_PAYLOAD, PholdElement::SCRATCH_PER_EVENT, PholdElement::SCRATCH_FIXED, "PHOLD-style node, integer delays, 8-byte payload" },
     { TYPE_CLOCKNODE, ClockNodeElement::ELI_NAME, ClockNodeElement::PERSIST_BYTES,
-        ClockNodeElement::AUX_BYTES, ClockNodeElement::HAS_PAYLOAD, "clock-driven node (coreTestComponent style)" },
+        ClockNodeElement::AUX_BYTES, ClockNodeElement::HAS_PAYLOAD, ClockNodeElement::SCRATCH_PER_EVENT, ClockNodeElement::SCRATCH_FIXED, "clock-driven node (coreTestComponent style)" },
     { TYPE_RNGCOMP, RngElement::ELI_NAME, RngElement::PERSIST_BYTES, RngElement::AUX_BYTES,
-        RngElement::HAS_PAYLOAD, "coreTestRNGComponent: 1 GHz clock drawing from an SST::RNG generator" },
+        RngElement::HAS_PAYLOAD, RngElement::SCRATCH_PER_EVENT, RngElement::SCRATCH_FIXED, "coreTestRNGComponent: 1 GHz clock drawing from an SST::RNG generator" },
 };
 constexpr int kNumElements = (int)(sizeof(kElements) / sizeof(kElements[0]));
 
@@ -1336,6 +1356,19 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
                 ++d.uniform_shift;
         }
     }
+    {
+        uint32_t ut = d.n_local ? m->comp_type[c0] : 0;
+        for ( uint32_t c = c0; c < c1 && ut; ++c )
+            if ( m->comp_type[c] != ut ) ut = 0;
+        d.uniform_type = ut;
+        d.scr_per_event = d.scr_fixed = 0;
+        for ( uint32_t c = c0; c < c1; ++c ) {
+            const ElementInfo* ei = element_by_type(m->comp_type[c]);
+            d.scr_per_event       = std::max(d.scr_per_event, ei->scratch_per_event);
+            d.scr_fixed           = std::max(d.scr_fixed, ei->scratch_fixed);
+            if ( ut ) break; // uniform: the first one says it all
+        }
+    }
     d.state_stride = (state_stride + 15u) & ~15u;
     d.aux_stride   = (aux_stride + 31u) & ~31u;
     d.has_payload  = has_payload;
@@ -1403,7 +1436,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
 
     e->smem_bytes = (size_t)d.lmax * 16 + (size_t)d.emax * (has_payload ? 8 : 0) + (size_t)d.emax * 16 +
                     (size_t)(BLOCK + 1 + BLOCK + BLOCK + BLOCK / 32 + 1 + 4 + 32 + 32) * 4 + (size_t)d.emax * 2 +
-                    (size_t)BLOCK * 2 + 16;
+                    (size_t)BLOCK * 2 + 16 + ((size_t)d.scr_per_event * d.emax + (size_t)d.scr_fixed * BLOCK) * 4 + 16;
     if ( e->smem_bytes > 227 * 1024 ) {
         set_error("engine_create: smem_events too large for 227 KB of shared memory");
         sstb200_engine_destroy(e);

@@ -38,6 +38,9 @@ namespace sstb200 {
 
 constexpr int MT_N = 624;
 constexpr int MT_M = 397;
+// a window's draws may be staged ahead of time only while no pair reads a word an earlier pair of the same window
+// wrote: pair k reads mt[i+2k+398] = the second word pair k-114 wrote.  Stay well below 114.
+constexpr uint32_t MT_STAGE_MAX_PAIRS = 100;
 
 SSTB_HD uint32_t
 mt_temper(uint32_t t)
@@ -134,6 +137,25 @@ SSTB_HD uint32_t
 mt_wrap(uint32_t i)
 {
     return i >= MT_N ? i - MT_N : i;
+}
+
+// One pair at even index i from words already read: a0,a1,a2 = mt[i], mt[i+1], mt[i+2]; b0,b1 = mt[i+397], mt[i+398]
+// (all mod 624).  Writes the two new-generation words back (one 8-byte store) and advances the index.
+SSTB_HD void
+mt_pair_from_words(uint32_t* mt, uint32_t& idx, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b0, uint32_t b1,
+    uint32_t& r0, uint32_t& r1)
+{
+    const uint32_t i  = idx;
+    const uint32_t y0 = (a0 & 0x80000000u) + (a1 & 0x7fffffffu);
+    uint32_t       v0 = b0 ^ (y0 >> 1);
+    if ( y0 & 1u ) v0 ^= 2567483615u;
+    const uint32_t y1 = (a1 & 0x80000000u) + (a2 & 0x7fffffffu);
+    uint32_t       v1 = b1 ^ (y1 >> 1);
+    if ( y1 & 1u ) v1 ^= 2567483615u;
+    *reinterpret_cast<uint2*>(mt + i) = uint2 { v0, v1 };
+    idx = mt_wrap(i + 2);
+    r0  = mt_temper(v0);
+    r1  = mt_temper(v1);
 }
 
 // loads the cache for a pair at even index i (C_j, C_j+1, mt[i+397], E_j)

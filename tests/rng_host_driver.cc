@@ -32,6 +32,29 @@ dev_mt_stream(uint32_t seed, int mode, uint32_t lead, uint64_t n, uint32_t* out)
             out[i] = g.u32();
         return;
     }
+    if ( mode == 4 ) { // windows of `lead`+1, 1, 7, 100 ... pairs, every window staged ahead like MeshElement::beginWindow
+        uint32_t       idx     = 0, wsel = 0;
+        const uint32_t sizes[] = { lead + 1, 1, 7, MT_STAGE_MAX_PAIRS, 3, 113 };
+        static uint32_t scr[4 * 128 + 8];
+        while ( i + 1 < n ) {
+            uint32_t np = sizes[wsel++ % 6];
+            if ( np > MT_STAGE_MAX_PAIRS ) np = MT_STAGE_MAX_PAIRS;
+            for ( uint32_t c = 0; c <= np; ++c ) {
+                scr[2 * c]     = mt[mt_wrap(mt_wrap(idx + 2 * c))];
+                scr[2 * c + 1] = mt[mt_wrap(mt_wrap(idx + 2 * c)) + 1];
+            }
+            uint32_t* scb = scr + 2 * np + 2;
+            for ( uint32_t j = 0; j <= 2 * np; ++j )
+                scb[j] = mt[mt_wrap(mt_wrap(idx + MT_M + j))];
+            for ( uint32_t kq = 0; kq < np && i + 1 < n; ++kq, i += 2 )
+                mt_pair_from_words(mt, idx, scr[2 * kq], scr[2 * kq + 1], scr[2 * kq + 2], scb[2 * kq], scb[2 * kq + 1],
+                    out[i], out[i + 1]);
+        }
+        g.idx = idx;
+        for ( ; i < n; ++i )
+            out[i] = g.u32();
+        return;
+    }
     if ( mode == 0 ) {
         for ( ; i < n; ++i )
             out[i] = g.u32();

@@ -50,6 +50,16 @@ def test_cached_paired_draw_equals_reference_stream(drv, lead):
     assert np.array_equal(out, ref)
 
 
+@pytest.mark.parametrize("lead", [0, 3, 50, 99])
+def test_window_staged_pairs_equal_reference_stream(drv, lead):
+    # MeshElement::beginWindow copies the words a whole window of pairs will read BEFORE any of them is drawn
+    n = 624 * 9 + 2
+    ref, _ = O.rng_u32_stream(0, 31337 + lead, 0, n)
+    out = np.zeros(n, dtype=np.uint32)
+    drv.dev_mt_stream(31337 + lead, 4, lead, n, out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out, ref)
+
+
 def test_marsaglia_and_xorshift(drv):
     n = 5000
     ref, _ = O.rng_u32_stream(1, 1053, 1447, n)
