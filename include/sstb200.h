@@ -91,20 +91,23 @@ int sstb200_engine_setup(sstb200_engine* e);
 int sstb200_engine_run(sstb200_engine* e, uint64_t max_windows, uint32_t check_every, int* finished);
 
 /* Multi-rank stepping (one lookahead window = SyncManager::execute):
- *   dispatch  : deliver this window's events and clock ticks; cross-rank sends land in per-destination outboxes
- *   exchange buffers are DEVICE memory owned by the engine; the driver moves outbox -> peer inbox (NCCL all-to-all)
- *   ingest    : bin received events into the local calendar
- *   advance   : fold the (all-reduced) control words and move to the next window                            */
+ *   dispatch  : deliver this window's events and clock ticks; cross-rank sends land in per-destination outboxes, and
+ *               this rank's control words are written into every outbox header
+ *   exchange  : the DRIVER moves outbox[r] of every rank to inbox[sender] of rank r (ONE all-to-all over NVLink/NCCL,
+ *               CUDA-aware MPI, or device copies); buffers are DEVICE memory owned by the engine
+ *   ingest    : bin received events into the local calendar; collect every rank's control words from the inbox headers
+ *   advance   : fold the control words (termination, errors) and open the next window                          */
 int sstb200_engine_dispatch(sstb200_engine* e);
 int sstb200_engine_ingest(sstb200_engine* e);
 int sstb200_engine_advance(sstb200_engine* e);
-/* device pointers + geometry of the exchange buffers: words per rank slot = 1 + capacity*4 u64
- * ([0] = count, then capacity x {time, dst_seq, payload, dst_comp}) */
+/* device pointers + geometry of the exchange buffers.  Slot layout (u64 words), one slot per rank:
+ *   [0] record count, [1..8] the sender's control words, [9] reserved, then capacity x {time, dst_seq, payload,
+ *   dst_comp}; words_per_rank = 10 + capacity*4 */
 int sstb200_engine_exchange_buffers(sstb200_engine* e, void** outbox_dev, void** inbox_dev, uint64_t* words_per_rank);
-/* device pointers to this rank's 8 x i64 control words and to the n_ranks x 8 buffer the driver must fill with every
- * rank's words (all-gather) between ingest and advance: [0] pending events (sent - delivered, may be negative on one
- * rank), [1] primary components still running, [2] active clocks, [3] error flag, [4] exit time, [5..7] reserved.
- * advance folds them: sums of 0..3, max of 4. */
+/* device pointers to this rank's 8 x i64 control words and to the n_ranks x 8 table `ingest` fills from the inbox
+ * headers: [0] pending events (sent - delivered, may be negative on one rank), [1] primary components still running,
+ * [2] active clocks, [3] error flag, [4] exit time, [5..7] reserved.  advance folds them: sums of 0..3, max of 4.
+ * (A driver that cannot piggy-back may instead all-gather `local` into `global` itself after ingest.) */
 int sstb200_engine_control_words(sstb200_engine* e, void** local_dev, void** global_dev);
 
 /* ---- results (finish() simulation.cc:1286-1311, statistics dump statapi/statengine.cc:476-548) ---- */

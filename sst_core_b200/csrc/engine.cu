@@ -60,6 +60,9 @@ constexpr uint64_t TIME_NEVER = ~0ull;
 
 enum : uint32_t { ERR_BIN_OVERFLOW = 1, ERR_SMEM_OVERFLOW = 2, ERR_TIME_FAULT = 3, ERR_OUTBOX_OVERFLOW = 4, ERR_TRACE_OVERFLOW = 5 };
 enum { CW_PENDING = 0, CW_PRIMARY = 1, CW_CLOCKS = 2, CW_ERROR = 3, CW_EXIT_TIME = 4, CW_WORDS = 8 };
+// exchange slot layout (u64 words): [0] record count, [1..8] the sender's control words (piggy-backed so that one
+// all-to-all per window carries everything), [9] reserved, then capacity x {time, dst_seq, payload, dst_comp}
+constexpr uint32_t XHDR = 10;
 
 struct Ctrl
 {
@@ -155,7 +158,7 @@ emit(const Dev& d, uint64_t k, uint64_t time, uint32_t dst_port, uint32_t dst_co
             raise_error(d, ERR_OUTBOX_OVERFLOW, r, pos, d.outbox_cap);
             return;
         }
-        unsigned long long* rec = box + 1 + pos * 4;
+        unsigned long long* rec = box + XHDR + pos * 4;
         rec[0]                  = time;
         rec[1]                  = ((unsigned long long)dst_port << 32) | seq;
         rec[2]                  = payload;
@@ -767,7 +770,7 @@ dispatch_kernel(Dev d)
                     raise_error(d, ERR_OUTBOX_OVERFLOW, r, pos, d.outbox_cap);
                 }
                 else {
-                    unsigned long long* rec = d.outbox + (uint64_t)r * d.xwords + 1 + (uint64_t)pos * 4;
+                    unsigned long long* rec = d.outbox + (uint64_t)r * d.xwords + XHDR + (uint64_t)pos * 4;
                     rec[0]                  = tm;
                     rec[1]                  = ds;
                     rec[2]                  = PAYLOAD ? s_pay[e] : 0;
@@ -850,7 +853,7 @@ ingest_kernel(Dev d)
         const unsigned long long* box = d.inbox + (uint64_t)r * d.xwords;
         const uint64_t            n   = box[0] < d.outbox_cap ? box[0] : d.outbox_cap;
         for ( uint64_t i = (uint64_t)blockIdx.x * BLOCK + threadIdx.x; i < n; i += (uint64_t)gridDim.x * BLOCK ) {
-            const unsigned long long* rec = box + 1 + i * 4;
+            const unsigned long long* rec = box + XHDR + i * 4;
             emit(d, k, rec[0], (uint32_t)(rec[1] >> 32), (uint32_t)rec[3], (uint32_t)rec[1], rec[2]);
         }
     }
@@ -913,8 +916,27 @@ advance_kernel(Dev d)
 __global__ void
 publish_control_kernel(Dev d)
 {
-    // snapshot of the error flag into the control words that get all-gathered
-    if ( threadIdx.x == 0 && blockIdx.x == 0 ) d.ctrl->local[CW_ERROR] = d.ctrl->error ? 1 : 0;
+    // after dispatch: snapshot this rank's control words (with the error flag) into the header of every outbox slot,
+    // so the all-to-all that ships the boundary events also ships them (RankSyncSerialSkip needs a second collective,
+    // MPI_Allreduce, for this: rankSyncSerialSkip.cc:318-335)
+    if ( blockIdx.x != 0 ) return;
+    if ( threadIdx.x == 0 ) d.ctrl->local[CW_ERROR] = d.ctrl->error ? 1 : 0;
+    __syncthreads();
+    if ( d.n_ranks > 1 )
+        for ( uint32_t i = threadIdx.x; i < d.n_ranks * CW_WORDS; i += blockDim.x )
+            d.outbox[(uint64_t)(i / CW_WORDS) * d.xwords + 1 + (i % CW_WORDS)] =
+                (unsigned long long)d.ctrl->local[i % CW_WORDS];
+}
+
+// after the exchange: every rank's control words, as received in the inbox headers (own words from ctrl)
+__global__ void
+collect_control_kernel(Dev d)
+{
+    if ( blockIdx.x != 0 ) return;
+    for ( uint32_t i = threadIdx.x; i < d.n_ranks * CW_WORDS; i += blockDim.x ) {
+        const uint32_t r = i / CW_WORDS, wd = i % CW_WORDS;
+        d.gathered[i]    = (r == d.rank) ? d.ctrl->local[wd] : (long long)d.inbox[(uint64_t)r * d.xwords + 1 + wd];
+    }
 }
 
 __global__ void __launch_bounds__(BLOCK)
@@ -1405,7 +1427,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     rc |= e->alloc(&d.bin_count, (size_t)d.W * d.nbins);
     rc |= e->alloc(&d.ctrl, 1);
     d.outbox_cap = o->outbox_capacity ? o->outbox_capacity : 65536;
-    d.xwords     = 1 + (uint64_t)d.outbox_cap * 4;
+    d.xwords     = XHDR + (uint64_t)d.outbox_cap * 4;
     if ( n_ranks > 1 ) {
         rc |= e->alloc(&d.outbox, (size_t)n_ranks * d.xwords);
         rc |= e->alloc(&d.inbox, (size_t)n_ranks * d.xwords);
@@ -1524,7 +1546,7 @@ sstb200_engine_dispatch(sstb200_engine* e)
     if ( !e || !e->is_setup ) return -1;
     CUDA_OK(cudaSetDevice(e->device));
     if ( int rc = e->launch_dispatch() ) return rc;
-    publish_control_kernel<<<1, 32, 0, e->stream>>>(e->d);
+    publish_control_kernel<<<1, 64, 0, e->stream>>>(e->d);
     e->launches++;
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -1539,7 +1561,7 @@ sstb200_engine_ingest(sstb200_engine* e)
         ingest_kernel<<<64, BLOCK, 0, e->stream>>>(e->d);
         e->launches++;
         CUDA_OK(cudaGetLastError());
-        publish_control_kernel<<<1, 32, 0, e->stream>>>(e->d);
+        collect_control_kernel<<<1, 64, 0, e->stream>>>(e->d);
         e->launches++;
         CUDA_OK(cudaGetLastError());
     }

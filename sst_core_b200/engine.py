@@ -333,7 +333,8 @@ class Engine:
 class DistributedRunner:
     """One lookahead window per step across all ranks of the torch.distributed world:
 
-        dispatch -> all-to-all of the outboxes (NVLink / NCCL) -> ingest -> all-gather of the control words -> advance
+        dispatch -> ONE all-to-all of the outboxes, control words piggy-backed in the headers (NVLink / NCCL) -> ingest
+        -> advance
 
     Replaces SyncManager::execute + RankSyncSerialSkip::exchange and its MPI_Allreduce calls
     (sync/syncManager.cc:547-732, sync/rankSyncSerialSkip.cc:209-343).  The engine may be the CUDA `Engine` or any
@@ -348,10 +349,9 @@ class DistributedRunner:
 
     def step(self):
         e = self.e
-        e.dispatch()
-        self.dist.all_to_all_single(self.inbox, self.outbox)
-        e.ingest()
-        self.dist.all_gather_into_tensor(self.gathered, self.local)
+        e.dispatch()  # ... which also writes this rank's control words into every outbox header
+        self.dist.all_to_all_single(self.inbox, self.outbox)  # the ONE collective of a window
+        e.ingest()  # bins received events, collects every rank's control words from the inbox headers
         e.advance()
 
     def run(self, max_windows: int = 0, check_every: int = 32) -> bool:
@@ -402,12 +402,6 @@ class LocalMultiRankRunner:
         t.cuda.synchronize()
         for e in self.engines:
             e.ingest()
-        for e in self.engines:
-            e.sync()
-        allw = t.cat([c[0] for c in self.ct])
-        for c in self.ct:
-            c[1].copy_(allw)
-        t.cuda.synchronize()
         for e in self.engines:
             e.advance()
         for e in self.engines:

@@ -11,6 +11,7 @@ import oracle_lib as O
 from sst_core_b200.engine import Status
 
 CW = 8
+XHDR = 10  # exchange slot header: count, 8 control words, reserved (include/sstb200.h)
 
 
 class OracleRankEngine:
@@ -35,7 +36,7 @@ class OracleRankEngine:
         conn = pm.peer_port != 0xFFFFFFFF
         self.w = int(pm.latency[conn].min()) if conn.any() else 1_000_000
         self.cap = outbox_capacity
-        self.words = 1 + 4 * outbox_capacity
+        self.words = XHDR + 4 * outbox_capacity
         self.outbox = torch.zeros((n_ranks, self.words), dtype=torch.int64)
         self.inbox = torch.zeros((n_ranks, self.words), dtype=torch.int64)
         self.local = torch.zeros(CW, dtype=torch.int64)
@@ -71,7 +72,13 @@ class OracleRankEngine:
             sel = rec[dst_rank == r]
             assert sel.shape[0] <= self.cap, "outbox overflow"
             ob[r, 0] = sel.shape[0]
-            ob[r, 1:1 + 4 * sel.shape[0]] = sel.reshape(-1)
+            ob[r, XHDR:XHDR + 4 * sel.shape[0]] = sel.reshape(-1)
+        # control words ride in every outbox header (pending counts what is still queued here plus what was just sent)
+        cw = np.zeros(CW, dtype=np.int64)
+        self.L.oracle_control_words(self.h, cw.ctypes.data_as(C.c_void_p))
+        cw[0] += n
+        self.outbox[:, 1:1 + CW] = torch.from_numpy(cw)
+        self.local.copy_(torch.from_numpy(cw))
 
     def ingest(self):
         if self.done:
@@ -81,12 +88,12 @@ class OracleRankEngine:
             if r == self.rank:
                 continue
             n = int(ib[r, 0])
-            rec = np.ascontiguousarray(ib[r, 1:1 + 4 * n])
+            rec = np.ascontiguousarray(ib[r, XHDR:XHDR + 4 * n])
             if n:
                 self.L.oracle_ingest(self.h, rec.ctypes.data_as(C.c_void_p), n)
-        cw = np.zeros(CW, dtype=np.int64)
-        self.L.oracle_control_words(self.h, cw.ctypes.data_as(C.c_void_p))
-        self.local.copy_(torch.from_numpy(cw))
+        g = self.gathered.view(self.n_ranks, CW)
+        for r in range(self.n_ranks):
+            g[r] = self.local if r == self.rank else self.inbox[r, 1:1 + CW]
 
     def advance(self):
         if self.done:
