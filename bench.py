@@ -246,7 +246,7 @@ def ours(a):
                 DistributedRunner(e).run(max_windows=W + K, check_every=W + K)
             else:
                 e.run(max_windows=W + K, check_every=W + K)
-            res = e.results(result_words(m))
+            res = e.results(result_words(m), compact=True)
             st = e.status()
         torch.cuda.synchronize(dev)
         secs = time.perf_counter() - t0
@@ -257,7 +257,7 @@ def ours(a):
             dist.all_reduce(ev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": float(ev[0].item()) / float(tt[0].item()), "unit": "events/s",
-               "h2d_bytes_per_step": model_bytes // (W + K), "d2h_bytes_per_step": (res.shape[0] * result_words(m) * 8) // (W + K),
+               "h2d_bytes_per_step": model_bytes // (W + K), "d2h_bytes_per_step": res.nbytes // (W + K),
                "seconds": float(tt[0].item()), "windows": W + K,
                "note": "engine create from host arrays + setup + windows + results to host, per rank slice"}
         e.close()

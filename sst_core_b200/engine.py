@@ -303,9 +303,10 @@ class Engine:
         """Wait for the engine's stream (status() does a device->host read on it)."""
         self.status()
 
-    def results(self, words: int = 0) -> np.ndarray:
-        """Result records of this rank's components; `words` > 0 downloads only the first `words` of the 32 words
-        (the rest of the returned [n, 32] array is zero)."""
+    def results(self, words: int = 0, compact: bool = False) -> np.ndarray:
+        """Result records of this rank's components.  `words` > 0 downloads only the first `words` of the 32 words per
+        component; the returned array is [n, 32] (rest zero) unless `compact`, then [n, words] with no host-side copy
+        (what a large run wants: 16.7 M components x 32 words is 4.3 GB of mostly zeros)."""
         n = self.comp_end - self.comp_begin
         if not words or words >= NRESULT:
             out = np.empty((n, NRESULT), dtype=np.uint64)
@@ -313,6 +314,8 @@ class Engine:
             return out
         part = np.empty((n, words), dtype=np.uint64)
         _check(self._L.sstb200_engine_results(self._h, _p(part), words), "engine_results")
+        if compact:
+            return part
         out = np.zeros((n, NRESULT), dtype=np.uint64)
         out[:, :words] = part
         return out
