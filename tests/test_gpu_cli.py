@@ -1,0 +1,41 @@
+"""The `sst`-like command line (python -m sst_core_b200) end to end on the GPU: console output and StatisticOutput.csv
+against the reference's golden file / fixtures, compared the way the reference's testsuites do (sorted diff)."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+GOLD = json.loads((ROOT / "tests" / "golden" / "reference_golden.json").read_text())
+
+
+def _run(args, cwd):
+    r = subprocess.run([sys.executable, "-m", "sst_core_b200", *args], capture_output=True, text=True, cwd=cwd,
+                       env={**__import__("os").environ, "PYTHONPATH": str(ROOT)}, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout
+
+
+def test_cli_mesh_6x6_matches_reference_golden_file(tmp_path):
+    out = _run(["--model-options", "6 6", str(ROOT / "tests/models/mesh.py")], tmp_path)
+    want = [f"{i} received {c} messages" for i, c in GOLD["mesh_6x6_10us"]["counts"].items()]
+    want.append("Simulation is complete, simulated time: 10 us")
+    assert sorted(out.strip().splitlines()) == sorted(want)
+
+
+def test_cli_stop_at_override_and_csv(tmp_path):
+    out = _run(["--stop-at", "100ns", "--model-options", "3 3 1 1 2 1", str(ROOT / "tests/models/mesh.py")], tmp_path)
+    assert out.strip().splitlines()[-1] == "Simulation is complete, simulated time: 100 ns"
+    rows = (tmp_path / "StatisticOutput.csv").read_text().strip().splitlines()
+    assert rows == GOLD["mesh_3x3_100ns_csv"]["rows"]
+
+
+def test_cli_unknown_element_is_fatal(tmp_path):
+    bad = tmp_path / "bad.py"
+    bad.write_text('import sst\nsst.Component("c0", "nolib.nothing")\n')
+    r = subprocess.run([sys.executable, "-m", "sst_core_b200", str(bad)], capture_output=True, text=True,
+                       env={**__import__("os").environ, "PYTHONPATH": str(ROOT)})
+    assert r.returncode == 1 and "can't find requested component" in r.stderr
