@@ -27,5 +27,7 @@ print("CTAs", nb, "kernel span %.1f us" % ((t[:, 5].max() - t[:, 0].min()) / 1e3
 for i, n in enumerate(names):
     print(f"{n:58s} mean {d[:, i].mean()/1e3:7.2f} us   p50 {np.median(d[:, i])/1e3:7.2f}   p95 {np.percentile(d[:, i],95)/1e3:7.2f}")
 print(f"{'phase 3 until the LIGHTEST warp (thread 255) is done':58s} mean {(t[:,7]-t[:,3]).mean()/1e3:7.2f} us")
+print(f"{'phase 3a (per component) until the barrier':58s} mean {(t[:,6]-t[:,3]).mean()/1e3:7.2f} us")
+print(f"{'phase 3b (event-parallel handlers + deferred writes)':58s} mean {(t[:,4]-t[:,6]).mean()/1e3:7.2f} us")
 print(f"{'CTA lifetime':58s} mean {(t[:,5]-t[:,0]).mean()/1e3:7.2f} us")
 e.close()

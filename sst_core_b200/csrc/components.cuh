@@ -59,6 +59,15 @@ struct Accumulator
         mx = v > mx ? v : mx;
         count++;
     }
+    // addData_impl_Ntimes (stataccumulator.h:97-103) + the collection count
+    SSTB_HD void addN(T v, uint64_t n)
+    {
+        sum += (T)n * v;
+        sumsq += (T)n * v * v;
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+        count += n;
+    }
     SSTB_HD void out(uint64_t* r) const
     {
         r[0] = (uint64_t)(int64_t)sum;
@@ -81,6 +90,14 @@ mixDelivery(uint64_t h, uint64_t time, uint64_t port, uint64_t payload)
 }
 
 #if defined(__CUDACC__)
+
+// what an event-parallel handler wants written to its component's aux block: applied by the engine after every
+// parallel handler of the block has done its reads
+struct DeferredWrite
+{
+    uint32_t word; // word offset into the aux block (8-byte aligned), 0xFFFFFFFF = none
+    uint32_t v0, v1;
+};
 
 __device__ __forceinline__ void
 prefetch_l2(const void* p)
@@ -164,6 +181,55 @@ struct MeshElement
         if ( n_events && (s.mt_idx & 1u) == 0 ) mt_cache_fill((const uint32_t*)ctx.aux, s.mt_idx, s.cache);
     }
 #endif
+    // ---- event-parallel handler.  RouteMessage::send's effect for the k-th event of a window is a pure function of
+    // the window-start state and k: its pair of draws reads mt[i+2k .. i+2k+2], mt[i+2k+397], mt[i+2k+398] -- words no
+    // earlier pair of the window writes (see MT_STAGE_MAX_PAIRS) -- and the state update (message_count, MT index,
+    // msg_count statistic) is a sum.  So the n events of a component run on n threads.
+    static constexpr bool     PARALLEL_EVENTS          = true;
+    static constexpr uint32_t PARALLEL_SENDS_PER_EVENT = 1;
+    __device__ static uint32_t parallelHeader(const State& s) { return s.mt_idx; }
+    __device__ static bool parallelOK(const State& s, uint32_t n)
+    {
+        return (s.mt_idx & 1u) == 0 && n <= MT_STAGE_MAX_PAIRS;
+    }
+    __device__ static void finishWindowParallel(State& s, uint32_t n, bool stats_on)
+    {
+        s.message_count += (int32_t)n;
+        s.mt_idx = mt_wrap(mt_wrap(s.mt_idx + 2 * n));
+        if ( stats_on ) s.mcnt.addN(1, n); // addData_impl_Ntimes, stataccumulator.h:97-103
+    }
+    template <class PCtx>
+    __device__ static DeferredWrite handleEventParallel(PCtx& ctx, const uint8_t* state, uint32_t mt_idx0, uint32_t k,
+        uint32_t /*n*/, int /*port*/, uint64_t payload)
+    {
+        const uint4     cst = __ldg(reinterpret_cast<const uint4*>(state + 16)); // ngroups, mod, counts
+        const uint32_t  ng  = cst.x;
+        const uint64_t  counts = ((uint64_t)cst.w << 32) | cst.z;
+        const uint32_t* mt  = (const uint32_t*)ctx.aux;
+        const uint32_t  i   = mt_wrap(mt_wrap(mt_idx0 + 2 * k)); // even
+        const uint2     a01 = *reinterpret_cast<const uint2*>(mt + i);
+        const uint32_t  a2  = mt[mt_wrap(i + 2)];
+        const uint32_t  b0  = mt[mt_wrap(i + MT_M)];
+        const uint32_t  b1  = mt[mt_wrap(i + MT_M + 1)];
+        const uint32_t  y0  = (a01.x & 0x80000000u) + (a01.y & 0x7fffffffu);
+        uint32_t        v0  = b0 ^ (y0 >> 1);
+        if ( y0 & 1u ) v0 ^= 2567483615u;
+        const uint32_t y1 = (a01.y & 0x80000000u) + (a2 & 0x7fffffffu);
+        uint32_t       v1 = b1 ^ (y1 >> 1);
+        if ( y1 & 1u ) v1 ^= 2567483615u;
+        const uint32_t r0 = mt_temper(v0), r1 = mt_temper(v1);
+        const uint32_t nextport = (ng & (ng - 1)) == 0 ? (r0 & (ng - 1)) : r0 % ng;
+        uint32_t       portnum = 0, base = nextport;
+        if ( counts != (0x0101010101010101ull >> (8 * (8 - ng))) ) {
+            const uint32_t cnt = (uint32_t)((counts >> (8 * nextport)) & 0xFF);
+            portnum            = r1 % cnt;
+            base               = 0;
+            for ( uint32_t g = 0; g < nextport; ++g )
+                base += (uint32_t)((counts >> (8 * g)) & 0xFF);
+        }
+        ctx.send((int)(base + portnum), 0, payload);
+        return DeferredWrite { i, v0, v1 };
+    }
     // dispatch prologue hook: pull towards L2 the MT19937 words the next handful of draws will read
     // (words idx.. and idx+397.. mod 624), so that the per-event draws hit L2 instead of paying an HBM round trip each
     __device__ static void prefetch(const uint8_t* state, const uint8_t* aux)
@@ -265,6 +331,7 @@ struct PholdElement
         uint64_t              pad1;
     };
     static constexpr uint32_t STORE_END = 32, CONST_END = 48, STATS_END = 96;
+    static constexpr bool     PARALLEL_EVENTS = false; // handlers chain through the state (hash, RNG): sequential
     static constexpr uint32_t SCRATCH_PER_EVENT = 0, SCRATCH_FIXED = 0;
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>
@@ -336,6 +403,7 @@ struct ClockNodeElement
         Accumulator<int32_t> count[4];
     };
     static constexpr uint32_t STORE_END = 48, CONST_END = 64, STATS_END = 160;
+    static constexpr bool     PARALLEL_EVENTS = false; // handlers chain through the state (hash, RNG): sequential
     static constexpr uint32_t SCRATCH_PER_EVENT = 0, SCRATCH_FIXED = 0;
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>
@@ -405,6 +473,7 @@ struct RngElement
         uint64_t pad1;
     };
     static constexpr uint32_t STORE_END = 96, CONST_END = 96, STATS_END = 96;
+    static constexpr bool     PARALLEL_EVENTS = false; // handlers chain through the state (hash, RNG): sequential
     static constexpr uint32_t SCRATCH_PER_EVENT = 0, SCRATCH_FIXED = 0;
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>
@@ -504,6 +573,7 @@ struct ElementInfo
     uint32_t    aux_bytes;
     int         has_payload;
     uint32_t    scratch_per_event, scratch_fixed; // shared-memory scratch words per due event / per component
+    bool        parallel_events;                  // has an event-parallel handler
     const char* description;
 };
 

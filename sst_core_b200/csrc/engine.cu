@@ -57,6 +57,7 @@ set_error(const std::string& s)
 #endif
 constexpr int      BLOCK      = SSTB200_BLOCK; // components per CTA == threads per CTA
 constexpr uint64_t TIME_NEVER = ~0ull;
+constexpr int      PARB       = 6; // event-parallel phase: positions t, t+256, ... t+5*256 per thread
 
 enum : uint32_t { ERR_BIN_OVERFLOW = 1, ERR_SMEM_OVERFLOW = 2, ERR_TIME_FAULT = 3, ERR_OUTBOX_OVERFLOW = 4, ERR_TRACE_OVERFLOW = 5 };
 enum { CW_PENDING = 0, CW_PRIMARY = 1, CW_CLOCKS = 2, CW_ERROR = 3, CW_EXIT_TIME = 4, CW_WORDS = 8 };
@@ -101,6 +102,7 @@ struct Dev
     uint32_t        uniform_shift;        // log2(uniform_nports) when it is a power of two, else 32
     uint32_t        uniform_type;         // the element type when every local component has the same one, else 0
     uint32_t        scr_per_event, scr_fixed; // shared-memory scratch words an element gets per due event / per component
+    uint32_t        any_parallel;         // some local element type has an event-parallel handler
     uint32_t        P0, nport_local;
     uint32_t        rank, n_ranks;
     const uint32_t* rank_comp_begin; // [n_ranks+1] (device)
@@ -391,6 +393,63 @@ gtimer()
 #define PHASE_MARK(i)
 #endif
 
+// (time, port, sequence) order of one component's segment: insertion sort by the owning thread (segments are a
+// handful of events; the lanes of a warp own components with nearly equal event counts)
+__device__ __forceinline__ void
+sort_segment(uint16_t* seg, uint32_t cnt, const uint32_t* s_time, const uint32_t* s_dst, const uint32_t* s_seq)
+{
+    for ( uint32_t a = 1; a < cnt; ++a ) {
+        const uint16_t ea = seg[a];
+        const uint32_t ta = s_time[ea], da = s_dst[ea], qa = s_seq[ea];
+        uint32_t       b  = a;
+        while ( b > 0 ) {
+            const uint16_t eb = seg[b - 1];
+            if ( !key_less(ta, da, qa, s_time[eb], s_dst[eb], s_seq[eb]) ) break;
+            seg[b] = eb;
+            --b;
+        }
+        seg[b] = ea;
+    }
+}
+
+// Context of an EVENT-PARALLEL handler (elements with PARALLEL_EVENTS): the handler of the k-th event (in delivery
+// order) of a component runs on its own thread, concurrently with the handlers of the component's other events of the
+// window.  It sees the component's state as it was at the start of the window (read-only), sends exactly
+// PARALLEL_SENDS_PER_EVENT events (staged in its own event's slot), and returns its writes to the aux block as a
+// deferred write that the engine applies after every parallel handler of the block has finished reading.
+struct ParCtx
+{
+    const Dev&   d;
+    uint64_t     now, k, T;
+    uint32_t     comp, port0, nports;
+    uint8_t*     aux;
+    uint32_t     seq; // sequence number of this event's (first) send
+    int          stats_on;
+    const uint4* links;
+    Stage        st;
+    uint32_t     slot; // this event's staging slot
+    bool         used;
+
+    __device__ __forceinline__ void send(int port, uint64_t delay, uint64_t payload)
+    {
+        const uint4 l = links[port];
+        if ( l.x == SSTB200_NO_PEER ) return;
+        const uint64_t when = now + delay + (((uint64_t)l.w << 32) | l.z);
+        const uint32_t sq   = seq++;
+        const uint64_t off  = when - T;
+        if ( !used && (off >> 32) == 0 ) {
+            used       = true;
+            st.t[slot] = (uint32_t)off;
+            st.a[slot] = l.x;
+            st.b[slot] = sq;
+            st.c[slot] = l.y;
+            if ( st.pay ) st.pay[slot] = payload;
+            return;
+        }
+        emit(d, k, when, l.x, l.y, sq, payload);
+    }
+};
+
 // ---- one lookahead window for one block of 256 components
 template <bool PAYLOAD>
 #ifndef SSTB200_MIN_BLOCKS
@@ -430,8 +489,10 @@ dispatch_kernel(Dev d)
     uint32_t* s_hbase    = s_hist + 32;             // [32]
     uint16_t* s_perm     = reinterpret_cast<uint16_t*>(s_hbase + 32); // [emax] per-component segments
     uint16_t* s_order    = s_perm + d.emax;                           // [BLOCK] thread -> component of the block
-    uint32_t* s_scratch  = reinterpret_cast<uint32_t*>( // [scr_per_event*emax + scr_fixed*BLOCK], 16-byte aligned
+    uint4*    s_hdr      = reinterpret_cast<uint4*>( // [BLOCK] per-component window header of the event-parallel path
         (reinterpret_cast<uintptr_t>(s_order + BLOCK) + 15) & ~(uintptr_t)15);
+    uint32_t* s_scratch  = reinterpret_cast<uint32_t*>(s_hdr + BLOCK); // [scr_per_event*emax + scr_fixed*BLOCK]
+    uint8_t*  s_pcomp    = reinterpret_cast<uint8_t*>(s_scratch + (size_t)d.scr_per_event * d.emax + (size_t)d.scr_fixed * BLOCK); // [emax] component of each segment position
 
     // ---- prologue: everything here is independent global traffic issued back to back.  The first 1024 records of
     // the bin are loaded before its fill count is known (the slots exist; what is past the count is ignored).
@@ -460,6 +521,7 @@ dispatch_kernel(Dev d)
             s_misc[0]         = 0;
         }
         s_cnt[tid] = 0;
+        s_hdr[tid] = make_uint4(0, 0, 0, 0);
         if ( tid < 32 ) s_hist[tid] = 0;
         if ( lc0 < d.n_local ) {
             // element hook: start pulling the state line and the aux words the handlers will touch towards L2
@@ -559,8 +621,10 @@ dispatch_kernel(Dev d)
     }
     __syncthreads();
     for ( uint32_t e = tid; e < n_due; e += BLOCK ) {
-        const uint32_t cr                        = s_cr[e];
-        s_perm[s_off[cr >> 16] + (cr & 0xFFFFu)] = (uint16_t)e;
+        const uint32_t cr  = s_cr[e];
+        const uint32_t pos = s_off[cr >> 16] + (cr & 0xFFFFu);
+        s_perm[pos]        = (uint16_t)e;
+        s_pcomp[pos]       = (uint8_t)(cr >> 16);
     }
     if ( tid < 32 ) { // exclusive scan of the 32 buckets by one warp
         const uint32_t v   = s_hist[tid];
@@ -609,21 +673,26 @@ dispatch_kernel(Dev d)
                 using E = decltype(el);
                 typename E::State s;
                 load_state(s, d.state + (uint64_t)lc * d.state_stride, 0, d.stats_on ? E::STATS_END : E::CONST_END);
-                E::beginWindow(ctx, s, my_cnt); // issues the element's first loads (MT19937 read-ahead) ...
-                // ... which the sort below overlaps.  (b) order inside the segment: (time, port, sequence).  Insertion sort by the owning thread; the lanes of a
-                // warp own components with (nearly) equal event counts, so the loops stay converged.
-                for ( uint32_t a = 1; a < my_cnt; ++a ) {
-                    const uint16_t ea = seg[a];
-                    const uint32_t ta = s_time[ea], da = s_dst[ea], qa = s_seq[ea];
-                    uint32_t       b  = a;
-                    while ( b > 0 ) {
-                        const uint16_t eb = seg[b - 1];
-                        if ( !key_less(ta, da, qa, s_time[eb], s_dst[eb], s_seq[eb]) ) break;
-                        seg[b] = eb;
-                        --b;
+                if constexpr ( E::PARALLEL_EVENTS ) {
+                    // event-parallel path: no clock tick due, the whole segment inside the register window of
+                    // phase 3b, and the element agrees (e.g. MT19937: even index, short enough run)
+                    if ( my_cnt > 0 && !(next_tick < T_end) && s_off[c] + my_cnt <= PARB * BLOCK &&
+                         E::parallelOK(s, my_cnt) ) {
+                        sort_segment(seg, my_cnt, s_time, s_dst, s_seq);
+                        s_hdr[c] = make_uint4(E::parallelHeader(s), ctx.seq, dseq, 1u | (E::TYPE << 8));
+                        E::finishWindowParallel(s, my_cnt, d.stats_on != 0);
+                        ctx.seq += my_cnt * E::PARALLEL_SENDS_PER_EVENT;
+                        ctx.sent += my_cnt * E::PARALLEL_SENDS_PER_EVENT;
+                        if ( d.trace_cap ) dseq += my_cnt;
+                        delivered = my_cnt;
+                        store_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::STORE_END);
+                        if ( d.stats_on )
+                            store_state(s, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
+                        return;
                     }
-                    seg[b] = ea;
                 }
+                E::beginWindow(ctx, s, my_cnt); // issues the element's first loads (MT19937 read-ahead) ...
+                sort_segment(seg, my_cnt, s_time, s_dst, s_seq); // ... which ordering the segment overlaps
                 uint64_t cycle = (next_tick != TIME_NEVER && period) ? next_tick / period : 0;
                 uint32_t i     = 0;
                 for ( ;; ) {
@@ -672,8 +741,64 @@ dispatch_kernel(Dev d)
     }
     if ( threadIdx.x == 255 ) {
 #ifdef SSTB200_TIMING
-        if ( blockIdx.x < (1 << 17) ) g_phase_times[blockIdx.x * 8 + 7] = gtimer(); // lightest warp done with phase 3
+        if ( blockIdx.x < (1 << 17) ) g_phase_times[blockIdx.x * 8 + 7] = gtimer(); // lightest warp done with phase 3a
 #endif
+    }
+    // ---- phase 3b: event-parallel handlers.  Thread t takes the events at positions t, t+256, ... of the ordered
+    // segments whose component chose the parallel path in 3a: perfectly balanced however the events are spread
+    // over components, and no sequential chain.  Reads of the aux block happen before the barrier, the handlers'
+    // deferred writes after it.
+    if ( d.any_parallel ) {
+        __syncthreads();
+        PHASE_MARK(6);
+        DeferredWrite dw[PARB];
+        uint32_t      dw_lc[PARB];
+#pragma unroll
+        for ( int j = 0; j < PARB; ++j ) {
+            dw[j].word       = 0xFFFFFFFFu;
+            const uint32_t p = tid + j * BLOCK;
+            if ( p >= n_due ) continue;
+            const uint32_t e   = s_perm[p];
+            const uint32_t cc  = s_pcomp[p];
+            const uint4    hdr = s_hdr[cc];
+            if ( !(hdr.w & 1u) ) continue;
+            const uint32_t kk   = p - s_off[cc];
+            const uint32_t lcc  = bin * BLOCK + cc;
+            const uint32_t p0   = s_port_off[cc];
+            const uint32_t port = s_dst[e] - p0;
+            const uint64_t pl   = PAYLOAD ? s_pay[e] : 0;
+            const uint64_t ev_t = T + s_time[e];
+            s_dst[e]            = SSTB200_NO_PEER; // consumed; a send re-fills the slot
+            dw_lc[j]            = lcc;
+            if ( d.trace_cap ) {
+                const unsigned long long tp = atomicAdd(&ctrl->trace_n, 1ull);
+                if ( tp < d.trace_cap ) {
+                    d.tr_time[tp]    = ev_t;
+                    d.tr_comp[tp]    = d.c0 + lcc;
+                    d.tr_port[tp]    = port;
+                    d.tr_idx[tp]     = hdr.z + kk;
+                    d.tr_payload[tp] = pl;
+                }
+            }
+            with_element(hdr.w >> 8, [&](auto el) {
+                using E = decltype(el);
+                if constexpr ( E::PARALLEL_EVENTS ) {
+                    ParCtx pc { d, ev_t, k, T, d.c0 + lcc, p0, s_port_off[cc + 1] - p0,
+                                d.aux + (uint64_t)lcc * d.aux_stride, hdr.y + kk * E::PARALLEL_SENDS_PER_EVENT,
+                                d.stats_on,
+                                links_in_smem ? (const uint4*)(s_link + (p0 - blk_port0)) : d.link + (p0 - d.P0),
+                                Stage { s_time, s_dst, s_seq, s_cr, PAYLOAD ? s_pay : nullptr }, e, false };
+                    dw[j] = E::handleEventParallel(pc, d.state + (uint64_t)lcc * d.state_stride, hdr.x, kk,
+                        s_cnt[cc], (int)port, pl);
+                }
+            });
+        }
+        __syncthreads();
+#pragma unroll
+        for ( int j = 0; j < PARB; ++j )
+            if ( dw[j].word != 0xFFFFFFFFu )
+                *reinterpret_cast<uint2*>(d.aux + (uint64_t)dw_lc[j] * d.aux_stride + (uint64_t)dw[j].word * 4) =
+                    make_uint2(dw[j].v0, dw[j].v1);
     }
     __syncthreads();
     PHASE_MARK(4);
@@ -1093,13 +1218,13 @@ rng_dist_kernel(int dist, const double* params, int np, int kind, uint64_t s1, u
 // ================================================================================================ host side
 static const ElementInfo kElements[] = {
     { TYPE_MESH, MeshElement::ELI_NAME, MeshElement::PERSIST_BYTES, MeshElement::AUX_BYTES,
-        MeshElement::HAS_PAYLOAD, MeshElement::SCRATCH_PER_EVENT, MeshElement::SCRATCH_FIXED, "message_mesh enclosing component with message_port/port_slot/route_message" },
+        MeshElement::HAS_PAYLOAD, MeshElement::SCRATCH_PER_EVENT, MeshElement::SCRATCH_FIXED, MeshElement::PARALLEL_EVENTS, "message_mesh enclosing component with message_port/port_slot/route_message" },
     { TYPE_PHOLD, PholdElement::ELI_NAME, PholdElement::PERSIST_BYTES, PholdElement::AUX_BYTES,
-        PholdElement::HAS_PAYLOAD, PholdElement::SCRATCH_PER_EVENT, PholdElement::SCRATCH_FIXED, "PHOLD-style node, integer delays, 8-byte payload" },
+        PholdElement::HAS_PAYLOAD, PholdElement::SCRATCH_PER_EVENT, PholdElement::SCRATCH_FIXED, PholdElement::PARALLEL_EVENTS, "PHOLD-style node, integer delays, 8-byte payload" },
     { TYPE_CLOCKNODE, ClockNodeElement::ELI_NAME, ClockNodeElement::PERSIST_BYTES,
-        ClockNodeElement::AUX_BYTES, ClockNodeElement::HAS_PAYLOAD, ClockNodeElement::SCRATCH_PER_EVENT, ClockNodeElement::SCRATCH_FIXED, "clock-driven node (coreTestComponent style)" },
+        ClockNodeElement::AUX_BYTES, ClockNodeElement::HAS_PAYLOAD, ClockNodeElement::SCRATCH_PER_EVENT, ClockNodeElement::SCRATCH_FIXED, ClockNodeElement::PARALLEL_EVENTS, "clock-driven node (coreTestComponent style)" },
     { TYPE_RNGCOMP, RngElement::ELI_NAME, RngElement::PERSIST_BYTES, RngElement::AUX_BYTES,
-        RngElement::HAS_PAYLOAD, RngElement::SCRATCH_PER_EVENT, RngElement::SCRATCH_FIXED, "coreTestRNGComponent: 1 GHz clock drawing from an SST::RNG generator" },
+        RngElement::HAS_PAYLOAD, RngElement::SCRATCH_PER_EVENT, RngElement::SCRATCH_FIXED, RngElement::PARALLEL_EVENTS, "coreTestRNGComponent: 1 GHz clock drawing from an SST::RNG generator" },
 };
 constexpr int kNumElements = (int)(sizeof(kElements) / sizeof(kElements[0]));
 
@@ -1384,10 +1509,12 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
             if ( m->comp_type[c] != ut ) ut = 0;
         d.uniform_type = ut;
         d.scr_per_event = d.scr_fixed = 0;
+        d.any_parallel  = 0;
         for ( uint32_t c = c0; c < c1; ++c ) {
             const ElementInfo* ei = element_by_type(m->comp_type[c]);
             d.scr_per_event       = std::max(d.scr_per_event, ei->scratch_per_event);
             d.scr_fixed           = std::max(d.scr_fixed, ei->scratch_fixed);
+            if ( ei->parallel_events ) d.any_parallel = 1;
             if ( ut ) break; // uniform: the first one says it all
         }
     }
@@ -1458,7 +1585,8 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
 
     e->smem_bytes = (size_t)d.lmax * 16 + (size_t)d.emax * (has_payload ? 8 : 0) + (size_t)d.emax * 16 +
                     (size_t)(BLOCK + 1 + BLOCK + BLOCK + BLOCK / 32 + 1 + 4 + 32 + 32) * 4 + (size_t)d.emax * 2 +
-                    (size_t)BLOCK * 2 + 16 + ((size_t)d.scr_per_event * d.emax + (size_t)d.scr_fixed * BLOCK) * 4 + 16;
+                    (size_t)BLOCK * 2 + 16 + (size_t)BLOCK * 16 + ((size_t)d.scr_per_event * d.emax + (size_t)d.scr_fixed * BLOCK) * 4 +
+                    (size_t)d.emax + 16;
     if ( e->smem_bytes > 227 * 1024 ) {
         set_error("engine_create: smem_events too large for 227 KB of shared memory");
         sstb200_engine_destroy(e);
