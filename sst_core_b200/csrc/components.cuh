@@ -129,58 +129,20 @@ struct MeshElement
         Accumulator<uint64_t> mcnt; // RouteMessage "msg_count"
         uint64_t              pad2;
         // register-only scratch, valid inside one window
-#ifdef SSTB200_MESH_STAGE_MT
-        uint32_t win_pair, win_n; // pairs drawn from the staged words so far / pairs staged (0 = nothing staged)
-#endif
         MtPairCache cache; // read-ahead of the MT19937 words the next two pairs need
     };
     static constexpr uint32_t STORE_END = 16, CONST_END = 32, STATS_END = 80, PERSIST_BYTES = 80;
     // shared-memory scratch: the MT19937 words this window's draws will read, 4 per event (+3 per component)
-#ifdef SSTB200_MESH_STAGE_MT
-    static constexpr uint32_t SCRATCH_PER_EVENT = 4, SCRATCH_FIXED = 4;
-#else
-    // measured (profiles/r01_notes.md): staging costs 28 KB of shared memory per CTA (3 instead of 4 CTAs per SM) and
-    // the heavy warp of a block is bound by its instruction chain, not by the MT19937 loads -- the register
-    // read-ahead (MtPairCache) wins.  The staged path stays available for elements whose draws are load-bound.
-    static constexpr uint32_t SCRATCH_PER_EVENT = 0, SCRATCH_FIXED = 0;
-#endif
-    // Start of a window in which this component has `n_events` events.  Every event draws one PAIR; pair k (index
-    // i + 2k, even) reads mt[i+2k .. i+2k+2] and mt[i+2k+397], mt[i+2k+398]: two contiguous runs of 2n+1 words.
-    // Copy both runs into shared memory now with ALL loads in flight at once (one memory round trip for the whole
-    // window instead of one per event), as 8-byte chunks.  Pairs never read what an earlier pair of the same window
-    // wrote (those are words i .. i+2n-1; a pair's reads start at its own index and at +397), provided the a-run does
-    // window is short enough: pair k reads mt[i+2k+398], which pair k-114 wrote (2*114+396 = 624), so at most
-    // MT_STAGE_MAX_PAIRS = 100 pairs are staged; busier components fall back to direct draws.
-#ifdef SSTB200_MESH_STAGE_MT
-    template <class Ctx>
-    __device__ static void beginWindow(Ctx& ctx, State& s, uint32_t n_events)
-    {
-        s.win_pair    = 0;
-        s.win_n       = 0;
-        s.cache.valid = 0;
-        const uint32_t i = s.mt_idx;
-        if ( n_events && (i & 1u) == 0 && ctx.scratch == nullptr ) mt_cache_fill((const uint32_t*)ctx.aux, i, s.cache);
-        if ( n_events == 0 || (i & 1u) || n_events > MT_STAGE_MAX_PAIRS || ctx.scratch == nullptr ) return;
-        // asynchronous copies (LDGSTS): nothing waits until the first draw, see mesh_words_ready()
-        const uint32_t* mt  = (const uint32_t*)ctx.aux;
-        uint32_t*       scr = ctx.scratch; // a-run: scr[0 .. 2n+1]; b-run: mt[i+397+j] at scr[2n+3+j], j = 0 .. 2n
-        for ( uint32_t c = 0; c <= n_events; ++c )
-            __pipeline_memcpy_async(scr + 2 * c, mt + mt_wrap(mt_wrap(i + 2 * c)), 8);
-        __pipeline_memcpy_async(scr + 2 * n_events + 3, mt + mt_wrap(i + MT_M), 4);
-        for ( uint32_t c = 0; c < n_events; ++c )
-            __pipeline_memcpy_async(scr + 2 * n_events + 4 + 2 * c, mt + mt_wrap(mt_wrap(i + MT_M + 1 + 2 * c)), 8);
-        __pipeline_commit();
-        s.win_n = n_events;
-    }
-#else
-    // issue the read-ahead loads now: they are in flight while the engine orders the component's events
+    // shared-memory scratch of the event-parallel path: the MT19937 words the window's pairs read (4 per event + 4)
+    // and the construction constants the handlers need (4 words)
+    static constexpr uint32_t SCRATCH_PER_EVENT = 4, SCRATCH_FIXED = 8;
+    // sequential path: issue the read-ahead loads now, they fly while the engine does the rest of its set-up
     template <class Ctx>
     __device__ static void beginWindow(Ctx& ctx, State& s, uint32_t n_events)
     {
         s.cache.valid = 0;
         if ( n_events && (s.mt_idx & 1u) == 0 ) mt_cache_fill((const uint32_t*)ctx.aux, s.mt_idx, s.cache);
     }
-#endif
     // ---- event-parallel handler.  RouteMessage::send's effect for the k-th event of a window is a pure function of
     // the window-start state and k: its pair of draws reads mt[i+2k .. i+2k+2], mt[i+2k+397], mt[i+2k+398] -- words no
     // earlier pair of the window writes (see MT_STAGE_MAX_PAIRS) -- and the state update (message_count, MT index,
@@ -192,31 +154,52 @@ struct MeshElement
     {
         return (s.mt_idx & 1u) == 0 && n <= MT_STAGE_MAX_PAIRS;
     }
+    // 3a, component thread: copy into the component's shared-memory scratch, asynchronously (LDGSTS, all copies in
+    // flight at once), everything the n parallel handlers will read:
+    //   scr[0 .. 2n+1]        mt[i .. i+2n+1]        (n+1 aligned 8-byte chunks)
+    //   scr[2n+3 .. 4n+3]     mt[i+397 .. i+397+2n]  (one word, then n aligned chunks)
+    //   scr[4n+4 .. 4n+6]     ngroups, counts        (construction constants)
+    // The engine waits for the copies and synchronises the block before 3b.
+    template <class Ctx>
+    __device__ static void stageParallel(Ctx& ctx, const State& s, uint32_t n)
+    {
+        const uint32_t* mt  = (const uint32_t*)ctx.aux;
+        uint32_t*       scr = ctx.scratch;
+        const uint32_t  i   = s.mt_idx;
+        for ( uint32_t c = 0; c <= n; ++c )
+            __pipeline_memcpy_async(scr + 2 * c, mt + mt_wrap(mt_wrap(i + 2 * c)), 8);
+        __pipeline_memcpy_async(scr + 2 * n + 3, mt + mt_wrap(i + MT_M), 4);
+        for ( uint32_t c = 0; c < n; ++c )
+            __pipeline_memcpy_async(scr + 2 * n + 4 + 2 * c, mt + mt_wrap(mt_wrap(i + MT_M + 1 + 2 * c)), 8);
+        scr[4 * n + 4] = s.ngroups;
+        scr[4 * n + 5] = (uint32_t)s.counts;
+        scr[4 * n + 6] = (uint32_t)(s.counts >> 32);
+    }
     __device__ static void finishWindowParallel(State& s, uint32_t n, bool stats_on)
     {
         s.message_count += (int32_t)n;
         s.mt_idx = mt_wrap(mt_wrap(s.mt_idx + 2 * n));
         if ( stats_on ) s.mcnt.addN(1, n); // addData_impl_Ntimes, stataccumulator.h:97-103
     }
+    // 3b, one thread per event: k-th event (delivery order) of a component that has n this window.  Reads shared
+    // memory only; writes the two new-generation words straight to the MT19937 state (nobody reads that state again
+    // in this window: every read was staged before the block synchronised).
     template <class PCtx>
-    __device__ static DeferredWrite handleEventParallel(PCtx& ctx, const uint8_t* state, uint32_t mt_idx0, uint32_t k,
-        uint32_t /*n*/, int /*port*/, uint64_t payload)
+    __device__ static DeferredWrite handleEventParallel(PCtx& ctx, const uint32_t* scr, uint32_t mt_idx0, uint32_t k,
+        uint32_t n, int /*port*/, uint64_t payload)
     {
-        const uint4     cst = __ldg(reinterpret_cast<const uint4*>(state + 16)); // ngroups, mod, counts
-        const uint32_t  ng  = cst.x;
-        const uint64_t  counts = ((uint64_t)cst.w << 32) | cst.z;
-        const uint32_t* mt  = (const uint32_t*)ctx.aux;
-        const uint32_t  i   = mt_wrap(mt_wrap(mt_idx0 + 2 * k)); // even
-        const uint2     a01 = *reinterpret_cast<const uint2*>(mt + i);
-        const uint32_t  a2  = mt[mt_wrap(i + 2)];
-        const uint32_t  b0  = mt[mt_wrap(i + MT_M)];
-        const uint32_t  b1  = mt[mt_wrap(i + MT_M + 1)];
-        const uint32_t  y0  = (a01.x & 0x80000000u) + (a01.y & 0x7fffffffu);
-        uint32_t        v0  = b0 ^ (y0 >> 1);
+        const uint32_t ng     = scr[4 * n + 4];
+        const uint64_t counts = ((uint64_t)scr[4 * n + 6] << 32) | scr[4 * n + 5];
+        const uint32_t a0 = scr[2 * k], a1 = scr[2 * k + 1], a2 = scr[2 * k + 2];
+        const uint32_t b0 = scr[2 * n + 3 + 2 * k], b1 = scr[2 * n + 4 + 2 * k];
+        const uint32_t y0 = (a0 & 0x80000000u) + (a1 & 0x7fffffffu);
+        uint32_t       v0 = b0 ^ (y0 >> 1);
         if ( y0 & 1u ) v0 ^= 2567483615u;
-        const uint32_t y1 = (a01.y & 0x80000000u) + (a2 & 0x7fffffffu);
+        const uint32_t y1 = (a1 & 0x80000000u) + (a2 & 0x7fffffffu);
         uint32_t       v1 = b1 ^ (y1 >> 1);
         if ( y1 & 1u ) v1 ^= 2567483615u;
+        const uint32_t i = mt_wrap(mt_wrap(mt_idx0 + 2 * k)); // even
+        *reinterpret_cast<uint2*>((uint32_t*)ctx.aux + i) = make_uint2(v0, v1);
         const uint32_t r0 = mt_temper(v0), r1 = mt_temper(v1);
         const uint32_t nextport = (ng & (ng - 1)) == 0 ? (r0 & (ng - 1)) : r0 % ng;
         uint32_t       portnum = 0, base = nextport;
@@ -228,7 +211,7 @@ struct MeshElement
                 base += (uint32_t)((counts >> (8 * g)) & 0xFF);
         }
         ctx.send((int)(base + portnum), 0, payload);
-        return DeferredWrite { i, v0, v1 };
+        return DeferredWrite { 0xFFFFFFFFu, 0, 0 };
     }
     // dispatch prologue hook: pull towards L2 the MT19937 words the next handful of draws will read
     // (words idx.. and idx+397.. mod 624), so that the per-event draws hit L2 instead of paying an HBM round trip each
@@ -273,17 +256,7 @@ struct MeshElement
     {
         s.message_count++;
         uint32_t r0, r1; // the two draws of RouteMessage::send
-#ifdef SSTB200_MESH_STAGE_MT
-        if ( s.win_pair < s.win_n ) { // from the words staged by beginWindow
-            const uint32_t  n = s.win_n, kq = s.win_pair++;
-            if ( kq == 0 ) __pipeline_wait_prior(0); // the staged words have landed
-            const uint32_t* a = ctx.scratch + 2 * kq;
-            const uint32_t* b = ctx.scratch + 2 * n + 3 + 2 * kq;
-            mt_pair_from_words((uint32_t*)ctx.aux, s.mt_idx, a[0], a[1], a[2], b[0], b[1], r0, r1);
-        }
-        else
-#endif
-            mt_u32x2_cached((uint32_t*)ctx.aux, s.mt_idx, s.cache, r0, r1);
+        mt_u32x2_cached((uint32_t*)ctx.aux, s.mt_idx, s.cache, r0, r1);
         // nextport = r0 % ports.size(); portnum = r1 % counts[nextport] (both draws are always made)
         const uint32_t ng       = s.ngroups;
         const uint32_t nextport = (ng & (ng - 1)) == 0 ? (r0 & (ng - 1)) : r0 % ng;

@@ -488,7 +488,8 @@ dispatch_kernel(Dev d)
     uint32_t* s_hist     = s_misc + 4;              // [32] components per event-count bucket, then bucket fill
     uint32_t* s_hbase    = s_hist + 32;             // [32]
     uint16_t* s_perm     = reinterpret_cast<uint16_t*>(s_hbase + 32); // [emax] per-component segments
-    uint16_t* s_order    = s_perm + d.emax;                           // [BLOCK] thread -> component of the block
+    uint16_t* s_sorted   = s_perm + d.emax;                           // [emax] segments in delivery order
+    uint16_t* s_order    = s_sorted + d.emax;                         // [BLOCK] thread -> component of the block
     uint4*    s_hdr      = reinterpret_cast<uint4*>( // [BLOCK] per-component window header of the event-parallel path
         (reinterpret_cast<uintptr_t>(s_order + BLOCK) + 15) & ~(uintptr_t)15);
     uint32_t* s_scratch  = reinterpret_cast<uint32_t*>(s_hdr + BLOCK); // [scr_per_event*emax + scr_fixed*BLOCK]
@@ -638,6 +639,21 @@ dispatch_kernel(Dev d)
         s_hist[tid]  = 0; // reused as the bucket fill counter
     }
     __syncthreads();
+    // (b) order inside each component's segment, (time, port, sequence): every EVENT counts the events of its segment
+    //     that precede it -- balanced over the CTA's threads whatever the distribution of events over components
+    //     (a per-component sort would make the block wait for its busiest component)
+    for ( uint32_t pos = tid; pos < n_due; pos += BLOCK ) {
+        const uint32_t e   = s_perm[pos];
+        const uint32_t cc  = s_pcomp[pos];
+        const uint32_t off = s_off[cc], cnt = s_cnt[cc];
+        const uint32_t te = s_time[e], de = s_dst[e], qe = s_seq[e];
+        uint32_t       rank = 0;
+        for ( uint32_t j = 0; j < cnt; ++j ) {
+            const uint32_t o = s_perm[off + j];
+            rank += key_less(s_time[o], s_dst[o], s_seq[o], te, de, qe) ? 1u : 0u;
+        }
+        s_sorted[off + rank] = (uint16_t)e;
+    }
     // (c, second half) thread -> component assignment
     {
         const uint32_t cnt_c  = s_cnt[tid];
@@ -653,7 +669,7 @@ dispatch_kernel(Dev d)
     const uint32_t  lc     = bin * BLOCK + c;
     const bool      valid  = lc < d.n_local;
     const uint32_t  my_cnt = s_cnt[c];
-    uint16_t*       seg    = s_perm + s_off[c];
+    uint16_t*       seg    = s_sorted + s_off[c];
     uint32_t        delivered = 0, ticks = 0, sent = 0, clocks_stopped = 0;
     if ( valid ) {
         const uint4*   ctlp      = reinterpret_cast<const uint4*>(&d.ctl[lc]);
@@ -678,8 +694,8 @@ dispatch_kernel(Dev d)
                     // phase 3b, and the element agrees (e.g. MT19937: even index, short enough run)
                     if ( my_cnt > 0 && !(next_tick < T_end) && s_off[c] + my_cnt <= PARB * BLOCK &&
                          E::parallelOK(s, my_cnt) ) {
-                        sort_segment(seg, my_cnt, s_time, s_dst, s_seq);
                         s_hdr[c] = make_uint4(E::parallelHeader(s), ctx.seq, dseq, 1u | (E::TYPE << 8));
+                        E::stageParallel(ctx, s, my_cnt); // asynchronous copies into the component's scratch
                         E::finishWindowParallel(s, my_cnt, d.stats_on != 0);
                         ctx.seq += my_cnt * E::PARALLEL_SENDS_PER_EVENT;
                         ctx.sent += my_cnt * E::PARALLEL_SENDS_PER_EVENT;
@@ -691,8 +707,7 @@ dispatch_kernel(Dev d)
                         return;
                     }
                 }
-                E::beginWindow(ctx, s, my_cnt); // issues the element's first loads (MT19937 read-ahead) ...
-                sort_segment(seg, my_cnt, s_time, s_dst, s_seq); // ... which ordering the segment overlaps
+                E::beginWindow(ctx, s, my_cnt); // issues the element's first loads (MT19937 read-ahead)
                 uint64_t cycle = (next_tick != TIME_NEVER && period) ? next_tick / period : 0;
                 uint32_t i     = 0;
                 for ( ;; ) {
@@ -749,7 +764,9 @@ dispatch_kernel(Dev d)
     // over components, and no sequential chain.  Reads of the aux block happen before the barrier, the handlers'
     // deferred writes after it.
     if ( d.any_parallel ) {
-        __syncthreads();
+        __pipeline_commit();
+        __pipeline_wait_prior(0); // this thread's staged copies have landed ...
+        __syncthreads();          // ... and everybody else's
         PHASE_MARK(6);
         DeferredWrite dw[PARB];
         uint32_t      dw_lc[PARB];
@@ -758,7 +775,7 @@ dispatch_kernel(Dev d)
             dw[j].word       = 0xFFFFFFFFu;
             const uint32_t p = tid + j * BLOCK;
             if ( p >= n_due ) continue;
-            const uint32_t e   = s_perm[p];
+            const uint32_t e   = s_sorted[p];
             const uint32_t cc  = s_pcomp[p];
             const uint4    hdr = s_hdr[cc];
             if ( !(hdr.w & 1u) ) continue;
@@ -788,7 +805,7 @@ dispatch_kernel(Dev d)
                                 d.stats_on,
                                 links_in_smem ? (const uint4*)(s_link + (p0 - blk_port0)) : d.link + (p0 - d.P0),
                                 Stage { s_time, s_dst, s_seq, s_cr, PAYLOAD ? s_pay : nullptr }, e, false };
-                    dw[j] = E::handleEventParallel(pc, d.state + (uint64_t)lcc * d.state_stride, hdr.x, kk,
+                    dw[j] = E::handleEventParallel(pc, s_scratch + d.scr_per_event * s_off[cc] + d.scr_fixed * cc, hdr.x, kk,
                         s_cnt[cc], (int)port, pl);
                 }
             });
@@ -1584,7 +1601,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     CUDA_OK(cudaMemcpyAsync(d.ctrl, e->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, e->stream));
 
     e->smem_bytes = (size_t)d.lmax * 16 + (size_t)d.emax * (has_payload ? 8 : 0) + (size_t)d.emax * 16 +
-                    (size_t)(BLOCK + 1 + BLOCK + BLOCK + BLOCK / 32 + 1 + 4 + 32 + 32) * 4 + (size_t)d.emax * 2 +
+                    (size_t)(BLOCK + 1 + BLOCK + BLOCK + BLOCK / 32 + 1 + 4 + 32 + 32) * 4 + (size_t)d.emax * 4 +
                     (size_t)BLOCK * 2 + 16 + (size_t)BLOCK * 16 + ((size_t)d.scr_per_event * d.emax + (size_t)d.scr_fixed * BLOCK) * 4 +
                     (size_t)d.emax + 16;
     if ( e->smem_bytes > 227 * 1024 ) {
