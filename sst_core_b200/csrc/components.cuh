@@ -133,9 +133,8 @@ struct MeshElement
     };
     static constexpr uint32_t STORE_END = 16, CONST_END = 32, STATS_END = 80, PERSIST_BYTES = 80;
     // shared-memory scratch: the MT19937 words this window's draws will read, 4 per event (+3 per component)
-    // shared-memory scratch of the event-parallel path: the MT19937 words the window's pairs read (4 per event + 4)
-    // and the construction constants the handlers need (4 words)
-    static constexpr uint32_t SCRATCH_PER_EVENT = 4, SCRATCH_FIXED = 8;
+    // no extra shared-memory scratch: the event-parallel path stages what it needs in arrays the sort has freed
+    static constexpr uint32_t SCRATCH_PER_EVENT = 0, SCRATCH_FIXED = 0;
     // sequential path: issue the read-ahead loads now, they fly while the engine does the rest of its set-up
     template <class Ctx>
     __device__ static void beginWindow(Ctx& ctx, State& s, uint32_t n_events)
@@ -149,31 +148,28 @@ struct MeshElement
     // msg_count statistic) is a sum.  So the n events of a component run on n threads.
     static constexpr bool     PARALLEL_EVENTS          = true;
     static constexpr uint32_t PARALLEL_SENDS_PER_EVENT = 1;
-    __device__ static uint32_t parallelHeader(const State& s) { return s.mt_idx; }
-    __device__ static bool parallelOK(const State& s, uint32_t n)
+    // may this component's n events of the window run in parallel?  Decided from the state in memory (16 bytes of
+    // core + 16 of constants): MT19937 index even, run short enough (MT_STAGE_MAX_PAIRS), one link per port group
+    // (so that the second draw only advances the generator)
+    __device__ static bool parallelOK(const uint8_t* state, uint32_t n)
     {
-        return (s.mt_idx & 1u) == 0 && n <= MT_STAGE_MAX_PAIRS;
+        const uint4    core = __ldg(reinterpret_cast<const uint4*>(state));
+        const uint4    cst  = __ldg(reinterpret_cast<const uint4*>(state + 16));
+        const uint64_t counts = ((uint64_t)cst.w << 32) | cst.z;
+        return (core.y & 1u) == 0 && n <= MT_STAGE_MAX_PAIRS && cst.x >= 1 && cst.x <= 8 &&
+               counts == (0x0101010101010101ull >> (8 * (8 - cst.x)));
     }
-    // 3a, component thread: copy into the component's shared-memory scratch, asynchronously (LDGSTS, all copies in
-    // flight at once), everything the n parallel handlers will read:
-    //   scr[0 .. 2n+1]        mt[i .. i+2n+1]        (n+1 aligned 8-byte chunks)
-    //   scr[2n+3 .. 4n+3]     mt[i+397 .. i+397+2n]  (one word, then n aligned chunks)
-    //   scr[4n+4 .. 4n+6]     ngroups, counts        (construction constants)
-    // The engine waits for the copies and synchronises the block before 3b.
-    template <class Ctx>
-    __device__ static void stageParallel(Ctx& ctx, const State& s, uint32_t n)
+    // header word the event threads get: MT19937 index at the start of the window | number of port groups << 16
+    __device__ static uint32_t parallelHeader(const State& s) { return s.mt_idx | (s.ngroups << 16); }
+    // 3a, component thread: asynchronous copies (LDGSTS) of the a-run: chunk j = (mt[i+2j], mt[i+2j+1]) to
+    // staged[j] (delivery position j of this component), and mt[i+2n] (the last pair's third word) to *extra
+    __device__ static void stageParallel(const uint8_t* aux, const State& s, uint32_t n, uint2* staged, uint32_t* extra)
     {
-        const uint32_t* mt  = (const uint32_t*)ctx.aux;
-        uint32_t*       scr = ctx.scratch;
-        const uint32_t  i   = s.mt_idx;
-        for ( uint32_t c = 0; c <= n; ++c )
-            __pipeline_memcpy_async(scr + 2 * c, mt + mt_wrap(mt_wrap(i + 2 * c)), 8);
-        __pipeline_memcpy_async(scr + 2 * n + 3, mt + mt_wrap(i + MT_M), 4);
-        for ( uint32_t c = 0; c < n; ++c )
-            __pipeline_memcpy_async(scr + 2 * n + 4 + 2 * c, mt + mt_wrap(mt_wrap(i + MT_M + 1 + 2 * c)), 8);
-        scr[4 * n + 4] = s.ngroups;
-        scr[4 * n + 5] = (uint32_t)s.counts;
-        scr[4 * n + 6] = (uint32_t)(s.counts >> 32);
+        const uint32_t* mt = (const uint32_t*)aux;
+        const uint32_t  i  = s.mt_idx;
+        for ( uint32_t j = 0; j < n; ++j )
+            __pipeline_memcpy_async(staged + j, mt + mt_wrap(mt_wrap(i + 2 * j)), 8);
+        __pipeline_memcpy_async(extra, mt + mt_wrap(mt_wrap(i + 2 * n)), 4);
     }
     __device__ static void finishWindowParallel(State& s, uint32_t n, bool stats_on)
     {
@@ -181,37 +177,39 @@ struct MeshElement
         s.mt_idx = mt_wrap(mt_wrap(s.mt_idx + 2 * n));
         if ( stats_on ) s.mcnt.addN(1, n); // addData_impl_Ntimes, stataccumulator.h:97-103
     }
-    // 3b, one thread per event: k-th event (delivery order) of a component that has n this window.  Reads shared
-    // memory only; writes the two new-generation words straight to the MT19937 state (nobody reads that state again
-    // in this window: every read was staged before the block synchronised).
-    template <class PCtx>
-    __device__ static DeferredWrite handleEventParallel(PCtx& ctx, const uint32_t* scr, uint32_t mt_idx0, uint32_t k,
-        uint32_t n, int /*port*/, uint64_t payload)
+    // 3b.1, event thread k: the b-run words mt[i+2k+397], mt[i+2k+398] straight from memory.  No pair of the window
+    // writes them (pair k' writes mt[i+2k'], mt[i+2k'+1]; 2(k'-k) = 397 is impossible and 2(k'-k)+1 = 397 needs
+    // k'-k = 198 > MT_STAGE_MAX_PAIRS), so reading them while other events write is race-free.
+    __device__ static uint2 parallelLoad(const uint8_t* aux, uint32_t hdr, uint32_t k)
     {
-        const uint32_t ng     = scr[4 * n + 4];
-        const uint64_t counts = ((uint64_t)scr[4 * n + 6] << 32) | scr[4 * n + 5];
-        const uint32_t a0 = scr[2 * k], a1 = scr[2 * k + 1], a2 = scr[2 * k + 2];
-        const uint32_t b0 = scr[2 * n + 3 + 2 * k], b1 = scr[2 * n + 4 + 2 * k];
-        const uint32_t y0 = (a0 & 0x80000000u) + (a1 & 0x7fffffffu);
-        uint32_t       v0 = b0 ^ (y0 >> 1);
+        const uint32_t* mt = (const uint32_t*)aux;
+        const uint32_t  i  = mt_wrap(mt_wrap((hdr & 0xFFFFu) + 2 * k));
+        return make_uint2(mt[mt_wrap(i + MT_M)], mt[mt_wrap(i + MT_M + 1)]);
+    }
+    // 3b.2: the pair of draws of RouteMessage::send for the k-th event, new-generation words written back; returns
+    // the port the event leaves on
+    __device__ static uint32_t parallelCompute(uint8_t* aux, const uint4& hdr, const uint2* staged, uint32_t k, uint32_t n,
+        uint2 b)
+    {
+        const uint2    a01 = staged[k];
+        const uint32_t a2  = (k + 1 < n) ? staged[k + 1].x : hdr.w;
+        const uint32_t y0  = (a01.x & 0x80000000u) + (a01.y & 0x7fffffffu);
+        uint32_t       v0  = b.x ^ (y0 >> 1);
         if ( y0 & 1u ) v0 ^= 2567483615u;
-        const uint32_t y1 = (a1 & 0x80000000u) + (a2 & 0x7fffffffu);
-        uint32_t       v1 = b1 ^ (y1 >> 1);
+        const uint32_t y1 = (a01.y & 0x80000000u) + (a2 & 0x7fffffffu);
+        uint32_t       v1 = b.y ^ (y1 >> 1);
         if ( y1 & 1u ) v1 ^= 2567483615u;
-        const uint32_t i = mt_wrap(mt_wrap(mt_idx0 + 2 * k)); // even
-        *reinterpret_cast<uint2*>((uint32_t*)ctx.aux + i) = make_uint2(v0, v1);
-        const uint32_t r0 = mt_temper(v0), r1 = mt_temper(v1);
-        const uint32_t nextport = (ng & (ng - 1)) == 0 ? (r0 & (ng - 1)) : r0 % ng;
-        uint32_t       portnum = 0, base = nextport;
-        if ( counts != (0x0101010101010101ull >> (8 * (8 - ng))) ) {
-            const uint32_t cnt = (uint32_t)((counts >> (8 * nextport)) & 0xFF);
-            portnum            = r1 % cnt;
-            base               = 0;
-            for ( uint32_t g = 0; g < nextport; ++g )
-                base += (uint32_t)((counts >> (8 * g)) & 0xFF);
-        }
-        ctx.send((int)(base + portnum), 0, payload);
-        return DeferredWrite { 0xFFFFFFFFu, 0, 0 };
+        const uint32_t i = mt_wrap(mt_wrap((hdr.x & 0xFFFFu) + 2 * k)); // even
+        *reinterpret_cast<uint2*>((uint32_t*)aux + i) = make_uint2(v0, v1);
+        const uint32_t r0 = mt_temper(v0);
+        const uint32_t ng = hdr.x >> 16;
+        return (ng & (ng - 1)) == 0 ? (r0 & (ng - 1)) : r0 % ng; // one link per group: port = group
+    }
+    // 3b.3: the send
+    template <class PCtx>
+    __device__ static void parallelSend(PCtx& ctx, uint32_t out_port, int /*port*/, uint64_t payload)
+    {
+        ctx.send((int)out_port, 0, payload);
     }
     // dispatch prologue hook: pull towards L2 the MT19937 words the next handful of draws will read
     // (words idx.. and idx+397.. mod 624), so that the per-event draws hit L2 instead of paying an HBM round trip each

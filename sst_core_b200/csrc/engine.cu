@@ -197,14 +197,13 @@ emit(const Dev& d, uint64_t k, uint64_t time, uint32_t dst_port, uint32_t dst_co
 // Shared-memory view of one block's staged events.  Due events are staged here by phase 1; as a component consumes
 // its events the slots are recycled for the events it sends (out-staging), and the owning warp flushes them with
 // warp-aggregated reservations.  Record layout per slot (4 x u32 [+ u64 payload]):
-//   staged-in : t = time - T, a = receiving port, b = sequence, c = comp<<16 | rank (sorting scratch)
-//   staged-out: t = arrival - T, a = receiving port, b = sequence, c = destination component
+//   staged-in : t = time - T, a = receiving port, sc = {sequence, comp<<16 | rank (sorting scratch)}
+//   staged-out: t = arrival - T, a = receiving port, sc = {sequence, destination component}
 struct Stage
 {
     uint32_t* t;
     uint32_t* a;
-    uint32_t* b;
-    uint32_t* c;
+    uint2*    sc; // {sequence, destination component}
     uint64_t* pay;
 };
 
@@ -246,8 +245,7 @@ struct CtxT
                 const uint32_t slot = seg[free_head++];
                 st.t[slot]          = (uint32_t)off;
                 st.a[slot]          = l.x;
-                st.b[slot]          = sq;
-                st.c[slot]          = l.y;
+                st.sc[slot]         = make_uint2(sq, l.y);
                 if ( st.pay ) st.pay[slot] = payload;
                 return;
             }
@@ -393,25 +391,6 @@ gtimer()
 #define PHASE_MARK(i)
 #endif
 
-// (time, port, sequence) order of one component's segment: insertion sort by the owning thread (segments are a
-// handful of events; the lanes of a warp own components with nearly equal event counts)
-__device__ __forceinline__ void
-sort_segment(uint16_t* seg, uint32_t cnt, const uint32_t* s_time, const uint32_t* s_dst, const uint32_t* s_seq)
-{
-    for ( uint32_t a = 1; a < cnt; ++a ) {
-        const uint16_t ea = seg[a];
-        const uint32_t ta = s_time[ea], da = s_dst[ea], qa = s_seq[ea];
-        uint32_t       b  = a;
-        while ( b > 0 ) {
-            const uint16_t eb = seg[b - 1];
-            if ( !key_less(ta, da, qa, s_time[eb], s_dst[eb], s_seq[eb]) ) break;
-            seg[b] = eb;
-            --b;
-        }
-        seg[b] = ea;
-    }
-}
-
 // Context of an EVENT-PARALLEL handler (elements with PARALLEL_EVENTS): the handler of the k-th event (in delivery
 // order) of a component runs on its own thread, concurrently with the handlers of the component's other events of the
 // window.  It sees the component's state as it was at the start of the window (read-only), sends exactly
@@ -441,8 +420,7 @@ struct ParCtx
             used       = true;
             st.t[slot] = (uint32_t)off;
             st.a[slot] = l.x;
-            st.b[slot] = sq;
-            st.c[slot] = l.y;
+            st.sc[slot] = make_uint2(sq, l.y);
             if ( st.pay ) st.pay[slot] = payload;
             return;
         }
@@ -478,9 +456,8 @@ dispatch_kernel(Dev d)
     uint8_t*  p          = reinterpret_cast<uint8_t*>(s_pay) + (PAYLOAD ? (size_t)d.emax * 8 : 0);
     uint32_t* s_time     = reinterpret_cast<uint32_t*>(p);
     uint32_t* s_dst      = s_time + d.emax;
-    uint32_t* s_seq      = s_dst + d.emax;
-    uint32_t* s_cr       = s_seq + d.emax;
-    uint32_t* s_port_off = s_cr + d.emax;           // [BLOCK+1]
+    uint2*    s_sc       = reinterpret_cast<uint2*>(s_dst + d.emax); // [emax] {sequence, comp<<16|rank / dst comp}
+    uint32_t* s_port_off = reinterpret_cast<uint32_t*>(s_sc + d.emax); // [BLOCK+1]
     uint32_t* s_cnt      = s_port_off + BLOCK + 1;  // [BLOCK]
     uint32_t* s_off      = s_cnt + BLOCK;           // [BLOCK]
     uint32_t* s_warp     = s_off + BLOCK;           // [BLOCK/32+1]
@@ -586,8 +563,7 @@ dispatch_kernel(Dev d)
                 const uint32_t r = atomicAdd(&s_cnt[lo], 1u);
                 s_time[e]        = (uint32_t)(t - T);
                 s_dst[e]         = dst;
-                s_seq[e]         = (uint32_t)ds;
-                s_cr[e]          = (lo << 16) | (r & 0xFFFFu);
+                s_sc[e]          = make_uint2((uint32_t)ds, (lo << 16) | (r & 0xFFFFu));
                 if ( PAYLOAD ) s_pay[e] = pl;
             }
         }
@@ -622,7 +598,7 @@ dispatch_kernel(Dev d)
     }
     __syncthreads();
     for ( uint32_t e = tid; e < n_due; e += BLOCK ) {
-        const uint32_t cr  = s_cr[e];
+        const uint32_t cr  = s_sc[e].y;
         const uint32_t pos = s_off[cr >> 16] + (cr & 0xFFFFu);
         s_perm[pos]        = (uint16_t)e;
         s_pcomp[pos]       = (uint8_t)(cr >> 16);
@@ -646,11 +622,11 @@ dispatch_kernel(Dev d)
         const uint32_t e   = s_perm[pos];
         const uint32_t cc  = s_pcomp[pos];
         const uint32_t off = s_off[cc], cnt = s_cnt[cc];
-        const uint32_t te = s_time[e], de = s_dst[e], qe = s_seq[e];
+        const uint32_t te = s_time[e], de = s_dst[e], qe = s_sc[e].x;
         uint32_t       rank = 0;
         for ( uint32_t j = 0; j < cnt; ++j ) {
             const uint32_t o = s_perm[off + j];
-            rank += key_less(s_time[o], s_dst[o], s_seq[o], te, de, qe) ? 1u : 0u;
+            rank += key_less(s_time[o], s_dst[o], s_sc[o].x, te, de, qe) ? 1u : 0u;
         }
         s_sorted[off + rank] = (uint16_t)e;
     }
@@ -663,130 +639,120 @@ dispatch_kernel(Dev d)
     __syncthreads();
 
     PHASE_MARK(3);
-    // ---- phase 3: thread t runs component s_order[t]: walks its segment in delivery order, merged with the
-    // component's clock ticks; sends are staged in the slots the component has already consumed
+    // ---- phase 3: run the handlers.  Thread t owns component s_order[t] (the t-th busiest of the block).
     const uint32_t  c      = s_order[tid];
     const uint32_t  lc     = bin * BLOCK + c;
     const bool      valid  = lc < d.n_local;
     const uint32_t  my_cnt = s_cnt[c];
     uint16_t*       seg    = s_sorted + s_off[c];
     uint32_t        delivered = 0, ticks = 0, sent = 0, clocks_stopped = 0;
+    uint4           c_lo = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0), c_hi = make_uint4(0, 0, 0, 0);
     if ( valid ) {
-        const uint4*   ctlp      = reinterpret_cast<const uint4*>(&d.ctl[lc]);
-        const uint4    c_lo = ctlp[0], c_hi = ctlp[1];
-        uint64_t       next_tick = ((uint64_t)c_lo.y << 32) | c_lo.x;
-        const uint64_t period    = ((uint64_t)c_hi.y << 32) | c_hi.x;
-        const bool     has_work  = my_cnt > 0 || next_tick < T_end;
+        const uint4* ctlp = reinterpret_cast<const uint4*>(&d.ctl[lc]);
+        c_lo              = ctlp[0];
+        c_hi              = ctlp[1];
+    }
+    uint64_t       next_tick = ((uint64_t)c_lo.y << 32) | c_lo.x;
+    const uint64_t period    = ((uint64_t)c_hi.y << 32) | c_hi.x;
+    const uint32_t my_type   = d.uniform_type ? d.uniform_type : c_hi.z;
+    const bool     has_work  = valid && (my_cnt > 0 || next_tick < T_end);
+    const uint32_t p0        = s_port_off[c];
+    const uint4*   my_links  = links_in_smem ? (const uint4*)(s_link + (p0 - blk_port0)) : d.link + (p0 - d.P0);
+
+    // ---- phase 3 (event-parallel form).  When EVERY component of the block that has work can take it -- its element
+    // has an event-parallel handler, no clock tick is due, the element agrees (MT19937: even index, short run) -- the
+    // block runs one thread per EVENT instead of one per component:
+    //   3a  component thread: window header (what the events need of the window-start state), asynchronous staging
+    //       of the aux words the handlers read into the (sequence, comp) array -- free after the sort, indexed by
+    //       delivery position --, the state update for all n events at once, write-back;
+    //   3b  event thread (positions t, t+256, ...): global words first (all loads in flight), then compute + aux
+    //       write-back, block barrier, then the sends into the events' own slots.
+    // Perfectly balanced however the events are spread over components; no sequential chain; a block's registers and
+    // shared memory are no longer held for its busiest component.
+    bool par_ok = !has_work; // components with nothing to do do not object
+    if ( has_work && d.any_parallel && n_due <= PARB * BLOCK && my_cnt > 0 && !(next_tick < T_end) ) {
+        with_element(my_type, [&](auto el) {
+            using E = decltype(el);
+            if constexpr ( E::PARALLEL_EVENTS )
+                par_ok = E::parallelOK(d.state + (uint64_t)lc * d.state_stride, my_cnt);
+        });
+    }
+    const bool block_par = d.any_parallel && __syncthreads_and(par_ok ? 1 : 0);
+    if ( block_par ) {
         if ( has_work ) {
-            const uint32_t p0 = s_port_off[c];
-            CtxT<true>     ctx { d, T, k, T, d.c0 + lc, p0, s_port_off[c + 1] - p0,
-                                 d.aux + (uint64_t)lc * d.aux_stride, c_lo.z, 0, d.stats_on,
-                                 links_in_smem ? (const uint4*)(s_link + (p0 - blk_port0)) : d.link + (p0 - d.P0),
-                                 d.scr_per_event | d.scr_fixed ? s_scratch + d.scr_per_event * s_off[c] + d.scr_fixed * c : nullptr,
-                                 Stage { s_time, s_dst, s_seq, s_cr, PAYLOAD ? s_pay : nullptr }, seg, 0, 0 };
-            uint32_t       dseq = c_lo.w;
-            with_element(d.uniform_type ? d.uniform_type : c_hi.z, [&](auto el) {
+            with_element(my_type, [&](auto el) {
                 using E = decltype(el);
-                typename E::State s;
-                load_state(s, d.state + (uint64_t)lc * d.state_stride, 0, d.stats_on ? E::STATS_END : E::CONST_END);
                 if constexpr ( E::PARALLEL_EVENTS ) {
-                    // event-parallel path: no clock tick due, the whole segment inside the register window of
-                    // phase 3b, and the element agrees (e.g. MT19937: even index, short enough run)
-                    if ( my_cnt > 0 && !(next_tick < T_end) && s_off[c] + my_cnt <= PARB * BLOCK &&
-                         E::parallelOK(s, my_cnt) ) {
-                        s_hdr[c] = make_uint4(E::parallelHeader(s), ctx.seq, dseq, 1u | (E::TYPE << 8));
-                        E::stageParallel(ctx, s, my_cnt); // asynchronous copies into the component's scratch
-                        E::finishWindowParallel(s, my_cnt, d.stats_on != 0);
-                        ctx.seq += my_cnt * E::PARALLEL_SENDS_PER_EVENT;
-                        ctx.sent += my_cnt * E::PARALLEL_SENDS_PER_EVENT;
-                        if ( d.trace_cap ) dseq += my_cnt;
-                        delivered = my_cnt;
-                        store_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::STORE_END);
-                        if ( d.stats_on )
-                            store_state(s, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
-                        return;
-                    }
+                    typename E::State st_;
+                    load_state(st_, d.state + (uint64_t)lc * d.state_stride, 0, d.stats_on ? E::STATS_END : E::CONST_END);
+                    uint4 hdr = make_uint4(E::parallelHeader(st_), c_lo.z, c_lo.w, 0);
+                    // stage: position-indexed chunk array (n entries) + one extra word (header .w)
+                    E::stageParallel(d.aux + (uint64_t)lc * d.aux_stride, st_, my_cnt, s_sc + s_off[c], &s_hdr[c].w);
+                    s_hdr[c].x = hdr.x;
+                    s_hdr[c].y = hdr.y;
+                    s_hdr[c].z = hdr.z;
+                    E::finishWindowParallel(st_, my_cnt, d.stats_on != 0);
+                    store_state(st_, d.state + (uint64_t)lc * d.state_stride, 0, E::STORE_END);
+                    if ( d.stats_on )
+                        store_state(st_, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
+                    const uint32_t nsend = my_cnt * E::PARALLEL_SENDS_PER_EVENT;
+                    *reinterpret_cast<uint4*>(&d.ctl[lc]) =
+                        make_uint4(c_lo.x, c_lo.y, c_lo.z + nsend, c_lo.w + (d.trace_cap ? my_cnt : 0));
+                    delivered = my_cnt;
+                    sent      = nsend;
                 }
-                E::beginWindow(ctx, s, my_cnt); // issues the element's first loads (MT19937 read-ahead)
-                uint64_t cycle = (next_tick != TIME_NEVER && period) ? next_tick / period : 0;
-                uint32_t i     = 0;
-                for ( ;; ) {
-                    const uint64_t ev_t = (i < my_cnt) ? T + s_time[seg[i]] : TIME_NEVER;
-                    if ( next_tick < T_end && next_tick <= ev_t ) {
-                        ctx.now         = next_tick;
-                        const bool stop = E::clockTick(ctx, s, cycle);
-                        ticks++;
-                        cycle++;
-                        if ( stop ) {
-                            next_tick = TIME_NEVER; // handler unregistered itself (clock.cc:324-367)
-                            clocks_stopped++;
-                        }
-                        else
-                            next_tick += period;
-                        continue;
-                    }
-                    if ( i >= my_cnt ) break;
-                    const uint32_t e    = seg[i++];
-                    const uint32_t port = s_dst[e] - ctx.port0;
-                    uint64_t       pl   = PAYLOAD ? s_pay[e] : 0;
-                    s_dst[e]            = SSTB200_NO_PEER; // slot e is consumed: free for out-staging
-                    ctx.free_tail       = i;
-                    ctx.now             = ev_t;
-                    if ( d.trace_cap ) {
-                        const unsigned long long tp = atomicAdd(&ctrl->trace_n, 1ull);
-                        if ( tp < d.trace_cap ) {
-                            d.tr_time[tp]    = ev_t;
-                            d.tr_comp[tp]    = ctx.comp;
-                            d.tr_port[tp]    = port;
-                            d.tr_idx[tp]     = dseq;
-                            d.tr_payload[tp] = pl;
-                        }
-                        dseq++;
-                    }
-                    E::handleEvent(ctx, s, (int)port, pl);
-                    delivered++;
-                }
-                store_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::STORE_END);
-                if ( d.stats_on ) store_state(s, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
             });
-            *reinterpret_cast<uint4*>(&d.ctl[lc]) =
-                make_uint4((uint32_t)next_tick, (uint32_t)(next_tick >> 32), ctx.seq, dseq);
-            sent = ctx.sent;
         }
-    }
-    if ( threadIdx.x == 255 ) {
-#ifdef SSTB200_TIMING
-        if ( blockIdx.x < (1 << 17) ) g_phase_times[blockIdx.x * 8 + 7] = gtimer(); // lightest warp done with phase 3a
-#endif
-    }
-    // ---- phase 3b: event-parallel handlers.  Thread t takes the events at positions t, t+256, ... of the ordered
-    // segments whose component chose the parallel path in 3a: perfectly balanced however the events are spread
-    // over components, and no sequential chain.  Reads of the aux block happen before the barrier, the handlers'
-    // deferred writes after it.
-    if ( d.any_parallel ) {
         __pipeline_commit();
         __pipeline_wait_prior(0); // this thread's staged copies have landed ...
         __syncthreads();          // ... and everybody else's
         PHASE_MARK(6);
-        DeferredWrite dw[PARB];
-        uint32_t      dw_lc[PARB];
+        // 3b.1: the global words each event needs, all loads issued before any is used
+        uint2    gw[PARB];
+        uint32_t tok[PARB];
 #pragma unroll
         for ( int j = 0; j < PARB; ++j ) {
-            dw[j].word       = 0xFFFFFFFFu;
+            const uint32_t p = tid + j * BLOCK;
+            gw[j]            = make_uint2(0, 0);
+            if ( p >= n_due ) continue;
+            const uint32_t cc = s_pcomp[p];
+            with_element(d.uniform_type ? d.uniform_type : d.comp_type[bin * BLOCK + cc], [&](auto el) {
+                using E = decltype(el);
+                if constexpr ( E::PARALLEL_EVENTS )
+                    gw[j] = E::parallelLoad(d.aux + (uint64_t)(bin * BLOCK + cc) * d.aux_stride, s_hdr[cc].x, p - s_off[cc]);
+            });
+        }
+        // 3b.2: compute; the handler writes its new aux words and returns what its send step needs
+#pragma unroll
+        for ( int j = 0; j < PARB; ++j ) {
+            const uint32_t p = tid + j * BLOCK;
+            tok[j]           = 0;
+            if ( p >= n_due ) continue;
+            const uint32_t cc = s_pcomp[p];
+            const uint32_t kk = p - s_off[cc], nn = s_cnt[cc];
+            with_element(d.uniform_type ? d.uniform_type : d.comp_type[bin * BLOCK + cc], [&](auto el) {
+                using E = decltype(el);
+                if constexpr ( E::PARALLEL_EVENTS )
+                    tok[j] = E::parallelCompute(d.aux + (uint64_t)(bin * BLOCK + cc) * d.aux_stride, s_hdr[cc],
+                        s_sc + s_off[cc], kk, nn, gw[j]);
+            });
+        }
+        __syncthreads(); // every staged word has been read: the (sequence, comp) array may be overwritten by sends
+        // 3b.3: the sends, each into its own event's slot
+#pragma unroll
+        for ( int j = 0; j < PARB; ++j ) {
             const uint32_t p = tid + j * BLOCK;
             if ( p >= n_due ) continue;
-            const uint32_t e   = s_sorted[p];
-            const uint32_t cc  = s_pcomp[p];
-            const uint4    hdr = s_hdr[cc];
-            if ( !(hdr.w & 1u) ) continue;
+            const uint32_t e    = s_sorted[p];
+            const uint32_t cc   = s_pcomp[p];
             const uint32_t kk   = p - s_off[cc];
             const uint32_t lcc  = bin * BLOCK + cc;
-            const uint32_t p0   = s_port_off[cc];
-            const uint32_t port = s_dst[e] - p0;
+            const uint32_t pp0  = s_port_off[cc];
+            const uint32_t port = s_dst[e] - pp0;
             const uint64_t pl   = PAYLOAD ? s_pay[e] : 0;
             const uint64_t ev_t = T + s_time[e];
+            const uint4    hdr  = s_hdr[cc];
             s_dst[e]            = SSTB200_NO_PEER; // consumed; a send re-fills the slot
-            dw_lc[j]            = lcc;
             if ( d.trace_cap ) {
                 const unsigned long long tp = atomicAdd(&ctrl->trace_n, 1ull);
                 if ( tp < d.trace_cap ) {
@@ -797,25 +763,76 @@ dispatch_kernel(Dev d)
                     d.tr_payload[tp] = pl;
                 }
             }
-            with_element(hdr.w >> 8, [&](auto el) {
+            with_element(d.uniform_type ? d.uniform_type : d.comp_type[lcc], [&](auto el) {
                 using E = decltype(el);
                 if constexpr ( E::PARALLEL_EVENTS ) {
-                    ParCtx pc { d, ev_t, k, T, d.c0 + lcc, p0, s_port_off[cc + 1] - p0,
+                    ParCtx pc { d, ev_t, k, T, d.c0 + lcc, pp0, s_port_off[cc + 1] - pp0,
                                 d.aux + (uint64_t)lcc * d.aux_stride, hdr.y + kk * E::PARALLEL_SENDS_PER_EVENT,
                                 d.stats_on,
-                                links_in_smem ? (const uint4*)(s_link + (p0 - blk_port0)) : d.link + (p0 - d.P0),
-                                Stage { s_time, s_dst, s_seq, s_cr, PAYLOAD ? s_pay : nullptr }, e, false };
-                    dw[j] = E::handleEventParallel(pc, s_scratch + d.scr_per_event * s_off[cc] + d.scr_fixed * cc, hdr.x, kk,
-                        s_cnt[cc], (int)port, pl);
+                                links_in_smem ? (const uint4*)(s_link + (pp0 - blk_port0)) : d.link + (pp0 - d.P0),
+                                Stage { s_time, s_dst, s_sc, PAYLOAD ? s_pay : nullptr }, e, false };
+                    E::parallelSend(pc, tok[j], (int)port, pl);
                 }
             });
         }
-        __syncthreads();
-#pragma unroll
-        for ( int j = 0; j < PARB; ++j )
-            if ( dw[j].word != 0xFFFFFFFFu )
-                *reinterpret_cast<uint2*>(d.aux + (uint64_t)dw_lc[j] * d.aux_stride + (uint64_t)dw[j].word * 4) =
-                    make_uint2(dw[j].v0, dw[j].v1);
+    }
+    else if ( has_work ) {
+        // ---- phase 3 (sequential form): walks the component's segment in delivery order, merged with its clock
+        // ticks; sends are staged in the slots the component has already consumed
+        CtxT<true> ctx { d, T, k, T, d.c0 + lc, p0, s_port_off[c + 1] - p0,
+                         d.aux + (uint64_t)lc * d.aux_stride, c_lo.z, 0, d.stats_on, my_links,
+                         d.scr_per_event | d.scr_fixed ? s_scratch + d.scr_per_event * s_off[c] + d.scr_fixed * c : nullptr,
+                         Stage { s_time, s_dst, s_sc, PAYLOAD ? s_pay : nullptr }, seg, 0, 0 };
+        uint32_t   dseq = c_lo.w;
+        with_element(my_type, [&](auto el) {
+            using E = decltype(el);
+            typename E::State s;
+            load_state(s, d.state + (uint64_t)lc * d.state_stride, 0, d.stats_on ? E::STATS_END : E::CONST_END);
+            E::beginWindow(ctx, s, my_cnt); // issues the element's first loads (MT19937 read-ahead)
+            uint64_t cycle = (next_tick != TIME_NEVER && period) ? next_tick / period : 0;
+            uint32_t i     = 0;
+            for ( ;; ) {
+                const uint64_t ev_t = (i < my_cnt) ? T + s_time[seg[i]] : TIME_NEVER;
+                if ( next_tick < T_end && next_tick <= ev_t ) {
+                    ctx.now         = next_tick;
+                    const bool stop = E::clockTick(ctx, s, cycle);
+                    ticks++;
+                    cycle++;
+                    if ( stop ) {
+                        next_tick = TIME_NEVER; // handler unregistered itself (clock.cc:324-367)
+                        clocks_stopped++;
+                    }
+                    else
+                        next_tick += period;
+                    continue;
+                }
+                if ( i >= my_cnt ) break;
+                const uint32_t e    = seg[i++];
+                const uint32_t port = s_dst[e] - ctx.port0;
+                uint64_t       pl   = PAYLOAD ? s_pay[e] : 0;
+                s_dst[e]            = SSTB200_NO_PEER; // slot e is consumed: free for out-staging
+                ctx.free_tail       = i;
+                ctx.now             = ev_t;
+                if ( d.trace_cap ) {
+                    const unsigned long long tp = atomicAdd(&ctrl->trace_n, 1ull);
+                    if ( tp < d.trace_cap ) {
+                        d.tr_time[tp]    = ev_t;
+                        d.tr_comp[tp]    = ctx.comp;
+                        d.tr_port[tp]    = port;
+                        d.tr_idx[tp]     = dseq;
+                        d.tr_payload[tp] = pl;
+                    }
+                    dseq++;
+                }
+                E::handleEvent(ctx, s, (int)port, pl);
+                delivered++;
+            }
+            store_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::STORE_END);
+            if ( d.stats_on ) store_state(s, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
+        });
+        *reinterpret_cast<uint4*>(&d.ctl[lc]) =
+            make_uint4((uint32_t)next_tick, (uint32_t)(next_tick >> 32), ctx.seq, dseq);
+        sent = ctx.sent;
     }
     __syncthreads();
     PHASE_MARK(4);
@@ -841,7 +858,7 @@ dispatch_kernel(Dev d)
         auto          classify_out = [&](uint32_t e, uint32_t& ky_out, uint32_t& ent_out, uint32_t& rank_out) {
             ent_out = 0xFFFFFFFFu;
             if ( e >= n_due || s_dst[e] == SSTB200_NO_PEER ) return;
-            const uint32_t dcomp = s_cr[e];
+            const uint32_t dcomp = s_sc[e].y;
             const uint32_t dt    = s_time[e];
             uint32_t       ky;
             if ( d.n_ranks > 1 && (dcomp < d.c0 || dcomp >= d.c0 + d.n_local) ) {
@@ -879,7 +896,7 @@ dispatch_kernel(Dev d)
                 rank_out = atomicAdd(&ht_cnt[ent_out], 1u);
             }
             else { // table full: reserve directly
-                emit(d, k, T + dt, s_dst[e], dcomp, s_seq[e], PAYLOAD ? s_pay[e] : 0);
+                emit(d, k, T + dt, s_dst[e], dcomp, s_sc[e].x, PAYLOAD ? s_pay[e] : 0);
             }
         };
 #pragma unroll
@@ -887,7 +904,7 @@ dispatch_kernel(Dev d)
             classify_out(tid + j * BLOCK, r_key[j], r_ent[j], r_rank[j]);
         for ( uint32_t e = tid + MAXR * BLOCK; e < n_due; e += BLOCK ) // beyond the register window: direct
             if ( s_dst[e] != SSTB200_NO_PEER )
-                emit(d, k, T + s_time[e], s_dst[e], s_cr[e], s_seq[e], PAYLOAD ? s_pay[e] : 0);
+                emit(d, k, T + s_time[e], s_dst[e], s_sc[e].y, s_sc[e].x, PAYLOAD ? s_pay[e] : 0);
         __syncthreads();
         if ( tid < HT && ht_key[tid] != 0xFFFFFFFFu && ht_cnt[tid] ) {
             const uint32_t ky = ht_key[tid];
@@ -905,7 +922,7 @@ dispatch_kernel(Dev d)
             const uint32_t ky  = r_key[j];
             const uint32_t pos = ht_base[r_ent[j]] + r_rank[j];
             const uint64_t tm  = T + s_time[e];
-            const uint64_t ds  = ((uint64_t)s_dst[e] << 32) | s_seq[e];
+            const uint64_t ds  = ((uint64_t)s_dst[e] << 32) | s_sc[e].x;
             if ( ky & 0x80000000u ) {
                 const uint32_t r = ky & 0x7FFFFFFFu;
                 if ( pos >= d.outbox_cap ) {
@@ -916,7 +933,7 @@ dispatch_kernel(Dev d)
                     rec[0]                  = tm;
                     rec[1]                  = ds;
                     rec[2]                  = PAYLOAD ? s_pay[e] : 0;
-                    rec[3]                  = s_cr[e];
+                    rec[3]                  = s_sc[e].y;
                 }
             }
             else if ( pos >= d.cap ) {
@@ -1456,6 +1473,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     if ( d.cap < BLOCK ) d.cap = BLOCK; // the dispatch prologue reads the first BLOCK slots of a bin unconditionally
     d.emax    = o->smem_events ? o->smem_events : 8 * BLOCK;
     if ( d.emax > 32768 ) d.emax = 32768;
+    d.emax = (d.emax + 3u) & ~3u;
     d.stats_on = m->stats_enabled;
 
     // lookahead window = minimum latency over every connected link (cut or not: a window is processed as one batch
