@@ -148,6 +148,10 @@ struct MeshElement
     // msg_count statistic) is a sum.  So the n events of a component run on n threads.
     static constexpr bool     PARALLEL_EVENTS          = true;
     static constexpr uint32_t PARALLEL_SENDS_PER_EVENT = 1;
+    // EnclosingComponent::handleEvent / RouteMessage::send look at neither the port an event came in on nor at its
+    // (empty) payload: events that are due at the same time are interchangeable, whatever order they are run in the
+    // component ends in the same state and sends the same events (enclosingComponent.cc:92-99,179-186)
+    static constexpr bool TIES_INTERCHANGEABLE = true;
     // may this component's n events of the window run in parallel?  Decided from the state in memory (16 bytes of
     // core + 16 of constants): MT19937 index even, run short enough (MT_STAGE_MAX_PAIRS), one link per port group
     // (so that the second draw only advances the generator)
@@ -302,6 +306,7 @@ struct PholdElement
         uint64_t              pad1;
     };
     static constexpr uint32_t STORE_END = 32, CONST_END = 48, STATS_END = 96;
+    static constexpr bool     TIES_INTERCHANGEABLE = false; // the delivery hash / handlers see port and order
     static constexpr bool     PARALLEL_EVENTS = false; // handlers chain through the state (hash, RNG): sequential
     static constexpr uint32_t SCRATCH_PER_EVENT = 0, SCRATCH_FIXED = 0;
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
@@ -374,6 +379,7 @@ struct ClockNodeElement
         Accumulator<int32_t> count[4];
     };
     static constexpr uint32_t STORE_END = 48, CONST_END = 64, STATS_END = 160;
+    static constexpr bool     TIES_INTERCHANGEABLE = false; // the delivery hash / handlers see port and order
     static constexpr bool     PARALLEL_EVENTS = false; // handlers chain through the state (hash, RNG): sequential
     static constexpr uint32_t SCRATCH_PER_EVENT = 0, SCRATCH_FIXED = 0;
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
@@ -444,6 +450,7 @@ struct RngElement
         uint64_t pad1;
     };
     static constexpr uint32_t STORE_END = 96, CONST_END = 96, STATS_END = 96;
+    static constexpr bool     TIES_INTERCHANGEABLE = false; // the delivery hash / handlers see port and order
     static constexpr bool     PARALLEL_EVENTS = false; // handlers chain through the state (hash, RNG): sequential
     static constexpr uint32_t SCRATCH_PER_EVENT = 0, SCRATCH_FIXED = 0;
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
@@ -545,6 +552,7 @@ struct ElementInfo
     int         has_payload;
     uint32_t    scratch_per_event, scratch_fixed; // shared-memory scratch words per due event / per component
     bool        parallel_events;                  // has an event-parallel handler
+    bool        ties_interchangeable;             // events of equal delivery time are interchangeable for the element
     const char* description;
 };
 

@@ -103,6 +103,7 @@ struct Dev
     uint32_t        uniform_type;         // the element type when every local component has the same one, else 0
     uint32_t        scr_per_event, scr_fixed; // shared-memory scratch words an element gets per due event / per component
     uint32_t        any_parallel;         // some local element type has an event-parallel handler
+    uint32_t        ties_free;            // every local element type declares events of equal time interchangeable
     uint32_t        P0, nport_local;
     uint32_t        rank, n_ranks;
     const uint32_t* rank_comp_begin; // [n_ranks+1] (device)
@@ -497,6 +498,8 @@ dispatch_kernel(Dev d)
             const uint32_t e  = (bin + 1) * BLOCK;
             s_port_off[BLOCK] = d.port_off[e <= d.n_local ? e : d.n_local];
             s_misc[0]         = 0;
+            s_misc[2]         = 0xFFFFFFFFu; // min / max time offset of the due events
+            s_misc[3]         = 0;
         }
         s_cnt[tid] = 0;
         s_hdr[tid] = make_uint4(0, 0, 0, 0);
@@ -523,7 +526,7 @@ dispatch_kernel(Dev d)
     __pipeline_commit();
 
     // ---- phase 1: load the bin; stage due events in shared memory, re-bin the ones that are not due yet
-    uint32_t       dropped  = 0;
+    uint32_t       dropped  = 0, t_lo = 0xFFFFFFFFu, t_hi = 0;
     const uint64_t bin_base = (uint64_t)(slot * d.nbins + bin) * d.cap;
     auto           classify = [&](uint64_t t, uint64_t ds, uint64_t pl) {
         const uint32_t dst = (uint32_t)(ds >> 32);
@@ -562,6 +565,8 @@ dispatch_kernel(Dev d)
             if ( e < d.emax ) {
                 const uint32_t r = atomicAdd(&s_cnt[lo], 1u);
                 s_time[e]        = (uint32_t)(t - T);
+                t_lo             = min(t_lo, (uint32_t)(t - T));
+                t_hi             = max(t_hi, (uint32_t)(t - T));
                 s_dst[e]         = dst;
                 s_sc[e]          = make_uint2((uint32_t)ds, (lo << 16) | (r & 0xFFFFu));
                 if ( PAYLOAD ) s_pay[e] = pl;
@@ -576,6 +581,10 @@ dispatch_kernel(Dev d)
         uint64_t         pl = 0;
         if ( PAYLOAD ) pl = d.ev_payload[bin_base + i];
         classify(ev.x, ev.y, pl);
+    }
+    if ( t_lo <= t_hi ) {
+        atomicMin(&s_misc[2], t_lo);
+        atomicMax(&s_misc[3], t_hi);
     }
     __pipeline_wait_prior(0);
     __syncthreads();
@@ -618,18 +627,37 @@ dispatch_kernel(Dev d)
     // (b) order inside each component's segment, (time, port, sequence): every EVENT counts the events of its segment
     //     that precede it -- balanced over the CTA's threads whatever the distribution of events over components
     //     (a per-component sort would make the block wait for its busiest component)
-    for ( uint32_t pos = tid; pos < n_due; pos += BLOCK ) {
-        const uint32_t e   = s_perm[pos];
-        const uint32_t cc  = s_pcomp[pos];
-        const uint32_t off = s_off[cc], cnt = s_cnt[cc];
-        const uint32_t te = s_time[e], de = s_dst[e], qe = s_sc[e].x;
-        uint32_t       rank = 0;
-        for ( uint32_t j = 0; j < cnt; ++j ) {
-            const uint32_t o = s_perm[off + j];
-            rank += key_less(s_time[o], s_dst[o], s_sc[o].x, te, de, qe) ? 1u : 0u;
+    // Elements that declare events of equal delivery time interchangeable (their handler looks at neither the port nor
+    // the payload, e.g. MessageMesh) need the order by time only; when the whole block has a single timestamp (every
+    // fixed-latency model) there is nothing to order at all.  With a delivery trace requested the full order is kept,
+    // so traces stay identical to the reference's.
+    const bool by_time_only = d.ties_free && d.trace_cap == 0;
+    const bool skip_order   = by_time_only && s_misc[2] == s_misc[3];
+    if ( !skip_order ) {
+        for ( uint32_t pos = tid; pos < n_due; pos += BLOCK ) {
+            const uint32_t e   = s_perm[pos];
+            const uint32_t cc  = s_pcomp[pos];
+            const uint32_t off = s_off[cc], cnt = s_cnt[cc];
+            uint32_t       rank = 0;
+            if ( by_time_only ) {
+                const uint32_t te = s_time[e];
+                for ( uint32_t j = 0; j < cnt; ++j ) {
+                    const uint32_t o  = s_perm[off + j];
+                    const uint32_t to = s_time[o];
+                    rank += (to < te || (to == te && o < e)) ? 1u : 0u;
+                }
+            }
+            else {
+                const uint32_t te = s_time[e], de = s_dst[e], qe = s_sc[e].x;
+                for ( uint32_t j = 0; j < cnt; ++j ) {
+                    const uint32_t o = s_perm[off + j];
+                    rank += key_less(s_time[o], s_dst[o], s_sc[o].x, te, de, qe) ? 1u : 0u;
+                }
+            }
+            s_sorted[off + rank] = (uint16_t)e;
         }
-        s_sorted[off + rank] = (uint16_t)e;
     }
+    const uint16_t* s_ordered = skip_order ? s_perm : s_sorted;
     // (c, second half) thread -> component assignment
     {
         const uint32_t cnt_c  = s_cnt[tid];
@@ -644,7 +672,7 @@ dispatch_kernel(Dev d)
     const uint32_t  lc     = bin * BLOCK + c;
     const bool      valid  = lc < d.n_local;
     const uint32_t  my_cnt = s_cnt[c];
-    uint16_t*       seg    = s_sorted + s_off[c];
+    const uint16_t* seg    = s_ordered + s_off[c];
     uint32_t        delivered = 0, ticks = 0, sent = 0, clocks_stopped = 0;
     uint4           c_lo = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0), c_hi = make_uint4(0, 0, 0, 0);
     if ( valid ) {
@@ -743,7 +771,7 @@ dispatch_kernel(Dev d)
         for ( int j = 0; j < PARB; ++j ) {
             const uint32_t p = tid + j * BLOCK;
             if ( p >= n_due ) continue;
-            const uint32_t e    = s_sorted[p];
+            const uint32_t e    = s_ordered[p];
             const uint32_t cc   = s_pcomp[p];
             const uint32_t kk   = p - s_off[cc];
             const uint32_t lcc  = bin * BLOCK + cc;
@@ -856,44 +884,55 @@ dispatch_kernel(Dev d)
         constexpr int MAXR = 6; // slots tid, tid+256, ... per thread in registers between the passes (1536 slots)
         uint32_t      r_key[MAXR], r_rank[MAXR], r_ent[MAXR];
         auto          classify_out = [&](uint32_t e, uint32_t& ky_out, uint32_t& ent_out, uint32_t& rank_out) {
-            ent_out = 0xFFFFFFFFu;
-            if ( e >= n_due || s_dst[e] == SSTB200_NO_PEER ) return;
-            const uint32_t dcomp = s_sc[e].y;
-            const uint32_t dt    = s_time[e];
-            uint32_t       ky;
-            if ( d.n_ranks > 1 && (dcomp < d.c0 || dcomp >= d.c0 + d.n_local) ) {
-                uint32_t r = 0;
-                while ( r + 1 < d.n_ranks && dcomp >= d.rank_comp_begin[r + 1] )
-                    ++r;
-                ky = 0x80000000u | r;
-            }
-            else if ( dt < w ) {
-                raise_error(d, ERR_TIME_FAULT, T + dt, T, dcomp); // a send violated the lookahead
-                return;
-            }
-            else {
-                uint32_t sl = slot1;
-                if ( dt >= 2 * w ) {
-                    uint32_t dk = dt / w;
-                    if ( dk > d.W - 1 ) dk = d.W - 1; // beyond the horizon: parked in the farthest slot
-                    sl = (uint32_t)((slot + dk) % d.W);
+            // called by all 32 lanes of a warp together (lanes without a record carry the key 0xFFFFFFFF)
+            ent_out      = 0xFFFFFFFFu;
+            uint32_t ky  = 0xFFFFFFFFu, dt = 0, dcomp = 0;
+            if ( e < n_due && s_dst[e] != SSTB200_NO_PEER ) {
+                dcomp = s_sc[e].y;
+                dt    = s_time[e];
+                if ( d.n_ranks > 1 && (dcomp < d.c0 || dcomp >= d.c0 + d.n_local) ) {
+                    uint32_t r = 0;
+                    while ( r + 1 < d.n_ranks && dcomp >= d.rank_comp_begin[r + 1] )
+                        ++r;
+                    ky = 0x80000000u | r;
                 }
-                ky = sl * d.nbins + (dcomp - d.c0) / BLOCK;
+                else if ( dt < w ) {
+                    raise_error(d, ERR_TIME_FAULT, T + dt, T, dcomp); // a send violated the lookahead
+                }
+                else {
+                    uint32_t sl = slot1;
+                    if ( dt >= 2 * w ) {
+                        uint32_t dk = dt / w;
+                        if ( dk > d.W - 1 ) dk = d.W - 1; // beyond the horizon: parked in the farthest slot
+                        sl = (uint32_t)((slot + dk) % d.W);
+                    }
+                    ky = sl * d.nbins + (dcomp - d.c0) / BLOCK;
+                }
             }
-            // find / claim the table entry of this bin (open addressing, 4 probes)
-            uint32_t h = (ky * 2654435761u) >> 26;
+            // lanes of the warp with the same bin go through the table as ONE entry look-up + ONE counter update
+            const uint32_t peers  = __match_any_sync(0xffffffffu, ky);
+            const uint32_t leader = __ffs(peers) - 1;
+            uint32_t       ent = 0xFFFFFFFFu, base = 0;
+            if ( ky != 0xFFFFFFFFu && lane == leader ) {
+                uint32_t h = (ky * 2654435761u) >> 26;
 #pragma unroll
-            for ( int pr = 0; pr < 4; ++pr ) {
-                const uint32_t old = atomicCAS(&ht_key[h], 0xFFFFFFFFu, ky);
-                if ( old == 0xFFFFFFFFu || old == ky ) {
-                    ent_out = h;
-                    break;
+                for ( int pr = 0; pr < 4; ++pr ) { // open addressing, 4 probes
+                    const uint32_t old = atomicCAS(&ht_key[h], 0xFFFFFFFFu, ky);
+                    if ( old == 0xFFFFFFFFu || old == ky ) {
+                        ent = h;
+                        break;
+                    }
+                    h = (h + 1) & (HT - 1);
                 }
-                h = (h + 1) & (HT - 1);
+                if ( ent != 0xFFFFFFFFu ) base = atomicAdd(&ht_cnt[ent], (uint32_t)__popc(peers));
             }
-            if ( ent_out != 0xFFFFFFFFu ) {
+            ent  = __shfl_sync(0xffffffffu, ent, leader);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if ( ky == 0xFFFFFFFFu ) return;
+            if ( ent != 0xFFFFFFFFu ) {
                 ky_out   = ky;
-                rank_out = atomicAdd(&ht_cnt[ent_out], 1u);
+                ent_out  = ent;
+                rank_out = base + __popc(peers & ((1u << lane) - 1));
             }
             else { // table full: reserve directly
                 emit(d, k, T + dt, s_dst[e], dcomp, s_sc[e].x, PAYLOAD ? s_pay[e] : 0);
@@ -1252,13 +1291,13 @@ rng_dist_kernel(int dist, const double* params, int np, int kind, uint64_t s1, u
 // ================================================================================================ host side
 static const ElementInfo kElements[] = {
     { TYPE_MESH, MeshElement::ELI_NAME, MeshElement::PERSIST_BYTES, MeshElement::AUX_BYTES,
-        MeshElement::HAS_PAYLOAD, MeshElement::SCRATCH_PER_EVENT, MeshElement::SCRATCH_FIXED, MeshElement::PARALLEL_EVENTS, "message_mesh enclosing component with message_port/port_slot/route_message" },
+        MeshElement::HAS_PAYLOAD, MeshElement::SCRATCH_PER_EVENT, MeshElement::SCRATCH_FIXED, MeshElement::PARALLEL_EVENTS, MeshElement::TIES_INTERCHANGEABLE, "message_mesh enclosing component with message_port/port_slot/route_message" },
     { TYPE_PHOLD, PholdElement::ELI_NAME, PholdElement::PERSIST_BYTES, PholdElement::AUX_BYTES,
-        PholdElement::HAS_PAYLOAD, PholdElement::SCRATCH_PER_EVENT, PholdElement::SCRATCH_FIXED, PholdElement::PARALLEL_EVENTS, "PHOLD-style node, integer delays, 8-byte payload" },
+        PholdElement::HAS_PAYLOAD, PholdElement::SCRATCH_PER_EVENT, PholdElement::SCRATCH_FIXED, PholdElement::PARALLEL_EVENTS, PholdElement::TIES_INTERCHANGEABLE, "PHOLD-style node, integer delays, 8-byte payload" },
     { TYPE_CLOCKNODE, ClockNodeElement::ELI_NAME, ClockNodeElement::PERSIST_BYTES,
-        ClockNodeElement::AUX_BYTES, ClockNodeElement::HAS_PAYLOAD, ClockNodeElement::SCRATCH_PER_EVENT, ClockNodeElement::SCRATCH_FIXED, ClockNodeElement::PARALLEL_EVENTS, "clock-driven node (coreTestComponent style)" },
+        ClockNodeElement::AUX_BYTES, ClockNodeElement::HAS_PAYLOAD, ClockNodeElement::SCRATCH_PER_EVENT, ClockNodeElement::SCRATCH_FIXED, ClockNodeElement::PARALLEL_EVENTS, ClockNodeElement::TIES_INTERCHANGEABLE, "clock-driven node (coreTestComponent style)" },
     { TYPE_RNGCOMP, RngElement::ELI_NAME, RngElement::PERSIST_BYTES, RngElement::AUX_BYTES,
-        RngElement::HAS_PAYLOAD, RngElement::SCRATCH_PER_EVENT, RngElement::SCRATCH_FIXED, RngElement::PARALLEL_EVENTS, "coreTestRNGComponent: 1 GHz clock drawing from an SST::RNG generator" },
+        RngElement::HAS_PAYLOAD, RngElement::SCRATCH_PER_EVENT, RngElement::SCRATCH_FIXED, RngElement::PARALLEL_EVENTS, RngElement::TIES_INTERCHANGEABLE, "coreTestRNGComponent: 1 GHz clock drawing from an SST::RNG generator" },
 };
 constexpr int kNumElements = (int)(sizeof(kElements) / sizeof(kElements[0]));
 
@@ -1545,11 +1584,13 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         d.uniform_type = ut;
         d.scr_per_event = d.scr_fixed = 0;
         d.any_parallel  = 0;
+        d.ties_free     = 1;
         for ( uint32_t c = c0; c < c1; ++c ) {
             const ElementInfo* ei = element_by_type(m->comp_type[c]);
             d.scr_per_event       = std::max(d.scr_per_event, ei->scratch_per_event);
             d.scr_fixed           = std::max(d.scr_fixed, ei->scratch_fixed);
             if ( ei->parallel_events ) d.any_parallel = 1;
+            if ( !ei->ties_interchangeable ) d.ties_free = 0;
             if ( ut ) break; // uniform: the first one says it all
         }
     }
