@@ -1,5 +1,4 @@
 #!/bin/bash
-# build variants on the GPU box and time mesh 4096^2 / PHOLD 1024^2 (kernel only)
 run() { python - <<PY
 import json,subprocess,sys
 for wl,extra in (("mesh",[]),("phold",["--x","1024","--y","1024","--warmup","10"])):
@@ -10,19 +9,8 @@ for wl,extra in (("mesh",[]),("phold",["--x","1024","--y","1024","--warmup","10"
         print("FAILED",out.stdout[-300:],out.stderr[-600:])
 PY
 }
-for v in "-DSSTB200_SPEC=1" "-DSSTB200_SPEC=2" "-DSSTB200_SPEC=4"; do
+for v in "-DSSTB200_FLUSH_NOMATCH" "-DSSTB200_SPEC=4"; do
   SSTB200_NVCC_EXTRA="$v" python -m sst_core_b200.build --force > gpurun_out/build_v.log 2>&1; grep -A2 "dispatch_kernelILb0" gpurun_out/build_v.log | grep -E "spill" 
   run "$v"
 done
 python -m sst_core_b200.build --force > /dev/null 2>&1
-python - <<'PY'
-import time, sys
-sys.path.insert(0, '.')
-from sst_core_b200 import models
-from sst_core_b200.run import simulate_model
-m = models.mesh_model(6, 6)
-simulate_model(m)
-for i in range(3):
-    t0 = time.perf_counter(); res, st = simulate_model(m); dt = time.perf_counter() - t0
-    print(f"mesh 6x6 10us end-to-end {dt*1e3:.1f} ms")
-PY

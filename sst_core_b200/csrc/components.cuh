@@ -152,25 +152,12 @@ struct MeshElement
     // (empty) payload: events that are due at the same time are interchangeable, whatever order they are run in the
     // component ends in the same state and sends the same events (enclosingComponent.cc:92-99,179-186)
     static constexpr bool TIES_INTERCHANGEABLE = true;
-    // may this component's n events of the window run in parallel?  Decided from the state in memory (16 bytes of
-    // core + 16 of constants): MT19937 index even, run short enough (MT_STAGE_MAX_PAIRS), one link per port group
-    // (so that the second draw only advances the generator)
-    __device__ static bool parallelOK(const uint8_t* state, uint32_t n)
-    {
-        const uint4    core = __ldg(reinterpret_cast<const uint4*>(state));
-        const uint4    cst  = __ldg(reinterpret_cast<const uint4*>(state + 16));
-        const uint64_t counts = ((uint64_t)cst.w << 32) | cst.z;
-        return (core.y & 1u) == 0 && n <= MT_STAGE_MAX_PAIRS && cst.x >= 1 && cst.x <= 8 &&
-               counts == (0x0101010101010101ull >> (8 * (8 - cst.x)));
-    }
-    // header word the event threads get: MT19937 index at the start of the window | number of port groups << 16
-    __device__ static uint32_t parallelHeader(const State& s) { return s.mt_idx | (s.ngroups << 16); }
     // 3a, component thread: asynchronous copies (LDGSTS) of the a-run: chunk j = (mt[i+2j], mt[i+2j+1]) to
     // staged[j] (delivery position j of this component), and mt[i+2n] (the last pair's third word) to *extra
-    __device__ static void stageParallel(const uint8_t* aux, const State& s, uint32_t n, uint2* staged, uint32_t* extra)
+    __device__ static void stageParallel(const uint8_t* aux, uint32_t hdr, uint32_t n, uint2* staged, uint32_t* extra)
     {
         const uint32_t* mt = (const uint32_t*)aux;
-        const uint32_t  i  = s.mt_idx;
+        const uint32_t  i  = hdr & 0xFFFFu;
         for ( uint32_t j = 0; j < n; ++j )
             __pipeline_memcpy_async(staged + j, mt + mt_wrap(mt_wrap(i + 2 * j)), 8);
         __pipeline_memcpy_async(extra, mt + mt_wrap(mt_wrap(i + 2 * n)), 4);
@@ -215,17 +202,25 @@ struct MeshElement
     {
         ctx.send((int)out_port, 0, payload);
     }
-    // dispatch prologue hook: pull towards L2 the MT19937 words the next handful of draws will read
-    // (words idx.. and idx+397.. mod 624), so that the per-event draws hit L2 instead of paying an HBM round trip each
-    __device__ static void prefetch(const uint8_t* state, const uint8_t* aux)
+    // dispatch prologue hook: pull towards L2 the MT19937 words the next handful of draws will read (words idx.. and
+    // idx+397.. mod 624), and probe whether this component's events of the window may run in the event-parallel form:
+    // MT19937 index even (pairs stay 8-byte aligned), one link per port group (the second draw only advances the
+    // generator).  Returns the header word the event threads get -- index | port groups << 16 -- or 0xFFFFFFFF.
+    __device__ static uint32_t prefetch(const uint8_t* state, const uint8_t* aux)
     {
-        const uint32_t  idx = reinterpret_cast<const State*>(state)->mt_idx;
-        const uint32_t  im  = (idx + MT_M >= MT_N) ? idx + MT_M - MT_N : idx + MT_M;
-        const uint32_t* mt  = reinterpret_cast<const uint32_t*>(aux);
+        const uint4     core = __ldg(reinterpret_cast<const uint4*>(state));      // message_count, mt_idx
+        const uint4     cst  = __ldg(reinterpret_cast<const uint4*>(state + 16)); // ngroups, mod, counts
+        const uint32_t  idx  = core.y;
+        const uint32_t  im   = (idx + MT_M >= MT_N) ? idx + MT_M - MT_N : idx + MT_M;
+        const uint32_t* mt   = reinterpret_cast<const uint32_t*>(aux);
         prefetch_l2(mt + idx);
         prefetch_l2(mt + (idx + 16 >= MT_N ? idx + 16 - MT_N : idx + 16));
         prefetch_l2(mt + im);
         prefetch_l2(mt + (im + 16 >= MT_N ? im + 16 - MT_N : im + 16));
+        const uint64_t counts = ((uint64_t)cst.w << 32) | cst.z;
+        const bool     ok     = (idx & 1u) == 0 && cst.x >= 1 && cst.x <= 8 &&
+                        counts == (0x0101010101010101ull >> (8 * (8 - cst.x)));
+        return ok ? (idx | (cst.x << 16)) : 0xFFFFFFFFu;
     }
     template <class Ctx>
     __device__ static void construct(Ctx& ctx, State& s, const int64_t* p)
@@ -313,7 +308,11 @@ struct PholdElement
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
     {}
-    __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
+    __device__ static uint32_t prefetch(const uint8_t* state, const uint8_t*)
+    {
+        prefetch_l2(state);
+        return 0xFFFFFFFFu;
+    }
     template <class Ctx>
     __device__ static void construct(Ctx&, State& s, const int64_t* p)
     {
@@ -386,7 +385,11 @@ struct ClockNodeElement
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
     {}
-    __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
+    __device__ static uint32_t prefetch(const uint8_t* state, const uint8_t*)
+    {
+        prefetch_l2(state);
+        return 0xFFFFFFFFu;
+    }
     template <class Ctx>
     __device__ static void construct(Ctx&, State& s, const int64_t* p)
     {
@@ -457,7 +460,11 @@ struct RngElement
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
     {}
-    __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
+    __device__ static uint32_t prefetch(const uint8_t* state, const uint8_t*)
+    {
+        prefetch_l2(state);
+        return 0xFFFFFFFFu;
+    }
     template <class Ctx>
     __device__ static void construct(Ctx& ctx, State& s, const int64_t* p)
     {

@@ -58,6 +58,7 @@ set_error(const std::string& s)
 constexpr int      BLOCK      = SSTB200_BLOCK; // components per CTA == threads per CTA
 constexpr uint64_t TIME_NEVER = ~0ull;
 constexpr int      PARB       = 6; // event-parallel phase: positions t, t+256, ... t+5*256 per thread
+constexpr uint32_t PAR_MAX_EVENTS = 100; // events of one component per window in the event-parallel form (<= MT_STAGE_MAX_PAIRS)
 
 enum : uint32_t { ERR_BIN_OVERFLOW = 1, ERR_SMEM_OVERFLOW = 2, ERR_TIME_FAULT = 3, ERR_OUTBOX_OVERFLOW = 4, ERR_TRACE_OVERFLOW = 5 };
 enum { CW_PENDING = 0, CW_PRIMARY = 1, CW_CLOCKS = 2, CW_ERROR = 3, CW_EXIT_TIME = 4, CW_WORDS = 8 };
@@ -392,6 +393,26 @@ gtimer()
 #define PHASE_MARK(i)
 #endif
 
+// (time, port, sequence) order of one component's segment: insertion sort by the owning thread.  Used when no local
+// element has an event-parallel form (the lanes of a warp own components with nearly equal event counts, and the sort
+// overlaps the element's first loads); otherwise the block orders its events with the event-parallel rank sort.
+__device__ __forceinline__ void
+sort_segment(uint16_t* seg, uint32_t cnt, const uint32_t* s_time, const uint32_t* s_dst, const uint2* s_sc)
+{
+    for ( uint32_t a = 1; a < cnt; ++a ) {
+        const uint16_t ea = seg[a];
+        const uint32_t ta = s_time[ea], da = s_dst[ea], qa = s_sc[ea].x;
+        uint32_t       b  = a;
+        while ( b > 0 ) {
+            const uint16_t eb = seg[b - 1];
+            if ( !key_less(ta, da, qa, s_time[eb], s_dst[eb], s_sc[eb].x) ) break;
+            seg[b] = eb;
+            --b;
+        }
+        seg[b] = ea;
+    }
+}
+
 // Context of an EVENT-PARALLEL handler (elements with PARALLEL_EVENTS): the handler of the k-th event (in delivery
 // order) of a component runs on its own thread, concurrently with the handlers of the component's other events of the
 // window.  It sees the component's state as it was at the start of the window (read-only), sends exactly
@@ -430,7 +451,7 @@ struct ParCtx
 };
 
 // ---- one lookahead window for one block of 256 components
-template <bool PAYLOAD>
+template <bool PAYLOAD, bool PARFORM>
 #ifndef SSTB200_MIN_BLOCKS
 #define SSTB200_MIN_BLOCKS 4
 #endif
@@ -502,16 +523,25 @@ dispatch_kernel(Dev d)
             s_misc[3]         = 0;
         }
         s_cnt[tid] = 0;
-        s_hdr[tid] = make_uint4(0, 0, 0, 0);
         if ( tid < 32 ) s_hist[tid] = 0;
+        // per-component window header, filled here from memory so that phase 3 starts without a memory round trip:
+        //   .x  element word for the event-parallel form (MT19937 index ...), 0xFFFFFFFF = cannot run in parallel
+        //   .y  send sequence at the start of the window      .z  deliveries so far (trace index)
+        //   .w  bit 0: a clock tick is due in this window; later: extra staged word of the element
+        uint4 hdr = make_uint4(0xFFFFFFFFu, 0, 0, 0);
         if ( lc0 < d.n_local ) {
-            // element hook: start pulling the state line and the aux words the handlers will touch towards L2
+            const uint4 c_lo0 = *reinterpret_cast<const uint4*>(&d.ctl[lc0]); // next_tick, send_seq, deliv_seq
+            // element hook: probe the state for the event-parallel form and start pulling the aux words the
+            // handlers will touch towards L2
             with_element(d.uniform_type ? d.uniform_type : d.comp_type[lc0], [&](auto el) {
                 using E = decltype(el);
-                E::prefetch(d.state + (uint64_t)lc0 * d.state_stride, d.aux + (uint64_t)lc0 * d.aux_stride);
+                hdr.x = E::prefetch(d.state + (uint64_t)lc0 * d.state_stride, d.aux + (uint64_t)lc0 * d.aux_stride);
             });
-            prefetch_l2(&d.ctl[lc0]);
+            hdr.y = c_lo0.z;
+            hdr.z = c_lo0.w;
+            hdr.w = ((((uint64_t)c_lo0.y << 32) | c_lo0.x) < T_end) ? 1u : 0u;
         }
+        s_hdr[tid] = hdr;
     }
     __syncthreads();
     PHASE_MARK(1);
@@ -632,7 +662,8 @@ dispatch_kernel(Dev d)
     // fixed-latency model) there is nothing to order at all.  With a delivery trace requested the full order is kept,
     // so traces stay identical to the reference's.
     const bool by_time_only = d.ties_free && d.trace_cap == 0;
-    const bool skip_order   = by_time_only && s_misc[2] == s_misc[3];
+    const bool owner_sorts  = !PARFORM; // sequential elements only: each owner thread sorts its own segment
+    const bool skip_order   = owner_sorts || (by_time_only && s_misc[2] == s_misc[3]);
     if ( !skip_order ) {
         for ( uint32_t pos = tid; pos < n_due; pos += BLOCK ) {
             const uint32_t e   = s_perm[pos];
@@ -697,45 +728,34 @@ dispatch_kernel(Dev d)
     //       write-back, block barrier, then the sends into the events' own slots.
     // Perfectly balanced however the events are spread over components; no sequential chain; a block's registers and
     // shared memory are no longer held for its busiest component.
-    bool par_ok = !has_work; // components with nothing to do do not object
-    if ( has_work && d.any_parallel && n_due <= PARB * BLOCK && my_cnt > 0 && !(next_tick < T_end) ) {
-        with_element(my_type, [&](auto el) {
-            using E = decltype(el);
-            if constexpr ( E::PARALLEL_EVENTS )
-                par_ok = E::parallelOK(d.state + (uint64_t)lc * d.state_stride, my_cnt);
-        });
+    // The decision uses the headers the prologue read from memory (component tid, natural order).
+    bool par_ok = true;
+    {
+        const uint32_t cn = s_cnt[tid];
+        const uint4    h  = s_hdr[tid];
+        if ( bin * BLOCK + tid < d.n_local && (cn > 0 || (h.w & 1u)) )
+            par_ok = d.any_parallel && cn > 0 && !(h.w & 1u) && h.x != 0xFFFFFFFFu && cn <= PAR_MAX_EVENTS &&
+                     n_due <= PARB * BLOCK;
     }
-    const bool block_par = d.any_parallel && __syncthreads_and(par_ok ? 1 : 0);
-    if ( block_par ) {
-        if ( has_work ) {
-            with_element(my_type, [&](auto el) {
+    bool block_par = false;
+    if constexpr ( PARFORM ) block_par = __syncthreads_and(par_ok ? 1 : 0) != 0;
+    if ( PARFORM && block_par ) {
+        // all three memory round trips of the phase are issued now and overlap:
+        // (1) component thread tid: asynchronous staging of the aux words its events read
+        const uint32_t pc_  = tid; // natural order: the work per component is uniform here
+        const uint32_t plc  = bin * BLOCK + pc_;
+        const uint32_t pcnt = s_cnt[pc_];
+        const uint32_t ptyp = d.uniform_type ? d.uniform_type : (plc < d.n_local ? d.comp_type[plc] : 0);
+        if ( pcnt ) {
+            with_element(ptyp, [&](auto el) {
                 using E = decltype(el);
-                if constexpr ( E::PARALLEL_EVENTS ) {
-                    typename E::State st_;
-                    load_state(st_, d.state + (uint64_t)lc * d.state_stride, 0, d.stats_on ? E::STATS_END : E::CONST_END);
-                    uint4 hdr = make_uint4(E::parallelHeader(st_), c_lo.z, c_lo.w, 0);
-                    // stage: position-indexed chunk array (n entries) + one extra word (header .w)
-                    E::stageParallel(d.aux + (uint64_t)lc * d.aux_stride, st_, my_cnt, s_sc + s_off[c], &s_hdr[c].w);
-                    s_hdr[c].x = hdr.x;
-                    s_hdr[c].y = hdr.y;
-                    s_hdr[c].z = hdr.z;
-                    E::finishWindowParallel(st_, my_cnt, d.stats_on != 0);
-                    store_state(st_, d.state + (uint64_t)lc * d.state_stride, 0, E::STORE_END);
-                    if ( d.stats_on )
-                        store_state(st_, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
-                    const uint32_t nsend = my_cnt * E::PARALLEL_SENDS_PER_EVENT;
-                    *reinterpret_cast<uint4*>(&d.ctl[lc]) =
-                        make_uint4(c_lo.x, c_lo.y, c_lo.z + nsend, c_lo.w + (d.trace_cap ? my_cnt : 0));
-                    delivered = my_cnt;
-                    sent      = nsend;
-                }
+                if constexpr ( E::PARALLEL_EVENTS )
+                    E::stageParallel(d.aux + (uint64_t)plc * d.aux_stride, s_hdr[pc_].x, pcnt, s_sc + s_off[pc_],
+                        &s_hdr[pc_].w);
             });
         }
         __pipeline_commit();
-        __pipeline_wait_prior(0); // this thread's staged copies have landed ...
-        __syncthreads();          // ... and everybody else's
-        PHASE_MARK(6);
-        // 3b.1: the global words each event needs, all loads issued before any is used
+        // (2) event threads: the global words each event needs
         uint2    gw[PARB];
         uint32_t tok[PARB];
 #pragma unroll
@@ -750,6 +770,29 @@ dispatch_kernel(Dev d)
                     gw[j] = E::parallelLoad(d.aux + (uint64_t)(bin * BLOCK + cc) * d.aux_stride, s_hdr[cc].x, p - s_off[cc]);
             });
         }
+        // (3) component thread: the state update for all its events at once (nothing in 3b depends on it)
+        if ( pcnt ) {
+            with_element(ptyp, [&](auto el) {
+                using E = decltype(el);
+                if constexpr ( E::PARALLEL_EVENTS ) {
+                    typename E::State st_;
+                    load_state(st_, d.state + (uint64_t)plc * d.state_stride, 0, d.stats_on ? E::STATS_END : E::CONST_END);
+                    E::finishWindowParallel(st_, pcnt, d.stats_on != 0);
+                    store_state(st_, d.state + (uint64_t)plc * d.state_stride, 0, E::STORE_END);
+                    if ( d.stats_on )
+                        store_state(st_, d.state + (uint64_t)plc * d.state_stride, E::CONST_END, E::STATS_END);
+                    const uint32_t nsend = pcnt * E::PARALLEL_SENDS_PER_EVENT;
+                    uint32_t*      ctlw  = reinterpret_cast<uint32_t*>(&d.ctl[plc]);
+                    const uint4    h     = s_hdr[pc_];
+                    *reinterpret_cast<uint2*>(ctlw + 2) = make_uint2(h.y + nsend, h.z + (d.trace_cap ? pcnt : 0));
+                    delivered = pcnt;
+                    sent      = nsend;
+                }
+            });
+        }
+        __pipeline_wait_prior(0); // this thread's staged copies have landed ...
+        __syncthreads();          // ... and everybody else's
+        PHASE_MARK(6);
         // 3b.2: compute; the handler writes its new aux words and returns what its send step needs
 #pragma unroll
         for ( int j = 0; j < PARB; ++j ) {
@@ -817,6 +860,7 @@ dispatch_kernel(Dev d)
             typename E::State s;
             load_state(s, d.state + (uint64_t)lc * d.state_stride, 0, d.stats_on ? E::STATS_END : E::CONST_END);
             E::beginWindow(ctx, s, my_cnt); // issues the element's first loads (MT19937 read-ahead)
+            if ( owner_sorts ) sort_segment(s_perm + s_off[c], my_cnt, s_time, s_dst, s_sc);
             uint64_t cycle = (next_tick != TIME_NEVER && period) ? next_tick / period : 0;
             uint32_t i     = 0;
             for ( ;; ) {
@@ -872,7 +916,7 @@ dispatch_kernel(Dev d)
     // written side by side.  Records that find no table entry (more than HT distinct bins per CTA: irregular graphs)
     // reserve their slot directly.
     {
-        constexpr uint32_t HT = 64;
+        constexpr uint32_t HT = 128;
         uint32_t* ht_key  = s_cnt;      // [HT] phase-2 scratch is dead by now
         uint32_t* ht_cnt  = s_cnt + HT; // [HT]
         uint32_t* ht_base = s_off;      // [HT] (low 32 bits of the reserved base)
@@ -910,14 +954,19 @@ dispatch_kernel(Dev d)
                 }
             }
             // lanes of the warp with the same bin go through the table as ONE entry look-up + ONE counter update
-            const uint32_t peers  = __match_any_sync(0xffffffffu, ky);
+#ifdef SSTB200_FLUSH_MATCH
+            const uint32_t peers  = __match_any_sync(0xffffffffu, ky); // lanes with the same bin share one look-up
+#else
+            const uint32_t peers  = 1u << lane; // every record looks its bin up itself (measured: same speed, less code)
+#endif
             const uint32_t leader = __ffs(peers) - 1;
             uint32_t       ent = 0xFFFFFFFFu, base = 0;
             if ( ky != 0xFFFFFFFFu && lane == leader ) {
-                uint32_t h = (ky * 2654435761u) >> 26;
+                uint32_t h = (ky * 2654435761u) >> 25;
 #pragma unroll
                 for ( int pr = 0; pr < 4; ++pr ) { // open addressing, 4 probes
-                    const uint32_t old = atomicCAS(&ht_key[h], 0xFFFFFFFFu, ky);
+                    uint32_t old = ht_key[h]; // usually already claimed for this bin: no atomic needed
+                    if ( old != ky ) old = atomicCAS(&ht_key[h], 0xFFFFFFFFu, ky);
                     if ( old == 0xFFFFFFFFu || old == ky ) {
                         ent = h;
                         break;
@@ -1356,9 +1405,9 @@ struct sstb200_engine
     int launch_dispatch()
     {
         if ( d.has_payload )
-            dispatch_kernel<true><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
+            (d.any_parallel ? dispatch_kernel<true, true> : dispatch_kernel<true, false>)<<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
         else
-            dispatch_kernel<false><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
+            (d.any_parallel ? dispatch_kernel<false, true> : dispatch_kernel<false, false>)<<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
         launches++;
         CUDA_OK(cudaGetLastError());
         return 0;
@@ -1668,8 +1717,10 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         sstb200_engine_destroy(e);
         return -1;
     }
-    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaStreamSynchronize(e->stream));
     *out = e;
     return 0;
