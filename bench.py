@@ -183,7 +183,7 @@ def build_model(a, windows):
     stop_ns = windows + 2
     if a.workload == "mesh":
         m = models.mesh_model(x, y, stop_at=f"{stop_ns}ns", verbose=0, stats_enabled=bool(a.stats))
-        opts = dict(calendar_slots=2, bin_capacity=2048, smem_events=1536, outbox_capacity=16384)
+        opts = dict(calendar_slots=2, bin_capacity=2048, smem_events=1280, outbox_capacity=16384)
         name = f"MessageMesh {x}x{y} torus, 1 ns links, MersenneRNG(id+100) per component, msg_count statistic {'on' if a.stats else 'off'}"
     elif a.workload == "clockpop":
         m = models.clockpop_model(x, y, stop_at=f"{stop_ns}ns", verbose=0, stats_enabled=True)

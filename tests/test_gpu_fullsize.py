@@ -26,7 +26,7 @@ def test_mesh_4096x4096_conservation():
     # after the first delivers exactly 4N events; counts and the msg_count statistic must add up to that
     n = 4096 * 4096
     m = models.mesh_model(4096, 4096, stop_at="1us", verbose=0, stats_enabled=True)
-    res, st = _run(m, 5, calendar_slots=2, bin_capacity=2048, smem_events=1536)
+    res, st = _run(m, 5, calendar_slots=2, bin_capacity=2048, smem_events=1280)
     assert st.windows == 5 and st.events_delivered == 4 * 4 * n  # windows 1..4 deliver, window 0 has nothing due
     assert int(res[:, 0].sum()) == st.events_delivered
     assert int(res[:, 1].sum()) == st.events_delivered and int(res[:, 3].sum()) == st.events_delivered
