@@ -89,6 +89,10 @@ mixDelivery(uint64_t h, uint64_t time, uint64_t port, uint64_t payload)
     return h;
 }
 
+#ifndef SSTB200_MESH_PREFETCH
+#define SSTB200_MESH_PREFETCH 2
+#endif
+
 #if defined(__CUDACC__)
 
 // what an event-parallel handler wants written to its component's aux block: applied by the engine after every
@@ -213,10 +217,14 @@ struct MeshElement
         const uint32_t  idx  = core.y;
         const uint32_t  im   = (idx + MT_M >= MT_N) ? idx + MT_M - MT_N : idx + MT_M;
         const uint32_t* mt   = reinterpret_cast<const uint32_t*>(aux);
+#if SSTB200_MESH_PREFETCH >= 1
         prefetch_l2(mt + idx);
-        prefetch_l2(mt + (idx + 16 >= MT_N ? idx + 16 - MT_N : idx + 16));
         prefetch_l2(mt + im);
+#endif
+#if SSTB200_MESH_PREFETCH >= 2
+        prefetch_l2(mt + (idx + 16 >= MT_N ? idx + 16 - MT_N : idx + 16));
         prefetch_l2(mt + (im + 16 >= MT_N ? im + 16 - MT_N : im + 16));
+#endif
         const uint64_t counts = ((uint64_t)cst.w << 32) | cst.z;
         const bool     ok     = (idx & 1u) == 0 && cst.x >= 1 && cst.x <= 8 &&
                         counts == (0x0101010101010101ull >> (8 * (8 - cst.x)));
