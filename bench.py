@@ -234,6 +234,12 @@ def ours(a):
 
     # ---- e2e: host arrays -> engine -> W+K windows -> results on host, wall clock, everything inside
     e2e = None
+    if dist:
+        # NCCL sets up its point-to-point channels lazily on the first all-to-all: do that before anything is timed
+        # (the kernel-timed region below has its own warm-up windows)
+        wu = torch.zeros(world * 8, dtype=torch.int64, device=dev)
+        dist.all_to_all_single(torch.empty_like(wu), wu)
+        torch.cuda.synchronize(dev)
     if not a.no_e2e:
         if dist:
             dist.barrier()

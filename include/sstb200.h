@@ -76,6 +76,8 @@ typedef struct sstb200_options {
     uint64_t window;          /* lookahead window in cycles; 0 = min link latency (configGraph.cc:711-730)    */
     uint64_t trace_capacity;  /* delivery trace records to keep (0 = tracing off)                             */
     void*    stream;          /* cudaStream_t to run on (NULL = engine-owned stream)                          */
+    uint32_t parallel_max_events; /* event-parallel form: most events of one component per window (0 = default 100;
+                                 blocks with a busier component run the sequential form; lower it to test that) */
 } sstb200_options;
 
 int  sstb200_engine_create(const sstb200_model* model, const sstb200_options* opt, sstb200_engine** out);

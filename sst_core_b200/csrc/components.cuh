@@ -95,14 +95,6 @@ mixDelivery(uint64_t h, uint64_t time, uint64_t port, uint64_t payload)
 
 #if defined(__CUDACC__)
 
-// what an event-parallel handler wants written to its component's aux block: applied by the engine after every
-// parallel handler of the block has done its reads
-struct DeferredWrite
-{
-    uint32_t word; // word offset into the aux block (8-byte aligned), 0xFFFFFFFF = none
-    uint32_t v0, v1;
-};
-
 __device__ __forceinline__ void
 prefetch_l2(const void* p)
 {
@@ -136,9 +128,6 @@ struct MeshElement
         MtPairCache cache; // read-ahead of the MT19937 words the next two pairs need
     };
     static constexpr uint32_t STORE_END = 16, CONST_END = 32, STATS_END = 80, PERSIST_BYTES = 80;
-    // shared-memory scratch: the MT19937 words this window's draws will read, 4 per event (+3 per component)
-    // no extra shared-memory scratch: the event-parallel path stages what it needs in arrays the sort has freed
-    static constexpr uint32_t SCRATCH_PER_EVENT = 0, SCRATCH_FIXED = 0;
     // sequential path: issue the read-ahead loads now, they fly while the engine does the rest of its set-up
     template <class Ctx>
     __device__ static void beginWindow(Ctx& ctx, State& s, uint32_t n_events)
@@ -311,7 +300,6 @@ struct PholdElement
     static constexpr uint32_t STORE_END = 32, CONST_END = 48, STATS_END = 96;
     static constexpr bool     TIES_INTERCHANGEABLE = false; // the delivery hash / handlers see port and order
     static constexpr bool     PARALLEL_EVENTS = false; // handlers chain through the state (hash, RNG): sequential
-    static constexpr uint32_t SCRATCH_PER_EVENT = 0, SCRATCH_FIXED = 0;
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
@@ -388,7 +376,6 @@ struct ClockNodeElement
     static constexpr uint32_t STORE_END = 48, CONST_END = 64, STATS_END = 160;
     static constexpr bool     TIES_INTERCHANGEABLE = false; // the delivery hash / handlers see port and order
     static constexpr bool     PARALLEL_EVENTS = false; // handlers chain through the state (hash, RNG): sequential
-    static constexpr uint32_t SCRATCH_PER_EVENT = 0, SCRATCH_FIXED = 0;
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
@@ -463,7 +450,6 @@ struct RngElement
     static constexpr uint32_t STORE_END = 96, CONST_END = 96, STATS_END = 96;
     static constexpr bool     TIES_INTERCHANGEABLE = false; // the delivery hash / handlers see port and order
     static constexpr bool     PARALLEL_EVENTS = false; // handlers chain through the state (hash, RNG): sequential
-    static constexpr uint32_t SCRATCH_PER_EVENT = 0, SCRATCH_FIXED = 0;
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
@@ -565,7 +551,6 @@ struct ElementInfo
     uint32_t    state_bytes;
     uint32_t    aux_bytes;
     int         has_payload;
-    uint32_t    scratch_per_event, scratch_fixed; // shared-memory scratch words per due event / per component
     bool        parallel_events;                  // has an event-parallel handler
     bool        ties_interchangeable;             // events of equal delivery time are interchangeable for the element
     const char* description;

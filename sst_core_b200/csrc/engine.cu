@@ -105,9 +105,9 @@ struct Dev
     uint32_t        lmax, uniform_nports; // link rows staged per block; ports per component when uniform (else 0)
     uint32_t        uniform_shift;        // log2(uniform_nports) when it is a power of two, else 32
     uint32_t        uniform_type;         // the element type when every local component has the same one, else 0
-    uint32_t        scr_per_event, scr_fixed; // shared-memory scratch words an element gets per due event / per component
     uint32_t        any_parallel;         // some local element type has an event-parallel handler
     uint32_t        ties_free;            // every local element type declares events of equal time interchangeable
+    uint32_t        par_max;              // most events of one component per window the event-parallel form takes
     uint32_t        P0, nport_local;
     uint32_t        rank, n_ranks;
     const uint32_t* rank_comp_begin; // [n_ranks+1] (device)
@@ -228,7 +228,6 @@ struct CtxT
     uint32_t     sent;
     int          stats_on;
     const uint4* links; // this component's link row (shared memory when the block's rows were staged, else global)
-    uint32_t*    scratch; // shared memory, scr_per_event * (events this window) + scr_fixed words (nullptr if none)
     // out-staging (STAGED only): this component's consumed slots are seg[free_head .. free_tail)
     Stage           st;
     const uint16_t* seg;
@@ -323,7 +322,7 @@ setup_kernel(Dev d)
     const uint32_t type = d.comp_type[lc];
     const uint32_t p0   = d.port_off[lc];
     CtxT<false>    ctx { d, 0, 0, 0, d.c0 + lc, p0, d.port_off[lc + 1] - p0, d.aux + (uint64_t)lc * d.aux_stride,
-                         0, 0, d.stats_on, d.link + (p0 - d.P0), nullptr, Stage {}, nullptr, 0, 0 };
+                         0, 0, d.stats_on, d.link + (p0 - d.P0), Stage {}, nullptr, 0, 0 };
     const uint64_t period = d.clock_period[lc];
     with_element(type, [&](auto el) {
         using E = decltype(el);
@@ -494,8 +493,7 @@ dispatch_kernel(Dev d)
     uint16_t* s_order    = s_sorted + d.emax;                         // [BLOCK] thread -> component of the block
     uint4*    s_hdr      = reinterpret_cast<uint4*>( // [BLOCK] per-component window header of the event-parallel path
         (reinterpret_cast<uintptr_t>(s_order + BLOCK) + 15) & ~(uintptr_t)15);
-    uint32_t* s_scratch  = reinterpret_cast<uint32_t*>(s_hdr + BLOCK); // [scr_per_event*emax + scr_fixed*BLOCK]
-    uint8_t*  s_pcomp    = reinterpret_cast<uint8_t*>(s_scratch + (size_t)d.scr_per_event * d.emax + (size_t)d.scr_fixed * BLOCK); // [emax] component of each segment position
+    uint8_t*  s_pcomp    = reinterpret_cast<uint8_t*>(s_hdr + BLOCK); // [emax] component of each segment position
 
     // ---- prologue: everything here is independent global traffic issued back to back.  The first 1024 records of
     // the bin are loaded before its fill count is known (the slots exist; what is past the count is ignored).
@@ -737,7 +735,7 @@ dispatch_kernel(Dev d)
         const uint32_t cn = s_cnt[tid];
         const uint4    h  = s_hdr[tid];
         if ( bin * BLOCK + tid < d.n_local && (cn > 0 || (h.w & 1u)) )
-            par_ok = d.any_parallel && cn > 0 && !(h.w & 1u) && h.x != 0xFFFFFFFFu && cn <= PAR_MAX_EVENTS &&
+            par_ok = d.any_parallel && cn > 0 && !(h.w & 1u) && h.x != 0xFFFFFFFFu && cn <= d.par_max &&
                      n_due <= PARB * BLOCK;
     }
     bool block_par = false;
@@ -855,7 +853,6 @@ dispatch_kernel(Dev d)
         // ticks; sends are staged in the slots the component has already consumed
         CtxT<true> ctx { d, T, k, T, d.c0 + lc, p0, s_port_off[c + 1] - p0,
                          d.aux + (uint64_t)lc * d.aux_stride, c_lo.z, 0, d.stats_on, my_links,
-                         d.scr_per_event | d.scr_fixed ? s_scratch + d.scr_per_event * s_off[c] + d.scr_fixed * c : nullptr,
                          Stage { s_time, s_dst, s_sc, PAYLOAD ? s_pay : nullptr }, seg, 0, 0 };
         uint32_t   dseq = c_lo.w;
         with_element(my_type, [&](auto el) {
@@ -1343,13 +1340,13 @@ rng_dist_kernel(int dist, const double* params, int np, int kind, uint64_t s1, u
 // ================================================================================================ host side
 static const ElementInfo kElements[] = {
     { TYPE_MESH, MeshElement::ELI_NAME, MeshElement::PERSIST_BYTES, MeshElement::AUX_BYTES,
-        MeshElement::HAS_PAYLOAD, MeshElement::SCRATCH_PER_EVENT, MeshElement::SCRATCH_FIXED, MeshElement::PARALLEL_EVENTS, MeshElement::TIES_INTERCHANGEABLE, "message_mesh enclosing component with message_port/port_slot/route_message" },
+        MeshElement::HAS_PAYLOAD, MeshElement::PARALLEL_EVENTS, MeshElement::TIES_INTERCHANGEABLE, "message_mesh enclosing component with message_port/port_slot/route_message" },
     { TYPE_PHOLD, PholdElement::ELI_NAME, PholdElement::PERSIST_BYTES, PholdElement::AUX_BYTES,
-        PholdElement::HAS_PAYLOAD, PholdElement::SCRATCH_PER_EVENT, PholdElement::SCRATCH_FIXED, PholdElement::PARALLEL_EVENTS, PholdElement::TIES_INTERCHANGEABLE, "PHOLD-style node, integer delays, 8-byte payload" },
+        PholdElement::HAS_PAYLOAD, PholdElement::PARALLEL_EVENTS, PholdElement::TIES_INTERCHANGEABLE, "PHOLD-style node, integer delays, 8-byte payload" },
     { TYPE_CLOCKNODE, ClockNodeElement::ELI_NAME, ClockNodeElement::PERSIST_BYTES,
-        ClockNodeElement::AUX_BYTES, ClockNodeElement::HAS_PAYLOAD, ClockNodeElement::SCRATCH_PER_EVENT, ClockNodeElement::SCRATCH_FIXED, ClockNodeElement::PARALLEL_EVENTS, ClockNodeElement::TIES_INTERCHANGEABLE, "clock-driven node (coreTestComponent style)" },
+        ClockNodeElement::AUX_BYTES, ClockNodeElement::HAS_PAYLOAD, ClockNodeElement::PARALLEL_EVENTS, ClockNodeElement::TIES_INTERCHANGEABLE, "clock-driven node (coreTestComponent style)" },
     { TYPE_RNGCOMP, RngElement::ELI_NAME, RngElement::PERSIST_BYTES, RngElement::AUX_BYTES,
-        RngElement::HAS_PAYLOAD, RngElement::SCRATCH_PER_EVENT, RngElement::SCRATCH_FIXED, RngElement::PARALLEL_EVENTS, RngElement::TIES_INTERCHANGEABLE, "coreTestRNGComponent: 1 GHz clock drawing from an SST::RNG generator" },
+        RngElement::HAS_PAYLOAD, RngElement::PARALLEL_EVENTS, RngElement::TIES_INTERCHANGEABLE, "coreTestRNGComponent: 1 GHz clock drawing from an SST::RNG generator" },
 };
 constexpr int kNumElements = (int)(sizeof(kElements) / sizeof(kElements[0]));
 
@@ -1634,13 +1631,11 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         for ( uint32_t c = c0; c < c1 && ut; ++c )
             if ( m->comp_type[c] != ut ) ut = 0;
         d.uniform_type = ut;
-        d.scr_per_event = d.scr_fixed = 0;
         d.any_parallel  = 0;
+        d.par_max       = (o->parallel_max_events && o->parallel_max_events < PAR_MAX_EVENTS) ? o->parallel_max_events : PAR_MAX_EVENTS;
         d.ties_free     = 1;
         for ( uint32_t c = c0; c < c1; ++c ) {
             const ElementInfo* ei = element_by_type(m->comp_type[c]);
-            d.scr_per_event       = std::max(d.scr_per_event, ei->scratch_per_event);
-            d.scr_fixed           = std::max(d.scr_fixed, ei->scratch_fixed);
             if ( ei->parallel_events ) d.any_parallel = 1;
             if ( !ei->ties_interchangeable ) d.ties_free = 0;
             if ( ut ) break; // uniform: the first one says it all
@@ -1713,8 +1708,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
 
     e->smem_bytes = (size_t)d.lmax * 16 + (size_t)d.emax * (has_payload ? 8 : 0) + (size_t)d.emax * 16 +
                     (size_t)(BLOCK + 1 + BLOCK + BLOCK + BLOCK / 32 + 1 + 4 + 32 + 32) * 4 + (size_t)d.emax * 4 +
-                    (size_t)BLOCK * 2 + 16 + (size_t)BLOCK * 16 + ((size_t)d.scr_per_event * d.emax + (size_t)d.scr_fixed * BLOCK) * 4 +
-                    (size_t)d.emax + 16;
+                    (size_t)BLOCK * 2 + 16 + (size_t)BLOCK * 16 + (size_t)d.emax + 16;
     if ( e->smem_bytes > 227 * 1024 ) {
         set_error("engine_create: smem_events too large for 227 KB of shared memory");
         sstb200_engine_destroy(e);

@@ -37,7 +37,8 @@ class _Options(C.Structure):
     _fields_ = [("device", C.c_int), ("rank", C.c_uint32), ("n_ranks", C.c_uint32), ("comp_begin", C.c_uint32),
                 ("comp_end", C.c_uint32), ("rank_comp_begin", C.c_void_p), ("calendar_slots", C.c_uint32),
                 ("bin_capacity", C.c_uint32), ("smem_events", C.c_uint32), ("outbox_capacity", C.c_uint32),
-                ("window", C.c_uint64), ("trace_capacity", C.c_uint64), ("stream", C.c_void_p)]
+                ("window", C.c_uint64), ("trace_capacity", C.c_uint64), ("stream", C.c_void_p),
+                ("parallel_max_events", C.c_uint32)]
 
 
 class _Status(C.Structure):
@@ -139,11 +140,11 @@ def partition_model(m: WiredModel, n_ranks: int) -> WiredModel:
     """Assign ranks with the linear partitioner and renumber components so that every rank owns one contiguous id
     range (the engine's layout); per-component port order -- hence delivery order -- is unchanged."""
     rank = partition_linear(m.ncomp, m.nocut_pairs, n_ranks)
-    order = np.argsort(rank, kind="stable")  # new id -> old id
-    if np.array_equal(order, np.arange(m.ncomp)):
+    if m.ncomp < 2 or bool(np.all(rank[:-1] <= rank[1:])):  # already contiguous per rank (the usual case): no renumbering
         m.rank, m.n_ranks = rank, n_ranks
         m.orig_id = np.arange(m.ncomp, dtype=np.uint32)
         return m
+    order = np.argsort(rank, kind="stable")  # new id -> old id
     nports = np.diff(m.port_off.astype(np.int64))
     new_nports = nports[order]
     new_port_off = np.zeros(m.ncomp + 1, dtype=np.int64)
@@ -202,7 +203,7 @@ class Engine:
 
     def __init__(self, model: WiredModel, device: int = 0, rank: int = 0, n_ranks: int = 1, calendar_slots: int = 2,
                  bin_capacity: int = 0, smem_events: int = 0, outbox_capacity: int = 0, window: int = 0,
-                 trace_capacity: int = 0, stream: int = 0):
+                 trace_capacity: int = 0, stream: int = 0, parallel_max_events: int = 0):
         L = lib()
         check_registry()
         self.model = model
@@ -223,7 +224,7 @@ class Engine:
             c0, c1 = 0, model.ncomp
         self.comp_begin, self.comp_end = c0, c1
         opt = _Options(device, rank, n_ranks, c0, c1, _p(self._begins), calendar_slots, bin_capacity, smem_events,
-                       outbox_capacity, window, trace_capacity, stream)
+                       outbox_capacity, window, trace_capacity, stream, parallel_max_events)
         h = C.c_void_p()
         _check(L.sstb200_engine_create(C.byref(cm), C.byref(opt), C.byref(h)), "engine_create")
         self._h = h

@@ -78,3 +78,40 @@ def test_gpu_error_reports():
                        bin_capacity=32768, smem_events=512)
     with pytest.raises(EngineError, match="window larger than a link latency|lookahead"):
         simulate_model(models.mesh_model(4, 4, stop_at="20ns"), window=5000)
+
+
+@pytest.mark.gpu
+def test_gpu_mesh_sequential_fallbacks_inside_the_event_parallel_kernel():
+    # MessageMesh normally takes the event-parallel form.  (1) cap the events one component may have in that form at
+    # 2: every block with a busier component falls back to the sequential form; (2) two links per port group: the
+    # element refuses the parallel form (its second draw then selects a link).  Results must not change.
+    from sst_core_b200 import models
+    from sst_core_b200.run import simulate_model
+    m = models.mesh_model(40, 30, stop_at="40ns", stats_enabled=True)
+    ref = O.run_model(m)
+    for opts in ({}, {"parallel_max_events": 2}, {"parallel_max_events": 5}):
+        res, st = simulate_model(m, **opts)
+        assert np.array_equal(res, ref.results), opts
+        assert st.events_delivered == ref.events
+    m2 = models.mesh_model(24, 24, stop_at="40ns", stats_enabled=True)
+    m2.comp_param[:, 4] = 2       # two port groups ...
+    m2.comp_param[:, 5] = 0x0202  # ... of two links each
+    _gpu_vs_oracle(m2)
+
+
+@pytest.mark.gpu
+def test_gpu_mesh_trace_keeps_the_full_delivery_order():
+    # with a delivery trace requested the (time, port, sequence) order is kept even for tie-interchangeable elements
+    from sst_core_b200 import models
+    from sst_core_b200.engine import Engine
+    m = models.mesh_model(5, 4, stop_at="12ns")
+    ref = O.run_model(m, trace=True)
+    e = Engine(m, trace_capacity=1 << 16)
+    e.setup()
+    e.run()
+    tr = e.trace()
+    e.close()
+    for c in range(20):
+        sel, rsel = tr["comp"] == c, ref.trace["comp"] == c
+        assert np.array_equal(tr["time"][sel], ref.trace["time"][rsel])
+        assert np.array_equal(tr["port"][sel], ref.trace["port"][rsel]), c
