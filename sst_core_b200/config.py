@@ -361,3 +361,84 @@ def build_graph(script_path: str, model_options: str = "", n_ranks: int = 1, my_
             # the reference tolerates dangling links only with a warning at checkForStructuralErrors
             pass
     return g
+
+
+def load_json(path: str, n_ranks: int = 1, my_rank: int = 0) -> ConfigGraph:
+    """Load a model in the reference's JSON interchange format: what ``sst --output-json`` writes
+    (``model/cfgoutput/jsonConfigOutput.cc``) and ``sst model.json`` reads (``model/json/jsonmodel.cc``).  A graph built
+    and checked by stock SST can thus be handed to this engine.  Handled keys: ``program_options``,
+    ``statistics_options``, ``components`` (``name``, ``type``, ``params``, ``statistics_options`` /
+    ``statistics``, nested ``subcomponents`` with ``slot_name`` / ``slot_number``) and ``links`` (``name``, ``noCut``,
+    ``left`` / ``right`` = ``{component: full name, port, latency}``)."""
+    import json
+
+    with open(path) as f:
+        doc = json.load(f)
+    g = ConfigGraph()
+    g.n_ranks, g.my_rank = n_ranks, my_rank
+    for k, v in doc.get("program_options", {}).items():
+        if v not in ("", None):
+            g.program_options[str(k)] = str(v)
+    so = doc.get("statistics_options", {}) or {}
+    if "statisticOutput" in so:
+        g.stat_output = (so["statisticOutput"], dict(so.get("params", {}) or {}))
+    g.stat_load_level = int(so.get("statisticLoadLevel", 0))
+
+    def stats_of(node, cfg):
+        o = node.get("statistics_options", {}) or {}
+        if o.get("enable_all_statistics"):
+            cfg.stats_enabled = "all"
+        names = [st.get("name") for st in (node.get("statistics", []) or []) if st.get("name")]
+        if names:
+            cfg.stats_enabled = names if cfg.stats_enabled is None else cfg.stats_enabled
+
+    def add_subs(node, parent):
+        for sub in node.get("subcomponents", []) or []:
+            child = ConfigComponent(g, None, None, str(sub["type"]), parent=parent, slot=str(sub["slot_name"]),
+                                    slot_num=int(sub.get("slot_number", 0)))
+            child.params = {str(k): _param_str(v) for k, v in (sub.get("params", {}) or {}).items()}
+            stats_of(sub, child)
+            parent.subs.append(child)
+            add_subs(sub, child)
+
+    for node in doc.get("components", []):
+        name = str(node["name"])
+        if name in g.comp_by_name:
+            raise ModelError(f"ERROR: trying to add Component with name that already exists: {name}")
+        cfg = ConfigComponent(g, len(g.components), name, str(node["type"]))
+        cfg.params = {str(k): _param_str(v) for k, v in (node.get("params", {}) or {}).items()}
+        stats_of(node, cfg)
+        g.components.append(cfg)
+        g.comp_by_name[name] = cfg
+        add_subs(node, cfg)
+    by_full = {}
+
+    def canon(name: str) -> str:
+        # the JSON writer always indexes slots ("comp:ports[2]:port[0]"); statistic names index a slot only when it
+        # holds several subcomponents (componentInfo.cc:125-144).  Look names up in the always-indexed form.
+        head, *rest = name.split(":")
+        return ":".join([head] + [seg if seg.endswith("]") else seg + "[0]" for seg in rest])
+
+    def index(c, key):
+        by_full[key] = c
+        for sc in c.subs:
+            index(sc, f"{key}:{sc.slot}[{sc.slot_num}]")
+
+    for c in g.components:
+        index(c, c.name)
+    for ln in doc.get("links", []):
+        cl = ConfigLink(len(g.links), str(ln["name"]), None)
+        cl.no_cut = bool(ln.get("noCut", False))
+        for side in ("left", "right"):
+            end = ln.get(side)
+            if not end:
+                continue
+            owner = by_full.get(canon(str(end["component"])))
+            if owner is None:
+                raise ModelError(f"link {cl.name}: unknown component {end['component']}")
+            cl.ends.append((owner, str(end["port"]), str(end["latency"])))
+            owner.links.append((str(end["port"]), cl, len(cl.ends) - 1))
+        g.links.append(cl)
+        g.link_by_name[cl.name] = cl
+    return g
+

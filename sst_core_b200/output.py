@@ -60,3 +60,27 @@ def stat_rows_csv(m: WiredModel, results: np.ndarray, end_time: int, rank_of=Non
             rows.append(f"{s.owner_name}, {s.name}, {s.subid}, Accumulator, {end_time}, {rk}, "
                         f"{vals[0]}, {vals[1]}, {vals[2]}, {vals[3]}, {vals[4]}")
     return rows
+
+
+def stat_lines_console(m: WiredModel, results: np.ndarray) -> List[str]:
+    """``sst.statOutputConsole`` (statapi/statoutputconsole.cc): one line per statistic, e.g.
+    `` component0:route.msg_count : Accumulator : Sum.u64 = 118; SumSQ.u64 = 118; Count.u64 = 118; Min.u64 = 1; Max.u64 = 1; ``"""
+    if not m.stats_enabled or not m.stats:
+        return []
+    order = np.argsort(m.orig_id) if m.orig_id is not None else np.arange(m.ncomp)
+    out = []
+    for i in order:
+        for s in m.stats[i]:
+            t = s.dtype
+            if s.offset is None:
+                vals = [0, 0, 0, 0, 0]
+            else:
+                vals = [int(x) for x in results[i, s.offset:s.offset + 5]]
+                if t == "i32":
+                    vals = [_signed(vals[0], 32), _signed(vals[1], 32), vals[2], _signed(vals[3], 32),
+                            _signed(vals[4], 32)]
+            name = f"{s.owner_name}.{s.name}" + (f".{s.subid}" if s.subid != "" else "")
+            out.append(f" {name} : Accumulator : Sum.{t} = {vals[0]}; SumSQ.{t} = {vals[1]}; Count.u64 = {vals[2]}; "
+                       f"Min.{t} = {vals[3]}; Max.{t} = {vals[4]}; ")
+    return out
+

@@ -22,19 +22,40 @@ def result_words(m) -> int:
     return max((RESULT_WORDS.get(int(t), NRESULT) for t in np.unique(m.comp_type)), default=NRESULT)
 
 
-def simulate_model(m: wireup.WiredModel, device: int = 0, **engine_opts):
-    """Run a WiredModel on one GPU.  Returns (results [ncomp,32] u64, Status)."""
-    from .engine import Engine
+def simulate_model(m: wireup.WiredModel, device: int = 0, auto_tune: bool = True, **engine_opts):
+    """Run a WiredModel on one GPU.  Returns (results [ncomp,32] u64, Status).
 
-    e = Engine(m, device=device, **engine_opts)
-    try:
-        e.setup()
-        e.run()
-        st = e.status()
-        e.raise_on_error(st)
-        return e.results(result_words(m)), st
-    finally:
-        e.close()
+    The calendar geometry (window slots, bin and staging capacities) is a tuning choice; when a run reports that one of
+    them overflowed and ``auto_tune`` is set, the run is repeated from the start with that resource doubled (an
+    overflow is always detected and reported, never silent -- see Engine.raise_on_error)."""
+    from .engine import Engine, EngineError
+
+    opts = dict(engine_opts)
+    for attempt in range(10):
+        e = Engine(m, device=device, **opts)
+        try:
+            e.setup()
+            try:
+                e.run()
+            except EngineError:
+                if not e.status().error:
+                    raise
+            st = e.status()
+            if st.error in (1, 2) and auto_tune and attempt < 9:
+                if st.error == 1:  # calendar bin overflow: more slots first (events spread over more bins), then bigger bins
+                    if opts.get("calendar_slots", 2) < 16:
+                        opts["calendar_slots"] = 2 * opts.get("calendar_slots", 2)
+                    else:
+                        opts["bin_capacity"] = 2 * (opts.get("bin_capacity", 0) or 2048)
+                else:  # shared-memory staging overflow
+                    opts["smem_events"] = min(2 * (opts.get("smem_events", 0) or 2048), 6144)
+                    opts["bin_capacity"] = max(opts.get("bin_capacity", 0) or 2048, 2 * opts["smem_events"])
+                continue
+            e.raise_on_error(st)
+            return e.results(result_words(m)), st
+        finally:
+            e.close()
+    raise EngineError("auto-tuning did not converge")
 
 
 def simulate_distributed(m: wireup.WiredModel, **engine_opts):
@@ -81,7 +102,10 @@ def main(argv: Optional[list] = None) -> int:
         print(f"FATAL: partitioner {a.partitioner} is not supported (only sst.linear)", file=sys.stderr)
         return 1
     try:
-        g = config.build_graph(a.script, a.model_options)
+        if a.script.endswith(".json"):
+            g = config.load_json(a.script)
+        else:
+            g = config.build_graph(a.script, a.model_options)
         if a.timebase:
             g.program_options["timebase"] = a.timebase
         m = wireup.wire(g, stop_at_override=a.stop_at)
@@ -96,6 +120,9 @@ def main(argv: Optional[list] = None) -> int:
     res, st = simulate_model(m, device=a.device, **opts)
     for line in output.finish_lines(m, res, st.end_time):
         print(line)
+    if m.stat_output[0] == "sst.statOutputConsole":
+        for line in output.stat_lines_console(m, res):
+            print(line)
     rows = output.stat_rows_csv(m, res, st.end_time)
     if rows and m.stat_output[0] == "sst.statOutputCSV":
         path = os.path.join(a.output_directory, m.stat_output[1].get("filepath", "StatisticOutput.csv"))

@@ -93,6 +93,24 @@ def main():
         out["phold_3x2_40ns_trace"] = {
             "source": "sstsim.x phold.py '3 2 40ns 4 3000 0' + pdes.trace: per-component [time, port] sequences",
             "seq": seq}
+    with tempfile.TemporaryDirectory() as td:
+        # the reference's JSON interchange format: written by the reference (--output-json), consumed by both
+        gj = Path(td) / "g.json"
+        O.run_ref(REF_TESTS / "test_MessageMesh.py", "3 2 1 1 1 1", extra=["--stop-at", "40ns", "--output-json", str(gj)],
+                  cwd=td)
+        (HERE / "mesh_3x2_stats.json").write_text(gj.read_text())
+        txt = O.run_ref(gj, cwd=td)  # the reference running its own JSON
+        out["mesh_3x2_json_run"] = {
+            "source": "sstsim.x test_MessageMesh.py '3 2 1 1 1 1' --stop-at 40ns --output-json; then sstsim.x g.json",
+            "counts": mesh_counts(txt), "rows": (Path(td) / "StatisticOutput.csv").read_text().strip().splitlines()}
+        # console statistic output
+        scr = Path(td) / "console.py"
+        scr.write_text((REF_TESTS / "test_MessageMesh.py").read_text().replace(
+            'sst.setStatisticOutput("sst.statOutputCSV")', 'sst.setStatisticOutput("sst.statOutputConsole")'))
+        txt = O.run_ref(scr, "2 2 1 1 1 1", extra=["--stop-at", "30ns"], cwd=td)
+        out["mesh_2x2_console_stats"] = {
+            "source": "sstsim.x test_MessageMesh.py (statOutputConsole) '2 2 1 1 1 1' --stop-at 30ns",
+            "lines": [l for l in txt.splitlines() if " : Accumulator : " in l]}
     (HERE / "reference_golden.json").write_text(json.dumps(out, indent=1, sort_keys=True))
     print("wrote", HERE / "reference_golden.json", (HERE / "reference_golden.json").stat().st_size, "bytes")
 

@@ -39,3 +39,21 @@ def test_cli_unknown_element_is_fatal(tmp_path):
     r = subprocess.run([sys.executable, "-m", "sst_core_b200", str(bad)], capture_output=True, text=True,
                        env={**__import__("os").environ, "PYTHONPATH": str(ROOT)})
     assert r.returncode == 1 and "can't find requested component" in r.stderr
+
+
+def test_cli_runs_the_reference_json_interchange_format(tmp_path):
+    out = _run([str(ROOT / "tests/golden/mesh_3x2_stats.json")], tmp_path)
+    counts = GOLD["mesh_3x2_json_run"]["counts"]
+    want = [f"{i} received {c} messages" for i, c in counts.items()] + ["Simulation is complete, simulated time: 40 ns"]
+    assert sorted(out.strip().splitlines()) == sorted(want)
+    assert (tmp_path / "StatisticOutput.csv").read_text().strip().splitlines() == GOLD["mesh_3x2_json_run"]["rows"]
+
+
+def test_auto_tuning_retries_after_a_reported_overflow():
+    from sst_core_b200 import models
+    from sst_core_b200.run import simulate_model
+    import oracle_lib as O
+    m = models.phold_model(16, 16, stop_at="60ns", init_events=24, stats_enabled=True)
+    res, st = simulate_model(m, calendar_slots=2, bin_capacity=1024, smem_events=1024)  # overflows at first
+    ref = O.run_model(m)
+    assert __import__("numpy").array_equal(res, ref.results) and st.events_delivered == ref.events

@@ -192,3 +192,28 @@ def test_mesh_csv_and_finish_lines_match_reference(tmp_path):
     lines = output.finish_lines(w, r.results, r.end_time)
     assert lines[-1] == "Simulation is complete, simulated time: 100 ns"
     assert lines[0].startswith("0 received ")
+
+
+def test_json_interchange_graph_equals_script_graph():
+    # a graph written by the reference (--output-json) loads into the same wired model as the script that made it
+    wj = wireup.wire(config.load_json(str(ROOT / "tests/golden/mesh_3x2_stats.json")))
+    ws = wireup.wire(config.build_graph(str(MODELS / "mesh.py"), "3 2 1 1 1 1"), stop_at_override="40ns")
+    for f in ("comp_type", "comp_param", "port_off", "peer_port", "latency", "clock_period"):
+        assert np.array_equal(getattr(wj, f), getattr(ws, f)), f
+    assert wj.stop_at == ws.stop_at == 40_000 and wj.stats_enabled and wj.names == ws.names
+    assert wj.stat_output[0] == "sst.statOutputCSV"
+
+
+def test_json_model_through_oracle_matches_reference_run_of_the_same_json():
+    import oracle_lib as O
+    w = wireup.wire(config.load_json(str(ROOT / "tests/golden/mesh_3x2_stats.json")))
+    r = O.run_model(w)
+    assert {str(i): int(r.results[i, 0]) for i in range(6)} == GOLD["mesh_3x2_json_run"]["counts"]
+    assert output.stat_rows_csv(w, r.results, r.end_time) == GOLD["mesh_3x2_json_run"]["rows"]
+
+
+def test_console_statistic_output_matches_reference():
+    import oracle_lib as O
+    w = wireup.wire(config.build_graph(str(MODELS / "mesh.py"), "2 2 1 1 1 1"), stop_at_override="30ns")
+    r = O.run_model(w)
+    assert output.stat_lines_console(w, r.results) == GOLD["mesh_2x2_console_stats"]["lines"]
