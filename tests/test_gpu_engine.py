@@ -158,7 +158,8 @@ def test_stop_inside_a_window_clips_it():
 def test_bin_overflow_is_reported_not_silent():
     from sst_core_b200.engine import EngineError
     with pytest.raises(EngineError, match="bin overflow"):
-        run_gpu(models.phold_model(16, 16, stop_at="50ns", init_events=64), calendar_slots=2, bin_capacity=512)
+        run_gpu(models.phold_model(16, 16, stop_at="50ns", init_events=64), calendar_slots=2, bin_capacity=512,
+                auto_tune=False)
 
 
 def test_rng_component_model_ends_by_primary_component_exit():

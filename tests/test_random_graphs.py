@@ -75,7 +75,7 @@ def test_gpu_error_reports():
     from sst_core_b200 import models
     with pytest.raises(EngineError, match="staging overflow"):
         simulate_model(models.phold_model(16, 16, stop_at="50ns", init_events=40, delay_mod=1), calendar_slots=4,
-                       bin_capacity=32768, smem_events=512)
+                       bin_capacity=32768, smem_events=512, auto_tune=False)
     with pytest.raises(EngineError, match="window larger than a link latency|lookahead"):
         simulate_model(models.mesh_model(4, 4, stop_at="20ns"), window=5000)
 
