@@ -59,41 +59,75 @@ def parse_args():
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, every ~5 ms; nvidia-smi as a fallback)."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
         self.samples, self.stop_flag, self.index = [], threading.Event(), index
+        self.max_mhz, self.reasons = None, set()
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.samples.append(f)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:  # map the CUDA ordinal to the NVML device (CUDA_VISIBLE_DEVICES may renumber)
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            h = None
+            if uuid:
+                for cand in ("GPU-" + uuid, uuid):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if hasattr(cand, "encode") else cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self.stop_flag.is_set():
+                self.samples.append(int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                try:
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.stop_flag.wait(0.005)
+            return
+        except Exception:
+            pass
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(int(float(f[0])))
+                self.max_mhz = int(float(f[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
 
     def start(self):
         self.t.start()
+        time.sleep(0.02)  # let the sampler come up before the timed region starts
 
     def stop(self):
         self.stop_flag.set()
         self.t.join(timeout=6)
-        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
-        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
-        reasons = set()
-        for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU / reference arm

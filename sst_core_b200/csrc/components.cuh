@@ -270,6 +270,8 @@ struct MeshElement
     {
         return true;
     }
+    // total number of addData calls so far: tells the engine whether a window touched the statistics
+    __device__ static uint64_t statsVersion(const State& s) { return s.mcnt.count; }
     __device__ static void results(const State& s, uint64_t* r)
     {
         r[0] = (uint64_t)(int64_t)s.message_count;
@@ -343,6 +345,8 @@ struct PholdElement
     {
         return true;
     }
+    // total number of addData calls so far: tells the engine whether a window touched the statistics
+    __device__ static uint64_t statsVersion(const State& s) { return s.delay.count; }
     __device__ static void results(const State& s, uint64_t* r)
     {
         r[0] = s.recv;
@@ -419,6 +423,8 @@ struct ClockNodeElement
         }
         return false;
     }
+    // total number of addData calls so far: tells the engine whether a window touched the statistics
+    __device__ static uint64_t statsVersion(const State& s) { return s.count[0].count + s.count[1].count + s.count[2].count + s.count[3].count; }
     __device__ static void results(const State& s, uint64_t* r)
     {
         r[0] = s.ticks;
@@ -531,6 +537,8 @@ struct RngElement
         }
         return false;
     }
+    // total number of addData calls so far: tells the engine whether a window touched the statistics
+    __device__ static uint64_t statsVersion(const State& s) { return 0; }
     __device__ static void results(const State& s, uint64_t* r)
     {
         r[0] = (uint64_t)s.rng_count;
