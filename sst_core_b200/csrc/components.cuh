@@ -68,6 +68,15 @@ struct Accumulator
         mx = v > mx ? v : mx;
         count += n;
     }
+    // fold the data another accumulator collected into this one (same result as presenting its values here)
+    SSTB_HD void merge(const Accumulator& o)
+    {
+        sum += o.sum;
+        sumsq += o.sumsq;
+        mn = o.mn < mn ? o.mn : mn;
+        mx = o.mx > mx ? o.mx : mx;
+        count += o.count;
+    }
     SSTB_HD void out(uint64_t* r) const
     {
         r[0] = (uint64_t)(int64_t)sum;
@@ -270,7 +279,11 @@ struct MeshElement
     {
         return true;
     }
-    // total number of addData calls so far: tells the engine whether a window touched the statistics
+    // statistics are collected per window into an empty accumulator and folded into memory only if the window
+    // added data: the statistics region is not even read by windows that leave it alone
+    __device__ static void initStats(State& s) { s.mcnt.init(); }
+    __device__ static void mergeStats(State& mem, const State& d) { mem.mcnt.merge(d.mcnt); }
+    // number of addData calls in the accumulators: tells the engine whether a window touched the statistics
     __device__ static uint64_t statsVersion(const State& s) { return s.mcnt.count; }
     __device__ static void results(const State& s, uint64_t* r)
     {
@@ -345,7 +358,11 @@ struct PholdElement
     {
         return true;
     }
-    // total number of addData calls so far: tells the engine whether a window touched the statistics
+    // statistics are collected per window into an empty accumulator and folded into memory only if the window
+    // added data: the statistics region is not even read by windows that leave it alone
+    __device__ static void initStats(State& s) { s.delay.init(); }
+    __device__ static void mergeStats(State& mem, const State& d) { mem.delay.merge(d.delay); }
+    // number of addData calls in the accumulators: tells the engine whether a window touched the statistics
     __device__ static uint64_t statsVersion(const State& s) { return s.delay.count; }
     __device__ static void results(const State& s, uint64_t* r)
     {
@@ -423,7 +440,11 @@ struct ClockNodeElement
         }
         return false;
     }
-    // total number of addData calls so far: tells the engine whether a window touched the statistics
+    // statistics are collected per window into an empty accumulator and folded into memory only if the window
+    // added data: the statistics region is not even read by windows that leave it alone
+    __device__ static void initStats(State& s) { for ( int i = 0; i < 4; ++i ) s.count[i].init(); }
+    __device__ static void mergeStats(State& mem, const State& d) { for ( int i = 0; i < 4; ++i ) mem.count[i].merge(d.count[i]); }
+    // number of addData calls in the accumulators: tells the engine whether a window touched the statistics
     __device__ static uint64_t statsVersion(const State& s) { return s.count[0].count + s.count[1].count + s.count[2].count + s.count[3].count; }
     __device__ static void results(const State& s, uint64_t* r)
     {
@@ -537,7 +558,11 @@ struct RngElement
         }
         return false;
     }
-    // total number of addData calls so far: tells the engine whether a window touched the statistics
+    // statistics are collected per window into an empty accumulator and folded into memory only if the window
+    // added data: the statistics region is not even read by windows that leave it alone
+    __device__ static void initStats(State& s) {  }
+    __device__ static void mergeStats(State& mem, const State& d) {  }
+    // number of addData calls in the accumulators: tells the engine whether a window touched the statistics
     __device__ static uint64_t statsVersion(const State& s) { return 0; }
     __device__ static void results(const State& s, uint64_t* r)
     {

@@ -858,8 +858,8 @@ dispatch_kernel(Dev d)
         with_element(my_type, [&](auto el) {
             using E = decltype(el);
             typename E::State s;
-            load_state(s, d.state + (uint64_t)lc * d.state_stride, 0, d.stats_on ? E::STATS_END : E::CONST_END);
-            const uint64_t stats_before = d.stats_on ? E::statsVersion(s) : 0;
+            load_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::CONST_END);
+            E::initStats(s); // this window's statistics start empty and are folded into memory at the end
             E::beginWindow(ctx, s, my_cnt); // issues the element's first loads (MT19937 read-ahead)
             if ( owner_sorts ) sort_segment(s_perm + s_off[c], my_cnt, s_time, s_dst, s_sc);
             uint64_t cycle = (next_tick != TIME_NEVER && period) ? next_tick / period : 0;
@@ -901,10 +901,14 @@ dispatch_kernel(Dev d)
                 delivered++;
             }
             store_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::STORE_END);
-            // statistics are written back only when the window added data to them (a clock-driven element may tick a
-            // thousand times between two addData calls)
-            if ( d.stats_on && E::statsVersion(s) != stats_before )
-                store_state(s, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
+            // statistics: read-modify-write only when the window added data (a clock-driven element may tick a thousand
+            // times between two addData calls)
+            if ( d.stats_on && E::statsVersion(s) != 0 ) {
+                typename E::State mem;
+                load_state(mem, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
+                E::mergeStats(mem, s);
+                store_state(mem, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
+            }
         });
         *reinterpret_cast<uint4*>(&d.ctl[lc]) =
             make_uint4((uint32_t)next_tick, (uint32_t)(next_tick >> 32), ctx.seq, dseq);
