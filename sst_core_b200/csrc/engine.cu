@@ -548,7 +548,9 @@ dispatch_kernel(Dev d)
     PHASE_MARK(1);
     const uint32_t blk_port0     = s_port_off[0];
     const uint32_t blk_nports    = s_port_off[BLOCK] - blk_port0;
-    const bool     links_in_smem = blk_nports <= d.lmax;
+    // stage the block's link rows in shared memory when the block has a fair number of events to forward; a block that
+    // only ticks (clock populations send once in a thousand ticks) reads the odd row it needs from memory instead
+    const bool     links_in_smem = blk_nports <= d.lmax && n_in >= BLOCK / 8;
     if ( links_in_smem ) { // asynchronous copy (LDGSTS): nobody waits for the rows until phase 3
         const uint4* src = d.link + (blk_port0 - d.P0);
         for ( uint32_t i = tid; i < blk_nports; i += BLOCK )
