@@ -1,10 +1,6 @@
 #!/bin/bash
-for v in "-DSSTB200_MESH_PREFETCH=0" "-DSSTB200_MESH_PREFETCH=1" "-DSSTB200_MESH_PREFETCH=2"; do
-  SSTB200_NVCC_EXTRA="$v" python -m sst_core_b200.build --force > gpurun_out/build_v.log 2>&1
-  ARGS="--steps 4 --warmup 3 --no-e2e --no-cpu-baseline"
-  python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$v', round(d['value']/1e9,2), 'G ev/s', round(d['ms_per_step'],3), 'ms')"
-  ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:dispatch_kernel -s 4 -c 1 --csv --log-file gpurun_out/t.csv python bench.py $ARGS > /dev/null 2>&1
-  grep dram__ gpurun_out/t.csv | awk -F'","' '{print $13, $15}'
-done
-python -m sst_core_b200.build --force > /dev/null 2>&1
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_gpu.log
+SSTB200_CREATE_TIMING=1 python profiles/e2e_breakdown.py --pin 2>&1 | tail -12
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_e2e.log 2>gpurun_out/bench_e2e.err; tail -c 700 gpurun_out/bench_e2e.log; tail -3 gpurun_out/bench_e2e.err
+python bench.py --workload phold --x 1024 --y 1024 --steps 20 --warmup 10 --no-cpu-baseline > gpurun_out/bench_phold.log 2>&1; tail -c 700 gpurun_out/bench_phold.log

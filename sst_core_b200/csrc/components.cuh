@@ -120,6 +120,10 @@ struct MeshElement
     static constexpr const char* ELI_NAME     = "coreTestElement.message_mesh.enclosing_component";
     static constexpr uint32_t    AUX_BYTES    = MT_N * 4;
     static constexpr bool        HAS_PAYLOAD  = false;
+    // the aux block is a MersenneRNG state the engine seeds warp-cooperatively before construct() (seed_mt_kernel):
+    // RouteMessage ctor, MersenneRNG(my_id + 100) (enclosingComponent.cc:164-170)
+    static constexpr bool AUX_MT_SEED = true;
+    __device__ static uint32_t auxSeed(const int64_t* p) { return (uint32_t)(p[0] + 100); }
     struct State
     {
         // [0,16) mutable core
@@ -239,7 +243,6 @@ struct MeshElement
         s.ngroups       = (uint32_t)p[4];
         s.counts        = (uint64_t)p[5];
         s.mcnt.init();
-        mt_seed((uint32_t*)ctx.aux, (uint32_t)(p[0] + 100)); // RouteMessage ctor: MersenneRNG(my_id + 100)
     }
     template <class Ctx>
     __device__ static void setup(Ctx& ctx, State& s)
@@ -299,6 +302,8 @@ struct PholdElement
     static constexpr uint32_t    TYPE        = TYPE_PHOLD;
     static constexpr const char* ELI_NAME    = "pdes.phold";
     static constexpr uint32_t    AUX_BYTES   = 0;
+    static constexpr bool        AUX_MT_SEED = false;
+    __device__ static uint32_t auxSeed(const int64_t*) { return 0; }
     static constexpr bool        HAS_PAYLOAD = true;
     struct State
     {
@@ -379,6 +384,8 @@ struct ClockNodeElement
     static constexpr uint32_t    TYPE        = TYPE_CLOCKNODE;
     static constexpr const char* ELI_NAME    = "pdes.clocknode";
     static constexpr uint32_t    AUX_BYTES   = 0;
+    static constexpr bool        AUX_MT_SEED = false;
+    __device__ static uint32_t auxSeed(const int64_t*) { return 0; }
     static constexpr bool        HAS_PAYLOAD = false;
     struct State
     {
@@ -464,6 +471,8 @@ struct RngElement
     static constexpr uint32_t    TYPE        = TYPE_RNGCOMP;
     static constexpr const char* ELI_NAME    = "coreTestElement.coreTestRNGComponent";
     static constexpr uint32_t    AUX_BYTES   = MT_N * 4;
+    static constexpr bool        AUX_MT_SEED = false;
+    __device__ static uint32_t auxSeed(const int64_t*) { return 0; }
     static constexpr bool        HAS_PAYLOAD = false;
     struct State
     {

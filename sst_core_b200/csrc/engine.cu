@@ -26,11 +26,14 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <limits>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace sstb200 {
@@ -311,6 +314,49 @@ store_state(const S& s, uint8_t* p, uint32_t from, uint32_t to)
 #pragma unroll
     for ( int i = 0; i < (int)((sizeof(S) + 15) / 16); ++i )
         if ( (uint32_t)i * 16 >= from && (uint32_t)i * 16 < to ) dst[i] = tmp[i];
+}
+
+// ---- MT19937 seeding (mersenne.cc:149-159) of the aux blocks of elements that declare AUX_MT_SEED.  A thread per
+// component storing its 624 words one by one costs one 4-byte L2 transaction per word at a 2.5 KB stride (88 ms for
+// 16.7 M components).  Here every lane still runs its own component's recurrence, but 16 words at a time go through a
+// shared-memory tile and the warp writes them out as 16-byte pieces, 64 contiguous bytes per component per store.
+__global__ void __launch_bounds__(BLOCK)
+seed_mt_kernel(Dev d)
+{
+    __shared__ uint32_t tile[BLOCK / 32][32][17];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lc   = blockIdx.x * BLOCK + threadIdx.x;
+    bool           want = false;
+    uint32_t       prev = 0;
+    if ( lc < d.n_local )
+        with_element(d.comp_type[lc], [&](auto el) {
+            using E = decltype(el);
+            if constexpr ( E::AUX_MT_SEED ) {
+                want = true;
+                prev = E::auxSeed(d.comp_param + (uint64_t)lc * NPARAM);
+            }
+        });
+    const uint32_t wantmask = __ballot_sync(0xffffffffu, want);
+    if ( !wantmask ) return;
+    uint8_t* const warp_aux = d.aux + (uint64_t)(lc - lane) * d.aux_stride;
+    for ( uint32_t chunk = 0; chunk < MT_N / 16; ++chunk ) {
+#pragma unroll
+        for ( uint32_t j = 0; j < 16; ++j ) {
+            const uint32_t i = chunk * 16 + j;
+            if ( i ) prev = 1812433253u * (prev ^ (prev >> 30)) + i;
+            tile[warp][lane][j] = prev;
+        }
+        __syncwarp();
+#pragma unroll
+        for ( uint32_t r = 0; r < 4; ++r ) {
+            const uint32_t comp = (lane >> 2) + 8 * r, piece = lane & 3;
+            if ( wantmask >> comp & 1u ) {
+                const uint32_t* t = &tile[warp][comp][piece * 4];
+                *(uint4*)(warp_aux + (uint64_t)comp * d.aux_stride + chunk * 64 + piece * 16) = make_uint4(t[0], t[1], t[2], t[3]);
+            }
+        }
+        __syncwarp();
+    }
 }
 
 // ---- construct + setup(): performWireUp (simulation.cc:824-859) and setup() (simulation.cc:969-987)
@@ -1549,6 +1595,17 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         return -1;
     }
     CUDA_OK(cudaSetDevice(o->device));
+    // SSTB200_CREATE_TIMING=1 prints where engine_create spends its time (host scans, uploads, allocations)
+    const bool create_timing = getenv("SSTB200_CREATE_TIMING") != nullptr;
+    auto       t_prev        = std::chrono::steady_clock::now();
+    auto       lap           = [&](const char* what, cudaStream_t s) {
+        if ( !create_timing ) return;
+        if ( s ) cudaStreamSynchronize(s);
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sstb200 create] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+        t_prev = t;
+    };
+    if ( const char* g = getenv("SSTB200_L2_FETCH") ) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
     sstb200_engine* e = new sstb200_engine();
     e->device         = o->device;
     e->n_ranks        = n_ranks;
@@ -1574,87 +1631,136 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     d.emax = (d.emax + 3u) & ~3u;
     d.stats_on = m->stats_enabled;
 
+    // The model scans below touch every port (67 M for a 4096x4096 torus) and every component once; they run on a few
+    // host threads so that engine_create is bound by the uploads, not by this.
+    auto scan = [](size_t n, auto&& body) { // body(lo, hi, slot) on up to 16 threads
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned T  = n < (1u << 20) ? 1u : std::min(16u, hw);
+        if ( T == 1 ) {
+            body((size_t)0, n, 0u);
+            return 1u;
+        }
+        std::vector<std::thread> th;
+        for ( unsigned t = 0; t < T; ++t )
+            th.emplace_back([&, t] { body(n * t / T, n * (t + 1) / T, t); });
+        for ( auto& x : th )
+            x.join();
+        return T;
+    };
     // lookahead window = minimum latency over every connected link (cut or not: a window is processed as one batch
     // per component, so nothing sent inside it may be due inside it)
-    uint64_t       w     = o->window;
     const uint32_t nport = m->port_off[m->ncomp];
-    if ( !w ) {
+    uint64_t       mn_lat[16];
+    for ( auto& v : mn_lat )
+        v = TIME_NEVER;
+    scan(nport, [&](size_t lo, size_t hi, unsigned t) {
         uint64_t mn = TIME_NEVER;
-        for ( uint32_t p = 0; p < nport; ++p )
+        for ( size_t p = lo; p < hi; ++p )
             if ( m->peer_port[p] != SSTB200_NO_PEER && m->latency[p] < mn ) mn = m->latency[p];
-        w = (mn == TIME_NEVER) ? 1000000ull : mn;
-    }
+        mn_lat[t] = mn;
+    });
+    const uint64_t mn = *std::min_element(mn_lat, mn_lat + 16);
+    uint64_t       w  = o->window ? o->window : (mn == TIME_NEVER ? 1000000ull : mn);
     if ( w == 0 || w > 0x7fffffffull ) {
         set_error("engine_create: lookahead window must be in [1, 2^31) cycles (zero-latency links are not allowed)");
         delete e;
         return -1;
     }
-    for ( uint32_t p = 0; p < nport; ++p )
-        if ( m->peer_port[p] != SSTB200_NO_PEER && m->latency[p] < w ) {
-            set_error("engine_create: window larger than a link latency");
-            delete e;
-            return -1;
-        }
+    if ( mn < w ) {
+        set_error("engine_create: window larger than a link latency");
+        delete e;
+        return -1;
+    }
+    lap("window scan", nullptr);
 
     // per-rank slices
     d.P0          = m->port_off[c0];
     d.nport_local = m->port_off[c1] - d.P0;
+    // one pass over the components: element types present (whole model: payload arrays are needed if ANY component of
+    // any rank carries payloads; this rank: state/aux strides, forms), port-count uniformity, ports per block (link
+    // rows of a block are staged in shared memory when they fit, 2048 rows = 32 KB; a uniform port count lets the
+    // kernel find an event's component with one division instead of a binary search)
+    const ElementInfo* by_type[TYPE_MAX] = {};
+    for ( int i = 0; i < kNumElements; ++i )
+        if ( kElements[i].type < TYPE_MAX ) by_type[kElements[i].type] = &kElements[i];
+    struct Part
+    {
+        uint32_t seen_all = 0, seen_local = 0, bad = 0xFFFFFFFFu, max_blk = 0;
+        bool     uni_ok = true;
+    } part[16];
+    const uint32_t uni0 = d.n_local ? m->port_off[c0 + 1] - m->port_off[c0] : 0;
+    scan(m->ncomp, [&](size_t lo, size_t hi, unsigned t) {
+        Part q;
+        for ( size_t c = lo; c < hi; ++c ) {
+            const uint32_t ty = m->comp_type[c];
+            if ( ty >= TYPE_MAX || !by_type[ty] ) {
+                if ( c >= c0 && c < c1 && q.bad == 0xFFFFFFFFu ) q.bad = (uint32_t)c;
+                continue;
+            }
+            q.seen_all |= 1u << ty;
+            if ( c >= c0 && c < c1 ) {
+                q.seen_local |= 1u << ty;
+                if ( m->port_off[c + 1] - m->port_off[c] != uni0 ) q.uni_ok = false;
+            }
+        }
+        part[t] = q;
+    });
+    scan(d.nbins, [&](size_t lo, size_t hi, unsigned t) {
+        uint32_t mx = 0;
+        for ( size_t b = lo; b < hi; ++b ) {
+            const uint32_t blo = c0 + (uint32_t)b * BLOCK, bhi = std::min<uint32_t>(c1, blo + BLOCK);
+            if ( blo < bhi ) mx = std::max(mx, m->port_off[bhi] - m->port_off[blo]);
+        }
+        part[t].max_blk = std::max(part[t].max_blk, mx);
+    });
+    uint32_t seen_all = 0, seen_local = 0, bad = 0xFFFFFFFFu, max_blk = 0;
+    bool     uni_ok = true;
+    for ( const Part& q : part ) {
+        seen_all |= q.seen_all;
+        seen_local |= q.seen_local;
+        bad     = std::min(bad, q.bad);
+        max_blk = std::max(max_blk, q.max_blk);
+        uni_ok  = uni_ok && q.uni_ok;
+    }
+    if ( bad != 0xFFFFFFFFu ) {
+        set_error("engine_create: component " + std::to_string(bad) + " has unknown type code " +
+                  std::to_string(m->comp_type[bad]));
+        delete e;
+        return -1;
+    }
     uint32_t state_stride = 8, aux_stride = 0;
     int      has_payload  = 0;
-    for ( uint32_t c = c0; c < c1; ++c ) {
-        const ElementInfo* ei = element_by_type(m->comp_type[c]);
-        if ( !ei ) {
-            set_error("engine_create: component " + std::to_string(c) + " has unknown type code " +
-                      std::to_string(m->comp_type[c]));
-            delete e;
-            return -1;
-        }
+    d.any_parallel        = 0;
+    d.ties_free           = 1;
+    d.uniform_type        = 0;
+    for ( uint32_t ty = 0; ty < TYPE_MAX; ++ty ) {
+        const ElementInfo* ei = by_type[ty];
+        if ( !ei ) continue;
+        if ( (seen_all >> ty & 1u) && ei->has_payload ) has_payload = 1;
+        if ( !(seen_local >> ty & 1u) ) continue;
         state_stride = std::max(state_stride, ei->state_bytes);
         aux_stride   = std::max(aux_stride, ei->aux_bytes);
+        if ( ei->parallel_events ) d.any_parallel = 1;
+        if ( !ei->ties_interchangeable ) d.ties_free = 0;
+        if ( (seen_local & (seen_local - 1)) == 0 ) d.uniform_type = ty; // the only type on this rank
     }
-    // payload arrays are needed if ANY component of the model (any rank) carries payloads
-    for ( uint32_t c = 0; c < m->ncomp; ++c ) {
-        const ElementInfo* ei = element_by_type(m->comp_type[c]);
-        if ( ei && ei->has_payload ) has_payload = 1;
-    }
-    // link rows of a block are staged in shared memory when they fit (2048 rows = 32 KB); a uniform port count lets
-    // the kernel find an event's component with one division instead of a binary search
+    d.par_max = (o->parallel_max_events && o->parallel_max_events < PAR_MAX_EVENTS) ? o->parallel_max_events : PAR_MAX_EVENTS;
     {
-        uint32_t max_blk = 0, uni = m->port_off[c0 + (d.n_local ? 1 : 0)] - m->port_off[c0];
-        for ( uint32_t b = 0; b < d.nbins; ++b ) {
-            const uint32_t lo = c0 + b * BLOCK, hi = std::min<uint32_t>(c1, lo + BLOCK);
-            max_blk           = std::max(max_blk, m->port_off[hi] - m->port_off[lo]);
-        }
-        for ( uint32_t c = c0; c < c1 && uni; ++c )
-            if ( m->port_off[c + 1] - m->port_off[c] != uni ) uni = 0;
-        d.lmax           = max_blk <= 2048 ? max_blk : 0;
-        d.uniform_nports = uni;
-        d.uniform_shift  = 32;
+        const uint32_t uni = uni_ok ? uni0 : 0;
+        d.lmax             = max_blk <= 2048 ? max_blk : 0;
+        d.uniform_nports   = uni;
+        d.uniform_shift    = 32;
         if ( uni && (uni & (uni - 1)) == 0 ) {
             d.uniform_shift = 0;
             while ( (1u << d.uniform_shift) < uni )
                 ++d.uniform_shift;
         }
     }
-    {
-        uint32_t ut = d.n_local ? m->comp_type[c0] : 0;
-        for ( uint32_t c = c0; c < c1 && ut; ++c )
-            if ( m->comp_type[c] != ut ) ut = 0;
-        d.uniform_type = ut;
-        d.any_parallel  = 0;
-        d.par_max       = (o->parallel_max_events && o->parallel_max_events < PAR_MAX_EVENTS) ? o->parallel_max_events : PAR_MAX_EVENTS;
-        d.ties_free     = 1;
-        for ( uint32_t c = c0; c < c1; ++c ) {
-            const ElementInfo* ei = element_by_type(m->comp_type[c]);
-            if ( ei->parallel_events ) d.any_parallel = 1;
-            if ( !ei->ties_interchangeable ) d.ties_free = 0;
-            if ( ut ) break; // uniform: the first one says it all
-        }
-    }
     d.state_stride = (state_stride + 15u) & ~15u;
     d.aux_stride   = (aux_stride + 31u) & ~31u;
     d.has_payload  = has_payload;
 
+    lap("element scans", nullptr);
     int rc = 0;
     rc |= e->upload(&d.comp_type, m->comp_type + c0, d.n_local);
     rc |= e->upload(&d.comp_param, m->comp_param + (size_t)c0 * NPARAM, (size_t)d.n_local * NPARAM);
@@ -1677,6 +1783,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         d.link = link_dev;
     }
     rc |= e->upload(&d.clock_period, m->clock_period + c0, d.n_local);
+    lap("uploads + link rows", e->stream);
     if ( n_ranks > 1 ) rc |= e->upload(&d.rank_comp_begin, o->rank_comp_begin, (size_t)n_ranks + 1);
     rc |= e->alloc(&d.ctl, d.n_local);
     rc |= e->alloc(&d.state, (size_t)d.n_local * d.state_stride);
@@ -1702,6 +1809,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         rc |= e->alloc(&d.tr_payload, d.trace_cap);
     }
     rc |= e->alloc(&e->d_results, (size_t)d.n_local * NRESULT);
+    lap("allocations + clears", e->stream);
     if ( rc ) {
         sstb200_engine_destroy(e);
         return -2;
@@ -1755,6 +1863,10 @@ sstb200_engine_setup(sstb200_engine* e)
     if ( e->is_setup ) {
         set_error("engine_setup called twice");
         return -1;
+    }
+    if ( e->d.aux_stride ) {
+        seed_mt_kernel<<<e->d.nbins, BLOCK, 0, e->stream>>>(e->d);
+        e->launches++;
     }
     setup_kernel<<<e->d.nbins, BLOCK, 0, e->stream>>>(e->d);
     e->launches++;

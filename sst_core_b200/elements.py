@@ -28,6 +28,8 @@ NPARAM = 8
 NRESULT = 32
 # words of the result record each element actually fills (the download can stop there)
 RESULT_WORDS = {1: 6, 2: 7, 3: 24, 4: 7}
+# ... and when statistics are disabled (the accumulator words stay zero)
+RESULT_WORDS_NOSTATS = {1: 1, 2: 2, 3: 4, 4: 7}
 
 
 @dataclass

@@ -304,11 +304,18 @@ class Engine:
         """Wait for the engine's stream (status() does a device->host read on it)."""
         self.status()
 
-    def results(self, words: int = 0, compact: bool = False) -> np.ndarray:
+    def results(self, words: int = 0, compact: bool = False, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Result records of this rank's components.  `words` > 0 downloads only the first `words` of the 32 words per
         component; the returned array is [n, 32] (rest zero) unless `compact`, then [n, words] with no host-side copy
-        (what a large run wants: 16.7 M components x 32 words is 4.3 GB of mostly zeros)."""
+        (what a large run wants: 16.7 M components x 32 words is 4.3 GB of mostly zeros).  `out` (compact form only):
+        a caller-owned C-contiguous uint64 [n, words] array to download into, e.g. ``wireup.pinned_empty`` memory."""
         n = self.comp_end - self.comp_begin
+        if out is not None:
+            w = words if words and words < NRESULT else NRESULT
+            if out.dtype != np.uint64 or out.shape != (n, w) or not out.flags.c_contiguous:
+                raise ValueError(f"results(out=): need a C-contiguous uint64 array of shape ({n}, {w})")
+            _check(self._L.sstb200_engine_results(self._h, _p(out), 0 if w == NRESULT else w), "engine_results")
+            return out
         if not words or words >= NRESULT:
             out = np.empty((n, NRESULT), dtype=np.uint64)
             _check(self._L.sstb200_engine_results(self._h, _p(out), 0), "engine_results")

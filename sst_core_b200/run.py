@@ -14,12 +14,20 @@ from typing import Optional
 import numpy as np
 
 from . import config, output, wireup
-from .elements import NRESULT, RESULT_WORDS
+from .elements import NRESULT, RESULT_WORDS, RESULT_WORDS_NOSTATS
 
 
 def result_words(m) -> int:
     """How many words of the 32-word result record the model's elements fill."""
-    return max((RESULT_WORDS.get(int(t), NRESULT) for t in np.unique(m.comp_type)), default=NRESULT)
+    table = RESULT_WORDS if m.stats_enabled else RESULT_WORDS_NOSTATS
+    return max((table.get(int(t), NRESULT) for t in _types_present(m)), default=NRESULT)
+
+
+def _types_present(m):
+    t = m.comp_type
+    if t.size and bool((t == t[0]).all()):  # the usual large model: one element type (np.unique would sort 16 M ids)
+        return [t[0]]
+    return np.unique(t)
 
 
 def simulate_model(m: wireup.WiredModel, device: int = 0, auto_tune: bool = True, **engine_opts):

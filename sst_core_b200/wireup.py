@@ -30,6 +30,23 @@ from .timelord import TimeLord
 NO_PEER = np.uint32(0xFFFFFFFF)
 
 
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array backed by page-locked host memory (a pinned torch byte tensor owns the storage)."""
+    import torch
+
+    dtype = np.dtype(dtype)
+    shape = tuple(int(v) for v in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    t = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+    return t.numpy()[:nbytes].view(dtype).reshape(shape)
+
+
+def pinned_like(a: np.ndarray) -> np.ndarray:
+    out = pinned_empty(a.shape, a.dtype)
+    np.copyto(out, a)
+    return out
+
+
 @dataclass
 class WiredModel:
     comp_type: np.ndarray
@@ -57,6 +74,14 @@ class WiredModel:
     @property
     def nport(self) -> int:
         return int(self.port_off[-1])
+
+    def pin(self) -> "WiredModel":
+        """Move the six model arrays into page-locked host memory (in place), so that ``sstb200_engine_create``'s
+        uploads run at PCIe speed instead of through the driver's pageable staging (2.2 GB for a 4096x4096 torus).
+        Needs a CUDA device; the arrays stay ordinary numpy arrays."""
+        for f in ("comp_type", "comp_param", "port_off", "peer_port", "latency", "clock_period"):
+            setattr(self, f, pinned_like(getattr(self, f)))
+        return self
 
     def min_latency(self) -> int:
         m = self.latency[self.peer_port != NO_PEER]
