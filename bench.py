@@ -66,6 +66,7 @@ class ClockSampler:
     def __init__(self, index=0):
         self.samples, self.stop_flag, self.index = [], threading.Event(), index
         self.max_mhz, self.reasons = None, set()
+        self.ready = threading.Event()  # set once the first sample has been taken
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
@@ -98,7 +99,8 @@ class ClockSampler:
                 for bit, name in self.REASONS.items():
                     if mask & bit:
                         self.reasons.add(name)
-                self.stop_flag.wait(0.005)
+                self.ready.set()
+                self.stop_flag.wait(0.002)
             return
         except Exception:
             pass
@@ -116,17 +118,20 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
+            self.ready.set()
             self.stop_flag.wait(0.1)
 
     def start(self):
         self.t.start()
-        time.sleep(0.02)  # let the sampler come up before the timed region starts
+        self.ready.wait(5.0)  # the sampler is up (NVML initialised, first sample taken) before the timed region starts
+        self.before = self.samples[-1] if self.samples else None
+        self.samples.clear()  # ... and only samples taken under load count
 
     def stop(self):
         self.stop_flag.set()
         self.t.join(timeout=6)
         sm = sorted(self.samples)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+        return {"sm_mhz": sm[len(sm) // 2] if sm else getattr(self, "before", None), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
@@ -277,7 +282,7 @@ def ours(a):
         wu = torch.zeros(world * 8, dtype=torch.int64, device=dev)
         dist.all_to_all_single(torch.empty_like(wu), wu)
         torch.cuda.synchronize(dev)
-    if not a.no_e2e and world == 1:
+    if not a.no_e2e:
         # process warm-up (CUDA context, lazy module load of the kernels, allocator): one tiny job of the same kind
         import copy
         aw = copy.copy(a)

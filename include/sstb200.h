@@ -78,6 +78,9 @@ typedef struct sstb200_options {
     void*    stream;          /* cudaStream_t to run on (NULL = engine-owned stream)                          */
     uint32_t parallel_max_events; /* event-parallel form: most events of one component per window (0 = default 100;
                                  blocks with a busier component run the sequential form; lower it to test that) */
+    uint32_t handler_counts;  /* non-zero: count deliveries per receiving port and clock-handler calls per component
+                                 (sst.profile.handler.event.count / .clock.count, profile/eventHandlerProfileTool.cc,
+                                 clockHandlerProfileTool.cc); read them with sstb200_engine_handler_counts          */
 } sstb200_options;
 
 int  sstb200_engine_create(const sstb200_model* model, const sstb200_options* opt, sstb200_engine** out);
@@ -136,6 +139,12 @@ int sstb200_engine_results(sstb200_engine* e, uint64_t* results, uint32_t words_
  * per-component delivery order; rows of one component are contiguous in `comp`-sorted order after this call.   */
 int sstb200_engine_trace(sstb200_engine* e, uint64_t* n_inout, uint64_t* time, uint32_t* comp, uint32_t* port,
                          uint64_t* payload);
+
+/* handler-count profile data of this rank (options.handler_counts): event_recv[local directed ports] = events
+ * delivered to the handler of each port (EventHandlerProfileToolCount::beforeHandler, eventHandlerProfileTool.cc:96-100),
+ * clock_calls[local components] = clock handler invocations (ClockHandlerProfileToolCount, clockHandlerProfileTool.cc:
+ * 76-86).  Either pointer may be NULL. */
+int sstb200_engine_handler_counts(sstb200_engine* e, uint64_t* event_recv, uint64_t* clock_calls);
 
 /* ---- SST::RNG streams on the device (rng/mersenne.cc, marsaglia.cc, xorshift.cc; BASELINE config 2) ----
  * kind: 0 mersenne(seed=s1), 1 marsaglia(z=s1,w=s2), 2 xorshift(seed=s1).

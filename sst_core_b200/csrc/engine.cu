@@ -139,6 +139,10 @@ struct Dev
     uint64_t*       tr_payload;
     uint64_t        trace_cap;
     int             stats_on, has_payload;
+    // handler-count profile tools (profile/eventHandlerProfileTool.cc:108-116, clockHandlerProfileTool.cc:89-97):
+    // deliveries per receiving port and clock-handler calls per component; null unless the option is set
+    unsigned long long* prof_recv;  // [nport_local]
+    unsigned long long* prof_clock; // [n_local]
 };
 
 // ================================================================================================ device side
@@ -641,6 +645,7 @@ dispatch_kernel(Dev d)
         }
         else {
             const uint32_t e = atomicAdd(&s_misc[0], 1u);
+            if ( d.prof_recv ) atomicAdd(&d.prof_recv[dst - d.P0], 1ull);
             if ( e < d.emax ) {
                 const uint32_t r = atomicAdd(&s_cnt[lo], 1u);
                 s_time[e]        = (uint32_t)(t - T);
@@ -961,6 +966,7 @@ dispatch_kernel(Dev d)
         *reinterpret_cast<uint4*>(&d.ctl[lc]) =
             make_uint4((uint32_t)next_tick, (uint32_t)(next_tick >> 32), ctx.seq, dseq);
         sent = ctx.sent;
+        if ( d.prof_clock && ticks ) d.prof_clock[lc] += ticks;
     }
     __syncthreads();
     PHASE_MARK(4);
@@ -1626,7 +1632,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     d.W       = o->calendar_slots >= 2 ? o->calendar_slots : 2;
     d.cap     = o->bin_capacity ? o->bin_capacity : 8 * BLOCK;
     if ( d.cap < BLOCK ) d.cap = BLOCK; // the dispatch prologue reads the first BLOCK slots of a bin unconditionally
-    d.emax    = o->smem_events ? o->smem_events : 8 * BLOCK;
+    d.emax    = o->smem_events ? o->smem_events : 5 * BLOCK; // 1280: three CTAs per SM also when events carry payloads
     if ( d.emax > 32768 ) d.emax = 32768;
     d.emax = (d.emax + 3u) & ~3u;
     d.stats_on = m->stats_enabled;
@@ -1807,6 +1813,10 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         rc |= e->alloc(&d.tr_port, d.trace_cap);
         rc |= e->alloc(&d.tr_idx, d.trace_cap);
         rc |= e->alloc(&d.tr_payload, d.trace_cap);
+    }
+    if ( o->handler_counts ) {
+        rc |= e->alloc(&d.prof_recv, d.nport_local);
+        rc |= e->alloc(&d.prof_clock, d.n_local);
     }
     rc |= e->alloc(&e->d_results, (size_t)d.n_local * NRESULT);
     lap("allocations + clears", e->stream);
@@ -2002,6 +2012,23 @@ sstb200_engine_results(sstb200_engine* e, uint64_t* results, uint32_t words_per_
     e->launches++;
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpyAsync(results, e->d_results, (size_t)e->d.n_local * words * 8, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int
+sstb200_engine_handler_counts(sstb200_engine* e, uint64_t* event_recv, uint64_t* clock_calls)
+{
+    if ( !e ) return -1;
+    if ( !e->d.prof_recv ) {
+        set_error("engine_handler_counts: the engine was created without options.handler_counts");
+        return -1;
+    }
+    CUDA_OK(cudaSetDevice(e->device));
+    if ( event_recv && e->d.nport_local )
+        CUDA_OK(cudaMemcpyAsync(event_recv, e->d.prof_recv, (size_t)e->d.nport_local * 8, cudaMemcpyDeviceToHost, e->stream));
+    if ( clock_calls && e->d.n_local )
+        CUDA_OK(cudaMemcpyAsync(clock_calls, e->d.prof_clock, (size_t)e->d.n_local * 8, cudaMemcpyDeviceToHost, e->stream));
     CUDA_OK(cudaStreamSynchronize(e->stream));
     return 0;
 }

@@ -38,7 +38,7 @@ class _Options(C.Structure):
                 ("comp_end", C.c_uint32), ("rank_comp_begin", C.c_void_p), ("calendar_slots", C.c_uint32),
                 ("bin_capacity", C.c_uint32), ("smem_events", C.c_uint32), ("outbox_capacity", C.c_uint32),
                 ("window", C.c_uint64), ("trace_capacity", C.c_uint64), ("stream", C.c_void_p),
-                ("parallel_max_events", C.c_uint32)]
+                ("parallel_max_events", C.c_uint32), ("handler_counts", C.c_uint32)]
 
 
 class _Status(C.Structure):
@@ -53,7 +53,8 @@ EXPORTS = [
     "sstb200_component_type_lookup", "sstb200_partition_linear", "sstb200_engine_create", "sstb200_engine_destroy",
     "sstb200_engine_setup", "sstb200_engine_run", "sstb200_engine_dispatch", "sstb200_engine_ingest",
     "sstb200_engine_advance", "sstb200_engine_exchange_buffers", "sstb200_engine_control_words",
-    "sstb200_engine_status", "sstb200_engine_results", "sstb200_engine_trace", "sstb200_rng_streams",
+    "sstb200_engine_status", "sstb200_engine_results", "sstb200_engine_trace", "sstb200_engine_handler_counts",
+    "sstb200_rng_streams",
     "sstb200_rng_ticks", "sstb200_rng_distribution",
 ]
 
@@ -88,6 +89,7 @@ def lib():
     L.sstb200_engine_results.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.sstb200_engine_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p]
+    L.sstb200_engine_handler_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sstb200_rng_streams.argtypes = [C.c_int, C.c_void_p, C.c_int] + [C.c_uint64] * 6 + [C.c_void_p, C.c_void_p]
     L.sstb200_rng_ticks.argtypes = [C.c_int, C.c_int] + [C.c_uint64] * 4 + [C.c_void_p]
     L.sstb200_rng_distribution.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
@@ -167,7 +169,9 @@ def partition_model(m: WiredModel, n_ranks: int) -> WiredModel:
         stats_enabled=m.stats_enabled, rank=rank[order], n_ranks=n_ranks, orig_id=order.astype(np.uint32),
         names=[m.names[i] for i in order] if m.names else None,
         stats=[m.stats[i] for i in order] if m.stats else None,
-        finish=[m.finish[i] for i in order] if m.finish else None, nocut_pairs=None, stat_output=m.stat_output)
+        finish=[m.finish[i] for i in order] if m.finish else None, nocut_pairs=None, stat_output=m.stat_output,
+        port_info=[m.port_info[int(i)] for i in old_ids] if m.port_info else None,
+        type_names=[m.type_names[i] for i in order] if m.type_names else None)
     out.validate()
     return out
 
@@ -203,7 +207,7 @@ class Engine:
 
     def __init__(self, model: WiredModel, device: int = 0, rank: int = 0, n_ranks: int = 1, calendar_slots: int = 2,
                  bin_capacity: int = 0, smem_events: int = 0, outbox_capacity: int = 0, window: int = 0,
-                 trace_capacity: int = 0, stream: int = 0, parallel_max_events: int = 0):
+                 trace_capacity: int = 0, stream: int = 0, parallel_max_events: int = 0, handler_counts: bool = False):
         L = lib()
         check_registry()
         self.model = model
@@ -224,7 +228,7 @@ class Engine:
             c0, c1 = 0, model.ncomp
         self.comp_begin, self.comp_end = c0, c1
         opt = _Options(device, rank, n_ranks, c0, c1, _p(self._begins), calendar_slots, bin_capacity, smem_events,
-                       outbox_capacity, window, trace_capacity, stream, parallel_max_events)
+                       outbox_capacity, window, trace_capacity, stream, parallel_max_events, int(bool(handler_counts)))
         h = C.c_void_p()
         _check(L.sstb200_engine_create(C.byref(cm), C.byref(opt), C.byref(h)), "engine_create")
         self._h = h
@@ -327,6 +331,16 @@ class Engine:
         out = np.zeros((n, NRESULT), dtype=np.uint64)
         out[:, :words] = part
         return out
+
+    def handler_counts(self):
+        """(event_recv [local directed ports], clock_calls [local components]) u64 -- the data of the reference's
+        ``sst.profile.handler.event.count`` / ``sst.profile.handler.clock.count`` tools (needs handler_counts=True)."""
+        m = self.model
+        np_local = int(m.port_off[self.comp_end]) - int(m.port_off[self.comp_begin])
+        recv = np.zeros(np_local, dtype=np.uint64)
+        clk = np.zeros(self.comp_end - self.comp_begin, dtype=np.uint64)
+        _check(self._L.sstb200_engine_handler_counts(self._h, _p(recv), _p(clk)), "engine_handler_counts")
+        return recv, clk
 
     def trace(self):
         n = C.c_uint64(0)

@@ -13,7 +13,7 @@ from typing import Optional
 
 import numpy as np
 
-from . import config, output, wireup
+from . import config, output, profile, wireup
 from .elements import NRESULT, RESULT_WORDS, RESULT_WORDS_NOSTATS
 
 
@@ -30,8 +30,10 @@ def _types_present(m):
     return np.unique(t)
 
 
-def simulate_model(m: wireup.WiredModel, device: int = 0, auto_tune: bool = True, **engine_opts):
-    """Run a WiredModel on one GPU.  Returns (results [ncomp,32] u64, Status).
+def simulate_model(m: wireup.WiredModel, device: int = 0, auto_tune: bool = True, extras: Optional[dict] = None,
+                   **engine_opts):
+    """Run a WiredModel on one GPU.  Returns (results [ncomp,32] u64, Status).  With ``handler_counts=True`` and an
+    ``extras`` dict, ``extras["handler_counts"]`` receives (deliveries per port, clock calls per component).
 
     The calendar geometry (window slots, bin and staging capacities) is a tuning choice; when a run reports that one of
     them overflowed and ``auto_tune`` is set, the run is repeated from the start with that resource doubled (an
@@ -56,10 +58,12 @@ def simulate_model(m: wireup.WiredModel, device: int = 0, auto_tune: bool = True
                     else:
                         opts["bin_capacity"] = 2 * (opts.get("bin_capacity", 0) or 2048)
                 else:  # shared-memory staging overflow
-                    opts["smem_events"] = min(2 * (opts.get("smem_events", 0) or 2048), 6144)
+                    opts["smem_events"] = min(2 * (opts.get("smem_events", 0) or 1280), 6144)
                     opts["bin_capacity"] = max(opts.get("bin_capacity", 0) or 2048, 2 * opts["smem_events"])
                 continue
             e.raise_on_error(st)
+            if extras is not None and opts.get("handler_counts"):
+                extras["handler_counts"] = e.handler_counts()
             return e.results(result_words(m)), st
         finally:
             e.close()
@@ -105,6 +109,9 @@ def main(argv: Optional[list] = None) -> int:
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--calendar-slots", type=int, default=0)
     ap.add_argument("--bin-capacity", type=int, default=0)
+    ap.add_argument("--enable-profiling", default="",
+                    help="name:type(key=value,...)[point,...];...  (handler count tools, see profile.py)")
+    ap.add_argument("--profiling-output", default="", help="file for the profiling records (default: stdout)")
     a = ap.parse_args(argv)
     if a.partitioner not in ("sst.linear", "linear"):
         print(f"FATAL: partitioner {a.partitioner} is not supported (only sst.linear)", file=sys.stderr)
@@ -117,6 +124,7 @@ def main(argv: Optional[list] = None) -> int:
         if a.timebase:
             g.program_options["timebase"] = a.timebase
         m = wireup.wire(g, stop_at_override=a.stop_at)
+        tools = profile.parse_enable_profiling(a.enable_profiling) if a.enable_profiling else []
     except config.ModelError as ex:
         print(f"FATAL: {ex}", file=sys.stderr)
         return 1
@@ -125,9 +133,20 @@ def main(argv: Optional[list] = None) -> int:
         opts["calendar_slots"] = a.calendar_slots
     if a.bin_capacity:
         opts["bin_capacity"] = a.bin_capacity
-    res, st = simulate_model(m, device=a.device, **opts)
+    extras = {}
+    if tools:
+        opts["handler_counts"] = True
+    res, st = simulate_model(m, device=a.device, extras=extras, **opts)
     for line in output.finish_lines(m, res, st.end_time):
         print(line)
+    if tools:
+        recv, calls = extras["handler_counts"]
+        text = profile.profiling_text(m, tools, recv, calls, st.end_time, os.path.abspath(a.script))
+        if a.profiling_output:
+            with open(os.path.join(a.output_directory, a.profiling_output), "w") as f:
+                f.write(text)
+        else:
+            sys.stdout.write(text)
     if m.stat_output[0] == "sst.statOutputConsole":
         for line in output.stat_lines_console(m, res):
             print(line)

@@ -66,6 +66,10 @@ class WiredModel:
     finish: Optional[list] = None
     nocut_pairs: Optional[np.ndarray] = None  # [k,2] component pairs joined by no-cut links
     stat_output: tuple = ("sst.statOutputConsole", {})
+    # per directed port: (full name of the (sub)component that configured the link, its ELI type, port name) -- the
+    # handler metadata the reference hands to profile tools (baseComponent.cc:593-600); None for unwired ports
+    port_info: Optional[list] = None
+    type_names: Optional[List[str]] = None  # ELI type of every top-level component
 
     @property
     def ncomp(self) -> int:
@@ -157,6 +161,9 @@ def wire(graph: ConfigGraph, stop_at_override: Optional[str] = None) -> WiredMod
         stats=[w.stats for w in wired], finish=[w.finish for w in wired],
         nocut_pairs=np.array(nocut, dtype=np.uint32).reshape(-1, 2),
         stat_output=graph.stat_output,
+        port_info=[(owner.full_name(), owner.type, pname) if pname is not None else None
+                   for w in wired for owner, pname in w.ports],
+        type_names=[c.type for c in graph.components],
     )
     m.validate()
     return m

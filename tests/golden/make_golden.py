@@ -111,6 +111,27 @@ def main():
         out["mesh_2x2_console_stats"] = {
             "source": "sstsim.x test_MessageMesh.py (statOutputConsole) '2 2 1 1 1 1' --stop-at 30ns",
             "lines": [l for l in txt.splitlines() if " : Accumulator : " in l]}
+    # handler-count profile tools: the reference's own goldens (4x4 mesh, 10 us) and runs of the reference binary
+    for lvl in ("global", "type", "component", "subcomponent"):
+        out[f"profiling_4x4_event_{lvl}"] = {
+            "source": f"tests/refFiles/test_Profiling_event_{lvl}.out",
+            "text": (REF_TESTS / f"refFiles/test_Profiling_event_{lvl}.out").read_text()}
+    with tempfile.TemporaryDirectory() as td:
+        spec = ("events:sst.profile.handler.event.count(level=component)[event];"
+                "clocks:sst.profile.handler.clock.count(level=component)[clock]")
+        O.run_ref(MODELS / "clockpop.py", "3 2 200ns 10", extra=["--profiling-output=p.txt", "--enable-profiling=" + spec],
+                  cwd=td)
+        out["profiling_clockpop_3x2_200ns"] = {"source": f"sstsim.x clockpop.py '3 2 200ns 10' --enable-profiling={spec}",
+                                               "spec": spec, "text": (Path(td) / "p.txt").read_text()}
+        spec = "ev:sst.profile.handler.event.count(level=subcomponent,track_ports=true)[event]"
+        O.run_ref(REF_TESTS / "test_MessageMesh.py", "3 2", extra=["--stop-at", "50ns", "--profiling-output=q.txt",
+                                                                  "--enable-profiling=" + spec], cwd=td)
+        out["profiling_mesh_3x2_50ns_ports"] = {"source": f"sstsim.x test_MessageMesh.py '3 2' --stop-at 50ns --enable-profiling={spec}",
+                                                "spec": spec, "text": (Path(td) / "q.txt").read_text()}
+        spec = "t:sst.profile.handler.clock.count(level=type)[clock];g:sst.profile.handler.event.count(level=type)[event]"
+        O.run_ref(MODELS / "phold.py", "4 3 60ns", extra=["--profiling-output=r.txt", "--enable-profiling=" + spec], cwd=td)
+        out["profiling_phold_4x3_60ns_type"] = {"source": f"sstsim.x phold.py '4 3 60ns' --enable-profiling={spec}",
+                                                "spec": spec, "text": (Path(td) / "r.txt").read_text()}
     (HERE / "reference_golden.json").write_text(json.dumps(out, indent=1, sort_keys=True))
     print("wrote", HERE / "reference_golden.json", (HERE / "reference_golden.json").stat().st_size, "bytes")
 

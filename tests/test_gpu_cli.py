@@ -57,3 +57,47 @@ def test_auto_tuning_retries_after_a_reported_overflow():
     res, st = simulate_model(m, calendar_slots=2, bin_capacity=1024, smem_events=1024)  # overflows at first
     ref = O.run_model(m)
     assert __import__("numpy").array_equal(res, ref.results) and st.events_delivered == ref.events
+
+
+def _comparable(text):
+    return sorted(l for l in text.splitlines() if not l.startswith("  Simulation Input File"))
+
+
+@pytest.mark.parametrize("level", ["global", "type", "component", "subcomponent"])
+def test_cli_event_handler_counts_match_the_reference_profiling_goldens(tmp_path, level):
+    """testsuite_default_profiling.py:36-80 pointed at the device engine: counters kept by dispatch_kernel."""
+    _run(["--model-options", "4 4", "--profiling-output", f"prof_{level}.txt", "--enable-profiling",
+          f"events:sst.profile.handler.event.count(level={level})[event]", str(ROOT / "tests/models/mesh.py")], tmp_path)
+    got = (tmp_path / f"prof_{level}.txt").read_text()
+    assert _comparable(got) == _comparable(GOLD[f"profiling_4x4_event_{level}"]["text"])
+
+
+@pytest.mark.parametrize("key,script,opts,extra", [
+    ("profiling_clockpop_3x2_200ns", "clockpop.py", "3 2 200ns 10", []),
+    ("profiling_mesh_3x2_50ns_ports", "mesh.py", "3 2", ["--stop-at", "50ns"]),
+    ("profiling_phold_4x3_60ns_type", "phold.py", "4 3 60ns", []),
+])
+def test_cli_handler_counts_match_reference_binary_runs(tmp_path, key, script, opts, extra):
+    _run(["--model-options", opts, "--profiling-output", "p.txt", "--enable-profiling", GOLD[key]["spec"], *extra,
+          str(ROOT / "tests/models" / script)], tmp_path)
+    assert _comparable((tmp_path / "p.txt").read_text()) == _comparable(GOLD[key]["text"])
+
+
+def test_handler_counts_sum_to_the_delivered_events_on_a_large_mesh():
+    """size-independent property at a size the oracle does not reach quickly: per-port counts add up to the number of
+    deliveries, per component they equal the element's own receive counter (event-parallel and sequential forms)"""
+    import numpy as np
+    from sst_core_b200 import models
+    from sst_core_b200.engine import Engine
+    m = models.mesh_model(512, 512, stop_at="30ns", verbose=0)
+    for par_max in (0, 2):
+        e = Engine(m, handler_counts=True, parallel_max_events=par_max)
+        e.setup()
+        e.run()
+        st = e.status()
+        e.raise_on_error(st)
+        recv, calls = e.handler_counts()
+        res = e.results(1, compact=True)
+        e.close()
+        assert int(recv.sum()) == st.events_delivered and int(calls.sum()) == 0
+        assert np.array_equal(recv.reshape(-1, 4).sum(axis=1), res[:, 0])
