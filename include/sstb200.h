@@ -140,6 +140,17 @@ int sstb200_engine_results(sstb200_engine* e, uint64_t* results, uint32_t words_
 int sstb200_engine_trace(sstb200_engine* e, uint64_t* n_inout, uint64_t* time, uint32_t* comp, uint32_t* port,
                          uint64_t* payload);
 
+/* ---- checkpoint / restart (Simulation::checkpoint simulation.cc:2015-2071, restart :2073-2200; CheckpointAction) ----
+ * The blob holds this rank's complete simulation state between two windows: engine control block, per-component
+ * control blocks and element state (RNGs, statistics), the event calendar, exchange buffers, handler counters.
+ * save:  after engine_setup, between windows (after engine_run returned / after engine_advance).
+ * load:  into an engine created from the SAME model slice with the same calendar_slots, bin_capacity, window, ranks
+ *        and handler_counts setting, INSTEAD of engine_setup; the run then continues bit-identically.
+ * A restart on a different number of ranks needs the records re-binned and is not provided. */
+int sstb200_engine_checkpoint_size(sstb200_engine* e, uint64_t* bytes);
+int sstb200_engine_checkpoint_save(sstb200_engine* e, void* blob_host, uint64_t bytes);
+int sstb200_engine_checkpoint_load(sstb200_engine* e, const void* blob_host, uint64_t bytes);
+
 /* handler-count profile data of this rank (options.handler_counts): event_recv[local directed ports] = events
  * delivered to the handler of each port (EventHandlerProfileToolCount::beforeHandler, eventHandlerProfileTool.cc:96-100),
  * clock_calls[local components] = clock handler invocations (ClockHandlerProfileToolCount, clockHandlerProfileTool.cc:

@@ -1437,6 +1437,18 @@ struct sstb200_engine
     uint64_t           launches    = 0;
     bool               is_setup    = false;
     uint32_t           n_ranks     = 1;
+    // device buffers that make up the simulation state (checkpoint sections, in a fixed order)
+    struct Section
+    {
+        void*  ptr;
+        size_t bytes;
+    };
+    std::vector<Section> sections;
+    template <class T>
+    void section(T* p, size_t count)
+    {
+        if ( p ) sections.push_back(Section { (void*)p, count * sizeof(T) });
+    }
 
     template <class T>
     int alloc(T** p, size_t count, bool zero = true)
@@ -1824,6 +1836,22 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         sstb200_engine_destroy(e);
         return -2;
     }
+    // everything a checkpoint has to carry (Simulation::checkpoint simulation.cc:2015-2071 serialises the same things:
+    // component state, the TimeVortex contents, clocks, statistics, sync queues)
+    e->section(d.ctrl, 1);
+    e->section(d.ctl, d.n_local);
+    e->section(d.state, (size_t)d.n_local * d.state_stride);
+    e->section(d.aux, (size_t)d.n_local * d.aux_stride);
+    e->section(d.bin_count, (size_t)d.W * d.nbins);
+    e->section(d.ev, nev);
+    e->section(d.ev_payload, has_payload ? nev : 0);
+    if ( n_ranks > 1 ) {
+        e->section(d.outbox, (size_t)n_ranks * d.xwords);
+        e->section(d.inbox, (size_t)n_ranks * d.xwords);
+        e->section(d.gathered, (size_t)n_ranks * CW_WORDS);
+    }
+    e->section(d.prof_recv, d.nport_local);
+    e->section(d.prof_clock, d.n_local);
     CUDA_OK(cudaMallocHost((void**)&e->h_ctrl, sizeof(Ctrl)));
     memset(e->h_ctrl, 0, sizeof(Ctrl));
     e->h_ctrl->w       = w;
@@ -2013,6 +2041,102 @@ sstb200_engine_results(sstb200_engine* e, uint64_t* results, uint32_t words_per_
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpyAsync(results, e->d_results, (size_t)e->d.n_local * words * 8, cudaMemcpyDeviceToHost, e->stream));
     CUDA_OK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// ---- checkpoint / restart of the device state.  Blob layout (u64 words unless noted):
+//   [0] magic "SSTB200C"  [1] ABI version  [2] number of sections  [3..14] geometry: n_local, nport_local, c0, P0, W,
+//   cap, state_stride, aux_stride, has_payload, n_ranks, rank, window;  then per section: byte count, bytes (padded to 8)
+namespace {
+constexpr uint64_t CKPT_MAGIC = 0x4330303242545353ull; // "SSTB200C" little-endian
+constexpr int      CKPT_HDR   = 15;
+void
+ckpt_geometry(const sstb200_engine* e, uint64_t* g)
+{
+    const Dev& d = e->d;
+    const uint64_t v[12] = { d.n_local, d.nport_local, d.c0, d.P0, d.W, d.cap, d.state_stride, d.aux_stride,
+                             (uint64_t)d.has_payload, d.n_ranks, d.rank, e->h_ctrl->w };
+    memcpy(g, v, sizeof v);
+}
+} // namespace
+
+int
+sstb200_engine_checkpoint_size(sstb200_engine* e, uint64_t* bytes)
+{
+    if ( !e || !bytes ) return -1;
+    uint64_t n = CKPT_HDR * 8;
+    for ( const auto& sec : e->sections )
+        n += 8 + ((sec.bytes + 7) & ~(size_t)7);
+    *bytes = n;
+    return 0;
+}
+
+int
+sstb200_engine_checkpoint_save(sstb200_engine* e, void* blob, uint64_t bytes)
+{
+    if ( !e || !blob ) return -1;
+    uint64_t need = 0;
+    sstb200_engine_checkpoint_size(e, &need);
+    if ( bytes < need ) {
+        set_error("checkpoint_save: buffer too small (" + std::to_string(bytes) + " < " + std::to_string(need) + ")");
+        return -1;
+    }
+    if ( !e->is_setup ) {
+        set_error("checkpoint_save before engine_setup");
+        return -1;
+    }
+    if ( e->d.trace_cap ) {
+        set_error("checkpoint_save: delivery tracing and checkpoints cannot be combined");
+        return -1;
+    }
+    CUDA_OK(cudaSetDevice(e->device));
+    uint64_t* h = (uint64_t*)blob;
+    h[0]        = CKPT_MAGIC;
+    h[1]        = SSTB200_ABI_VERSION;
+    h[2]        = e->sections.size();
+    ckpt_geometry(e, h + 3);
+    uint8_t* p = (uint8_t*)blob + CKPT_HDR * 8;
+    for ( const auto& sec : e->sections ) {
+        *(uint64_t*)p = sec.bytes;
+        p += 8;
+        if ( sec.bytes ) CUDA_OK(cudaMemcpyAsync(p, sec.ptr, sec.bytes, cudaMemcpyDeviceToHost, e->stream));
+        p += (sec.bytes + 7) & ~(size_t)7;
+    }
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int
+sstb200_engine_checkpoint_load(sstb200_engine* e, const void* blob, uint64_t bytes)
+{
+    if ( !e || !blob ) return -1;
+    uint64_t need = 0;
+    sstb200_engine_checkpoint_size(e, &need);
+    const uint64_t* h = (const uint64_t*)blob;
+    if ( bytes < CKPT_HDR * 8 || h[0] != CKPT_MAGIC ) {
+        set_error("checkpoint_load: not a checkpoint of this engine");
+        return -1;
+    }
+    uint64_t g[12];
+    ckpt_geometry(e, g);
+    if ( h[1] != SSTB200_ABI_VERSION || h[2] != e->sections.size() || memcmp(h + 3, g, sizeof g) != 0 || bytes < need ) {
+        set_error("checkpoint_load: the checkpoint was written by an engine with a different model slice or calendar "
+                  "geometry (components, ports, calendar_slots, bin_capacity, window, ranks and options must match)");
+        return -1;
+    }
+    CUDA_OK(cudaSetDevice(e->device));
+    const uint8_t* p = (const uint8_t*)blob + CKPT_HDR * 8;
+    for ( const auto& sec : e->sections ) {
+        if ( *(const uint64_t*)p != sec.bytes ) {
+            set_error("checkpoint_load: section size mismatch");
+            return -1;
+        }
+        p += 8;
+        if ( sec.bytes ) CUDA_OK(cudaMemcpyAsync(sec.ptr, p, sec.bytes, cudaMemcpyHostToDevice, e->stream));
+        p += (sec.bytes + 7) & ~(size_t)7;
+    }
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    e->is_setup = true; // the restored state replaces construct + setup()
     return 0;
 }
 

@@ -54,6 +54,7 @@ EXPORTS = [
     "sstb200_engine_setup", "sstb200_engine_run", "sstb200_engine_dispatch", "sstb200_engine_ingest",
     "sstb200_engine_advance", "sstb200_engine_exchange_buffers", "sstb200_engine_control_words",
     "sstb200_engine_status", "sstb200_engine_results", "sstb200_engine_trace", "sstb200_engine_handler_counts",
+    "sstb200_engine_checkpoint_size", "sstb200_engine_checkpoint_save", "sstb200_engine_checkpoint_load",
     "sstb200_rng_streams",
     "sstb200_rng_ticks", "sstb200_rng_distribution",
 ]
@@ -90,6 +91,9 @@ def lib():
     L.sstb200_engine_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p]
     L.sstb200_engine_handler_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sstb200_engine_checkpoint_size.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.sstb200_engine_checkpoint_save.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.sstb200_engine_checkpoint_load.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.sstb200_rng_streams.argtypes = [C.c_int, C.c_void_p, C.c_int] + [C.c_uint64] * 6 + [C.c_void_p, C.c_void_p]
     L.sstb200_rng_ticks.argtypes = [C.c_int, C.c_int] + [C.c_uint64] * 4 + [C.c_void_p]
     L.sstb200_rng_distribution.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
@@ -234,6 +238,7 @@ class Engine:
         self._h = h
         self._L = L
         self.device = device
+        self._window = window
 
     def close(self):
         if getattr(self, "_h", None):
@@ -331,6 +336,33 @@ class Engine:
         out = np.zeros((n, NRESULT), dtype=np.uint64)
         out[:, :words] = part
         return out
+
+    def window(self) -> int:
+        """Lookahead window in cycles (the option, else the model's minimum link latency)."""
+        if not getattr(self, "_window", 0):
+            self._window = self.model.min_latency() or 1000000
+        return self._window
+
+    def checkpoint(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """This rank's complete simulation state between two windows as a uint8 array (``out``: a caller-owned,
+        e.g. pinned, buffer of at least ``checkpoint_size()`` bytes)."""
+        n = self.checkpoint_size()
+        blob = out if out is not None else np.empty(n, dtype=np.uint8)
+        if blob.dtype != np.uint8 or blob.size < n or not blob.flags.c_contiguous:
+            raise ValueError(f"checkpoint(out=): need a C-contiguous uint8 array of at least {n} bytes")
+        _check(self._L.sstb200_engine_checkpoint_save(self._h, _p(blob), blob.size), "engine_checkpoint_save")
+        return blob[:n]
+
+    def checkpoint_size(self) -> int:
+        n = C.c_uint64(0)
+        _check(self._L.sstb200_engine_checkpoint_size(self._h, C.byref(n)), "engine_checkpoint_size")
+        return int(n.value)
+
+    def restore(self, blob: np.ndarray):
+        """Load a checkpoint written by an engine with the same model slice and calendar geometry; call it INSTEAD of
+        setup().  The run continues bit-identically to the one that wrote the checkpoint."""
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        _check(self._L.sstb200_engine_checkpoint_load(self._h, _p(blob), blob.size), "engine_checkpoint_load")
 
     def handler_counts(self):
         """(event_recv [local directed ports], clock_calls [local components]) u64 -- the data of the reference's

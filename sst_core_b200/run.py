@@ -13,7 +13,7 @@ from typing import Optional
 
 import numpy as np
 
-from . import config, output, profile, wireup
+from . import checkpoint, config, output, profile, wireup
 from .elements import NRESULT, RESULT_WORDS, RESULT_WORDS_NOSTATS
 
 
@@ -31,9 +31,11 @@ def _types_present(m):
 
 
 def simulate_model(m: wireup.WiredModel, device: int = 0, auto_tune: bool = True, extras: Optional[dict] = None,
-                   **engine_opts):
+                   checkpoint_period: int = 0, checkpoint_writer=None, restore_blob=None, **engine_opts):
     """Run a WiredModel on one GPU.  Returns (results [ncomp,32] u64, Status).  With ``handler_counts=True`` and an
     ``extras`` dict, ``extras["handler_counts"]`` receives (deliveries per port, clock calls per component).
+    ``checkpoint_period`` (cycles) + ``checkpoint_writer`` (checkpoint.CheckpointWriter): write a checkpoint every
+    period of simulated time; ``restore_blob``: continue from a checkpoint instead of running setup().
 
     The calendar geometry (window slots, bin and staging capacities) is a tuning choice; when a run reports that one of
     them overflowed and ``auto_tune`` is set, the run is repeated from the start with that resource doubled (an
@@ -44,14 +46,22 @@ def simulate_model(m: wireup.WiredModel, device: int = 0, auto_tune: bool = True
     for attempt in range(10):
         e = Engine(m, device=device, **opts)
         try:
-            e.setup()
+            if restore_blob is not None:
+                e.restore(restore_blob)
+            else:
+                e.setup()
             try:
-                e.run()
+                if checkpoint_period:
+                    if checkpoint_writer is not None:
+                        checkpoint_writer.next_id = 1 if restore_blob is None else checkpoint_writer.next_id
+                    checkpoint.run_with_checkpoints(e, checkpoint_period, checkpoint_writer, opts)
+                else:
+                    e.run()
             except EngineError:
                 if not e.status().error:
                     raise
             st = e.status()
-            if st.error in (1, 2) and auto_tune and attempt < 9:
+            if st.error in (1, 2) and auto_tune and attempt < 9 and restore_blob is None:
                 if st.error == 1:  # calendar bin overflow: more slots first (events spread over more bins), then bigger bins
                     if opts.get("calendar_slots", 2) < 16:
                         opts["calendar_slots"] = 2 * opts.get("calendar_slots", 2)
@@ -109,6 +119,11 @@ def main(argv: Optional[list] = None) -> int:
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--calendar-slots", type=int, default=0)
     ap.add_argument("--bin-capacity", type=int, default=0)
+    ap.add_argument("--checkpoint-sim-period", "--checkpoint-period", default="", metavar="PERIOD",
+                    help="write a checkpoint every PERIOD of simulated time (e.g. 100ns)")
+    ap.add_argument("--checkpoint-prefix", default="checkpoint")
+    ap.add_argument("--load-checkpoint", action="store_true",
+                    help="the input file is a checkpoint registry (*.sstcpt): restart from it")
     ap.add_argument("--enable-profiling", default="",
                     help="name:type(key=value,...)[point,...];...  (handler count tools, see profile.py)")
     ap.add_argument("--profiling-output", default="", help="file for the profiling records (default: stdout)")
@@ -116,7 +131,15 @@ def main(argv: Optional[list] = None) -> int:
     if a.partitioner not in ("sst.linear", "linear"):
         print(f"FATAL: partitioner {a.partitioner} is not supported (only sst.linear)", file=sys.stderr)
         return 1
+    reg = None
     try:
+        if a.load_checkpoint:
+            # simulation.cc:2073-2200: the run's configuration comes from the checkpoint, not from the command line
+            reg = checkpoint.load_registry(a.script)
+            rec = reg["recipe"]
+            a.script, a.model_options, a.stop_at, a.timebase = (rec["script"], rec["model_options"], rec["stop_at"],
+                                                                rec["timebase"])
+            a.enable_profiling = a.enable_profiling or rec.get("enable_profiling", "")
         if a.script.endswith(".json"):
             g = config.load_json(a.script)
         else:
@@ -124,6 +147,8 @@ def main(argv: Optional[list] = None) -> int:
         if a.timebase:
             g.program_options["timebase"] = a.timebase
         m = wireup.wire(g, stop_at_override=a.stop_at)
+        if reg is not None and checkpoint.model_fingerprint(m) != reg["model_fingerprint"]:
+            raise config.ModelError(f"the model rebuilt from {a.script} is not the one the checkpoint was taken from")
         tools = profile.parse_enable_profiling(a.enable_profiling) if a.enable_profiling else []
     except config.ModelError as ex:
         print(f"FATAL: {ex}", file=sys.stderr)
@@ -136,7 +161,19 @@ def main(argv: Optional[list] = None) -> int:
     extras = {}
     if tools:
         opts["handler_counts"] = True
-    res, st = simulate_model(m, device=a.device, extras=extras, **opts)
+    ckpt = {}
+    if reg is not None:
+        opts = dict(reg["engine_opts"])
+        ckpt["restore_blob"] = checkpoint.read_partition(reg, 0)
+    if a.checkpoint_sim_period:
+        from .timelord import TimeLord
+        recipe = {"script": os.path.abspath(a.script), "model_options": a.model_options, "stop_at": a.stop_at,
+                  "timebase": a.timebase, "enable_profiling": a.enable_profiling}
+        ckpt["checkpoint_period"] = TimeLord(m.timebase).cycles(a.checkpoint_sim_period)
+        ckpt["checkpoint_writer"] = checkpoint.CheckpointWriter(a.output_directory, a.checkpoint_prefix, recipe, m)
+        if reg is not None:
+            ckpt["checkpoint_writer"].next_id = reg["checkpoint_id"] + 1
+    res, st = simulate_model(m, device=a.device, extras=extras, **ckpt, **opts)
     for line in output.finish_lines(m, res, st.end_time):
         print(line)
     if tools:
