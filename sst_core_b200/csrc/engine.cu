@@ -111,6 +111,10 @@ struct Dev
     uint32_t        any_parallel;         // some local element type has an event-parallel handler
     uint32_t        ties_free;            // every local element type declares events of equal time interchangeable
     uint32_t        par_max;              // most events of one component per window the event-parallel form takes
+    // the per-component control blocks are neither read nor written by dispatch_kernel when nothing in them can
+    // matter: no local component has a clock, one local element type, no tracing, and EVERY element type of the model
+    // (any rank) treats events of equal time as interchangeable, so nobody ever looks at a send sequence number
+    uint32_t        ctl_free;
     uint32_t        P0, nport_local;
     uint32_t        rank, n_ranks;
     const uint32_t* rank_comp_begin; // [n_ranks+1] (device)
@@ -581,7 +585,8 @@ dispatch_kernel(Dev d)
         //   .w  bit 0: a clock tick is due in this window; later: extra staged word of the element
         uint4 hdr = make_uint4(0xFFFFFFFFu, 0, 0, 0);
         if ( lc0 < d.n_local ) {
-            const uint4 c_lo0 = *reinterpret_cast<const uint4*>(&d.ctl[lc0]); // next_tick, send_seq, deliv_seq
+            uint4 c_lo0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0); // next_tick, send_seq, deliv_seq
+            if ( !d.ctl_free ) c_lo0 = *reinterpret_cast<const uint4*>(&d.ctl[lc0]);
             // element hook: probe the state for the event-parallel form and start pulling the aux words the
             // handlers will touch towards L2
             with_element(d.uniform_type ? d.uniform_type : d.comp_type[lc0], [&](auto el) {
@@ -760,7 +765,7 @@ dispatch_kernel(Dev d)
     const uint16_t* seg    = s_ordered + s_off[c];
     uint32_t        delivered = 0, ticks = 0, sent = 0, clocks_stopped = 0;
     uint4           c_lo = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0), c_hi = make_uint4(0, 0, 0, 0);
-    if ( valid ) {
+    if ( valid && !d.ctl_free ) {
         const uint4* ctlp = reinterpret_cast<const uint4*>(&d.ctl[lc]);
         c_lo              = ctlp[0];
         c_hi              = ctlp[1];
@@ -838,7 +843,8 @@ dispatch_kernel(Dev d)
                     const uint32_t nsend = pcnt * E::PARALLEL_SENDS_PER_EVENT;
                     uint32_t*      ctlw  = reinterpret_cast<uint32_t*>(&d.ctl[plc]);
                     const uint4    h     = s_hdr[pc_];
-                    *reinterpret_cast<uint2*>(ctlw + 2) = make_uint2(h.y + nsend, h.z + (d.trace_cap ? pcnt : 0));
+                    if ( !d.ctl_free )
+                        *reinterpret_cast<uint2*>(ctlw + 2) = make_uint2(h.y + nsend, h.z + (d.trace_cap ? pcnt : 0));
                     delivered = pcnt;
                     sent      = nsend;
                 }
@@ -963,8 +969,9 @@ dispatch_kernel(Dev d)
                 store_state(mem, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
             }
         });
-        *reinterpret_cast<uint4*>(&d.ctl[lc]) =
-            make_uint4((uint32_t)next_tick, (uint32_t)(next_tick >> 32), ctx.seq, dseq);
+        if ( !d.ctl_free )
+            *reinterpret_cast<uint4*>(&d.ctl[lc]) =
+                make_uint4((uint32_t)next_tick, (uint32_t)(next_tick >> 32), ctx.seq, dseq);
         sent = ctx.sent;
         if ( d.prof_clock && ticks ) d.prof_clock[lc] += ticks;
     }
@@ -1623,7 +1630,13 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         fprintf(stderr, "[sstb200 create] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_prev).count());
         t_prev = t;
     };
-    if ( const char* g = getenv("SSTB200_L2_FETCH") ) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+    if ( const char* g = getenv("SSTB200_L2_FETCH") ) { // experiment knob: the L2's DRAM fetch granularity hint
+        size_t            before = 0, after = 0;
+        cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+        const cudaError_t rc = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+        cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "[sstb200] L2 fetch granularity %zu -> %zu (%s)\n", before, after, cudaGetErrorString(rc));
+    }
     sstb200_engine* e = new sstb200_engine();
     e->device         = o->device;
     e->n_ranks        = n_ranks;
@@ -1704,7 +1717,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     struct Part
     {
         uint32_t seen_all = 0, seen_local = 0, bad = 0xFFFFFFFFu, max_blk = 0;
-        bool     uni_ok = true;
+        bool     uni_ok = true, clocks = false;
     } part[16];
     const uint32_t uni0 = d.n_local ? m->port_off[c0 + 1] - m->port_off[c0] : 0;
     scan(m->ncomp, [&](size_t lo, size_t hi, unsigned t) {
@@ -1719,6 +1732,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
             if ( c >= c0 && c < c1 ) {
                 q.seen_local |= 1u << ty;
                 if ( m->port_off[c + 1] - m->port_off[c] != uni0 ) q.uni_ok = false;
+                if ( m->clock_period[c] ) q.clocks = true;
             }
         }
         part[t] = q;
@@ -1732,8 +1746,9 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         part[t].max_blk = std::max(part[t].max_blk, mx);
     });
     uint32_t seen_all = 0, seen_local = 0, bad = 0xFFFFFFFFu, max_blk = 0;
-    bool     uni_ok = true;
+    bool     uni_ok = true, any_clock = false;
     for ( const Part& q : part ) {
+        any_clock = any_clock || q.clocks;
         seen_all |= q.seen_all;
         seen_local |= q.seen_local;
         bad     = std::min(bad, q.bad);
@@ -1762,6 +1777,10 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         if ( !ei->ties_interchangeable ) d.ties_free = 0;
         if ( (seen_local & (seen_local - 1)) == 0 ) d.uniform_type = ty; // the only type on this rank
     }
+    bool ties_free_model = true;
+    for ( uint32_t ty = 0; ty < TYPE_MAX; ++ty )
+        if ( (seen_all >> ty & 1u) && by_type[ty] && !by_type[ty]->ties_interchangeable ) ties_free_model = false;
+    d.ctl_free = (!any_clock && d.uniform_type && ties_free_model && o->trace_capacity == 0) ? 1u : 0u;
     d.par_max = (o->parallel_max_events && o->parallel_max_events < PAR_MAX_EVENTS) ? o->parallel_max_events : PAR_MAX_EVENTS;
     {
         const uint32_t uni = uni_ok ? uni0 : 0;
