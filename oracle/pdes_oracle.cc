@@ -199,7 +199,7 @@ struct Accumulator
 // ------------------------------------------------------------------------------------------------ engine
 enum : uint64_t { PRIO_STOP = 30, PRIO_CLOCK = 40, PRIO_EVENT = 50, PRIO_EXIT = 99 };
 enum { KIND_EVENT, KIND_CLOCK, KIND_STOP, KIND_EXIT };
-enum { TYPE_MESH = 1, TYPE_PHOLD = 2, TYPE_CLOCKNODE = 3, TYPE_RNGCOMP = 4 };
+enum { TYPE_MESH = 1, TYPE_PHOLD = 2, TYPE_CLOCKNODE = 3, TYPE_RNGCOMP = 4, TYPE_CORETEST = 5 };
 constexpr int      NPARAM   = 8;
 constexpr int      NRESULT  = 32;
 constexpr uint32_t NO_PEER  = 0xFFFFFFFFu;
@@ -494,6 +494,41 @@ struct ClockNodeComp : Component
     }
 };
 
+// testElements/coreTest_Component.cc:25-173 (tests/test_Component.py): MarsagliaRNG(11, 272727) in every component;
+// ctor :52-53 neighbor = generateNextInt32() % 4 (a C++ int: may start negative); clockTic :114-165 draws
+// generateNextInt32() % commFreq, on 0 advances neighbor = (neighbor + 1) % 4 and sends on N/S/E/W = 0/1/2/3 with
+// countX->addData(1), any other value prints "bad neighbor" and sends nothing; handleEvent :87-101 only touches the
+// payload it then deletes.
+struct CoreTestComp : Component
+{
+    int32_t          commFreq;
+    int32_t          neighbor;
+    uint64_t         bad = 0;
+    Marsaglia        rng;
+    Accumulator<int> count[4];
+    CoreTestComp(const int64_t* p) : commFreq((int32_t)p[1]), rng(11u, 272727u) { neighbor = rng.i32() % 4; }
+    bool tick(uint64_t) override
+    {
+        if ( (rng.i32() % commFreq) == 0 ) {
+            neighbor = (neighbor + 1) % 4;
+            if ( neighbor >= 0 ) {
+                send(neighbor, 0, 0);
+                if ( sim->stats_on ) count[neighbor].add(1);
+            }
+            else
+                bad++;
+        }
+        return false;
+    }
+    void handleEvent(int, uint64_t&) override {}
+    void results(uint64_t* r) const override
+    {
+        r[0] = bad;
+        for ( int i = 0; i < 4; ++i )
+            count[i].out(r + 4 + 5 * i);
+    }
+};
+
 // testElements/coreTest_RNGComponent.cc:26-109
 struct RngComp : Component
 {
@@ -575,6 +610,9 @@ oracle_create(uint32_t ncomp, const uint32_t* comp_type, const int64_t* comp_par
             break;
         case TYPE_RNGCOMP:
             k = new RngComp(p);
+            break;
+        case TYPE_CORETEST:
+            k = new CoreTestComp(p);
             break;
         default:
             delete s;

@@ -33,7 +33,7 @@
 
 namespace sstb200 {
 
-enum : uint32_t { TYPE_MESH = 1, TYPE_PHOLD = 2, TYPE_CLOCKNODE = 3, TYPE_RNGCOMP = 4, TYPE_MAX = 5 };
+enum : uint32_t { TYPE_MESH = 1, TYPE_PHOLD = 2, TYPE_CLOCKNODE = 3, TYPE_RNGCOMP = 4, TYPE_CORETEST = 5, TYPE_MAX = 6 };
 constexpr int NPARAM  = 8;
 constexpr int NRESULT = 32;
 
@@ -458,6 +458,91 @@ struct ClockNodeElement
         r[1] = s.last_cycle;
         r[2] = s.recv;
         r[3] = s.hash;
+        for ( int i = 0; i < 4; ++i )
+            s.count[i].out(r + 4 + 5 * i);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// coreTestElement.coreTestComponent (testElements/coreTest_Component.cc:25-173; tests/test_Component.py): one clock
+// handler; every tick draws generateNextInt32() and, with probability 1/commFreq, sends an event to the next of its
+// four neighbours (N, S, E, W in turn) and counts it in that direction's statistic.  All components seed
+// MarsagliaRNG(11, 272727).  `neighbor` is a C++ int: the constructor's generateNextInt32() % 4 may be negative, and
+// then the first sends fall into the switch's default ("bad neighbor", nothing sent) until it has counted up to 0.
+// The event's payload (commSize bytes of 1) is only summed into itself by the receiver and never observed, so the
+// device event carries none; workPerCycle is a busy loop without effect.
+struct CoreTestElement
+{
+    static constexpr uint32_t    TYPE        = TYPE_CORETEST;
+    static constexpr const char* ELI_NAME    = "coreTestElement.coreTestComponent";
+    static constexpr uint32_t    AUX_BYTES   = 0;
+    static constexpr bool        AUX_MT_SEED = false;
+    __device__ static uint32_t auxSeed(const int64_t*) { return 0; }
+    static constexpr bool        HAS_PAYLOAD = false;
+    struct State
+    {
+        // [0,16) mutable core
+        MarsagliaDev rng;
+        int32_t      neighbor;
+        uint32_t     bad; // "bad neighbor" lines the reference would have printed
+        // [16,32) construction constants
+        int32_t  commFreq;
+        uint32_t pad0;
+        uint64_t pad1;
+        // [32,128) statistics N, S, E, W
+        Accumulator<int32_t> count[4];
+    };
+    static constexpr uint32_t STORE_END = 16, CONST_END = 32, STATS_END = 128;
+    static constexpr bool     TIES_INTERCHANGEABLE = true; // handleEvent looks at nothing but the payload it deletes
+    static constexpr bool     PARALLEL_EVENTS      = false;
+    static constexpr uint32_t PERSIST_BYTES        = sizeof(State);
+    template <class Ctx>
+    __device__ static void beginWindow(Ctx&, State&, uint32_t)
+    {}
+    __device__ static uint32_t prefetch(const uint8_t* state, const uint8_t*)
+    {
+        prefetch_l2(state);
+        return 0xFFFFFFFFu;
+    }
+    template <class Ctx>
+    __device__ static void construct(Ctx&, State& s, const int64_t* p)
+    {
+        s.rng.z    = 11u;
+        s.rng.w    = 272727u;
+        s.commFreq = (int32_t)p[1];
+        s.neighbor = rng_i32(s.rng) % 4;
+        s.bad      = 0;
+        s.pad0     = 0;
+        s.pad1     = 0;
+        for ( int i = 0; i < 4; ++i )
+            s.count[i].init();
+    }
+    template <class Ctx>
+    __device__ static void setup(Ctx&, State&)
+    {}
+    template <class Ctx>
+    __device__ static void handleEvent(Ctx&, State&, int, uint64_t&)
+    {}
+    template <class Ctx>
+    __device__ static bool clockTick(Ctx& ctx, State& s, uint64_t)
+    {
+        if ( (rng_i32(s.rng) % s.commFreq) == 0 ) {
+            s.neighbor = (s.neighbor + 1) % 4; // C++ remainder: stays negative until it reaches 0
+            if ( s.neighbor >= 0 ) {
+                ctx.send(s.neighbor, 0, 0);
+                if ( ctx.stats_on ) s.count[s.neighbor].add(1);
+            }
+            else
+                s.bad++;
+        }
+        return false;
+    }
+    __device__ static void initStats(State& s) { for ( int i = 0; i < 4; ++i ) s.count[i].init(); }
+    __device__ static void mergeStats(State& mem, const State& d) { for ( int i = 0; i < 4; ++i ) mem.count[i].merge(d.count[i]); }
+    __device__ static uint64_t statsVersion(const State& s) { return s.count[0].count + s.count[1].count + s.count[2].count + s.count[3].count; }
+    __device__ static void results(const State& s, uint64_t* r)
+    {
+        r[0] = s.bad;
         for ( int i = 0; i < 4; ++i )
             s.count[i].out(r + 4 + 5 * i);
     }

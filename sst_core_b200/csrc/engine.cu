@@ -291,6 +291,9 @@ with_element(uint32_t type, F&& f)
     case TYPE_RNGCOMP:
         f(RngElement {});
         break;
+    case TYPE_CORETEST:
+        f(CoreTestElement {});
+        break;
     default:
         break;
     }
@@ -1416,6 +1419,8 @@ static const ElementInfo kElements[] = {
         ClockNodeElement::AUX_BYTES, ClockNodeElement::HAS_PAYLOAD, ClockNodeElement::PARALLEL_EVENTS, ClockNodeElement::TIES_INTERCHANGEABLE, "clock-driven node (coreTestComponent style)" },
     { TYPE_RNGCOMP, RngElement::ELI_NAME, RngElement::PERSIST_BYTES, RngElement::AUX_BYTES,
         RngElement::HAS_PAYLOAD, RngElement::PARALLEL_EVENTS, RngElement::TIES_INTERCHANGEABLE, "coreTestRNGComponent: 1 GHz clock drawing from an SST::RNG generator" },
+    { TYPE_CORETEST, CoreTestElement::ELI_NAME, CoreTestElement::PERSIST_BYTES, CoreTestElement::AUX_BYTES,
+        CoreTestElement::HAS_PAYLOAD, CoreTestElement::PARALLEL_EVENTS, CoreTestElement::TIES_INTERCHANGEABLE, "coreTestComponent: clock handler sending to its N/S/E/W neighbours in turn" },
 };
 constexpr int kNumElements = (int)(sizeof(kElements) / sizeof(kElements[0]));
 

@@ -23,13 +23,13 @@ from typing import Callable, Dict, List, Optional, Tuple
 from .config import ConfigComponent, ModelError
 from .timelord import TimeLord
 
-TYPE_MESH, TYPE_PHOLD, TYPE_CLOCKNODE, TYPE_RNGCOMP = 1, 2, 3, 4
+TYPE_MESH, TYPE_PHOLD, TYPE_CLOCKNODE, TYPE_RNGCOMP, TYPE_CORETEST = 1, 2, 3, 4, 5
 NPARAM = 8
 NRESULT = 32
 # words of the result record each element actually fills (the download can stop there)
-RESULT_WORDS = {1: 6, 2: 7, 3: 24, 4: 7}
+RESULT_WORDS = {1: 6, 2: 7, 3: 24, 4: 7, 5: 24}
 # ... and when statistics are disabled (the accumulator words stay zero)
-RESULT_WORDS_NOSTATS = {1: 1, 2: 2, 3: 4, 4: 7}
+RESULT_WORDS_NOSTATS = {1: 1, 2: 2, 3: 4, 4: 7, 5: 1}
 
 
 @dataclass
@@ -163,6 +163,27 @@ def _wire_clocknode(c: ConfigComponent, tl: TimeLord) -> Wired:
     return Wired(TYPE_CLOCKNODE, [my_id, comm, verbose, 0, 0, 0, 0, 0], ports, period, stats, finish)
 
 
+# ---- coreTestElement.coreTestComponent (testElements/coreTest_Component.cc:25-84; tests/test_Component.py)
+def _wire_coretest(c: ConfigComponent, tl: TimeLord) -> Wired:
+    _find_int(c, "workPerCycle", required_msg="couldn't find work per cycle")  # a busy loop: no simulated effect
+    comm = _find_int(c, "commFreq", required_msg="couldn't find communication frequency")
+    _find_int(c, "commSize", 16)  # payload bytes, summed by the receiver and dropped: not carried on the device
+    if comm == 0:
+        raise ModelError("commFreq must be non-zero (generateNextInt32() % commFreq)")
+    period = tl.cycles(c.params.get("clockFrequency", "1GHz"))
+    have = {p for p, _, _ in c.links}
+    names = ["Nlink", "Slink", "Elink", "Wlink"]
+    for n in names:  # coreTest_Component.cc:66-69 assert(N) ... assert(W)
+        if n not in have:
+            raise ModelError(f"coreTestComponent {c.name}: port {n} is not connected (the reference asserts on it)")
+    stats = [StatDesc(c.full_name(), n, "", "i32", 4 + 5 * i) for i, n in enumerate("NSEW")]
+
+    def finish(r):
+        return "\n".join(["bad neighbor"] * int(r[0]) + ["Component Finished."])
+
+    return Wired(TYPE_CORETEST, [0, comm, 0, 0, 0, 0, 0, 0], [(c, n) for n in names], period, stats, finish)
+
+
 # ---- coreTestElement.coreTestRNGComponent (testElements/coreTest_RNGComponent.cc:26-74)
 def _wire_rngcomp(c: ConfigComponent, tl: TimeLord) -> Wired:
     count = _find_int(c, "count", 1000)
@@ -190,6 +211,7 @@ ELEMENTS: Dict[str, Callable[[ConfigComponent, TimeLord], Wired]] = {
     "pdes.phold": _wire_phold,
     "pdes.clocknode": _wire_clocknode,
     "coreTestElement.coreTestRNGComponent": _wire_rngcomp,
+    "coreTestElement.coreTestComponent": _wire_coretest,
 }
 
 TYPE_NAMES = {
@@ -197,4 +219,5 @@ TYPE_NAMES = {
     TYPE_PHOLD: "pdes.phold",
     TYPE_CLOCKNODE: "pdes.clocknode",
     TYPE_RNGCOMP: "coreTestElement.coreTestRNGComponent",
+    TYPE_CORETEST: "coreTestElement.coreTestComponent",
 }

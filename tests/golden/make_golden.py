@@ -132,6 +132,20 @@ def main():
         O.run_ref(MODELS / "phold.py", "4 3 60ns", extra=["--profiling-output=r.txt", "--enable-profiling=" + spec], cwd=td)
         out["profiling_phold_4x3_60ns_type"] = {"source": f"sstsim.x phold.py '4 3 60ns' --enable-profiling={spec}",
                                                 "spec": spec, "text": (Path(td) / "r.txt").read_text()}
+    # coreTestElement.coreTestComponent: the reference's own model script and golden file, plus handler counts and
+    # statistics of the same model from the reference binary (the golden file itself holds no numbers)
+    out["component_golden"] = {"source": "tests/refFiles/test_Component.out",
+                               "lines": (REF_TESTS / "refFiles/test_Component.out").read_text().strip().splitlines()}
+    with tempfile.TemporaryDirectory() as td:
+        spec = ("events:sst.profile.handler.event.count(level=component)[event];"
+                "clocks:sst.profile.handler.clock.count(level=component)[clock]")
+        txt = O.run_ref(REF_TESTS / "test_Component.py", extra=["--profiling-output=p.txt", "--enable-profiling=" + spec], cwd=td)
+        out["component_profile"] = {"source": f"sstsim.x tests/test_Component.py --enable-profiling={spec}", "spec": spec,
+                                    "stdout": txt.strip().splitlines(), "text": (Path(td) / "p.txt").read_text()}
+        O.run_ref(MODELS / "component.py", "10 10 37 3us 1", cwd=td)
+        out["component_stats_csv"] = {"source": "sstsim.x tests/models/component.py '10 10 37 3us 1' (the test_Component.py "
+                                                "graph with commFreq 37, 3 us, all statistics enabled)",
+                                      "rows": (Path(td) / "StatisticOutput.csv").read_text().strip().splitlines()}
     (HERE / "reference_golden.json").write_text(json.dumps(out, indent=1, sort_keys=True))
     print("wrote", HERE / "reference_golden.json", (HERE / "reference_golden.json").stat().st_size, "bytes")
 
