@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--x", type=int, default=0)
     ap.add_argument("--y", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="multi-rank: time all-to-all / ingest / advance per window")
     ap.add_argument("--smem-events", type=int, default=0, help="override the staging capacity (tuning)")
     ap.add_argument("--bin-capacity", type=int, default=0, help="override the calendar bin capacity (tuning)")
     ap.add_argument("--stats", type=int, default=1, help="1: statistics enabled (accumulators updated), 0: disabled")
@@ -100,7 +101,7 @@ class ClockSampler:
                     if mask & bit:
                         self.reasons.add(name)
                 self.ready.set()
-                self.stop_flag.wait(0.002)
+                self.stop_flag.wait(float(os.environ.get('SSTB200_CLOCK_MS', '2')) * 1e-3)
             return
         except Exception:
             pass
@@ -331,6 +332,8 @@ def ours(a):
         e.setup()
         runner = DistributedRunner(e) if world > 1 else None
 
+        seg = []  # --breakdown: CUDA events between the four stages of a multi-rank window
+
         def step(ev_pair=None):
             if ev_pair:
                 ev_pair[0].record(stream)
@@ -338,6 +341,16 @@ def ours(a):
                 e.dispatch()
                 if ev_pair:
                     ev_pair[1].record(stream)
+                if a.breakdown and ev_pair:
+                    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                    dist.all_to_all_single(runner.inbox, runner.outbox)
+                    evs[0].record(stream)
+                    e.ingest()
+                    evs[1].record(stream)
+                    e.advance()
+                    evs[2].record(stream)
+                    seg.append((ev_pair[1], *evs))
+                    return
                 dist.all_to_all_single(runner.inbox, runner.outbox)
                 e.ingest()
                 e.advance()
@@ -352,12 +365,12 @@ def ours(a):
         torch.cuda.synchronize(dev)
         st0 = e.status()
         e.raise_on_error(st0)
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()  # before the barrier: bringing NVML up takes milliseconds the other ranks must not wait for
         if dist:
             dist.barrier()
         torch.cuda.synchronize(dev)
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_beg.record(stream)
@@ -370,6 +383,16 @@ def ours(a):
         clocks = sampler.stop() if rank == 0 else None
         st1 = e.status()
         e.raise_on_error(st1)
+    if seg:
+        names = ["all_to_all", "ingest", "advance"]
+        tot = [sum(x[i].elapsed_time(x[i + 1]) for x in seg) / len(seg) for i in range(3)]
+        disp = [p[0].elapsed_time(p[1]) for p in pairs]
+        gaps = [seg[i][3].elapsed_time(pairs[i + 1][0]) for i in range(len(seg) - 1)]
+        print(f"[breakdown] rank {rank} per window: " + ", ".join(f"{n} {t * 1e3:.1f} us" for n, t in zip(names, tot))
+              + f"; dispatch min/mean/max {min(disp):.3f}/{sum(disp) / len(disp):.3f}/{max(disp):.3f} ms"
+              + f"; a2a max {max(x[0].elapsed_time(x[1]) for x in seg) * 1e3:.0f} us"
+              + f"; gap advance->next window mean {sum(gaps) / len(gaps) * 1e3:.1f} us max {max(gaps) * 1e3:.0f} us",
+              file=sys.stderr)
     ms_total = t_beg.elapsed_time(t_end)
     ms_dispatch = sum(p[0].elapsed_time(p[1]) for p in pairs) / K
     events = (st1.events_delivered - st0.events_delivered) + (st1.clock_ticks - st0.clock_ticks)
