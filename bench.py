@@ -314,7 +314,7 @@ def ours(a):
         torch.cuda.synchronize(dev)
         secs = time.perf_counter() - t0
         e.raise_on_error(st)
-        ev = torch.tensor([st.events_delivered, 0], dtype=torch.float64, device=dev)
+        ev = torch.tensor([st.events_delivered + st.clock_ticks, 0], dtype=torch.float64, device=dev)  # same unit as `value`
         tt = torch.tensor([secs], dtype=torch.float64, device=dev)
         if dist:
             dist.all_reduce(ev)
