@@ -158,6 +158,7 @@ struct MeshElement
     // (empty) payload: events that are due at the same time are interchangeable, whatever order they are run in the
     // component ends in the same state and sends the same events (enclosingComponent.cc:92-99,179-186)
     static constexpr bool TIES_INTERCHANGEABLE = true;
+    static constexpr bool     STATS_EVERY_EVENT = false;
     // 3a, component thread: asynchronous copies (LDGSTS) of the a-run: chunk j = (mt[i+2j], mt[i+2j+1]) to
     // staged[j] (delivery position j of this component), and mt[i+2n] (the last pair's third word) to *extra
     __device__ static void stageParallel(const uint8_t* aux, uint32_t hdr, uint32_t n, uint2* staged, uint32_t* extra)
@@ -318,6 +319,9 @@ struct PholdElement
     };
     static constexpr uint32_t STORE_END = 32, CONST_END = 48, STATS_END = 96;
     static constexpr bool     TIES_INTERCHANGEABLE = false; // the delivery hash / handlers see port and order
+    // every delivery adds to the "delay" statistic: a window with events loads the statistics region together
+    // with the rest of the state and stores it back, instead of folding a per-window accumulator afterwards
+    static constexpr bool     STATS_EVERY_EVENT = true;
     static constexpr bool     PARALLEL_EVENTS = false; // handlers chain through the state (hash, RNG): sequential
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>
@@ -402,6 +406,7 @@ struct ClockNodeElement
     };
     static constexpr uint32_t STORE_END = 48, CONST_END = 64, STATS_END = 160;
     static constexpr bool     TIES_INTERCHANGEABLE = false; // the delivery hash / handlers see port and order
+    static constexpr bool     STATS_EVERY_EVENT = false;
     static constexpr bool     PARALLEL_EVENTS = false; // handlers chain through the state (hash, RNG): sequential
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>
@@ -494,6 +499,7 @@ struct CoreTestElement
     };
     static constexpr uint32_t STORE_END = 16, CONST_END = 32, STATS_END = 128;
     static constexpr bool     TIES_INTERCHANGEABLE = true; // handleEvent looks at nothing but the payload it deletes
+    static constexpr bool     STATS_EVERY_EVENT = false;
     static constexpr bool     PARALLEL_EVENTS      = false;
     static constexpr uint32_t PERSIST_BYTES        = sizeof(State);
     template <class Ctx>
@@ -569,6 +575,7 @@ struct RngElement
     };
     static constexpr uint32_t STORE_END = 96, CONST_END = 96, STATS_END = 96;
     static constexpr bool     TIES_INTERCHANGEABLE = false; // the delivery hash / handlers see port and order
+    static constexpr bool     STATS_EVERY_EVENT = false;
     static constexpr bool     PARALLEL_EVENTS = false; // handlers chain through the state (hash, RNG): sequential
     static constexpr uint32_t PERSIST_BYTES = sizeof(State);
     template <class Ctx>

@@ -920,8 +920,12 @@ dispatch_kernel(Dev d)
         with_element(my_type, [&](auto el) {
             using E = decltype(el);
             typename E::State s;
-            load_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::CONST_END);
-            E::initStats(s); // this window's statistics start empty and are folded into memory at the end
+            // statistics: elements that add data with every delivery get their statistics region in the same round
+            // trip as the rest of the state; for the others this window's statistics start empty and are folded into
+            // memory at the end, if the window added any
+            const bool stats_direct = E::STATS_EVERY_EVENT && d.stats_on && my_cnt > 0;
+            load_state(s, d.state + (uint64_t)lc * d.state_stride, 0, stats_direct ? E::STATS_END : E::CONST_END);
+            if ( !stats_direct ) E::initStats(s);
             E::beginWindow(ctx, s, my_cnt); // issues the element's first loads (MT19937 read-ahead)
             if ( owner_sorts ) sort_segment(s_perm + s_off[c], my_cnt, s_time, s_dst, s_sc);
             uint64_t cycle = (next_tick != TIME_NEVER && period) ? next_tick / period : 0;
@@ -965,7 +969,10 @@ dispatch_kernel(Dev d)
             store_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::STORE_END);
             // statistics: read-modify-write only when the window added data (a clock-driven element may tick a thousand
             // times between two addData calls)
-            if ( d.stats_on && E::statsVersion(s) != 0 ) {
+            if ( stats_direct ) {
+                store_state(s, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
+            }
+            else if ( d.stats_on && E::statsVersion(s) != 0 ) {
                 typename E::State mem;
                 load_state(mem, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
                 E::mergeStats(mem, s);
