@@ -140,6 +140,18 @@ int sstb200_engine_results(sstb200_engine* e, uint64_t* results, uint32_t words_
 int sstb200_engine_trace(sstb200_engine* e, uint64_t* n_inout, uint64_t* time, uint32_t* comp, uint32_t* port,
                          uint64_t* payload);
 
+/* ---- periodic statistic output (StatisticProcessingEngine::performStatisticOutput at a statistic clock,
+ * statapi/statengine.cc:346-376; the clock runs at priority 85, i.e. AFTER the clock handlers and events of its time) ----
+ * run_to_report: run whole windows up to and including the one that contains report_time and return every local
+ *   component's result record as of the END of time report_time (layout as sstb200_engine_results).  *reported = 0 and
+ *   nothing is run past the end when the simulation ends first or report_time >= stop_at (StopAction, priority 30, wins).
+ * report_begin / report_end: the same for a driver that steps windows itself (multi-rank): bracket the window that
+ *   contains report_time -- begin, dispatch [exchange, ingest], advance, end. */
+int sstb200_engine_run_to_report(sstb200_engine* e, uint64_t report_time, uint64_t* results, uint32_t words_per_component,
+                                 int* reported, int* finished);
+int sstb200_engine_report_begin(sstb200_engine* e, uint64_t report_time);
+int sstb200_engine_report_end(sstb200_engine* e, uint64_t* results, uint32_t words_per_component);
+
 /* ---- checkpoint / restart (Simulation::checkpoint simulation.cc:2015-2071, restart :2073-2200; CheckpointAction) ----
  * The blob holds this rank's complete simulation state between two windows: engine control block, per-component
  * control blocks and element state (RNGs, statistics), the event calendar, exchange buffers, handler counters.

@@ -1,9 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-echo skip tests
-for i in 1 2; do
-python bench.py --workload phold --x 1024 --y 1024 --steps 20 --warmup 10 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
-import json,sys;d=json.loads(sys.stdin.read().strip().splitlines()[-1]);print('phold',round(d['value']/1e9,2),round(d['ms_per_step'],4), round(d['roofline']['frac'],4))"
-done
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -25 gpurun_out/pytest_gpu.log
 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
 import json,sys;d=json.loads(sys.stdin.read().strip().splitlines()[-1]);print('mesh',round(d['value']/1e9,2),round(d['ms_per_step'],4), round(d['roofline']['frac'],4))"
+python bench.py --workload phold --x 1024 --y 1024 --steps 20 --warmup 10 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
+import json,sys;d=json.loads(sys.stdin.read().strip().splitlines()[-1]);print('phold',round(d['value']/1e9,2),round(d['ms_per_step'],4), round(d['roofline']['frac'],4))"

@@ -269,8 +269,15 @@ def setStatisticLoadLevel(level):
     _g().stat_load_level = int(level)
 
 
-def enableAllStatisticsForAllComponents(params=None):
-    _g().enable_all_stats = dict(params or {})
+_NO_ARG = object()
+
+
+def enableAllStatisticsForAllComponents(params=_NO_ARG):
+    # pymodel.cc enableAllStatisticsForAllComponents parses "|O!" with PyDict_Type: the argument may be left out but,
+    # when given, must be a dict
+    if params is not _NO_ARG and not isinstance(params, dict):
+        raise TypeError(f"argument 1 must be dict, not {type(params).__name__}")
+    _g().enable_all_stats = dict(params) if params is not _NO_ARG else {}
 
 
 def enableAllStatisticsForComponentName(name, params=None, recursive=False):

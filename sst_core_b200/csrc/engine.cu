@@ -86,6 +86,10 @@ struct Ctrl
     unsigned long long trace_n;
     uint64_t           windows;
     uint32_t           had_primary, pad;
+    // periodic statistic output (statengine.cc:346-376): when report_at lies inside the current window every component
+    // leaves its result record as of the END of time report_at (StatisticOutput clocks run at priority 85, after the
+    // clock handlers and events of their time) in Dev::snapshot; TIME_NEVER otherwise
+    uint64_t           report_at;
 };
 
 // Per-component engine control block: everything the dispatch kernel needs about a component besides its element
@@ -147,6 +151,7 @@ struct Dev
     // deliveries per receiving port and clock-handler calls per component; null unless the option is set
     unsigned long long* prof_recv;  // [nport_local]
     unsigned long long* prof_clock; // [n_local]
+    uint8_t*            snapshot;   // copy of `state` holding every component's state as of Ctrl::report_at
 };
 
 // ================================================================================================ device side
@@ -510,7 +515,9 @@ struct ParCtx
 };
 
 // ---- one lookahead window for one block of 256 components
-template <bool PAYLOAD, bool PARFORM>
+// REPORT: the launch of a window that contains a periodic-statistics report time (Ctrl::report_at); always the
+// sequential form.  A separate instantiation so that the ordinary launches carry none of it.
+template <bool PAYLOAD, bool PARFORM, bool REPORT = false>
 #ifndef SSTB200_MIN_BLOCKS
 #define SSTB200_MIN_BLOCKS 3 // 80 registers, no spills, 3 CTAs/SM: measured 27 % faster than 4 CTAs/SM at 64 registers with spills
 #endif
@@ -577,6 +584,12 @@ dispatch_kernel(Dev d)
             const uint32_t e  = (bin + 1) * BLOCK;
             s_port_off[BLOCK] = d.port_off[e <= d.n_local ? e : d.n_local];
             s_misc[0]         = 0;
+            // periodic statistic output falls into this window when T <= report_at < T_end: its offset, else all ones
+            // (kept in shared memory: two more registers live across the whole kernel would spill)
+            if constexpr ( REPORT ) {
+                const uint64_t rep = ctrl->report_at;
+                s_misc[1]          = (rep >= T && rep < T_end) ? (uint32_t)(rep - T) : 0xFFFFFFFFu;
+            }
             s_misc[2]         = 0xFFFFFFFFu; // min / max time offset of the due events
             s_misc[3]         = 0;
         }
@@ -930,8 +943,28 @@ dispatch_kernel(Dev d)
             if ( owner_sorts ) sort_segment(s_perm + s_off[c], my_cnt, s_time, s_dst, s_sc);
             uint64_t cycle = (next_tick != TIME_NEVER && period) ? next_tick / period : 0;
             uint32_t i     = 0;
+            const uint32_t r_off   = REPORT ? s_misc[1] : 0xFFFFFFFFu;
+            const uint64_t R       = T + r_off;
+            bool           snapped = r_off == 0xFFFFFFFFu;
             for ( ;; ) {
                 const uint64_t ev_t = (i < my_cnt) ? T + s_time[seg[i]] : TIME_NEVER;
+                if ( REPORT && !snapped && ev_t > R && !(next_tick < T_end && next_tick <= R) ) {
+                    // everything up to the report time has run: leave the component's state as of now in the snapshot
+                    // copy (results_kernel turns it into result records afterwards).  Statistics collected per window
+                    // are folded with what is in memory first.
+                    uint8_t* const snap = d.snapshot + (uint64_t)lc * d.state_stride;
+                    store_state(s, snap, 0, E::CONST_END);
+                    if ( stats_direct ) {
+                        store_state(s, snap, E::CONST_END, E::STATS_END);
+                    }
+                    else if ( d.stats_on && E::statsVersion(s) != 0 ) {
+                        typename E::State mem;
+                        load_state(mem, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
+                        E::mergeStats(mem, s);
+                        store_state(mem, snap, E::CONST_END, E::STATS_END);
+                    }
+                    snapped = true;
+                }
                 if ( next_tick < T_end && next_tick <= ev_t ) {
                     ctx.now         = next_tick;
                     const bool stop = E::clockTick(ctx, s, cycle);
@@ -1455,6 +1488,7 @@ struct sstb200_engine
     size_t             smem_bytes  = 0;
     uint64_t           launches    = 0;
     bool               is_setup    = false;
+    bool               report_pending = false; // between report_begin and report_end: dispatch uses the REPORT kernel
     uint32_t           n_ranks     = 1;
     // device buffers that make up the simulation state (checkpoint sections, in a fixed order)
     struct Section
@@ -1495,9 +1529,15 @@ struct sstb200_engine
         CUDA_OK(cudaStreamSynchronize(stream));
         return 0;
     }
-    int launch_dispatch()
+    int launch_dispatch(bool report = false)
     {
-        if ( d.has_payload )
+        if ( report ) {
+            if ( d.has_payload )
+                dispatch_kernel<true, false, true><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
+            else
+                dispatch_kernel<false, false, true><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
+        }
+        else if ( d.has_payload )
             (d.any_parallel ? dispatch_kernel<true, true> : dispatch_kernel<true, false>)<<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
         else
             (d.any_parallel ? dispatch_kernel<false, true> : dispatch_kernel<false, false>)<<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
@@ -1891,6 +1931,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     e->h_ctrl->T       = 0;
     e->h_ctrl->T_end   = (m->stop_at && w > m->stop_at) ? m->stop_at : w;
     e->h_ctrl->had_primary = 1;
+    e->h_ctrl->report_at   = TIME_NEVER;
     CUDA_OK(cudaMemcpyAsync(d.ctrl, e->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, e->stream));
 
     e->smem_bytes = (size_t)d.lmax * 16 + (size_t)d.emax * (has_payload ? 8 : 0) + (size_t)d.emax * 16 +
@@ -1905,6 +1946,8 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaStreamSynchronize(e->stream));
     *out = e;
     return 0;
@@ -1988,7 +2031,7 @@ sstb200_engine_dispatch(sstb200_engine* e)
 {
     if ( !e || !e->is_setup ) return -1;
     CUDA_OK(cudaSetDevice(e->device));
-    if ( int rc = e->launch_dispatch() ) return rc;
+    if ( int rc = e->launch_dispatch(e->report_pending) ) return rc;
     publish_control_kernel<<<1, 64, 0, e->stream>>>(e->d);
     e->launches++;
     CUDA_OK(cudaGetLastError());
@@ -2168,6 +2211,90 @@ sstb200_engine_checkpoint_load(sstb200_engine* e, const void* blob, uint64_t byt
     }
     CUDA_OK(cudaStreamSynchronize(e->stream));
     e->is_setup = true; // the restored state replaces construct + setup()
+    return 0;
+}
+
+// ---- periodic statistic output -----------------------------------------------------------------------------------
+int
+sstb200_engine_report_begin(sstb200_engine* e, uint64_t report_time)
+{
+    if ( !e || !e->is_setup ) return -1;
+    CUDA_OK(cudaSetDevice(e->device));
+    const size_t bytes = (size_t)e->d.n_local * e->d.state_stride;
+    if ( !e->d.snapshot ) {
+        if ( int rc = e->alloc(&e->d.snapshot, bytes, false) ) return rc;
+        e->graph_failed = true; // the captured graph holds the old kernel arguments: plain launches from now on
+    }
+    // components that do nothing in the window up to the report time keep the state they have now
+    if ( bytes ) CUDA_OK(cudaMemcpyAsync(e->d.snapshot, e->d.state, bytes, cudaMemcpyDeviceToDevice, e->stream));
+    CUDA_OK(cudaMemcpyAsync(&e->d.ctrl->report_at, &report_time, 8, cudaMemcpyHostToDevice, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream)); // report_time is a stack variable
+    e->report_pending = true;
+    return 0;
+}
+
+int
+sstb200_engine_report_end(sstb200_engine* e, uint64_t* results, uint32_t words_per_component)
+{
+    if ( !e || !results || !e->d.snapshot ) return -1;
+    const uint32_t words = (words_per_component == 0 || words_per_component > NRESULT) ? NRESULT : words_per_component;
+    CUDA_OK(cudaSetDevice(e->device));
+    const uint64_t never = TIME_NEVER;
+    e->report_pending    = false;
+    CUDA_OK(cudaMemcpyAsync(&e->d.ctrl->report_at, &never, 8, cudaMemcpyHostToDevice, e->stream));
+    Dev snap   = e->d;
+    snap.state = e->d.snapshot; // result records of the snapshot copy
+    results_kernel<<<e->d.nbins, BLOCK, 0, e->stream>>>(snap, e->d_results, words);
+    e->launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(results, e->d_results, (size_t)e->d.n_local * words * 8, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int
+sstb200_engine_run_to_report(sstb200_engine* e, uint64_t report_time, uint64_t* results, uint32_t words_per_component,
+    int* reported, int* finished)
+{
+    if ( !e || !results ) return -1;
+    if ( reported ) *reported = 0;
+    if ( finished ) *finished = 0;
+    if ( e->n_ranks > 1 ) {
+        set_error("engine_run_to_report is single-rank; a multi-rank driver brackets the window with report_begin/end");
+        return -1;
+    }
+    CUDA_OK(cudaSetDevice(e->device));
+    if ( int rc = e->fetch_ctrl() ) return rc;
+    const Ctrl& c = *e->h_ctrl;
+    if ( c.done ) {
+        if ( finished ) *finished = 1;
+        return 0;
+    }
+    if ( report_time < c.T ) {
+        set_error("engine_run_to_report: the report time lies before the current window");
+        return -1;
+    }
+    if ( c.stop_at && report_time >= c.stop_at ) return 0; // StopAction (priority 30) ends the run before that output
+    const uint64_t before = report_time / c.w - c.k;
+    if ( before ) {
+        int fin = 0;
+        if ( int rc = sstb200_engine_run(e, before, 64, &fin) ) return rc;
+        if ( fin ) {
+            if ( finished ) *finished = 1;
+            return 0;
+        }
+    }
+    if ( int rc = sstb200_engine_report_begin(e, report_time) ) return rc;
+    if ( int rc = e->launch_dispatch(true) ) return rc;
+    if ( int rc = e->launch_advance() ) return rc;
+    if ( int rc = sstb200_engine_report_end(e, results, words_per_component) ) return rc;
+    if ( int rc = e->fetch_ctrl() ) return rc;
+    if ( e->h_ctrl->error ) {
+        set_error("engine error " + std::to_string(e->h_ctrl->error) + " in the report window");
+        return -4;
+    }
+    if ( reported ) *reported = 1;
+    if ( finished ) *finished = e->h_ctrl->done ? 1 : 0;
     return 0;
 }
 

@@ -55,6 +55,7 @@ EXPORTS = [
     "sstb200_engine_advance", "sstb200_engine_exchange_buffers", "sstb200_engine_control_words",
     "sstb200_engine_status", "sstb200_engine_results", "sstb200_engine_trace", "sstb200_engine_handler_counts",
     "sstb200_engine_checkpoint_size", "sstb200_engine_checkpoint_save", "sstb200_engine_checkpoint_load",
+    "sstb200_engine_run_to_report", "sstb200_engine_report_begin", "sstb200_engine_report_end",
     "sstb200_rng_streams",
     "sstb200_rng_ticks", "sstb200_rng_distribution",
 ]
@@ -91,6 +92,10 @@ def lib():
     L.sstb200_engine_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p]
     L.sstb200_engine_handler_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sstb200_engine_run_to_report.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(C.c_int),
+                                               C.POINTER(C.c_int)]
+    L.sstb200_engine_report_begin.argtypes = [C.c_void_p, C.c_uint64]
+    L.sstb200_engine_report_end.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.sstb200_engine_checkpoint_size.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.sstb200_engine_checkpoint_save.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     L.sstb200_engine_checkpoint_load.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
@@ -175,7 +180,7 @@ def partition_model(m: WiredModel, n_ranks: int) -> WiredModel:
         stats=[m.stats[i] for i in order] if m.stats else None,
         finish=[m.finish[i] for i in order] if m.finish else None, nocut_pairs=None, stat_output=m.stat_output,
         port_info=[m.port_info[int(i)] for i in old_ids] if m.port_info else None,
-        type_names=[m.type_names[i] for i in order] if m.type_names else None)
+        type_names=[m.type_names[i] for i in order] if m.type_names else None, stat_rate=m.stat_rate)
     out.validate()
     return out
 
@@ -336,6 +341,25 @@ class Engine:
         out = np.zeros((n, NRESULT), dtype=np.uint64)
         out[:, :words] = part
         return out
+
+    def run_to_report(self, report_time: int, words: int = 0):
+        """Run up to and including the window that contains ``report_time`` (cycles).  Returns (records, finished):
+        records = the result records [n, 32] as of the END of that time (periodic statistic output), or None when
+        the simulation ended first or the time is at/after stop-at."""
+        n = self.comp_end - self.comp_begin
+        w = words if words and words < NRESULT else NRESULT
+        part = np.zeros((n, w), dtype=np.uint64)
+        rep, fin = C.c_int(0), C.c_int(0)
+        rc = self._L.sstb200_engine_run_to_report(self._h, int(report_time), _p(part), 0 if w == NRESULT else w,
+                                                  C.byref(rep), C.byref(fin))
+        if rc == -4:
+            self.raise_on_error()
+        _check(rc, "engine_run_to_report")
+        if not rep.value:
+            return None, bool(fin.value)
+        out = np.zeros((n, NRESULT), dtype=np.uint64)
+        out[:, :w] = part
+        return out, bool(fin.value)
 
     def window(self) -> int:
         """Lookahead window in cycles (the option, else the model's minimum link latency)."""

@@ -37,9 +37,16 @@ def finish_lines(m: WiredModel, results: np.ndarray, end_time: int) -> List[str]
     return lines
 
 
-def stat_rows_csv(m: WiredModel, results: np.ndarray, end_time: int, rank_of=None) -> List[str]:
+def stat_rows_csv(m: WiredModel, results: np.ndarray, end_time: int, rank_of=None, periodic=()) -> List[str]:
+    """Header + one block of rows per output: the periodic outputs first (``periodic`` = [(sim time, records), ...],
+    the statistic clock of a "rate" parameter, statengine.cc:346-376), then the end-of-simulation block."""
     if not m.stats_enabled or not m.stats:
         return []
+    if periodic:
+        rows = stat_rows_csv(m, periodic[0][1], periodic[0][0])
+        for t_p, rec in periodic[1:]:
+            rows += stat_rows_csv(m, rec, t_p)[1:]
+        return rows + stat_rows_csv(m, results, end_time)[1:]
     order = np.argsort(m.orig_id) if m.orig_id is not None else np.arange(m.ncomp)
     dtypes = {s.dtype for sl in m.stats for s in sl}
     t = "u64" if dtypes <= {"u64"} else "i32" if dtypes <= {"i32"} else None

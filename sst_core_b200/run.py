@@ -51,7 +51,22 @@ def simulate_model(m: wireup.WiredModel, device: int = 0, auto_tune: bool = True
             else:
                 e.setup()
             try:
-                if checkpoint_period:
+                if m.stat_rate and m.stats_enabled and extras is not None:
+                    # periodic statistic output: the first at `rate`, then every `rate` (a statistic clock)
+                    extras["periodic"] = []
+                    t_next = (e.status().now // m.stat_rate + 1) * m.stat_rate
+                    while True:
+                        rec, fin = e.run_to_report(t_next, result_words(m))
+                        if rec is None:
+                            break
+                        extras["periodic"].append((t_next, rec))
+                        t_next += m.stat_rate
+                        if fin:
+                            break
+                    if checkpoint_period:
+                        raise EngineError("periodic statistic output and checkpoints cannot be combined yet")
+                    e.run()
+                elif checkpoint_period:
                     if checkpoint_writer is not None:
                         checkpoint_writer.next_id = 1 if restore_blob is None else checkpoint_writer.next_id
                     checkpoint.run_with_checkpoints(e, checkpoint_period, checkpoint_writer, opts)
@@ -187,7 +202,7 @@ def main(argv: Optional[list] = None) -> int:
     if m.stat_output[0] == "sst.statOutputConsole":
         for line in output.stat_lines_console(m, res):
             print(line)
-    rows = output.stat_rows_csv(m, res, st.end_time)
+    rows = output.stat_rows_csv(m, res, st.end_time, periodic=extras.get("periodic", ()))
     if rows and m.stat_output[0] == "sst.statOutputCSV":
         path = os.path.join(a.output_directory, m.stat_output[1].get("filepath", "StatisticOutput.csv"))
         with open(path, "w") as f:

@@ -70,6 +70,7 @@ class WiredModel:
     # handler metadata the reference hands to profile tools (baseComponent.cc:593-600); None for unwired ports
     port_info: Optional[list] = None
     type_names: Optional[List[str]] = None  # ELI type of every top-level component
+    stat_rate: int = 0  # cycles between periodic statistic outputs ("rate" statistic parameter), 0 = only at the end
 
     @property
     def ncomp(self) -> int:
@@ -150,6 +151,17 @@ def wire(graph: ConfigGraph, stop_at_override: Optional[str] = None) -> WiredMod
     stop = stop_at_override if stop_at_override is not None else graph.program_options.get("stop-at")
     stop_at = tl.cycles(stop) if stop not in (None, "", "0 ns") else 0
     nocut = [(l.ends[0][0].top().id, l.ends[1][0].top().id) for l in graph.links if l.no_cut and len(l.ends) == 2]
+    # periodic output: the "rate" parameter of enableAllStatistics... (statengine.cc:152-200 registers a statistic clock
+    # per distinct rate); one rate for the whole model is supported here
+    rates = set()
+    if graph.enable_all_stats and graph.enable_all_stats.get("rate"):
+        rates.add(str(graph.enable_all_stats["rate"]))
+    for c in graph.components:
+        if c.stat_params.get("rate"):
+            rates.add(str(c.stat_params["rate"]))
+    rates = {tl.cycles(r) for r in rates if r not in ("0", "0ns", "0 ns")}
+    if len(rates) > 1:
+        raise ModelError("statistics with different output rates in one model are not supported on the device engine")
     m = WiredModel(
         comp_type=np.array([w.type_code for w in wired], dtype=np.uint32),
         comp_param=np.array([w.params for w in wired], dtype=np.int64).reshape(ncomp, NPARAM),
@@ -164,6 +176,7 @@ def wire(graph: ConfigGraph, stop_at_override: Optional[str] = None) -> WiredMod
         port_info=[(owner.full_name(), owner.type, pname) if pname is not None else None
                    for w in wired for owner, pname in w.ports],
         type_names=[c.type for c in graph.components],
+        stat_rate=rates.pop() if rates else 0,
     )
     m.validate()
     return m

@@ -146,6 +146,16 @@ def main():
         out["component_stats_csv"] = {"source": "sstsim.x tests/models/component.py '10 10 37 3us 1' (the test_Component.py "
                                                 "graph with commFreq 37, 3 us, all statistics enabled)",
                                       "rows": (Path(td) / "StatisticOutput.csv").read_text().strip().splitlines()}
+    # periodic statistic output ("rate"): the reference's own script option, and our probe elements where event times do
+    # not line up with the lookahead windows
+    with tempfile.TemporaryDirectory() as td:
+        for key, script, opts, extra in [
+                ("rate_mesh_2x2_600ns", REF_TESTS / "test_MessageMesh.py", "2 2 1 1 2 2", ["--stop-at", "600ns"]),
+                ("rate_phold_3x3_100ns", MODELS / "phold.py", "3 3 100ns 16 8000 1 1 17ns", []),
+                ("rate_clockpop_3x3_1us", MODELS / "clockpop.py", "3 3 1us 10 1 1 130ns", [])]:
+            O.run_ref(script, opts, extra=extra, cwd=td)
+            out[key] = {"source": f"sstsim.x {Path(script).name} '{opts}' {' '.join(extra)} StatisticOutput.csv",
+                        "opts": opts, "rows": (Path(td) / "StatisticOutput.csv").read_text().strip().splitlines()}
     (HERE / "reference_golden.json").write_text(json.dumps(out, indent=1, sort_keys=True))
     print("wrote", HERE / "reference_golden.json", (HERE / "reference_golden.json").stat().st_size, "bytes")
 

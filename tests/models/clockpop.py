@@ -1,6 +1,6 @@
 # Clock-driven population: coreTestComponent-style nodes on a 2-D torus,
 # clock period chosen by id % 4 from {1GHz, 500MHz, 250MHz, 2GHz}.
-# args: X Y [stop_at] [commFreq] [verbose] [stats]
+# args: X Y [stop_at] [commFreq] [verbose] [stats] [stat_rate]
 import sys
 
 import sst
@@ -11,6 +11,7 @@ stop_at = sys.argv[3] if len(sys.argv) > 3 else "1us"
 comm_freq = int(sys.argv[4]) if len(sys.argv) > 4 else 1000
 verbose = int(sys.argv[5]) if len(sys.argv) > 5 else 1
 stats = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+stat_rate = sys.argv[7] if len(sys.argv) > 7 else ""  # periodic statistic output every <rate>
 
 sst.setProgramOption("stop-at", stop_at)
 CLOCKS = ["1GHz", "500MHz", "250MHz", "2GHz"]
@@ -38,5 +39,5 @@ for i in range(x_size * y_size):
 
 if stats:
     sst.setStatisticOutput("sst.statOutputCSV")
-    sst.enableAllStatisticsForAllComponents()
+    sst.enableAllStatisticsForAllComponents({"rate": stat_rate} if stat_rate else {})
     sst.setStatisticLoadLevel(2)

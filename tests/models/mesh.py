@@ -49,6 +49,8 @@ for i in range(x_size * y_size):
     port_yn.addLink(get_link(yn, here), "port0", "1ns")
 
 sst.setStatisticOutput("sst.statOutputCSV")
-if stat_gen == 1:
+if stat_gen == 2:  # dump at rate (the reference script uses 250ns; an optional 7th argument overrides it)
+    sst.enableAllStatisticsForAllComponents({"rate": sys.argv[7] if len(sys.argv) > 7 else "250ns"})
+elif stat_gen == 1:
     sst.enableAllStatisticsForAllComponents()
 sst.setStatisticLoadLevel(2)

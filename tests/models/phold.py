@@ -1,6 +1,6 @@
 # PHOLD-style synthetic model.  Runs unchanged under the reference `sst`
 # (with oracle/_ref's libpdes.so on --lib-path) and under sst_core_b200's `sst` module.
-# args: X Y [stop_at] [init_events] [delay_mod] [verbose] [stats]
+# args: X Y [stop_at] [init_events] [delay_mod] [verbose] [stats] [stat_rate]
 import sys
 
 import sst
@@ -12,6 +12,7 @@ init_events = int(sys.argv[4]) if len(sys.argv) > 4 else 16
 delay_mod = int(sys.argv[5]) if len(sys.argv) > 5 else 8000
 verbose = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 stats = int(sys.argv[7]) if len(sys.argv) > 7 else 0
+stat_rate = sys.argv[8] if len(sys.argv) > 8 else ""  # periodic statistic output every <rate>
 
 sst.setProgramOption("stop-at", stop_at)
 
@@ -38,5 +39,5 @@ for i in range(x_size * y_size):
 
 if stats:
     sst.setStatisticOutput("sst.statOutputCSV")
-    sst.enableAllStatisticsForAllComponents()
+    sst.enableAllStatisticsForAllComponents({"rate": stat_rate} if stat_rate else {})
     sst.setStatisticLoadLevel(2)
