@@ -174,6 +174,13 @@ def main():
         probe_objs.append(obj)
         tasks.append((p, obj, probe_flags))
 
+    # reference-side bindings of the C ABI (integration/*.cc): ELI plugins for stock SST that call libsstb200.so
+    shim_objs = []
+    for p in sorted((HERE.parent / "integration").glob("*.cc")):
+        obj = OUT / "obj" / "integration" / (p.stem + ".o")
+        shim_objs.append(obj)
+        tasks.append((p, obj, probe_flags + [f"-I{HERE.parent / 'include'}"]))
+
     print(f"[build_ref] {len(tasks)} translation units, {jobs} jobs", flush=True)
     with cf.ThreadPoolExecutor(jobs) as ex:
         list(ex.map(compile_one, tasks))
@@ -187,6 +194,10 @@ def main():
     run(["g++", "-shared", "-o", str(libdir / "libcoreTestElement.so"), *map(str, te_objs)])
     if probe_objs:
         run(["g++", "-shared", "-o", str(libdir / "libpdes.so"), *map(str, probe_objs)])
+    product = HERE.parent / "sst_core_b200"
+    if shim_objs and (product / "libsstb200.so").exists():
+        run(["g++", "-shared", "-o", str(libdir / "libb200.so"), *map(str, shim_objs), f"-L{product}", "-lsstb200",
+             "-Wl,-rpath,$ORIGIN/../../../../sst_core_b200"])
     etc = OUT / "etc" / "sst"
     etc.mkdir(parents=True, exist_ok=True)
     (etc / "sstsimulator.conf").write_text(f"[SSTCore]\nprefix={OUT}\nlibdir={libdir}\n")
