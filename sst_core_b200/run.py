@@ -188,7 +188,30 @@ def main(argv: Optional[list] = None) -> int:
         ckpt["checkpoint_writer"] = checkpoint.CheckpointWriter(a.output_directory, a.checkpoint_prefix, recipe, m)
         if reg is not None:
             ckpt["checkpoint_writer"].next_id = reg["checkpoint_id"] + 1
-    res, st = simulate_model(m, device=a.device, extras=extras, **ckpt, **opts)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # under torchrun: one process per GPU, the model cut by sst.linear, results gathered on rank 0
+        #   python -m torch.distributed.run --nproc-per-node N -m sst_core_b200 [options] model.py
+        if tools or ckpt or m.stat_rate:
+            print("FATAL: profiling, checkpoints and periodic statistics are single-GPU options for now", file=sys.stderr)
+            return 1
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        try:
+            part, st, m = simulate_distributed(m, **opts)  # m: renumbered so that every rank owns a contiguous range
+            parts = [None] * world if dist.get_rank() == 0 else None
+            dist.gather_object(part, parts, dst=0)
+            if dist.get_rank() != 0:
+                return 0
+            res = np.concatenate(parts, axis=0)
+        finally:
+            dist.barrier()
+            dist.destroy_process_group()
+    else:
+        res, st = simulate_model(m, device=a.device, extras=extras, **ckpt, **opts)
     for line in output.finish_lines(m, res, st.end_time):
         print(line)
     if tools:

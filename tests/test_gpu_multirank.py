@@ -64,3 +64,34 @@ def test_real_multi_gpu_nccl_ranks():
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTI_GPU_OK" in r.stdout
+
+
+def test_cli_under_torchrun_prints_what_the_reference_prints(tmp_path):
+    """python -m torch.distributed.run -m sst_core_b200 model.py: one process per GPU, console output and
+    StatisticOutput.csv against the reference's golden file / fixtures"""
+    import json
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = 2 if n < 4 else 4
+    gold = json.loads((ROOT / "tests" / "golden" / "reference_golden.json").read_text())
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", PYTHONPATH=str(ROOT))
+
+    def cli(*args):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                            "--master-addr", "127.0.0.1", "--master-port", "29619", "-m", "sst_core_b200", *args],
+                           capture_output=True, text=True, timeout=600, env=env, cwd=tmp_path)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+        return r.stdout
+
+    out = cli("--model-options", "6 6", str(ROOT / "tests/models/mesh.py"))
+    want = [f"{i} received {c} messages" for i, c in gold["mesh_6x6_10us"]["counts"].items()]
+    want.append("Simulation is complete, simulated time: 10 us")
+    assert sorted(l for l in out.strip().splitlines() if "received" in l or "Simulation is" in l) == sorted(want)
+    cli("--stop-at", "100ns", "--model-options", "3 3 1 1 2 1", str(ROOT / "tests/models/mesh.py"))
+    rows = (tmp_path / "StatisticOutput.csv").read_text().strip().splitlines()
+    ref_rows = gold["mesh_3x3_100ns_csv"]["rows"]
+    # the Rank column holds the GPU that owns the component here (the fixture was written by a one-rank run)
+    strip_rank = lambda rr: [", ".join(x.split(", ")[:5] + x.split(", ")[6:]) for x in rr]
+    assert strip_rank(rows) == strip_rank(ref_rows)
