@@ -101,3 +101,158 @@ def run_with_checkpoints(engine, period: int, writer: Optional[CheckpointWriter]
             if writer is not None:
                 writer.write(engine, st.now, engine_opts)
             nxt = (st.now // period + 1) * period
+
+
+# ------------------------------------------------------------------------------------------------ repartitioned restart
+# A checkpoint written on N ranks restarted on M (testsuite_default_Checkpoint.py:175-193 restarts MessageMesh runs on
+# other rank/thread counts).  The blob format is that of sstb200_engine_checkpoint_save (sst_core_b200/csrc/engine.cu):
+# 15 u64 header words -- magic, ABI version, number of sections, then n_local, nport_local, c0, P0, W, cap,
+# state_stride, aux_stride, has_payload, n_ranks, rank, window -- then per section a byte count and the bytes, padded
+# to 8: ctrl, ctl, state, aux, bin_count, ev, [ev_payload], [outbox, inbox, gathered], [prof_recv, prof_clock].
+# Per-component arrays are re-sliced; calendar records carry GLOBAL destination ports, so each goes to the bin
+# (same window slot, block of its destination component) of the rank that owns that component now; counters are summed
+# onto rank 0.  Requires both partitions to keep the model's component numbering (sst.linear over contiguous groups).
+_MAGIC = 0x4330303242545353
+_HDR = 15
+_CTRL = np.dtype([("k", "<u8"), ("T", "<u8"), ("T_end", "<u8"), ("stop_at", "<u8"), ("w", "<u8"),
+                  ("events_delivered", "<u8"), ("clock_ticks", "<u8"), ("events_sent", "<u8"), ("max_bin_fill", "<u8"),
+                  ("max_due", "<u8"), ("end_time", "<u8"), ("done", "<u4"), ("error", "<u4"), ("error_info", "<u8", 4),
+                  ("local", "<i8", 8), ("trace_n", "<u8"), ("windows", "<u8"), ("had_primary", "<u4"), ("pad", "<u4"),
+                  ("report_at", "<u8")])
+_NEVER = np.uint64(0xFFFFFFFFFFFFFFFF)
+_BLOCK = 256
+_XHDR = 10
+
+
+def _parse_blob(blob: np.ndarray) -> dict:
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    h = blob[:_HDR * 8].view("<u8")
+    if h[0] != _MAGIC:
+        raise ValueError("not a checkpoint of this engine")
+    names = ["n_local", "nport_local", "c0", "P0", "W", "cap", "state_stride", "aux_stride", "has_payload", "n_ranks",
+             "rank", "window"]
+    g = {n: int(v) for n, v in zip(names, h[3:15])}
+    secs, pos = [], _HDR * 8
+    for _ in range(int(h[2])):
+        n = int(blob[pos:pos + 8].view("<u8")[0])
+        secs.append(blob[pos + 8:pos + 8 + n])
+        pos += 8 + ((n + 7) & ~7)
+    order = ["ctrl", "ctl", "state", "aux", "bin_count", "ev"] + (["ev_payload"] if g["has_payload"] else []) + \
+            (["outbox", "inbox", "gathered"] if g["n_ranks"] > 1 else [])
+    rest = len(secs) - len(order)
+    if rest not in (0, 2) or int(h[1]) != 1:
+        raise ValueError("unexpected checkpoint layout")
+    order += ["prof_recv", "prof_clock"] if rest == 2 else []
+    return {"abi": int(h[1]), "geom": g, **dict(zip(order, secs))}
+
+
+def _build_blob(abi: int, geom: dict, sections: list) -> np.ndarray:
+    names = ["n_local", "nport_local", "c0", "P0", "W", "cap", "state_stride", "aux_stride", "has_payload", "n_ranks",
+             "rank", "window"]
+    parts = [np.array([_MAGIC, abi, len(sections)] + [geom[n] for n in names], dtype="<u8").view(np.uint8)]
+    for s in sections:
+        b = np.ascontiguousarray(s).view(np.uint8).reshape(-1)
+        parts.append(np.array([b.size], dtype="<u8").view(np.uint8))
+        parts.append(b)
+        if b.size % 8:
+            parts.append(np.zeros(8 - b.size % 8, dtype=np.uint8))
+    return np.concatenate(parts)
+
+
+def repartition_checkpoints(blobs, model: WiredModel, new_rank_of_component: np.ndarray, n_new: int,
+                            outbox_capacity: int = 65536):
+    """``blobs``: the old ranks' checkpoints in rank order; ``model``: the wired model in the numbering both partitions
+    use; ``new_rank_of_component``: the new owner of every component (non-decreasing).  Returns the ``n_new`` blobs to
+    ``Engine.restore`` into engines created for the new partition with the same calendar_slots / bin_capacity /
+    handler_counts and ``outbox_capacity``."""
+    old = [_parse_blob(b) for b in blobs]
+    g0 = old[0]["geom"]
+    for i, o in enumerate(old):
+        g = o["geom"]
+        if g["rank"] != i or g["n_ranks"] != len(old) or any(g[k] != g0[k] for k in
+                                                             ("W", "cap", "state_stride", "aux_stride", "has_payload", "window")):
+            raise ValueError("the checkpoints are not the rank-ordered parts of one run")
+    ncomp = model.ncomp
+    if sum(o["geom"]["n_local"] for o in old) != ncomp or old[0]["geom"]["c0"] != 0:
+        raise ValueError("the checkpoints do not cover the model")
+    new_rank = np.asarray(new_rank_of_component, dtype=np.int64)
+    if new_rank.shape != (ncomp,) or (np.diff(new_rank) < 0).any():
+        raise ValueError("the new partition must own contiguous component ranges in the model's numbering")
+    begins = np.searchsorted(new_rank, np.arange(n_new + 1)).astype(np.int64)
+    port_off = model.port_off.astype(np.int64)
+    W, cap, ss, as_, has_pl = g0["W"], g0["cap"], g0["state_stride"], g0["aux_stride"], g0["has_payload"]
+
+    ctrl_old = [o["ctrl"].view(_CTRL)[0] for o in old]
+    if any(c["error"] for c in ctrl_old):
+        raise ValueError("a rank had reported an error when the checkpoint was taken")
+    if sum(int(c["local"][1]) for c in ctrl_old) != ncomp:
+        raise ValueError("some primary components have already finished: their ranks cannot be told apart any more")
+    cat = lambda key: np.concatenate([o[key] for o in old])
+    ctl, state, aux = cat("ctl").reshape(ncomp, 32), cat("state").reshape(ncomp, ss), cat("aux").reshape(ncomp, as_)
+    prof = "prof_recv" in old[0]
+    if prof:
+        prof_recv, prof_clock = cat("prof_recv").view("<u8"), cat("prof_clock").view("<u8")
+
+    # every record of every bin of every old rank, with its window slot
+    rec_all, pay_all, slot_all = [], [], []
+    for o in old:
+        nb = max(1, -(-o["geom"]["n_local"] // _BLOCK))
+        cnt = o["bin_count"].view("<u4").reshape(W, nb).astype(np.int64)
+        ev = o["ev"].view("<u8").reshape(W, nb, cap, 2)
+        live = np.arange(cap)[None, None, :] < cnt[:, :, None]
+        rec_all.append(ev[live])
+        slot_all.append(np.broadcast_to(np.arange(W)[:, None, None], live.shape)[live])
+        if has_pl:
+            pay_all.append(o["ev_payload"].view("<u8").reshape(W, nb, cap)[live])
+    rec, slot = np.concatenate(rec_all), np.concatenate(slot_all)
+    pay = np.concatenate(pay_all) if has_pl else None
+    dst_comp = np.searchsorted(port_off, (rec[:, 1] >> np.uint64(32)).astype(np.int64), side="right") - 1
+    dst_rank = new_rank[dst_comp]
+
+    out = []
+    for r in range(n_new):
+        c0, c1 = int(begins[r]), int(begins[r + 1])
+        n_local, nb = c1 - c0, max(1, -(-(c1 - c0) // _BLOCK))
+        sel = np.nonzero(dst_rank == r)[0]
+        b = (dst_comp[sel] - c0) // _BLOCK
+        key = slot[sel] * nb + b
+        order = np.argsort(key, kind="stable")
+        sel, key = sel[order], key[order]
+        counts = np.bincount(key, minlength=W * nb)
+        if counts.size and counts.max() > cap:
+            raise ValueError(f"a calendar bin of the new partition would overflow ({counts.max()} > {cap})")
+        first = np.concatenate([[0], np.cumsum(counts)[:-1]])
+        within = np.arange(sel.size) - first[key]
+        ev = np.zeros((W * nb, cap, 2), dtype="<u8")
+        ev[key, within] = rec[sel]
+        secs = []
+        c = np.zeros(1, dtype=_CTRL)[0]
+        for f in ("k", "T", "T_end", "stop_at", "w", "end_time", "done", "windows", "had_primary"):
+            c[f] = ctrl_old[0][f]
+        c["report_at"] = _NEVER
+        c["max_bin_fill"] = max(int(x["max_bin_fill"]) for x in ctrl_old)
+        c["max_due"] = max(int(x["max_due"]) for x in ctrl_old)
+        if r == 0:
+            for f in ("events_delivered", "clock_ticks", "events_sent"):
+                c[f] = sum(int(x[f]) for x in ctrl_old)
+            c["local"][0] = sum(int(x["local"][0]) for x in ctrl_old)  # pending = sent - delivered, only the sum counts
+        ctl_r = np.ascontiguousarray(ctl[c0:c1])
+        c["local"][1] = n_local
+        c["local"][2] = int((ctl_r.view("<u8").reshape(-1, 4)[:, 0] != _NEVER).sum()) if n_local else 0
+        c["local"][4] = max(int(x["local"][4]) for x in ctrl_old)
+        secs += [np.array([c], dtype=_CTRL).view(np.uint8), ctl_r, state[c0:c1], aux[c0:c1],
+                 counts.astype("<u4"), ev]
+        if has_pl:
+            pl = np.zeros((W * nb, cap), dtype="<u8")
+            pl[key, within] = pay[sel]
+            secs.append(pl)
+        if n_new > 1:
+            xw = _XHDR + 4 * outbox_capacity
+            secs += [np.zeros(n_new * xw, dtype="<u8"), np.zeros(n_new * xw, dtype="<u8"), np.zeros(n_new * 8, dtype="<i8")]
+        if prof:
+            secs += [prof_recv[int(port_off[c0]):int(port_off[c1])], prof_clock[c0:c1]]
+        geom = {"n_local": n_local, "nport_local": int(port_off[c1] - port_off[c0]), "c0": c0, "P0": int(port_off[c0]),
+                "W": W, "cap": cap, "state_stride": ss, "aux_stride": as_, "has_payload": has_pl, "n_ranks": n_new,
+                "rank": r, "window": g0["window"]}
+        out.append(_build_blob(old[0]["abi"], geom, secs))
+    return out

@@ -161,3 +161,50 @@ def test_cli_checkpoint_directories_and_restart(tmp_path):
     assert sorted(p.name for p in d.iterdir()) == ["ck_2_8000000.sstcpt", "ck_2_8000000_0_0.bin"]
     out2 = _cli(["--load-checkpoint", str(tmp_path / "ck" / "ck_1_4000000" / "ck_1_4000000.sstcpt")], tmp_path)
     assert sorted(out2.strip().splitlines()) == sorted(want)
+
+
+@pytest.mark.parametrize("n_old,n_new", [(3, 1), (3, 2), (1, 4), (2, 5)])
+def test_restart_on_another_number_of_ranks(n_old, n_new):
+    """testsuite_default_Checkpoint.py:175-193 restarts runs on other rank counts: the old ranks' blobs are re-cut by
+    checkpoint.repartition_checkpoints; the restarted run ends bit-identically to the oracle (ranks share one GPU here)"""
+    from sst_core_b200 import checkpoint
+    from sst_core_b200.engine import partition_model
+    for m, opts, k in [(models.phold_model(24, 23, stop_at="120ns", stats_enabled=True), dict(calendar_slots=16), 37),
+                       (models.mesh_model(28, 21, stop_at="90ns", stats_enabled=True), dict(handler_counts=True), 40),
+                       (models.clockpop_model(25, 22, stop_at="300ns", comm_freq=5, stats_enabled=True), dict(calendar_slots=4), 111)]:
+        ref = O.run_model(m)
+        if n_old > 1:
+            a = LocalMultiRankRunner(m, n_old, **opts)
+            a.setup()
+            a.run(max_windows=k, check_every=k)
+            assert np.array_equal(a.pm.orig_id, np.arange(m.ncomp))  # sst.linear kept the numbering
+            blobs = [e.checkpoint().copy() for e in a.engines]
+            a.close()
+        else:
+            e = Engine(m, **opts)
+            e.setup()
+            e.run(max_windows=k, check_every=k)
+            blobs = [e.checkpoint().copy()]
+            e.close()
+        pm = partition_model(m, n_new)
+        new = checkpoint.repartition_checkpoints(blobs, m, pm.rank, n_new)
+        if n_new > 1:
+            b = LocalMultiRankRunner(m, n_new, **opts)
+            for e, blob in zip(b.engines, new):
+                e.restore(blob)
+            b.run()
+            res = b.results()
+            if opts.get("handler_counts"):
+                recv = np.concatenate([e.handler_counts()[0] for e in b.engines])
+                assert int(recv.sum()) == ref.events
+            b.close()
+        else:
+            e = Engine(m, **opts)
+            e.restore(new[0])
+            e.run()
+            st = e.status()
+            e.raise_on_error(st)
+            res = e.results()
+            assert (st.events_delivered, st.clock_ticks, st.end_time) == (ref.events, ref.ticks, ref.end_time)
+            e.close()
+        assert np.array_equal(res, ref.results), (n_old, n_new, int(m.comp_type[0]))
