@@ -83,16 +83,32 @@ def read_partition(reg: dict, rank: int = 0) -> np.ndarray:
     return np.fromfile(os.path.join(reg["directory"], reg["partition_files"][rank]), dtype=np.uint8)
 
 
+def blob_for_rank(reg: dict, model: WiredModel, rank: int, n_ranks: int, outbox_capacity: int = 0) -> np.ndarray:
+    """The state blob rank ``rank`` of ``n_ranks`` restores from: its own partition file when the checkpoint was taken
+    on the same number of ranks, else the old ranks' blobs re-cut for the new partition (``model`` = the partitioned
+    model of the NEW run; both partitions must keep the script's component numbering)."""
+    if int(reg["ranks"]) == n_ranks:
+        return read_partition(reg, rank)
+    if model.orig_id is not None and not np.array_equal(model.orig_id, np.arange(model.ncomp)):
+        raise ValueError("this partition renumbers the components: a checkpoint cannot be re-cut onto it")
+    new_rank = model.rank if model.rank is not None else np.zeros(model.ncomp, dtype=np.int64)
+    blobs = [read_partition(reg, r) for r in range(int(reg["ranks"]))]
+    return repartition_checkpoints(blobs, model, new_rank, n_ranks, outbox_capacity or 65536)[rank]
+
+
 def run_with_checkpoints(engine, period: int, writer: Optional[CheckpointWriter], engine_opts: dict,
-                         first_at: Optional[int] = None) -> None:
-    """Run a set-up (or restored) single-rank engine to the end, writing a checkpoint at the first window boundary at
-    or after every multiple of ``period`` cycles (CheckpointAction::execute, checkpointAction.cc:143-152)."""
+                         first_at: Optional[int] = None, runner=None) -> None:
+    """Run a set-up (or restored) engine to the end, writing a checkpoint at the first window boundary at or after
+    every multiple of ``period`` cycles (CheckpointAction::execute, checkpointAction.cc:143-152).  ``runner``: what
+    steps the windows -- the engine itself on one GPU, a DistributedRunner when every rank of a torch.distributed world
+    calls this (each rank writes its own partition file, rank 0 the registry)."""
+    runner = runner or engine
     st = engine.status()
     w = engine.window()
     nxt = first_at if first_at is not None else (st.now // period + 1) * period
     while True:
         windows = max(1, -(-(nxt - st.now) // w))
-        finished = engine.run(max_windows=windows, check_every=min(windows, 64))
+        finished = runner.run(max_windows=windows, check_every=min(windows, 64))
         st = engine.status()
         engine.raise_on_error(st)
         if finished or st.finished:

@@ -95,9 +95,13 @@ def simulate_model(m: wireup.WiredModel, device: int = 0, auto_tune: bool = True
     raise EngineError("auto-tuning did not converge")
 
 
-def simulate_distributed(m: wireup.WiredModel, **engine_opts):
+def simulate_distributed(m: wireup.WiredModel, extras: Optional[dict] = None, checkpoint_period: int = 0,
+                         checkpoint_writer=None, restore_registry: Optional[dict] = None, **engine_opts):
     """Run a WiredModel partitioned over the ranks of the initialised torch.distributed world (one GPU per rank).
-    Returns (results of THIS rank's components, Status, partitioned model)."""
+    Returns (results of THIS rank's components, Status, partitioned model).  ``extras["handler_counts"]`` (with
+    ``handler_counts=True``): this rank's counters.  ``checkpoint_period`` / ``checkpoint_writer(rank, n, pm)``: every
+    rank writes its partition file, rank 0 the registry.  ``restore_registry``: continue from a checkpoint -- taken on
+    any number of ranks -- instead of running setup()."""
     import torch
     import torch.distributed as dist
 
@@ -112,10 +116,20 @@ def simulate_distributed(m: wireup.WiredModel, **engine_opts):
     with torch.cuda.stream(stream):
         e = Engine(pm, device=dev, rank=r, n_ranks=n, stream=stream.cuda_stream, **engine_opts)
         try:
-            e.setup()
-            DistributedRunner(e).run()
+            if restore_registry is not None:
+                e.restore(checkpoint.blob_for_rank(restore_registry, pm, r, n, engine_opts.get("outbox_capacity", 0)))
+            else:
+                e.setup()
+            runner = DistributedRunner(e)
+            if checkpoint_period:
+                writer = checkpoint_writer(r, n, pm) if checkpoint_writer else None
+                checkpoint.run_with_checkpoints(e, checkpoint_period, writer, engine_opts, runner=runner)
+            else:
+                runner.run()
             st = e.status()
             e.raise_on_error(st)
+            if extras is not None and engine_opts.get("handler_counts"):
+                extras["handler_counts"] = e.handler_counts()
             return e.results(result_words(pm)), st, pm
         finally:
             e.close()
@@ -176,24 +190,30 @@ def main(argv: Optional[list] = None) -> int:
     extras = {}
     if tools:
         opts["handler_counts"] = True
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     ckpt = {}
+    recipe = None
     if reg is not None:
         opts = dict(reg["engine_opts"])
-        ckpt["restore_blob"] = checkpoint.read_partition(reg, 0)
     if a.checkpoint_sim_period:
         from .timelord import TimeLord
         recipe = {"script": os.path.abspath(a.script), "model_options": a.model_options, "stop_at": a.stop_at,
                   "timebase": a.timebase, "enable_profiling": a.enable_profiling}
         ckpt["checkpoint_period"] = TimeLord(m.timebase).cycles(a.checkpoint_sim_period)
-        ckpt["checkpoint_writer"] = checkpoint.CheckpointWriter(a.output_directory, a.checkpoint_prefix, recipe, m)
+
+    wired = m  # the fingerprint in the registry is that of the model as wired from the script, before any renumbering
+
+    def make_writer(rank, n_ranks, _partitioned=None):
+        w = checkpoint.CheckpointWriter(a.output_directory, a.checkpoint_prefix, recipe, wired, rank=rank, n_ranks=n_ranks)
         if reg is not None:
-            ckpt["checkpoint_writer"].next_id = reg["checkpoint_id"] + 1
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+            w.next_id = reg["checkpoint_id"] + 1
+        return w
+
     if world > 1:
         # under torchrun: one process per GPU, the model cut by sst.linear, results gathered on rank 0
         #   python -m torch.distributed.run --nproc-per-node N -m sst_core_b200 [options] model.py
-        if tools or ckpt or m.stat_rate:
-            print("FATAL: profiling, checkpoints and periodic statistics are single-GPU options for now", file=sys.stderr)
+        if m.stat_rate:
+            print("FATAL: periodic statistic output is a single-GPU option for now", file=sys.stderr)
             return 1
         import torch
         import torch.distributed as dist
@@ -201,16 +221,25 @@ def main(argv: Optional[list] = None) -> int:
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         try:
-            part, st, m = simulate_distributed(m, **opts)  # m: renumbered so that every rank owns a contiguous range
+            if recipe is not None:
+                ckpt["checkpoint_writer"] = make_writer
+            # m: renumbered so that every rank owns a contiguous range
+            part, st, m = simulate_distributed(m, extras=extras, restore_registry=reg, **ckpt, **opts)
             parts = [None] * world if dist.get_rank() == 0 else None
-            dist.gather_object(part, parts, dst=0)
+            dist.gather_object((part, extras.get("handler_counts")), parts, dst=0)
             if dist.get_rank() != 0:
                 return 0
-            res = np.concatenate(parts, axis=0)
+            res = np.concatenate([p[0] for p in parts], axis=0)
+            if tools:
+                extras["handler_counts"] = tuple(np.concatenate([p[1][i] for p in parts]) for i in (0, 1))
         finally:
             dist.barrier()
             dist.destroy_process_group()
     else:
+        if reg is not None:
+            ckpt["restore_blob"] = checkpoint.blob_for_rank(reg, m, 0, 1)
+        if recipe is not None:
+            ckpt["checkpoint_writer"] = make_writer(0, 1, m)
         res, st = simulate_model(m, device=a.device, extras=extras, **ckpt, **opts)
     for line in output.finish_lines(m, res, st.end_time):
         print(line)

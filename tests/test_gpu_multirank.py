@@ -95,3 +95,39 @@ def test_cli_under_torchrun_prints_what_the_reference_prints(tmp_path):
     # the Rank column holds the GPU that owns the component here (the fixture was written by a one-rank run)
     strip_rank = lambda rr: [", ".join(x.split(", ")[:5] + x.split(", ")[6:]) for x in rr]
     assert strip_rank(rows) == strip_rank(ref_rows)
+
+
+def test_cli_under_torchrun_profiling_checkpoints_and_restart_on_other_rank_counts(tmp_path):
+    import json
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    gold = json.loads((ROOT / "tests" / "golden" / "reference_golden.json").read_text())
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", PYTHONPATH=str(ROOT))
+
+    def cli(n, *args):
+        head = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+                "127.0.0.1", "--master-port", "29621", "-m", "sst_core_b200"] if n > 1 else [sys.executable, "-m", "sst_core_b200"]
+        r = subprocess.run([*head, *args], capture_output=True, text=True, timeout=600, env=env, cwd=tmp_path)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+        return r.stdout
+
+    keep = lambda text: sorted(l for l in text.splitlines() if "received" in l or "Simulation is" in l)
+    mesh = str(ROOT / "tests/models/mesh.py")
+    # handler counts gathered from both ranks: the reference's profiling golden (component level)
+    cli(2, "--model-options", "4 4", "--profiling-output", "p.txt", "--enable-profiling",
+        "events:sst.profile.handler.event.count(level=component)[event]", mesh)
+    strip = lambda t: sorted(l for l in t.splitlines() if not l.startswith("  Simulation Input File"))
+    assert strip((tmp_path / "p.txt").read_text()) == strip(gold["profiling_4x4_event_component"]["text"])
+    # checkpoints written by 2 ranks; restart on 1 GPU (2 -> 1) and under torchrun (2 -> 2)
+    want = sorted([f"{i} received {c} messages" for i, c in gold["mesh_6x6_10us"]["counts"].items()]
+                  + ["Simulation is complete, simulated time: 10 us"])
+    out = cli(2, "--model-options", "6 6", "--checkpoint-sim-period", "4us", "--checkpoint-prefix", "two", mesh)
+    assert keep(out) == want
+    d = tmp_path / "two" / "two_1_4000000"
+    assert sorted(p.name for p in d.iterdir()) == ["two_1_4000000.sstcpt", "two_1_4000000_0_0.bin", "two_1_4000000_1_0.bin"]
+    assert keep(cli(1, "--load-checkpoint", str(d / "two_1_4000000.sstcpt"))) == want
+    assert keep(cli(2, "--load-checkpoint", str(d / "two_1_4000000.sstcpt"))) == want
+    # a single-GPU checkpoint restarted on 2 GPUs (1 -> 2)
+    cli(1, "--model-options", "6 6", "--checkpoint-sim-period", "7us", "--checkpoint-prefix", "one", mesh)
+    assert keep(cli(2, "--load-checkpoint", str(tmp_path / "one" / "one_1_7000000" / "one_1_7000000.sstcpt"))) == want
