@@ -156,6 +156,22 @@ def main():
             O.run_ref(script, opts, extra=extra, cwd=td)
             out[key] = {"source": f"sstsim.x {Path(script).name} '{opts}' {' '.join(extra)} StatisticOutput.csv",
                         "opts": opts, "rows": (Path(td) / "StatisticOutput.csv").read_text().strip().splitlines()}
+    # larger parity sizes, kept as digests: the threaded reference on a 128 x 128 mesh
+    # and on a 48 x 40 PHOLD torus
+    import hashlib
+    import numpy as np
+    txt = O.run_ref(REF_TESTS / "test_MessageMesh.py", "128 128", extra=["--stop-at=150ns"], threads=8)
+    counts = mesh_counts(txt)
+    arr = np.array([counts[i] for i in range(128 * 128)], dtype="<i4")
+    out["mesh_128x128_150ns_n8_digest"] = {"source": "sstsim.x -n 8 test_MessageMesh.py '128 128' --stop-at=150ns",
+                                           "sum": int(arr.sum()), "sha256": hashlib.sha256(arr.tobytes()).hexdigest()}
+    txt = O.run_ref(MODELS / "phold.py", "48 40 250ns", threads=4)
+    rows = sorted((int(m.group(1)), int(m.group(2)), m.group(3)) for m in
+                  re.finditer(r"^phold (\d+) recv (\d+) hash ([0-9a-f]+)", txt, re.M))
+    blob = "\n".join(f"{i} {r} {h}" for i, r, h in rows).encode()
+    out["phold_48x40_250ns_n4_digest"] = {"source": "sstsim.x -n 4 tests/models/phold.py '48 40 250ns'",
+                                          "components": len(rows), "recv_sum": sum(r for _, r, _ in rows),
+                                          "sha256": hashlib.sha256(blob).hexdigest()}
     (HERE / "reference_golden.json").write_text(json.dumps(out, indent=1, sort_keys=True))
     print("wrote", HERE / "reference_golden.json", (HERE / "reference_golden.json").stat().st_size, "bytes")
 
