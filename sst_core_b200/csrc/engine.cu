@@ -61,9 +61,9 @@ set_error(const std::string& s)
 constexpr int      BLOCK      = SSTB200_BLOCK; // components per CTA == threads per CTA
 constexpr uint64_t TIME_NEVER = ~0ull;
 #ifndef SSTB200_PARB
-#define SSTB200_PARB 6
+#define SSTB200_PARB 5
 #endif
-constexpr int      PARB       = SSTB200_PARB; // event-parallel phase: positions t, t+256, ... t+5*256 per thread
+constexpr int      PARB       = SSTB200_PARB; // event-parallel phase: positions t, t+256, ... t+4*256 per thread (1280 = the default staging capacity)
 constexpr uint32_t PAR_MAX_EVENTS = 100; // events of one component per window in the event-parallel form (<= MT_STAGE_MAX_PAIRS)
 
 enum : uint32_t { ERR_BIN_OVERFLOW = 1, ERR_SMEM_OVERFLOW = 2, ERR_TIME_FAULT = 3, ERR_OUTBOX_OVERFLOW = 4, ERR_TRACE_OVERFLOW = 5 };
@@ -1037,7 +1037,10 @@ dispatch_kernel(Dev d)
             ht_cnt[tid] = 0;
         }
         __syncthreads();
-        constexpr int MAXR = 6; // slots tid, tid+256, ... per thread in registers between the passes (1536 slots)
+#ifndef SSTB200_MAXR
+#define SSTB200_MAXR 5
+#endif
+        constexpr int MAXR = SSTB200_MAXR; // slots tid, tid+256, ... per thread in registers between the passes
         uint32_t      r_key[MAXR], r_rank[MAXR], r_ent[MAXR];
         auto          classify_out = [&](uint32_t e, uint32_t& ky_out, uint32_t& ent_out, uint32_t& rank_out) {
             // called by all 32 lanes of a warp together (lanes without a record carry the key 0xFFFFFFFF)
