@@ -361,6 +361,19 @@ class Engine:
         out[:, :w] = part
         return out, bool(fin.value)
 
+    def report_begin(self, report_time: int):
+        """Bracket the next window (dispatch .. advance) that contains ``report_time``: see run_to_report."""
+        _check(self._L.sstb200_engine_report_begin(self._h, int(report_time)), "engine_report_begin")
+
+    def report_end(self, words: int = 0) -> np.ndarray:
+        n = self.comp_end - self.comp_begin
+        w = words if words and words < NRESULT else NRESULT
+        part = np.zeros((n, w), dtype=np.uint64)
+        _check(self._L.sstb200_engine_report_end(self._h, _p(part), 0 if w == NRESULT else w), "engine_report_end")
+        out = np.zeros((n, NRESULT), dtype=np.uint64)
+        out[:, :w] = part
+        return out
+
     def window(self) -> int:
         """Lookahead window in cycles (the option, else the model's minimum link latency)."""
         if not getattr(self, "_window", 0):
@@ -449,6 +462,30 @@ class DistributedRunner:
             if max_windows and done_windows >= max_windows:
                 return False
 
+    def run_to_report(self, report_time: int, words: int = 0):
+        """Periodic statistic output across the ranks: run up to and including the window that contains
+        ``report_time`` and return (this rank's result records as of the END of that time, finished) -- (None, finished)
+        when the simulation ends first or the time is at/after stop-at.  Every rank calls it with the same time."""
+        e = self.e
+        st = e.status()
+        if st.finished:
+            return None, True
+        stop_at = int(e.model.stop_at)
+        if stop_at and report_time >= stop_at:
+            return None, False
+        w = e.window()
+        before = report_time // w - st.now // w
+        if before < 0:
+            raise EngineError("run_to_report: the report time lies before the current window")
+        if before and self.run(max_windows=before, check_every=min(before, 32)):
+            return None, True
+        e.report_begin(report_time)
+        self.step()
+        rec = e.report_end(words)
+        st = e.status()
+        e.raise_on_error(st)
+        return rec, bool(st.finished)
+
 
 class LocalMultiRankRunner:
     """All partitions of a model stepped by ONE process on ONE GPU: the same device code path as a multi-GPU run
@@ -503,6 +540,30 @@ class LocalMultiRankRunner:
                 return True
             if max_windows and done >= max_windows:
                 return False
+
+    def run_to_report(self, report_time: int):
+        """Periodic statistic output with every rank in this process: (records of all components in ENGINE id order as
+        of the END of ``report_time``, finished), or (None, finished) -- see DistributedRunner.run_to_report."""
+        st = self.engines[0].status()
+        if st.finished:
+            return None, True
+        stop_at = int(self.pm.stop_at)
+        if stop_at and report_time >= stop_at:
+            return None, False
+        w = self.engines[0].window()
+        before = report_time // w - st.now // w
+        if before < 0:
+            raise EngineError("run_to_report: the report time lies before the current window")
+        if before and self.run(max_windows=before, check_every=min(before, 16)):
+            return None, True
+        for e in self.engines:
+            e.report_begin(report_time)
+        self.step()
+        rec = np.concatenate([e.report_end() for e in self.engines], axis=0)
+        sts = [e.status() for e in self.engines]
+        for e, s_ in zip(self.engines, sts):
+            e.raise_on_error(s_)
+        return rec, all(s_.finished for s_ in sts)
 
     def results(self) -> np.ndarray:
         """Results of all components in ENGINE id order (use self.pm.orig_id to map back)."""

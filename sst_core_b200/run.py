@@ -105,7 +105,7 @@ def simulate_distributed(m: wireup.WiredModel, extras: Optional[dict] = None, ch
     import torch
     import torch.distributed as dist
 
-    from .engine import DistributedRunner, Engine, partition_model
+    from .engine import DistributedRunner, Engine, EngineError, partition_model
 
     n, r = dist.get_world_size(), dist.get_rank()
     pm = partition_model(m, n)
@@ -121,7 +121,21 @@ def simulate_distributed(m: wireup.WiredModel, extras: Optional[dict] = None, ch
             else:
                 e.setup()
             runner = DistributedRunner(e)
-            if checkpoint_period:
+            if pm.stat_rate and pm.stats_enabled and extras is not None:
+                if checkpoint_period:
+                    raise EngineError("periodic statistic output and checkpoints cannot be combined yet")
+                extras["periodic"] = []
+                t_next = (e.status().now // pm.stat_rate + 1) * pm.stat_rate
+                while True:
+                    rec, fin = runner.run_to_report(t_next, result_words(pm))
+                    if rec is None:
+                        break
+                    extras["periodic"].append((t_next, rec))
+                    t_next += pm.stat_rate
+                    if fin:
+                        break
+                runner.run()
+            elif checkpoint_period:
                 writer = checkpoint_writer(r, n, pm) if checkpoint_writer else None
                 checkpoint.run_with_checkpoints(e, checkpoint_period, writer, engine_opts, runner=runner)
             else:
@@ -212,9 +226,6 @@ def main(argv: Optional[list] = None) -> int:
     if world > 1:
         # under torchrun: one process per GPU, the model cut by sst.linear, results gathered on rank 0
         #   python -m torch.distributed.run --nproc-per-node N -m sst_core_b200 [options] model.py
-        if m.stat_rate:
-            print("FATAL: periodic statistic output is a single-GPU option for now", file=sys.stderr)
-            return 1
         import torch
         import torch.distributed as dist
         local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -226,10 +237,12 @@ def main(argv: Optional[list] = None) -> int:
             # m: renumbered so that every rank owns a contiguous range
             part, st, m = simulate_distributed(m, extras=extras, restore_registry=reg, **ckpt, **opts)
             parts = [None] * world if dist.get_rank() == 0 else None
-            dist.gather_object((part, extras.get("handler_counts")), parts, dst=0)
+            dist.gather_object((part, extras.get("handler_counts"), extras.get("periodic", [])), parts, dst=0)
             if dist.get_rank() != 0:
                 return 0
             res = np.concatenate([p[0] for p in parts], axis=0)
+            extras["periodic"] = [(t, np.concatenate([p[2][i][1] for p in parts], axis=0))
+                                  for i, (t, _) in enumerate(parts[0][2])]
             if tools:
                 extras["handler_counts"] = tuple(np.concatenate([p[1][i] for p in parts]) for i in (0, 1))
         finally:

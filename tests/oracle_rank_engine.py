@@ -43,6 +43,8 @@ class OracleRankEngine:
         self.gathered = torch.zeros(CW * n_ranks, dtype=torch.int64)
         self.k, self.done, self.end_time, self.windows = 0, False, 0, 0
         self.stop_at = int(pm.stop_at)
+        self.model = pm
+        self._report_at, self._snapshot = None, None
 
     # ---- Engine interface
     def setup(self):
@@ -58,9 +60,24 @@ class OracleRankEngine:
         t = (self.k + 1) * self.w
         return min(t, self.stop_at) if self.stop_at else t
 
+    def window(self):
+        return self.w
+
+    # periodic statistic output: bracket the window that contains the report time (Engine.report_begin/report_end)
+    def report_begin(self, report_time):
+        self._report_at = int(report_time)
+
+    def report_end(self, words=0):
+        self._report_at = None
+        return self._snapshot
+
     def dispatch(self):
         if self.done:
             return
+        n = 0
+        if self._report_at is not None and self.k * self.w <= self._report_at < self._t_end():
+            n = int(self.L.oracle_run_until(self.h, self._report_at + 1))  # everything with time <= the report time
+            self._snapshot = self.results()
         n = int(self.L.oracle_run_until(self.h, self._t_end()))
         rec = np.zeros((n, 4), dtype=np.uint64)
         if n:

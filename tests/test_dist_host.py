@@ -65,3 +65,63 @@ def test_two_rank_gloo_run_equals_serial_oracle(tmp_path, kind):
         assert end == ref.end_time
     assert np.array_equal(got, ref.results)
     assert ev == ref.events and ticks == ref.ticks
+
+
+def _report_worker(rank, world, port, kind, rate, out_dir):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    import torch.distributed as dist
+
+    from oracle_rank_engine import OracleRankEngine
+    from sst_core_b200 import models
+    from sst_core_b200.engine import DistributedRunner, partition_model
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pm = partition_model(_model(kind, models), world)
+    e = OracleRankEngine(pm, rank, world)
+    e.setup()
+    runner, t, snaps = DistributedRunner(e), rate, []
+    while True:
+        rec, fin = runner.run_to_report(t)
+        if rec is None:
+            break
+        snaps.append(rec)
+        t += rate
+        if fin:
+            break
+    runner.run()
+    np.save(os.path.join(out_dir, f"snaps_{rank}.npy"), np.array(snaps))
+    np.save(os.path.join(out_dir, f"res_{rank}.npy"), e.results())
+    np.save(os.path.join(out_dir, f"meta_{rank}.npy"), np.array([e.c0, e.c1], dtype=np.int64))
+    np.save(os.path.join(out_dir, f"orig_{rank}.npy"), pm.orig_id)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind,rate", [("mesh", 7000), ("phold", 13300), ("clockpop", 99999)])
+def test_two_rank_periodic_reports_equal_the_serial_oracle(tmp_path, kind, rate):
+    """DistributedRunner.run_to_report over gloo: every rank brackets the window that contains the report time; the
+    union of the ranks' snapshots equals the serial oracle stepped to the same times (report times inside windows)"""
+    from sst_core_b200 import models
+    from test_periodic_stats import oracle_periodic
+
+    world, port = 2, 31500 + (os.getpid() % 2000)
+    mp.spawn(_report_worker, args=(world, port, kind, rate, str(tmp_path)), nprocs=world, join=True)
+    m = _model(kind, models)
+    m.stat_rate = rate
+    want, final = oracle_periodic(m)
+    orig = np.load(tmp_path / "orig_0.npy")
+    snaps = [np.load(tmp_path / f"snaps_{r}.npy") for r in range(world)]
+    assert all(len(s) == len(want) for s in snaps) and len(want) >= 3
+    for i, (_, w) in enumerate(want):
+        got = np.zeros_like(w)
+        for r in range(world):
+            c0, c1 = np.load(tmp_path / f"meta_{r}.npy")
+            got[orig[c0:c1]] = snaps[r][i]
+        assert np.array_equal(got, w), (kind, i)
+    got = np.zeros_like(final)
+    for r in range(world):
+        c0, c1 = np.load(tmp_path / f"meta_{r}.npy")
+        got[orig[c0:c1]] = np.load(tmp_path / f"res_{r}.npy")
+    assert np.array_equal(got, final)

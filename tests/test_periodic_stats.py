@@ -119,3 +119,36 @@ def test_gpu_report_records_match_the_oracle_mid_window_and_in_both_forms():
         for (t, a), (_, b) in zip(got, want):
             assert np.array_equal(a, b), (rate, t)
         assert np.array_equal(res, final) and st.end_time == m.stop_at
+
+
+@pytest.mark.gpu
+def test_gpu_periodic_reports_over_three_partitions():
+    """the multi-rank bracket (report_begin, dispatch, exchange, ingest, advance, report_end) with the CUDA engine:
+    the union of the ranks' snapshots equals the serial oracle at report times inside windows"""
+    from sst_core_b200 import models
+    from sst_core_b200.engine import LocalMultiRankRunner
+    for m, opts, rate in [(models.phold_model(13, 11, stop_at="70ns", stats_enabled=True), dict(calendar_slots=16), 6100),
+                          (models.clockpop_model(10, 9, stop_at="300ns", comm_freq=5, stats_enabled=True), dict(calendar_slots=4), 41500),
+                          (models.mesh_model(18, 14, stop_at="50ns", stats_enabled=True), dict(), 3000)]:
+        m.stat_rate = rate
+        want, final = oracle_periodic(m)
+        r = LocalMultiRankRunner(m, 3, **opts)
+        r.setup()
+        t, got = rate, []
+        while True:
+            rec, fin = r.run_to_report(t)
+            if rec is None:
+                break
+            back = np.empty_like(rec)
+            back[r.pm.orig_id] = rec
+            got.append(back)
+            t += rate
+        r.run()
+        res = r.results()
+        back = np.empty_like(res)
+        back[r.pm.orig_id] = res
+        r.close()
+        assert len(got) == len(want)
+        for a, (_, b) in zip(got, want):
+            assert np.array_equal(a, b)
+        assert np.array_equal(back, final)
