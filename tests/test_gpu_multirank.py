@@ -131,3 +131,21 @@ def test_cli_under_torchrun_profiling_checkpoints_and_restart_on_other_rank_coun
     # a single-GPU checkpoint restarted on 2 GPUs (1 -> 2)
     cli(1, "--model-options", "6 6", "--checkpoint-sim-period", "7us", "--checkpoint-prefix", "one", mesh)
     assert keep(cli(2, "--load-checkpoint", str(tmp_path / "one" / "one_1_7000000" / "one_1_7000000.sstcpt"))) == want
+
+
+def test_cli_under_torchrun_periodic_statistics(tmp_path):
+    import json
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    gold = json.loads((ROOT / "tests" / "golden" / "reference_golden.json").read_text())
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", PYTHONPATH=str(ROOT))
+    key = "rate_phold_3x3_100ns"
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29623", "-m", "sst_core_b200", "--calendar-slots", "16",
+                        "--model-options", gold[key]["opts"], str(ROOT / "tests/models/phold.py")],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=tmp_path)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    rows = (tmp_path / "StatisticOutput.csv").read_text().strip().splitlines()
+    strip_rank = lambda rr: [", ".join(x.split(", ")[:5] + x.split(", ")[6:]) for x in rr]
+    assert strip_rank(rows) == strip_rank(gold[key]["rows"])
