@@ -217,3 +217,16 @@ def test_console_statistic_output_matches_reference():
     w = wireup.wire(config.build_graph(str(MODELS / "mesh.py"), "2 2 1 1 1 1"), stop_at_override="30ns")
     r = O.run_model(w)
     assert output.stat_lines_console(w, r.results) == GOLD["mesh_2x2_console_stats"]["lines"]
+
+
+def test_info_lists_every_registered_element(capsys):
+    """sst-info analogue: the native element table joined with the host halves (needs no GPU)"""
+    from sst_core_b200 import info
+    from sst_core_b200.elements import ELEMENTS
+    assert info.main([]) == 0
+    out = capsys.readouterr().out
+    for name in ELEMENTS:
+        assert f"ELEMENT {name} " in out
+    assert set(info.DOCS) == set(ELEMENTS)
+    assert info.main(["pdes.phold"]) == 0
+    assert capsys.readouterr().out.count("ELEMENT ") == 1
