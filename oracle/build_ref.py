@@ -189,6 +189,11 @@ def main():
     libexec.mkdir(exist_ok=True)
     exe = libexec / "sstsim.x"
     run(["g++", "-rdynamic", "-o", str(exe), *map(str, core_objs), *pyld, "-lz", "-ldl", "-lrt", "-lpthread", "-lm"])
+    # the reference's generator classes behind a tiny command-line driver (long-stream fixtures)
+    tool = HERE / "tools" / "rng_ref_driver.cc"
+    if tool.exists():
+        run(["g++", *probe_flags, "-rdynamic", "-o", str(libexec / "rng_ref_driver"), str(tool),
+             *[str(o) for o in core_objs if o.name != "main.o"], *pyld, "-lz", "-ldl", "-lrt", "-lpthread", "-lm"])
     libdir = OUT / "lib" / "sst-elements-library"
     libdir.mkdir(parents=True, exist_ok=True)
     run(["g++", "-shared", "-o", str(libdir / "libcoreTestElement.so"), *map(str, te_objs)])

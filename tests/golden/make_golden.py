@@ -172,6 +172,27 @@ def main():
     out["phold_48x40_250ns_n4_digest"] = {"source": "sstsim.x -n 4 tests/models/phold.py '48 40 250ns'",
                                           "components": len(rows), "recv_sum": sum(r for _, r, _ in rows),
                                           "sha256": hashlib.sha256(blob).hexdigest()}
+    # long streams of the reference's own generator classes (oracle/tools/rng_ref_driver.cc): the seeds and lengths
+    # tests/test_gpu_rng.py draws on the device, and 2^24 draws per generator in blocks of 2^20
+    import subprocess
+    drv = ROOT / "oracle" / "_ref" / "libexec" / "rng_ref_driver"
+    streams = []
+    base = {0: (1447, 0), 1: (1053, 1447), 2: (1447, 0)}
+    for kind, (s1, s2) in base.items():
+        cases = [(s1 + 3 * j, s2 + 5 * j, 5000) for j in (0, 1, 17, 63)] + \
+                [(s1 + j, s2 + 2 * j, 1 << 14) for j in (0, 65535, 12345)] + [(s1, s2, 1 << 24)]
+        for a, b, n in cases:
+            txt = subprocess.run([str(drv), str(kind), str(a), str(b), str(n)], capture_output=True, text=True, check=True).stdout
+            tot = re.search(r"total (\d+) first (\d+) last (\d+)", txt)
+            streams.append({"kind": kind, "s1": a, "s2": b, "n": n, "total": int(tot.group(1)), "first": int(tot.group(2)),
+                            "last": int(tot.group(3)), "blocks": [int(x) for x in re.findall(r"block \d+ (\d+)", txt)]})
+        txt = subprocess.run([str(drv), str(kind), str(s1), str(s2), str(100000), "u64"], capture_output=True, text=True, check=True).stdout
+        tot = re.search(r"total (\d+) first (\d+) last (\d+)", txt)
+        streams.append({"kind": kind, "s1": s1, "s2": s2, "n": 100000, "u64": True, "total": int(tot.group(1)),
+                        "first": int(tot.group(2)), "last": int(tot.group(3)), "blocks": []})
+    out["rng_reference_class_streams"] = {"source": "oracle/tools/rng_ref_driver.cc linked with the reference's rng/*.o: "
+                                                    "sum_i (i+1)*draw_i mod 2^64 (total and per 2^20-draw block)",
+                                          "streams": streams}
     (HERE / "reference_golden.json").write_text(json.dumps(out, indent=1, sort_keys=True))
     print("wrote", HERE / "reference_golden.json", (HERE / "reference_golden.json").stat().st_size, "bytes")
 
