@@ -193,6 +193,16 @@ def main():
     out["rng_reference_class_streams"] = {"source": "oracle/tools/rng_ref_driver.cc linked with the reference's rng/*.o: "
                                                     "sum_i (i+1)*draw_i mod 2^64 (total and per 2^20-draw block)",
                                           "streams": streams}
+    # the reference's distribution classes over its generators: 400 values each, as bit patterns of the doubles
+    dists = []
+    for d, params in [(0, [0.1, 0.3, 0.35, 0.15, 0.1]), (1, [1.25]), (2, [10.0, 2.5]), (3, [3.5]), (4, [7]), (5, [42.0])]:
+        for kind, (s1, s2) in base.items():
+            txt = subprocess.run([str(drv), "dist", str(d), str(kind), str(s1), str(s2), "400", *map(str, params)],
+                                 capture_output=True, text=True, check=True).stdout
+            dists.append({"dist": d, "params": params, "kind": kind, "s1": s1, "s2": s2, "bits": [int(x) for x in txt.split()]})
+    out["rng_reference_class_distributions"] = {"source": "oracle/tools/rng_ref_driver.cc dist ...: SST::RNG::*Distribution "
+                                                          "(rng/discrete.h, expon.h, gaussian.h, poisson.h, uniform.h, constant.h)",
+                                                "cases": dists}
     (HERE / "reference_golden.json").write_text(json.dumps(out, indent=1, sort_keys=True))
     print("wrote", HERE / "reference_golden.json", (HERE / "reference_golden.json").stat().st_size, "bytes")
 
