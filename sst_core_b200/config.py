@@ -449,3 +449,64 @@ def load_json(path: str, n_ranks: int = 1, my_rank: int = 0) -> ConfigGraph:
         g.link_by_name[cl.name] = cl
     return g
 
+
+def dump_json(g: ConfigGraph, path: str) -> None:
+    """Write a ConfigGraph in the reference's JSON interchange format (what ``sst --output-json`` writes,
+    ``model/cfgoutput/jsonConfigOutput.cc``), so that a model built through this module's ``sst`` surface can be run --
+    or partitioned, or inspected -- by stock SST: ``sst model.json``.  The inverse of :func:`load_json`; like the
+    reference's writer it records "all statistics enabled" per (sub)component but not their parameters."""
+    import json
+
+    all_on = g.enable_all_stats is not None
+
+    def stat_opts(c):
+        node = {}
+        if all_on or c.stats_enabled == "all":
+            node["statistics_options"] = {"enable_all_statistics": True}
+        elif isinstance(c.stats_enabled, list) and c.stats_enabled:
+            node["statistics"] = [{"name": n} for n in c.stats_enabled]
+        return node
+
+    def subs_of(c):
+        out = []
+        for sc in c.subs:
+            node = {"slot_name": sc.slot, "slot_number": int(sc.slot_num), "type": sc.type}
+            if sc.params:
+                node["params"] = dict(sc.params)
+            node.update(stat_opts(sc))
+            kids = subs_of(sc)
+            if kids:
+                node["subcomponents"] = kids
+            out.append(node)
+        return out
+
+    def indexed_name(c):
+        parts = []
+        while c.parent is not None:
+            parts.append(f"{c.slot}[{c.slot_num}]")
+            c = c.parent
+        return ":".join([c.name] + parts[::-1])
+
+    comps = []
+    for c in g.components:
+        node = {"name": c.name, "type": c.type}
+        node.update(stat_opts(c))
+        if c.params:
+            node["params"] = dict(c.params)
+        kids = subs_of(c)
+        if kids:
+            node["subcomponents"] = kids
+        comps.append(node)
+    links = []
+    for l in g.links:
+        node = {"name": l.name, "noCut": bool(l.no_cut), "nonlocal": False}
+        for side, (owner, port, lat) in zip(("left", "right"), l.ends):
+            node[side] = {"component": indexed_name(owner), "port": port, "latency": str(lat)}
+        links.append(node)
+    so = {"statisticLoadLevel": int(g.stat_load_level or 0), "statisticOutput": g.stat_output[0]}
+    if g.stat_output[1]:
+        so["params"] = dict(g.stat_output[1])
+    doc = {"program_options": dict(g.program_options), "statistics_options": so, "components": comps,
+           "statistics_group": [], "links": links}
+    with open(path, "w") as f:
+        json.dump(doc, f, indent=1)

@@ -167,6 +167,10 @@ def main(argv: Optional[list] = None) -> int:
     ap.add_argument("--checkpoint-prefix", default="checkpoint")
     ap.add_argument("--load-checkpoint", action="store_true",
                     help="the input file is a checkpoint registry (*.sstcpt): restart from it")
+    ap.add_argument("--output-json", default="", metavar="FILE",
+                    help="write the configuration graph in the reference's JSON interchange format (sst model.json)")
+    ap.add_argument("--run-mode", default="both", choices=["init", "run", "both"],
+                    help="init: build (and write) the graph only")
     ap.add_argument("--enable-profiling", default="",
                     help="name:type(key=value,...)[point,...];...  (handler count tools, see profile.py)")
     ap.add_argument("--profiling-output", default="", help="file for the profiling records (default: stdout)")
@@ -189,6 +193,12 @@ def main(argv: Optional[list] = None) -> int:
             g = config.build_graph(a.script, a.model_options)
         if a.timebase:
             g.program_options["timebase"] = a.timebase
+        if a.output_json:
+            if a.stop_at:
+                g.program_options["stop-at"] = a.stop_at
+            config.dump_json(g, os.path.join(a.output_directory, a.output_json))
+        if a.run_mode == "init":
+            return 0
         m = wireup.wire(g, stop_at_override=a.stop_at)
         if reg is not None and checkpoint.model_fingerprint(m) != reg["model_fingerprint"]:
             raise config.ModelError(f"the model rebuilt from {a.script} is not the one the checkpoint was taken from")
