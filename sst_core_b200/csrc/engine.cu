@@ -1467,14 +1467,6 @@ static const ElementInfo kElements[] = {
 };
 constexpr int kNumElements = (int)(sizeof(kElements) / sizeof(kElements[0]));
 
-static const ElementInfo*
-element_by_type(uint32_t t)
-{
-    for ( int i = 0; i < kNumElements; ++i )
-        if ( kElements[i].type == t ) return &kElements[i];
-    return nullptr;
-}
-
 } // namespace sstb200
 
 using namespace sstb200;
