@@ -295,6 +295,66 @@ def enableAllStatisticsForComponentType(ctype, params=None, recursive=False):
             c.stat_params = dict(params or {})
 
 
+def _named(name):
+    c = _g().comp_by_name.get(name)
+    if c is None:
+        raise ModelError(f"component name {name} not found")
+    return c
+
+
+def enableStatisticsForComponentName(name, stats, params=None, recursive=False):
+    """pymodel.cc enableStatisticsForComponentName: a list of statistic names (or one name) on the named component"""
+    c = _named(name)
+    names = [stats] if isinstance(stats, str) else list(stats)
+    cur = c.stats_enabled if isinstance(c.stats_enabled, list) else []
+    c.stats_enabled = cur + names if c.stats_enabled != "all" else "all"
+    c.stat_params = dict(params or {})
+
+
+def enableStatisticForComponentName(name, stat, params=None, recursive=False):
+    enableStatisticsForComponentName(name, [stat], params, recursive)
+
+
+def enableStatisticsForComponentType(ctype, stats, params=None, recursive=False):
+    names = [stats] if isinstance(stats, str) else list(stats)
+    for c in _g().components:
+        if c.type == ctype:
+            cur = c.stats_enabled if isinstance(c.stats_enabled, list) else []
+            c.stats_enabled = cur + names if c.stats_enabled != "all" else "all"
+            c.stat_params = dict(params or {})
+
+
+def enableStatisticForComponentType(ctype, stat, params=None, recursive=False):
+    enableStatisticsForComponentType(ctype, [stat], params, recursive)
+
+
+def setStatisticLoadLevelForComponentName(name, level, recursive=False):
+    _named(name).stat_load_level = int(level)
+
+
+def setStatisticLoadLevelForComponentType(ctype, level, recursive=False):
+    for c in _g().components:
+        if c.type == ctype:
+            c.stat_load_level = int(level)
+
+
+_T0 = __import__("time").perf_counter()
+
+
+def getElapsedExecutionTime():
+    """seconds since the front end started, as the reference's UnitAlgebra prints it ("<x> s")"""
+    return f"{__import__('time').perf_counter() - _T0:.6f} s"
+
+
+def getLocalMemoryUsage():
+    import resource
+    return f"{resource.getrusage(resource.RUSAGE_SELF).ru_maxrss} KB"
+
+
+def setCallPythonFinalize(flag):
+    pass  # interpreter shutdown policy of the embedded CPython: nothing to do here
+
+
 def findComponentByName(name):
     c = _g().comp_by_name.get(name)
     if c is None:
@@ -327,7 +387,9 @@ _API = [
     "setStatisticOutput", "setStatisticOutputOption", "setStatisticOutputOptions", "setStatisticLoadLevel",
     "enableAllStatisticsForAllComponents", "enableAllStatisticsForComponentName",
     "enableAllStatisticsForComponentType", "findComponentByName", "addSharedParam", "addSharedParams",
-    "addGlobalParam", "addGlobalParams", "exit",
+    "addGlobalParam", "addGlobalParams", "exit", "enableStatisticForComponentName", "enableStatisticsForComponentName",
+    "enableStatisticForComponentType", "enableStatisticsForComponentType", "setStatisticLoadLevelForComponentName",
+    "setStatisticLoadLevelForComponentType", "getElapsedExecutionTime", "getLocalMemoryUsage", "setCallPythonFinalize",
 ]
 
 

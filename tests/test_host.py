@@ -230,3 +230,33 @@ def test_info_lists_every_registered_element(capsys):
     assert set(info.DOCS) == set(ELEMENTS)
     assert info.main(["pdes.phold"]) == 0
     assert capsys.readouterr().out.count("ELEMENT ") == 1
+
+
+def test_sst_module_statistic_enabling_by_name_and_type(tmp_path):
+    """the by-name / by-type variants of the reference's statistics API (pymodel.cc function table)"""
+    from sst_core_b200 import config, wireup
+    src = ('import sst\n'
+           'a = sst.Component("a", "pdes.phold"); a.addParams({"id": 0})\n'
+           'b = sst.Component("b", "pdes.phold"); b.addParams({"id": 1})\n'
+           'c = sst.Component("c", "pdes.clocknode"); c.addParams({"id": 2})\n'
+           'sst.Link("l0").connect((a, "port0", "2ns"), (b, "port0", "2ns"))\n'
+           'sst.Link("l1").connect((b, "port1", "2ns"), (c, "port0", "2ns"))\n'
+           'sst.setProgramOption("stop-at", "50ns")\n'
+           'sst.enableStatisticForComponentName("a", "delay", {"rate": "10ns"})\n'
+           'sst.enableStatisticsForComponentType("pdes.clocknode", ["N", "S"])\n'
+           'sst.setStatisticLoadLevelForComponentName("b", 4)\n'
+           'sst.setStatisticLoadLevelForComponentType("pdes.phold", 3)\n'
+           'assert sst.getElapsedExecutionTime().endswith(" s") and sst.getLocalMemoryUsage().endswith(" KB")\n'
+           'sst.setCallPythonFinalize(True)\n')
+    p = tmp_path / "m.py"
+    p.write_text(src)
+    g = config.build_graph(str(p))
+    by = {c.name: c for c in g.components}
+    assert by["a"].stats_enabled == ["delay"] and by["a"].stat_params == {"rate": "10ns"}
+    assert by["b"].stats_enabled is None and by["c"].stats_enabled == ["N", "S"]
+    assert (by["a"].stat_load_level, by["b"].stat_load_level, by["c"].stat_load_level) == (3, 3, None)
+    m = wireup.wire(g)
+    assert m.stats_enabled and m.stat_rate == 10000
+    with pytest.raises(config.ModelError, match="component name zz not found"):
+        (tmp_path / "n.py").write_text(src + 'sst.enableStatisticForComponentName("zz", "delay")\n')
+        config.build_graph(str(tmp_path / "n.py"))
