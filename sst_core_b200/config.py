@@ -141,14 +141,25 @@ class _CompBase:
     def getType(self):
         return self._c.type
 
+    def _each(self, recursive):
+        todo = [self._c]
+        while todo:
+            c = todo.pop()
+            yield c
+            if recursive:
+                todo += c.subs
+
     def enableAllStatistics(self, params=None, recursive=False):
-        self._c.stats_enabled = "all"
-        self._c.stat_params = dict(params or {})
+        for c in self._each(recursive):
+            c.stats_enabled = "all"
+            c.stat_params = dict(params or {})
 
     def enableStatistics(self, names, params=None, recursive=False):
-        cur = self._c.stats_enabled if isinstance(self._c.stats_enabled, list) else []
-        self._c.stats_enabled = cur + list(names)
-        self._c.stat_params = dict(params or {})
+        for c in self._each(recursive):
+            if c.stats_enabled != "all":
+                cur = c.stats_enabled if isinstance(c.stats_enabled, list) else []
+                c.stats_enabled = cur + list(names)
+            c.stat_params = dict(params or {})
 
     def enableStatistic(self, name, params=None, recursive=False):
         self.enableStatistics([name], params)

@@ -48,12 +48,16 @@ def stat_rows_csv(m: WiredModel, results: np.ndarray, end_time: int, rank_of=Non
             rows += stat_rows_csv(m, rec, t_p)[1:]
         return rows + stat_rows_csv(m, results, end_time)[1:]
     order = np.argsort(m.orig_id) if m.orig_id is not None else np.arange(m.ncomp)
-    dtypes = {s.dtype for sl in m.stats for s in sl}
-    t = "u64" if dtypes <= {"u64"} else "i32" if dtypes <= {"i32"} else None
-    if t is None:
-        raise NotImplementedError("mixed statistic field types in one CSV are out of scope (statoutputcsv.cc)")
-    rows = [f"ComponentName, StatisticName, StatisticSubId, StatisticType, SimTime, Rank, "
-            f"Sum.{t}, SumSQ.{t}, Count.u64, Min.{t}, Max.{t}"]
+    # output fields are registered as the (enabled) statistics are created, component by component: an accumulator of
+    # type t brings Sum.t, SumSQ.t, Count.u64, Min.t, Max.t; Count.u64 is shared by all types (statoutput.cc
+    # registerField; observed: "Sum.u64, SumSQ.u64, Count.u64, Min.u64, Max.u64, Sum.i32, SumSQ.i32, Min.i32, Max.i32")
+    fields = []
+    for i in order:
+        for s in m.stats[i]:
+            for f in (f"Sum.{s.dtype}", f"SumSQ.{s.dtype}", "Count.u64", f"Min.{s.dtype}", f"Max.{s.dtype}"):
+                if f not in fields:
+                    fields.append(f)
+    rows = ["ComponentName, StatisticName, StatisticSubId, StatisticType, SimTime, Rank, " + ", ".join(fields)]
     for i in order:
         rk = int(m.rank[i]) if m.rank is not None else 0
         for s in m.stats[i]:
@@ -64,8 +68,9 @@ def stat_rows_csv(m: WiredModel, results: np.ndarray, end_time: int, rank_of=Non
                 if s.dtype == "i32":
                     vals = [_signed(vals[0], 32), _signed(vals[1], 32), vals[2], _signed(vals[3], 32),
                             _signed(vals[4], 32)]
+            mine = dict(zip((f"Sum.{s.dtype}", f"SumSQ.{s.dtype}", "Count.u64", f"Min.{s.dtype}", f"Max.{s.dtype}"), vals))
             rows.append(f"{s.owner_name}, {s.name}, {s.subid}, Accumulator, {end_time}, {rk}, "
-                        f"{vals[0]}, {vals[1]}, {vals[2]}, {vals[3]}, {vals[4]}")
+                        + ", ".join(str(mine.get(f, 0)) for f in fields))
     return rows
 
 

@@ -162,13 +162,34 @@ def wire(graph: ConfigGraph, stop_at_override: Optional[str] = None) -> WiredMod
     rates = {tl.cycles(r) for r in rates if r not in ("0", "0ns", "0 ns")}
     if len(rates) > 1:
         raise ModelError("statistics with different output rates in one model are not supported on the device engine")
+    # only ENABLED statistics exist for the output (a statistic that is not enabled is a NullStatistic in the reference,
+    # baseComponent.cc registerStatistic): everything when enableAllStatisticsForAllComponents was called, else what was
+    # enabled on the (sub)component that registers it -- all of its statistics, or the named ones
+    owners = {}
+
+    def index(c):
+        owners[c.full_name()] = c
+        for sc in c.subs:
+            index(sc)
+
+    for c in graph.components:
+        index(c)
+
+    def enabled(sd):
+        if graph.enable_all_stats is not None:
+            return True
+        o = owners.get(sd.owner_name)
+        return o is not None and (o.stats_enabled == "all" or (isinstance(o.stats_enabled, list) and sd.name in o.stats_enabled))
+
+    for w in wired:
+        w.stats = [sd for sd in w.stats if enabled(sd)]
     m = WiredModel(
         comp_type=np.array([w.type_code for w in wired], dtype=np.uint32),
         comp_param=np.array([w.params for w in wired], dtype=np.int64).reshape(ncomp, NPARAM),
         port_off=port_off, peer_port=peer_port, latency=latency,
         clock_period=np.array([w.clock_period for w in wired], dtype=np.uint64),
         stop_at=stop_at, timebase=tl.timebase_string,
-        stats_enabled=graph.enable_all_stats is not None or any(c.stats_enabled for c in graph.components),
+        stats_enabled=any(w.stats for w in wired),
         names=[c.name for c in graph.components],
         stats=[w.stats for w in wired], finish=[w.finish for w in wired],
         nocut_pairs=np.array(nocut, dtype=np.uint32).reshape(-1, 2),

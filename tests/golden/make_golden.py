@@ -203,6 +203,12 @@ def main():
     out["rng_reference_class_distributions"] = {"source": "oracle/tools/rng_ref_driver.cc dist ...: SST::RNG::*Distribution "
                                                           "(rng/discrete.h, expon.h, gaussian.h, poisson.h, uniform.h, constant.h)",
                                                 "cases": dists}
+    # statistics enabled on some components only (by object, by name, by type): only those are written, and field
+    # columns of both value types share one CSV
+    with tempfile.TemporaryDirectory() as td:
+        txt = O.run_ref(MODELS / "partial_stats.py", cwd=td)
+        out["partial_stats_csv"] = {"source": "sstsim.x tests/models/partial_stats.py StatisticOutput.csv",
+                                    "rows": (Path(td) / "StatisticOutput.csv").read_text().strip().splitlines()}
     (HERE / "reference_golden.json").write_text(json.dumps(out, indent=1, sort_keys=True))
     print("wrote", HERE / "reference_golden.json", (HERE / "reference_golden.json").stat().st_size, "bytes")
 

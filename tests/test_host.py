@@ -79,7 +79,9 @@ def test_script_wireup_equals_vectorised_builder(tmp_path, dims):
     assert canon(w.nocut_pairs) == canon(m.nocut_pairs)
     assert w.stop_at == m.stop_at == 10_000_000
     assert w.names[1] == "component1"
-    assert w.stats[0][0].owner_name == "component0:route"
+    assert w.stats[0] == [] and not w.stats_enabled  # nothing enabled: the statistics are NullStatistics
+    w1 = wireup.wire(config.build_graph(str(MODELS / "mesh.py"), dims.split()[0] + " " + dims.split()[1] + " 1 1 0 1"))
+    assert w1.stats[0][0].owner_name == "component0:route" and w1.stats_enabled
 
 
 def test_phold_and_clockpop_scripts_equal_builders():

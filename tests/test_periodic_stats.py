@@ -152,3 +152,21 @@ def test_gpu_periodic_reports_over_three_partitions():
         for a, (_, b) in zip(got, want):
             assert np.array_equal(a, b)
         assert np.array_equal(back, final)
+
+
+def test_only_enabled_statistics_are_written_and_field_types_mix():
+    """tests/models/partial_stats.py enables statistics by object, by name and by type on a mixed PHOLD / clocknode
+    model: the reference writes only those, u64 and i32 field columns side by side"""
+    m = wireup.wire(config.build_graph(str(ROOT / "tests/models/partial_stats.py")))
+    assert [len(s) for s in m.stats] == [1, 0, 1, 0, 2, 0]
+    run = O.run_model(m)
+    assert output.stat_rows_csv(m, run.results, run.end_time) == GOLD["partial_stats_csv"]["rows"]
+
+
+@pytest.mark.gpu
+def test_gpu_cli_partial_statistics(tmp_path):
+    r = subprocess.run([sys.executable, "-m", "sst_core_b200", "--calendar-slots", "8", str(ROOT / "tests/models/partial_stats.py")],
+                       capture_output=True, text=True, cwd=tmp_path,
+                       env={**__import__("os").environ, "PYTHONPATH": str(ROOT)}, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert (tmp_path / "StatisticOutput.csv").read_text().strip().splitlines() == GOLD["partial_stats_csv"]["rows"]
