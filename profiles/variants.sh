@@ -1,3 +1,7 @@
 #!/bin/bash
+# scratch script for one-off GPU experiments during kernel work (gpurun -- 'bash profiles/variants.sh'); the measurement
+# sets that produce the files under profiles/ are final.sh (one GPU), multi.sh (N GPUs), ncu_full.sh, ncu_traffic.sh,
+# timing.sh
 mkdir -p gpurun_out
-timeout 200 python -m pytest tests/test_gpu_multirank.py -m gpu -q -x --timeout 150 -k periodic > gpurun_out/pytest_multi.log 2>&1; echo "pytest exit $?"; tail -15 gpurun_out/pytest_multi.log
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
+import json,sys;d=json.loads(sys.stdin.read().strip().splitlines()[-1]);print('mesh',round(d['value']/1e9,2),round(d['ms_per_step'],4), round(d['roofline']['frac'],4))"
