@@ -100,7 +100,13 @@ public:
 
     void handleEvent(SST::Event* ev, int port)
     {
-        PholdEvent* pe = static_cast<PholdEvent*>(ev);
+        // an event of another element (pdes.clocknode sends payload-less events) counts as delay 0 and is replaced by
+        // a PHOLD event on its way on -- the device engine's events carry one 8-byte payload, 0 when the sender has none
+        PholdEvent* pe = dynamic_cast<PholdEvent*>(ev);
+        if ( !pe ) {
+            delete ev;
+            pe = new PholdEvent(0);
+        }
         recv_++;
         delay_->addData(pe->d);
         hash_      = mixDelivery(hash_, getCurrentSimCycle(), (uint64_t)port, pe->d);

@@ -209,6 +209,16 @@ def main():
         txt = O.run_ref(MODELS / "partial_stats.py", cwd=td)
         out["partial_stats_csv"] = {"source": "sstsim.x tests/models/partial_stats.py StatisticOutput.csv",
                                     "rows": (Path(td) / "StatisticOutput.csv").read_text().strip().splitlines()}
+    # irregular random models (mixed element types, 1..6 ports, different latencies at the two ends of a link): the
+    # PHOLD delivery hash is order-sensitive, so these pin per-component event ORDER on irregular graphs
+    with tempfile.TemporaryDirectory() as td:
+        cases = []
+        for opts in ("1 40 400ns", "2 40 400ns", "3 40 400ns", "6 17 900ns", "6 2 20ns"):
+            txt = O.run_ref(MODELS / "random_graph.py", opts, cwd=td)
+            cases.append({"opts": opts,
+                          "lines": sorted(l for l in txt.splitlines() if l.startswith(("phold", "clocknode", "Simulation is"))),
+                          "rows": (Path(td) / "StatisticOutput.csv").read_text().strip().splitlines()})
+        out["random_graphs"] = {"source": "sstsim.x tests/models/random_graph.py '<seed> <components> <stop>'", "cases": cases}
     (HERE / "reference_golden.json").write_text(json.dumps(out, indent=1, sort_keys=True))
     print("wrote", HERE / "reference_golden.json", (HERE / "reference_golden.json").stat().st_size, "bytes")
 
