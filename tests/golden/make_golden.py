@@ -213,7 +213,7 @@ def main():
     # PHOLD delivery hash is order-sensitive, so these pin per-component event ORDER on irregular graphs
     with tempfile.TemporaryDirectory() as td:
         cases = []
-        for opts in ("1 40 400ns", "2 40 400ns", "3 40 400ns", "6 17 900ns", "6 2 20ns"):
+        for opts in ("1 40 400ns", "2 40 400ns", "3 40 400ns", "6 17 900ns", "6 2 20ns", "4 25 333333ps", "9 33 100001ps"):
             txt = O.run_ref(MODELS / "random_graph.py", opts, cwd=td)
             cases.append({"opts": opts,
                           "lines": sorted(l for l in txt.splitlines() if l.startswith(("phold", "clocknode", "Simulation is"))),
