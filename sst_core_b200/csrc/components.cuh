@@ -98,10 +98,6 @@ mixDelivery(uint64_t h, uint64_t time, uint64_t port, uint64_t payload)
     return h;
 }
 
-#ifndef SSTB200_MESH_PREFETCH
-#define SSTB200_MESH_PREFETCH 2
-#endif
-
 #if defined(__CUDACC__)
 
 __device__ __forceinline__ void
@@ -114,157 +110,141 @@ prefetch_l2(const void* p)
 // coreTestElement.message_mesh.enclosing_component (+ message_port / port_slot / route_message subcomponents,
 // flattened).  Reference: testElements/message_mesh/enclosingComponent.cc:29-69 (ctor), :72-81 (setup), :92-99
 // (handleEvent), :164-199 (RouteMessage).
+//
+// Component record (RECORD_BYTES = 112; a block's 256 records are moved to shared memory by one bulk copy):
+//   [0,16)    mutable core: message_count, MT19937 position (index | buffer << 12), msg_count statistic
+//   [16,32)   construction constants
+//   [32,112)  route digest of the generator's current generation (rng.cuh): the port RouteMessage::send picks for the
+//             pair of draws starting at word 2j, 2 bits per pair.  The handler of an event is then a table look-up.
+// aux block: two 624-word MT19937 generations (rng.cuh MtGenDev).
+enum : uint32_t { MAINT_INIT = MT_OP_INIT, MAINT_REGEN = MT_OP_REGEN, MAINT_TAIL = MT_OP_TAIL };
+
 struct MeshElement
 {
     static constexpr uint32_t    TYPE         = TYPE_MESH;
     static constexpr const char* ELI_NAME     = "coreTestElement.message_mesh.enclosing_component";
-    static constexpr uint32_t    AUX_BYTES    = MT_N * 4;
+    static constexpr uint32_t    AUX_BYTES    = 2 * MT_N * 4;
     static constexpr bool        HAS_PAYLOAD  = false;
     // the aux block is a MersenneRNG state the engine seeds warp-cooperatively before construct() (seed_mt_kernel):
-    // RouteMessage ctor, MersenneRNG(my_id + 100) (enclosingComponent.cc:164-170)
-    static constexpr bool AUX_MT_SEED = true;
+    // RouteMessage ctor, MersenneRNG(my_id + 100) (enclosingComponent.cc:164-170).  The seed words go to the second
+    // buffer; maintain(MAINT_INIT) builds the first generation from them.
+    static constexpr bool     AUX_MT_SEED     = true;
+    static constexpr uint32_t AUX_SEED_OFFSET = MT_N * 4;
     __device__ static uint32_t auxSeed(const int64_t* p) { return (uint32_t)(p[0] + 100); }
     struct State
     {
         // [0,16) mutable core
         int32_t  message_count;
-        uint32_t mt_idx;
+        uint32_t mt_pos;
         // RouteMessage's "msg_count" statistic only ever sees addData(1) (enclosingComponent.cc:179-186), so its
-        // Accumulator after n calls is (Sum, SumSQ, Count, Min, Max) = (n, n, n, 1, 1): it is kept as n alone, which
-        // makes the component's whole persistent state one 32-byte sector instead of 80 bytes over three or four
+        // Accumulator after n calls is (Sum, SumSQ, Count, Min, Max) = (n, n, n, 1, 1): it is kept as n alone
         uint64_t stat_n;
         // [16,32) construction constants
-        uint32_t ngroups;
+        uint16_t ngroups;
+        uint16_t digest_ok; // the route digest is maintained: one link per port group, 2 or 4 ports
         uint32_t mod;
         uint64_t counts; // links per port group, 8 bits each
-        // register-only scratch, valid inside one window
-        MtPairCache cache; // read-ahead of the MT19937 words the next two pairs need
     };
     static constexpr uint32_t STORE_END = 16, CONST_END = 32, STATS_END = 32, PERSIST_BYTES = 32;
-    // sequential path: issue the read-ahead loads now, they fly while the engine does the rest of its set-up
-    template <class Ctx>
-    __device__ static void beginWindow(Ctx& ctx, State& s, uint32_t n_events)
-    {
-        s.cache.valid = 0;
-        if ( n_events && (s.mt_idx & 1u) == 0 ) mt_cache_fill((const uint32_t*)ctx.aux, s.mt_idx, s.cache);
-    }
-    // ---- event-parallel handler.  RouteMessage::send's effect for the k-th event of a window is a pure function of
-    // the window-start state and k: its pair of draws reads mt[i+2k .. i+2k+2], mt[i+2k+397], mt[i+2k+398] -- words no
-    // earlier pair of the window writes (see MT_STAGE_MAX_PAIRS) -- and the state update (message_count, MT index,
-    // msg_count statistic) is a sum.  So the n events of a component run on n threads.
-    static constexpr bool     PARALLEL_EVENTS          = true;
-    static constexpr uint32_t PARALLEL_SENDS_PER_EVENT = 1;
+    static constexpr uint32_t RECORD_BYTES = 112, DIGEST_OFF = 32; // 28 words: a warp's 16-byte accesses to 32 records are bank-conflict free
+    static constexpr bool     TIES_INTERCHANGEABLE = true;
+    static constexpr bool     STATS_EVERY_EVENT    = false;
     // EnclosingComponent::handleEvent / RouteMessage::send look at neither the port an event came in on nor at its
     // (empty) payload: events that are due at the same time are interchangeable, whatever order they are run in the
     // component ends in the same state and sends the same events (enclosingComponent.cc:92-99,179-186)
-    static constexpr bool TIES_INTERCHANGEABLE = true;
-    static constexpr bool     STATS_EVERY_EVENT = false;
-    // 3a, component thread: asynchronous copies (LDGSTS) of the a-run: chunk j = (mt[i+2j], mt[i+2j+1]) to
-    // staged[j] (delivery position j of this component), and mt[i+2n] (the last pair's third word) to *extra
-    __device__ static void stageParallel(const uint8_t* aux, uint32_t hdr, uint32_t n, uint2* staged, uint32_t* extra)
+
+    // ---- event-parallel form (window_parallel_kernel).  RouteMessage::send's effect for the k-th event of a window
+    // is a pure function of the window-start record and k: its pair of draws starts at word index + 2k, the port is
+    // that pair's digest entry, and the state update (message_count, MT position, msg_count statistic) is a sum.
+    static constexpr bool     PARALLEL_EVENTS     = true;
+    static constexpr uint32_t PARALLEL_MAX_EVENTS = MT_MAX_PAIRS_PER_WINDOW; // 100
+    // component thread, start of the window: may this component's events run in the event-parallel form (even MT19937
+    // index, route digest maintained)?  hdr = the digest entries of the window's first 16 pairs (2 bits each)
+    __device__ static bool parHeader(const uint8_t* rec, uint32_t& hdr)
     {
-        const uint32_t* mt = (const uint32_t*)aux;
-        const uint32_t  i  = hdr & 0xFFFFu;
-        for ( uint32_t j = 0; j < n; ++j )
-            __pipeline_memcpy_async(staged + j, mt + mt_wrap(mt_wrap(i + 2 * j)), 8);
-        __pipeline_memcpy_async(extra, mt + mt_wrap(mt_wrap(i + 2 * n)), 4);
+        const uint32_t* r32 = reinterpret_cast<const uint32_t*>(rec);
+        const uint32_t  idx = r32[1] & ((1u << MT_POS_SHIFT) - 1);
+        hdr                 = 0;
+        if ( (r32[4] >> 16) == 0 || (idx & 1u) != 0 ) return false;
+        hdr = route_digest_window16(r32 + DIGEST_OFF / 4, idx >> 1);
+        return true;
     }
-    __device__ static void finishWindowParallel(State& s, uint32_t n, bool stats_on)
+    // the port the k-th event of the window leaves on
+    __device__ static uint32_t parRoute(uint32_t hdr, const uint8_t* rec, uint32_t k)
     {
-        s.message_count += (int32_t)n;
-        s.mt_idx = mt_wrap(mt_wrap(s.mt_idx + 2 * n));
-        if ( stats_on ) s.stat_n += n; // n x addData(1)
+        if ( k < 16 ) return (hdr >> (2 * k)) & 3u;
+        const uint32_t* r32 = reinterpret_cast<const uint32_t*>(rec);
+        return route_digest_entry(r32 + DIGEST_OFF / 4, ((r32[1] & ((1u << MT_POS_SHIFT) - 1)) >> 1) + k);
     }
-    // 3b.1, event thread k: the b-run words mt[i+2k+397], mt[i+2k+398] straight from memory.  No pair of the window
-    // writes them (pair k' writes mt[i+2k'], mt[i+2k'+1]; 2(k'-k) = 397 is impossible and 2(k'-k)+1 = 397 needs
-    // k'-k = 198 > MT_STAGE_MAX_PAIRS), so reading them while other events write is race-free.
-    __device__ static uint2 parallelLoad(const uint8_t* aux, uint32_t hdr, uint32_t k)
+    // all n events of the window at once on the mutable core; returns the maintenance the component needs afterwards
+    __device__ static uint32_t parFinish(uint4& core, uint32_t n, bool stats_on)
     {
-        const uint32_t* mt = (const uint32_t*)aux;
-        const uint32_t  i  = mt_wrap(mt_wrap((hdr & 0xFFFFu) + 2 * k));
-        return make_uint2(mt[mt_wrap(i + MT_M)], mt[mt_wrap(i + MT_M + 1)]);
+        core.x += n;
+        const uint32_t op = mt_pos_advance_pairs(core.y, n);
+        if ( stats_on ) {
+            const uint64_t sn = (((uint64_t)core.w << 32) | core.z) + n; // n x addData(1)
+            core.z            = (uint32_t)sn;
+            core.w            = (uint32_t)(sn >> 32);
+        }
+        return op;
     }
-    // 3b.2: the pair of draws of RouteMessage::send for the k-th event, new-generation words written back; returns
-    // the port the event leaves on
-    __device__ static uint32_t parallelCompute(uint8_t* aux, const uint4& hdr, const uint2* staged, uint32_t k, uint32_t n,
-        uint2 b)
+    // warp-cooperative maintenance (maintenance_kernel): gen = 624 words of shared memory owned by the warp
+    __device__ static void maintain(uint32_t op, uint8_t* rec, uint8_t* aux, const int64_t* param, uint32_t* gen,
+        uint32_t lane);
+
+    template <class Ctx>
+    __device__ static MtGenDev generator(Ctx& ctx, const State& s)
     {
-        const uint2    a01 = staged[k];
-        const uint32_t a2  = (k + 1 < n) ? staged[k + 1].x : hdr.w;
-        const uint32_t y0  = (a01.x & 0x80000000u) + (a01.y & 0x7fffffffu);
-        uint32_t       v0  = b.x ^ (y0 >> 1);
-        if ( y0 & 1u ) v0 ^= 2567483615u;
-        const uint32_t y1 = (a01.y & 0x80000000u) + (a2 & 0x7fffffffu);
-        uint32_t       v1 = b.y ^ (y1 >> 1);
-        if ( y1 & 1u ) v1 ^= 2567483615u;
-        const uint32_t i = mt_wrap(mt_wrap((hdr.x & 0xFFFFu) + 2 * k)); // even
-        *reinterpret_cast<uint2*>((uint32_t*)aux + i) = make_uint2(v0, v1);
-        const uint32_t r0 = mt_temper(v0);
-        const uint32_t ng = hdr.x >> 16;
-        return (ng & (ng - 1)) == 0 ? (r0 & (ng - 1)) : r0 % ng; // one link per group: port = group
+        return MtGenDev { (uint32_t*)ctx.aux, s.mt_pos,
+            s.digest_ok ? reinterpret_cast<uint32_t*>(ctx.rec + DIGEST_OFF) : nullptr, s.ngroups };
     }
-    // 3b.3: the send
-    template <class PCtx>
-    __device__ static void parallelSend(PCtx& ctx, uint32_t out_port, int /*port*/, uint64_t payload)
+    template <class Ctx>
+    __device__ static void beginWindow(Ctx&, State&, uint32_t)
+    {}
+    __device__ static void prefetch(const uint8_t* state, const uint8_t* aux)
     {
-        ctx.send((int)out_port, 0, payload);
-    }
-    // dispatch prologue hook: pull towards L2 the MT19937 words the next handful of draws will read (words idx.. and
-    // idx+397.. mod 624), and probe whether this component's events of the window may run in the event-parallel form:
-    // MT19937 index even (pairs stay 8-byte aligned), one link per port group (the second draw only advances the
-    // generator).  Returns the header word the event threads get -- index | port groups << 16 -- or 0xFFFFFFFF.
-    __device__ static uint32_t prefetch(const uint8_t* state, const uint8_t* aux)
-    {
-        const uint4     core = __ldg(reinterpret_cast<const uint4*>(state));      // message_count, mt_idx
-        const uint4     cst  = __ldg(reinterpret_cast<const uint4*>(state + 16)); // ngroups, mod, counts
-        const uint32_t  idx  = core.y;
-        const uint32_t  im   = (idx + MT_M >= MT_N) ? idx + MT_M - MT_N : idx + MT_M;
-        const uint32_t* mt   = reinterpret_cast<const uint32_t*>(aux);
-#if SSTB200_MESH_PREFETCH >= 1
-        prefetch_l2(mt + idx);
-        prefetch_l2(mt + im);
-#endif
-#if SSTB200_MESH_PREFETCH >= 2
-        prefetch_l2(mt + (idx + 16 >= MT_N ? idx + 16 - MT_N : idx + 16));
-        prefetch_l2(mt + (im + 16 >= MT_N ? im + 16 - MT_N : im + 16));
-#endif
-        const uint64_t counts = ((uint64_t)cst.w << 32) | cst.z;
-        const bool     ok     = (idx & 1u) == 0 && cst.x >= 1 && cst.x <= 8 &&
-                        counts == (0x0101010101010101ull >> (8 * (8 - cst.x)));
-        return ok ? (idx | (cst.x << 16)) : 0xFFFFFFFFu;
+        const uint32_t pos = __ldg(reinterpret_cast<const uint32_t*>(state) + 1);
+        prefetch_l2(aux + ((pos >> MT_POS_SHIFT) * MT_N + (pos & ((1u << MT_POS_SHIFT) - 1))) * 4);
     }
     template <class Ctx>
     __device__ static void construct(Ctx& ctx, State& s, const int64_t* p)
     {
         s.message_count = 0;
-        s.mt_idx        = 0;
+        s.mt_pos        = 0;
         s.stat_n        = 0;
         s.mod           = (uint32_t)p[1];
-        s.ngroups       = (uint32_t)p[4];
+        s.ngroups       = (uint16_t)p[4];
         s.counts        = (uint64_t)p[5];
+        s.digest_ok     = digestOk(p) ? 1 : 0;
+    }
+    __device__ static bool digestOk(const int64_t* p)
+    {
+        const uint64_t ng = (uint64_t)p[4];
+        return (ng == 2 || ng == 4) && (uint64_t)p[5] == (0x0101010101010101ull >> (8 * (8 - ng)));
     }
     template <class Ctx>
     __device__ static void setup(Ctx& ctx, State& s)
     {
         // RouteMessage::sendInitialEvents :188-199
-        MersenneDev rng { (uint32_t*)ctx.aux, s.mt_idx };
-        uint32_t    flat = 0;
+        MtGenDev rng  = generator(ctx, s);
+        uint32_t flat = 0;
         for ( uint32_t i = 0; i < s.ngroups; i++ ) {
             uint32_t cnt = (uint32_t)((s.counts >> (8 * i)) & 0xFF);
             for ( uint32_t j = 0; j < cnt; j++, flat++ )
                 if ( (rng.u32() % s.mod) == 0 ) ctx.send((int)flat, 0, 0);
         }
-        s.mt_idx = rng.idx;
+        s.mt_pos = rng.pos;
     }
     template <class Ctx>
     __device__ static void handleEvent(Ctx& ctx, State& s, int /*port*/, uint64_t& payload)
     {
         s.message_count++;
-        uint32_t r0, r1; // the two draws of RouteMessage::send
-        mt_u32x2_cached((uint32_t*)ctx.aux, s.mt_idx, s.cache, r0, r1);
+        MtGenDev       rng = generator(ctx, s);
+        const uint32_t r0 = rng.u32(), r1 = rng.u32(); // the two draws of RouteMessage::send
+        s.mt_pos = rng.pos;
         // nextport = r0 % ports.size(); portnum = r1 % counts[nextport] (both draws are always made)
         const uint32_t ng       = s.ngroups;
-        const uint32_t nextport = (ng & (ng - 1)) == 0 ? (r0 & (ng - 1)) : r0 % ng;
+        const uint32_t nextport = r0 % ng;
         uint32_t       portnum = 0, base = nextport;
         if ( s.counts != (0x0101010101010101ull >> (8 * (8 - ng))) ) { // not the one-link-per-port-group case
             const uint32_t cnt = (uint32_t)((s.counts >> (8 * nextport)) & 0xFF);
@@ -303,6 +283,7 @@ struct PholdElement
     static constexpr const char* ELI_NAME    = "pdes.phold";
     static constexpr uint32_t    AUX_BYTES   = 0;
     static constexpr bool        AUX_MT_SEED = false;
+    static constexpr uint32_t    AUX_SEED_OFFSET = 0;
     __device__ static uint32_t auxSeed(const int64_t*) { return 0; }
     static constexpr bool        HAS_PAYLOAD = true;
     struct State
@@ -323,15 +304,11 @@ struct PholdElement
     // with the rest of the state and stores it back, instead of folding a per-window accumulator afterwards
     static constexpr bool     STATS_EVERY_EVENT = true;
     static constexpr bool     PARALLEL_EVENTS = false; // handlers chain through the state (hash, RNG): sequential
-    static constexpr uint32_t PERSIST_BYTES = sizeof(State);
+    static constexpr uint32_t PERSIST_BYTES = sizeof(State), RECORD_BYTES = sizeof(State);
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
     {}
-    __device__ static uint32_t prefetch(const uint8_t* state, const uint8_t*)
-    {
-        prefetch_l2(state);
-        return 0xFFFFFFFFu;
-    }
+    __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
     template <class Ctx>
     __device__ static void construct(Ctx&, State& s, const int64_t* p)
     {
@@ -388,6 +365,7 @@ struct ClockNodeElement
     static constexpr const char* ELI_NAME    = "pdes.clocknode";
     static constexpr uint32_t    AUX_BYTES   = 0;
     static constexpr bool        AUX_MT_SEED = false;
+    static constexpr uint32_t    AUX_SEED_OFFSET = 0;
     __device__ static uint32_t auxSeed(const int64_t*) { return 0; }
     static constexpr bool        HAS_PAYLOAD = false;
     struct State
@@ -408,15 +386,11 @@ struct ClockNodeElement
     static constexpr bool     TIES_INTERCHANGEABLE = false; // the delivery hash / handlers see port and order
     static constexpr bool     STATS_EVERY_EVENT = false;
     static constexpr bool     PARALLEL_EVENTS = false; // handlers chain through the state (hash, RNG): sequential
-    static constexpr uint32_t PERSIST_BYTES = sizeof(State);
+    static constexpr uint32_t PERSIST_BYTES = sizeof(State), RECORD_BYTES = sizeof(State);
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
     {}
-    __device__ static uint32_t prefetch(const uint8_t* state, const uint8_t*)
-    {
-        prefetch_l2(state);
-        return 0xFFFFFFFFu;
-    }
+    __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
     template <class Ctx>
     __device__ static void construct(Ctx&, State& s, const int64_t* p)
     {
@@ -482,6 +456,7 @@ struct CoreTestElement
     static constexpr const char* ELI_NAME    = "coreTestElement.coreTestComponent";
     static constexpr uint32_t    AUX_BYTES   = 0;
     static constexpr bool        AUX_MT_SEED = false;
+    static constexpr uint32_t    AUX_SEED_OFFSET = 0;
     __device__ static uint32_t auxSeed(const int64_t*) { return 0; }
     static constexpr bool        HAS_PAYLOAD = false;
     struct State
@@ -501,15 +476,11 @@ struct CoreTestElement
     static constexpr bool     TIES_INTERCHANGEABLE = true; // handleEvent looks at nothing but the payload it deletes
     static constexpr bool     STATS_EVERY_EVENT = false;
     static constexpr bool     PARALLEL_EVENTS      = false;
-    static constexpr uint32_t PERSIST_BYTES        = sizeof(State);
+    static constexpr uint32_t PERSIST_BYTES        = sizeof(State), RECORD_BYTES = sizeof(State);
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
     {}
-    __device__ static uint32_t prefetch(const uint8_t* state, const uint8_t*)
-    {
-        prefetch_l2(state);
-        return 0xFFFFFFFFu;
-    }
+    __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
     template <class Ctx>
     __device__ static void construct(Ctx&, State& s, const int64_t* p)
     {
@@ -562,6 +533,7 @@ struct RngElement
     static constexpr const char* ELI_NAME    = "coreTestElement.coreTestRNGComponent";
     static constexpr uint32_t    AUX_BYTES   = MT_N * 4;
     static constexpr bool        AUX_MT_SEED = false;
+    static constexpr uint32_t    AUX_SEED_OFFSET = 0;
     __device__ static uint32_t auxSeed(const int64_t*) { return 0; }
     static constexpr bool        HAS_PAYLOAD = false;
     struct State
@@ -577,15 +549,11 @@ struct RngElement
     static constexpr bool     TIES_INTERCHANGEABLE = false; // the delivery hash / handlers see port and order
     static constexpr bool     STATS_EVERY_EVENT = false;
     static constexpr bool     PARALLEL_EVENTS = false; // handlers chain through the state (hash, RNG): sequential
-    static constexpr uint32_t PERSIST_BYTES = sizeof(State);
+    static constexpr uint32_t PERSIST_BYTES = sizeof(State), RECORD_BYTES = sizeof(State);
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
     {}
-    __device__ static uint32_t prefetch(const uint8_t* state, const uint8_t*)
-    {
-        prefetch_l2(state);
-        return 0xFFFFFFFFu;
-    }
+    __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
     template <class Ctx>
     __device__ static void construct(Ctx& ctx, State& s, const int64_t* p)
     {

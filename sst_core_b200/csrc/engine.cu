@@ -60,11 +60,7 @@ set_error(const std::string& s)
 #endif
 constexpr int      BLOCK      = SSTB200_BLOCK; // components per CTA == threads per CTA
 constexpr uint64_t TIME_NEVER = ~0ull;
-#ifndef SSTB200_PARB
-#define SSTB200_PARB 5
-#endif
-constexpr int      PARB       = SSTB200_PARB; // event-parallel phase: positions t, t+256, ... t+4*256 per thread (1280 = the default staging capacity)
-constexpr uint32_t PAR_MAX_EVENTS = 100; // events of one component per window in the event-parallel form (<= MT_STAGE_MAX_PAIRS)
+constexpr uint32_t PAR_MAX_EVENTS = MeshElement::PARALLEL_MAX_EVENTS; // events of one component per window in the event-parallel form
 
 enum : uint32_t { ERR_BIN_OVERFLOW = 1, ERR_SMEM_OVERFLOW = 2, ERR_TIME_FAULT = 3, ERR_OUTBOX_OVERFLOW = 4, ERR_TRACE_OVERFLOW = 5 };
 enum { CW_PENDING = 0, CW_PRIMARY = 1, CW_CLOCKS = 2, CW_ERROR = 3, CW_EXIT_TIME = 4, CW_WORDS = 8 };
@@ -90,6 +86,9 @@ struct Ctrl
     // leaves its result record as of the END of time report_at (StatisticOutput clocks run at priority 85, after the
     // clock handlers and events of their time) in Dev::snapshot; TIME_NEVER otherwise
     uint64_t           report_at;
+    // event-parallel form (parallel_form.cuh): blocks of this window left to the sequential form, components whose
+    // generator needs maintenance after this window; both reset by advance_kernel
+    uint32_t           fb_n, maint_n;
 };
 
 // Per-component engine control block: everything the dispatch kernel needs about a component besides its element
@@ -112,7 +111,6 @@ struct Dev
     uint32_t        lmax, uniform_nports; // link rows staged per block; ports per component when uniform (else 0)
     uint32_t        uniform_shift;        // log2(uniform_nports) when it is a power of two, else 32
     uint32_t        uniform_type;         // the element type when every local component has the same one, else 0
-    uint32_t        any_parallel;         // some local element type has an event-parallel handler
     uint32_t        ties_free;            // every local element type declares events of equal time interchangeable
     uint32_t        par_max;              // most events of one component per window the event-parallel form takes
     // the per-component control blocks are neither read nor written by dispatch_kernel when nothing in them can
@@ -152,6 +150,10 @@ struct Dev
     unsigned long long* prof_recv;  // [nport_local]
     unsigned long long* prof_clock; // [n_local]
     uint8_t*            snapshot;   // copy of `state` holding every component's state as of Ctrl::report_at
+    // event-parallel form: staging capacity for a bin's records, the two lists (see Ctrl)
+    uint32_t            pf_rcap;
+    uint32_t*           fb_list;    // [nbins]
+    uint32_t*           maint_list; // [n_local] component | operation << 30
 };
 
 // ================================================================================================ device side
@@ -240,6 +242,7 @@ struct CtxT
     uint32_t     port0; // global id of this component's first directed port
     uint32_t     nports;
     uint8_t*     aux;
+    uint8_t*     rec;   // the component's record in memory (what of it is not part of State: MessageMesh route digest)
     uint32_t     seq;   // per-component send sequence: the FIFO tie-break the reference gets from queue_order
     uint32_t     sent;
     int          stats_on;
@@ -343,13 +346,14 @@ seed_mt_kernel(Dev d)
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lc   = blockIdx.x * BLOCK + threadIdx.x;
     bool           want = false;
-    uint32_t       prev = 0;
+    uint32_t       prev = 0, seed_off = 0;
     if ( lc < d.n_local )
         with_element(d.comp_type[lc], [&](auto el) {
             using E = decltype(el);
             if constexpr ( E::AUX_MT_SEED ) {
-                want = true;
-                prev = E::auxSeed(d.comp_param + (uint64_t)lc * NPARAM);
+                want     = true;
+                prev     = E::auxSeed(d.comp_param + (uint64_t)lc * NPARAM);
+                seed_off = E::AUX_SEED_OFFSET;
             }
         });
     const uint32_t wantmask = __ballot_sync(0xffffffffu, want);
@@ -366,9 +370,10 @@ seed_mt_kernel(Dev d)
 #pragma unroll
         for ( uint32_t r = 0; r < 4; ++r ) {
             const uint32_t comp = (lane >> 2) + 8 * r, piece = lane & 3;
+            const uint32_t off  = __shfl_sync(0xffffffffu, seed_off, comp);
             if ( wantmask >> comp & 1u ) {
                 const uint32_t* t = &tile[warp][comp][piece * 4];
-                *(uint4*)(warp_aux + (uint64_t)comp * d.aux_stride + chunk * 64 + piece * 16) = make_uint4(t[0], t[1], t[2], t[3]);
+                *(uint4*)(warp_aux + (uint64_t)comp * d.aux_stride + off + chunk * 64 + piece * 16) = make_uint4(t[0], t[1], t[2], t[3]);
             }
         }
         __syncwarp();
@@ -384,7 +389,8 @@ setup_kernel(Dev d)
     const uint32_t type = d.comp_type[lc];
     const uint32_t p0   = d.port_off[lc];
     CtxT<false>    ctx { d, 0, 0, 0, d.c0 + lc, p0, d.port_off[lc + 1] - p0, d.aux + (uint64_t)lc * d.aux_stride,
-                         0, 0, d.stats_on, d.link + (p0 - d.P0), Stage {}, nullptr, 0, 0 };
+                         d.state + (uint64_t)lc * d.state_stride, 0, 0, d.stats_on, d.link + (p0 - d.P0), Stage {},
+                         nullptr, 0, 0 };
     const uint64_t period = d.clock_period[lc];
     with_element(type, [&](auto el) {
         using E = decltype(el);
@@ -477,61 +483,19 @@ sort_segment(uint16_t* seg, uint32_t cnt, const uint32_t* s_time, const uint32_t
     }
 }
 
-// Context of an EVENT-PARALLEL handler (elements with PARALLEL_EVENTS): the handler of the k-th event (in delivery
-// order) of a component runs on its own thread, concurrently with the handlers of the component's other events of the
-// window.  It sees the component's state as it was at the start of the window (read-only), sends exactly
-// PARALLEL_SENDS_PER_EVENT events (staged in its own event's slot), and returns its writes to the aux block as a
-// deferred write that the engine applies after every parallel handler of the block has finished reading.
-struct ParCtx
-{
-    const Dev&   d;
-    uint64_t     now, k, T;
-    uint32_t     comp, port0, nports;
-    uint8_t*     aux;
-    uint32_t     seq; // sequence number of this event's (first) send
-    int          stats_on;
-    const uint4* links;
-    Stage        st;
-    uint32_t     slot; // this event's staging slot
-    bool         used;
-
-    __device__ __forceinline__ void send(int port, uint64_t delay, uint64_t payload)
-    {
-        const uint4 l = links[port];
-        if ( l.x == SSTB200_NO_PEER ) return;
-        const uint64_t when = now + delay + (((uint64_t)l.w << 32) | l.z);
-        const uint32_t sq   = seq++;
-        const uint64_t off  = when - T;
-        if ( !used && (off >> 32) == 0 ) {
-            used       = true;
-            st.t[slot] = (uint32_t)off;
-            st.a[slot] = l.x;
-            st.sc[slot] = make_uint2(sq, l.y);
-            if ( st.pay ) st.pay[slot] = payload;
-            return;
-        }
-        emit(d, k, when, l.x, l.y, sq, payload);
-    }
-};
-
 // ---- one lookahead window for one block of 256 components
-// REPORT: the launch of a window that contains a periodic-statistics report time (Ctrl::report_at); always the
-// sequential form.  A separate instantiation so that the ordinary launches carry none of it.
-template <bool PAYLOAD, bool PARFORM, bool REPORT = false>
-#ifndef SSTB200_MIN_BLOCKS
-#define SSTB200_MIN_BLOCKS 3 // 80 registers, no spills, 3 CTAs/SM: measured 27 % faster than 4 CTAs/SM at 64 registers with spills
-#endif
-__global__ void __launch_bounds__(BLOCK, SSTB200_MIN_BLOCKS)
-dispatch_kernel(Dev d)
+// (the sequential form: one thread per component walks the component's events and clock ticks in delivery order).
+// REPORT: the launch of a window that contains a periodic-statistics report time (Ctrl::report_at).  A separate
+// instantiation so that the ordinary launches carry none of it.
+template <bool PAYLOAD, bool REPORT>
+__device__ __forceinline__ void
+dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
 {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    Ctrl* const    ctrl = d.ctrl;
-    if ( ctrl->done ) return;
+    Ctrl* const    ctrl  = d.ctrl;
     const uint64_t k     = ctrl->k;
     const uint64_t T     = ctrl->T;
     const uint64_t T_end = ctrl->T_end;
     const uint32_t w     = (uint32_t)ctrl->w; // < 2^31 (checked by the host)
-    const uint32_t bin   = blockIdx.x;
     const uint32_t slot  = (uint32_t)(k % d.W);
     const uint32_t slot1 = slot + 1 == d.W ? 0 : slot + 1; // where events due in the next window go
     const uint32_t tid   = threadIdx.x;
@@ -553,11 +517,7 @@ dispatch_kernel(Dev d)
     uint32_t* s_hist     = s_misc + 4;              // [32] components per event-count bucket, then bucket fill
     uint32_t* s_hbase    = s_hist + 32;             // [32]
     uint16_t* s_perm     = reinterpret_cast<uint16_t*>(s_hbase + 32); // [emax] per-component segments
-    uint16_t* s_sorted   = s_perm + d.emax;                           // [emax] segments in delivery order
-    uint16_t* s_order    = s_sorted + d.emax;                         // [BLOCK] thread -> component of the block
-    uint4*    s_hdr      = reinterpret_cast<uint4*>( // [BLOCK] per-component window header of the event-parallel path
-        (reinterpret_cast<uintptr_t>(s_order + BLOCK) + 15) & ~(uintptr_t)15);
-    uint8_t*  s_pcomp    = reinterpret_cast<uint8_t*>(s_hdr + BLOCK); // [emax] component of each segment position
+    uint16_t* s_order    = s_perm + d.emax;                           // [BLOCK] thread -> component of the block
 
     // ---- prologue: everything here is independent global traffic issued back to back.  The first 1024 records of
     // the bin are loaded before its fill count is known (the slots exist; what is past the count is ignored).
@@ -590,30 +550,15 @@ dispatch_kernel(Dev d)
                 const uint64_t rep = ctrl->report_at;
                 s_misc[1]          = (rep >= T && rep < T_end) ? (uint32_t)(rep - T) : 0xFFFFFFFFu;
             }
-            s_misc[2]         = 0xFFFFFFFFu; // min / max time offset of the due events
-            s_misc[3]         = 0;
         }
         s_cnt[tid] = 0;
         if ( tid < 32 ) s_hist[tid] = 0;
-        // per-component window header, filled here from memory so that phase 3 starts without a memory round trip:
-        //   .x  element word for the event-parallel form (MT19937 index ...), 0xFFFFFFFF = cannot run in parallel
-        //   .y  send sequence at the start of the window      .z  deliveries so far (trace index)
-        //   .w  bit 0: a clock tick is due in this window; later: extra staged word of the element
-        uint4 hdr = make_uint4(0xFFFFFFFFu, 0, 0, 0);
-        if ( lc0 < d.n_local ) {
-            uint4 c_lo0 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0); // next_tick, send_seq, deliv_seq
-            if ( !d.ctl_free ) c_lo0 = *reinterpret_cast<const uint4*>(&d.ctl[lc0]);
-            // element hook: probe the state for the event-parallel form and start pulling the aux words the
-            // handlers will touch towards L2
+        // element hook: start pulling what the handlers will touch towards L2
+        if ( lc0 < d.n_local )
             with_element(d.uniform_type ? d.uniform_type : d.comp_type[lc0], [&](auto el) {
                 using E = decltype(el);
-                hdr.x = E::prefetch(d.state + (uint64_t)lc0 * d.state_stride, d.aux + (uint64_t)lc0 * d.aux_stride);
+                E::prefetch(d.state + (uint64_t)lc0 * d.state_stride, d.aux + (uint64_t)lc0 * d.aux_stride);
             });
-            hdr.y = c_lo0.z;
-            hdr.z = c_lo0.w;
-            hdr.w = ((((uint64_t)c_lo0.y << 32) | c_lo0.x) < T_end) ? 1u : 0u;
-        }
-        s_hdr[tid] = hdr;
     }
     __syncthreads();
     PHASE_MARK(1);
@@ -630,7 +575,7 @@ dispatch_kernel(Dev d)
     __pipeline_commit();
 
     // ---- phase 1: load the bin; stage due events in shared memory, re-bin the ones that are not due yet
-    uint32_t       dropped  = 0, t_lo = 0xFFFFFFFFu, t_hi = 0;
+    uint32_t       dropped  = 0;
     const uint64_t bin_base = (uint64_t)(slot * d.nbins + bin) * d.cap;
     auto           classify = [&](uint64_t t, uint64_t ds, uint64_t pl) {
         const uint32_t dst = (uint32_t)(ds >> 32);
@@ -670,8 +615,6 @@ dispatch_kernel(Dev d)
             if ( e < d.emax ) {
                 const uint32_t r = atomicAdd(&s_cnt[lo], 1u);
                 s_time[e]        = (uint32_t)(t - T);
-                t_lo             = min(t_lo, (uint32_t)(t - T));
-                t_hi             = max(t_hi, (uint32_t)(t - T));
                 s_dst[e]         = dst;
                 s_sc[e]          = make_uint2((uint32_t)ds, (lo << 16) | (r & 0xFFFFu));
                 if ( PAYLOAD ) s_pay[e] = pl;
@@ -686,10 +629,6 @@ dispatch_kernel(Dev d)
         uint64_t         pl = 0;
         if ( PAYLOAD ) pl = d.ev_payload[bin_base + i];
         classify(ev.x, ev.y, pl);
-    }
-    if ( t_lo <= t_hi ) {
-        atomicMin(&s_misc[2], t_lo);
-        atomicMax(&s_misc[3], t_hi);
     }
     __pipeline_wait_prior(0);
     __syncthreads();
@@ -715,7 +654,6 @@ dispatch_kernel(Dev d)
         const uint32_t cr  = s_sc[e].y;
         const uint32_t pos = s_off[cr >> 16] + (cr & 0xFFFFu);
         s_perm[pos]        = (uint16_t)e;
-        s_pcomp[pos]       = (uint8_t)(cr >> 16);
     }
     if ( tid < 32 ) { // exclusive scan of the 32 buckets by one warp
         const uint32_t v   = s_hist[tid];
@@ -729,41 +667,10 @@ dispatch_kernel(Dev d)
         s_hist[tid]  = 0; // reused as the bucket fill counter
     }
     __syncthreads();
-    // (b) order inside each component's segment, (time, port, sequence): every EVENT counts the events of its segment
-    //     that precede it -- balanced over the CTA's threads whatever the distribution of events over components
-    //     (a per-component sort would make the block wait for its busiest component)
-    // Elements that declare events of equal delivery time interchangeable (their handler looks at neither the port nor
-    // the payload, e.g. MessageMesh) need the order by time only; when the whole block has a single timestamp (every
-    // fixed-latency model) there is nothing to order at all.  With a delivery trace requested the full order is kept,
-    // so traces stay identical to the reference's.
-    const bool by_time_only = d.ties_free && d.trace_cap == 0;
-    const bool owner_sorts  = !PARFORM; // sequential elements only: each owner thread sorts its own segment
-    const bool skip_order   = owner_sorts || (by_time_only && s_misc[2] == s_misc[3]);
-    if ( !skip_order ) {
-        for ( uint32_t pos = tid; pos < n_due; pos += BLOCK ) {
-            const uint32_t e   = s_perm[pos];
-            const uint32_t cc  = s_pcomp[pos];
-            const uint32_t off = s_off[cc], cnt = s_cnt[cc];
-            uint32_t       rank = 0;
-            if ( by_time_only ) {
-                const uint32_t te = s_time[e];
-                for ( uint32_t j = 0; j < cnt; ++j ) {
-                    const uint32_t o  = s_perm[off + j];
-                    const uint32_t to = s_time[o];
-                    rank += (to < te || (to == te && o < e)) ? 1u : 0u;
-                }
-            }
-            else {
-                const uint32_t te = s_time[e], de = s_dst[e], qe = s_sc[e].x;
-                for ( uint32_t j = 0; j < cnt; ++j ) {
-                    const uint32_t o = s_perm[off + j];
-                    rank += key_less(s_time[o], s_dst[o], s_sc[o].x, te, de, qe) ? 1u : 0u;
-                }
-            }
-            s_sorted[off + rank] = (uint16_t)e;
-        }
-    }
-    const uint16_t* s_ordered = skip_order ? s_perm : s_sorted;
+    // (b) the order inside each component's segment, (time, port, sequence), is made by the owning thread in phase 3
+    // (insertion sort: the lanes of a warp own components with nearly equal event counts, and the sort overlaps the
+    // element's first loads)
+    const uint16_t* s_ordered = s_perm;
     // (c, second half) thread -> component assignment
     {
         const uint32_t cnt_c  = s_cnt[tid];
@@ -793,141 +700,12 @@ dispatch_kernel(Dev d)
     const uint32_t p0        = s_port_off[c];
     const uint4*   my_links  = links_in_smem ? (const uint4*)(s_link + (p0 - blk_port0)) : d.link + (p0 - d.P0);
 
-    // ---- phase 3 (event-parallel form).  When EVERY component of the block that has work can take it -- its element
-    // has an event-parallel handler, no clock tick is due, the element agrees (MT19937: even index, short run) -- the
-    // block runs one thread per EVENT instead of one per component:
-    //   3a  component thread: window header (what the events need of the window-start state), asynchronous staging
-    //       of the aux words the handlers read into the (sequence, comp) array -- free after the sort, indexed by
-    //       delivery position --, the state update for all n events at once, write-back;
-    //   3b  event thread (positions t, t+256, ...): global words first (all loads in flight), then compute + aux
-    //       write-back, block barrier, then the sends into the events' own slots.
-    // Perfectly balanced however the events are spread over components; no sequential chain; a block's registers and
-    // shared memory are no longer held for its busiest component.
-    // The decision uses the headers the prologue read from memory (component tid, natural order).
-    bool par_ok = true;
-    {
-        const uint32_t cn = s_cnt[tid];
-        const uint4    h  = s_hdr[tid];
-        if ( bin * BLOCK + tid < d.n_local && (cn > 0 || (h.w & 1u)) )
-            par_ok = d.any_parallel && cn > 0 && !(h.w & 1u) && h.x != 0xFFFFFFFFu && cn <= d.par_max &&
-                     n_due <= PARB * BLOCK;
-    }
-    bool block_par = false;
-    if constexpr ( PARFORM ) block_par = __syncthreads_and(par_ok ? 1 : 0) != 0;
-    if ( PARFORM && block_par ) {
-        // all three memory round trips of the phase are issued now and overlap:
-        // (1) component thread tid: asynchronous staging of the aux words its events read
-        const uint32_t pc_  = tid; // natural order: the work per component is uniform here
-        const uint32_t plc  = bin * BLOCK + pc_;
-        const uint32_t pcnt = s_cnt[pc_];
-        const uint32_t ptyp = d.uniform_type ? d.uniform_type : (plc < d.n_local ? d.comp_type[plc] : 0);
-        if ( pcnt ) {
-            with_element(ptyp, [&](auto el) {
-                using E = decltype(el);
-                if constexpr ( E::PARALLEL_EVENTS )
-                    E::stageParallel(d.aux + (uint64_t)plc * d.aux_stride, s_hdr[pc_].x, pcnt, s_sc + s_off[pc_],
-                        &s_hdr[pc_].w);
-            });
-        }
-        __pipeline_commit();
-        // (2) event threads: the global words each event needs
-        uint2    gw[PARB];
-        uint32_t tok[PARB];
-#pragma unroll
-        for ( int j = 0; j < PARB; ++j ) {
-            const uint32_t p = tid + j * BLOCK;
-            gw[j]            = make_uint2(0, 0);
-            if ( p >= n_due ) continue;
-            const uint32_t cc = s_pcomp[p];
-            with_element(d.uniform_type ? d.uniform_type : d.comp_type[bin * BLOCK + cc], [&](auto el) {
-                using E = decltype(el);
-                if constexpr ( E::PARALLEL_EVENTS )
-                    gw[j] = E::parallelLoad(d.aux + (uint64_t)(bin * BLOCK + cc) * d.aux_stride, s_hdr[cc].x, p - s_off[cc]);
-            });
-        }
-        // (3) component thread: the state update for all its events at once (nothing in 3b depends on it)
-        if ( pcnt ) {
-            with_element(ptyp, [&](auto el) {
-                using E = decltype(el);
-                if constexpr ( E::PARALLEL_EVENTS ) {
-                    typename E::State st_;
-                    load_state(st_, d.state + (uint64_t)plc * d.state_stride, 0, d.stats_on ? E::STATS_END : E::CONST_END);
-                    E::finishWindowParallel(st_, pcnt, d.stats_on != 0);
-                    store_state(st_, d.state + (uint64_t)plc * d.state_stride, 0, E::STORE_END);
-                    if ( d.stats_on )
-                        store_state(st_, d.state + (uint64_t)plc * d.state_stride, E::CONST_END, E::STATS_END);
-                    const uint32_t nsend = pcnt * E::PARALLEL_SENDS_PER_EVENT;
-                    uint32_t*      ctlw  = reinterpret_cast<uint32_t*>(&d.ctl[plc]);
-                    const uint4    h     = s_hdr[pc_];
-                    if ( !d.ctl_free )
-                        *reinterpret_cast<uint2*>(ctlw + 2) = make_uint2(h.y + nsend, h.z + (d.trace_cap ? pcnt : 0));
-                    delivered = pcnt;
-                    sent      = nsend;
-                }
-            });
-        }
-        __pipeline_wait_prior(0); // this thread's staged copies have landed ...
-        __syncthreads();          // ... and everybody else's
-        PHASE_MARK(6);
-        // 3b.2: compute; the handler writes its new aux words and returns what its send step needs
-#pragma unroll
-        for ( int j = 0; j < PARB; ++j ) {
-            const uint32_t p = tid + j * BLOCK;
-            tok[j]           = 0;
-            if ( p >= n_due ) continue;
-            const uint32_t cc = s_pcomp[p];
-            const uint32_t kk = p - s_off[cc], nn = s_cnt[cc];
-            with_element(d.uniform_type ? d.uniform_type : d.comp_type[bin * BLOCK + cc], [&](auto el) {
-                using E = decltype(el);
-                if constexpr ( E::PARALLEL_EVENTS )
-                    tok[j] = E::parallelCompute(d.aux + (uint64_t)(bin * BLOCK + cc) * d.aux_stride, s_hdr[cc],
-                        s_sc + s_off[cc], kk, nn, gw[j]);
-            });
-        }
-        __syncthreads(); // every staged word has been read: the (sequence, comp) array may be overwritten by sends
-        // 3b.3: the sends, each into its own event's slot
-#pragma unroll
-        for ( int j = 0; j < PARB; ++j ) {
-            const uint32_t p = tid + j * BLOCK;
-            if ( p >= n_due ) continue;
-            const uint32_t e    = s_ordered[p];
-            const uint32_t cc   = s_pcomp[p];
-            const uint32_t kk   = p - s_off[cc];
-            const uint32_t lcc  = bin * BLOCK + cc;
-            const uint32_t pp0  = s_port_off[cc];
-            const uint32_t port = s_dst[e] - pp0;
-            const uint64_t pl   = PAYLOAD ? s_pay[e] : 0;
-            const uint64_t ev_t = T + s_time[e];
-            const uint4    hdr  = s_hdr[cc];
-            s_dst[e]            = SSTB200_NO_PEER; // consumed; a send re-fills the slot
-            if ( d.trace_cap ) {
-                const unsigned long long tp = atomicAdd(&ctrl->trace_n, 1ull);
-                if ( tp < d.trace_cap ) {
-                    d.tr_time[tp]    = ev_t;
-                    d.tr_comp[tp]    = d.c0 + lcc;
-                    d.tr_port[tp]    = port;
-                    d.tr_idx[tp]     = hdr.z + kk;
-                    d.tr_payload[tp] = pl;
-                }
-            }
-            with_element(d.uniform_type ? d.uniform_type : d.comp_type[lcc], [&](auto el) {
-                using E = decltype(el);
-                if constexpr ( E::PARALLEL_EVENTS ) {
-                    ParCtx pc { d, ev_t, k, T, d.c0 + lcc, pp0, s_port_off[cc + 1] - pp0,
-                                d.aux + (uint64_t)lcc * d.aux_stride, hdr.y + kk * E::PARALLEL_SENDS_PER_EVENT,
-                                d.stats_on,
-                                links_in_smem ? (const uint4*)(s_link + (pp0 - blk_port0)) : d.link + (pp0 - d.P0),
-                                Stage { s_time, s_dst, s_sc, PAYLOAD ? s_pay : nullptr }, e, false };
-                    E::parallelSend(pc, tok[j], (int)port, pl);
-                }
-            });
-        }
-    }
-    else if ( has_work ) {
+    if ( has_work ) {
         // ---- phase 3 (sequential form): walks the component's segment in delivery order, merged with its clock
         // ticks; sends are staged in the slots the component has already consumed
         CtxT<true> ctx { d, T, k, T, d.c0 + lc, p0, s_port_off[c + 1] - p0,
-                         d.aux + (uint64_t)lc * d.aux_stride, c_lo.z, 0, d.stats_on, my_links,
+                         d.aux + (uint64_t)lc * d.aux_stride, d.state + (uint64_t)lc * d.state_stride, c_lo.z, 0,
+                         d.stats_on, my_links,
                          Stage { s_time, s_dst, s_sc, PAYLOAD ? s_pay : nullptr }, seg, 0, 0 };
         uint32_t   dseq = c_lo.w;
         with_element(my_type, [&](auto el) {
@@ -940,7 +718,7 @@ dispatch_kernel(Dev d)
             load_state(s, d.state + (uint64_t)lc * d.state_stride, 0, stats_direct ? E::STATS_END : E::CONST_END);
             if ( !stats_direct ) E::initStats(s);
             E::beginWindow(ctx, s, my_cnt); // issues the element's first loads (MT19937 read-ahead)
-            if ( owner_sorts ) sort_segment(s_perm + s_off[c], my_cnt, s_time, s_dst, s_sc);
+            sort_segment(s_perm + s_off[c], my_cnt, s_time, s_dst, s_sc);
             uint64_t cycle = (next_tick != TIME_NEVER && period) ? next_tick / period : 0;
             uint32_t i     = 0;
             const uint32_t r_off   = REPORT ? s_misc[1] : 0xFFFFFFFFu;
@@ -1179,6 +957,32 @@ dispatch_kernel(Dev d)
     }
 }
 
+#ifndef SSTB200_MIN_BLOCKS
+#define SSTB200_MIN_BLOCKS 3 // 80 registers, no spills, 3 CTAs/SM: measured 27 % faster than 4 CTAs/SM at 64 registers with spills
+#endif
+// list_mode 0: one CTA per block of the rank.  list_mode 1: the blocks the event-parallel kernel left to this form
+// (Dev::fb_list), walked by a small grid.
+template <bool PAYLOAD, bool REPORT = false>
+__global__ void __launch_bounds__(BLOCK, SSTB200_MIN_BLOCKS)
+dispatch_kernel(Dev d, int list_mode)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    if ( d.ctrl->done ) return;
+    if ( !list_mode ) {
+        dispatch_block<PAYLOAD, REPORT>(d, blockIdx.x, smem_raw);
+        return;
+    }
+    const uint32_t n = min(d.ctrl->fb_n, d.nbins);
+    for ( uint32_t i = blockIdx.x; i < n; i += gridDim.x ) {
+        dispatch_block<PAYLOAD, REPORT>(d, d.fb_list[i], smem_raw);
+        __syncthreads();
+    }
+}
+
+} // namespace sstb200
+#include "parallel_form.cuh"
+namespace sstb200 {
+
 // ---- wire-up on the device: link row of every local directed port = {peer port, component owning the peer (binary
 // search in the GLOBAL port CSR), send latency}.  Replaces the per-Link object setup of Simulation::prepareLinks
 // (simulation.cc:668-820) for 67 M ports without a host loop.
@@ -1249,6 +1053,8 @@ advance_kernel(Dev d)
         exit_time = (uint64_t)c->local[CW_EXIT_TIME];
     }
     c->windows++;
+    c->fb_n    = 0;
+    c->maint_n = 0;
     if ( c->error || err ) {
         if ( !c->error ) c->error = (uint32_t)0x80000000u; // another rank failed
         c->done = 1;
@@ -1454,15 +1260,15 @@ rng_dist_kernel(int dist, const double* params, int np, int kind, uint64_t s1, u
 
 // ================================================================================================ host side
 static const ElementInfo kElements[] = {
-    { TYPE_MESH, MeshElement::ELI_NAME, MeshElement::PERSIST_BYTES, MeshElement::AUX_BYTES,
+    { TYPE_MESH, MeshElement::ELI_NAME, MeshElement::RECORD_BYTES, MeshElement::AUX_BYTES,
         MeshElement::HAS_PAYLOAD, MeshElement::PARALLEL_EVENTS, MeshElement::TIES_INTERCHANGEABLE, "message_mesh enclosing component with message_port/port_slot/route_message" },
-    { TYPE_PHOLD, PholdElement::ELI_NAME, PholdElement::PERSIST_BYTES, PholdElement::AUX_BYTES,
+    { TYPE_PHOLD, PholdElement::ELI_NAME, PholdElement::RECORD_BYTES, PholdElement::AUX_BYTES,
         PholdElement::HAS_PAYLOAD, PholdElement::PARALLEL_EVENTS, PholdElement::TIES_INTERCHANGEABLE, "PHOLD-style node, integer delays, 8-byte payload" },
-    { TYPE_CLOCKNODE, ClockNodeElement::ELI_NAME, ClockNodeElement::PERSIST_BYTES,
+    { TYPE_CLOCKNODE, ClockNodeElement::ELI_NAME, ClockNodeElement::RECORD_BYTES,
         ClockNodeElement::AUX_BYTES, ClockNodeElement::HAS_PAYLOAD, ClockNodeElement::PARALLEL_EVENTS, ClockNodeElement::TIES_INTERCHANGEABLE, "clock-driven node (coreTestComponent style)" },
-    { TYPE_RNGCOMP, RngElement::ELI_NAME, RngElement::PERSIST_BYTES, RngElement::AUX_BYTES,
+    { TYPE_RNGCOMP, RngElement::ELI_NAME, RngElement::RECORD_BYTES, RngElement::AUX_BYTES,
         RngElement::HAS_PAYLOAD, RngElement::PARALLEL_EVENTS, RngElement::TIES_INTERCHANGEABLE, "coreTestRNGComponent: 1 GHz clock drawing from an SST::RNG generator" },
-    { TYPE_CORETEST, CoreTestElement::ELI_NAME, CoreTestElement::PERSIST_BYTES, CoreTestElement::AUX_BYTES,
+    { TYPE_CORETEST, CoreTestElement::ELI_NAME, CoreTestElement::RECORD_BYTES, CoreTestElement::AUX_BYTES,
         CoreTestElement::HAS_PAYLOAD, CoreTestElement::PARALLEL_EVENTS, CoreTestElement::TIES_INTERCHANGEABLE, "coreTestComponent: clock handler sending to its N/S/E/W neighbours in turn" },
 };
 constexpr int kNumElements = (int)(sizeof(kElements) / sizeof(kElements[0]));
@@ -1524,22 +1330,42 @@ struct sstb200_engine
         CUDA_OK(cudaStreamSynchronize(stream));
         return 0;
     }
+    // event-parallel form (parallel_form.cuh): on when every local component is of one element type with
+    // PARALLEL_EVENTS and nothing of the model needs what the form leaves out (see engine_create)
+    bool     pf_on = false;
+    size_t   pf_smem = 0;
+    uint32_t pf_grid = 0, fb_grid = 0, maint_grid = 0;
+    // one lookahead window: the event-parallel kernel, the sequential kernel over the blocks it left (or over all
+    // blocks when the form is off, or for a window with a statistics report), generator maintenance
     int launch_dispatch(bool report = false)
     {
         if ( report ) {
             if ( d.has_payload )
-                dispatch_kernel<true, false, true><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
+                dispatch_kernel<true, true><<<d.nbins, BLOCK, smem_bytes, stream>>>(d, 0);
             else
-                dispatch_kernel<false, false, true><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
+                dispatch_kernel<false, true><<<d.nbins, BLOCK, smem_bytes, stream>>>(d, 0);
+            launches++;
         }
-        else if ( d.has_payload )
-            (d.any_parallel ? dispatch_kernel<true, true> : dispatch_kernel<true, false>)<<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
-        else
-            (d.any_parallel ? dispatch_kernel<false, true> : dispatch_kernel<false, false>)<<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
-        launches++;
+        else if ( pf_on ) {
+            window_parallel_kernel<MeshElement><<<pf_grid, PF_THREADS, pf_smem, stream>>>(d);
+            dispatch_kernel<false><<<fb_grid, BLOCK, smem_bytes, stream>>>(d, 1);
+            launches += 2;
+        }
+        else {
+            if ( d.has_payload )
+                dispatch_kernel<true><<<d.nbins, BLOCK, smem_bytes, stream>>>(d, 0);
+            else
+                dispatch_kernel<false><<<d.nbins, BLOCK, smem_bytes, stream>>>(d, 0);
+            launches++;
+        }
+        if ( pf_on ) {
+            maintenance_kernel<<<maint_grid, 256, 0, stream>>>(d, 0);
+            launches++;
+        }
         CUDA_OK(cudaGetLastError());
         return 0;
     }
+    uint32_t launches_per_window() const { return pf_on ? 4u : 2u; }
     // `n` windows (dispatch + advance each).  The kernels take the same arguments every window -- the window state
     // lives in device memory -- so a chunk is captured once into a CUDA graph and replayed: small models are bound by
     // launch overhead, not by the kernels.
@@ -1572,7 +1398,7 @@ struct sstb200_engine
             }
             if ( graph_exec && graph_chunk == n ) {
                 CUDA_OK(cudaGraphLaunch(graph_exec, stream));
-                launches += 2ull * n;
+                launches += (uint64_t)launches_per_window() * n;
                 return 0;
             }
         }
@@ -1728,16 +1554,23 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     // lookahead window = minimum latency over every connected link (cut or not: a window is processed as one batch
     // per component, so nothing sent inside it may be due inside it)
     const uint32_t nport = m->port_off[m->ncomp];
-    uint64_t       mn_lat[16];
+    uint64_t       mn_lat[16], mx_lat[16];
     for ( auto& v : mn_lat )
         v = TIME_NEVER;
+    for ( auto& v : mx_lat )
+        v = 0;
     scan(nport, [&](size_t lo, size_t hi, unsigned t) {
-        uint64_t mn = TIME_NEVER;
+        uint64_t mn = TIME_NEVER, mx = 0;
         for ( size_t p = lo; p < hi; ++p )
-            if ( m->peer_port[p] != SSTB200_NO_PEER && m->latency[p] < mn ) mn = m->latency[p];
+            if ( m->peer_port[p] != SSTB200_NO_PEER ) {
+                if ( m->latency[p] < mn ) mn = m->latency[p];
+                if ( m->latency[p] > mx ) mx = m->latency[p];
+            }
         mn_lat[t] = mn;
+        mx_lat[t] = mx;
     });
-    const uint64_t mn = *std::min_element(mn_lat, mn_lat + 16);
+    const uint64_t mn     = *std::min_element(mn_lat, mn_lat + 16);
+    const uint64_t mx_lat_all = *std::max_element(mx_lat, mx_lat + 16);
     uint64_t       w  = o->window ? o->window : (mn == TIME_NEVER ? 1000000ull : mn);
     if ( w == 0 || w > 0x7fffffffull ) {
         set_error("engine_create: lookahead window must be in [1, 2^31) cycles (zero-latency links are not allowed)");
@@ -1810,7 +1643,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     }
     uint32_t state_stride = 8, aux_stride = 0;
     int      has_payload  = 0;
-    d.any_parallel        = 0;
+    bool any_parallel     = false;
     d.ties_free           = 1;
     d.uniform_type        = 0;
     for ( uint32_t ty = 0; ty < TYPE_MAX; ++ty ) {
@@ -1820,7 +1653,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         if ( !(seen_local >> ty & 1u) ) continue;
         state_stride = std::max(state_stride, ei->state_bytes);
         aux_stride   = std::max(aux_stride, ei->aux_bytes);
-        if ( ei->parallel_events ) d.any_parallel = 1;
+        if ( ei->parallel_events ) any_parallel = true;
         if ( !ei->ties_interchangeable ) d.ties_free = 0;
         if ( (seen_local & (seen_local - 1)) == 0 ) d.uniform_type = ty; // the only type on this rank
     }
@@ -1829,6 +1662,17 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         if ( (seen_all >> ty & 1u) && by_type[ty] && !by_type[ty]->ties_interchangeable ) ties_free_model = false;
     d.ctl_free = (!any_clock && d.uniform_type && ties_free_model && o->trace_capacity == 0) ? 1u : 0u;
     d.par_max = (o->parallel_max_events && o->parallel_max_events < PAR_MAX_EVENTS) ? o->parallel_max_events : PAR_MAX_EVENTS;
+    // The event-parallel form runs the windows of this rank when: one local element type, and it has the form; nobody
+    // in the model looks at send sequence numbers, clocks or traces (ctl_free); a power-of-two port count per
+    // component whose link rows fit the staging buffer; no payloads; no handler counting; link latencies below 2^31.
+    // Blocks it cannot take in some window (see parallel_form.cuh) are run by the sequential form in that window.
+    e->pf_on = any_parallel && d.uniform_type == TYPE_MESH && d.ctl_free && uni_ok && uni0 && (uni0 & (uni0 - 1)) == 0 &&
+               (size_t)uni0 * BLOCK <= 2048 && !has_payload && !o->handler_counts && mx_lat_all < 0x7fffffffull &&
+               getenv("SSTB200_NO_PARALLEL_FORM") == nullptr;
+    d.pf_rcap = 1152;
+    if ( const char* rc_env = getenv("SSTB200_PF_RCAP") ) d.pf_rcap = (uint32_t)atoi(rc_env);
+    if ( d.pf_rcap > (uint32_t)PF_ROUNDS * PF_THREADS ) d.pf_rcap = PF_ROUNDS * PF_THREADS;
+    if ( d.pf_rcap < 16 ) d.pf_rcap = 16;
     {
         const uint32_t uni = uni_ok ? uni0 : 0;
         d.lmax             = max_blk <= 2048 ? max_blk : 0;
@@ -1896,6 +1740,10 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         rc |= e->alloc(&d.prof_recv, d.nport_local);
         rc |= e->alloc(&d.prof_clock, d.n_local);
     }
+    if ( e->pf_on ) {
+        rc |= e->alloc(&d.fb_list, d.nbins);
+        rc |= e->alloc(&d.maint_list, d.n_local);
+    }
     rc |= e->alloc(&e->d_results, (size_t)d.n_local * NRESULT);
     lap("allocations + clears", e->stream);
     if ( rc ) {
@@ -1930,8 +1778,8 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     CUDA_OK(cudaMemcpyAsync(d.ctrl, e->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, e->stream));
 
     e->smem_bytes = (size_t)d.lmax * 16 + (size_t)d.emax * (has_payload ? 8 : 0) + (size_t)d.emax * 16 +
-                    (size_t)(BLOCK + 1 + BLOCK + BLOCK + BLOCK / 32 + 1 + 4 + 32 + 32) * 4 + (size_t)d.emax * 4 +
-                    (size_t)BLOCK * 2 + 16 + (size_t)BLOCK * 16 + (size_t)d.emax + 16;
+                    (size_t)(BLOCK + 1 + BLOCK + BLOCK + BLOCK / 32 + 1 + 4 + 32 + 32) * 4 + (size_t)d.emax * 2 +
+                    (size_t)BLOCK * 2 + 16;
     if ( e->smem_bytes > 227 * 1024 ) {
         set_error("engine_create: smem_events too large for 227 KB of shared memory");
         sstb200_engine_destroy(e);
@@ -1941,8 +1789,23 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    int n_sm = 148;
+    CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, o->device));
+    e->maint_grid = (uint32_t)n_sm * 8;
+    if ( e->pf_on ) {
+        // persistent grid: as many CTAs as fit, each walks blocks b, b + grid, ...
+        e->pf_smem = (size_t)BLOCK * MeshElement::RECORD_BYTES + ((size_t)BLOCK * uni0) * 16 + (size_t)d.pf_rcap * 16 +
+                     (size_t)(2 * BLOCK + 3 * PF_HT + 2) * 4 + 3 * 8 + 16;
+        CUDA_OK(cudaFuncSetAttribute(window_parallel_kernel<MeshElement>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            (int)e->pf_smem));
+        int per_sm = 0;
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, window_parallel_kernel<MeshElement>, PF_THREADS,
+            e->pf_smem));
+        if ( per_sm < 1 ) per_sm = 1;
+        if ( const char* g = getenv("SSTB200_PF_CTAS") ) per_sm = std::max(1, atoi(g));
+        e->pf_grid = std::min<uint32_t>(d.nbins, (uint32_t)(per_sm * n_sm));
+        e->fb_grid = std::min<uint32_t>(d.nbins, (uint32_t)(2 * n_sm));
+    }
     CUDA_OK(cudaStreamSynchronize(e->stream));
     *out = e;
     return 0;
@@ -1973,6 +1836,9 @@ sstb200_engine_setup(sstb200_engine* e)
     }
     if ( e->d.aux_stride ) {
         seed_mt_kernel<<<e->d.nbins, BLOCK, 0, e->stream>>>(e->d);
+        e->launches++;
+        // first MT19937 generation (and route digest) of every generator seeded above
+        maintenance_kernel<<<e->maint_grid, 256, 0, e->stream>>>(e->d, 1);
         e->launches++;
     }
     setup_kernel<<<e->d.nbins, BLOCK, 0, e->stream>>>(e->d);

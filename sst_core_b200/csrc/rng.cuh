@@ -38,9 +38,6 @@ namespace sstb200 {
 
 constexpr int MT_N = 624;
 constexpr int MT_M = 397;
-// a window's draws may be staged ahead of time only while no pair reads a word an earlier pair of the same window
-// wrote: pair k reads mt[i+2k+398] = the second word pair k-114 wrote.  Stay well below 114.
-constexpr uint32_t MT_STAGE_MAX_PAIRS = 100;
 
 SSTB_HD uint32_t
 mt_temper(uint32_t t)
@@ -117,98 +114,144 @@ struct MersenneDev
     }
 };
 
-// Register-resident read-ahead for a run of paired draws at EVEN index (624 is even, so parity never changes while a
-// component only draws in pairs).  The words a pair needs are mt[i], mt[i+1], mt[i+2] and mt[i+397], mt[i+398]; with
-// 8-byte-aligned chunks C_j = (mt[2j], mt[2j+1]) that is C_j + first word of C_j+1, and second word of the chunk
-// holding mt[i+397] + first word of E_j = (mt[i+398], mt[i+399]).  The cache holds C_j, C_j+1, that second word and
-// E_j, all loaded during EARLIER pairs: a pair is computed from registers only, then the two 8-byte loads for the
-// pair after next are issued and are not waited for until they are needed -- one iteration of the handler loop later.
-// Per pair: two 8-byte loads + one 8-byte store (instead of five 4-byte loads + two 4-byte stores), off the
-// critical path.  Reading up to two pairs early is safe: pairs j and j+1 write only mt[i..i+3], and the words read
-// early (mt[i+4], mt[i+5], mt[i+400], mt[i+401]) are never congruent to those mod 624.
-struct MtPairCache
-{
-    uint32_t a0, a1, a2, a3; // C_j, C_j+1
-    uint32_t b0, b1, b2;     // mt[i+397]; E_j = (mt[i+398], mt[i+399])
-    uint32_t valid;
-};
+// ---- MT19937 kept as WHOLE generations: the reference's own representation (mersenne.cc:56-68 generateNextBatch
+// rebuilds all 624 words when the index wraps; a draw is temper(numbers[index++])).  A generator owns two 624-word
+// buffers: buf[par] is the current generation, the other one receives the NEXT generation ahead of time -- as soon as
+// the index passes MT_REGEN_AT -- so that a lookahead window whose draws run over the end of the current generation
+// finds the following one in place, and so that a draw is ONE read and no write.  What element code keeps in its POD
+// state is `pos` = index | par << 12.
+constexpr uint32_t MT_REGEN_AT  = 424;  // 624 - 2 * (most pairs one window may draw in the event-parallel form)
+constexpr uint32_t MT_POS_SHIFT = 12;
 
 SSTB_HD uint32_t
-mt_wrap(uint32_t i)
+mt_twist(uint32_t a, uint32_t b, uint32_t m)
 {
-    return i >= MT_N ? i - MT_N : i;
+    const uint32_t y = (a & 0x80000000u) + (b & 0x7fffffffu);
+    uint32_t       v = m ^ (y >> 1);
+    if ( y & 1u ) v ^= 2567483615u;
+    return v;
 }
 
-// One pair at even index i from words already read: a0,a1,a2 = mt[i], mt[i+1], mt[i+2]; b0,b1 = mt[i+397], mt[i+398]
-// (all mod 624).  Writes the two new-generation words back (one 8-byte store) and advances the index.
+// next[] = the generation after cur[], exactly as the reference's in-place loop produces it (word i reads the NEW
+// word i-227 for i >= 227, and the last word reads the NEW word 0).  One thread; the warp-cooperative form is
+// mt_warp_regen in parallel_form.cuh.
 SSTB_HD void
-mt_pair_from_words(uint32_t* mt, uint32_t& idx, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b0, uint32_t b1,
-    uint32_t& r0, uint32_t& r1)
+mt_regen_serial(const uint32_t* cur, uint32_t* next)
 {
-    const uint32_t i  = idx;
-    const uint32_t y0 = (a0 & 0x80000000u) + (a1 & 0x7fffffffu);
-    uint32_t       v0 = b0 ^ (y0 >> 1);
-    if ( y0 & 1u ) v0 ^= 2567483615u;
-    const uint32_t y1 = (a1 & 0x80000000u) + (a2 & 0x7fffffffu);
-    uint32_t       v1 = b1 ^ (y1 >> 1);
-    if ( y1 & 1u ) v1 ^= 2567483615u;
-    *reinterpret_cast<uint2*>(mt + i) = uint2 { v0, v1 };
-    idx = mt_wrap(i + 2);
-    r0  = mt_temper(v0);
-    r1  = mt_temper(v1);
-}
-
-// loads the cache for a pair at even index i (C_j, C_j+1, mt[i+397], E_j)
-SSTB_HD void
-mt_cache_fill(const uint32_t* mt, uint32_t i, MtPairCache& c)
-{
-    const uint2 ca = *reinterpret_cast<const uint2*>(mt + i);
-    const uint2 cb = *reinterpret_cast<const uint2*>(mt + mt_wrap(i + 2));
-    const uint2 ce = *reinterpret_cast<const uint2*>(mt + mt_wrap(i + MT_M + 1));
-    c.b0           = mt[mt_wrap(i + MT_M)];
-    c.a0           = ca.x;
-    c.a1           = ca.y;
-    c.a2           = cb.x;
-    c.a3           = cb.y;
-    c.b1           = ce.x;
-    c.b2           = ce.y;
-    c.valid        = 1;
-}
-
-SSTB_HD void
-mt_u32x2_cached(uint32_t* mt, uint32_t& idx, MtPairCache& c, uint32_t& r0, uint32_t& r1)
-{
-    const uint32_t i = idx;
-    if ( (i & 1u) != 0 ) { // odd position: plain path
-        c.valid = 0;
-        MersenneDev g { mt, i };
-        g.u32x2(r0, r1);
-        idx = g.idx;
-        return;
+    for ( int i = 0; i < MT_N; ++i ) {
+        const uint32_t b = (i + 1 == MT_N) ? next[0] : cur[i + 1];
+        const uint32_t m = (i < MT_N - MT_M) ? cur[i + MT_M] : next[i - (MT_N - MT_M)];
+        next[i]          = mt_twist(cur[i], b, m);
     }
-    if ( !c.valid ) mt_cache_fill(mt, i, c);
-    const uint32_t y0 = (c.a0 & 0x80000000u) + (c.a1 & 0x7fffffffu);
-    uint32_t       v0 = c.b0 ^ (y0 >> 1);
-    if ( y0 & 1u ) v0 ^= 2567483615u;
-    const uint32_t y1 = (c.a1 & 0x80000000u) + (c.a2 & 0x7fffffffu);
-    uint32_t       v1 = c.b1 ^ (y1 >> 1);
-    if ( y1 & 1u ) v1 ^= 2567483615u;
-    *reinterpret_cast<uint2*>(mt + i) = uint2 { v0, v1 };
-    // read-ahead for the pair after next
-    const uint2 na = *reinterpret_cast<const uint2*>(mt + mt_wrap(i + 4));        // C_j+2
-    const uint2 ne = *reinterpret_cast<const uint2*>(mt + mt_wrap(i + MT_M + 3)); // E_j+1
-    c.a0    = c.a2;
-    c.a1    = c.a3;
-    c.b0    = c.b2;
-    c.a2    = na.x;
-    c.a3    = na.y;
-    c.b1    = ne.x;
-    c.b2    = ne.y;
-    c.valid = 1;
-    idx     = mt_wrap(i + 2);
-    r0      = mt_temper(v0);
-    r1      = mt_temper(v1);
 }
+
+// ---- route digest (MessageMesh RouteMessage): the port choice of the pair of draws that starts at word 2j of a
+// generation, temper(gen[2j]) % ng, 2 bits per pair, 16 pairs per word, 312 pairs = 20 words (the last half empty)
+constexpr uint32_t MT_PAIRS             = MT_N / 2;
+constexpr uint32_t ROUTE_DIGEST_WORDS   = 20;
+constexpr uint32_t ROUTE_DIGEST_SPLIT   = 13; // words [0,13) = pairs [0,208) are refreshed when the next generation is
+                                              // built, words [13,20) = pairs [208,312) when it becomes the current one
+SSTB_HD uint32_t
+route_digest_word(const uint32_t* gen, uint32_t wd, uint32_t ng)
+{
+    uint32_t out = 0;
+    for ( uint32_t e = 0; e < 16; ++e ) {
+        const uint32_t j = 16 * wd + e;
+        if ( j < MT_PAIRS ) out |= (mt_temper(gen[2 * j]) % ng) << (2 * e);
+    }
+    return out;
+}
+
+// the digest entries of 16 consecutive pairs starting at pair h.  The entries form a bit stream: words 0..18, the low
+// half of word 19, then the NEXT generation from word 0 on (in place once the index has passed MT_REGEN_AT).
+SSTB_HD uint32_t
+route_digest_window16(const uint32_t* dig, uint32_t h)
+{
+    const uint32_t wi = h >> 4;
+    uint64_t       v;
+    if ( wi == ROUTE_DIGEST_WORDS - 1 )
+        v = (uint64_t)(dig[wi] & 0xFFFFu) | ((uint64_t)dig[0] << 16) | ((uint64_t)dig[1] << 48);
+    else if ( wi == ROUTE_DIGEST_WORDS - 2 )
+        v = (uint64_t)dig[wi] | ((uint64_t)(dig[wi + 1] & 0xFFFFu) << 32) | ((uint64_t)dig[0] << 48);
+    else
+        v = (uint64_t)dig[wi] | ((uint64_t)dig[wi + 1] << 32);
+    return (uint32_t)(v >> ((h & 15u) * 2));
+}
+// entry of pair p, p in [0, 2 * 312): pairs past the end of the current generation belong to the next one
+SSTB_HD uint32_t
+route_digest_entry(const uint32_t* dig, uint32_t p)
+{
+    if ( p >= MT_PAIRS ) p -= MT_PAIRS;
+    return (dig[p >> 4] >> ((p & 15u) * 2)) & 3u;
+}
+// n pairs drawn at once (n <= (624 - MT_REGEN_AT) / 2, even index): new position, and what has to be done before the
+// next window: MT_OP_REGEN (the index passed MT_REGEN_AT: build the next generation and digest entries [0,208) of it)
+// or MT_OP_TAIL (the next generation became the current one: digest entries [208,312) of it)
+enum : uint32_t { MT_OP_NONE = 0, MT_OP_INIT = 1, MT_OP_REGEN = 2, MT_OP_TAIL = 3 };
+constexpr uint32_t MT_MAX_PAIRS_PER_WINDOW = (MT_N - MT_REGEN_AT) / 2;
+static_assert(MT_PAIRS + MT_MAX_PAIRS_PER_WINDOW - MT_PAIRS <= ROUTE_DIGEST_SPLIT * 16,
+    "pairs read from the next generation in one window must lie in the digest words refreshed with it");
+static_assert(MT_REGEN_AT / 2 >= ROUTE_DIGEST_SPLIT * 16, "digest entries refreshed at MT_REGEN_AT must be consumed");
+SSTB_HD uint32_t
+mt_pos_advance_pairs(uint32_t& pos, uint32_t n)
+{
+    uint32_t       idx = pos & ((1u << MT_POS_SHIFT) - 1), par = pos >> MT_POS_SHIFT, op = MT_OP_NONE;
+    const uint32_t ni  = idx + 2 * n;
+    if ( idx < MT_REGEN_AT && ni >= MT_REGEN_AT ) op = MT_OP_REGEN;
+    idx = ni;
+    if ( ni >= (uint32_t)MT_N ) { // cannot also have passed MT_REGEN_AT in this window: 2n <= 624 - MT_REGEN_AT
+        idx = ni - MT_N;
+        par ^= 1u;
+        op = MT_OP_TAIL;
+    }
+    pos = idx | (par << MT_POS_SHIFT);
+    return op;
+}
+
+// Sequential draws from the two-generation storage (the element's slow path; the event-parallel form reads the
+// digest).  `digest` (may be null) is kept in step: it is what later windows in the event-parallel form will read.
+// The two rare steps are kept out of line so that the handler code around a draw stays small.
+#if defined(__CUDACC__)
+#define SSTB_RARE __host__ __device__ __noinline__
+#else
+#define SSTB_RARE inline
+#endif
+SSTB_RARE void
+mt_gen_build_next(uint32_t* buf, uint32_t par, uint32_t* digest, uint32_t ng)
+{
+    mt_regen_serial(buf + par * MT_N, buf + (par ^ 1u) * MT_N);
+    if ( digest )
+        for ( uint32_t wd = 0; wd < ROUTE_DIGEST_SPLIT; ++wd )
+            digest[wd] = route_digest_word(buf + (par ^ 1u) * MT_N, wd, ng);
+}
+SSTB_RARE void
+mt_gen_digest_tail(const uint32_t* gen, uint32_t* digest, uint32_t ng)
+{
+    for ( uint32_t wd = ROUTE_DIGEST_SPLIT; wd < ROUTE_DIGEST_WORDS; ++wd )
+        digest[wd] = route_digest_word(gen, wd, ng);
+}
+
+struct MtGenDev
+{
+    uint32_t* buf;    // [2][624]
+    uint32_t  pos;    // index | par << 12
+    uint32_t* digest; // [ROUTE_DIGEST_WORDS] or null
+    uint32_t  ng;
+    SSTB_HD uint32_t u32()
+    {
+        uint32_t       idx = pos & ((1u << MT_POS_SHIFT) - 1), par = pos >> MT_POS_SHIFT;
+        const uint32_t v   = buf[par * MT_N + idx];
+        ++idx;
+        if ( idx == MT_REGEN_AT ) mt_gen_build_next(buf, par, digest, ng);
+        if ( idx == (uint32_t)MT_N ) {
+            idx = 0;
+            par ^= 1u;
+            if ( digest ) mt_gen_digest_tail(buf + par * MT_N, digest, ng);
+        }
+        pos = idx | (par << MT_POS_SHIFT);
+        return mt_temper(v);
+    }
+};
 
 struct MarsagliaDev
 {

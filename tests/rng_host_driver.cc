@@ -18,43 +18,6 @@ dev_mt_stream(uint32_t seed, int mode, uint32_t lead, uint64_t n, uint32_t* out)
     if ( mode == 2 )
         for ( ; i < lead && i < n; ++i )
             out[i] = g.u32();
-    if ( mode == 3 ) { // `lead` single draws, then cached pairs; the cache is dropped every `lead+3` pairs (window end)
-        for ( ; i < lead && i < n; ++i )
-            out[i] = g.u32();
-        MtPairCache c {};
-        uint32_t    idx = g.idx, pairs = 0;
-        for ( ; i + 1 < n; i += 2 ) {
-            mt_u32x2_cached(mt, idx, c, out[i], out[i + 1]);
-            if ( ++pairs % (lead + 3) == 0 ) c.valid = 0;
-        }
-        g.idx = idx;
-        for ( ; i < n; ++i )
-            out[i] = g.u32();
-        return;
-    }
-    if ( mode == 4 ) { // windows of `lead`+1, 1, 7, 100 ... pairs, every window staged ahead like MeshElement::beginWindow
-        uint32_t       idx     = 0, wsel = 0;
-        const uint32_t sizes[] = { lead + 1, 1, 7, MT_STAGE_MAX_PAIRS, 3, 113 };
-        static uint32_t scr[4 * 128 + 8];
-        while ( i + 1 < n ) {
-            uint32_t np = sizes[wsel++ % 6];
-            if ( np > MT_STAGE_MAX_PAIRS ) np = MT_STAGE_MAX_PAIRS;
-            for ( uint32_t c = 0; c <= np; ++c ) {
-                scr[2 * c]     = mt[mt_wrap(mt_wrap(idx + 2 * c))];
-                scr[2 * c + 1] = mt[mt_wrap(mt_wrap(idx + 2 * c)) + 1];
-            }
-            uint32_t* scb = scr + 2 * np + 2;
-            for ( uint32_t j = 0; j <= 2 * np; ++j )
-                scb[j] = mt[mt_wrap(mt_wrap(idx + MT_M + j))];
-            for ( uint32_t kq = 0; kq < np && i + 1 < n; ++kq, i += 2 )
-                mt_pair_from_words(mt, idx, scr[2 * kq], scr[2 * kq + 1], scr[2 * kq + 2], scb[2 * kq], scb[2 * kq + 1],
-                    out[i], out[i + 1]);
-        }
-        g.idx = idx;
-        for ( ; i < n; ++i )
-            out[i] = g.u32();
-        return;
-    }
     if ( mode == 0 ) {
         for ( ; i < n; ++i )
             out[i] = g.u32();
@@ -65,6 +28,59 @@ dev_mt_stream(uint32_t seed, int mode, uint32_t lead, uint64_t n, uint32_t* out)
         for ( ; i < n; ++i )
             out[i] = g.u32();
     }
+}
+// MT19937 kept as whole generations (rng.cuh MtGenDev, what MeshElement uses): seed words in the second buffer, first
+// generation built from them, then n sequential draws with the route digest maintained on the way
+void
+dev_mtgen_stream(uint32_t seed, uint64_t n, uint32_t* out)
+{
+    static uint32_t buf[2 * MT_N], dig[ROUTE_DIGEST_WORDS];
+    mt_seed(buf + MT_N, seed);
+    mt_regen_serial(buf + MT_N, buf);
+    MtGenDev g { buf, 0, dig, 4 };
+    for ( uint64_t i = 0; i < n; ++i )
+        out[i] = g.u32();
+}
+// The event-parallel form of MessageMesh on the host: `lead` single draws (setup), then windows of n pairs whose
+// ports are read from the route digest (first 16 from the window word, the rest entry by entry), the position
+// advanced for all n at once and the maintenance operation it asks for applied after the window -- exactly what
+// window_parallel_kernel + maintenance_kernel do.  Every 5th window is run by the sequential form instead (a block
+// that fell back).  out[j] = port of the j-th pair; returns the number of pairs.
+uint64_t
+dev_mesh_routes(uint32_t seed, uint32_t lead, uint32_t ng, uint64_t max_pairs, const uint32_t* sizes, uint32_t n_sizes,
+    uint32_t* out)
+{
+    static uint32_t buf[2 * MT_N], dig[ROUTE_DIGEST_WORDS];
+    mt_seed(buf + MT_N, seed);
+    mt_regen_serial(buf + MT_N, buf);
+    for ( uint32_t wd = 0; wd < ROUTE_DIGEST_WORDS; ++wd )
+        dig[wd] = route_digest_word(buf, wd, ng);
+    MtGenDev g { buf, 0, dig, ng };
+    for ( uint32_t i = 0; i < lead; ++i )
+        g.u32();
+    uint32_t pos = g.pos;
+    uint64_t j   = 0;
+    for ( uint32_t wsel = 0; j < max_pairs; ++wsel ) {
+        uint32_t n = sizes[wsel % n_sizes];
+        if ( j + n > max_pairs ) n = (uint32_t)(max_pairs - j);
+        if ( wsel % 5 == 4 ) { // sequential form
+            MtGenDev q { buf, pos, dig, ng };
+            for ( uint32_t kq = 0; kq < n; ++kq ) {
+                out[j++] = q.u32() % ng;
+                q.u32();
+            }
+            pos = q.pos;
+            continue;
+        }
+        const uint32_t h   = (pos & ((1u << MT_POS_SHIFT) - 1)) >> 1;
+        const uint32_t hdr = route_digest_window16(dig, h);
+        for ( uint32_t kq = 0; kq < n; ++kq )
+            out[j++] = kq < 16 ? (hdr >> (2 * kq)) & 3u : route_digest_entry(dig, h + kq);
+        const uint32_t op = mt_pos_advance_pairs(pos, n);
+        if ( op == MT_OP_REGEN ) mt_gen_build_next(buf, pos >> MT_POS_SHIFT, dig, ng);
+        if ( op == MT_OP_TAIL ) mt_gen_digest_tail(buf + (pos >> MT_POS_SHIFT) * MT_N, dig, ng);
+    }
+    return j;
 }
 void
 dev_marsaglia_stream(uint32_t z, uint32_t w, uint64_t n, uint32_t* out, double* uni)

@@ -70,3 +70,39 @@ def test_phold_512x512_vs_oracle():
     ref = O.run_model(m)
     assert st.events_delivered == ref.events
     assert np.array_equal(res[:, :7], ref.results[:, :7])
+
+
+# ---- the benchmarked configurations against the oracle, record for record (256^2 / 512^2 /
+# 1024^2 meshes vs the oracle; bench.py's own engine options)
+BENCH_MESH = dict(calendar_slots=2, bin_capacity=2048, smem_events=1280, outbox_capacity=16384)
+BENCH_PHOLD = dict(calendar_slots=16, bin_capacity=2560, smem_events=1280, outbox_capacity=16384)
+
+
+@pytest.mark.parametrize("size,ns", [(256, 40), (512, 16), (1024, 13)])
+def test_mesh_at_bench_options_vs_oracle(size, ns):
+    import oracle_lib as O
+    m = models.mesh_model(size, size, stop_at=f"{ns}ns", verbose=0, stats_enabled=True)
+    res, st = _run(m, 0, **BENCH_MESH)
+    ref = O.run_model(m)
+    assert st.events_delivered == ref.events == (ns - 1) * 4 * size * size and st.end_time == ref.end_time
+    assert np.array_equal(res[:, :8], ref.results[:, :8])
+
+
+def test_mesh_1024_long_run_crosses_mt19937_generations_vs_oracle():
+    # 180 windows = ~1440 draws per component: every generator is rebuilt at least twice (624 words per generation), so
+    # the generation maintenance of the event-parallel form (next generation, digest tail) is covered at scale
+    import oracle_lib as O
+    m = models.mesh_model(256, 512, stop_at="181ns", verbose=0, stats_enabled=True)
+    res, st = _run(m, 0, **BENCH_MESH)
+    ref = O.run_model(m)
+    assert st.events_delivered == ref.events
+    assert np.array_equal(res[:, :8], ref.results[:, :8])
+
+
+def test_phold_1024x1024_at_bench_options_vs_oracle():
+    import oracle_lib as O
+    m = models.phold_model(1024, 1024, stop_at="12ns", verbose=0, stats_enabled=True)
+    res, st = _run(m, 0, **BENCH_PHOLD)
+    ref = O.run_model(m)
+    assert st.events_delivered == ref.events
+    assert np.array_equal(res[:, :7], ref.results[:, :7])

@@ -19,6 +19,9 @@ def drv(tmp_path_factory):
                            str(HERE / "rng_host_driver.cc")])
     L = C.CDLL(str(so))
     L.dev_mt_stream.argtypes = [C.c_uint32, C.c_int, C.c_uint32, C.c_uint64, C.c_void_p]
+    L.dev_mtgen_stream.argtypes = [C.c_uint32, C.c_uint64, C.c_void_p]
+    L.dev_mesh_routes.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.dev_mesh_routes.restype = C.c_uint64
     L.dev_marsaglia_stream.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]
     L.dev_xorshift_stream.argtypes = [C.c_uint32, C.c_uint64, C.c_void_p]
     return L
@@ -41,23 +44,28 @@ def test_paired_draw_equals_two_single_draws(drv, lead):
     assert np.array_equal(out, ref)
 
 
-@pytest.mark.parametrize("lead", [0, 1, 2, 4, 226, 227, 620, 622, 623, 624])
-def test_cached_paired_draw_equals_reference_stream(drv, lead):
-    n = 624 * 6 + 11
-    ref, _ = O.rng_u32_stream(0, 7000 + lead, 0, n)
+def test_whole_generation_storage_equals_reference_stream(drv):
+    # rng.cuh MtGenDev: the reference's own representation (mersenne.cc:56-68), next generation built ahead of time
+    n = 624 * 7 + 13
+    ref, _ = O.rng_u32_stream(0, 4242, 0, n)
     out = np.zeros(n, dtype=np.uint32)
-    drv.dev_mt_stream(7000 + lead, 3, lead, n, out.ctypes.data_as(C.c_void_p))
+    drv.dev_mtgen_stream(4242, n, out.ctypes.data_as(C.c_void_p))
     assert np.array_equal(out, ref)
 
 
-@pytest.mark.parametrize("lead", [0, 3, 50, 99])
-def test_window_staged_pairs_equal_reference_stream(drv, lead):
-    # MeshElement::beginWindow copies the words a whole window of pairs will read BEFORE any of them is drawn
-    n = 624 * 9 + 2
-    ref, _ = O.rng_u32_stream(0, 31337 + lead, 0, n)
-    out = np.zeros(n, dtype=np.uint32)
-    drv.dev_mt_stream(31337 + lead, 4, lead, n, out.ctypes.data_as(C.c_void_p))
-    assert np.array_equal(out, ref)
+@pytest.mark.parametrize("ng,lead", [(4, 4), (2, 2), (4, 0), (4, 422), (4, 424), (4, 622)])
+def test_route_digest_windows_equal_sequential_draws(drv, ng, lead):
+    # the event-parallel form of MessageMesh (window_parallel_kernel + maintenance_kernel) restated on the host: the
+    # port of the j-th pair of draws must be (first draw of the pair) % ng whatever the window sizes are, across
+    # generation boundaries, with windows run by the sequential form in between
+    pairs = 312 * 9 + 5
+    sizes = np.array([1, 7, 100, 3, 16, 17, 0, 99, 100, 100, 2, 15, 33, 64, 5, 100, 31], dtype=np.uint32)
+    ref, _ = O.rng_u32_stream(0, 100 + lead + ng, 0, lead + 2 * pairs)
+    out = np.zeros(pairs, dtype=np.uint32)
+    got = drv.dev_mesh_routes(100 + lead + ng, lead, ng, pairs, sizes.ctypes.data_as(C.c_void_p), len(sizes),
+                              out.ctypes.data_as(C.c_void_p))
+    assert got == pairs
+    assert np.array_equal(out, ref[lead:lead + 2 * pairs:2] % ng)
 
 
 def test_marsaglia_and_xorshift(drv):
