@@ -98,6 +98,22 @@ mixDelivery(uint64_t h, uint64_t time, uint64_t port, uint64_t payload)
     return h;
 }
 
+// addData(1) on one of four accumulators chosen at run time, written as a static selection so that the accumulators
+// (and with them the element's whole State) stay in registers instead of a dynamically indexed local-memory array
+template <typename T>
+SSTB_HD void
+add_one_of4(Accumulator<T>* a, uint32_t which)
+{
+    if ( which == 0 )
+        a[0].add(1);
+    else if ( which == 1 )
+        a[1].add(1);
+    else if ( which == 2 )
+        a[2].add(1);
+    else
+        a[3].add(1);
+}
+
 #if defined(__CUDACC__)
 
 __device__ __forceinline__ void
@@ -196,7 +212,7 @@ struct MeshElement
     __device__ static MtGenDev generator(Ctx& ctx, const State& s)
     {
         return MtGenDev { (uint32_t*)ctx.aux, s.mt_pos,
-            s.digest_ok ? reinterpret_cast<uint32_t*>(ctx.rec + DIGEST_OFF) : nullptr, s.ngroups };
+            s.digest_ok ? reinterpret_cast<uint32_t*>(ctx.record() + DIGEST_OFF) : nullptr, s.ngroups };
     }
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
@@ -420,7 +436,7 @@ struct ClockNodeElement
             s.neighbor = (s.neighbor + 1) % 4;
             if ( s.neighbor < ctx.nports && ctx.connected((int)s.neighbor) ) {
                 ctx.send((int)s.neighbor, 0, 0);
-                if ( ctx.stats_on ) s.count[s.neighbor].add(1);
+                if ( ctx.stats_on ) add_one_of4(s.count, s.neighbor);
             }
         }
         return false;
@@ -507,7 +523,7 @@ struct CoreTestElement
             s.neighbor = (s.neighbor + 1) % 4; // C++ remainder: stays negative until it reaches 0
             if ( s.neighbor >= 0 ) {
                 ctx.send(s.neighbor, 0, 0);
-                if ( ctx.stats_on ) s.count[s.neighbor].add(1);
+                if ( ctx.stats_on ) add_one_of4(s.count, (uint32_t)s.neighbor);
             }
             else
                 s.bad++;

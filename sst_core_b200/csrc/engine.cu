@@ -27,6 +27,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <type_traits>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -242,7 +243,6 @@ struct CtxT
     uint32_t     port0; // global id of this component's first directed port
     uint32_t     nports;
     uint8_t*     aux;
-    uint8_t*     rec;   // the component's record in memory (what of it is not part of State: MessageMesh route digest)
     uint32_t     seq;   // per-component send sequence: the FIFO tie-break the reference gets from queue_order
     uint32_t     sent;
     int          stats_on;
@@ -253,6 +253,8 @@ struct CtxT
     uint32_t        free_head, free_tail;
 
     __device__ __forceinline__ bool connected(int port) const { return links[port].x != SSTB200_NO_PEER; }
+    // the component's record in memory (what of it is not part of State: MessageMesh route digest)
+    __device__ __forceinline__ uint8_t* record() const { return d.state + (uint64_t)(comp - d.c0) * d.state_stride; }
     // Link::send(delay, ev): delivery time = now + delay + latency of the sending end (link.cc:636)
     __device__ __forceinline__ void send(int port, uint64_t delay, uint64_t payload)
     {
@@ -305,6 +307,18 @@ with_element(uint32_t type, F&& f)
     default:
         break;
     }
+}
+
+// EU = the rank's only element type when it has just one (the kernel is then compiled for that element alone: no
+// type switch, registers allocated for one handler), void otherwise
+template <class EU, class F>
+__device__ __forceinline__ void
+with_element_of(uint32_t type, F&& f)
+{
+    if constexpr ( std::is_void<EU>::value )
+        with_element(type, static_cast<F&&>(f));
+    else
+        f(EU {});
 }
 
 // Element state moves between HBM and registers in 16-byte pieces (state_stride is a multiple of 16).  `bytes` may be
@@ -389,8 +403,7 @@ setup_kernel(Dev d)
     const uint32_t type = d.comp_type[lc];
     const uint32_t p0   = d.port_off[lc];
     CtxT<false>    ctx { d, 0, 0, 0, d.c0 + lc, p0, d.port_off[lc + 1] - p0, d.aux + (uint64_t)lc * d.aux_stride,
-                         d.state + (uint64_t)lc * d.state_stride, 0, 0, d.stats_on, d.link + (p0 - d.P0), Stage {},
-                         nullptr, 0, 0 };
+                         0, 0, d.stats_on, d.link + (p0 - d.P0), Stage {}, nullptr, 0, 0 };
     const uint64_t period = d.clock_period[lc];
     with_element(type, [&](auto el) {
         using E = decltype(el);
@@ -487,7 +500,7 @@ sort_segment(uint16_t* seg, uint32_t cnt, const uint32_t* s_time, const uint32_t
 // (the sequential form: one thread per component walks the component's events and clock ticks in delivery order).
 // REPORT: the launch of a window that contains a periodic-statistics report time (Ctrl::report_at).  A separate
 // instantiation so that the ordinary launches carry none of it.
-template <bool PAYLOAD, bool REPORT>
+template <bool PAYLOAD, bool REPORT, class EU>
 __device__ __forceinline__ void
 dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
 {
@@ -555,7 +568,7 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
         if ( tid < 32 ) s_hist[tid] = 0;
         // element hook: start pulling what the handlers will touch towards L2
         if ( lc0 < d.n_local )
-            with_element(d.uniform_type ? d.uniform_type : d.comp_type[lc0], [&](auto el) {
+            with_element_of<EU>(d.uniform_type ? d.uniform_type : d.comp_type[lc0], [&](auto el) {
                 using E = decltype(el);
                 E::prefetch(d.state + (uint64_t)lc0 * d.state_stride, d.aux + (uint64_t)lc0 * d.aux_stride);
             });
@@ -704,11 +717,10 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
         // ---- phase 3 (sequential form): walks the component's segment in delivery order, merged with its clock
         // ticks; sends are staged in the slots the component has already consumed
         CtxT<true> ctx { d, T, k, T, d.c0 + lc, p0, s_port_off[c + 1] - p0,
-                         d.aux + (uint64_t)lc * d.aux_stride, d.state + (uint64_t)lc * d.state_stride, c_lo.z, 0,
-                         d.stats_on, my_links,
+                         d.aux + (uint64_t)lc * d.aux_stride, c_lo.z, 0, d.stats_on, my_links,
                          Stage { s_time, s_dst, s_sc, PAYLOAD ? s_pay : nullptr }, seg, 0, 0 };
         uint32_t   dseq = c_lo.w;
-        with_element(my_type, [&](auto el) {
+        with_element_of<EU>(my_type, [&](auto el) {
             using E = decltype(el);
             typename E::State s;
             // statistics: elements that add data with every delivery get their statistics region in the same round
@@ -960,22 +972,23 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
 #ifndef SSTB200_MIN_BLOCKS
 #define SSTB200_MIN_BLOCKS 3 // 80 registers, no spills, 3 CTAs/SM: measured 27 % faster than 4 CTAs/SM at 64 registers with spills
 #endif
-// list_mode 0: one CTA per block of the rank.  list_mode 1: the blocks the event-parallel kernel left to this form
+// LIST false: one CTA per block of the rank.  LIST true: the blocks the event-parallel kernel left to this form
 // (Dev::fb_list), walked by a small grid.
-template <bool PAYLOAD, bool REPORT = false>
+template <bool PAYLOAD, bool REPORT = false, class EU = void, bool LIST = false>
 __global__ void __launch_bounds__(BLOCK, SSTB200_MIN_BLOCKS)
-dispatch_kernel(Dev d, int list_mode)
+dispatch_kernel(Dev d)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     if ( d.ctrl->done ) return;
-    if ( !list_mode ) {
-        dispatch_block<PAYLOAD, REPORT>(d, blockIdx.x, smem_raw);
-        return;
+    if constexpr ( !LIST ) {
+        dispatch_block<PAYLOAD, REPORT, EU>(d, blockIdx.x, smem_raw);
     }
-    const uint32_t n = min(d.ctrl->fb_n, d.nbins);
-    for ( uint32_t i = blockIdx.x; i < n; i += gridDim.x ) {
-        dispatch_block<PAYLOAD, REPORT>(d, d.fb_list[i], smem_raw);
-        __syncthreads();
+    else {
+        const uint32_t n = min(d.ctrl->fb_n, d.nbins);
+        for ( uint32_t i = blockIdx.x; i < n; i += gridDim.x ) {
+            dispatch_block<PAYLOAD, REPORT, EU>(d, d.fb_list[i], smem_raw);
+            __syncthreads();
+        }
     }
 }
 
@@ -988,12 +1001,15 @@ namespace sstb200 {
 // (simulation.cc:668-820) for 67 M ports without a host loop.
 __global__ void __launch_bounds__(BLOCK)
 build_links_kernel(uint4* link, const uint32_t* peer, const uint64_t* latency, const uint32_t* port_off_global,
-    uint32_t ncomp_global, uint32_t nport_local)
+    uint32_t ncomp_global, uint32_t nport_local, uint32_t global_shift)
 {
     for ( uint32_t p = blockIdx.x * BLOCK + threadIdx.x; p < nport_local; p += gridDim.x * BLOCK ) {
         const uint32_t pr = peer[p];
         uint32_t       lo = 0;
-        if ( pr != SSTB200_NO_PEER ) {
+        if ( pr != SSTB200_NO_PEER && global_shift < 32 ) {
+            lo = pr >> global_shift; // every component of the model has 2^shift ports: no table needed
+        }
+        else if ( pr != SSTB200_NO_PEER ) {
             uint32_t hi = ncomp_global; // largest c with port_off[c] <= pr
             while ( hi - lo > 1 ) {
                 const uint32_t mid = lo + ((hi - lo) >> 1);
@@ -1282,6 +1298,7 @@ struct sstb200_engine
     Dev                d {};
     int                device      = 0;
     cudaStream_t       stream      = nullptr;
+    cudaStream_t       up_stream   = nullptr; // engine_create's second upload stream
     bool               own_stream  = false;
     std::vector<void*> allocs;
     Ctrl*              h_ctrl      = nullptr; // pinned mirror
@@ -1341,21 +1358,32 @@ struct sstb200_engine
     {
         if ( report ) {
             if ( d.has_payload )
-                dispatch_kernel<true, true><<<d.nbins, BLOCK, smem_bytes, stream>>>(d, 0);
+                dispatch_kernel<true, true><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
             else
-                dispatch_kernel<false, true><<<d.nbins, BLOCK, smem_bytes, stream>>>(d, 0);
+                dispatch_kernel<false, true><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
             launches++;
         }
         else if ( pf_on ) {
             window_parallel_kernel<MeshElement><<<pf_grid, PF_THREADS, pf_smem, stream>>>(d);
-            dispatch_kernel<false><<<fb_grid, BLOCK, smem_bytes, stream>>>(d, 1);
+            dispatch_kernel<false, false, MeshElement, true><<<fb_grid, BLOCK, smem_bytes, stream>>>(d);
             launches += 2;
         }
         else {
-            if ( d.has_payload )
-                dispatch_kernel<true><<<d.nbins, BLOCK, smem_bytes, stream>>>(d, 0);
+            // one element type on the rank and the model's payload setting is that element's own: the kernel compiled
+            // for that element alone; else the kernel that switches on the type of every component
+            const uint32_t ut = d.uniform_type;
+            if ( ut == TYPE_PHOLD && d.has_payload == (int)PholdElement::HAS_PAYLOAD )
+                dispatch_kernel<PholdElement::HAS_PAYLOAD, false, PholdElement><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
+            else if ( ut == TYPE_CLOCKNODE && d.has_payload == (int)ClockNodeElement::HAS_PAYLOAD )
+                dispatch_kernel<ClockNodeElement::HAS_PAYLOAD, false, ClockNodeElement><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
+            else if ( ut == TYPE_MESH && d.has_payload == (int)MeshElement::HAS_PAYLOAD )
+                dispatch_kernel<MeshElement::HAS_PAYLOAD, false, MeshElement><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
+            else if ( ut == TYPE_CORETEST && d.has_payload == (int)CoreTestElement::HAS_PAYLOAD )
+                dispatch_kernel<CoreTestElement::HAS_PAYLOAD, false, CoreTestElement><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
+            else if ( d.has_payload )
+                dispatch_kernel<true><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
             else
-                dispatch_kernel<false><<<d.nbins, BLOCK, smem_bytes, stream>>>(d, 0);
+                dispatch_kernel<false><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
             launches++;
         }
         if ( pf_on ) {
@@ -1535,8 +1563,12 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     d.emax = (d.emax + 3u) & ~3u;
     d.stats_on = m->stats_enabled;
 
-    // The model scans below touch every port (67 M for a 4096x4096 torus) and every component once; they run on a few
-    // host threads so that engine_create is bound by the uploads, not by this.
+    // Host scans run on a few threads.  Order of engine_create: (1) the component scan (element types, strides);
+    // (2) the uploads start: component types and parameters on the engine's stream, followed there by the MT19937
+    // seeding and first-generation kernels (they need nothing else), the port arrays and the link-row kernel on a second
+    // stream; (3) WHILE those run, the port scan for the lookahead window on the host; (4) the remaining allocations.
+    // engine_create returns when the caller's arrays have been consumed; the seeding kernels may still be running
+    // (engine_setup and everything else is ordered behind them on the engine's stream).
     auto scan = [](size_t n, auto&& body) { // body(lo, hi, slot) on up to 16 threads
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
         const unsigned T  = n < (1u << 20) ? 1u : std::min(16u, hw);
@@ -1551,39 +1583,6 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
             x.join();
         return T;
     };
-    // lookahead window = minimum latency over every connected link (cut or not: a window is processed as one batch
-    // per component, so nothing sent inside it may be due inside it)
-    const uint32_t nport = m->port_off[m->ncomp];
-    uint64_t       mn_lat[16], mx_lat[16];
-    for ( auto& v : mn_lat )
-        v = TIME_NEVER;
-    for ( auto& v : mx_lat )
-        v = 0;
-    scan(nport, [&](size_t lo, size_t hi, unsigned t) {
-        uint64_t mn = TIME_NEVER, mx = 0;
-        for ( size_t p = lo; p < hi; ++p )
-            if ( m->peer_port[p] != SSTB200_NO_PEER ) {
-                if ( m->latency[p] < mn ) mn = m->latency[p];
-                if ( m->latency[p] > mx ) mx = m->latency[p];
-            }
-        mn_lat[t] = mn;
-        mx_lat[t] = mx;
-    });
-    const uint64_t mn     = *std::min_element(mn_lat, mn_lat + 16);
-    const uint64_t mx_lat_all = *std::max_element(mx_lat, mx_lat + 16);
-    uint64_t       w  = o->window ? o->window : (mn == TIME_NEVER ? 1000000ull : mn);
-    if ( w == 0 || w > 0x7fffffffull ) {
-        set_error("engine_create: lookahead window must be in [1, 2^31) cycles (zero-latency links are not allowed)");
-        delete e;
-        return -1;
-    }
-    if ( mn < w ) {
-        set_error("engine_create: window larger than a link latency");
-        delete e;
-        return -1;
-    }
-    lap("window scan", nullptr);
-
     // per-rank slices
     d.P0          = m->port_off[c0];
     d.nport_local = m->port_off[c1] - d.P0;
@@ -1597,13 +1596,14 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     struct Part
     {
         uint32_t seen_all = 0, seen_local = 0, bad = 0xFFFFFFFFu, max_blk = 0;
-        bool     uni_ok = true, clocks = false;
+        bool     uni_ok = true, uni_all = true, clocks = false;
     } part[16];
     const uint32_t uni0 = d.n_local ? m->port_off[c0 + 1] - m->port_off[c0] : 0;
     scan(m->ncomp, [&](size_t lo, size_t hi, unsigned t) {
         Part q;
         for ( size_t c = lo; c < hi; ++c ) {
             const uint32_t ty = m->comp_type[c];
+            if ( m->port_off[c + 1] - m->port_off[c] != uni0 ) q.uni_all = false;
             if ( ty >= TYPE_MAX || !by_type[ty] ) {
                 if ( c >= c0 && c < c1 && q.bad == 0xFFFFFFFFu ) q.bad = (uint32_t)c;
                 continue;
@@ -1626,7 +1626,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         part[t].max_blk = std::max(part[t].max_blk, mx);
     });
     uint32_t seen_all = 0, seen_local = 0, bad = 0xFFFFFFFFu, max_blk = 0;
-    bool     uni_ok = true, any_clock = false;
+    bool     uni_ok = true, uni_all = true, any_clock = false;
     for ( const Part& q : part ) {
         any_clock = any_clock || q.clocks;
         seen_all |= q.seen_all;
@@ -1634,6 +1634,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         bad     = std::min(bad, q.bad);
         max_blk = std::max(max_blk, q.max_blk);
         uni_ok  = uni_ok && q.uni_ok;
+        uni_all = uni_all && q.uni_all;
     }
     if ( bad != 0xFFFFFFFFu ) {
         set_error("engine_create: component " + std::to_string(bad) + " has unknown type code " +
@@ -1662,17 +1663,11 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         if ( (seen_all >> ty & 1u) && by_type[ty] && !by_type[ty]->ties_interchangeable ) ties_free_model = false;
     d.ctl_free = (!any_clock && d.uniform_type && ties_free_model && o->trace_capacity == 0) ? 1u : 0u;
     d.par_max = (o->parallel_max_events && o->parallel_max_events < PAR_MAX_EVENTS) ? o->parallel_max_events : PAR_MAX_EVENTS;
-    // The event-parallel form runs the windows of this rank when: one local element type, and it has the form; nobody
-    // in the model looks at send sequence numbers, clocks or traces (ctl_free); a power-of-two port count per
-    // component whose link rows fit the staging buffer; no payloads; no handler counting; link latencies below 2^31.
-    // Blocks it cannot take in some window (see parallel_form.cuh) are run by the sequential form in that window.
-    e->pf_on = any_parallel && d.uniform_type == TYPE_MESH && d.ctl_free && uni_ok && uni0 && (uni0 & (uni0 - 1)) == 0 &&
-               (size_t)uni0 * BLOCK <= 2048 && !has_payload && !o->handler_counts && mx_lat_all < 0x7fffffffull &&
-               getenv("SSTB200_NO_PARALLEL_FORM") == nullptr;
-    d.pf_rcap = 1152;
+    d.pf_rcap = PF_ROUNDS * PF_THREADS; // 1280 records: a 4096^2 mesh bin holds 1024 +- 32
     if ( const char* rc_env = getenv("SSTB200_PF_RCAP") ) d.pf_rcap = (uint32_t)atoi(rc_env);
     if ( d.pf_rcap > (uint32_t)PF_ROUNDS * PF_THREADS ) d.pf_rcap = PF_ROUNDS * PF_THREADS;
     if ( d.pf_rcap < 16 ) d.pf_rcap = 16;
+    uint32_t global_shift = 32; // log2(ports per component) when EVERY component of the model has that many
     {
         const uint32_t uni = uni_ok ? uni0 : 0;
         d.lmax             = max_blk <= 2048 ? max_blk : 0;
@@ -1682,19 +1677,40 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
             d.uniform_shift = 0;
             while ( (1u << d.uniform_shift) < uni )
                 ++d.uniform_shift;
+            if ( uni_all ) global_shift = d.uniform_shift;
         }
     }
     d.state_stride = (state_stride + 15u) & ~15u;
     d.aux_stride   = (aux_stride + 31u) & ~31u;
     d.has_payload  = has_payload;
-
     lap("element scans", nullptr);
+
     int rc = 0;
+    CUDA_OK(cudaStreamCreateWithFlags(&e->up_stream, cudaStreamNonBlocking));
+    cudaEvent_t ev_params = nullptr, ev_up = nullptr;
+    CUDA_OK(cudaEventCreateWithFlags(&ev_params, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming));
+    // (2a) engine stream: component types + parameters, element state, then the generators
     rc |= e->upload(&d.comp_type, m->comp_type + c0, d.n_local);
     rc |= e->upload(&d.comp_param, m->comp_param + (size_t)c0 * NPARAM, (size_t)d.n_local * NPARAM);
-    rc |= e->upload(&d.port_off, m->port_off + c0, (size_t)d.n_local + 1);
+    CUDA_OK(cudaEventRecord(ev_params, e->stream));
+    rc |= e->alloc(&d.state, (size_t)d.n_local * d.state_stride);
+    rc |= e->alloc(&d.aux, (size_t)d.n_local * d.aux_stride, false);
+    if ( !rc && d.aux_stride && d.n_local ) {
+        seed_mt_kernel<<<d.nbins, BLOCK, 0, e->stream>>>(d);
+        e->launches++;
+        // first MT19937 generation (and route digest) of every generator seeded above
+        int n_sm0 = 148;
+        cudaDeviceGetAttribute(&n_sm0, cudaDevAttrMultiProcessorCount, o->device);
+        maintenance_kernel<<<(uint32_t)n_sm0 * 8, 256, 0, e->stream>>>(d, 1);
+        e->launches++;
+    }
+    // (2b) second stream: the port arrays; link rows are built on the device from the rank's slice of peer_port /
+    // latency (and the global port CSR when port counts differ between components)
     {
-        // link rows are built on the device from the rank's slice of peer_port / latency and the global port CSR
+        cudaStream_t main_stream = e->stream;
+        e->stream                = e->up_stream; // alloc()/upload() below work on the second stream
+        rc |= e->upload(&d.port_off, m->port_off + c0, (size_t)d.n_local + 1);
         uint4*          link_dev = nullptr;
         const uint32_t* peer_dev = nullptr;
         const uint64_t* lat_dev  = nullptr;
@@ -1702,20 +1718,64 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         rc |= e->alloc(&link_dev, d.nport_local, false);
         rc |= e->upload(&peer_dev, m->peer_port + d.P0, d.nport_local);
         rc |= e->upload(&lat_dev, m->latency + d.P0, d.nport_local);
-        rc |= e->upload(&poff_dev, m->port_off, (size_t)m->ncomp + 1);
+        if ( global_shift >= 32 ) rc |= e->upload(&poff_dev, m->port_off, (size_t)m->ncomp + 1);
         if ( !rc && d.nport_local ) {
             build_links_kernel<<<148 * 8, BLOCK, 0, e->stream>>>(link_dev, peer_dev, lat_dev, poff_dev, m->ncomp,
-                d.nport_local);
+                d.nport_local, global_shift);
             e->launches++;
         }
         d.link = link_dev;
+        rc |= e->upload(&d.clock_period, m->clock_period + c0, d.n_local);
+        if ( n_ranks > 1 ) rc |= e->upload(&d.rank_comp_begin, o->rank_comp_begin, (size_t)n_ranks + 1);
+        CUDA_OK(cudaEventRecord(ev_up, e->stream));
+        e->stream = main_stream;
     }
-    rc |= e->upload(&d.clock_period, m->clock_period + c0, d.n_local);
-    lap("uploads + link rows", e->stream);
-    if ( n_ranks > 1 ) rc |= e->upload(&d.rank_comp_begin, o->rank_comp_begin, (size_t)n_ranks + 1);
-    rc |= e->alloc(&d.ctl, d.n_local);
-    rc |= e->alloc(&d.state, (size_t)d.n_local * d.state_stride);
-    rc |= e->alloc(&d.aux, (size_t)d.n_local * d.aux_stride, false);
+    lap("uploads issued", nullptr);
+
+    // (3) lookahead window = minimum latency over every connected link (cut or not: a window is processed as one batch
+    // per component, so nothing sent inside it may be due inside it).  A multi-rank driver that passes the window (the
+    // minimum over ALL ranks, which it can get from one MIN all-reduce) lets every rank scan its own ports only.
+    const uint32_t nport   = m->port_off[m->ncomp];
+    const size_t   scan_lo = o->window ? d.P0 : 0, scan_hi = o->window ? (size_t)d.P0 + d.nport_local : nport;
+    uint64_t       mn_lat[16], mx_lat[16];
+    for ( auto& v : mn_lat )
+        v = TIME_NEVER;
+    for ( auto& v : mx_lat )
+        v = 0;
+    scan(scan_hi - scan_lo, [&](size_t lo, size_t hi, unsigned t) {
+        uint64_t mn = TIME_NEVER, mx = 0;
+        for ( size_t p = scan_lo + lo; p < scan_lo + hi; ++p )
+            if ( m->peer_port[p] != SSTB200_NO_PEER ) {
+                if ( m->latency[p] < mn ) mn = m->latency[p];
+                if ( m->latency[p] > mx ) mx = m->latency[p];
+            }
+        mn_lat[t] = mn;
+        mx_lat[t] = mx;
+    });
+    const uint64_t mn         = *std::min_element(mn_lat, mn_lat + 16);
+    const uint64_t mx_lat_all = *std::max_element(mx_lat, mx_lat + 16);
+    uint64_t       w          = o->window ? o->window : (mn == TIME_NEVER ? 1000000ull : mn);
+    if ( w == 0 || w > 0x7fffffffull ) {
+        set_error("engine_create: lookahead window must be in [1, 2^31) cycles (zero-latency links are not allowed)");
+        sstb200_engine_destroy(e);
+        return -1;
+    }
+    if ( mn < w ) {
+        set_error("engine_create: window larger than a link latency");
+        sstb200_engine_destroy(e);
+        return -1;
+    }
+    lap("window scan", nullptr);
+    // The event-parallel form runs the windows of this rank when: one local element type, and it has the form; nobody
+    // in the model looks at send sequence numbers, clocks or traces (ctl_free); a power-of-two port count per
+    // component whose link rows fit the staging buffer; no payloads; no handler counting; link latencies below 2^31.
+    // Blocks it cannot take in some window (see parallel_form.cuh) are run by the sequential form in that window.
+    e->pf_on = any_parallel && d.uniform_type == TYPE_MESH && d.ctl_free && uni_ok && uni0 && (uni0 & (uni0 - 1)) == 0 &&
+               (size_t)uni0 * BLOCK <= 2048 && !has_payload && !o->handler_counts && mx_lat_all < 0x7fffffffull &&
+               getenv("SSTB200_NO_PARALLEL_FORM") == nullptr;
+
+    // (4) the remaining allocations (engine stream)
+    rc |= e->alloc(&d.ctl, d.n_local, false); // every record is written by setup_kernel
     const size_t nev = (size_t)d.W * d.nbins * d.cap;
     rc |= e->alloc(&d.ev, nev, false);
     if ( has_payload ) rc |= e->alloc(&d.ev_payload, nev, false);
@@ -1741,11 +1801,21 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         rc |= e->alloc(&d.prof_clock, d.n_local);
     }
     if ( e->pf_on ) {
-        rc |= e->alloc(&d.fb_list, d.nbins);
-        rc |= e->alloc(&d.maint_list, d.n_local);
+        rc |= e->alloc(&d.fb_list, d.nbins, false);
+        rc |= e->alloc(&d.maint_list, d.n_local, false);
     }
-    rc |= e->alloc(&e->d_results, (size_t)d.n_local * NRESULT);
-    lap("allocations + clears", e->stream);
+    rc |= e->alloc(&e->d_results, (size_t)d.n_local * NRESULT, false); // results_kernel writes every word it exports
+    lap("allocations", nullptr);
+    // the caller's arrays have been consumed once both upload batches are through; whatever follows on the engine's
+    // stream is ordered behind the second stream's work
+    if ( !rc ) {
+        CUDA_OK(cudaStreamWaitEvent(e->stream, ev_up, 0));
+        CUDA_OK(cudaEventSynchronize(ev_params));
+        CUDA_OK(cudaEventSynchronize(ev_up));
+    }
+    cudaEventDestroy(ev_params);
+    cudaEventDestroy(ev_up);
+    lap("uploads done", nullptr);
     if ( rc ) {
         sstb200_engine_destroy(e);
         return -2;
@@ -1789,6 +1859,11 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<PholdElement::HAS_PAYLOAD, false, PholdElement>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<ClockNodeElement::HAS_PAYLOAD, false, ClockNodeElement>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<MeshElement::HAS_PAYLOAD, false, MeshElement>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false, false, MeshElement, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<CoreTestElement::HAS_PAYLOAD, false, CoreTestElement>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int n_sm = 148;
     CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, o->device));
     e->maint_grid = (uint32_t)n_sm * 8;
@@ -1806,7 +1881,9 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         e->pf_grid = std::min<uint32_t>(d.nbins, (uint32_t)(per_sm * n_sm));
         e->fb_grid = std::min<uint32_t>(d.nbins, (uint32_t)(2 * n_sm));
     }
-    CUDA_OK(cudaStreamSynchronize(e->stream));
+    // (the Ctrl mirror is pinned memory of the engine: later copies on the same stream are ordered behind this one)
+    if ( create_timing ) CUDA_OK(cudaStreamSynchronize(e->stream));
+    lap("generators seeded (waited for only when timing)", nullptr);
     *out = e;
     return 0;
 }
@@ -1821,6 +1898,10 @@ sstb200_engine_destroy(sstb200_engine* e)
         cudaFree(p);
     if ( e->graph_exec ) cudaGraphExecDestroy(e->graph_exec);
     if ( e->h_ctrl ) cudaFreeHost(e->h_ctrl);
+    if ( e->up_stream ) {
+        cudaStreamSynchronize(e->up_stream);
+        cudaStreamDestroy(e->up_stream);
+    }
     if ( e->own_stream && e->stream ) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -1834,13 +1915,7 @@ sstb200_engine_setup(sstb200_engine* e)
         set_error("engine_setup called twice");
         return -1;
     }
-    if ( e->d.aux_stride ) {
-        seed_mt_kernel<<<e->d.nbins, BLOCK, 0, e->stream>>>(e->d);
-        e->launches++;
-        // first MT19937 generation (and route digest) of every generator seeded above
-        maintenance_kernel<<<e->maint_grid, 256, 0, e->stream>>>(e->d, 1);
-        e->launches++;
-    }
+    // (the generators were seeded by engine_create, on this stream)
     setup_kernel<<<e->d.nbins, BLOCK, 0, e->stream>>>(e->d);
     e->launches++;
     CUDA_OK(cudaGetLastError());

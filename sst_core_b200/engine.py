@@ -211,6 +211,34 @@ _ERRORS = {
 }
 
 
+def _global_window(model: WiredModel, c0: int, c1: int, rank: int, n_ranks: int, device: int) -> int:
+    """Lookahead window of a partitioned model = the minimum link latency over ALL ranks.  Inside a torch.distributed
+    job of n_ranks processes every rank scans its own ports and one MIN all-reduce gives the result (the reference does
+    the same with MPI_Allreduce, sync/syncManager.cc:276-377); otherwise the model's ports are scanned once."""
+    try:
+        import torch
+        import torch.distributed as dist
+        in_job = dist.is_available() and dist.is_initialized() and dist.get_world_size() == n_ranks and \
+            dist.get_rank() == rank
+    except Exception:
+        in_job = False
+    if not in_job:
+        w = getattr(model, "_min_latency", None)
+        if w is None:
+            w = model._min_latency = model.min_latency()
+        return w or 0
+    p0, p1 = int(model.port_off[c0]), int(model.port_off[c1])
+    lat = model.latency[p0:p1][model.peer_port[p0:p1] != 0xFFFFFFFF]
+    local = int(lat.min()) if lat.size else (1 << 62)
+    if dist.get_backend() == "nccl":
+        t = torch.tensor([local], dtype=torch.int64, device=torch.device("cuda", device))
+    else:
+        t = torch.tensor([local], dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    w = int(t.item())
+    return 0 if w >= (1 << 62) else w
+
+
 class Engine:
     """One rank's engine.  ``Engine(model).run()`` for a single GPU; see :func:`run_distributed` for N GPUs."""
 
@@ -227,11 +255,14 @@ class Engine:
         if n_ranks > 1:
             if model.rank is None or model.n_ranks != n_ranks:
                 raise EngineError("multi-rank engine needs a model prepared by partition_model(model, n_ranks)")
-            counts = np.bincount(model.rank, minlength=n_ranks)
-            begins = np.zeros(n_ranks + 1, dtype=np.uint32)
-            begins[1:] = np.cumsum(counts)
+            begins = getattr(model, "_rank_begins", None)
+            if begins is None or len(begins) != n_ranks + 1:  # once per partitioned model, not once per engine
+                begins = np.searchsorted(model.rank, np.arange(n_ranks + 1)).astype(np.uint32)
+                model._rank_begins = begins
             self._begins = begins
             c0, c1 = int(begins[rank]), int(begins[rank + 1])
+            if not window:
+                window = _global_window(model, c0, c1, rank, n_ranks, device)
         else:
             self._begins = np.array([0, model.ncomp], dtype=np.uint32)
             c0, c1 = 0, model.ncomp

@@ -25,6 +25,29 @@ def build_oracle(force=False):
     return ORACLE_SO
 
 
+MESH_GOLDEN_SO = ROOT / "oracle" / "libmeshgolden.so"
+_mesh_lib = None
+
+
+def mesh_golden_counts(x, y, windows, threads=0):
+    """oracle/mesh_golden.cc: per-component received counts of an X x Y MessageMesh after `windows` lookahead windows
+    (count-only golden model for sizes the event-by-event oracle cannot hold).  Returns (counts int32 [x*y], events)."""
+    global _mesh_lib
+    src = ROOT / "oracle" / "mesh_golden.cc"
+    if _mesh_lib is None:
+        if not MESH_GOLDEN_SO.exists() or MESH_GOLDEN_SO.stat().st_mtime < src.stat().st_mtime:
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", str(MESH_GOLDEN_SO),
+                                   str(src)])
+        _mesh_lib = C.CDLL(str(MESH_GOLDEN_SO))
+        _mesh_lib.mesh_golden_counts.restype = C.c_uint64
+        _mesh_lib.mesh_golden_counts.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint, C.c_void_p]
+    counts = np.zeros(x * y, dtype=np.int32)
+    ev = _mesh_lib.mesh_golden_counts(x, y, windows, threads or (os.cpu_count() or 1), _p(counts))
+    if ev == 0xFFFFFFFFFFFFFFFF:
+        raise RuntimeError("mesh_golden: a component used more than one MT19937 generation; run fewer windows")
+    return counts, int(ev)
+
+
 _lib = None
 
 

@@ -106,3 +106,18 @@ def test_phold_1024x1024_at_bench_options_vs_oracle():
     ref = O.run_model(m)
     assert st.events_delivered == ref.events
     assert np.array_equal(res[:, :7], ref.results[:, :7])
+
+
+def test_mesh_4096x4096_25_windows_digest_equals_cpu_golden_model():
+    # BASELINE config 4 exactly as bench.py runs it (25 windows): the digest of all 16.7 M result records against
+    # tests/golden/bench_digests.json, computed on the CPU by oracle/mesh_golden.cc (tests/golden/make_bench_digests.py)
+    import json
+    from pathlib import Path
+    from sst_core_b200.digest import records_digest
+    fix = json.loads((Path(__file__).parent / "golden" / "bench_digests.json").read_text())["digests"]
+    n = 4096 * 4096
+    m = models.mesh_model(4096, 4096, stop_at="28ns", verbose=0, stats_enabled=True)
+    res, st = _run(m, 25, **BENCH_MESH)
+    want = fix["mesh_4096x4096_w25_stats1"]
+    assert st.events_delivered == want["events"] == 24 * 4 * n
+    assert f"{records_digest(np.arange(n), res[:, :6]):016x}" == want["digest"]
