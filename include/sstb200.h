@@ -105,6 +105,25 @@ int sstb200_engine_run(sstb200_engine* e, uint64_t max_windows, uint32_t check_e
 int sstb200_engine_dispatch(sstb200_engine* e);
 int sstb200_engine_ingest(sstb200_engine* e);
 int sstb200_engine_advance(sstb200_engine* e);
+/* ---- peer mode: the exchange over NVLink without a collective (replaces RankSyncSerialSkip::exchange's MPI_Isend/
+ * Irecv of serialized event vectors, sync/rankSyncSerialSkip.cc:239-300, and its two MPI_Allreduce, :318-335).
+ * Every rank maps the others' calendars; a send to a remote component reserves its slot in the OWNER's bin with a
+ * system-scope atomic and stores the record there (peer stores over NVLink); `dispatch` then ends with one mailbox
+ * write per rank (control words + window sequence number), `ingest` has nothing to do, and `advance` waits for all
+ * ranks' mailbox entries of the window before it folds them.  With the ranks connected, sstb200_engine_run drives a
+ * multi-rank engine natively (CUDA-graph replay of whole windows) -- every rank calls it with the same arguments.
+ *   peer_export : after engine_create; handle64 = 64-byte CUDA IPC handle of this rank's peer-visible region (may be
+ *                 NULL), *nbins = its number of component blocks, *region_dev = the region's device pointer
+ *   peer_connect: before engine_setup, on every rank, after ALL ranks have been created: handles = n_ranks x 64 bytes
+ *                 and nbins[n_ranks] gathered from peer_export in rank order (the entry of this rank is ignored)
+ *   peer_connect_local: the same for ranks living in ONE process on one GPU (regions = their device pointers);
+ *                 the driver steps the ranks itself: dispatch on all, then advance on all */
+int sstb200_engine_peer_export(sstb200_engine* e, void* handle64, uint32_t* nbins, void** region_dev);
+int sstb200_engine_peer_connect(sstb200_engine* e, const void* handles, const uint32_t* nbins);
+int sstb200_engine_peer_connect_local(sstb200_engine* e, void* const* regions, const uint32_t* nbins);
+/* the cudaStream_t the engine launches on (options.stream, or the one it created) */
+int sstb200_engine_stream(sstb200_engine* e, void** stream_out);
+
 /* device pointers + geometry of the exchange buffers.  Slot layout (u64 words), one slot per rank:
  *   [0] record count, [1..8] the sender's control words, [9] reserved, then capacity x {time, dst_seq, payload,
  *   dst_comp}; words_per_rank = 10 + capacity*4 */
@@ -127,7 +146,7 @@ typedef struct sstb200_status {
     uint64_t max_due;          /* high-water mark of due events in one block                                  */
     uint32_t finished;
     uint32_t error;            /* 0 ok; 1 calendar bin overflow; 2 shared-memory staging overflow; 3 time fault;
-                                  4 outbox overflow; 5 trace overflow                                         */
+                                  4 outbox overflow; 5 trace overflow; 6 a rank's mailbox entry did not arrive  */
     uint64_t error_info[4];
     uint64_t launches;         /* kernels launched by the engine so far                                       */
 } sstb200_status;

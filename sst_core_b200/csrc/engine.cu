@@ -63,11 +63,17 @@ constexpr int      BLOCK      = SSTB200_BLOCK; // components per CTA == threads 
 constexpr uint64_t TIME_NEVER = ~0ull;
 constexpr uint32_t PAR_MAX_EVENTS = MeshElement::PARALLEL_MAX_EVENTS; // events of one component per window in the event-parallel form
 
-enum : uint32_t { ERR_BIN_OVERFLOW = 1, ERR_SMEM_OVERFLOW = 2, ERR_TIME_FAULT = 3, ERR_OUTBOX_OVERFLOW = 4, ERR_TRACE_OVERFLOW = 5 };
+enum : uint32_t { ERR_BIN_OVERFLOW = 1, ERR_SMEM_OVERFLOW = 2, ERR_TIME_FAULT = 3, ERR_OUTBOX_OVERFLOW = 4, ERR_TRACE_OVERFLOW = 5,
+                  ERR_PEER_SYNC = 6 };
 enum { CW_PENDING = 0, CW_PRIMARY = 1, CW_CLOCKS = 2, CW_ERROR = 3, CW_EXIT_TIME = 4, CW_WORDS = 8 };
 // exchange slot layout (u64 words): [0] record count, [1..8] the sender's control words (piggy-backed so that one
 // all-to-all per window carries everything), [9] reserved, then capacity x {time, dst_seq, payload, dst_comp}
 constexpr uint32_t XHDR = 10;
+// peer mode (NVLink): every rank maps the calendars of the others and a send to a remote component is a reservation
+// + record store in the OWNER's calendar; what is left of the window's exchange is one small mailbox write per rank.
+// Mailbox slot (u64 words): [0..7] the sender's control words, [8] sequence number (windows completed + 1), [9] pad
+constexpr uint32_t MAX_RANKS = 16;
+constexpr uint32_t MAILW     = 10;
 
 struct Ctrl
 {
@@ -155,6 +161,14 @@ struct Dev
     uint32_t            pf_rcap;
     uint32_t*           fb_list;    // [nbins]
     uint32_t*           maint_list; // [n_local] component | operation << 30
+    // peer mode: the other ranks' calendars and mailboxes as mapped in this process (own entries = own buffers)
+    uint32_t            peer_on;
+    ulonglong2*         peer_ev[MAX_RANKS];
+    uint64_t*           peer_pay[MAX_RANKS];
+    uint32_t*           peer_bin_count[MAX_RANKS];
+    unsigned long long* peer_mail[MAX_RANKS]; // [2][n_ranks][MAILW] of the owner
+    uint32_t            peer_nbins[MAX_RANKS];
+    unsigned long long* mail;                 // this rank's mailbox
 };
 
 // ================================================================================================ device side
@@ -174,24 +188,37 @@ raise_error(const Dev& d, uint32_t code, uint64_t a, uint64_t b, uint64_t c)
 __device__ __forceinline__ void
 emit(const Dev& d, uint64_t k, uint64_t time, uint32_t dst_port, uint32_t dst_comp, uint32_t seq, uint64_t payload)
 {
+    uint32_t*   counts = d.bin_count;
+    ulonglong2* evs    = d.ev;
+    uint64_t*   pays   = d.ev_payload;
+    uint32_t    nb = d.nbins, lc = dst_comp - d.c0;
+    bool        remote = false;
     if ( d.n_ranks > 1 && (dst_comp < d.c0 || dst_comp >= d.c0 + d.n_local) ) {
         uint32_t r = 0;
         while ( r + 1 < d.n_ranks && dst_comp >= d.rank_comp_begin[r + 1] )
             ++r;
-        unsigned long long* box = d.outbox + (uint64_t)r * d.xwords;
-        unsigned long long  pos = atomicAdd(&box[0], 1ull);
-        if ( pos >= d.outbox_cap ) {
-            raise_error(d, ERR_OUTBOX_OVERFLOW, r, pos, d.outbox_cap);
+        if ( !d.peer_on ) {
+            unsigned long long* box = d.outbox + (uint64_t)r * d.xwords;
+            unsigned long long  pos = atomicAdd(&box[0], 1ull);
+            if ( pos >= d.outbox_cap ) {
+                raise_error(d, ERR_OUTBOX_OVERFLOW, r, pos, d.outbox_cap);
+                return;
+            }
+            unsigned long long* rec = box + XHDR + pos * 4;
+            rec[0]                  = time;
+            rec[1]                  = ((unsigned long long)dst_port << 32) | seq;
+            rec[2]                  = payload;
+            rec[3]                  = dst_comp;
             return;
         }
-        unsigned long long* rec = box + XHDR + pos * 4;
-        rec[0]                  = time;
-        rec[1]                  = ((unsigned long long)dst_port << 32) | seq;
-        rec[2]                  = payload;
-        rec[3]                  = dst_comp;
-        return;
+        // peer mode: straight into the owner's calendar (all ranks run the same window k, same slots, same capacity)
+        counts = d.peer_bin_count[r];
+        evs    = d.peer_ev[r];
+        pays   = d.peer_pay[r];
+        nb     = d.peer_nbins[r];
+        lc     = dst_comp - d.rank_comp_begin[r];
+        remote = true;
     }
-    const uint32_t lc   = dst_comp - d.c0;
     const uint32_t bin  = lc / BLOCK;
     const uint64_t base = k * d.ctrl->w;
     uint64_t       dk;
@@ -207,15 +234,56 @@ emit(const Dev& d, uint64_t k, uint64_t time, uint32_t dst_port, uint32_t dst_co
         dk = dt / d.ctrl->w;
     if ( dk > d.W - 1 ) dk = d.W - 1; // beyond the calendar horizon: parked in the farthest slot, re-binned there
     const uint32_t slot = (uint32_t)((k + dk) % d.W);
-    const uint32_t idx  = slot * d.nbins + bin;
-    const uint32_t pos  = atomicAdd(&d.bin_count[idx], 1u);
+    const uint32_t idx  = slot * nb + bin;
+    const uint32_t pos  = remote ? atomicAdd_system(&counts[idx], 1u) : atomicAdd(&counts[idx], 1u);
     if ( pos >= d.cap ) {
         raise_error(d, ERR_BIN_OVERFLOW, slot, bin, pos);
         return;
     }
     const uint64_t off = (uint64_t)idx * d.cap + pos;
-    d.ev[off] = make_ulonglong2(time, ((unsigned long long)dst_port << 32) | seq);
-    if ( d.has_payload ) d.ev_payload[off] = payload;
+    evs[off] = make_ulonglong2(time, ((unsigned long long)dst_port << 32) | seq);
+    if ( d.has_payload ) pays[off] = payload;
+}
+
+// ---- remote destinations in the block-wide flush of both window kernels.  Key of a remote destination bin:
+// outbox mode 0x80000000 | rank; peer mode 0x80000000 | rank << 27 | index of the bin in the owner's calendar
+__device__ __forceinline__ uint32_t
+remote_key(const Dev& d, uint32_t dcomp, uint32_t sl)
+{
+    uint32_t r = 0;
+    while ( r + 1 < d.n_ranks && dcomp >= d.rank_comp_begin[r + 1] )
+        ++r;
+    if ( !d.peer_on ) return 0x80000000u | r;
+    return 0x80000000u | (r << 27) | (sl * d.peer_nbins[r] + (dcomp - d.rank_comp_begin[r]) / BLOCK);
+}
+__device__ __forceinline__ uint32_t
+remote_reserve(const Dev& d, uint32_t ky, uint32_t cnt)
+{
+    if ( d.peer_on ) return atomicAdd_system(&d.peer_bin_count[(ky >> 27) & 15u][ky & 0x7FFFFFFu], cnt);
+    return (uint32_t)atomicAdd(&d.outbox[(uint64_t)(ky & 0x7FFFFFFFu) * d.xwords], (unsigned long long)cnt);
+}
+__device__ __forceinline__ void
+remote_write(const Dev& d, uint32_t ky, uint32_t pos, uint64_t tm, uint64_t ds, uint64_t payload, uint32_t dcomp)
+{
+    if ( d.peer_on ) {
+        const uint32_t r = (ky >> 27) & 15u, idx = ky & 0x7FFFFFFu;
+        if ( pos >= d.cap ) {
+            raise_error(d, ERR_BIN_OVERFLOW, idx / d.peer_nbins[r], idx % d.peer_nbins[r], pos);
+            return;
+        }
+        const uint64_t off = (uint64_t)idx * d.cap + pos;
+        d.peer_ev[r][off]  = make_ulonglong2(tm, ds);
+        if ( d.has_payload ) d.peer_pay[r][off] = payload;
+        return;
+    }
+    const uint32_t r = ky & 0x7FFFFFFFu;
+    if ( pos >= d.outbox_cap ) {
+        raise_error(d, ERR_OUTBOX_OVERFLOW, r, pos, d.outbox_cap);
+        return;
+    }
+    ulonglong2* rec = reinterpret_cast<ulonglong2*>(d.outbox + (uint64_t)r * d.xwords + XHDR + (uint64_t)pos * 4);
+    rec[0]          = make_ulonglong2(tm, ds);
+    rec[1]          = make_ulonglong2(payload, dcomp);
 }
 
 // Shared-memory view of one block's staged events.  Due events are staged here by phase 1; as a component consumes
@@ -349,19 +417,21 @@ store_state(const S& s, uint8_t* p, uint32_t from, uint32_t to)
         if ( (uint32_t)i * 16 >= from && (uint32_t)i * 16 < to ) dst[i] = tmp[i];
 }
 
-// ---- MT19937 seeding (mersenne.cc:149-159) of the aux blocks of elements that declare AUX_MT_SEED.  A thread per
-// component storing its 624 words one by one costs one 4-byte L2 transaction per word at a 2.5 KB stride (88 ms for
-// 16.7 M components).  Here every lane still runs its own component's recurrence, but 16 words at a time go through a
-// shared-memory tile and the warp writes them out as 16-byte pieces, 64 contiguous bytes per component per store.
-__global__ void __launch_bounds__(BLOCK)
-seed_mt_kernel(Dev d)
+// ---- MT19937 seeding (mersenne.cc:149-159) of the aux blocks of elements that declare AUX_MT_SEED.  The recurrence is
+// serial per generator, so every lane runs its own component's; 64 words at a time go through a shared-memory tile and
+// the warp writes them out one component per store instruction: 256 contiguous bytes (two full DRAM lines) each.
+// (A thread per component storing its words one by one costs one 4-byte L2 transaction per word at a 2.5 KB stride --
+// 88 ms for 16.7 M components; 64-byte pieces per component still left the 42 GB of stores at 1.2 TB/s.)
+constexpr uint32_t SEED_TILE = 64;
+__global__ void __launch_bounds__(128)
+seed_mt_kernel(Dev d, uint32_t c_lo, uint32_t c_hi)
 {
-    __shared__ uint32_t tile[BLOCK / 32][32][17];
+    __shared__ uint32_t tile[4][32][SEED_TILE + 1];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t lc   = blockIdx.x * BLOCK + threadIdx.x;
+    const uint32_t lc   = c_lo + blockIdx.x * 128 + threadIdx.x;
     bool           want = false;
     uint32_t       prev = 0, seed_off = 0;
-    if ( lc < d.n_local )
+    if ( lc < c_hi )
         with_element(d.comp_type[lc], [&](auto el) {
             using E = decltype(el);
             if constexpr ( E::AUX_MT_SEED ) {
@@ -373,22 +443,21 @@ seed_mt_kernel(Dev d)
     const uint32_t wantmask = __ballot_sync(0xffffffffu, want);
     if ( !wantmask ) return;
     uint8_t* const warp_aux = d.aux + (uint64_t)(lc - lane) * d.aux_stride;
-    for ( uint32_t chunk = 0; chunk < MT_N / 16; ++chunk ) {
-#pragma unroll
-        for ( uint32_t j = 0; j < 16; ++j ) {
-            const uint32_t i = chunk * 16 + j;
+    for ( uint32_t chunk = 0; chunk < (MT_N + SEED_TILE - 1) / SEED_TILE; ++chunk ) {
+#pragma unroll 8
+        for ( uint32_t j = 0; j < SEED_TILE; ++j ) {
+            const uint32_t i = chunk * SEED_TILE + j;
             if ( i ) prev = 1812433253u * (prev ^ (prev >> 30)) + i;
             tile[warp][lane][j] = prev;
         }
         __syncwarp();
-#pragma unroll
-        for ( uint32_t r = 0; r < 4; ++r ) {
-            const uint32_t comp = (lane >> 2) + 8 * r, piece = lane & 3;
-            const uint32_t off  = __shfl_sync(0xffffffffu, seed_off, comp);
-            if ( wantmask >> comp & 1u ) {
-                const uint32_t* t = &tile[warp][comp][piece * 4];
-                *(uint4*)(warp_aux + (uint64_t)comp * d.aux_stride + off + chunk * 64 + piece * 16) = make_uint4(t[0], t[1], t[2], t[3]);
-            }
+        // words [chunk*64, chunk*64+64) of one component per iteration: lane l writes words 2l, 2l+1
+        const uint32_t w0 = chunk * SEED_TILE + 2 * lane;
+        for ( uint32_t comp = 0; comp < 32; ++comp ) {
+            const uint32_t off = __shfl_sync(0xffffffffu, seed_off, comp);
+            if ( (wantmask >> comp & 1u) && w0 < (uint32_t)MT_N )
+                *(uint2*)(warp_aux + (uint64_t)comp * d.aux_stride + off + (uint64_t)w0 * 4) =
+                    make_uint2(tile[warp][comp][2 * lane], tile[warp][comp][2 * lane + 1]);
         }
         __syncwarp();
     }
@@ -839,13 +908,8 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
             if ( e < n_due && s_dst[e] != SSTB200_NO_PEER ) {
                 dcomp = s_sc[e].y;
                 dt    = s_time[e];
-                if ( d.n_ranks > 1 && (dcomp < d.c0 || dcomp >= d.c0 + d.n_local) ) {
-                    uint32_t r = 0;
-                    while ( r + 1 < d.n_ranks && dcomp >= d.rank_comp_begin[r + 1] )
-                        ++r;
-                    ky = 0x80000000u | r;
-                }
-                else if ( dt < w ) {
+                const bool remote = d.n_ranks > 1 && (dcomp < d.c0 || dcomp >= d.c0 + d.n_local);
+                if ( dt < w && (!remote || d.peer_on) ) {
                     raise_error(d, ERR_TIME_FAULT, T + dt, T, dcomp); // a send violated the lookahead
                 }
                 else {
@@ -855,7 +919,7 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
                         if ( dk > d.W - 1 ) dk = d.W - 1; // beyond the horizon: parked in the farthest slot
                         sl = (uint32_t)((slot + dk) % d.W);
                     }
-                    ky = sl * d.nbins + (dcomp - d.c0) / BLOCK;
+                    ky = remote ? remote_key(d, dcomp, sl) : sl * d.nbins + (dcomp - d.c0) / BLOCK;
                 }
             }
             // lanes of the warp with the same bin go through the table as ONE entry look-up + ONE counter update
@@ -902,8 +966,7 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
         if ( tid < HT && ht_key[tid] != 0xFFFFFFFFu && ht_cnt[tid] ) {
             const uint32_t ky = ht_key[tid];
             if ( ky & 0x80000000u )
-                ht_base[tid] = (uint32_t)atomicAdd(&d.outbox[(uint64_t)(ky & 0x7FFFFFFFu) * d.xwords],
-                    (unsigned long long)ht_cnt[tid]);
+                ht_base[tid] = remote_reserve(d, ky, ht_cnt[tid]);
             else
                 ht_base[tid] = atomicAdd(&d.bin_count[ky], ht_cnt[tid]);
         }
@@ -917,17 +980,7 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
             const uint64_t tm  = T + s_time[e];
             const uint64_t ds  = ((uint64_t)s_dst[e] << 32) | s_sc[e].x;
             if ( ky & 0x80000000u ) {
-                const uint32_t r = ky & 0x7FFFFFFFu;
-                if ( pos >= d.outbox_cap ) {
-                    raise_error(d, ERR_OUTBOX_OVERFLOW, r, pos, d.outbox_cap);
-                }
-                else {
-                    unsigned long long* rec = d.outbox + (uint64_t)r * d.xwords + XHDR + (uint64_t)pos * 4;
-                    rec[0]                  = tm;
-                    rec[1]                  = ds;
-                    rec[2]                  = PAYLOAD ? s_pay[e] : 0;
-                    rec[3]                  = s_sc[e].y;
-                }
+                remote_write(d, ky, pos, tm, ds, PAYLOAD ? s_pay[e] : 0, s_sc[e].y);
             }
             else if ( pos >= d.cap ) {
                 raise_error(d, ERR_BIN_OVERFLOW, ky / d.nbins, ky % d.nbins, pos);
@@ -1042,12 +1095,10 @@ ingest_kernel(Dev d)
 }
 
 // ---- open the next window (SyncManager::computeNextInsert syncManager.cc:772-798; Exit::check exit.cc:111-132)
-__global__ void
-advance_kernel(Dev d)
+__device__ void
+advance_fold(const Dev& d)
 {
-    if ( threadIdx.x != 0 || blockIdx.x != 0 ) return;
     Ctrl* c = d.ctrl;
-    if ( c->done ) return;
     long long pending = 0, primary = 0, clocks = 0, err = 0;
     uint64_t  exit_time = 0;
     if ( d.n_ranks > 1 ) {
@@ -1059,8 +1110,9 @@ advance_kernel(Dev d)
             err += g[CW_ERROR];
             if ( (uint64_t)g[CW_EXIT_TIME] > exit_time ) exit_time = (uint64_t)g[CW_EXIT_TIME];
         }
-        for ( uint32_t r = 0; r < d.n_ranks; ++r )
-            d.outbox[(uint64_t)r * d.xwords] = 0; // outboxes have been shipped
+        if ( !d.peer_on )
+            for ( uint32_t r = 0; r < d.n_ranks; ++r )
+                d.outbox[(uint64_t)r * d.xwords] = 0; // outboxes have been shipped
     }
     else {
         pending   = c->local[CW_PENDING];
@@ -1095,6 +1147,66 @@ advance_kernel(Dev d)
     c->k     = c->k + 1;
     c->T     = next_T;
     c->T_end = (c->stop_at && next_T + c->w > c->stop_at) ? c->stop_at : next_T + c->w;
+}
+
+__global__ void
+advance_kernel(Dev d)
+{
+    if ( threadIdx.x != 0 || blockIdx.x != 0 || d.ctrl->done ) return;
+    advance_fold(d);
+}
+
+// ---- peer mode: the window's exchange.  The boundary events are already in their owners' calendars (emit /
+// remote_write); what RankSyncSerialSkip::exchange still needs (rankSyncSerialSkip.cc:209-343: "everybody is done with
+// this window" + the MIN/flag all-reduce) is one mailbox write per rank: this rank's control words and the sequence
+// number of the window, stored over NVLink into every rank's mailbox, after a system-scope fence.
+__global__ void
+peer_post_kernel(Dev d)
+{
+    Ctrl* c = d.ctrl;
+    if ( c->done || blockIdx.x != 0 ) return;
+    const unsigned long long seq = c->windows + 1;
+    const uint32_t           par = (uint32_t)(seq & 1ull);
+    if ( threadIdx.x == 0 ) c->local[CW_ERROR] = c->error ? 1 : 0;
+    __syncthreads();
+    __threadfence_system(); // this rank's records are in the peers' calendars before anybody sees the sequence number
+    const uint32_t r = threadIdx.x;
+    if ( r < d.n_ranks ) {
+        volatile unsigned long long* m = d.peer_mail[r] + ((uint64_t)par * d.n_ranks + d.rank) * MAILW;
+        for ( uint32_t i = 0; i < (uint32_t)CW_WORDS; ++i )
+            m[i] = (unsigned long long)c->local[i];
+        __threadfence_system();
+        m[CW_WORDS] = seq;
+    }
+}
+
+// wait for every rank's mailbox entry of this window (spin: the peers are other GPUs running their own kernels; with
+// all ranks stepped by one process on one GPU the entries are already there and a missing one is an error), then fold
+// the control words and open the next window exactly like advance_kernel
+__global__ void
+peer_advance_kernel(Dev d, int spin)
+{
+    Ctrl* c = d.ctrl;
+    if ( c->done || blockIdx.x != 0 ) return;
+    const unsigned long long seq = c->windows + 1;
+    const uint32_t           par = (uint32_t)(seq & 1ull);
+    const uint32_t           r   = threadIdx.x;
+    if ( r < d.n_ranks ) {
+        volatile unsigned long long* m = d.mail + ((uint64_t)par * d.n_ranks + r) * MAILW;
+        if ( spin ) {
+            const long long t0 = clock64();
+            while ( m[CW_WORDS] != seq ) {
+                __nanosleep(200);
+                if ( clock64() - t0 > 20000000000ll ) break; // ~10 s: a peer is gone
+            }
+        }
+        if ( m[CW_WORDS] != seq ) raise_error(d, ERR_PEER_SYNC, r, seq, m[CW_WORDS]);
+        __threadfence_system();
+        for ( uint32_t i = 0; i < (uint32_t)CW_WORDS; ++i )
+            d.gathered[(uint64_t)r * CW_WORDS + i] = (long long)m[i];
+    }
+    __syncthreads();
+    if ( threadIdx.x == 0 ) advance_fold(d);
 }
 
 __global__ void
@@ -1387,13 +1499,13 @@ struct sstb200_engine
             launches++;
         }
         if ( pf_on ) {
-            maintenance_kernel<<<maint_grid, 256, 0, stream>>>(d, 0);
+            maintenance_kernel<<<maint_grid, 256, 0, stream>>>(d, 0, 0, 0);
             launches++;
         }
         CUDA_OK(cudaGetLastError());
         return 0;
     }
-    uint32_t launches_per_window() const { return pf_on ? 4u : 2u; }
+    uint32_t launches_per_window() const { return (pf_on ? 4u : 2u) + (n_ranks > 1 ? 1u : 0u); }
     // `n` windows (dispatch + advance each).  The kernels take the same arguments every window -- the window state
     // lives in device memory -- so a chunk is captured once into a CUDA graph and replayed: small models are bound by
     // launch overhead, not by the kernels.
@@ -1410,6 +1522,7 @@ struct sstb200_engine
                     int            rc     = 0;
                     for ( uint32_t i = 0; i < n && !rc; ++i ) {
                         rc = launch_dispatch();
+                        if ( !rc && n_ranks > 1 ) rc = launch_publish();
                         if ( !rc ) rc = launch_advance();
                     }
                     launches = before; // counted per replay below
@@ -1432,17 +1545,40 @@ struct sstb200_engine
         }
         for ( uint32_t i = 0; i < n; ++i ) {
             if ( int rc = launch_dispatch() ) return rc;
+            if ( n_ranks > 1 )
+                if ( int rc = launch_publish() ) return rc;
             if ( int rc = launch_advance() ) return rc;
         }
         return 0;
     }
     int launch_advance()
     {
-        advance_kernel<<<1, 32, 0, stream>>>(d);
+        if ( d.peer_on )
+            peer_advance_kernel<<<1, 32, 0, stream>>>(d, peer_spin ? 1 : 0);
+        else
+            advance_kernel<<<1, 32, 0, stream>>>(d);
         launches++;
         CUDA_OK(cudaGetLastError());
         return 0;
     }
+    // what follows this rank's window kernels in a multi-rank run: outbox mode -- the control words into the outbox
+    // headers (the driver then exchanges the outboxes); peer mode -- the mailbox write to every rank
+    int launch_publish()
+    {
+        if ( d.peer_on )
+            peer_post_kernel<<<1, 32, 0, stream>>>(d);
+        else
+            publish_control_kernel<<<1, 64, 0, stream>>>(d);
+        launches++;
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    // peer mode (sstb200_engine_peer_connect*): one device allocation holds everything other ranks write into --
+    // calendar records, payloads, bin fill counts, mailbox -- so that one IPC handle per rank maps it all
+    uint8_t*           region       = nullptr;
+    size_t             region_bytes = 0;
+    bool               peer_spin    = false; // peers are other processes / GPUs: peer_advance_kernel waits for them
+    std::vector<void*> ipc_opened;
 };
 
 #ifdef SSTB200_TIMING
@@ -1692,19 +1828,36 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     CUDA_OK(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming));
     // (2a) engine stream: component types + parameters, element state, then the generators
     rc |= e->upload(&d.comp_type, m->comp_type + c0, d.n_local);
-    rc |= e->upload(&d.comp_param, m->comp_param + (size_t)c0 * NPARAM, (size_t)d.n_local * NPARAM);
-    CUDA_OK(cudaEventRecord(ev_params, e->stream));
     rc |= e->alloc(&d.state, (size_t)d.n_local * d.state_stride);
     rc |= e->alloc(&d.aux, (size_t)d.n_local * d.aux_stride, false);
-    if ( !rc && d.aux_stride && d.n_local ) {
-        seed_mt_kernel<<<d.nbins, BLOCK, 0, e->stream>>>(d);
-        e->launches++;
-        // first MT19937 generation (and route digest) of every generator seeded above
+    {
+        // parameters in a few chunks, each followed by the seeding of its components: the generators of the first
+        // chunk are being built while the rest of the model is still crossing PCIe
+        int64_t* param_dev = nullptr;
+        rc |= e->alloc(&param_dev, (size_t)d.n_local * NPARAM, false);
+        d.comp_param = param_dev;
         int n_sm0 = 148;
         cudaDeviceGetAttribute(&n_sm0, cudaDevAttrMultiProcessorCount, o->device);
-        maintenance_kernel<<<(uint32_t)n_sm0 * 8, 256, 0, e->stream>>>(d, 1);
-        e->launches++;
+        const uint32_t n_chunks = d.n_local >= (1u << 20) ? 8u : 1u;
+        for ( uint32_t ch = 0; ch < n_chunks && !rc; ++ch ) {
+            const uint32_t lo = (uint32_t)((uint64_t)d.n_local * ch / n_chunks) & ~127u;
+            const uint32_t hi = ch + 1 == n_chunks ? d.n_local : (uint32_t)((uint64_t)d.n_local * (ch + 1) / n_chunks) & ~127u;
+            if ( hi <= lo ) continue;
+            CUDA_OK(cudaMemcpyAsync(param_dev + (size_t)lo * NPARAM, m->comp_param + ((size_t)c0 + lo) * NPARAM,
+                (size_t)(hi - lo) * NPARAM * sizeof(int64_t), cudaMemcpyHostToDevice, e->stream));
+            if ( ch + 1 == n_chunks ) CUDA_OK(cudaEventRecord(ev_params, e->stream));
+            if ( d.aux_stride ) {
+                seed_mt_kernel<<<(hi - lo + 127) / 128, 128, 0, e->stream>>>(d, lo, hi);
+                // first MT19937 generation (and route digest) of every generator seeded above
+                maintenance_kernel<<<(uint32_t)n_sm0 * 8, 256, 0, e->stream>>>(d, 1, lo, hi);
+                e->launches += 2;
+            }
+        }
+        if ( !d.n_local ) CUDA_OK(cudaEventRecord(ev_params, e->stream));
     }
+    // (the port arrays below start crossing PCIe when the parameters are through: two concurrent copies would only
+    // share the link and delay the seeding)
+    CUDA_OK(cudaStreamWaitEvent(e->up_stream, ev_params, 0));
     // (2b) second stream: the port arrays; link rows are built on the device from the rank's slice of peer_port /
     // latency (and the global port CSR when port counts differ between components)
     {
@@ -1777,9 +1930,22 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     // (4) the remaining allocations (engine stream)
     rc |= e->alloc(&d.ctl, d.n_local, false); // every record is written by setup_kernel
     const size_t nev = (size_t)d.W * d.nbins * d.cap;
-    rc |= e->alloc(&d.ev, nev, false);
-    if ( has_payload ) rc |= e->alloc(&d.ev_payload, nev, false);
-    rc |= e->alloc(&d.bin_count, (size_t)d.W * d.nbins);
+    {
+        // one allocation for what other ranks may write into (see sstb200_engine::region): records | payloads | bin
+        // fill counts | mailbox; only the counts and the mailbox are cleared
+        const size_t ev_b  = nev * sizeof(ulonglong2), pay_b = has_payload ? nev * 8 : 0;
+        const size_t cnt_b = (((size_t)d.W * d.nbins * 4) + 255) & ~(size_t)255;
+        const size_t mail_b = (size_t)2 * MAX_RANKS * MAILW * 8;
+        e->region_bytes     = ev_b + pay_b + cnt_b + mail_b;
+        rc |= e->alloc(&e->region, e->region_bytes, false);
+        if ( !rc ) {
+            d.ev         = reinterpret_cast<ulonglong2*>(e->region);
+            d.ev_payload = has_payload ? reinterpret_cast<uint64_t*>(e->region + ev_b) : nullptr;
+            d.bin_count  = reinterpret_cast<uint32_t*>(e->region + ev_b + pay_b);
+            d.mail       = reinterpret_cast<unsigned long long*>(e->region + ev_b + pay_b + cnt_b);
+            CUDA_OK(cudaMemsetAsync(d.bin_count, 0, cnt_b + mail_b, e->stream));
+        }
+    }
     rc |= e->alloc(&d.ctrl, 1);
     d.outbox_cap = o->outbox_capacity ? o->outbox_capacity : 65536;
     d.xwords     = XHDR + (uint64_t)d.outbox_cap * 4;
@@ -1894,6 +2060,8 @@ sstb200_engine_destroy(sstb200_engine* e)
     if ( !e ) return;
     cudaSetDevice(e->device);
     if ( e->stream ) cudaStreamSynchronize(e->stream);
+    for ( void* p : e->ipc_opened )
+        cudaIpcCloseMemHandle(p);
     for ( void* p : e->allocs )
         cudaFree(p);
     if ( e->graph_exec ) cudaGraphExecDestroy(e->graph_exec);
@@ -1932,8 +2100,9 @@ sstb200_engine_run(sstb200_engine* e, uint64_t max_windows, uint32_t check_every
         set_error("engine_run before engine_setup");
         return -1;
     }
-    if ( e->n_ranks > 1 ) {
-        set_error("engine_run is single-rank; step a multi-rank engine with dispatch/ingest/advance");
+    if ( e->n_ranks > 1 && !(e->d.peer_on && e->peer_spin) ) {
+        set_error("engine_run needs a single rank or ranks connected in peer mode (sstb200_engine_peer_connect); "
+                  "otherwise step the ranks with dispatch / exchange / ingest / advance");
         return -1;
     }
     if ( !check_every ) check_every = 64;
@@ -1968,10 +2137,7 @@ sstb200_engine_dispatch(sstb200_engine* e)
     if ( !e || !e->is_setup ) return -1;
     CUDA_OK(cudaSetDevice(e->device));
     if ( int rc = e->launch_dispatch(e->report_pending) ) return rc;
-    publish_control_kernel<<<1, 64, 0, e->stream>>>(e->d);
-    e->launches++;
-    CUDA_OK(cudaGetLastError());
-    return 0;
+    return e->launch_publish();
 }
 
 int
@@ -1979,7 +2145,7 @@ sstb200_engine_ingest(sstb200_engine* e)
 {
     if ( !e || !e->is_setup ) return -1;
     CUDA_OK(cudaSetDevice(e->device));
-    if ( e->n_ranks > 1 ) {
+    if ( e->n_ranks > 1 && !e->d.peer_on ) { // peer mode: the records are already in the calendar
         ingest_kernel<<<64, BLOCK, 0, e->stream>>>(e->d);
         e->launches++;
         CUDA_OK(cudaGetLastError());
@@ -1996,6 +2162,100 @@ sstb200_engine_advance(sstb200_engine* e)
     if ( !e || !e->is_setup ) return -1;
     CUDA_OK(cudaSetDevice(e->device));
     return e->launch_advance();
+}
+
+// ---- peer mode ----------------------------------------------------------------------------------------------------
+namespace {
+// where rank r's buffers lie inside its region, from the geometry every rank can compute (W, cap, payload setting are
+// the same on all ranks; the number of component blocks differs)
+void
+peer_layout(const Dev& d, uint32_t nbins_r, uint8_t* base, uint32_t r, Dev& out)
+{
+    const size_t nev   = (size_t)d.W * nbins_r * d.cap;
+    const size_t ev_b  = nev * sizeof(ulonglong2), pay_b = d.has_payload ? nev * 8 : 0;
+    const size_t cnt_b = (((size_t)d.W * nbins_r * 4) + 255) & ~(size_t)255;
+    out.peer_ev[r]        = reinterpret_cast<ulonglong2*>(base);
+    out.peer_pay[r]       = d.has_payload ? reinterpret_cast<uint64_t*>(base + ev_b) : nullptr;
+    out.peer_bin_count[r] = reinterpret_cast<uint32_t*>(base + ev_b + pay_b);
+    out.peer_mail[r]      = reinterpret_cast<unsigned long long*>(base + ev_b + pay_b + cnt_b);
+    out.peer_nbins[r]     = nbins_r;
+}
+int
+peer_check(sstb200_engine* e, const char* what)
+{
+    if ( !e ) return -1;
+    if ( e->n_ranks < 2 || e->n_ranks > MAX_RANKS ) {
+        set_error(std::string(what) + ": peer mode needs 2.." + std::to_string(MAX_RANKS) + " ranks");
+        return -1;
+    }
+    if ( e->is_setup ) {
+        set_error(std::string(what) + ": connect the ranks before engine_setup (setup() already sends events)");
+        return -1;
+    }
+    return 0;
+}
+} // namespace
+
+int
+sstb200_engine_peer_export(sstb200_engine* e, void* handle64, uint32_t* nbins, void** region_dev)
+{
+    if ( !e ) return -1;
+    CUDA_OK(cudaSetDevice(e->device));
+    CUDA_OK(cudaStreamSynchronize(e->stream)); // the region has been cleared before anybody may write into it
+    if ( handle64 ) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        CUDA_OK(cudaIpcGetMemHandle(&h, e->region));
+        memcpy(handle64, &h, 64);
+    }
+    if ( nbins ) *nbins = e->d.nbins;
+    if ( region_dev ) *region_dev = e->region;
+    return 0;
+}
+
+int
+sstb200_engine_peer_connect(sstb200_engine* e, const void* handles, const uint32_t* nbins)
+{
+    if ( int rc = peer_check(e, "engine_peer_connect") ) return rc;
+    if ( !handles || !nbins ) return -1;
+    CUDA_OK(cudaSetDevice(e->device));
+    Dev& d = e->d;
+    for ( uint32_t r = 0; r < e->n_ranks; ++r ) {
+        uint8_t* base = e->region;
+        if ( r != d.rank ) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const uint8_t*)handles + (size_t)r * 64, 64);
+            void* p = nullptr;
+            CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            e->ipc_opened.push_back(p);
+            base = (uint8_t*)p;
+        }
+        peer_layout(d, nbins[r], base, r, d);
+    }
+    d.peer_on    = 1;
+    e->peer_spin = true;
+    return 0;
+}
+
+int
+sstb200_engine_peer_connect_local(sstb200_engine* e, void* const* regions, const uint32_t* nbins)
+{
+    if ( int rc = peer_check(e, "engine_peer_connect_local") ) return rc;
+    if ( !regions || !nbins ) return -1;
+    Dev& d = e->d;
+    for ( uint32_t r = 0; r < e->n_ranks; ++r )
+        peer_layout(d, nbins[r], (uint8_t*)regions[r], r, d);
+    d.peer_on    = 1;
+    e->peer_spin = false; // the ranks are stepped one after the other on one GPU: nothing to wait for
+    return 0;
+}
+
+int
+sstb200_engine_stream(sstb200_engine* e, void** stream_out)
+{
+    if ( !e || !stream_out ) return -1;
+    *stream_out = (void*)e->stream;
+    return 0;
 }
 
 int

@@ -235,16 +235,11 @@ window_parallel_kernel(Dev d)
             dpt[j]            = l.x;
             dcp[j]            = l.y;
             dtm[j]            = dt;
-            if ( d.n_ranks > 1 && (l.y < d.c0 || l.y >= d.c0 + d.n_local) ) {
-                uint32_t r = 0;
-                while ( r + 1 < d.n_ranks && l.y >= d.rank_comp_begin[r + 1] )
-                    ++r;
-                key[j] = 0x80000000u | r;
-            }
-            else {
-                const uint32_t sl = dt < 2 * w ? slot1 : pf_far_slot(dt, w, slot, d.W);
-                key[j]            = sl * d.nbins + (l.y - d.c0) / BLOCK;
-            }
+            const uint32_t sl = dt < 2 * w ? slot1 : pf_far_slot(dt, w, slot, d.W);
+            if ( d.n_ranks > 1 && (l.y < d.c0 || l.y >= d.c0 + d.n_local) )
+                key[j] = remote_key(d, l.y, sl);
+            else
+                key[j] = sl * d.nbins + (l.y - d.c0) / BLOCK;
         }
         // ---- rank of every record inside its destination bin
 #pragma unroll
@@ -285,8 +280,7 @@ window_parallel_kernel(Dev d)
         if ( tid < PF_HT && ht_cnt[tid] ) {
             const uint32_t ky = ht_key[tid];
             if ( ky & 0x80000000u )
-                ht_base[tid] = (uint32_t)atomicAdd(&d.outbox[(uint64_t)(ky & 0x7FFFFFFFu) * d.xwords],
-                    (unsigned long long)ht_cnt[tid]);
+                ht_base[tid] = remote_reserve(d, ky, ht_cnt[tid]);
             else
                 ht_base[tid] = atomicAdd(&d.bin_count[ky], ht_cnt[tid]);
         }
@@ -299,15 +293,7 @@ window_parallel_kernel(Dev d)
             const uint64_t tm  = T + dtm[j];
             const uint64_t ds  = (uint64_t)dpt[j] << 32; // nobody reads a sequence number in these models (ctl_free)
             if ( ky & 0x80000000u ) {
-                const uint32_t r = ky & 0x7FFFFFFFu;
-                if ( pos >= d.outbox_cap ) {
-                    raise_error(d, ERR_OUTBOX_OVERFLOW, r, pos, d.outbox_cap);
-                }
-                else {
-                    ulonglong2* rec = reinterpret_cast<ulonglong2*>(d.outbox + (uint64_t)r * d.xwords + XHDR + (uint64_t)pos * 4);
-                    rec[0]          = make_ulonglong2(tm, ds);
-                    rec[1]          = make_ulonglong2(0, dcp[j]);
-                }
+                remote_write(d, ky, pos, tm, ds, 0, dcp[j]);
             }
             else if ( pos >= d.cap ) {
                 raise_error(d, ERR_BIN_OVERFLOW, ky / d.nbins, ky % d.nbins, pos);
@@ -398,20 +384,20 @@ MeshElement::maintain(uint32_t op, uint8_t* rec, uint8_t* aux, const int64_t* pa
     if ( ok && lane < (op == MAINT_INIT ? ROUTE_DIGEST_WORDS : ROUTE_DIGEST_SPLIT) ) dig[lane] = route_digest_word(gen, lane, ng);
 }
 
-// after a window (list mode) or before setup() (init_all: every local component): a warp per entry
+// after a window (list mode) or before setup() (init_all: every local component in [c_lo, c_hi)): a warp per entry
 __global__ void __launch_bounds__(256)
-maintenance_kernel(Dev d, int init_all)
+maintenance_kernel(Dev d, int init_all, uint32_t c_lo, uint32_t c_hi)
 {
     __shared__ __align__(16) uint32_t s_gen[8][MT_N];
     const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     const uint32_t nw = gridDim.x * 8, gw = blockIdx.x * 8 + wic;
-    uint32_t       n  = d.n_local;
+    uint32_t       n  = c_hi - c_lo;
     if ( !init_all ) {
         if ( d.ctrl->done ) return;
         n = min(d.ctrl->maint_n, d.n_local);
     }
     for ( uint32_t i = gw; i < n; i += nw ) {
-        const uint32_t ent = init_all ? (i | ((uint32_t)MAINT_INIT << 30)) : d.maint_list[i];
+        const uint32_t ent = init_all ? ((c_lo + i) | ((uint32_t)MAINT_INIT << 30)) : d.maint_list[i];
         const uint32_t lc = ent & 0x3FFFFFFFu, op = ent >> 30;
         with_element(d.uniform_type ? d.uniform_type : d.comp_type[lc], [&](auto el) {
             using E = decltype(el);

@@ -58,6 +58,8 @@ EXPORTS = [
     "sstb200_engine_run_to_report", "sstb200_engine_report_begin", "sstb200_engine_report_end",
     "sstb200_rng_streams",
     "sstb200_rng_ticks", "sstb200_rng_distribution",
+    "sstb200_engine_peer_export", "sstb200_engine_peer_connect", "sstb200_engine_peer_connect_local",
+    "sstb200_engine_stream",
 ]
 
 _lib = None
@@ -87,6 +89,10 @@ def lib():
     L.sstb200_engine_exchange_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                                   C.POINTER(C.c_uint64)]
     L.sstb200_engine_control_words.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.sstb200_engine_peer_export.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_void_p)]
+    L.sstb200_engine_peer_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sstb200_engine_peer_connect_local.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sstb200_engine_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.sstb200_engine_status.argtypes = [C.c_void_p, C.POINTER(_Status)]
     L.sstb200_engine_results.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.sstb200_engine_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -207,6 +213,7 @@ _ERRORS = {
     3: "time fault: event for time {0} while the window starts at {1} (component {2}); a send violated the lookahead",
     4: "outbox overflow (raise outbox_capacity): to rank {0}, fill {1}, capacity {2}",
     5: "trace overflow",
+    6: "peer mode: the mailbox entry of rank {0} for window sequence {1} did not arrive (found {2})",
     0x80000000: "another rank reported an error",
 }
 
@@ -275,6 +282,7 @@ class Engine:
         self._L = L
         self.device = device
         self._window = window
+        self.peer = None  # "ipc" / "local" once the ranks are connected in peer mode
 
     def close(self):
         if getattr(self, "_h", None):
@@ -319,6 +327,34 @@ class Engine:
 
     def advance(self):
         _check(self._L.sstb200_engine_advance(self._h), "engine_advance")
+
+    # ---- peer mode (include/sstb200.h): boundary events stored straight into the owning rank's calendar over NVLink
+    def peer_export(self):
+        """(64-byte CUDA IPC handle, number of component blocks, device pointer) of this rank's peer-visible region."""
+        h = (C.c_uint8 * 64)()
+        nb, reg = C.c_uint32(0), C.c_void_p()
+        _check(self._L.sstb200_engine_peer_export(self._h, h, C.byref(nb), C.byref(reg)), "engine_peer_export")
+        return bytes(h), int(nb.value), reg.value
+
+    def peer_connect(self, handles, nbins):
+        """handles: n_ranks x 64 bytes, nbins: n_ranks block counts, both in rank order (from every rank's peer_export).
+        Call on every rank before setup()."""
+        hb = np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
+        nb = np.ascontiguousarray(nbins, dtype=np.uint32)
+        _check(self._L.sstb200_engine_peer_connect(self._h, _p(hb), _p(nb)), "engine_peer_connect")
+        self.peer = "ipc"
+
+    def peer_connect_local(self, regions, nbins):
+        """The same for ranks of one process on one GPU: regions = their device pointers."""
+        rg = (C.c_void_p * len(regions))(*regions)
+        nb = np.ascontiguousarray(nbins, dtype=np.uint32)
+        _check(self._L.sstb200_engine_peer_connect_local(self._h, rg, _p(nb)), "engine_peer_connect_local")
+        self.peer = "local"
+
+    def stream_handle(self) -> int:
+        st = C.c_void_p()
+        _check(self._L.sstb200_engine_stream(self._h, C.byref(st)), "engine_stream")
+        return int(st.value or 0)
 
     def exchange_buffers(self):
         ob, ib, w = C.c_void_p(), C.c_void_p(), C.c_uint64()
@@ -455,11 +491,43 @@ class Engine:
 
 
 # ------------------------------------------------------------------------------------------------ multi-GPU stepping
-class DistributedRunner:
-    """One lookahead window per step across all ranks of the torch.distributed world:
+def connect_peers(engine) -> bool:
+    """Put the ranks of a torch.distributed job (NCCL backend, one process per GPU of one node) into PEER MODE: every
+    rank maps the others' calendars over CUDA IPC, boundary events are stored straight into the owner's bins over NVLink
+    and the per-window exchange is a mailbox write -- no collective in the window loop (include/sstb200.h, "peer
+    mode").  Collective: every rank calls it after creating its Engine and BEFORE setup().  Returns False (and changes
+    nothing) outside such a job or when SSTB200_NO_PEER is set; the ranks then exchange outboxes with one all-to-all per
+    window (DistributedRunner)."""
+    import os
 
-        dispatch -> ONE all-to-all of the outboxes, control words piggy-backed in the headers (NVLink / NCCL) -> ingest
-        -> advance
+    try:
+        import torch
+        import torch.distributed as dist
+    except Exception:
+        return False
+    n = engine.n_ranks
+    if os.environ.get("SSTB200_NO_PEER") or n < 2 or not (dist.is_available() and dist.is_initialized()):
+        return False
+    if dist.get_backend() != "nccl" or dist.get_world_size() != n or dist.get_rank() != engine.rank:
+        return False
+    handle, nbins, _ = engine.peer_export()
+    dev = torch.device("cuda", engine.device)
+    mine = np.concatenate([np.frombuffer(handle, dtype=np.uint8), np.array([nbins], dtype=np.uint32).view(np.uint8)])
+    allt = torch.empty(n * 68, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allt, torch.from_numpy(mine.copy()).to(dev))  # also: every rank's region is cleared
+    a = allt.cpu().numpy().reshape(n, 68)
+    engine.peer_connect([bytes(a[r, :64]) for r in range(n)], np.ascontiguousarray(a[:, 64:]).view(np.uint32).ravel())
+    return True
+
+
+class DistributedRunner:
+    """One lookahead window per step across all ranks of the torch.distributed world.
+
+    Peer mode (the engine was connected with :func:`connect_peers`):  dispatch -> advance.  The boundary events are in
+    their owners' calendars when dispatch ends; advance waits on the device for every rank's mailbox entry.  ``run``
+    hands whole chunks of windows to the native driver (CUDA-graph replay).
+    Outbox mode:  dispatch -> ONE all-to-all of the outboxes, control words piggy-backed in the headers (NCCL) ->
+    ingest -> advance.
 
     Replaces SyncManager::execute + RankSyncSerialSkip::exchange and its MPI_Allreduce calls
     (sync/syncManager.cc:547-732, sync/rankSyncSerialSkip.cc:209-343).  The engine may be the CUDA `Engine` or any
@@ -469,17 +537,36 @@ class DistributedRunner:
         import torch.distributed as dist
 
         self.dist, self.e = dist, engine
+        self.peer = getattr(engine, "peer", None) == "ipc"
+        self._stream_ctx = None
+        if self.peer:
+            return
         self.outbox, self.inbox = engine.exchange_tensors()
         self.local, self.gathered = engine.control_tensors()
+        if hasattr(engine, "stream_handle"):
+            # the all-to-all must run on the ENGINE's stream, between its dispatch and ingest kernels: NCCL orders
+            # itself behind torch's current stream only
+            import torch
+            ext = torch.cuda.ExternalStream(engine.stream_handle(), device=torch.device("cuda", engine.device))
+            self._stream_ctx = lambda: torch.cuda.stream(ext)
 
     def step(self):
         e = self.e
-        e.dispatch()  # ... which also writes this rank's control words into every outbox header
-        self.dist.all_to_all_single(self.inbox, self.outbox)  # the ONE collective of a window
+        e.dispatch()  # ... which also publishes this rank's control words (outbox headers / the ranks' mailboxes)
+        if self.peer:
+            e.advance()
+            return
+        if self._stream_ctx:
+            with self._stream_ctx():
+                self.dist.all_to_all_single(self.inbox, self.outbox)  # the ONE collective of a window
+        else:
+            self.dist.all_to_all_single(self.inbox, self.outbox)
         e.ingest()  # bins received events, collects every rank's control words from the inbox headers
         e.advance()
 
     def run(self, max_windows: int = 0, check_every: int = 32) -> bool:
+        if self.peer:
+            return self.e.run(max_windows=max_windows, check_every=check_every)
         done_windows = 0
         while True:
             chunk = check_every if not max_windows else min(check_every, max_windows - done_windows)
@@ -525,19 +612,28 @@ class LocalMultiRankRunner:
     partitions than GPUs.  Kernels of different ranks never wait on each other, so running them back to back on one
     stream is safe."""
 
-    def __init__(self, model: WiredModel, n_ranks: int, device: int = 0, **engine_opts):
+    def __init__(self, model: WiredModel, n_ranks: int, device: int = 0, peer: bool = True, **engine_opts):
         import torch
 
         self.torch = torch
         self.pm = partition_model(model, n_ranks)
         self.engines = [Engine(self.pm, device=device, rank=r, n_ranks=n_ranks, **engine_opts) for r in range(n_ranks)]
         self.n = n_ranks
-        self.xt = [e.exchange_tensors() for e in self.engines]
-        self.ct = [e.control_tensors() for e in self.engines]
+        self.peer = bool(peer) and n_ranks > 1
+        if self.peer:
+            # peer mode inside one process: every engine writes boundary events straight into the others' calendars
+            ex = [e.peer_export() for e in self.engines]
+            for e in self.engines:
+                e.peer_connect_local([x[2] for x in ex], [x[1] for x in ex])
+        else:
+            self.xt = [e.exchange_tensors() for e in self.engines]
+            self.ct = [e.control_tensors() for e in self.engines]
 
     def setup(self):
         for e in self.engines:
             e.setup()
+        for e in self.engines:
+            e.sync()
 
     def step(self):
         t = self.torch
@@ -545,12 +641,13 @@ class LocalMultiRankRunner:
             e.dispatch()
         for e in self.engines:
             e.sync()
-        for r in range(self.n):  # inbox[r][src] = outbox[src][r]
-            for src in range(self.n):
-                self.xt[r][1][src].copy_(self.xt[src][0][r])
-        t.cuda.synchronize()
-        for e in self.engines:
-            e.ingest()
+        if not self.peer:
+            for r in range(self.n):  # inbox[r][src] = outbox[src][r]
+                for src in range(self.n):
+                    self.xt[r][1][src].copy_(self.xt[src][0][r])
+            t.cuda.synchronize()
+            for e in self.engines:
+                e.ingest()
         for e in self.engines:
             e.advance()
         for e in self.engines:

@@ -105,7 +105,7 @@ def simulate_distributed(m: wireup.WiredModel, extras: Optional[dict] = None, ch
     import torch
     import torch.distributed as dist
 
-    from .engine import DistributedRunner, Engine, EngineError, partition_model
+    from .engine import DistributedRunner, Engine, EngineError, connect_peers, partition_model
 
     n, r = dist.get_world_size(), dist.get_rank()
     pm = partition_model(m, n)
@@ -116,6 +116,7 @@ def simulate_distributed(m: wireup.WiredModel, extras: Optional[dict] = None, ch
     with torch.cuda.stream(stream):
         e = Engine(pm, device=dev, rank=r, n_ranks=n, stream=stream.cuda_stream, **engine_opts)
         try:
+            connect_peers(e)  # NVLink peer mode when the job allows it (collective; before setup / restore)
             if restore_registry is not None:
                 e.restore(checkpoint.blob_for_rank(restore_registry, pm, r, n, engine_opts.get("outbox_capacity", 0)))
             else:

@@ -36,16 +36,26 @@ def _check_local(m, n_ranks, **opts):
     assert all(s.end_time == ref.end_time for s in sts)
 
 
+# peer=True: boundary events stored straight into the owner's calendar + mailbox (the NVLink peer mode, here inside one
+# process); peer=False: outboxes, exchanged by copies, ingest kernel (the path a collective-based driver uses)
+@pytest.mark.parametrize("peer", [True, False])
 @pytest.mark.parametrize("n_ranks", [2, 3, 8])
-def test_mesh_partitions_on_one_gpu(n_ranks):
-    _check_local(models.mesh_model(32, 24, stop_at="80ns", stats_enabled=True), n_ranks)
+def test_mesh_partitions_on_one_gpu(n_ranks, peer):
+    _check_local(models.mesh_model(32, 24, stop_at="80ns", stats_enabled=True), n_ranks, peer=peer)
 
 
+def test_mesh_partitions_larger_blocks_cross_ranks_event_parallel_form():
+    # 96 x 64 = 24 blocks of 256 components over 3 ranks: the event-parallel kernel with remote destinations in both modes
+    for peer in (True, False):
+        _check_local(models.mesh_model(96, 64, stop_at="120ns", stats_enabled=True), 3, peer=peer)
+
+
+@pytest.mark.parametrize("peer", [True, False])
 @pytest.mark.parametrize("n_ranks", [2, 4])
-def test_phold_partitions_on_one_gpu(n_ranks):
+def test_phold_partitions_on_one_gpu(n_ranks, peer):
     m = models.phold_model(20, 20, stop_at="100ns", stats_enabled=True)
     m.nocut_pairs = np.array([[0, 399], [5, 200]], dtype=np.uint32)  # non-contiguous no-cut groups: renumbering
-    _check_local(m, n_ranks, calendar_slots=16)
+    _check_local(m, n_ranks, calendar_slots=16, peer=peer)
 
 
 def test_clockpop_partitions_on_one_gpu():
