@@ -114,6 +114,15 @@ add_one_of4(Accumulator<T>* a, uint32_t which)
         a[3].add(1);
 }
 
+// (x % f) == 0 for a signed draw x and a positive divisor f fixed at construction (the C++ remainder is zero exactly
+// when |x| is a multiple of f)
+SSTB_HD bool
+divisible_i32(int32_t x, uint64_t magic, int32_t f)
+{
+    const uint32_t a = x < 0 ? 0u - (uint32_t)x : (uint32_t)x;
+    return fastmod_u32(a, magic, (uint32_t)f) == 0;
+}
+
 #if defined(__CUDACC__)
 
 __device__ __forceinline__ void
@@ -309,7 +318,7 @@ struct PholdElement
         XorShiftDev rng;
         // [32,48) construction constants
         uint32_t dmod, init;
-        uint64_t pad0;
+        uint64_t dmod_magic; // fastmod_magic(dmod)
         // [48,96) statistics
         Accumulator<uint64_t> delay;
         uint64_t              pad1;
@@ -333,6 +342,7 @@ struct PholdElement
         s.rng.seed((uint32_t)(p[0] + 1));
         s.init = (uint32_t)p[1];
         s.dmod = (uint32_t)p[2];
+        s.dmod_magic = fastmod_magic(s.dmod);
         s.delay.init();
     }
     template <class Ctx>
@@ -340,7 +350,7 @@ struct PholdElement
     {
         for ( uint32_t i = 0; i < s.init; ++i ) {
             uint32_t pp = s.rng.u32() % ctx.nports;
-            uint64_t d  = s.rng.u32() % s.dmod;
+            uint64_t d  = fastmod_u32(s.rng.u32(), s.dmod_magic, s.dmod);
             ctx.send((int)pp, d, d);
         }
     }
@@ -349,9 +359,10 @@ struct PholdElement
     {
         s.recv++;
         if ( ctx.stats_on ) s.delay.add(payload);
-        s.hash      = mixDelivery(s.hash, ctx.now, (uint64_t)port, payload);
-        uint32_t pp = s.rng.u32() % ctx.nports;
-        uint64_t d  = s.rng.u32() % s.dmod;
+        s.hash            = mixDelivery(s.hash, ctx.now, (uint64_t)port, payload);
+        const uint32_t np = ctx.nports, r0 = s.rng.u32();
+        const uint32_t pp = (np & (np - 1)) == 0 ? (r0 & (np - 1)) : r0 % np;
+        const uint64_t d  = fastmod_u32(s.rng.u32(), s.dmod_magic, s.dmod);
         ctx.send((int)pp, d, d);
     }
     template <class Ctx>
@@ -394,7 +405,7 @@ struct ClockNodeElement
         // [48,64) construction constants
         int32_t  commFreq;
         uint32_t pad1;
-        uint64_t pad2;
+        uint64_t comm_magic; // fastmod_magic(commFreq)
         // [64,160) statistics
         Accumulator<int32_t> count[4];
     };
@@ -413,8 +424,9 @@ struct ClockNodeElement
         s.ticks = s.last_cycle = s.recv = s.hash = 0;
         s.rng.z    = (uint32_t)(11 + p[0]);
         s.rng.w    = 272727u;
-        s.commFreq = (int32_t)p[1];
-        s.neighbor = s.rng.u32() % 4;
+        s.commFreq   = (int32_t)p[1];
+        s.comm_magic = fastmod_magic((uint32_t)s.commFreq);
+        s.neighbor   = s.rng.u32() % 4;
         for ( int i = 0; i < 4; ++i )
             s.count[i].init();
     }
@@ -432,7 +444,7 @@ struct ClockNodeElement
     {
         s.ticks++;
         s.last_cycle = cycle;
-        if ( (rng_i32(s.rng) % s.commFreq) == 0 ) {
+        if ( divisible_i32(rng_i32(s.rng), s.comm_magic, s.commFreq) ) {
             s.neighbor = (s.neighbor + 1) % 4;
             if ( s.neighbor < ctx.nports && ctx.connected((int)s.neighbor) ) {
                 ctx.send((int)s.neighbor, 0, 0);
@@ -484,7 +496,7 @@ struct CoreTestElement
         // [16,32) construction constants
         int32_t  commFreq;
         uint32_t pad0;
-        uint64_t pad1;
+        uint64_t comm_magic; // fastmod_magic(commFreq)
         // [32,128) statistics N, S, E, W
         Accumulator<int32_t> count[4];
     };
@@ -502,11 +514,11 @@ struct CoreTestElement
     {
         s.rng.z    = 11u;
         s.rng.w    = 272727u;
-        s.commFreq = (int32_t)p[1];
-        s.neighbor = rng_i32(s.rng) % 4;
-        s.bad      = 0;
-        s.pad0     = 0;
-        s.pad1     = 0;
+        s.commFreq   = (int32_t)p[1];
+        s.comm_magic = fastmod_magic((uint32_t)s.commFreq);
+        s.neighbor   = rng_i32(s.rng) % 4;
+        s.bad        = 0;
+        s.pad0       = 0;
         for ( int i = 0; i < 4; ++i )
             s.count[i].init();
     }
@@ -519,7 +531,7 @@ struct CoreTestElement
     template <class Ctx>
     __device__ static bool clockTick(Ctx& ctx, State& s, uint64_t)
     {
-        if ( (rng_i32(s.rng) % s.commFreq) == 0 ) {
+        if ( divisible_i32(rng_i32(s.rng), s.comm_magic, s.commFreq) ) {
             s.neighbor = (s.neighbor + 1) % 4; // C++ remainder: stays negative until it reaches 0
             if ( s.neighbor >= 0 ) {
                 ctx.send(s.neighbor, 0, 0);

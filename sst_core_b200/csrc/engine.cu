@@ -601,8 +601,9 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
     uint16_t* s_perm     = reinterpret_cast<uint16_t*>(s_hbase + 32); // [emax] per-component segments
     uint16_t* s_order    = s_perm + d.emax;                           // [BLOCK] thread -> component of the block
 
-    // ---- prologue: everything here is independent global traffic issued back to back.  The first 1024 records of
-    // the bin are loaded before its fill count is known (the slots exist; what is past the count is ignored).
+    // ---- prologue: the bin's records (as many as its fill count says: clock-driven populations have near-empty bins,
+    // and loading 1024 slots blindly cost them 16 KB of DRAM reads per block) and everything else a block needs from
+    // memory, issued back to back.
     const uint32_t n_in     = d.bin_count[slot * d.nbins + bin];
 #ifndef SSTB200_SPEC
 #define SSTB200_SPEC 4
@@ -614,7 +615,7 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
     for ( int b = 0; b < SPEC; ++b ) {
         const uint32_t i = tid + b * BLOCK;
         pl_spec[b]       = 0;
-        if ( i < d.cap ) {
+        if ( i < n_in ) {
             ev_spec[b] = d.ev[(uint64_t)(slot * d.nbins + bin) * d.cap + i];
             if ( PAYLOAD ) pl_spec[b] = d.ev_payload[(uint64_t)(slot * d.nbins + bin) * d.cap + i];
         }
@@ -721,7 +722,10 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
         return; // uniform across the CTA
     }
 
-    // ---- phase 2: finish the sort in shared memory
+    // ---- phase 2: finish the sort in shared memory (skipped by a block without due events: a whole-population clock
+    // tick needs none of it, and its sends go straight to the calendar)
+    uint32_t c = tid;
+    if ( n_due ) {
     // (a) counting sort by component: exclusive scan of the per-component counts (warp shuffles), scatter
     {
         const uint32_t cnt_c = s_cnt[tid];
@@ -752,7 +756,6 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
     // (b) the order inside each component's segment, (time, port, sequence), is made by the owning thread in phase 3
     // (insertion sort: the lanes of a warp own components with nearly equal event counts, and the sort overlaps the
     // element's first loads)
-    const uint16_t* s_ordered = s_perm;
     // (c, second half) thread -> component assignment
     {
         const uint32_t cnt_c  = s_cnt[tid];
@@ -760,14 +763,16 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
         s_order[s_hbase[bucket] + atomicAdd(&s_hist[bucket], 1u)] = (uint16_t)tid;
     }
     __syncthreads();
+    c = s_order[tid];
+    }
+    const uint16_t* s_ordered = s_perm;
 
     PHASE_MARK(3);
     // ---- phase 3: run the handlers.  Thread t owns component s_order[t] (the t-th busiest of the block).
-    const uint32_t  c      = s_order[tid];
     const uint32_t  lc     = bin * BLOCK + c;
     const bool      valid  = lc < d.n_local;
-    const uint32_t  my_cnt = s_cnt[c];
-    const uint16_t* seg    = s_ordered + s_off[c];
+    const uint32_t  my_cnt = n_due ? s_cnt[c] : 0;
+    const uint16_t* seg    = s_ordered + (n_due ? s_off[c] : 0);
     uint32_t        delivered = 0, ticks = 0, sent = 0, clocks_stopped = 0;
     uint4           c_lo = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0), c_hi = make_uint4(0, 0, 0, 0);
     if ( valid && !d.ctl_free ) {
@@ -885,8 +890,8 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
     // (key = window slot x destination block, or the destination rank): a record's rank inside its bin comes from a
     // shared-memory atomic, ONE global atomic per distinct bin reserves the calendar slots, then the records are
     // written side by side.  Records that find no table entry (more than HT distinct bins per CTA: irregular graphs)
-    // reserve their slot directly.
-    {
+    // reserve their slot directly.  (Nothing is staged in a block without due events.)
+    if ( n_due ) {
         constexpr uint32_t HT = 128;
         uint32_t* ht_key  = s_cnt;      // [HT] phase-2 scratch is dead by now
         uint32_t* ht_cnt  = s_cnt + HT; // [HT]
@@ -1256,41 +1261,97 @@ results_kernel(Dev d, uint64_t* out, uint32_t words)
 }
 
 // ================================================================================================ RNG stream kernels
+// BASELINE config 2: n_streams independent generators x `draws` u32 each, written stream-major, plus the position-
+// weighted checksum sum (i+1) * draw_i per stream.
+// Marsaglia / xorshift (8 / 16 bytes of state): a lane per generator, 64 draws at a time through a shared-memory tile;
+// the warp then writes one generator's 64 draws per store instruction (256 contiguous bytes), so the stores are full
+// DRAM lines instead of one 4-byte word per lane at a stride of `draws` words.
+constexpr uint32_t RNG_TILE = 64;
 template <class G>
 __device__ __forceinline__ void
-stream_body(G& g, uint64_t n, uint32_t* out, unsigned long long* checksum)
+small_stream_body(G& g, bool valid, uint64_t draws, uint32_t* warp_out, uint64_t stream_stride, uint32_t lane,
+    uint32_t (*tile)[RNG_TILE + 1], unsigned long long* checksum)
 {
     unsigned long long cs = 0;
-    for ( uint64_t i = 0; i < n; ++i ) {
-        const uint32_t v = g.u32();
-        if ( out ) out[i] = v;
-        cs += (i + 1) * (unsigned long long)v;
+    for ( uint64_t base = 0; base < draws; base += RNG_TILE ) {
+        const uint32_t n = (uint32_t)min((uint64_t)RNG_TILE, draws - base);
+        if ( valid ) {
+#pragma unroll 8
+            for ( uint32_t j = 0; j < n; ++j ) {
+                const uint32_t v = g.u32();
+                cs += (base + j + 1) * (unsigned long long)v;
+                if ( warp_out ) tile[lane][j] = v;
+            }
+        }
+        if ( warp_out ) {
+            __syncwarp();
+            const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
+            for ( uint32_t sidx = 0; sidx < 32; ++sidx ) {
+                if ( !(valid_mask >> sidx & 1u) ) continue;
+                uint32_t* o = warp_out + (uint64_t)sidx * stream_stride + base;
+                if ( n == RNG_TILE && (((uintptr_t)o) & 7u) == 0 )
+                    reinterpret_cast<uint2*>(o)[lane] = make_uint2(tile[sidx][2 * lane], tile[sidx][2 * lane + 1]);
+                else
+                    for ( uint32_t j = lane; j < n; j += 32 )
+                        o[j] = tile[sidx][j];
+            }
+            __syncwarp();
+        }
     }
-    *checksum = cs;
+    if ( valid ) *checksum = cs;
 }
 
 __global__ void __launch_bounds__(128)
-rng_stream_kernel(int kind, uint64_t s1, uint64_t s2, uint64_t stride1, uint64_t stride2, uint64_t n_streams,
-    uint64_t draws, uint32_t* out, unsigned long long* checksum, uint32_t* mt_scratch)
+rng_small_stream_kernel(int kind, uint64_t s1, uint64_t s2, uint64_t stride1, uint64_t stride2, uint64_t n_streams,
+    uint64_t draws, uint32_t* out, unsigned long long* checksum)
 {
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if ( j >= n_streams ) return;
-    uint32_t* o = out ? out + j * draws : nullptr;
+    __shared__ uint32_t tile[4][32][RNG_TILE + 1];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t j     = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool     valid = j < n_streams;
+    uint32_t*      wout  = out ? out + (j - lane) * draws : nullptr;
     const uint64_t a = s1 + j * stride1, b = s2 + j * stride2;
-    if ( kind == 0 ) {
-        uint32_t* mt = mt_scratch + j * MT_N;
-        mt_seed(mt, (uint32_t)a);
-        MersenneDev g { mt, 0 };
-        stream_body(g, draws, o, checksum + j);
-    }
-    else if ( kind == 1 ) {
+    if ( kind == 1 ) {
         MarsagliaDev g { (uint32_t)a, (uint32_t)b };
-        stream_body(g, draws, o, checksum + j);
+        small_stream_body(g, valid, draws, wout, draws, lane, tile[warp], checksum + j);
     }
     else {
         XorShiftDev g;
         g.seed((uint32_t)a);
-        stream_body(g, draws, o, checksum + j);
+        small_stream_body(g, valid, draws, wout, draws, lane, tile[warp], checksum + j);
+    }
+}
+
+// MersenneRNG (2.5 KB of state): a WARP per generator, the state in shared memory.  Seeding is the serial recurrence
+// (one lane); every generation is then built by the 32 lanes together (mt_warp_twist) and its 624 draws are tempered
+// and written by the warp as contiguous 128-byte lines.
+__global__ void __launch_bounds__(256)
+rng_mt_stream_kernel(uint64_t s1, uint64_t stride1, uint64_t n_streams, uint64_t draws, uint32_t* out,
+    unsigned long long* checksum)
+{
+    __shared__ __align__(16) uint32_t s_gen[8][MT_N];
+    const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    uint32_t* const gen = s_gen[wic];
+    const uint64_t  nw = (uint64_t)gridDim.x * 8;
+    for ( uint64_t j = (uint64_t)blockIdx.x * 8 + wic; j < n_streams; j += nw ) {
+        if ( lane == 0 ) mt_seed(gen, (uint32_t)(s1 + j * stride1));
+        __syncwarp();
+        unsigned long long cs = 0;
+        uint32_t*          o  = out ? out + j * draws : nullptr;
+        for ( uint64_t base = 0; base < draws; base += MT_N ) {
+            mt_warp_twist(gen, lane);
+            const uint32_t n = (uint32_t)min((uint64_t)MT_N, draws - base);
+            for ( uint32_t i = lane; i < n; i += 32 ) {
+                const uint32_t v = mt_temper(gen[i]);
+                cs += (base + i + 1) * (unsigned long long)v;
+                if ( o ) o[base + i] = v;
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for ( int off = 16; off > 0; off >>= 1 )
+            cs += __shfl_down_sync(0xffffffffu, cs, off);
+        if ( lane == 0 ) checksum[j] = cs;
     }
 }
 
@@ -1823,46 +1884,39 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
 
     int rc = 0;
     CUDA_OK(cudaStreamCreateWithFlags(&e->up_stream, cudaStreamNonBlocking));
-    cudaEvent_t ev_params = nullptr, ev_up = nullptr;
-    CUDA_OK(cudaEventCreateWithFlags(&ev_params, cudaEventDisableTiming));
+    cudaEvent_t ev_up = nullptr;
     CUDA_OK(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming));
-    // (2a) engine stream: component types + parameters, element state, then the generators
-    rc |= e->upload(&d.comp_type, m->comp_type + c0, d.n_local);
-    rc |= e->alloc(&d.state, (size_t)d.n_local * d.state_stride);
-    rc |= e->alloc(&d.aux, (size_t)d.n_local * d.aux_stride, false);
+    // (2) Every host->device copy goes through the second stream, back to back, so that PCIe never idles: component
+    // types, the parameters in a few chunks, then the port arrays (+ the link-row kernel).  The engine's stream clears
+    // the element state and, chunk by chunk as the parameters arrive, seeds the generators and builds their first
+    // generation: the generators of the first chunk are being built while the rest of the model is still crossing PCIe.
     {
-        // parameters in a few chunks, each followed by the seeding of its components: the generators of the first
-        // chunk are being built while the rest of the model is still crossing PCIe
+        cudaStream_t main_stream = e->stream;
+        e->stream                = e->up_stream; // alloc()/upload() below work on the second stream
+        rc |= e->upload(&d.comp_type, m->comp_type + c0, d.n_local);
         int64_t* param_dev = nullptr;
         rc |= e->alloc(&param_dev, (size_t)d.n_local * NPARAM, false);
         d.comp_param = param_dev;
-        int n_sm0 = 148;
-        cudaDeviceGetAttribute(&n_sm0, cudaDevAttrMultiProcessorCount, o->device);
-        const uint32_t n_chunks = d.n_local >= (1u << 20) ? 8u : 1u;
+        struct Chunk
+        {
+            uint32_t    lo, hi;
+            cudaEvent_t ev;
+        };
+        std::vector<Chunk> chunks;
+        const uint32_t     n_chunks = d.n_local >= (1u << 20) ? 8u : 1u;
         for ( uint32_t ch = 0; ch < n_chunks && !rc; ++ch ) {
             const uint32_t lo = (uint32_t)((uint64_t)d.n_local * ch / n_chunks) & ~127u;
             const uint32_t hi = ch + 1 == n_chunks ? d.n_local : (uint32_t)((uint64_t)d.n_local * (ch + 1) / n_chunks) & ~127u;
             if ( hi <= lo ) continue;
             CUDA_OK(cudaMemcpyAsync(param_dev + (size_t)lo * NPARAM, m->comp_param + ((size_t)c0 + lo) * NPARAM,
-                (size_t)(hi - lo) * NPARAM * sizeof(int64_t), cudaMemcpyHostToDevice, e->stream));
-            if ( ch + 1 == n_chunks ) CUDA_OK(cudaEventRecord(ev_params, e->stream));
-            if ( d.aux_stride ) {
-                seed_mt_kernel<<<(hi - lo + 127) / 128, 128, 0, e->stream>>>(d, lo, hi);
-                // first MT19937 generation (and route digest) of every generator seeded above
-                maintenance_kernel<<<(uint32_t)n_sm0 * 8, 256, 0, e->stream>>>(d, 1, lo, hi);
-                e->launches += 2;
-            }
+                (size_t)(hi - lo) * NPARAM * sizeof(int64_t), cudaMemcpyHostToDevice, e->up_stream));
+            Chunk c { lo, hi, nullptr };
+            CUDA_OK(cudaEventCreateWithFlags(&c.ev, cudaEventDisableTiming));
+            CUDA_OK(cudaEventRecord(c.ev, e->up_stream));
+            chunks.push_back(c);
         }
-        if ( !d.n_local ) CUDA_OK(cudaEventRecord(ev_params, e->stream));
-    }
-    // (the port arrays below start crossing PCIe when the parameters are through: two concurrent copies would only
-    // share the link and delay the seeding)
-    CUDA_OK(cudaStreamWaitEvent(e->up_stream, ev_params, 0));
-    // (2b) second stream: the port arrays; link rows are built on the device from the rank's slice of peer_port /
-    // latency (and the global port CSR when port counts differ between components)
-    {
-        cudaStream_t main_stream = e->stream;
-        e->stream                = e->up_stream; // alloc()/upload() below work on the second stream
+        // the port arrays; link rows are built on the device from the rank's slice of peer_port / latency (and the
+        // global port CSR when port counts differ between components)
         rc |= e->upload(&d.port_off, m->port_off + c0, (size_t)d.n_local + 1);
         uint4*          link_dev = nullptr;
         const uint32_t* peer_dev = nullptr;
@@ -1882,6 +1936,22 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         if ( n_ranks > 1 ) rc |= e->upload(&d.rank_comp_begin, o->rank_comp_begin, (size_t)n_ranks + 1);
         CUDA_OK(cudaEventRecord(ev_up, e->stream));
         e->stream = main_stream;
+        // every copy is queued: PCIe is busy from here on.  Now the big allocations (tens of milliseconds for the 80 GB
+        // of generator state of a 16.7 M-component mesh), then the generators, chunk by chunk as their parameters arrive
+        rc |= e->alloc(&d.state, (size_t)d.n_local * d.state_stride);
+        rc |= e->alloc(&d.aux, (size_t)d.n_local * d.aux_stride, false);
+        int n_sm0 = 148;
+        cudaDeviceGetAttribute(&n_sm0, cudaDevAttrMultiProcessorCount, o->device);
+        for ( const Chunk& c : chunks ) {
+            if ( !rc ) CUDA_OK(cudaStreamWaitEvent(main_stream, c.ev, 0));
+            cudaEventDestroy(c.ev); // released once the wait has been satisfied
+            if ( !rc && d.aux_stride ) {
+                seed_mt_kernel<<<(c.hi - c.lo + 127) / 128, 128, 0, main_stream>>>(d, c.lo, c.hi);
+                // first MT19937 generation (and route digest) of every generator seeded above
+                maintenance_kernel<<<(uint32_t)n_sm0 * 8, 256, 0, main_stream>>>(d, 1, c.lo, c.hi);
+                e->launches += 2;
+            }
+        }
     }
     lap("uploads issued", nullptr);
 
@@ -1976,10 +2046,8 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     // stream is ordered behind the second stream's work
     if ( !rc ) {
         CUDA_OK(cudaStreamWaitEvent(e->stream, ev_up, 0));
-        CUDA_OK(cudaEventSynchronize(ev_params));
         CUDA_OK(cudaEventSynchronize(ev_up));
     }
-    cudaEventDestroy(ev_params);
     cudaEventDestroy(ev_up);
     lap("uploads done", nullptr);
     if ( rc ) {
@@ -2572,14 +2640,19 @@ sstb200_rng_streams(int device, void* stream, int kind, uint64_t s1, uint64_t s2
         return -1;
     }
     CUDA_OK(cudaSetDevice(device));
-    uint32_t* mt = nullptr;
-    if ( kind == 0 ) CUDA_OK(cudaMallocAsync((void**)&mt, n_streams * MT_N * 4, (cudaStream_t)stream));
-    const uint32_t threads = 128;
-    const uint64_t blocks  = (n_streams + threads - 1) / threads;
-    rng_stream_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(kind, s1, s2, stride1, stride2, n_streams,
-        draws, (uint32_t*)out_dev, (unsigned long long*)checksum_dev, mt);
+    if ( kind == 0 ) {
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+        const uint64_t blocks = std::min<uint64_t>((n_streams + 7) / 8, (uint64_t)n_sm * 8);
+        rng_mt_stream_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s1, stride1, n_streams, draws,
+            (uint32_t*)out_dev, (unsigned long long*)checksum_dev);
+    }
+    else {
+        const uint64_t blocks = (n_streams + 127) / 128;
+        rng_small_stream_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(kind, s1, s2, stride1, stride2,
+            n_streams, draws, (uint32_t*)out_dev, (unsigned long long*)checksum_dev);
+    }
     CUDA_OK(cudaGetLastError());
-    if ( mt ) CUDA_OK(cudaFreeAsync(mt, (cudaStream_t)stream));
     return 0;
 }
 

@@ -338,10 +338,10 @@ mt_warp_load(uint32_t* gen, const uint32_t* src, uint32_t lane)
         reinterpret_cast<uint4*>(gen)[i] = reinterpret_cast<const uint4*>(src)[i];
     __syncwarp();
 }
+// gen (shared memory) <- the generation after gen, in place
 __device__ __forceinline__ void
-mt_warp_regen(uint32_t* gen, const uint32_t* src, uint32_t* dst, uint32_t lane)
+mt_warp_twist(uint32_t* gen, uint32_t lane)
 {
-    mt_warp_load(gen, src, lane);
     for ( uint32_t c = 0; c < (MT_N + 31) / 32; ++c ) {
         const uint32_t i   = c * 32 + lane;
         const bool     act = i < (uint32_t)MT_N;
@@ -351,10 +351,15 @@ mt_warp_regen(uint32_t* gen, const uint32_t* src, uint32_t* dst, uint32_t lane)
         if ( act ) gen[i] = v;
         __syncwarp();
     }
+}
+__device__ __forceinline__ void
+mt_warp_regen(uint32_t* gen, const uint32_t* src, uint32_t* dst, uint32_t lane)
+{
+    mt_warp_load(gen, src, lane);
+    mt_warp_twist(gen, lane);
     for ( uint32_t i = lane; i < MT_N / 4; i += 32 )
         reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(gen)[i];
 }
-
 __device__ inline void
 MeshElement::maintain(uint32_t op, uint8_t* rec, uint8_t* aux, const int64_t* param, uint32_t* gen, uint32_t lane)
 {

@@ -301,6 +301,25 @@ struct XorShiftDev
     }
 };
 
+// x % d for 32-bit x and a divisor fixed at construction: M = 2^64 / d (rounded up) is kept with the component's
+// constants and the remainder is the high half of (M * x mod 2^64) * d -- two multiplications instead of a division
+// sequence (D. Lemire, "Faster remainder by direct computation", 2019; exact for all 32-bit x and d >= 1)
+SSTB_HD uint64_t
+fastmod_magic(uint32_t d)
+{
+    return 0xFFFFFFFFFFFFFFFFull / d + 1;
+}
+SSTB_HD uint32_t
+fastmod_u32(uint32_t x, uint64_t M, uint32_t d)
+{
+    const uint64_t low = M * x;
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__umul64hi(low, d);
+#else
+    return (uint32_t)(((unsigned __int128)low * d) >> 64);
+#endif
+}
+
 // Composite draws shared by all generators (Random interface, rng/rng.h:29-65).
 template <class G>
 SSTB_HD int32_t

@@ -101,3 +101,12 @@ dev_xorshift_stream(uint32_t seed, uint64_t n, uint32_t* out)
         out[i] = g.u32();
 }
 }
+
+extern "C" int
+dev_fastmod_check(uint32_t d, const uint32_t* xs, uint64_t n)
+{
+    const uint64_t M = fastmod_magic(d);
+    for ( uint64_t i = 0; i < n; ++i )
+        if ( fastmod_u32(xs[i], M, d) != xs[i] % d ) return 0;
+    return 1;
+}

@@ -78,3 +78,13 @@ def test_marsaglia_and_xorshift(drv):
     ref, _ = O.rng_u32_stream(2, 1447, 0, n)
     drv.dev_xorshift_stream(1447, n, out.ctypes.data_as(C.c_void_p))
     assert np.array_equal(out, ref)
+
+
+def test_fastmod_equals_the_remainder_operator(drv):
+    # PHOLD's `u32 % dmod` and the clock-driven elements' `i32 % commFreq == 0` use a multiply-high remainder
+    rng = np.random.default_rng(7)
+    xs = np.concatenate([rng.integers(0, 1 << 32, 200000, dtype=np.uint64).astype(np.uint32),
+                         np.array([0, 1, 2, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFF, 0xFFFFFFFE], dtype=np.uint32)])
+    drv.dev_fastmod_check.argtypes = [C.c_uint32, C.c_void_p, C.c_uint64]
+    for d in [1, 2, 3, 4, 5, 7, 1000, 8000, 65535, 65536, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFF, 12345677]:
+        assert drv.dev_fastmod_check(d, xs.ctypes.data_as(C.c_void_p), len(xs)) == 1, d
