@@ -148,12 +148,15 @@ def run_reference_sample(size, ns, threads):
     Returns (events, execute-region seconds)."""
     exe, libdir = ref_paths()
     script = ROOT / "tests" / "models" / "mesh.py"
-    cmd = [str(exe), "--lib-path", str(libdir), "--timing-info=2", "--stop-at", f"{ns}ns",
+    cmd = [str(exe), "--lib-path", str(libdir), "--timing-info=3", "--stop-at", f"{ns}ns",
            "--model-options", f"{size} {size} 1 0", str(script)]
     if threads > 1:
         cmd[1:1] = ["-n", str(threads)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=3000, cwd="/tmp").stdout
-    m = re.search(r"execute\s*\n.*?Duration:\s*([0-9.eE+-]+)\s*(s|ms|us)", out, re.S)
+    # the `run` sub-region of `execute` (Simulation::run, simulation.cc:1072-1193): what the hot path replaces --
+    # init / setup / complete / finish of the 65 k components are not part of it
+    m = re.search(r"■ run\s*\n.*?Duration:\s*([0-9.eE+-]+)\s*(s|ms|us)", out, re.S) or \
+        re.search(r"execute\s*\n.*?Duration:\s*([0-9.eE+-]+)\s*(s|ms|us)", out, re.S)
     if not m:
         raise RuntimeError("could not parse the reference's --timing-info output:\n" + out[-1500:])
     secs = float(m.group(1)) * {"s": 1.0, "ms": 1e-3, "us": 1e-6}[m.group(2)]
@@ -166,8 +169,8 @@ def cpu_baseline(size, ns):
     if exe.exists():
         ev, secs = run_reference_sample(size, ns, cores)
         return {"value": ev / secs, "unit": "events/s", "cores": cores, "kind": "reference",
-                "sample": f"sstsim.x -n {cores} MessageMesh {size}x{size}, {ns} ns ({ev} events, execute region "
-                          f"{secs:.2f} s of --timing-info=2)"}
+                "sample": f"sstsim.x -n {cores} MessageMesh {size}x{size}, {ns} ns ({ev} events, `run` region "
+                          f"{secs:.2f} s of --timing-info=3)"}
     sys.path.insert(0, str(ROOT / "tests"))
     import oracle_lib as O
     from sst_core_b200 import models
@@ -271,12 +274,18 @@ def ours(a):
     pm = partition_model(m, world) if world > 1 else m
     pm.pin()
 
-    def make_engine():
+    def make_engine(bd=None):
+        ta = time.perf_counter()
         if world > 1:
             eng = Engine(pm, device=local_rank, rank=rank, n_ranks=world, stream=stream.cuda_stream, **opts)
+            tb = time.perf_counter()
             connect_peers(eng)  # peer mode: boundary events straight into the owner's calendar over NVLink
-            return eng
-        return Engine(pm, device=local_rank, stream=stream.cuda_stream, **opts)
+        else:
+            eng = Engine(pm, device=local_rank, stream=stream.cuda_stream, **opts)
+            tb = time.perf_counter()
+        if bd is not None:
+            bd.update({"create_s": tb - ta, "connect_peers_s": time.perf_counter() - tb})
+        return eng
 
     # ---- parity: an order-independent 64-bit digest of the result records every rank downloads (sst_core_b200/digest.py),
     # summed over the ranks, against tests/golden/bench_digests.json (the CPU golden model's digest of the same
@@ -296,6 +305,9 @@ def ours(a):
         # (the kernel-timed region below has its own warm-up windows)
         wu = torch.zeros(world * 8, dtype=torch.int64, device=dev)
         dist.all_to_all_single(torch.empty_like(wu), wu)
+        # ... and the two small collectives an engine start uses (window MIN all-reduce, IPC handle all-gather)
+        dist.all_reduce(wu[:1], op=dist.ReduceOp.MIN)
+        dist.all_gather_into_tensor(torch.empty(world * 8, dtype=torch.int64, device=dev), wu[:8])
         torch.cuda.synchronize(dev)
     if not a.no_e2e:
         # process warm-up (CUDA context, lazy module load of the kernels, allocator): one tiny job of the same kind
@@ -316,17 +328,24 @@ def ours(a):
             dist.barrier()
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
+        bd = {}
         with torch.cuda.stream(stream):
-            e = make_engine()
+            e = make_engine(bd)
+            t1 = time.perf_counter()
             e.setup()
+            e.sync()
+            t2 = time.perf_counter()
             if world > 1:
                 DistributedRunner(e).run(max_windows=W + K, check_every=W + K)
             else:
                 e.run(max_windows=W + K, check_every=W + K)
+            e.sync()
+            t3 = time.perf_counter()
             res = e.results(result_words(m), compact=True, out=res_buf)
             st = e.status()
         torch.cuda.synchronize(dev)
         secs = time.perf_counter() - t0
+        bd.update({"setup_s": t2 - t1, "windows_s": t3 - t2, "results_s": time.perf_counter() - t3})
         e.raise_on_error(st)
         digests["e2e"] = local_digest(res)
         ev = torch.tensor([st.events_delivered + st.clock_ticks, 0], dtype=torch.float64, device=dev)  # same unit as `value`
@@ -337,6 +356,7 @@ def ours(a):
         e2e = {"value": float(ev[0].item()) / float(tt[0].item()), "unit": "events/s",
                "h2d_bytes_per_step": model_bytes // (W + K), "d2h_bytes_per_step": res.nbytes // (W + K),
                "seconds": float(tt[0].item()), "windows": W + K,
+               "breakdown": {k: round(v, 4) for k, v in bd.items()},  # rank 0's own phases (host wall clock)
                "note": "engine create from host arrays + setup + windows + results to host, per rank slice"}
         e.close()
         del res
@@ -506,6 +526,27 @@ def ours(a):
         if not a.no_cpu_baseline and world == 1:
             try:
                 line["cpu_baseline"] = cpu_baseline(a.cpu_size, a.cpu_ns)
+                if a.workload == "mesh":
+                    # the SAME model at the SAME size on the GPU (a same-config pair next to the reference's number;
+                    # the 4096^2 headline cannot be held by the reference: ~20 KB per component)
+                    from sst_core_b200 import models as _models
+                    ms_ = _models.mesh_model(a.cpu_size, a.cpu_size, stop_at=f"{a.cpu_ns}ns", verbose=0,
+                                             stats_enabled=bool(a.stats))
+                    with torch.cuda.stream(stream):
+                        es = Engine(ms_, device=local_rank, stream=stream.cuda_stream, calendar_slots=2, bin_capacity=2048)
+                        es.setup()
+                        es.run(max_windows=2, check_every=2)
+                        torch.cuda.synchronize(dev)
+                        t0s = time.perf_counter()
+                        es.run(max_windows=0, check_every=a.cpu_ns)
+                        torch.cuda.synchronize(dev)
+                        dts = time.perf_counter() - t0s
+                        sts = es.status()
+                        es.close()
+                    line["cpu_baseline"]["same_size_gpu_value"] = (a.cpu_size * a.cpu_size * 4 * (a.cpu_ns - 2)) / dts
+                    line["cpu_baseline"]["same_size_note"] = (
+                        f"this engine on the same MessageMesh {a.cpu_size}x{a.cpu_size}, windows 2..{a.cpu_ns - 1} wall "
+                        f"clock {dts * 1e3:.2f} ms, {sts.events_delivered} events in all: a same-config pair")
             except Exception as ex:  # the baseline must not take the bench line down
                 line["cpu_baseline"] = {"value": None, "unit": "events/s", "cores": 0, "kind": "unavailable",
                                         "sample": repr(ex)[:200]}
