@@ -1,22 +1,19 @@
 #!/bin/bash
-# multi-GPU validation + strong-scaling bench lines (run with gpurun --gpus N)
+# multi-GPU measurement set: bash profiles/multi.sh N  (run under `gpurun --gpus N`)
 N=${1:-2}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_multirank.py -m gpu -q --timeout 600 > gpurun_out/pytest_multi.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/pytest_multi.log
-for g in $(seq 1 8); do
-  [ $g -le $N ] || continue
-  [ $g -eq 1 ] || [ $g -eq 2 ] || [ $g -eq 4 ] || [ $g -eq 8 ] || continue
-  if [ $g -eq 1 ]; then
-    timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_${g}gpu.log 2> gpurun_out/bench_${g}gpu.err
-  else
-    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $g --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $g --steps 20 --warmup 5 > gpurun_out/bench_${g}gpu.log 2> gpurun_out/bench_${g}gpu.err
-  fi
-  python - <<PY
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+timeout 600 $TR --master-port 29511 tests/multi_gpu_check.py 2>&1 | grep -E "bit-exact|digest|MULTI_GPU_OK|Error|error" | tail -12
+timeout 600 $TR --master-port 29512 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_${N}gpu.log 2> gpurun_out/bench_${N}gpu.err
+python - <<PY
 import json
-try:
-    d = json.loads([l for l in open('gpurun_out/bench_${g}gpu.log') if l.startswith('{')][-1])
-    print('$g GPU:', round(d['value'] / 1e9, 2), 'G ev/s', round(d['ms_per_step'], 4), 'ms/window  dispatch', round(d['roofline']['ms_per_launch'], 4), 'ms  e2e', round(d['e2e']['value'] / 1e9, 3), 'G ev/s in', round(d['e2e']['seconds'], 3), 's  launches', d['gpu_launches'])
-except Exception as e:
-    print('$g GPU: FAILED', e); print(open('gpurun_out/bench_${g}gpu.err').read()[-1500:])
+d=json.loads(open("gpurun_out/bench_${N}gpu.log").read().strip().splitlines()[-1])
+print("mesh $N gpus: value %.4g ms %.4f frac %.3f e2e %.4g (%s) parity %s exchange %s" % (d["value"], d["ms_per_step"], d["roofline"]["frac"], d["e2e"]["value"], d["e2e"]["breakdown"], d["parity"]["match"], d["config"]["exchange"]))
 PY
+tail -3 gpurun_out/bench_${N}gpu.err
+for w in clockpop phold; do
+  X=""; [ $w = phold ] && X="--x 1024 --y 1024"
+  timeout 600 $TR --master-port 29513 bench.py --gpus $N --workload $w $X --steps 20 --warmup 10 --no-e2e > gpurun_out/bench_${w}_${N}gpu.log 2> gpurun_out/bench_${w}_${N}gpu.err
+  python -c "
+import json;d=json.loads(open('gpurun_out/bench_${w}_${N}gpu.log').read().strip().splitlines()[-1]);print('$w $N gpus', d['value'], d['ms_per_step'], d['roofline']['frac'])"
 done

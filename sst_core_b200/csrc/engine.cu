@@ -1165,11 +1165,10 @@ advance_kernel(Dev d)
 // remote_write); what RankSyncSerialSkip::exchange still needs (rankSyncSerialSkip.cc:209-343: "everybody is done with
 // this window" + the MIN/flag all-reduce) is one mailbox write per rank: this rank's control words and the sequence
 // number of the window, stored over NVLink into every rank's mailbox, after a system-scope fence.
-__global__ void
-peer_post_kernel(Dev d)
+__device__ __forceinline__ void
+peer_post(const Dev& d)
 {
-    Ctrl* c = d.ctrl;
-    if ( c->done || blockIdx.x != 0 ) return;
+    Ctrl* const              c   = d.ctrl;
     const unsigned long long seq = c->windows + 1;
     const uint32_t           par = (uint32_t)(seq & 1ull);
     if ( threadIdx.x == 0 ) c->local[CW_ERROR] = c->error ? 1 : 0;
@@ -1184,15 +1183,22 @@ peer_post_kernel(Dev d)
         m[CW_WORDS] = seq;
     }
 }
+__global__ void
+peer_post_kernel(Dev d)
+{
+    if ( d.ctrl->done || blockIdx.x != 0 ) return;
+    peer_post(d);
+}
 
 // wait for every rank's mailbox entry of this window (spin: the peers are other GPUs running their own kernels; with
 // all ranks stepped by one process on one GPU the entries are already there and a missing one is an error), then fold
 // the control words and open the next window exactly like advance_kernel
 __global__ void
-peer_advance_kernel(Dev d, int spin)
+peer_advance_kernel(Dev d, int spin, int post_first)
 {
     Ctrl* c = d.ctrl;
     if ( c->done || blockIdx.x != 0 ) return;
+    if ( post_first ) peer_post(d); // ranks on their own GPUs: the mailbox write and the wait in one launch
     const unsigned long long seq = c->windows + 1;
     const uint32_t           par = (uint32_t)(seq & 1ull);
     const uint32_t           r   = threadIdx.x;
@@ -1566,7 +1572,7 @@ struct sstb200_engine
         CUDA_OK(cudaGetLastError());
         return 0;
     }
-    uint32_t launches_per_window() const { return (pf_on ? 4u : 2u) + (n_ranks > 1 ? 1u : 0u); }
+    uint32_t launches_per_window() const { return (pf_on ? 4u : 2u) + (n_ranks > 1 && !(d.peer_on && peer_spin) ? 1u : 0u); }
     // `n` windows (dispatch + advance each).  The kernels take the same arguments every window -- the window state
     // lives in device memory -- so a chunk is captured once into a CUDA graph and replayed: small models are bound by
     // launch overhead, not by the kernels.
@@ -1615,7 +1621,7 @@ struct sstb200_engine
     int launch_advance()
     {
         if ( d.peer_on )
-            peer_advance_kernel<<<1, 32, 0, stream>>>(d, peer_spin ? 1 : 0);
+            peer_advance_kernel<<<1, 32, 0, stream>>>(d, peer_spin ? 1 : 0, peer_spin ? 1 : 0);
         else
             advance_kernel<<<1, 32, 0, stream>>>(d);
         launches++;
@@ -1626,6 +1632,7 @@ struct sstb200_engine
     // headers (the driver then exchanges the outboxes); peer mode -- the mailbox write to every rank
     int launch_publish()
     {
+        if ( d.peer_on && peer_spin ) return 0; // posted by peer_advance_kernel itself
         if ( d.peer_on )
             peer_post_kernel<<<1, 32, 0, stream>>>(d);
         else
@@ -2269,7 +2276,13 @@ sstb200_engine_peer_export(sstb200_engine* e, void* handle64, uint32_t* nbins, v
 {
     if ( !e ) return -1;
     CUDA_OK(cudaSetDevice(e->device));
-    CUDA_OK(cudaStreamSynchronize(e->stream)); // the region has been cleared before anybody may write into it
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        CUDA_OK(cudaStreamSynchronize(e->stream)); // the region has been cleared before anybody may write into it
+        if ( getenv("SSTB200_CREATE_TIMING") )
+            fprintf(stderr, "[sstb200 peer] rank %u export: waited %.3f ms for the engine's stream\n", e->d.rank,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
     if ( handle64 ) {
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
         cudaIpcMemHandle_t h;
@@ -2287,16 +2300,21 @@ sstb200_engine_peer_connect(sstb200_engine* e, const void* handles, const uint32
     if ( int rc = peer_check(e, "engine_peer_connect") ) return rc;
     if ( !handles || !nbins ) return -1;
     CUDA_OK(cudaSetDevice(e->device));
-    Dev& d = e->d;
+    Dev&       d      = e->d;
+    const bool timing = getenv("SSTB200_CREATE_TIMING") != nullptr;
     for ( uint32_t r = 0; r < e->n_ranks; ++r ) {
         uint8_t* base = e->region;
         if ( r != d.rank ) {
+            const auto         t0 = std::chrono::steady_clock::now();
             cudaIpcMemHandle_t h;
             memcpy(&h, (const uint8_t*)handles + (size_t)r * 64, 64);
             void* p = nullptr;
             CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
             e->ipc_opened.push_back(p);
             base = (uint8_t*)p;
+            if ( timing )
+                fprintf(stderr, "[sstb200 peer] rank %u opens rank %u's region: %.3f ms\n", d.rank, r,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         }
         peer_layout(d, nbins[r], base, r, d);
     }
