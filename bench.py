@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--no-steady", action="store_true", help="skip the steady-state re-timing (mesh, 1 GPU)")
     ap.add_argument("--cpu-size", type=int, default=256, help="reference sample: S x S mesh")
     ap.add_argument("--cpu-ns", type=int, default=100, help="reference sample: simulated ns")
+    ap.add_argument("--e2e-ns", type=int, default=100, help="end-to-end leg: simulated ns (= lookahead windows of 1 ns); "
+                    "SURVEY.md 8d config 4's short run, the reference arm's own stop time")
     return ap.parse_args()
 
 
@@ -264,7 +266,8 @@ def ours(a):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     W, K = max(a.warmup, 3), a.steps
-    m, opts, name = build_model(a, W + K + 1)
+    E = max(a.e2e_ns, 2)  # windows of the end-to-end leg
+    m, opts, name = build_model(a, max(W + K, E) + 1)
     model_bytes = sum(arr.nbytes for arr in (m.comp_type, m.comp_param, m.port_off, m.peer_port, m.latency,
                                              m.clock_period))
     stream = torch.cuda.Stream(dev)
@@ -298,7 +301,7 @@ def ours(a):
         ids = (pm.orig_id if getattr(pm, "orig_id", None) is not None else np.arange(m.ncomp))[c_begin:c_begin + res.shape[0]]
         return records_digest(ids, res)
 
-    # ---- e2e: host arrays -> engine -> W+K windows -> results on host, wall clock, everything inside
+    # ---- e2e: host arrays -> engine -> E windows (stop-at E ns) -> results on host, wall clock, everything inside
     e2e = None
     if dist:
         # NCCL sets up its point-to-point channels lazily on the first all-to-all: do that before anything is timed
@@ -336,9 +339,9 @@ def ours(a):
             e.sync()
             t2 = time.perf_counter()
             if world > 1:
-                DistributedRunner(e).run(max_windows=W + K, check_every=W + K)
+                DistributedRunner(e).run(max_windows=E, check_every=E)
             else:
-                e.run(max_windows=W + K, check_every=W + K)
+                e.run(max_windows=E, check_every=E)
             e.sync()
             t3 = time.perf_counter()
             res = e.results(result_words(m), compact=True, out=res_buf)
@@ -354,10 +357,11 @@ def ours(a):
             dist.all_reduce(ev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": float(ev[0].item()) / float(tt[0].item()), "unit": "events/s",
-               "h2d_bytes_per_step": model_bytes // (W + K), "d2h_bytes_per_step": res.nbytes // (W + K),
-               "seconds": float(tt[0].item()), "windows": W + K,
+               "h2d_bytes_per_step": model_bytes // E, "d2h_bytes_per_step": res.nbytes // E,
+               "seconds": float(tt[0].item()), "windows": E,
                "breakdown": {k: round(v, 4) for k, v in bd.items()},  # rank 0's own phases (host wall clock)
-               "note": "engine create from host arrays + setup + windows + results to host, per rank slice"}
+               "note": f"one run to stop-at {E} ns: engine create from pinned host arrays (H2D) + setup + {E} windows + "
+                       "result records to host (D2H), per rank slice; bytes per step = totals / windows"}
         e.close()
         del res
 
@@ -513,15 +517,20 @@ def ours(a):
         if a.workload == "mesh":
             x, y = a.x or 4096, a.y or 4096
             gp = ROOT / "tests" / "golden" / "bench_digests.json"
-            gold = json.loads(gp.read_text())["digests"].get(f"mesh_{x}x{y}_w{W + K}_stats{int(bool(a.stats))}") if gp.exists() else None
+            gall = json.loads(gp.read_text())["digests"] if gp.exists() else {}
+            gold = gall.get(f"mesh_{x}x{y}_w{W + K}_stats{int(bool(a.stats))}")
+            gold_e2e = gall.get(f"mesh_{x}x{y}_w{E}_stats{int(bool(a.stats))}")
             n_all = x * y
             parity["conservation"] = {"events_total": total_all, "expected": (W + K - 1) * 4 * n_all,
                                       "ok": total_all == (W + K - 1) * 4 * n_all}
             if gold:
                 parity["golden"] = gold["digest"]
                 parity["golden_source"] = "tests/golden/bench_digests.json (oracle/mesh_golden.cc on CPU, pinned to the oracle and the reference)"
-                parity["match"] = (parity["digest"] == gold["digest"] and parity.get("e2e_digest", gold["digest"]) == gold["digest"]
-                                   and total_all == gold["events"])
+                parity["match"] = parity["digest"] == gold["digest"] and total_all == gold["events"]
+            if "e2e_digest" in parity and gold_e2e:
+                parity["e2e_golden"] = gold_e2e["digest"]
+                parity["e2e_match"] = parity["e2e_digest"] == gold_e2e["digest"]
+                parity["match"] = bool(parity["match"]) and parity["e2e_match"] if gold else parity["e2e_match"]
         line["parity"] = parity
         if not a.no_cpu_baseline and world == 1:
             try:

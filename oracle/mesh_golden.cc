@@ -10,9 +10,9 @@
 // torus wrap, tests/test_MessageMesh.py:26-121).  Mesh events carry no payload and all events of a step share one
 // timestamp, so per-component results do not depend on the order inside a step.
 //
-// Memory: the route decisions of the first generation's pairs are kept as 2 bits each (78 bytes per component), not
-// the 2.5 KB generator; a run may therefore use at most 310 pairs per component (a few hundred windows at 4 events
-// per window on average) -- the function fails rather than wrap.
+// Memory: the route decisions of a component's first PAIRS pairs of draws are kept as 2 bits each, not the 2.5 KB
+// generator.  PAIRS is sized from the number of windows (4 events per component and window on average, plus 10 standard
+// deviations and a margin); a component that needs more makes the function fail rather than wrap.
 //
 // Pinned by tests/test_oracle.py: equal to pdes_oracle.cc (itself pinned to the reference's golden files) on meshes
 // up to 256 x 256, and to tests/refFiles/test_MessageMesh.out's run through the 6 x 6 fixture for its first windows.
@@ -23,8 +23,13 @@
 #include <vector>
 
 namespace {
-constexpr uint32_t PAIRS = 310; // (624 - 4 setup draws) / 2
-constexpr uint32_t WORDS = (PAIRS + 15) / 16;
+uint32_t
+pairs_for(uint32_t windows)
+{
+    const double mean = 4.0 * windows;
+    uint32_t     p    = (uint32_t)(mean + 10.0 * __builtin_sqrt(mean) + 64.0);
+    return p < 310 ? 310 : p;
+}
 
 template <class F>
 void
@@ -51,6 +56,7 @@ uint64_t
 mesh_golden_counts(uint32_t X, uint32_t Y, uint32_t windows, unsigned threads, int32_t* counts_out)
 {
     const uint64_t n = (uint64_t)X * Y;
+    const uint32_t PAIRS = pairs_for(windows), WORDS = (PAIRS + 15) / 16;
     std::vector<uint32_t> route(n * WORDS);
     parallel_for(n, threads, [&](uint64_t lo, uint64_t hi) {
         for ( uint64_t c = lo; c < hi; ++c ) {

@@ -19,7 +19,7 @@ out = {"_doc": "key mesh_<X>x<Y>_w<windows>_stats<0|1>: records_digest(ids, resu
                "(tests/models/mesh.py semantics, mod 1) after <windows> lookahead windows of 1 ns; events = events delivered",
        "digests": {}}
 for size in (256, 1024, 2048, 4096):
-    for windows in (8, 13, 25, 45):
+    for windows in (8, 13, 25, 45, 100):
         counts, events = O.mesh_golden_counts(size, size, windows)
         ids = np.arange(size * size, dtype=np.uint64)
         for stats in (0, 1):

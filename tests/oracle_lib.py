@@ -44,7 +44,7 @@ def mesh_golden_counts(x, y, windows, threads=0):
     counts = np.zeros(x * y, dtype=np.int32)
     ev = _mesh_lib.mesh_golden_counts(x, y, windows, threads or (os.cpu_count() or 1), _p(counts))
     if ev == 0xFFFFFFFFFFFFFFFF:
-        raise RuntimeError("mesh_golden: a component used more than one MT19937 generation; run fewer windows")
+        raise RuntimeError("mesh_golden: a component drew more pairs than the route table holds (pairs_for in mesh_golden.cc)")
     return counts, int(ev)
 
 
