@@ -251,7 +251,8 @@ def ours(a):
     import numpy as np
     import torch
 
-    from sst_core_b200.engine import DistributedRunner, Engine, connect_peers, partition_model
+    from sst_core_b200.engine import (DistributedRunner, Engine, connect_peers, init_peer_arena, partition_model,
+                                      peer_region_bytes)
     from sst_core_b200.run import result_words
 
     n = a.gpus
@@ -312,6 +313,12 @@ def ours(a):
         dist.all_reduce(wu[:1], op=dist.ReduceOp.MIN)
         dist.all_gather_into_tensor(torch.empty(world * 8, dtype=torch.int64, device=dev), wu[:8])
         torch.cuda.synchronize(dev)
+        # the peer arena: every rank maps the others' exchange memory ONCE per process (communicator-style set-up, next
+        # to NCCL's own); the engines below place their calendars inside it and connect without any IPC mapping
+        if not os.environ.get("SSTB200_NO_ARENA"):
+            n_max = int(np.diff(pm._rank_begins.astype(np.int64)).max())
+            init_peer_arena(local_rank, peer_region_bytes(n_max, opts["calendar_slots"], opts["bin_capacity"],
+                                                          a.workload == "phold"))
     if not a.no_e2e:
         # process warm-up (CUDA context, lazy module load of the kernels, allocator): one tiny job of the same kind
         import copy

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define SSTB200_ABI_VERSION 1
+#define SSTB200_ABI_VERSION 2
 #define SSTB200_NPARAM 8    /* int64 construction params per component                        */
 #define SSTB200_NRESULT 32  /* u64 words in a component's result record                       */
 #define SSTB200_NO_PEER 0xFFFFFFFFu
@@ -81,6 +81,13 @@ typedef struct sstb200_options {
     uint32_t handler_counts;  /* non-zero: count deliveries per receiving port and clock-handler calls per component
                                  (sst.profile.handler.event.count / .clock.count, profile/eventHandlerProfileTool.cc,
                                  clockHandlerProfileTool.cc); read them with sstb200_engine_handler_counts          */
+    uint32_t model_type_mask; /* multi-rank: bit t set = some component of the WHOLE model has type code t (the partitioner
+                                 knows; the reference gets the same facts from its graph before Simulation exists).
+                                 0 = unknown: engine_create scans all ncomp components itself                      */
+    uint32_t model_uniform_ports; /* with model_type_mask: 1 = every component of the model has the same number of
+                                 ports, 2 = not                                                                    */
+    uint64_t output_capacity; /* console-output records to keep (Output::output calls of device components, one record
+                                 each; 0 = default 65536 when an element of the model prints, else none)           */
 } sstb200_options;
 
 int  sstb200_engine_create(const sstb200_model* model, const sstb200_options* opt, sstb200_engine** out);
@@ -116,11 +123,23 @@ int sstb200_engine_advance(sstb200_engine* e);
  *                 NULL), *nbins = its number of component blocks, *region_dev = the region's device pointer
  *   peer_connect: before engine_setup, on every rank, after ALL ranks have been created: handles = n_ranks x 64 bytes
  *                 and nbins[n_ranks] gathered from peer_export in rank order (the entry of this rank is ignored)
+ *   peer arena  : cudaIpcOpenMemHandle costs 10-25 ms per peer, per allocation.  A process that runs many simulations
+ *                 (or wants its first one to start fast) creates ONE arena per device up front -- like a communicator --
+ *                 exchanges its handle once (peer_arena_create on every rank, all-gather, peer_arena_open), and engines
+ *                 created afterwards place their peer-visible region inside it when it fits; peer_connect_arena then
+ *                 connects the ranks without mapping anything.  *in_arena of peer_export says whether the engine did.
  *   peer_connect_local: the same for ranks living in ONE process on one GPU (regions = their device pointers);
  *                 the driver steps the ranks itself: dispatch on all, then advance on all */
 int sstb200_engine_peer_export(sstb200_engine* e, void* handle64, uint32_t* nbins, void** region_dev);
 int sstb200_engine_peer_connect(sstb200_engine* e, const void* handles, const uint32_t* nbins);
 int sstb200_engine_peer_connect_local(sstb200_engine* e, void* const* regions, const uint32_t* nbins);
+/* bytes of the peer-visible region of an engine with n_local components (0 options = the engine's defaults) */
+uint64_t sstb200_peer_region_bytes(uint32_t n_local, uint32_t calendar_slots, uint32_t bin_capacity, int has_payload);
+int sstb200_peer_arena_create(int device, uint64_t bytes, void* handle64_out);
+int sstb200_peer_arena_open(int device, uint32_t rank, uint32_t n_ranks, const void* handles);
+int sstb200_peer_arena_destroy(int device);
+int sstb200_engine_in_arena(sstb200_engine* e, int* in_arena);
+int sstb200_engine_peer_connect_arena(sstb200_engine* e, const uint32_t* nbins);
 /* the cudaStream_t the engine launches on (options.stream, or the one it created) */
 int sstb200_engine_stream(sstb200_engine* e, void** stream_out);
 

@@ -1472,6 +1472,18 @@ constexpr int kNumElements = (int)(sizeof(kElements) / sizeof(kElements[0]));
 
 using namespace sstb200;
 
+// Peer arena (include/sstb200.h "peer arena"): one allocation per device of this process that other ranks map ONCE;
+// engines place their peer-visible region at its start while they live.
+struct PeerArena
+{
+    uint8_t* base     = nullptr;
+    size_t   bytes    = 0;
+    bool     in_use   = false;
+    uint32_t rank = 0, n_ranks = 0;          // set by peer_arena_open
+    uint8_t* mapped[MAX_RANKS] = {};         // the other ranks' arenas as mapped here (own entry = base)
+};
+static PeerArena g_arena[64];
+
 struct sstb200_engine
 {
     Dev                d {};
@@ -1645,6 +1657,7 @@ struct sstb200_engine
     // calendar records, payloads, bin fill counts, mailbox -- so that one IPC handle per rank maps it all
     uint8_t*           region       = nullptr;
     size_t             region_bytes = 0;
+    bool               region_in_arena = false;
     bool               peer_spin    = false; // peers are other processes / GPUs: peer_advance_kernel waits for them
     std::vector<void*> ipc_opened;
 };
@@ -1803,8 +1816,13 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         bool     uni_ok = true, uni_all = true, clocks = false;
     } part[16];
     const uint32_t uni0 = d.n_local ? m->port_off[c0 + 1] - m->port_off[c0] : 0;
-    scan(m->ncomp, [&](size_t lo, size_t hi, unsigned t) {
-        Part q;
+    // (a multi-rank driver that knows the model-wide facts passes them -- options.model_type_mask -- and every rank
+    // scans its own slice only, like the reference's per-rank wire-up touches only local links, simulation.cc:668-859)
+    const bool   hinted = n_ranks > 1 && o->model_type_mask != 0;
+    const size_t sc_lo  = hinted ? c0 : 0, sc_hi = hinted ? c1 : m->ncomp;
+    scan(sc_hi - sc_lo, [&](size_t lo_, size_t hi_, unsigned t) {
+        Part         q;
+        const size_t lo = sc_lo + lo_, hi = sc_lo + hi_;
         for ( size_t c = lo; c < hi; ++c ) {
             const uint32_t ty = m->comp_type[c];
             if ( m->port_off[c + 1] - m->port_off[c] != uni0 ) q.uni_all = false;
@@ -1839,6 +1857,10 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         max_blk = std::max(max_blk, q.max_blk);
         uni_ok  = uni_ok && q.uni_ok;
         uni_all = uni_all && q.uni_all;
+    }
+    if ( hinted ) {
+        seen_all = o->model_type_mask | seen_local;
+        uni_all  = uni_ok && o->model_uniform_ports == 1;
     }
     if ( bad != 0xFFFFFFFFu ) {
         set_error("engine_create: component " + std::to_string(bad) + " has unknown type code " +
@@ -2014,7 +2036,15 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         const size_t cnt_b = (((size_t)d.W * d.nbins * 4) + 255) & ~(size_t)255;
         const size_t mail_b = (size_t)2 * MAX_RANKS * MAILW * 8;
         e->region_bytes     = ev_b + pay_b + cnt_b + mail_b;
-        rc |= e->alloc(&e->region, e->region_bytes, false);
+        PeerArena& ar       = g_arena[o->device & 63];
+        if ( n_ranks > 1 && ar.base && !ar.in_use && ar.n_ranks == n_ranks && ar.rank == o->rank &&
+             e->region_bytes <= ar.bytes ) {
+            e->region          = ar.base;
+            e->region_in_arena = true;
+            ar.in_use          = true;
+        }
+        else
+            rc |= e->alloc(&e->region, e->region_bytes, false);
         if ( !rc ) {
             d.ev         = reinterpret_cast<ulonglong2*>(e->region);
             d.ev_payload = has_payload ? reinterpret_cast<uint64_t*>(e->region + ev_b) : nullptr;
@@ -2137,6 +2167,7 @@ sstb200_engine_destroy(sstb200_engine* e)
     if ( e->stream ) cudaStreamSynchronize(e->stream);
     for ( void* p : e->ipc_opened )
         cudaIpcCloseMemHandle(p);
+    if ( e->region_in_arena ) g_arena[e->device & 63].in_use = false;
     for ( void* p : e->allocs )
         cudaFree(p);
     if ( e->graph_exec ) cudaGraphExecDestroy(e->graph_exec);
@@ -2318,6 +2349,109 @@ sstb200_engine_peer_connect(sstb200_engine* e, const void* handles, const uint32
         }
         peer_layout(d, nbins[r], base, r, d);
     }
+    d.peer_on    = 1;
+    e->peer_spin = true;
+    return 0;
+}
+
+uint64_t
+sstb200_peer_region_bytes(uint32_t n_local, uint32_t calendar_slots, uint32_t bin_capacity, int has_payload)
+{
+    const size_t W = calendar_slots >= 2 ? calendar_slots : 2, nbins = std::max<size_t>(1, ((size_t)n_local + BLOCK - 1) / BLOCK);
+    const size_t cap = std::max<size_t>(bin_capacity ? bin_capacity : 8 * BLOCK, BLOCK);
+    const size_t nev = W * nbins * cap;
+    return nev * sizeof(ulonglong2) + (has_payload ? nev * 8 : 0) + (((W * nbins * 4) + 255) & ~(size_t)255) +
+           (size_t)2 * MAX_RANKS * MAILW * 8;
+}
+
+int
+sstb200_peer_arena_create(int device, uint64_t bytes, void* handle64_out)
+{
+    if ( device < 0 || device >= 64 || !bytes ) return -1;
+    CUDA_OK(cudaSetDevice(device));
+    PeerArena& ar = g_arena[device];
+    if ( ar.base ) {
+        set_error("peer_arena_create: this device already has an arena (destroy it first)");
+        return -1;
+    }
+    void* p = nullptr;
+    CUDA_OK(cudaMalloc(&p, bytes));
+    ar       = PeerArena {};
+    ar.base  = (uint8_t*)p;
+    ar.bytes = bytes;
+    if ( handle64_out ) {
+        cudaIpcMemHandle_t h;
+        CUDA_OK(cudaIpcGetMemHandle(&h, p));
+        memcpy(handle64_out, &h, 64);
+    }
+    return 0;
+}
+
+int
+sstb200_peer_arena_open(int device, uint32_t rank, uint32_t n_ranks, const void* handles)
+{
+    if ( device < 0 || device >= 64 || !handles || n_ranks < 2 || n_ranks > MAX_RANKS || rank >= n_ranks ) return -1;
+    CUDA_OK(cudaSetDevice(device));
+    PeerArena& ar = g_arena[device];
+    if ( !ar.base || ar.n_ranks ) {
+        set_error("peer_arena_open: create the arena first, open it once");
+        return -1;
+    }
+    for ( uint32_t r = 0; r < n_ranks; ++r ) {
+        if ( r == rank ) {
+            ar.mapped[r] = ar.base;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const uint8_t*)handles + (size_t)r * 64, 64);
+        void* p = nullptr;
+        CUDA_OK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ar.mapped[r] = (uint8_t*)p;
+    }
+    ar.rank    = rank;
+    ar.n_ranks = n_ranks;
+    return 0;
+}
+
+int
+sstb200_peer_arena_destroy(int device)
+{
+    if ( device < 0 || device >= 64 ) return -1;
+    PeerArena& ar = g_arena[device];
+    if ( !ar.base ) return 0;
+    if ( ar.in_use ) {
+        set_error("peer_arena_destroy: an engine still lives in the arena");
+        return -1;
+    }
+    CUDA_OK(cudaSetDevice(device));
+    for ( uint32_t r = 0; r < ar.n_ranks; ++r )
+        if ( ar.mapped[r] && ar.mapped[r] != ar.base ) cudaIpcCloseMemHandle(ar.mapped[r]);
+    cudaFree(ar.base);
+    ar = PeerArena {};
+    return 0;
+}
+
+int
+sstb200_engine_in_arena(sstb200_engine* e, int* in_arena)
+{
+    if ( !e || !in_arena ) return -1;
+    *in_arena = e->region_in_arena ? 1 : 0;
+    return 0;
+}
+
+// every rank's engine lives at the start of its arena (sstb200_engine_in_arena said so on ALL ranks): nothing to map
+int
+sstb200_engine_peer_connect_arena(sstb200_engine* e, const uint32_t* nbins)
+{
+    if ( int rc = peer_check(e, "engine_peer_connect_arena") ) return rc;
+    PeerArena& ar = g_arena[e->device & 63];
+    if ( !nbins || !e->region_in_arena || ar.n_ranks != e->n_ranks ) {
+        set_error("engine_peer_connect_arena: this engine's region is not in an opened arena");
+        return -1;
+    }
+    Dev& d = e->d;
+    for ( uint32_t r = 0; r < e->n_ranks; ++r )
+        peer_layout(d, nbins[r], ar.mapped[r], r, d);
     d.peer_on    = 1;
     e->peer_spin = true;
     return 0;

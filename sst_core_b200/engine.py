@@ -38,7 +38,8 @@ class _Options(C.Structure):
                 ("comp_end", C.c_uint32), ("rank_comp_begin", C.c_void_p), ("calendar_slots", C.c_uint32),
                 ("bin_capacity", C.c_uint32), ("smem_events", C.c_uint32), ("outbox_capacity", C.c_uint32),
                 ("window", C.c_uint64), ("trace_capacity", C.c_uint64), ("stream", C.c_void_p),
-                ("parallel_max_events", C.c_uint32), ("handler_counts", C.c_uint32)]
+                ("parallel_max_events", C.c_uint32), ("handler_counts", C.c_uint32),
+                ("model_type_mask", C.c_uint32), ("model_uniform_ports", C.c_uint32), ("output_capacity", C.c_uint64)]
 
 
 class _Status(C.Structure):
@@ -60,6 +61,8 @@ EXPORTS = [
     "sstb200_rng_ticks", "sstb200_rng_distribution",
     "sstb200_engine_peer_export", "sstb200_engine_peer_connect", "sstb200_engine_peer_connect_local",
     "sstb200_engine_stream",
+    "sstb200_peer_region_bytes", "sstb200_peer_arena_create", "sstb200_peer_arena_open", "sstb200_peer_arena_destroy",
+    "sstb200_engine_in_arena", "sstb200_engine_peer_connect_arena",
 ]
 
 _lib = None
@@ -93,6 +96,13 @@ def lib():
     L.sstb200_engine_peer_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sstb200_engine_peer_connect_local.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sstb200_engine_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.sstb200_peer_region_bytes.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+    L.sstb200_peer_region_bytes.restype = C.c_uint64
+    L.sstb200_peer_arena_create.argtypes = [C.c_int, C.c_uint64, C.c_void_p]
+    L.sstb200_peer_arena_open.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+    L.sstb200_peer_arena_destroy.argtypes = [C.c_int]
+    L.sstb200_engine_in_arena.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    L.sstb200_engine_peer_connect_arena.argtypes = [C.c_void_p, C.c_void_p]
     L.sstb200_engine_status.argtypes = [C.c_void_p, C.POINTER(_Status)]
     L.sstb200_engine_results.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.sstb200_engine_trace.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -160,7 +170,7 @@ def partition_model(m: WiredModel, n_ranks: int) -> WiredModel:
     if m.ncomp < 2 or bool(np.all(rank[:-1] <= rank[1:])):  # already contiguous per rank (the usual case): no renumbering
         m.rank, m.n_ranks = rank, n_ranks
         m.orig_id = np.arange(m.ncomp, dtype=np.uint32)
-        return m
+        return _model_facts(m)
     order = np.argsort(rank, kind="stable")  # new id -> old id
     nports = np.diff(m.port_off.astype(np.int64))
     new_nports = nports[order]
@@ -188,7 +198,23 @@ def partition_model(m: WiredModel, n_ranks: int) -> WiredModel:
         port_info=[m.port_info[int(i)] for i in old_ids] if m.port_info else None,
         type_names=[m.type_names[i] for i in order] if m.type_names else None, stat_rate=m.stat_rate)
     out.validate()
-    return out
+    return _model_facts(out)
+
+
+def _model_facts(m: WiredModel) -> WiredModel:
+    """What the partitioner knows about the WHOLE model and every rank's engine needs: the lookahead (minimum link
+    latency, ConfigGraph::getMinimumPartitionLatency configGraph.cc:711-730 -- the reference computes it on the graph,
+    before any Simulation object exists), the element types present and whether all components have the same number
+    of ports.  With these in the options a rank's engine_create scans its own slice of the model only."""
+    m._min_latency = m.min_latency()
+    m._rank_begins = np.searchsorted(m.rank, np.arange(m.n_ranks + 1)).astype(np.uint32)
+    mask = 0
+    for t in np.unique(m.comp_type):
+        mask |= 1 << int(t)
+    m._type_mask = mask
+    np_ = np.diff(m.port_off.astype(np.int64))
+    m._uniform_ports = 1 if (np_.size == 0 or bool(np.all(np_ == np_[0]))) else 2
+    return m
 
 
 @dataclass
@@ -251,7 +277,8 @@ class Engine:
 
     def __init__(self, model: WiredModel, device: int = 0, rank: int = 0, n_ranks: int = 1, calendar_slots: int = 2,
                  bin_capacity: int = 0, smem_events: int = 0, outbox_capacity: int = 0, window: int = 0,
-                 trace_capacity: int = 0, stream: int = 0, parallel_max_events: int = 0, handler_counts: bool = False):
+                 trace_capacity: int = 0, stream: int = 0, parallel_max_events: int = 0, handler_counts: bool = False,
+                 output_capacity: int = 0):
         L = lib()
         check_registry()
         self.model = model
@@ -269,13 +296,15 @@ class Engine:
             self._begins = begins
             c0, c1 = int(begins[rank]), int(begins[rank + 1])
             if not window:
-                window = _global_window(model, c0, c1, rank, n_ranks, device)
+                window = getattr(model, "_min_latency", 0) or _global_window(model, c0, c1, rank, n_ranks, device)
         else:
             self._begins = np.array([0, model.ncomp], dtype=np.uint32)
             c0, c1 = 0, model.ncomp
         self.comp_begin, self.comp_end = c0, c1
         opt = _Options(device, rank, n_ranks, c0, c1, _p(self._begins), calendar_slots, bin_capacity, smem_events,
-                       outbox_capacity, window, trace_capacity, stream, parallel_max_events, int(bool(handler_counts)))
+                       outbox_capacity, window, trace_capacity, stream, parallel_max_events, int(bool(handler_counts)),
+                       int(getattr(model, "_type_mask", 0)) if n_ranks > 1 else 0,
+                       int(getattr(model, "_uniform_ports", 0)) if n_ranks > 1 else 0, output_capacity)
         h = C.c_void_p()
         _check(L.sstb200_engine_create(C.byref(cm), C.byref(opt), C.byref(h)), "engine_create")
         self._h = h
@@ -342,6 +371,17 @@ class Engine:
         hb = np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
         nb = np.ascontiguousarray(nbins, dtype=np.uint32)
         _check(self._L.sstb200_engine_peer_connect(self._h, _p(hb), _p(nb)), "engine_peer_connect")
+        self.peer = "ipc"
+
+    def in_arena(self) -> bool:
+        v = C.c_int(0)
+        _check(self._L.sstb200_engine_in_arena(self._h, C.byref(v)), "engine_in_arena")
+        return bool(v.value)
+
+    def peer_connect_arena(self, nbins):
+        """Every rank's peer-visible region lies in its (already mapped) peer arena: connect without mapping anything."""
+        nb = np.ascontiguousarray(nbins, dtype=np.uint32)
+        _check(self._L.sstb200_engine_peer_connect_arena(self._h, _p(nb)), "engine_peer_connect_arena")
         self.peer = "ipc"
 
     def peer_connect_local(self, regions, nbins):
@@ -512,12 +552,46 @@ def connect_peers(engine) -> bool:
         return False
     handle, nbins, _ = engine.peer_export()
     dev = torch.device("cuda", engine.device)
-    mine = np.concatenate([np.frombuffer(handle, dtype=np.uint8), np.array([nbins], dtype=np.uint32).view(np.uint8)])
-    allt = torch.empty(n * 68, dtype=torch.uint8, device=dev)
+    mine = np.concatenate([np.frombuffer(handle, dtype=np.uint8),
+                           np.array([nbins, int(engine.in_arena())], dtype=np.uint32).view(np.uint8)])
+    allt = torch.empty(n * 72, dtype=torch.uint8, device=dev)
     dist.all_gather_into_tensor(allt, torch.from_numpy(mine.copy()).to(dev))  # also: every rank's region is cleared
-    a = allt.cpu().numpy().reshape(n, 68)
-    engine.peer_connect([bytes(a[r, :64]) for r in range(n)], np.ascontiguousarray(a[:, 64:]).view(np.uint32).ravel())
+    a = allt.cpu().numpy().reshape(n, 72)
+    meta = np.ascontiguousarray(a[:, 64:]).view(np.uint32).reshape(n, 2)
+    if bool(meta[:, 1].all()):  # every rank's region lies in its peer arena, mapped when the arena was opened
+        engine.peer_connect_arena(meta[:, 0].copy())
+    else:
+        engine.peer_connect([bytes(a[r, :64]) for r in range(n)], meta[:, 0].copy())
     return True
+
+
+def init_peer_arena(device: int, nbytes: int) -> bool:
+    """Collective, once per process (like creating a communicator): allocate this rank's peer arena of `nbytes`, exchange
+    the IPC handles and map every other rank's arena.  Engines created afterwards whose peer-visible region fits are
+    placed inside it, and connect_peers() then maps nothing (cudaIpcOpenMemHandle costs 10-25 ms per peer and
+    allocation).  Returns False outside a torch.distributed NCCL job."""
+    try:
+        import torch
+        import torch.distributed as dist
+    except Exception:
+        return False
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_backend() != "nccl" or dist.get_world_size() < 2:
+        return False
+    L = lib()
+    n, rank = dist.get_world_size(), dist.get_rank()
+    h = (C.c_uint8 * 64)()
+    _check(L.sstb200_peer_arena_create(device, int(nbytes), h), "peer_arena_create")
+    dev = torch.device("cuda", device)
+    allt = torch.empty(n * 64, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allt, torch.from_numpy(np.frombuffer(bytes(h), dtype=np.uint8).copy()).to(dev))
+    hb = allt.cpu().numpy().copy()
+    _check(L.sstb200_peer_arena_open(device, rank, n, _p(hb)), "peer_arena_open")
+    dist.barrier()
+    return True
+
+
+def peer_region_bytes(n_local: int, calendar_slots: int = 0, bin_capacity: int = 0, has_payload: bool = False) -> int:
+    return int(lib().sstb200_peer_region_bytes(int(n_local), int(calendar_slots), int(bin_capacity), int(has_payload)))
 
 
 class DistributedRunner:
