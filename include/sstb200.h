@@ -30,6 +30,8 @@ extern "C" {
  *   2 pdes.phold:      [0] recv, [1] delivery hash, [2..6] "delay"
  *   3 pdes.clocknode:  [0] ticks, [1] last cycle, [2] recv, [3] delivery hash, [4+5i..] "N","S","E","W" (i32)
  *   4 coreTestElement.coreTestRNGComponent: [0] rng_count, [1..5] last tick (double bits,u32,u64,i32,i64), [6] hash
+ *   6 coreTestElement.coreTestClockerComponent: [0] id, [1] instructions issued, [2] done, [3] ordered variable,
+ *     [4..12] the nine clocks' counters
  */
 
 typedef struct sstb200_engine sstb200_engine;
@@ -62,6 +64,15 @@ typedef struct sstb200_model {
     const uint64_t* clock_period; /* [ncomp]   cycles, 0 = no clock (registerClock, clock.cc:400-420)         */
     uint64_t        stop_at;      /* --stop-at in cycles, 0 = none (StopAction priority 30)                   */
     int             stats_enabled;
+    const uint8_t*  port_self;    /* [nport] or NULL: 1 = a configureSelfLink port (baseComponent.cc:374-378,
+                                               link.h:512-521): peer_port[p] == p, latency may be 0, its events are
+                                               delivered after those of the component's other ports at equal time (the
+                                               link keeps order tag 0xFFFFFFFF, link.h:309-319) -- self-link ports are
+                                               the LAST ports of their component -- and it never limits the lookahead */
+    const uint32_t* xparam_off;   /* [ncomp+1] or NULL: CSR over `xparam`, further int64 construction parameters of
+                                               components whose Params do not fit the 8 fixed ones (the host half of
+                                               the element defines their meaning)                               */
+    const int64_t*  xparam;
 } sstb200_model;
 
 typedef struct sstb200_options {
@@ -133,6 +144,11 @@ int sstb200_engine_advance(sstb200_engine* e);
 int sstb200_engine_peer_export(sstb200_engine* e, void* handle64, uint32_t* nbins, void** region_dev);
 int sstb200_engine_peer_connect(sstb200_engine* e, const void* handles, const uint32_t* nbins);
 int sstb200_engine_peer_connect_local(sstb200_engine* e, void* const* regions, const uint32_t* nbins);
+/* console output of device components (Output::output, output.cc:156-215): records of 8 u64 words
+ * {time, component | code << 32, v0, v1, v2, v3, v4, 0}; per component in the order it printed them.  *n_inout: capacity of
+ * `records` in records on entry, number written on return (records == NULL: only the count).  The host half of the
+ * element owns the format strings (sst_core_b200/elements.py). */
+int sstb200_engine_output(sstb200_engine* e, uint64_t* n_inout, uint64_t* records);
 /* bytes of the peer-visible region of an engine with n_local components (0 options = the engine's defaults) */
 uint64_t sstb200_peer_region_bytes(uint32_t n_local, uint32_t calendar_slots, uint32_t bin_capacity, int has_payload);
 int sstb200_peer_arena_create(int device, uint64_t bytes, void* handle64_out);

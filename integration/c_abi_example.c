@@ -17,21 +17,24 @@ static int
 print_layout(void)
 {
     printf("model %zu ncomp %zu comp_type %zu comp_param %zu port_off %zu peer_port %zu latency %zu clock_period %zu "
-           "stop_at %zu stats_enabled %zu\n",
+           "stop_at %zu stats_enabled %zu port_self %zu xparam_off %zu xparam %zu\n",
         sizeof(sstb200_model), offsetof(sstb200_model, ncomp), offsetof(sstb200_model, comp_type),
         offsetof(sstb200_model, comp_param), offsetof(sstb200_model, port_off), offsetof(sstb200_model, peer_port),
         offsetof(sstb200_model, latency), offsetof(sstb200_model, clock_period), offsetof(sstb200_model, stop_at),
-        offsetof(sstb200_model, stats_enabled));
+        offsetof(sstb200_model, stats_enabled), offsetof(sstb200_model, port_self), offsetof(sstb200_model, xparam_off),
+        offsetof(sstb200_model, xparam));
     printf("options %zu device %zu rank %zu n_ranks %zu comp_begin %zu comp_end %zu rank_comp_begin %zu calendar_slots %zu "
            "bin_capacity %zu smem_events %zu outbox_capacity %zu window %zu trace_capacity %zu stream %zu "
-           "parallel_max_events %zu handler_counts %zu\n",
+           "parallel_max_events %zu handler_counts %zu model_type_mask %zu model_uniform_ports %zu output_capacity %zu\n",
         sizeof(sstb200_options), offsetof(sstb200_options, device), offsetof(sstb200_options, rank),
         offsetof(sstb200_options, n_ranks), offsetof(sstb200_options, comp_begin), offsetof(sstb200_options, comp_end),
         offsetof(sstb200_options, rank_comp_begin), offsetof(sstb200_options, calendar_slots),
         offsetof(sstb200_options, bin_capacity), offsetof(sstb200_options, smem_events),
         offsetof(sstb200_options, outbox_capacity), offsetof(sstb200_options, window),
         offsetof(sstb200_options, trace_capacity), offsetof(sstb200_options, stream),
-        offsetof(sstb200_options, parallel_max_events), offsetof(sstb200_options, handler_counts));
+        offsetof(sstb200_options, parallel_max_events), offsetof(sstb200_options, handler_counts),
+        offsetof(sstb200_options, model_type_mask), offsetof(sstb200_options, model_uniform_ports),
+        offsetof(sstb200_options, output_capacity));
     printf("status %zu now %zu end_time %zu windows %zu events_delivered %zu clock_ticks %zu events_sent %zu "
            "max_bin_fill %zu max_due %zu finished %zu error %zu error_info %zu launches %zu\n",
         sizeof(sstb200_status), offsetof(sstb200_status, now), offsetof(sstb200_status, end_time),
@@ -75,7 +78,7 @@ main(int argc, char** argv)
             latency[4 * i + k] = 1000; /* "1ns" */
     }
     port_off[n] = 4 * n;
-    sstb200_model   m = { n, comp_type, param, port_off, peer, latency, clock, stop, 0 };
+    sstb200_model   m = { n, comp_type, param, port_off, peer, latency, clock, stop, 0, NULL, NULL, NULL };
     sstb200_options o;
     memset(&o, 0, sizeof o);
     o.n_ranks        = 1;

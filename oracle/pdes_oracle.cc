@@ -199,7 +199,7 @@ struct Accumulator
 // ------------------------------------------------------------------------------------------------ engine
 enum : uint64_t { PRIO_STOP = 30, PRIO_CLOCK = 40, PRIO_EVENT = 50, PRIO_EXIT = 99 };
 enum { KIND_EVENT, KIND_CLOCK, KIND_STOP, KIND_EXIT };
-enum { TYPE_MESH = 1, TYPE_PHOLD = 2, TYPE_CLOCKNODE = 3, TYPE_RNGCOMP = 4, TYPE_CORETEST = 5 };
+enum { TYPE_MESH = 1, TYPE_PHOLD = 2, TYPE_CLOCKNODE = 3, TYPE_RNGCOMP = 4, TYPE_CORETEST = 5, TYPE_CLOCKER = 6 };
 constexpr int      NPARAM   = 8;
 constexpr int      NRESULT  = 32;
 constexpr uint32_t NO_PEER  = 0xFFFFFFFFu;
@@ -241,15 +241,57 @@ struct Component
     virtual void setup() {}
     virtual void handleEvent(int /*port*/, uint64_t& /*payload*/) {}
     virtual bool tick(uint64_t /*cycle*/) { return true; }
+    // Clock::Handler<cls, &cls::fn, int>(this, hid): several handlers per component (coreTest_ClockerComponent.cc);
+    // a component with one handler only overrides tick()
+    virtual bool clockHandler(int /*hid*/, uint64_t cycle) { return tick(cycle); }
     virtual void results(uint64_t* /*r*/) const {}
     void         send(int port, uint64_t delay, uint64_t payload);
+    void         output(uint32_t code, uint64_t a, uint64_t b); // getSimulationOutput().output(...): one log record
 };
 
+// clock.h:60-260 Clock::HandlerBase as seen by the core: which clock (or ordered group) it belongs to, whether it is
+// in the call list, its position among the ordered handlers of its group (order_ < 0: unordered)
+struct ClockObj;
+struct ClockGroup;
+struct ClockHandler
+{
+    uint32_t    comp   = 0;
+    int         hid    = 0;
+    bool        active = false;
+    int         order  = -1;
+    ClockObj*   clock  = nullptr;
+    ClockGroup* group  = nullptr;
+};
+// clock.h Clock::Group / clock.cc:25-155: the ordered handlers of ONE component on one clock, called in registration
+// order after the clock's unordered handlers
+struct ClockGroup
+{
+    ClockObj*                  clock = nullptr;
+    uint32_t                   comp  = 0;
+    std::vector<ClockHandler*> all; // by order_
+    bool                       in_list = false;
+    bool anyActive() const
+    {
+        for ( auto* h : all )
+            if ( h->active ) return true;
+        return false;
+    }
+};
 struct ClockObj
 {
-    uint64_t              period;
-    std::vector<uint32_t> handlers; // component ids in registration order
-    uint64_t              cycle = 0;
+    uint64_t                   period;
+    std::vector<ClockHandler*> handlers; // active unordered handlers, call order = (re)registration order
+    std::vector<ClockGroup*>   groups;   // active groups, activation order
+    uint64_t                   cycle     = 0;
+    bool                       scheduled = false;
+    uint32_t                   index     = 0;
+};
+
+struct OutRec
+{
+    uint64_t time;
+    uint32_t comp, code;
+    uint64_t a, b;
 };
 
 struct TraceRec
@@ -265,7 +307,11 @@ struct Sim
     std::vector<Component*>  comps;
     std::vector<uint32_t>    port_off, peer_port, port_comp, port_tag;
     std::vector<uint64_t>    latency;
-    std::vector<ClockObj>    clocks;
+    std::vector<ClockObj*>   clocks;
+    std::vector<ClockHandler*> all_handlers;
+    std::vector<ClockGroup*>   all_groups;
+    std::vector<OutRec>      out_log;
+    uint64_t                 cur_prio = 0; // priority of the activity being executed (Simulation::getCurrentPriority)
     std::priority_queue<Activity, std::vector<Activity>, ActGreater> pq;
     uint64_t                 insert_order = 0;
     uint64_t                 now = 0, stop_at = 0, end_time = 0;
@@ -284,26 +330,172 @@ struct Sim
     {
         for ( auto c : comps )
             delete c;
+        for ( auto c : clocks )
+            delete c;
+        for ( auto h : all_handlers )
+            delete h;
+        for ( auto g : all_groups )
+            delete g;
     }
     void insert(Activity a)
     {
         a.queue_order = insert_order++;
         pq.push(a);
     }
-    void registerClock(uint32_t comp, uint64_t period)
+    // ---- clocks (simulation.cc:1403-1516, clock.cc).  One Clock object per period (all handlers here run at
+    // CLOCKPRIORITY); it is created and scheduled the first time anybody asks for the period.
+    ClockObj* clockFor(uint64_t period)
     {
-        // simulation.cc:1403-1427: one Clock per period; created + scheduled on first registration (clock.cc:400-420:
-        // at time 0 the first tick is at `period`).
-        for ( size_t i = 0; i < clocks.size(); ++i )
-            if ( clocks[i].period == period ) {
-                clocks[i].handlers.push_back(comp);
-                return;
-            }
-        ClockObj c;
-        c.period = period;
-        c.handlers.push_back(comp);
+        for ( auto* c : clocks )
+            if ( c->period == period ) return c;
+        ClockObj* c = new ClockObj();
+        c->period   = period;
+        c->index    = (uint32_t)clocks.size();
         clocks.push_back(c);
-        insert({ period, PRIO_CLOCK << 32, 0, KIND_CLOCK, (uint32_t)(clocks.size() - 1), 0 });
+        schedule(c);
+        return c;
+    }
+    // Clock::schedule clock.cc:400-420
+    void schedule(ClockObj* c)
+    {
+        c->cycle      = now / c->period;
+        uint64_t next = c->cycle * c->period + c->period;
+        if ( cur_prio < PRIO_CLOCK && now != 0 && !end_sim ) {
+            if ( now % c->period == 0 ) {
+                next = now;
+                c->cycle--;
+            }
+        }
+        insert({ next, PRIO_CLOCK << 32, 0, KIND_CLOCK, c->index, 0 });
+        c->scheduled = true;
+    }
+    uint64_t nextCycle(ClockObj* c) // Clock::getNextCycle clock.cc:305-311
+    {
+        if ( !c->scheduled ) c->cycle = now / c->period;
+        return c->cycle + 1;
+    }
+    void attach(ClockHandler* h) // Clock::registerHandler clock.cc:193-231
+    {
+        if ( h->active ) return;
+        h->active = true;
+        h->clock->handlers.push_back(h);
+        if ( !h->clock->scheduled ) schedule(h->clock);
+    }
+    void activateGroup(ClockGroup* g) // Clock::activateGroup clock.cc:289-303
+    {
+        if ( g->in_list ) return;
+        g->in_list = true;
+        g->clock->groups.push_back(g);
+        if ( !g->clock->scheduled ) schedule(g->clock);
+    }
+    ClockHandler* newHandler(uint32_t comp, uint64_t period, int hid)
+    {
+        ClockHandler* h = new ClockHandler();
+        h->comp         = comp;
+        h->hid          = hid;
+        h->clock        = clockFor(period);
+        all_handlers.push_back(h);
+        return h;
+    }
+    // BaseComponent::registerClock -> Simulation::registerClock
+    ClockHandler* registerClock(uint32_t comp, uint64_t period, int hid = 0)
+    {
+        ClockHandler* h = newHandler(comp, period, hid);
+        attach(h);
+        return h;
+    }
+    // BaseComponent::registerOrderedClock -> Component::getClockGroup (component.cc:34-45) + Group::registerHandler
+    // (clock.cc:25-46)
+    ClockHandler* registerOrderedClock(uint32_t comp, uint64_t period, int hid)
+    {
+        ClockHandler* h = newHandler(comp, period, hid);
+        ClockGroup*   g = nullptr;
+        for ( auto* x : all_groups )
+            if ( x->comp == comp && x->clock == h->clock ) g = x;
+        if ( !g ) {
+            g        = new ClockGroup();
+            g->clock = h->clock;
+            g->comp  = comp;
+            all_groups.push_back(g);
+        }
+        h->group  = g;
+        h->order  = (int)g->all.size();
+        h->active = true;
+        g->all.push_back(h);
+        activateGroup(g);
+        return h;
+    }
+    // HandlerBase::activate clock.h:180-190 (= reregisterClock for unordered handlers, simulation.cc:1441-1451)
+    uint64_t activate(ClockHandler* h)
+    {
+        if ( h->order < 0 ) {
+            attach(h);
+        }
+        else if ( !h->active ) {
+            h->active = true;
+            activateGroup(h->group);
+        }
+        return nextCycle(h->clock);
+    }
+    // HandlerBase::deactivate clock.h:195-204 (= unregisterClock, clock.cc:233-250)
+    void deactivate(ClockHandler* h)
+    {
+        if ( !h->active ) return;
+        h->active = false;
+        if ( h->order < 0 ) {
+            auto& v = h->clock->handlers;
+            for ( size_t i = 0; i < v.size(); ++i )
+                if ( v[i] == h ) {
+                    v.erase(v.begin() + (long)i);
+                    break;
+                }
+        }
+        // (a group notices at its next execute that nobody is active, clock.cc:104-108)
+    }
+    // Clock::execute clock.cc:314-397 + Clock::Group::execute clock.cc:110-155
+    void executeClock(ClockObj& ck)
+    {
+        if ( ck.handlers.empty() && ck.groups.empty() ) {
+            ck.scheduled = false;
+            return;
+        }
+        ck.cycle++;
+        for ( size_t i = 0; i < ck.handlers.size(); ) {
+            ClockHandler* h = ck.handlers[i];
+            clock_ticks++;
+            const bool stop = comps[h->comp]->clockHandler(h->hid, ck.cycle);
+            // the callee may have changed the list: find the handler again
+            size_t at = ck.handlers.size();
+            for ( size_t j = 0; j < ck.handlers.size(); ++j )
+                if ( ck.handlers[j] == h ) {
+                    at = j;
+                    break;
+                }
+            if ( at == ck.handlers.size() ) continue; // it removed itself: the next one has moved into slot i
+            if ( stop ) {
+                h->active = false;
+                ck.handlers.erase(ck.handlers.begin() + (long)at);
+                i = at;
+            }
+            else
+                i = at + 1;
+        }
+        for ( size_t gi = 0; gi < ck.groups.size(); ) {
+            ClockGroup* g = ck.groups[gi];
+            for ( size_t j = 0; j < g->all.size(); ++j ) {
+                ClockHandler* h = g->all[j];
+                if ( !h->active ) continue;
+                clock_ticks++;
+                if ( comps[h->comp]->clockHandler(h->hid, ck.cycle) ) h->active = false;
+            }
+            if ( !g->anyActive() ) {
+                g->in_list = false;
+                ck.groups.erase(ck.groups.begin() + (long)gi);
+            }
+            else
+                ++gi;
+        }
+        insert({ now + ck.period, PRIO_CLOCK << 32, 0, KIND_CLOCK, ck.index, 0 });
     }
     void primaryOK()
     {
@@ -322,7 +514,8 @@ struct Sim
         while ( !end_sim && !pq.empty() ) {
             Activity a = pq.top();
             pq.pop();
-            now = a.time;
+            now      = a.time;
+            cur_prio = a.prio_order >> 32;
             switch ( a.kind ) {
             case KIND_EVENT:
             {
@@ -334,20 +527,8 @@ struct Sim
                 break;
             }
             case KIND_CLOCK:
-            {
-                ClockObj& ck = clocks[a.target];
-                if ( ck.handlers.empty() ) break; // clock.cc:316-319: goes unscheduled
-                ck.cycle++;
-                size_t keep = 0;
-                for ( size_t i = 0; i < ck.handlers.size(); ++i ) {
-                    clock_ticks++;
-                    bool done = comps[ck.handlers[i]]->tick(ck.cycle);
-                    if ( !done ) ck.handlers[keep++] = ck.handlers[i];
-                }
-                ck.handlers.resize(keep);
-                insert({ now + ck.period, PRIO_CLOCK << 32, 0, KIND_CLOCK, a.target, 0 });
+                executeClock(*clocks[a.target]);
                 break;
-            }
             case KIND_STOP:
                 end_sim  = true;
                 end_time = now;
@@ -369,11 +550,17 @@ Component::send(int port, uint64_t delay, uint64_t payload)
     uint64_t t  = sim->now + delay + sim->latency[p];
     uint32_t dc = sim->port_comp[peer];
     uint32_t sq = sim->send_seq[id]++;
-    if ( dc < sim->own_lo || dc >= sim->own_hi ) {
+    if ( peer != p && (dc < sim->own_lo || dc >= sim->own_hi) ) {
         sim->outbox.insert(sim->outbox.end(), { t, ((uint64_t)peer << 32) | sq, payload, (uint64_t)dc });
         return;
     }
     sim->insert({ t, (PRIO_EVENT << 32) | sim->port_tag[peer], 0, KIND_EVENT, peer, payload });
+}
+
+void
+Component::output(uint32_t code, uint64_t a, uint64_t b)
+{
+    sim->out_log.push_back({ sim->now, id, code, a, b });
 }
 
 // ------------------------------------------------------------------------------------------------ models
@@ -569,6 +756,151 @@ struct RngComp : Component
     }
 };
 
+// testElements/coreTest_ClockerComponent.{h,cc} (tests/test_Clocks.py, tests/refFiles/test_Clocks_basic.out): a chain
+// of components, each running the same schedule of start / stop operations on nine test clocks: old-style
+// register/unregister/reregisterClock (0, 1), handler activate()/deactivate() (2, 3) and five ordered handlers (4..8, two
+// of them registered by subcomponents) that operate on one variable in registration order.  The master clock (5 ns)
+// issues the operations as events on a self link, so that they run after every clock of that time.
+// Ports: 0 "left", 1 "right", 2 "inst_link" (configureSelfLink).  Handler ids: 0..8 the test clocks, 9 the master.
+// Output record codes (a = id | second integer << 32, b = the 64-bit value):
+//   0 "%d: starting test sequence at %llu"      1 "%d: Starting test sequence at %llu"
+//   2 "%d: Clock %d will restart at cycle %llu" 3 "%d: Stopping Clock %d at time %llu"
+//   4 "%d: Terminating test sequence at %llu"   5 "%d: Clock %d at cycle %llu"
+//   6 "%d: Self stopping Clock %d at time %llu" 7 "%d: ordered clock result = %d (cycle = %llu)"
+struct ClockerComp : Component
+{
+    static constexpr int      total_count   = 3;
+    static constexpr uint64_t master_period = 5000, test_period = 1000; // "5ns", "1ns" at a 1 ps time base
+    enum { OP_NOP, OP_START, OP_STOP, OP_TERM };
+    struct OpBundle
+    {
+        int op, clock;
+    };
+    int           id_ = -1, inst_count_ = 0;
+    bool          done_ = false;
+    ClockHandler* master_ = nullptr;
+    struct ClockInfo
+    {
+        ClockHandler* handler;
+        int64_t       counter;
+        bool          new_style;
+    };
+    std::vector<ClockInfo> clocks_;
+    int                    ordered_var_test_       = -1;
+    bool                   ordered_handler_remove_ = false;
+
+    static const std::vector<std::vector<OpBundle>>& program()
+    {
+        // coreTest_ClockerComponent.h:265-276
+        static const std::vector<std::vector<OpBundle>> p = {
+            { { OP_START, 1 }, { OP_START, 5 }, { OP_START, 6 }, { OP_START, 7 }, { OP_START, 8 } },
+            { { OP_START, 0 }, { OP_STOP, 6 } }, { { OP_START, 3 }, { OP_STOP, 7 } },
+            { { OP_STOP, 1 }, { OP_START, 6 } },
+            { { OP_START, 2 }, { OP_START, 4 } },
+            { { OP_STOP, 3 }, { OP_START, 5 }, { OP_START, 6 }, { OP_START, 8 } },
+            { { OP_START, 1 }, { OP_START, 6 }, { OP_START, 5 }, { OP_START, 8 }, { OP_START, 7 } },
+            { { OP_START, 0 } }, { { OP_START, 3 } }, { { OP_STOP, 1 } }, { { OP_START, 2 } }, { { OP_STOP, 3 } },
+            { { OP_TERM, -1 } }
+        };
+        return p;
+    }
+    // the constructor's clock registrations (coreTest_ClockerComponent.cc:75-165); called once ports are known
+    void construct()
+    {
+        const bool left_connected = nports > 0 && sim->peer_port[port0 + 0] != NO_PEER;
+        if ( !left_connected ) id_ = 0;
+        master_ = sim->registerClock(id, master_period, 9);
+        if ( id_ != 0 ) sim->deactivate(master_);
+        for ( int i = 0; i < 4; ++i )
+            clocks_.push_back({ sim->registerClock(id, test_period, i), total_count, i >= 2 });
+        for ( int i = 0; i < 4; ++i )
+            sim->deactivate(clocks_[i].handler); // unregisterClock x2, deactivate x2
+        for ( int i = 4; i <= 8; ++i ) { // 6 and 7 come from the anonymous and the user subcomponent
+            ClockHandler* h = sim->registerOrderedClock(id, test_period, i);
+            sim->deactivate(h);
+            clocks_.push_back({ h, total_count, true });
+        }
+    }
+    uint64_t tag(int second) const { return (uint64_t)(uint32_t)id_ | ((uint64_t)(uint32_t)second << 32); }
+    void     setup() override
+    {
+        if ( id_ != 0 ) return;
+        output(0, tag(0), sim->now);
+        send(1, 1 * master_period, 1); // IntEvent(1) on "right", delayed by one master period
+    }
+    void handleEvent(int port, uint64_t& payload) override
+    {
+        if ( port == 0 ) { // handle_left
+            id_ = (int)payload;
+            payload++;
+            send(1, 0, payload);
+            sim->activate(master_);
+            output(1, tag(0), sim->now);
+            return;
+        }
+        // inst_handler
+        const int  op = (int)(payload & 0xFF), clock = (int)(int8_t)((payload >> 8) & 0xFF);
+        switch ( op ) {
+        case OP_START:
+        {
+            ClockInfo& info = clocks_[clock];
+            uint64_t   next = sim->activate(info.handler); // activate() / reregisterClock()
+            output(2, tag(clock), next);
+            break;
+        }
+        case OP_STOP:
+            sim->deactivate(clocks_[clock].handler); // deactivate() / unregisterClock()
+            output(3, tag(clock), sim->now);
+            break;
+        case OP_TERM:
+            sim->primaryOK();
+            done_ = true;
+            output(4, tag(0), sim->now);
+            break;
+        default:
+            break;
+        }
+    }
+    bool clockHandler(int hid, uint64_t cycle) override
+    {
+        if ( hid == 9 ) { // master_handler
+            if ( done_ ) return true;
+            for ( const OpBundle& x : program()[inst_count_++] )
+                send(2, 0, (uint64_t)x.op | ((uint64_t)(uint8_t)x.clock << 8));
+            return false;
+        }
+        if ( hid <= 3 ) { // test_handler
+            output(5, tag(hid), cycle);
+            if ( hid == 0 || hid == 2 ) {
+                if ( --clocks_[hid].counter == 0 ) {
+                    output(6, tag(hid), sim->now);
+                    clocks_[hid].counter = total_count;
+                    return true;
+                }
+            }
+            return false;
+        }
+        // test_ordered_handler
+        switch ( hid ) {
+        case 4: ordered_handler_remove_ = true; break;
+        case 5: ordered_var_test_ = 36; break;
+        case 6: ordered_var_test_ /= 2; break;
+        case 7: ordered_var_test_ -= 6; break;
+        case 8: output(7, tag(ordered_var_test_), cycle); break;
+        }
+        return ordered_handler_remove_;
+    }
+    void results(uint64_t* r) const override
+    {
+        r[0] = (uint64_t)(int64_t)id_;
+        r[1] = (uint64_t)inst_count_;
+        r[2] = done_ ? 1 : 0;
+        r[3] = (uint64_t)(int64_t)ordered_var_test_;
+        for ( int i = 0; i < 9; ++i )
+            r[4 + i] = (uint64_t)clocks_[i].counter;
+    }
+};
+
 } // namespace
 
 // ================================================================================================ C interface
@@ -577,10 +909,13 @@ extern "C" {
 // Build a serial simulation from the raw wired-model arrays (same layout the product's C-ABI takes; see
 // include/sstb200.h): component types + 8 int64 params each, directed-port CSR in configureLink order, peer port and
 // send latency per directed port, clock period per component (0 = none), stop time (0 = none).
+// port_self (may be NULL): 1 = a configureSelfLink port (baseComponent.cc:374-378, link.h:512-521): its peer is itself,
+// its latency may be 0 and it keeps order tag 0xFFFFFFFF (Link::setTag link.h:309-319 leaves a SelfLink's tag alone),
+// although the configureLink call still takes the next tag number.
 void*
-oracle_create(uint32_t ncomp, const uint32_t* comp_type, const int64_t* comp_param, const uint32_t* port_off,
-    const uint32_t* peer_port, const uint64_t* latency, const uint64_t* clock_period, uint64_t stop_at, int stats_on,
-    int tracing)
+oracle_create2(uint32_t ncomp, const uint32_t* comp_type, const int64_t* comp_param, const uint32_t* port_off,
+    const uint32_t* peer_port, const uint64_t* latency, const uint64_t* clock_period, const uint8_t* port_self,
+    uint64_t stop_at, int stats_on, int tracing)
 {
     Sim* s      = new Sim();
     s->ncomp    = ncomp;
@@ -614,6 +949,9 @@ oracle_create(uint32_t ncomp, const uint32_t* comp_type, const int64_t* comp_par
         case TYPE_CORETEST:
             k = new CoreTestComp(p);
             break;
+        case TYPE_CLOCKER:
+            k = new ClockerComp();
+            break;
         default:
             delete s;
             return nullptr;
@@ -629,12 +967,42 @@ oracle_create(uint32_t ncomp, const uint32_t* comp_type, const int64_t* comp_par
             // 0xFFFFFFFF (link.cc:469-479), are not used by any in-scope model and are not representable here; a
             // config-graph loopback, peer == own port, is configured like any other link.)
             s->port_tag[q] = (peer_port[q] == NO_PEER) ? 0 : next_tag++;
+            if ( port_self && port_self[q] ) s->port_tag[q] = 0xFFFFFFFFu;
         }
+        if ( comp_type[c] == TYPE_CLOCKER ) static_cast<ClockerComp*>(k)->construct();
         // every in-scope model registers as primary and says DoNotEndSim in its constructor
         s->primary++;
         if ( clock_period[c] ) s->registerClock(c, clock_period[c]);
     }
     return s;
+}
+
+void*
+oracle_create(uint32_t ncomp, const uint32_t* comp_type, const int64_t* comp_param, const uint32_t* port_off,
+    const uint32_t* peer_port, const uint64_t* latency, const uint64_t* clock_period, uint64_t stop_at, int stats_on,
+    int tracing)
+{
+    return oracle_create2(ncomp, comp_type, comp_param, port_off, peer_port, latency, clock_period, nullptr, stop_at,
+        stats_on, tracing);
+}
+
+// console-output records (Component::output) in the order the serial run produced them
+uint64_t
+oracle_output_count(void* h)
+{
+    return ((Sim*)h)->out_log.size();
+}
+void
+oracle_output(void* h, uint64_t* time, uint32_t* comp, uint32_t* code, uint64_t* a, uint64_t* b)
+{
+    Sim* s = (Sim*)h;
+    for ( size_t i = 0; i < s->out_log.size(); ++i ) {
+        time[i] = s->out_log[i].time;
+        comp[i] = s->out_log[i].comp;
+        code[i] = s->out_log[i].code;
+        a[i]    = s->out_log[i].a;
+        b[i]    = s->out_log[i].b;
+    }
 }
 
 // ---- partitioned stepping: the reference's conservative window protocol (SyncManager::execute +
@@ -653,11 +1021,15 @@ oracle_setup_owned(void* h)
 {
     Sim* s = (Sim*)h;
     // non-owned components: remove their clock registrations and primary counts
-    for ( auto& ck : s->clocks ) {
-        std::vector<uint32_t> keep;
-        for ( uint32_t c : ck.handlers )
-            if ( c >= s->own_lo && c < s->own_hi ) keep.push_back(c);
-        ck.handlers = keep;
+    for ( auto* ck : s->clocks ) {
+        std::vector<ClockHandler*> keep;
+        for ( auto* h : ck->handlers )
+            if ( h->comp >= s->own_lo && h->comp < s->own_hi ) keep.push_back(h);
+        ck->handlers = keep;
+        std::vector<ClockGroup*> keepg;
+        for ( auto* g : ck->groups )
+            if ( g->comp >= s->own_lo && g->comp < s->own_hi ) keepg.push_back(g);
+        ck->groups = keepg;
     }
     s->primary = 0;
     for ( uint32_t c = s->own_lo; c < s->own_hi && c < s->ncomp; ++c )
@@ -677,7 +1049,8 @@ oracle_run_until(void* h, uint64_t t_end)
         Activity a = s->pq.top();
         if ( a.time >= t_end ) break;
         s->pq.pop();
-        s->now = a.time;
+        s->now      = a.time;
+        s->cur_prio = a.prio_order >> 32;
         if ( a.kind == KIND_EVENT ) {
             uint32_t   c = s->port_comp[a.target];
             Component* k = s->comps[c];
@@ -686,16 +1059,7 @@ oracle_run_until(void* h, uint64_t t_end)
             k->handleEvent((int)(a.target - k->port0), a.payload);
         }
         else if ( a.kind == KIND_CLOCK ) {
-            ClockObj& ck = s->clocks[a.target];
-            if ( ck.handlers.empty() ) continue;
-            ck.cycle++;
-            size_t keep = 0;
-            for ( size_t i = 0; i < ck.handlers.size(); ++i ) {
-                s->clock_ticks++;
-                if ( !s->comps[ck.handlers[i]]->tick(ck.cycle) ) ck.handlers[keep++] = ck.handlers[i];
-            }
-            ck.handlers.resize(keep);
-            s->insert({ s->now + ck.period, PRIO_CLOCK << 32, 0, KIND_CLOCK, a.target, 0 });
+            s->executeClock(*s->clocks[a.target]);
         }
     }
     return s->outbox.size() / 4;
@@ -741,8 +1105,12 @@ oracle_control_words(void* h, int64_t* out)
         if ( copy.top().kind == KIND_EVENT ) pending++;
         copy.pop();
     }
-    for ( auto& ck : s->clocks )
-        clocks += (int64_t)ck.handlers.size();
+    for ( auto* ck : s->clocks ) {
+        clocks += (int64_t)ck->handlers.size();
+        for ( auto* g : ck->groups )
+            for ( auto* h : g->all )
+                clocks += h->active ? 1 : 0;
+    }
     out[0] = pending + (int64_t)(s->outbox.size() / 4);
     out[1] = s->primary;
     out[2] = clocks;

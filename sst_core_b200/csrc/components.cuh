@@ -17,6 +17,15 @@
 //                                                         the handlers will read this window
 //   finish()                                              ->  static results(const State&, uint64_t r[32]); the host
 //                                                         half formats the console line / statistic rows from r.
+//   several clocks / handlers per component, ordered handlers, activate() / deactivate() / reregisterClock()
+//   (clock.h:60-260, clock.cc:25-155,193-250; baseComponent.h:488-620)
+//                                                         ->  MULTI_CLOCK = true + a ClockSet<> in the State:
+//                                                         static clockFire(Ctx&, State&, time) runs every handler due at
+//                                                         `time`, static nextClock(State&) is the next such time
+//   configureSelfLink (baseComponent.cc:374-378)          ->  SELF_LINKS = true; the self-link ports are the LAST ports of
+//                                                         the component, ctx.send() on them may arrive inside the window
+//   getSimulationOutput().output(fmt, ...)                ->  ctx.output(code, a, b): one record of the engine's output
+//                                                         log; the host half owns the format strings
 //
 // A handler runs on exactly one thread and is never concurrent with another handler of the same component -- the
 // reference's threading contract.  Components touch no memory but their own State, their aux
@@ -33,7 +42,8 @@
 
 namespace sstb200 {
 
-enum : uint32_t { TYPE_MESH = 1, TYPE_PHOLD = 2, TYPE_CLOCKNODE = 3, TYPE_RNGCOMP = 4, TYPE_CORETEST = 5, TYPE_MAX = 6 };
+enum : uint32_t { TYPE_MESH = 1, TYPE_PHOLD = 2, TYPE_CLOCKNODE = 3, TYPE_RNGCOMP = 4, TYPE_CORETEST = 5, TYPE_CLOCKER = 6,
+                  TYPE_MAX = 7 };
 constexpr int NPARAM  = 8;
 constexpr int NRESULT = 32;
 
@@ -122,6 +132,161 @@ divisible_i32(int32_t x, uint64_t magic, int32_t f)
     const uint32_t a = x < 0 ? 0u - (uint32_t)x : (uint32_t)x;
     return fastmod_u32(a, magic, (uint32_t)f) == 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// The clocks of ONE component (clock.cc / clock.h restated per component).  In the reference a Clock object per period
+// is shared by all components of a partition (simulation.cc:1403-1427); what a component can observe of it is:
+//   * its own unordered handlers are called in the order they were (re)registered / activated (Clock::registerHandler
+//     appends, clock.cc:193-231; removal keeps the order of the others, :233-250, :324-367);
+//   * its ordered handlers -- its Clock::Group on that clock (component.cc:34-45) -- are called after them, in
+//     registration order (Group::activateHandler re-inserts by order_, clock.cc:48-88; Clock::execute runs the groups
+//     after the handler list, :369-390);
+//   * a handler that returns true is removed; the cycle number passed is time / period;
+//   * a handler (re)activated at time t from an event handler first fires at the next multiple of the period after t
+//     (Clock::schedule / getNextCycle, clock.cc:305-311,400-420: events run at priority 50, after the clocks of t).
+// Between Clock objects of different periods due at the same time the reference's order is the TimeVortex insertion
+// order -- the longer period was re-inserted earlier and runs first in steady state.  That is the order used here; a
+// handler activated by a clock handler of a longer period therefore still fires at the same time when that time is a
+// multiple of its own period.  (The reference leaves this case to global state no component controls, which is why
+// coreTestClockerComponent routes its operations through a self link, coreTest_ClockerComponent.h:154-160.)
+// Handlers are numbered 0..NH-1 in registration order; classes (periods) 0..NC-1.
+template <int NC, int NH>
+struct ClockSet
+{
+    uint64_t period[NC];
+    uint64_t next[NC];     // next time class c fires, meaningful while it has an active handler
+    uint8_t  list[NC][NH]; // active unordered handlers of the class, call order
+    uint8_t  n[NC];
+    uint8_t  cls[NH], ordered[NH], active[NH];
+    uint8_t  nh, nclass, phase, pad0; // phase: class being executed by fire(), NC outside
+    static constexpr uint64_t NEVER = ~0ull;
+
+    SSTB_HD void init()
+    {
+        for ( int c = 0; c < NC; ++c ) {
+            period[c] = 0;
+            next[c]   = NEVER;
+            n[c]      = 0;
+            for ( int h = 0; h < NH; ++h )
+                list[c][h] = 0;
+        }
+        for ( int h = 0; h < NH; ++h )
+            cls[h] = ordered[h] = active[h] = 0;
+        nh = nclass = 0;
+        phase       = NC;
+        pad0        = 0;
+    }
+    SSTB_HD int classFor(uint64_t per)
+    {
+        for ( int c = 0; c < (int)nclass; ++c )
+            if ( period[c] == per ) return c;
+        period[nclass] = per;
+        return (int)nclass++;
+    }
+    SSTB_HD bool anyActive(int c) const
+    {
+        if ( n[c] ) return true;
+        for ( int h = 0; h < (int)nh; ++h )
+            if ( cls[h] == c && ordered[h] && active[h] ) return true;
+        return false;
+    }
+    // registerClock / registerOrderedClock at time `now` (0 in a constructor): returns the handler id
+    SSTB_HD int add(uint64_t per, bool is_ordered, uint64_t now)
+    {
+        const int h = (int)nh++;
+        cls[h]      = (uint8_t)classFor(per);
+        ordered[h]  = is_ordered ? 1 : 0;
+        active[h]   = 0;
+        activate(h, now);
+        return h;
+    }
+    // HandlerBase::activate / reregisterClock: returns the cycle at which the clock fires next (getNextCycle)
+    SSTB_HD uint64_t activate(int h, uint64_t now)
+    {
+        const int      c     = cls[h];
+        const uint64_t per   = period[c];
+        // has this time's execute of the handler's clock still to come? (only inside fire(), for a shorter period)
+        const bool     later = phase < NC && per < period[phase] && now != 0 && now % per == 0;
+        if ( !active[h] ) {
+            const bool was_empty = !anyActive(c);
+            active[h]            = 1;
+            if ( !ordered[h] ) list[c][n[c]++] = (uint8_t)h;
+            if ( was_empty ) next[c] = later ? now : (now / per + 1) * per;
+        }
+        return later ? now / per : now / per + 1;
+    }
+    // HandlerBase::deactivate / unregisterClock
+    SSTB_HD void deactivate(int h)
+    {
+        if ( !active[h] ) return;
+        active[h]   = 0;
+        const int c = cls[h];
+        if ( ordered[h] ) return;
+        int at = -1;
+        for ( int j = 0; j < (int)n[c]; ++j )
+            if ( list[c][j] == h ) at = j;
+        if ( at < 0 ) return;
+        for ( int j = at; j + 1 < (int)n[c]; ++j )
+            list[c][j] = list[c][j + 1];
+        n[c]--;
+    }
+    SSTB_HD uint64_t nextTime() const
+    {
+        uint64_t t = NEVER;
+        for ( int c = 0; c < (int)nclass; ++c )
+            if ( next[c] < t && anyActive(c) ) t = next[c];
+        return t;
+    }
+    // Clock::execute of every clock of this component due at time t; call(h, cycle) -> true = remove the handler.
+    // Returns the number of handler calls.
+    template <class F>
+    SSTB_HD uint32_t fire(uint64_t t, F&& call)
+    {
+        uint32_t calls = 0, done = 0;
+        for ( int pass = 0; pass < (int)nclass; ++pass ) {
+            int c = -1;
+            for ( int k = 0; k < (int)nclass; ++k )
+                if ( !(done >> k & 1u) && next[k] == t && anyActive(k) && (c < 0 || period[k] > period[c]) ) c = k;
+            if ( c < 0 ) break;
+            done |= 1u << c;
+            phase                = (uint8_t)c;
+            const uint64_t cycle = t / period[c];
+            for ( int i = 0; i < (int)n[c]; ) {
+                const int  h    = list[c][i];
+                const bool stop = call(h, cycle);
+                calls++;
+                int at = -1; // the callee may have changed the list
+                for ( int j = 0; j < (int)n[c]; ++j )
+                    if ( list[c][j] == h ) at = j;
+                if ( at < 0 ) continue;
+                if ( stop ) {
+                    deactivate(h);
+                    i = at;
+                }
+                else
+                    i = at + 1;
+            }
+            for ( int h = 0; h < (int)nh; ++h )
+                if ( cls[h] == c && ordered[h] && active[h] ) {
+                    if ( call(h, cycle) ) active[h] = 0;
+                    calls++;
+                }
+            next[c] = t + period[c];
+        }
+        phase = NC;
+        return calls;
+    }
+};
+
+// events a component sent to itself over a self link that are due inside the current window: a small queue in the
+// owning thread, ordered by (time, port, sequence)
+struct SelfQueue
+{
+    static constexpr int CAP = 8;
+    uint32_t n;
+    uint32_t port[CAP], seq[CAP];
+    uint64_t time[CAP], pay[CAP];
+};
 
 #if defined(__CUDACC__)
 
@@ -669,6 +834,175 @@ struct RngElement
     }
 };
 
+// ------------------------------------------------------------------------------------------------------------------
+// coreTestElement.coreTestClockerComponent (testElements/coreTest_ClockerComponent.{h,cc}; tests/test_Clocks.py,
+// tests/refFiles/test_Clocks_basic.out).  Ports: 0 "left", 1 "right", 2 "inst_link" (self link).  Handlers: 0..3 the
+// test clocks registered with registerClock (0, 1 old style: unregisterClock / reregisterClock; 2, 3: activate /
+// deactivate), 4..8 the ordered handlers (6 and 7 registered by the anonymous and the user ClockSubComponent, into the
+// parent's group: baseComponent.h:1426), 9 the master clock.  Output codes: sst_core_b200/elements.py _CLOCKER_FMT.
+struct ClockerElement
+{
+    static constexpr uint32_t    TYPE            = TYPE_CLOCKER;
+    static constexpr const char* ELI_NAME        = "coreTestElement.coreTestClockerComponent";
+    static constexpr uint32_t    AUX_BYTES       = 0;
+    static constexpr bool        AUX_MT_SEED     = false;
+    static constexpr uint32_t    AUX_SEED_OFFSET = 0;
+    __device__ static uint32_t auxSeed(const int64_t*) { return 0; }
+    static constexpr bool HAS_PAYLOAD = true; // IntEvent / OpEvent
+    static constexpr bool MULTI_CLOCK = true;
+    static constexpr bool SELF_LINKS  = true;
+    static constexpr uint64_t MASTER_PERIOD = 5000, TEST_PERIOD = 1000; // "5ns", "1ns" at the 1 ps time base
+    static constexpr int      TOTAL_COUNT   = 3;
+    enum { OP_NOP, OP_START, OP_STOP, OP_TERM };
+    struct State
+    {
+        int32_t         id_, inst_count, ordered_var;
+        uint8_t         done, ordered_remove, pad0, pad1;
+        int32_t         counter[4];
+        ClockSet<2, 10> clk;
+        uint64_t        pad2;
+    };
+    static_assert(sizeof(State) % 16 == 0, "State is moved in 16-byte pieces");
+    static constexpr uint32_t STORE_END = sizeof(State), CONST_END = sizeof(State), STATS_END = sizeof(State);
+    static constexpr bool     TIES_INTERCHANGEABLE = false;
+    static constexpr bool     STATS_EVERY_EVENT    = false;
+    static constexpr bool     PARALLEL_EVENTS      = false;
+    static constexpr uint32_t PERSIST_BYTES = sizeof(State), RECORD_BYTES = sizeof(State);
+    // coreTest_ClockerComponent.h:265-276: op << 4 | clock, 0 ends an instruction
+    __device__ static uint8_t program(int inst, int k)
+    {
+        constexpr uint8_t S = OP_START << 4, P = OP_STOP << 4, T = OP_TERM << 4;
+        static constexpr uint8_t prog[13][6] = {
+            { S | 1, S | 5, S | 6, S | 7, S | 8, 0 }, { S | 0, P | 6, 0 }, { S | 3, P | 7, 0 }, { P | 1, S | 6, 0 },
+            { S | 2, S | 4, 0 }, { P | 3, S | 5, S | 6, S | 8, 0 }, { S | 1, S | 6, S | 5, S | 8, S | 7, 0 }, { S | 0, 0 },
+            { S | 3, 0 }, { P | 1, 0 }, { S | 2, 0 }, { P | 3, 0 }, { T | 15, 0 } };
+        return inst < 13 ? prog[inst][k] : 0;
+    }
+    template <class Ctx>
+    __device__ static void beginWindow(Ctx&, State&, uint32_t)
+    {}
+    __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
+    __device__ static uint64_t tag(const State& s, int second)
+    {
+        return (uint64_t)(uint32_t)s.id_ | ((uint64_t)(uint32_t)second << 32);
+    }
+    template <class Ctx>
+    __device__ static void construct(Ctx& ctx, State& s, const int64_t*)
+    {
+        s.id_ = -1;
+        s.inst_count = 0;
+        s.ordered_var = -1;
+        s.done = s.ordered_remove = s.pad0 = s.pad1 = 0;
+        for ( int i = 0; i < 4; ++i )
+            s.counter[i] = TOTAL_COUNT;
+        s.clk.init();
+        s.pad2 = 0;
+        if ( !ctx.connected(0) ) s.id_ = 0; // nullptr == left_
+        // handler ids follow the registration order: the test clocks first here (ids 0..8), the master last (9); what
+        // the reference's order between the master and the test handlers would be is not observable (different clocks)
+        for ( int i = 0; i < 4; ++i )
+            s.clk.deactivate(s.clk.add(TEST_PERIOD, false, 0)); // registered, then unregistered / deactivated
+        for ( int i = 4; i <= 8; ++i )
+            s.clk.deactivate(s.clk.add(TEST_PERIOD, true, 0));
+        const int m = s.clk.add(MASTER_PERIOD, false, 0);
+        if ( s.id_ != 0 ) s.clk.deactivate(m);
+    }
+    template <class Ctx>
+    __device__ static void setup(Ctx& ctx, State& s)
+    {
+        if ( s.id_ != 0 ) return;
+        ctx.output(0, tag(s, 0), ctx.now);
+        ctx.send(1, 1 * MASTER_PERIOD, 1); // IntEvent(1), delayed by one master period
+    }
+    template <class Ctx>
+    __device__ static void handleEvent(Ctx& ctx, State& s, int port, uint64_t& payload)
+    {
+        if ( port == 0 ) { // handle_left
+            s.id_ = (int32_t)payload;
+            payload++;
+            ctx.send(1, 0, payload);
+            s.clk.activate(9, ctx.now);
+            ctx.output(1, tag(s, 0), ctx.now);
+            return;
+        }
+        // inst_handler
+        const int op = (int)(payload & 0xFF), clock = (int)((payload >> 8) & 0xFF);
+        if ( op == OP_START ) {
+            const uint64_t next = s.clk.activate(clock, ctx.now);
+            ctx.output(2, tag(s, clock), next);
+        }
+        else if ( op == OP_STOP ) {
+            s.clk.deactivate(clock);
+            ctx.output(3, tag(s, clock), ctx.now);
+        }
+        else if ( op == OP_TERM ) {
+            ctx.primaryComponentOKToEndSim();
+            s.done = 1;
+            ctx.output(4, tag(s, 0), ctx.now);
+        }
+    }
+    template <class Ctx>
+    __device__ static bool handler(Ctx& ctx, State& s, int hid, uint64_t cycle)
+    {
+        if ( hid == 9 ) { // master_handler
+            if ( s.done ) return true;
+            const int inst = s.inst_count++;
+            for ( int k = 0; k < 6; ++k ) {
+                const uint8_t b = program(inst, k);
+                if ( !b ) break;
+                ctx.send(2, 0, (uint64_t)(b >> 4) | ((uint64_t)(b & 15) << 8));
+            }
+            return false;
+        }
+        if ( hid <= 3 ) { // test_handler
+            ctx.output(5, tag(s, hid), cycle);
+            if ( hid == 0 || hid == 2 ) {
+                if ( --s.counter[hid] == 0 ) {
+                    ctx.output(6, tag(s, hid), ctx.now);
+                    s.counter[hid] = TOTAL_COUNT;
+                    return true;
+                }
+            }
+            return false;
+        }
+        // test_ordered_handler
+        if ( hid == 4 )
+            s.ordered_remove = 1;
+        else if ( hid == 5 )
+            s.ordered_var = 36;
+        else if ( hid == 6 )
+            s.ordered_var /= 2;
+        else if ( hid == 7 )
+            s.ordered_var -= 6;
+        else
+            ctx.output(7, tag(s, s.ordered_var), cycle);
+        return s.ordered_remove != 0;
+    }
+    template <class Ctx>
+    __device__ static uint32_t clockFire(Ctx& ctx, State& s, uint64_t t)
+    {
+        return s.clk.fire(t, [&](int h, uint64_t cycle) { return handler(ctx, s, h, cycle); });
+    }
+    __device__ static uint64_t nextClock(const State& s) { return s.clk.nextTime(); }
+    template <class Ctx>
+    __device__ static bool clockTick(Ctx&, State&, uint64_t)
+    {
+        return true;
+    }
+    __device__ static void initStats(State&) {}
+    __device__ static void mergeStats(State&, const State&) {}
+    __device__ static uint64_t statsVersion(const State&) { return 0; }
+    __device__ static void results(const State& s, uint64_t* r)
+    {
+        r[0] = (uint64_t)(int64_t)s.id_;
+        r[1] = (uint64_t)s.inst_count;
+        r[2] = s.done;
+        r[3] = (uint64_t)(int64_t)s.ordered_var;
+        for ( int i = 0; i < 9; ++i )
+            r[4 + i] = (uint64_t)(int64_t)(i < 4 ? s.counter[i] : TOTAL_COUNT);
+    }
+};
+
 #endif // __CUDACC__
 
 // ---- the registry: what SST_ELI_REGISTER_COMPONENT's static initialisers build in the reference
@@ -683,6 +1017,8 @@ struct ElementInfo
     bool        parallel_events;                  // has an event-parallel handler
     bool        ties_interchangeable;             // events of equal delivery time are interchangeable for the element
     const char* description;
+    bool        prints = false;                   // calls ctx.output(): the engine keeps an output log
+    bool        self_links = false;               // configures self links
 };
 
 } // namespace sstb200

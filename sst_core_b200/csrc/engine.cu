@@ -64,7 +64,7 @@ constexpr uint64_t TIME_NEVER = ~0ull;
 constexpr uint32_t PAR_MAX_EVENTS = MeshElement::PARALLEL_MAX_EVENTS; // events of one component per window in the event-parallel form
 
 enum : uint32_t { ERR_BIN_OVERFLOW = 1, ERR_SMEM_OVERFLOW = 2, ERR_TIME_FAULT = 3, ERR_OUTBOX_OVERFLOW = 4, ERR_TRACE_OVERFLOW = 5,
-                  ERR_PEER_SYNC = 6 };
+                  ERR_PEER_SYNC = 6, ERR_OUTPUT_OVERFLOW = 7, ERR_SELF_QUEUE = 8 };
 enum { CW_PENDING = 0, CW_PRIMARY = 1, CW_CLOCKS = 2, CW_ERROR = 3, CW_EXIT_TIME = 4, CW_WORDS = 8 };
 // exchange slot layout (u64 words): [0] record count, [1..8] the sender's control words (piggy-backed so that one
 // all-to-all per window carries everything), [9] reserved, then capacity x {time, dst_seq, payload, dst_comp}
@@ -96,7 +96,9 @@ struct Ctrl
     // event-parallel form (parallel_form.cuh): blocks of this window left to the sequential form, components whose
     // generator needs maintenance after this window; both reset by advance_kernel
     uint32_t           fb_n, maint_n;
+    unsigned long long out_n; // console-output records written (Dev::out_log)
 };
+static_assert(sizeof(Ctrl) == 240, "Ctrl changed: keep _CTRL in sst_core_b200/checkpoint.py (repartitioned restart) in step");
 
 // Per-component engine control block: everything the dispatch kernel needs about a component besides its element
 // state, in one 32-byte record (two 16-byte loads; only the first half is ever written back).
@@ -151,6 +153,10 @@ struct Dev
     uint32_t*       tr_idx;
     uint64_t*       tr_payload;
     uint64_t        trace_cap;
+    // console output of device components (Output::output, output.cc): records of 8 words
+    // {time, component | code << 32, v0..v4, 0}, in the order the owning threads wrote them
+    unsigned long long* out_log;
+    uint64_t        out_cap;
     int             stats_on, has_payload;
     // handler-count profile tools (profile/eventHandlerProfileTool.cc:108-116, clockHandlerProfileTool.cc:89-97):
     // deliveries per receiving port and clock-handler calls per component; null unless the option is set
@@ -319,8 +325,28 @@ struct CtxT
     Stage           st;
     const uint16_t* seg;
     uint32_t        free_head, free_tail;
+    // elements with self links (SELF_LINKS): end of the window being run and the owning thread's queue of self events
+    // that are due before it; null for every other element
+    uint64_t        T_end  = 0;
+    SelfQueue*      selfq  = nullptr;
 
     __device__ __forceinline__ bool connected(int port) const { return links[port].x != SSTB200_NO_PEER; }
+    // getSimulationOutput().output(...): one record of the output log
+    __device__ __forceinline__ void output(uint32_t code, uint64_t v0, uint64_t v1 = 0, uint64_t v2 = 0, uint64_t v3 = 0,
+        uint64_t v4 = 0)
+    {
+        if ( !d.out_cap ) return;
+        const unsigned long long pos = atomicAdd(&d.ctrl->out_n, 1ull);
+        if ( pos >= d.out_cap ) {
+            raise_error(d, ERR_OUTPUT_OVERFLOW, pos, d.out_cap, comp);
+            return;
+        }
+        ulonglong2* r = reinterpret_cast<ulonglong2*>(d.out_log + pos * 8);
+        r[0]          = make_ulonglong2(now, (unsigned long long)comp | ((unsigned long long)code << 32));
+        r[1]          = make_ulonglong2(v0, v1);
+        r[2]          = make_ulonglong2(v2, v3);
+        r[3]          = make_ulonglong2(v4, 0);
+    }
     // the component's record in memory (what of it is not part of State: MessageMesh route digest)
     __device__ __forceinline__ uint8_t* record() const { return d.state + (uint64_t)(comp - d.c0) * d.state_stride; }
     // Link::send(delay, ev): delivery time = now + delay + latency of the sending end (link.cc:636)
@@ -332,6 +358,28 @@ struct CtxT
         const uint64_t when = now + delay + lat;
         const uint32_t sq   = seq++;
         sent++;
+        if ( selfq != nullptr && l.x == port0 + (uint32_t)port && when < T + d.ctrl->w ) {
+            // a self link, due inside this window: stays with the owning thread, ordered by (time, port, sequence)
+            if ( when >= T_end ) return; // at or after the stop time: never delivered
+            SelfQueue& q = *selfq;
+            if ( q.n >= (uint32_t)SelfQueue::CAP ) {
+                raise_error(d, ERR_SELF_QUEUE, comp, q.n, when);
+                return;
+            }
+            int i = (int)q.n++;
+            while ( i > 0 && (q.time[i - 1] > when || (q.time[i - 1] == when && q.port[i - 1] > l.x)) ) {
+                q.time[i] = q.time[i - 1];
+                q.port[i] = q.port[i - 1];
+                q.seq[i]  = q.seq[i - 1];
+                q.pay[i]  = q.pay[i - 1];
+                --i;
+            }
+            q.time[i] = when;
+            q.port[i] = l.x;
+            q.seq[i]  = sq;
+            q.pay[i]  = payload;
+            return;
+        }
         if ( STAGED ) {
             const uint64_t off = when - T;
             if ( free_head < free_tail && (off >> 32) == 0 ) {
@@ -372,10 +420,27 @@ with_element(uint32_t type, F&& f)
     case TYPE_CORETEST:
         f(CoreTestElement {});
         break;
+    case TYPE_CLOCKER:
+        f(ClockerElement {});
+        break;
     default:
         break;
     }
 }
+
+// optional element traits (absent = false)
+template <class E, class = void>
+struct multi_clock_of : std::false_type
+{};
+template <class E>
+struct multi_clock_of<E, std::void_t<decltype(E::MULTI_CLOCK)>> : std::bool_constant<E::MULTI_CLOCK>
+{};
+template <class E, class = void>
+struct self_links_of : std::false_type
+{};
+template <class E>
+struct self_links_of<E, std::void_t<decltype(E::SELF_LINKS)>> : std::bool_constant<E::SELF_LINKS>
+{};
 
 // EU = the rank's only element type when it has just one (the kernel is then compiled for that element alone: no
 // type switch, registers allocated for one handler), void otherwise
@@ -474,20 +539,21 @@ setup_kernel(Dev d)
     CtxT<false>    ctx { d, 0, 0, 0, d.c0 + lc, p0, d.port_off[lc + 1] - p0, d.aux + (uint64_t)lc * d.aux_stride,
                          0, 0, d.stats_on, d.link + (p0 - d.P0), Stage {}, nullptr, 0, 0 };
     const uint64_t period = d.clock_period[lc];
+    uint64_t       first  = period ? period : TIME_NEVER; // first tick at `period`, never at 0 (clock.cc:400-420)
     with_element(type, [&](auto el) {
         using E = decltype(el);
         typename E::State s;
         E::construct(ctx, s, d.comp_param + (uint64_t)lc * NPARAM);
         E::setup(ctx, s);
+        if constexpr ( multi_clock_of<E>::value ) first = E::nextClock(s); // the constructor registered its clocks
         store_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::PERSIST_BYTES);
     });
-    // first tick at `period`, never at 0 (clock.cc:400-420)
-    d.ctl[lc] = CompCtl { period ? period : TIME_NEVER, ctx.seq, 0, period, type, 0 };
+    d.ctl[lc] = CompCtl { first, ctx.seq, 0, period, type, 0 };
     if ( ctx.sent ) {
         atomicAdd(&d.ctrl->events_sent, (unsigned long long)ctx.sent);
         atomicAdd((unsigned long long*)&d.ctrl->local[CW_PENDING], (unsigned long long)ctx.sent);
     }
-    if ( period ) atomicAdd((unsigned long long*)&d.ctrl->local[CW_CLOCKS], 1ull);
+    if ( first != TIME_NEVER ) atomicAdd((unsigned long long*)&d.ctrl->local[CW_CLOCKS], 1ull);
     atomicAdd((unsigned long long*)&d.ctrl->local[CW_PRIMARY], 1ull); // every in-scope element is a primary component
 }
 
@@ -773,7 +839,8 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
     const bool      valid  = lc < d.n_local;
     const uint32_t  my_cnt = n_due ? s_cnt[c] : 0;
     const uint16_t* seg    = s_ordered + (n_due ? s_off[c] : 0);
-    uint32_t        delivered = 0, ticks = 0, sent = 0, clocks_stopped = 0;
+    uint32_t        delivered = 0, ticks = 0, sent = 0;
+    int32_t         clock_delta = 0; // components whose clocks went quiet (-1) / came back (+1) in this window
     uint4           c_lo = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0), c_hi = make_uint4(0, 0, 0, 0);
     if ( valid && !d.ctl_free ) {
         const uint4* ctlp = reinterpret_cast<const uint4*>(&d.ctl[lc]);
@@ -807,11 +874,34 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
             sort_segment(s_perm + s_off[c], my_cnt, s_time, s_dst, s_sc);
             uint64_t cycle = (next_tick != TIME_NEVER && period) ? next_tick / period : 0;
             uint32_t i     = 0;
+            constexpr bool MC = multi_clock_of<E>::value, SL = self_links_of<E>::value;
+            const bool     had_clock = next_tick != TIME_NEVER;
+            SelfQueue      selfq;
+            if constexpr ( SL ) {
+                selfq.n   = 0;
+                ctx.selfq = &selfq;
+                ctx.T_end = T_end;
+            }
             const uint32_t r_off   = REPORT ? s_misc[1] : 0xFFFFFFFFu;
             const uint64_t R       = T + r_off;
             bool           snapped = r_off == 0xFFFFFFFFu;
             for ( ;; ) {
-                const uint64_t ev_t = (i < my_cnt) ? T + s_time[seg[i]] : TIME_NEVER;
+                uint64_t ev_t      = (i < my_cnt) ? T + s_time[seg[i]] : TIME_NEVER;
+                bool     from_self = false;
+                if constexpr ( SL ) {
+                    // the next event is the earlier of the calendar's and the self queue's, by (time, port, sequence)
+                    if ( selfq.n ) {
+                        const uint64_t st = selfq.time[0];
+                        if ( st < ev_t )
+                            from_self = true;
+                        else if ( st == ev_t ) {
+                            const uint32_t e0 = seg[i];
+                            from_self = selfq.port[0] < s_dst[e0] ||
+                                        (selfq.port[0] == s_dst[e0] && (int32_t)(selfq.seq[0] - s_sc[e0].x) < 0);
+                        }
+                        if ( from_self ) ev_t = st;
+                    }
+                }
                 if ( REPORT && !snapped && ev_t > R && !(next_tick < T_end && next_tick <= R) ) {
                     // everything up to the report time has run: leave the component's state as of now in the snapshot
                     // copy (results_kernel turns it into result records afterwards).  Statistics collected per window
@@ -830,25 +920,45 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
                     snapped = true;
                 }
                 if ( next_tick < T_end && next_tick <= ev_t ) {
-                    ctx.now         = next_tick;
-                    const bool stop = E::clockTick(ctx, s, cycle);
-                    ticks++;
-                    cycle++;
-                    if ( stop ) {
-                        next_tick = TIME_NEVER; // handler unregistered itself (clock.cc:324-367)
-                        clocks_stopped++;
+                    ctx.now = next_tick;
+                    if constexpr ( MC ) {
+                        // every clock of the component due now, each with all its handlers (ClockSet::fire)
+                        ticks += E::clockFire(ctx, s, next_tick);
+                        next_tick = E::nextClock(s);
                     }
-                    else
-                        next_tick += period;
+                    else {
+                        const bool stop = E::clockTick(ctx, s, cycle);
+                        ticks++;
+                        cycle++;
+                        if ( stop )
+                            next_tick = TIME_NEVER; // handler unregistered itself (clock.cc:324-367)
+                        else
+                            next_tick += period;
+                    }
                     continue;
                 }
-                if ( i >= my_cnt ) break;
-                const uint32_t e    = seg[i++];
-                const uint32_t port = s_dst[e] - ctx.port0;
-                uint64_t       pl   = PAYLOAD ? s_pay[e] : 0;
-                s_dst[e]            = SSTB200_NO_PEER; // slot e is consumed: free for out-staging
-                ctx.free_tail       = i;
-                ctx.now             = ev_t;
+                uint32_t port;
+                uint64_t pl;
+                if ( SL && from_self ) {
+                    port = selfq.port[0] - ctx.port0;
+                    pl   = selfq.pay[0];
+                    selfq.n--;
+                    for ( uint32_t j = 0; j < selfq.n; ++j ) {
+                        selfq.time[j] = selfq.time[j + 1];
+                        selfq.port[j] = selfq.port[j + 1];
+                        selfq.seq[j]  = selfq.seq[j + 1];
+                        selfq.pay[j]  = selfq.pay[j + 1];
+                    }
+                }
+                else {
+                    if ( i >= my_cnt ) break;
+                    const uint32_t e = seg[i++];
+                    port             = s_dst[e] - ctx.port0;
+                    pl               = PAYLOAD ? s_pay[e] : 0;
+                    s_dst[e]         = SSTB200_NO_PEER; // slot e is consumed: free for out-staging
+                    ctx.free_tail    = i;
+                }
+                ctx.now = ev_t;
                 if ( d.trace_cap ) {
                     const unsigned long long tp = atomicAdd(&ctrl->trace_n, 1ull);
                     if ( tp < d.trace_cap ) {
@@ -862,7 +972,9 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
                 }
                 E::handleEvent(ctx, s, (int)port, pl);
                 delivered++;
+                if constexpr ( MC ) next_tick = E::nextClock(s); // the handler may have started or stopped a clock
             }
+            clock_delta = (int32_t)(next_tick != TIME_NEVER) - (int32_t)had_clock;
             store_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::STORE_END);
             // statistics: read-modify-write only when the window added data (a clock-driven element may tick a thousand
             // times between two addData calls)
@@ -1001,7 +1113,7 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
     PHASE_MARK(5);
     // ---- phase 5: fold counters (one atomic per warp), recycle the bin
     {
-        uint32_t v0 = delivered, v1 = ticks, v2 = sent, v3 = clocks_stopped, v4 = dropped;
+        uint32_t v0 = delivered, v1 = ticks, v2 = sent, v3 = (uint32_t)clock_delta, v4 = dropped;
 #pragma unroll
         for ( int o = 16; o > 0; o >>= 1 ) {
             v0 += __shfl_down_sync(0xffffffffu, v0, o);
@@ -1016,7 +1128,7 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
             if ( v2 ) atomicAdd(&ctrl->events_sent, (unsigned long long)v2);
             const long long dp = (long long)v2 - (long long)v0 - (long long)v4;
             if ( dp ) atomicAdd((unsigned long long*)&ctrl->local[CW_PENDING], (unsigned long long)dp);
-            if ( v3 ) atomicAdd((unsigned long long*)&ctrl->local[CW_CLOCKS], (unsigned long long)(-(long long)v3));
+            if ( v3 ) atomicAdd((unsigned long long*)&ctrl->local[CW_CLOCKS], (unsigned long long)(long long)(int32_t)v3);
         }
     }
     if ( tid == 0 ) {
@@ -1465,6 +1577,9 @@ static const ElementInfo kElements[] = {
         RngElement::HAS_PAYLOAD, RngElement::PARALLEL_EVENTS, RngElement::TIES_INTERCHANGEABLE, "coreTestRNGComponent: 1 GHz clock drawing from an SST::RNG generator" },
     { TYPE_CORETEST, CoreTestElement::ELI_NAME, CoreTestElement::RECORD_BYTES, CoreTestElement::AUX_BYTES,
         CoreTestElement::HAS_PAYLOAD, CoreTestElement::PARALLEL_EVENTS, CoreTestElement::TIES_INTERCHANGEABLE, "coreTestComponent: clock handler sending to its N/S/E/W neighbours in turn" },
+    { TYPE_CLOCKER, ClockerElement::ELI_NAME, ClockerElement::RECORD_BYTES, ClockerElement::AUX_BYTES,
+        ClockerElement::HAS_PAYLOAD, ClockerElement::PARALLEL_EVENTS, ClockerElement::TIES_INTERCHANGEABLE,
+        "coreTestClockerComponent: ten clock handlers (ordered and unordered) started and stopped over a self link", true, true },
 };
 constexpr int kNumElements = (int)(sizeof(kElements) / sizeof(kElements[0]));
 
@@ -1997,7 +2112,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     scan(scan_hi - scan_lo, [&](size_t lo, size_t hi, unsigned t) {
         uint64_t mn = TIME_NEVER, mx = 0;
         for ( size_t p = scan_lo + lo; p < scan_lo + hi; ++p )
-            if ( m->peer_port[p] != SSTB200_NO_PEER ) {
+            if ( m->peer_port[p] != SSTB200_NO_PEER && !(m->port_self && m->port_self[p]) ) {
                 if ( m->latency[p] < mn ) mn = m->latency[p];
                 if ( m->latency[p] > mx ) mx = m->latency[p];
             }
@@ -2068,6 +2183,13 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         rc |= e->alloc(&d.tr_port, d.trace_cap);
         rc |= e->alloc(&d.tr_idx, d.trace_cap);
         rc |= e->alloc(&d.tr_payload, d.trace_cap);
+    }
+    {
+        bool prints = false;
+        for ( uint32_t ty = 0; ty < TYPE_MAX; ++ty )
+            if ( (seen_local >> ty & 1u) && by_type[ty] && by_type[ty]->prints ) prints = true;
+        d.out_cap = o->output_capacity ? o->output_capacity : (prints ? 65536 : 0);
+        if ( d.out_cap ) rc |= e->alloc(&d.out_log, (size_t)d.out_cap * 8, false);
     }
     if ( o->handler_counts ) {
         rc |= e->alloc(&d.prof_recv, d.nport_local);
@@ -2467,6 +2589,29 @@ sstb200_engine_peer_connect_local(sstb200_engine* e, void* const* regions, const
         peer_layout(d, nbins[r], (uint8_t*)regions[r], r, d);
     d.peer_on    = 1;
     e->peer_spin = false; // the ranks are stepped one after the other on one GPU: nothing to wait for
+    return 0;
+}
+
+int
+sstb200_engine_output(sstb200_engine* e, uint64_t* n_inout, uint64_t* records)
+{
+    if ( !e || !n_inout ) return -1;
+    CUDA_OK(cudaSetDevice(e->device));
+    if ( int rc = e->fetch_ctrl() ) return rc;
+    const uint64_t n = e->h_ctrl->out_n < e->d.out_cap ? e->h_ctrl->out_n : e->d.out_cap;
+    if ( !records ) {
+        *n_inout = n;
+        return 0;
+    }
+    if ( *n_inout < n ) {
+        set_error("engine_output: buffer too small");
+        return -1;
+    }
+    if ( n ) {
+        CUDA_OK(cudaMemcpyAsync(records, e->d.out_log, (size_t)n * 64, cudaMemcpyDeviceToHost, e->stream));
+        CUDA_OK(cudaStreamSynchronize(e->stream));
+    }
+    *n_inout = n;
     return 0;
 }
 

@@ -23,13 +23,13 @@ from typing import Callable, Dict, List, Optional, Tuple
 from .config import ConfigComponent, ModelError
 from .timelord import TimeLord
 
-TYPE_MESH, TYPE_PHOLD, TYPE_CLOCKNODE, TYPE_RNGCOMP, TYPE_CORETEST = 1, 2, 3, 4, 5
+TYPE_MESH, TYPE_PHOLD, TYPE_CLOCKNODE, TYPE_RNGCOMP, TYPE_CORETEST, TYPE_CLOCKER = 1, 2, 3, 4, 5, 6
 NPARAM = 8
 NRESULT = 32
 # words of the result record each element actually fills (the download can stop there)
-RESULT_WORDS = {1: 6, 2: 7, 3: 24, 4: 7, 5: 24}
+RESULT_WORDS = {1: 6, 2: 7, 3: 24, 4: 7, 5: 24, 6: 13}
 # ... and when statistics are disabled (the accumulator words stay zero)
-RESULT_WORDS_NOSTATS = {1: 1, 2: 2, 3: 4, 4: 7, 5: 1}
+RESULT_WORDS_NOSTATS = {1: 1, 2: 2, 3: 4, 4: 7, 5: 1, 6: 13}
 
 
 @dataclass
@@ -49,6 +49,11 @@ class Wired:
     clock_period: int = 0
     stats: List[StatDesc] = field(default_factory=list)
     finish: Optional[Callable] = None  # (result record) -> console line or None
+    # ports the constructor adds with configureSelfLink (baseComponent.cc:374-378), after its configureLink calls: links
+    # from the component to itself, latency 0, delivered after the events of every other port of the same time
+    self_links: List[str] = field(default_factory=list)
+    # (code, a, b) of a console-output record -> the line getSimulationOutput().output() would have printed
+    output_fmt: Optional[Callable] = None
 
 
 def _find_int(c: ConfigComponent, key: str, default=None, required_msg=None) -> int:
@@ -206,12 +211,44 @@ def _wire_rngcomp(c: ConfigComponent, tl: TimeLord) -> Wired:
     return Wired(TYPE_RNGCOMP, [kind, s1, s2, count, verbose, 0, 0, 0], [], tl.cycles("1GHz"), [], None)
 
 
+# ---- coreTestElement.coreTestClockerComponent (testElements/coreTest_ClockerComponent.cc:75-165; tests/test_Clocks.py)
+def _s32(v: int) -> int:
+    v &= 0xFFFFFFFF
+    return v - (1 << 32) if v >= (1 << 31) else v
+
+
+_CLOCKER_FMT = {
+    0: "{i}: starting test sequence at {b}", 1: "{i}: Starting test sequence at {b}",
+    2: "{i}: Clock {x} will restart at cycle {b}", 3: "{i}: Stopping Clock {x} at time {b}",
+    4: "{i}: Terminating test sequence at {b}", 5: "{i}: Clock {x} at cycle {b}",
+    6: "{i}: Self stopping Clock {x} at time {b}", 7: "{i}: ordered clock result = {x} (cycle = {b})",
+}
+
+
+def _clocker_line(code: int, a: int, b: int) -> str:
+    return _CLOCKER_FMT[code].format(i=_s32(a), x=_s32(a >> 32), b=b)
+
+
+def _wire_clocker(c: ConfigComponent, tl: TimeLord) -> Wired:
+    if tl.cycles("1ns") != 1000:
+        raise ModelError("coreTestClockerComponent on the device assumes the default 1 ps time base")
+    user = c.sub_in_slot("user_slot")
+    if not user or user[0].type != "coreTestElement.ClockSubComponent":
+        raise ModelError("coreTestClockerComponent needs a coreTestElement.ClockSubComponent in slot 'user_slot' "
+                         "(the reference dereferences it, coreTest_ClockerComponent.cc:150-153)")
+    have = {p for p, _, _ in c.links}
+    ports = [(c, n) if n in have else (c, None) for n in ("left", "right")]
+    # the clocks are registered by the device constructor (several per component): no single period here
+    return Wired(TYPE_CLOCKER, [0] * NPARAM, ports, 0, [], None, self_links=["inst_link"], output_fmt=_clocker_line)
+
+
 ELEMENTS: Dict[str, Callable[[ConfigComponent, TimeLord], Wired]] = {
     "coreTestElement.message_mesh.enclosing_component": _wire_mesh,
     "pdes.phold": _wire_phold,
     "pdes.clocknode": _wire_clocknode,
     "coreTestElement.coreTestRNGComponent": _wire_rngcomp,
     "coreTestElement.coreTestComponent": _wire_coretest,
+    "coreTestElement.coreTestClockerComponent": _wire_clocker,
 }
 
 TYPE_NAMES = {
@@ -220,4 +257,5 @@ TYPE_NAMES = {
     TYPE_CLOCKNODE: "pdes.clocknode",
     TYPE_RNGCOMP: "coreTestElement.coreTestRNGComponent",
     TYPE_CORETEST: "coreTestElement.coreTestComponent",
+    TYPE_CLOCKER: "coreTestElement.coreTestClockerComponent",
 }

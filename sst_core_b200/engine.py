@@ -30,7 +30,8 @@ class EngineError(RuntimeError):
 class _Model(C.Structure):
     _fields_ = [("ncomp", C.c_uint32), ("comp_type", C.c_void_p), ("comp_param", C.c_void_p),
                 ("port_off", C.c_void_p), ("peer_port", C.c_void_p), ("latency", C.c_void_p),
-                ("clock_period", C.c_void_p), ("stop_at", C.c_uint64), ("stats_enabled", C.c_int)]
+                ("clock_period", C.c_void_p), ("stop_at", C.c_uint64), ("stats_enabled", C.c_int),
+                ("port_self", C.c_void_p), ("xparam_off", C.c_void_p), ("xparam", C.c_void_p)]
 
 
 class _Options(C.Structure):
@@ -62,7 +63,7 @@ EXPORTS = [
     "sstb200_engine_peer_export", "sstb200_engine_peer_connect", "sstb200_engine_peer_connect_local",
     "sstb200_engine_stream",
     "sstb200_peer_region_bytes", "sstb200_peer_arena_create", "sstb200_peer_arena_open", "sstb200_peer_arena_destroy",
-    "sstb200_engine_in_arena", "sstb200_engine_peer_connect_arena",
+    "sstb200_engine_in_arena", "sstb200_engine_peer_connect_arena", "sstb200_engine_output",
 ]
 
 _lib = None
@@ -96,6 +97,7 @@ def lib():
     L.sstb200_engine_peer_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sstb200_engine_peer_connect_local.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sstb200_engine_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.sstb200_engine_output.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
     L.sstb200_peer_region_bytes.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
     L.sstb200_peer_region_bytes.restype = C.c_uint64
     L.sstb200_peer_arena_create.argtypes = [C.c_int, C.c_uint64, C.c_void_p]
@@ -196,7 +198,9 @@ def partition_model(m: WiredModel, n_ranks: int) -> WiredModel:
         stats=[m.stats[i] for i in order] if m.stats else None,
         finish=[m.finish[i] for i in order] if m.finish else None, nocut_pairs=None, stat_output=m.stat_output,
         port_info=[m.port_info[int(i)] for i in old_ids] if m.port_info else None,
-        type_names=[m.type_names[i] for i in order] if m.type_names else None, stat_rate=m.stat_rate)
+        type_names=[m.type_names[i] for i in order] if m.type_names else None, stat_rate=m.stat_rate,
+        port_self=np.ascontiguousarray(m.port_self[old_ids]) if m.port_self is not None else None,
+        output_fmt=[m.output_fmt[i] for i in order] if m.output_fmt else None)
     out.validate()
     return _model_facts(out)
 
@@ -240,6 +244,8 @@ _ERRORS = {
     4: "outbox overflow (raise outbox_capacity): to rank {0}, fill {1}, capacity {2}",
     5: "trace overflow",
     6: "peer mode: the mailbox entry of rank {0} for window sequence {1} did not arrive (found {2})",
+    7: "output log overflow (raise output_capacity): record {0}, capacity {1}, component {2}",
+    8: "self-link queue overflow: component {0} has {1} self events pending inside one window (time {2})",
     0x80000000: "another rank reported an error",
 }
 
@@ -285,7 +291,14 @@ class Engine:
         self.rank, self.n_ranks = rank, n_ranks
         self._keep = [np.ascontiguousarray(a) for a in (model.comp_type, model.comp_param, model.port_off,
                                                         model.peer_port, model.latency, model.clock_period)]
-        cm = _Model(model.ncomp, *[_p(a) for a in self._keep], int(model.stop_at), int(bool(model.stats_enabled)))
+        ps = getattr(model, "port_self", None)
+        self._port_self = np.ascontiguousarray(ps, dtype=np.uint8) if ps is not None else None
+        cm = _Model(model.ncomp, *[_p(a) for a in self._keep], int(model.stop_at), int(bool(model.stats_enabled)),
+                    _p(self._port_self) if self._port_self is not None else None, None, None)
+        xo = getattr(model, "xparam_off", None)
+        if xo is not None:
+            self._xparam = (np.ascontiguousarray(xo, dtype=np.uint32), np.ascontiguousarray(model.xparam, dtype=np.int64))
+            cm.xparam_off, cm.xparam = _p(self._xparam[0]), _p(self._xparam[1])
         if n_ranks > 1:
             if model.rank is None or model.n_ranks != n_ranks:
                 raise EngineError("multi-rank engine needs a model prepared by partition_model(model, n_ranks)")
@@ -390,6 +403,16 @@ class Engine:
         nb = np.ascontiguousarray(nbins, dtype=np.uint32)
         _check(self._L.sstb200_engine_peer_connect_local(self._h, rg, _p(nb)), "engine_peer_connect_local")
         self.peer = "local"
+
+    def output_records(self) -> np.ndarray:
+        """Console-output records of this rank's device components: u64 [n, 8] = {time, component | code << 32,
+        v0..v4, 0}; a component's records appear in the order it printed them."""
+        n = C.c_uint64(0)
+        _check(self._L.sstb200_engine_output(self._h, C.byref(n), None), "engine_output")
+        out = np.zeros((int(n.value), 8), dtype=np.uint64)
+        if n.value:
+            _check(self._L.sstb200_engine_output(self._h, C.byref(n), _p(out)), "engine_output")
+        return out[:int(n.value)]
 
     def stream_handle(self) -> int:
         st = C.c_void_p()

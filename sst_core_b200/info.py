@@ -37,6 +37,11 @@ DOCS = {
         params=[("id", "seeds MarsagliaRNG(11+id, 272727)", "required"), ("commFreq", "send with probability 1/commFreq per tick", "1000"),
                 ("clock", "clock frequency", "1GHz"), ("verbose", "print at finish", "1")],
         ports=["port0..port3 (unconnected ones are skipped)"], stats=["N, S, E, W (i32 accumulators)"]),
+    "coreTestElement.coreTestClockerComponent": dict(
+        params=[],
+        ports=["left", "right", "inst_link (self link, configured by the component)",
+               "subcomponent slot 'user_slot' (coreTestElement.ClockSubComponent, required)"],
+        stats=[]),
 }
 
 

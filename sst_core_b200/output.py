@@ -22,6 +22,21 @@ def _signed(v: int, bits: int) -> int:
     return v - (1 << bits) if v >> (bits - 1) else v
 
 
+def console_lines(m: WiredModel, records: np.ndarray, end_time: int, comp_begin: int = 0) -> List[str]:
+    """Lines device components printed through ctx.output (records u64 [n, 8] of Engine.output_records or the five
+    arrays of the oracle; component ids are engine ids).  Nothing at a later time than the end of the simulation is
+    shown: the engine finishes its last lookahead window, the reference stops right after the Exit time."""
+    if records is None or not m.output_fmt:
+        return []
+    lines = []
+    for r in records:
+        t, comp, code = int(r[0]), int(r[1]) & 0xFFFFFFFF, int(r[1]) >> 32
+        fn = m.output_fmt[comp]
+        if fn is not None and t <= end_time:
+            lines.append(fn(code, int(r[2]), int(r[3])))
+    return lines
+
+
 def finish_lines(m: WiredModel, results: np.ndarray, end_time: int) -> List[str]:
     """results are indexed by engine id; lines are returned in ConfigGraph id order."""
     order = np.argsort(m.orig_id) if m.orig_id is not None else np.arange(m.ncomp)

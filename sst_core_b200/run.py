@@ -89,6 +89,8 @@ def simulate_model(m: wireup.WiredModel, device: int = 0, auto_tune: bool = True
             e.raise_on_error(st)
             if extras is not None and opts.get("handler_counts"):
                 extras["handler_counts"] = e.handler_counts()
+            if extras is not None and m.output_fmt and any(f is not None for f in m.output_fmt):
+                extras["output"] = e.output_records()
             return e.results(result_words(m)), st
         finally:
             e.close()
@@ -265,6 +267,8 @@ def main(argv: Optional[list] = None) -> int:
         if recipe is not None:
             ckpt["checkpoint_writer"] = make_writer(0, 1, m)
         res, st = simulate_model(m, device=a.device, extras=extras, **ckpt, **opts)
+    for line in output.console_lines(m, extras.get("output"), st.end_time):
+        print(line)
     for line in output.finish_lines(m, res, st.end_time):
         print(line)
     if tools:

@@ -71,6 +71,10 @@ class WiredModel:
     port_info: Optional[list] = None
     type_names: Optional[List[str]] = None  # ELI type of every top-level component
     stat_rate: int = 0  # cycles between periodic statistic outputs ("rate" statistic parameter), 0 = only at the end
+    # u8 [nport] or None: 1 = configureSelfLink port (peer_port[p] == p, latency may be 0, delivered after the events of
+    # the component's other ports at equal time; never constrains the lookahead)
+    port_self: Optional[np.ndarray] = None
+    output_fmt: Optional[list] = None  # per component: (code, a, b) -> console line, or None
 
     @property
     def ncomp(self) -> int:
@@ -89,7 +93,10 @@ class WiredModel:
         return self
 
     def min_latency(self) -> int:
-        m = self.latency[self.peer_port != NO_PEER]
+        keep = self.peer_port != NO_PEER
+        if self.port_self is not None:
+            keep &= self.port_self == 0
+        m = self.latency[keep]
         return int(m.min()) if m.size else 0
 
     def validate(self):
@@ -106,8 +113,13 @@ class WiredModel:
             # links are symmetric: my peer's peer is me
             idx = np.nonzero(conn)[0]
             assert np.array_equal(self.peer_port[pp].astype(np.int64), idx), "peer_port is not an involution"
-            if (self.latency[conn] == 0).any():
+            real = conn if self.port_self is None else conn & (self.port_self == 0)
+            if (self.latency[real] == 0).any():
                 raise ModelError("zero-latency links are not allowed (link.cc / configGraph checks)")
+        if self.port_self is not None:
+            assert self.port_self.dtype == np.uint8 and self.port_self.shape == (self.nport,)
+            sp = np.nonzero(self.port_self)[0]
+            assert np.array_equal(self.peer_port[sp].astype(np.int64), sp), "a self-link port must be its own peer"
 
 
 def wire(graph: ConfigGraph, stop_at_override: Optional[str] = None) -> WiredModel:
@@ -123,10 +135,17 @@ def wire(graph: ConfigGraph, stop_at_override: Optional[str] = None) -> WiredMod
     ncomp = len(wired)
     port_off = np.zeros(ncomp + 1, dtype=np.uint32)
     for i, w in enumerate(wired):
-        port_off[i + 1] = port_off[i] + len(w.ports)
+        port_off[i + 1] = port_off[i] + len(w.ports) + len(w.self_links)
     nport = int(port_off[-1])
     peer_port = np.full(nport, NO_PEER, dtype=np.uint32)
     latency = np.zeros(nport, dtype=np.uint64)
+    port_self = None
+    if any(w.self_links for w in wired):
+        port_self = np.zeros(nport, dtype=np.uint8)
+        for i, w in enumerate(wired):
+            for k in range(len(w.self_links)):  # after the configureLink ports: a self link's events sort last
+                p = int(port_off[i]) + len(w.ports) + k
+                peer_port[p], port_self[p] = p, 1
     # (owner ConfigComponent id(), port name) -> directed port id
     where = {}
     for i, w in enumerate(wired):
@@ -195,7 +214,9 @@ def wire(graph: ConfigGraph, stop_at_override: Optional[str] = None) -> WiredMod
         nocut_pairs=np.array(nocut, dtype=np.uint32).reshape(-1, 2),
         stat_output=graph.stat_output,
         port_info=[(owner.full_name(), owner.type, pname) if pname is not None else None
-                   for w in wired for owner, pname in w.ports],
+                   for c, w in zip(graph.components, wired)
+                   for owner, pname in list(w.ports) + [(c, n) for n in w.self_links]],
+        port_self=port_self, output_fmt=[w.output_fmt for w in wired],
         type_names=[c.type for c in graph.components],
         stat_rate=rates.pop() if rates else 0,
     )

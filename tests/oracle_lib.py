@@ -58,6 +58,11 @@ def lib():
         L = C.CDLL(str(ORACLE_SO))
         L.oracle_create.restype = C.c_void_p
         L.oracle_create.argtypes = [C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint64, C.c_int, C.c_int]
+        L.oracle_create2.restype = C.c_void_p
+        L.oracle_create2.argtypes = [C.c_uint32] + [C.c_void_p] * 7 + [C.c_uint64, C.c_int, C.c_int]
+        L.oracle_output_count.restype = C.c_uint64
+        L.oracle_output_count.argtypes = [C.c_void_p]
+        L.oracle_output.argtypes = [C.c_void_p] * 6
         L.oracle_destroy.argtypes = [C.c_void_p]
         L.oracle_run.argtypes = [C.c_void_p]
         L.oracle_results.argtypes = [C.c_void_p, C.c_void_p]
@@ -77,8 +82,9 @@ def _p(a):
 
 
 class OracleRun:
-    def __init__(self, results, events, ticks, end_time, trace=None):
+    def __init__(self, results, events, ticks, end_time, trace=None, output=None):
         self.results, self.events, self.ticks, self.end_time, self.trace = results, events, ticks, end_time, trace
+        self.output = output  # console-output records in serial order: dict(time, comp, code, a, b)
 
 
 def run_model(m, trace=False) -> OracleRun:
@@ -86,7 +92,10 @@ def run_model(m, trace=False) -> OracleRun:
     L = lib()
     arrs = [np.ascontiguousarray(a) for a in
             (m.comp_type, m.comp_param, m.port_off, m.peer_port, m.latency, m.clock_period)]
-    h = L.oracle_create(m.ncomp, *[_p(a) for a in arrs], int(m.stop_at), int(bool(m.stats_enabled)), int(trace))
+    ps = getattr(m, "port_self", None)
+    ps = np.ascontiguousarray(ps, dtype=np.uint8) if ps is not None else None
+    h = L.oracle_create2(m.ncomp, *[_p(a) for a in arrs], _p(ps) if ps is not None else None, int(m.stop_at),
+                         int(bool(m.stats_enabled)), int(trace))
     if not h:
         raise RuntimeError("oracle_create failed (unknown component type)")
     try:
@@ -101,7 +110,12 @@ def run_model(m, trace=False) -> OracleRun:
             tr = dict(time=np.zeros(n, np.uint64), comp=np.zeros(n, np.uint32), port=np.zeros(n, np.uint32),
                       payload=np.zeros(n, np.uint64))
             L.oracle_trace(h, _p(tr["time"]), _p(tr["comp"]), _p(tr["port"]), _p(tr["payload"]))
-        return OracleRun(res, int(cnt[0]), int(cnt[1]), int(cnt[2]), tr)
+        no = int(L.oracle_output_count(h))
+        out = dict(time=np.zeros(no, np.uint64), comp=np.zeros(no, np.uint32), code=np.zeros(no, np.uint32),
+                   a=np.zeros(no, np.uint64), b=np.zeros(no, np.uint64))
+        if no:
+            L.oracle_output(h, *[_p(out[k]) for k in ("time", "comp", "code", "a", "b")])
+        return OracleRun(res, int(cnt[0]), int(cnt[1]), int(cnt[2]), tr, out)
     finally:
         L.oracle_destroy(h)
 

@@ -147,7 +147,7 @@ def test_c_abi_exports_every_declared_symbol():
     L = ctypes.CDLL(str(engine.LIB_PATH))
     for name in declared:
         assert hasattr(L, name), name
-    assert L.sstb200_abi_version() == 1
+    assert L.sstb200_abi_version() == 2
 
 
 def test_native_registry_matches_host_descriptors():
