@@ -198,8 +198,10 @@ struct Accumulator
 
 // ------------------------------------------------------------------------------------------------ engine
 enum : uint64_t { PRIO_STOP = 30, PRIO_CLOCK = 40, PRIO_EVENT = 50, PRIO_EXIT = 99 };
-enum { KIND_EVENT, KIND_CLOCK, KIND_STOP, KIND_EXIT };
-enum { TYPE_MESH = 1, TYPE_PHOLD = 2, TYPE_CLOCKNODE = 3, TYPE_RNGCOMP = 4, TYPE_CORETEST = 5, TYPE_CLOCKER = 6 };
+enum { KIND_EVENT, KIND_CLOCK, KIND_STOP, KIND_EXIT, KIND_STAT };
+constexpr uint64_t PRIO_STATCLOCK = 85; // STATISTICCLOCKPRIORITY activity.h:38
+enum { TYPE_MESH = 1, TYPE_PHOLD = 2, TYPE_CLOCKNODE = 3, TYPE_RNGCOMP = 4, TYPE_CORETEST = 5, TYPE_CLOCKER = 6, TYPE_STATS_INT = 7,
+       TYPE_STATS_FLOAT = 8 };
 constexpr int      NPARAM   = 8;
 constexpr int      NRESULT  = 32;
 constexpr uint32_t NO_PEER  = 0xFFFFFFFFu;
@@ -244,6 +246,9 @@ struct Component
     // Clock::Handler<cls, &cls::fn, int>(this, hid): several handlers per component (coreTest_ClockerComponent.cc);
     // a component with one handler only overrides tick()
     virtual bool clockHandler(int /*hid*/, uint64_t cycle) { return tick(cycle); }
+    // statistics engine activities of this component (priority 85): what = slot | kind << 8
+    virtual void statEvent(uint32_t /*what*/) {}
+    virtual void endOfSimulation() {} // StatisticProcessingEngine::endOfSimulation statengine.cc:296-311
     virtual void results(uint64_t* /*r*/) const {}
     void         send(int port, uint64_t delay, uint64_t payload);
     void         output(uint32_t code, uint64_t a, uint64_t b); // getSimulationOutput().output(...): one log record
@@ -311,6 +316,11 @@ struct Sim
     std::vector<ClockHandler*> all_handlers;
     std::vector<ClockGroup*>   all_groups;
     std::vector<OutRec>      out_log;
+    struct OutExtra
+    {
+        uint64_t c, d, e;
+    };
+    std::vector<OutExtra>    out_extra; // third to fifth value of the records that carry five (statistic outputs)
     uint64_t                 cur_prio = 0; // priority of the activity being executed (Simulation::getCurrentPriority)
     std::priority_queue<Activity, std::vector<Activity>, ActGreater> pq;
     uint64_t                 insert_order = 0;
@@ -529,6 +539,9 @@ struct Sim
             case KIND_CLOCK:
                 executeClock(*clocks[a.target]);
                 break;
+            case KIND_STAT:
+                comps[a.target]->statEvent((uint32_t)a.payload);
+                break;
             case KIND_STOP:
                 end_sim  = true;
                 end_time = now;
@@ -538,6 +551,9 @@ struct Sim
                 break;
             }
         }
+        now = end_time;
+        for ( auto c : comps )
+            c->endOfSimulation();
     }
 };
 
@@ -903,6 +919,243 @@ struct ClockerComp : Component
 
 } // namespace
 
+// ---- statistics with their engine (statapi/statbase.h:393-401 addData, statbase.cc:84-142 collection counts,
+// statengine.cc:107-204 registration: "rate" in time or events, "startat", "stopat", "resetOnOutput"; :346-376,468-505
+// periodic output and what follows an output; :296-311 the output at the end), restated per statistic.  A statistic
+// slot is described by six int64 (the element's extra parameters, see sst_core_b200/elements.py):
+//   [0] flags: 1 exists (not a NullStatistic), 2 resetOnOutput, 4 event-based rate   [1] rate: cycles, or events
+//   [2] startat cycles   [3] stopat cycles   [4] index of the statistic object the slot adds to (shared objects)
+//   [5] unused here (the host's output routing)
+// Output record: code = slot | end_of_sim << 8, then Sum, SumSQ, Count, Min, Max as raw 64-bit patterns.
+enum { ST_EXISTS = 1, ST_CLEAR = 2, ST_EVENT = 4 };
+enum { SE_OUTPUT = 0, SE_START = 1, SE_STOP = 2 };
+template <typename T>
+uint64_t
+bitsOf(T v)
+{
+    if constexpr ( std::is_same<T, float>::value ) {
+        uint32_t u;
+        memcpy(&u, &v, 4);
+        return u;
+    }
+    else if constexpr ( std::is_same<T, double>::value ) {
+        uint64_t u;
+        memcpy(&u, &v, 8);
+        return u;
+    }
+    else
+        return (uint64_t)(int64_t)v;
+}
+struct StatSlotBase
+{
+    Component* comp = nullptr;
+    uint32_t   slot = 0;
+    int64_t    flags = 0, rate = 0, start = 0, stop = 0;
+    bool       registered = false, enabled = true;
+    uint64_t   count = 0, out_count = 0; // current_collection_count_, output_collection_count_
+    virtual ~StatSlotBase() {}
+    virtual void clearData()               = 0;
+    virtual void fields(uint64_t* v) const = 0;
+    void         configure(Component* c, uint32_t s, const int64_t* x)
+    {
+        comp = c, slot = s, flags = x[0], rate = x[1], start = x[2], stop = x[3];
+    }
+    // registerStatisticWithEngine at time `now` (0 in a constructor, later for a statistic registered in a handler)
+    void registerNow()
+    {
+        if ( !(flags & ST_EXISTS) || registered ) return;
+        registered   = true;
+        Sim*     sim = comp->sim;
+        uint64_t now = sim->now;
+        if ( !(flags & ST_EVENT) && rate > 0 ) // the rate's statistic clock: next multiple of the rate (clock.cc:400-420)
+            sim->insert({ (now / (uint64_t)rate + 1) * (uint64_t)rate, PRIO_STATCLOCK << 32, 0, KIND_STAT, comp->id,
+                slot | (SE_OUTPUT << 8) });
+        if ( start > 0 && (uint64_t)start > now ) { // setStatisticStartTime statengine.cc:395-422
+            enabled = false;
+            sim->insert({ (uint64_t)start, PRIO_STATCLOCK << 32, 0, KIND_STAT, comp->id, slot | (SE_START << 8) });
+        }
+        if ( stop > 0 && (uint64_t)stop > now ) // setStatisticStopTime :436-460
+            sim->insert({ (uint64_t)stop, PRIO_STATCLOCK << 32, 0, KIND_STAT, comp->id, slot | (SE_STOP << 8) });
+    }
+    void output(bool end)
+    {
+        uint64_t v[5];
+        fields(v);
+        comp->output(slot | (end ? 0x100u : 0u), 0, 0); // placeholder replaced below
+        OutRec& r = comp->sim->out_log.back();
+        r.a = v[0], r.b = v[1];
+        comp->sim->out_extra.push_back({ v[2], v[3], v[4] });
+        if ( !end ) { // performStatisticOutputImpl statengine.cc:478-491
+            if ( flags & ST_EVENT ) out_count = 0;
+            if ( flags & ST_CLEAR ) {
+                clearData();
+                count = out_count = 0;
+            }
+        }
+    }
+    void event(uint32_t kind)
+    {
+        if ( kind == SE_START )
+            enabled = true;
+        else if ( kind == SE_STOP )
+            enabled = false;
+        else {
+            output(false);
+            comp->sim->insert({ comp->sim->now + (uint64_t)rate, PRIO_STATCLOCK << 32, 0, KIND_STAT, comp->id,
+                slot | (SE_OUTPUT << 8) });
+        }
+    }
+    void counted() // incrementCollectionCount + checkEventForOutput statbase.cc:84-90,134-142
+    {
+        count++;
+        out_count++;
+        if ( (flags & ST_EVENT) && rate >= 1 && out_count >= (uint64_t)rate ) output(false);
+    }
+};
+template <typename T>
+struct StatSlot : StatSlotBase
+{
+    T sum = 0, sumsq = 0, mn = std::numeric_limits<T>::max(), mx = std::numeric_limits<T>::min();
+    void clearData() override
+    {
+        sum = 0, sumsq = 0, mn = std::numeric_limits<T>::max(), mx = std::numeric_limits<T>::min();
+    }
+    void addData(T v)
+    {
+        if ( !registered || !enabled ) return; // NullStatistic / disabled statistic
+        sum += v;
+        sumsq += (v * v);
+        mn = (v < mn) ? v : mn;
+        mx = (v > mx) ? v : mx;
+        counted();
+    }
+    void fields(uint64_t* v) const override
+    {
+        v[0] = bitsOf(sum), v[1] = bitsOf(sumsq), v[2] = count;
+        v[3] = count ? bitsOf(mn) : 0, v[4] = count ? bitsOf(mx) : 0;
+    }
+};
+
+// testElements/coreTest_StatisticsComponent.cc:26-140 StatisticsComponentInt: a 1 ns clock draws u32, u64, i32, i64,
+// scales them and adds them to stat1_U32 .. stat4_I64 (and to stat5_dyn, registered at tick `register_dynamic`)
+struct StatsIntComp : Component
+{
+    Random*           rng;
+    int64_t           rng_count = 0, max_count, dynamic_reg;
+    StatSlot<uint32_t> s1;
+    StatSlot<uint64_t> s2;
+    StatSlot<int32_t>  s3;
+    StatSlot<int64_t>  s4, s5;
+    StatSlotBase*      slots[5];
+    StatsIntComp(const int64_t* p) :
+        rng(makeRng((int)p[0], (uint64_t)p[1], (uint64_t)p[2])), max_count(p[3]), dynamic_reg(p[4])
+    {
+        slots[0] = &s1, slots[1] = &s2, slots[2] = &s3, slots[3] = &s4, slots[4] = &s5;
+    }
+    ~StatsIntComp() { delete rng; }
+    void construct(const int64_t* x, uint32_t nx)
+    {
+        for ( uint32_t i = 0; i < 5; ++i ) {
+            static const int64_t none[6] = { 0, 0, 0, 0, 0, 0 };
+            slots[i]->configure(this, i, i * 6 + 6 <= nx ? x + i * 6 : none);
+            if ( i < 4 ) slots[i]->registerNow();
+        }
+        // (the 1 ns clock comes with the model's clock_period array)
+    }
+    bool tick(uint64_t) override
+    {
+        uint32_t U32 = rng->u32();
+        uint64_t U64 = rng->u64();
+        int32_t  I32 = rng->i32();
+        int64_t  I64 = rng->i64();
+        rng_count++;
+        s1.addData(U32 / 10000000);
+        s2.addData(U64 / 1000000000000000ull);
+        s3.addData(I32 / 10000000);
+        s4.addData(I64 / 1000000000000000ll);
+        s5.addData(I64 / 1000000000000000ll);
+        if ( rng_count == dynamic_reg ) s5.registerNow();
+        if ( rng_count >= max_count ) {
+            sim->primaryOK();
+            return true;
+        }
+        return false;
+    }
+    void statEvent(uint32_t what) override { slots[what & 0xFF]->event(what >> 8); }
+    void endOfSimulation() override
+    {
+        for ( auto* s : slots )
+            if ( s->registered ) s->output(true);
+    }
+    void results(uint64_t* r) const override
+    {
+        r[0] = (uint64_t)rng_count;
+        for ( int i = 0; i < 5; ++i )
+            slots[i]->fields(r + 1 + 5 * i);
+    }
+};
+
+// coreTest_StatisticsComponent.cc:160-260 StatisticsComponentFloat: two nextUniform() per tick; stat1_F32 gets
+// (float)(a * 1000), stat2_F64 gets b * 1000, stat3_F64 gets b * 1000 + 10.  Slots may share a statistic object
+// (createStatistic + setStatistic): slot parameter [4] names the object a slot adds to.
+struct StatsFloatComp : Component
+{
+    Random*          rng;
+    int64_t          rng_count = 0, max_count;
+    StatSlot<float>  s1;
+    StatSlot<double> s2, s3;
+    StatSlotBase*    slots[3];
+    int              target[3] = { 0, 1, 2 };
+    StatsFloatComp(const int64_t* p) : rng(makeRng((int)p[0], (uint64_t)p[1], (uint64_t)p[2])), max_count(p[3])
+    {
+        slots[0] = &s1, slots[1] = &s2, slots[2] = &s3;
+    }
+    ~StatsFloatComp() { delete rng; }
+    void construct(const int64_t* x, uint32_t nx)
+    {
+        for ( uint32_t i = 0; i < 3; ++i ) {
+            static const int64_t none[6] = { 0, 0, 0, 0, 0, 0 };
+            const int64_t*       c       = i * 6 + 6 <= nx ? x + i * 6 : none;
+            target[i]                    = (c[0] & ST_EXISTS) ? (int)c[4] : (int)i;
+            slots[i]->configure(this, i, c);
+            if ( target[i] == (int)i ) slots[i]->registerNow();
+        }
+    }
+    void addD(int slot, double v)
+    {
+        if ( target[slot] == 1 )
+            s2.addData(v);
+        else if ( target[slot] == 2 )
+            s3.addData(v);
+    }
+    bool tick(uint64_t) override
+    {
+        double a = rng->uniform();
+        double b = rng->uniform();
+        rng_count++;
+        s1.addData((float)(a * 1000));
+        addD(1, b * 1000);
+        addD(2, b * 1000 + 10.0);
+        if ( rng_count >= max_count ) {
+            sim->primaryOK();
+            return true;
+        }
+        return false;
+    }
+    void statEvent(uint32_t what) override { slots[what & 0xFF]->event(what >> 8); }
+    void endOfSimulation() override
+    {
+        for ( int i = 0; i < 3; ++i )
+            if ( slots[i]->registered && target[i] == i ) slots[i]->output(true);
+    }
+    void results(uint64_t* r) const override
+    {
+        r[0] = (uint64_t)rng_count;
+        for ( int i = 0; i < 3; ++i )
+            slots[i]->fields(r + 1 + 5 * i);
+    }
+};
+
 // ================================================================================================ C interface
 extern "C" {
 
@@ -912,10 +1165,11 @@ extern "C" {
 // port_self (may be NULL): 1 = a configureSelfLink port (baseComponent.cc:374-378, link.h:512-521): its peer is itself,
 // its latency may be 0 and it keeps order tag 0xFFFFFFFF (Link::setTag link.h:309-319 leaves a SelfLink's tag alone),
 // although the configureLink call still takes the next tag number.
+// xparam_off / xparam (may be NULL): CSR of further int64 construction parameters per component.
 void*
-oracle_create2(uint32_t ncomp, const uint32_t* comp_type, const int64_t* comp_param, const uint32_t* port_off,
+oracle_create3(uint32_t ncomp, const uint32_t* comp_type, const int64_t* comp_param, const uint32_t* port_off,
     const uint32_t* peer_port, const uint64_t* latency, const uint64_t* clock_period, const uint8_t* port_self,
-    uint64_t stop_at, int stats_on, int tracing)
+    const uint32_t* xparam_off, const int64_t* xparam, uint64_t stop_at, int stats_on, int tracing)
 {
     Sim* s      = new Sim();
     s->ncomp    = ncomp;
@@ -952,6 +1206,12 @@ oracle_create2(uint32_t ncomp, const uint32_t* comp_type, const int64_t* comp_pa
         case TYPE_CLOCKER:
             k = new ClockerComp();
             break;
+        case TYPE_STATS_INT:
+            k = new StatsIntComp(p);
+            break;
+        case TYPE_STATS_FLOAT:
+            k = new StatsFloatComp(p);
+            break;
         default:
             delete s;
             return nullptr;
@@ -970,6 +1230,10 @@ oracle_create2(uint32_t ncomp, const uint32_t* comp_type, const int64_t* comp_pa
             if ( port_self && port_self[q] ) s->port_tag[q] = 0xFFFFFFFFu;
         }
         if ( comp_type[c] == TYPE_CLOCKER ) static_cast<ClockerComp*>(k)->construct();
+        const int64_t* xp = xparam_off ? xparam + xparam_off[c] : nullptr;
+        const uint32_t nx = xparam_off ? xparam_off[c + 1] - xparam_off[c] : 0;
+        if ( comp_type[c] == TYPE_STATS_INT ) static_cast<StatsIntComp*>(k)->construct(xp, nx);
+        if ( comp_type[c] == TYPE_STATS_FLOAT ) static_cast<StatsFloatComp*>(k)->construct(xp, nx);
         // every in-scope model registers as primary and says DoNotEndSim in its constructor
         s->primary++;
         if ( clock_period[c] ) s->registerClock(c, clock_period[c]);
@@ -978,12 +1242,37 @@ oracle_create2(uint32_t ncomp, const uint32_t* comp_type, const int64_t* comp_pa
 }
 
 void*
+oracle_create2(uint32_t ncomp, const uint32_t* comp_type, const int64_t* comp_param, const uint32_t* port_off,
+    const uint32_t* peer_port, const uint64_t* latency, const uint64_t* clock_period, const uint8_t* port_self,
+    uint64_t stop_at, int stats_on, int tracing)
+{
+    return oracle_create3(ncomp, comp_type, comp_param, port_off, peer_port, latency, clock_period, port_self, nullptr,
+        nullptr, stop_at, stats_on, tracing);
+}
+void*
 oracle_create(uint32_t ncomp, const uint32_t* comp_type, const int64_t* comp_param, const uint32_t* port_off,
     const uint32_t* peer_port, const uint64_t* latency, const uint64_t* clock_period, uint64_t stop_at, int stats_on,
     int tracing)
 {
     return oracle_create2(ncomp, comp_type, comp_param, port_off, peer_port, latency, clock_period, nullptr, stop_at,
         stats_on, tracing);
+}
+// the third to fifth value of the records that have them, in record order (records with code >= ... carry five values
+// when their component is a statistics element): extra[n_extra][3]
+uint64_t
+oracle_output_extra_count(void* h)
+{
+    return ((Sim*)h)->out_extra.size();
+}
+void
+oracle_output_extra(void* h, uint64_t* extra)
+{
+    Sim* s = (Sim*)h;
+    for ( size_t i = 0; i < s->out_extra.size(); ++i ) {
+        extra[3 * i]     = s->out_extra[i].c;
+        extra[3 * i + 1] = s->out_extra[i].d;
+        extra[3 * i + 2] = s->out_extra[i].e;
+    }
 }
 
 // console-output records (Component::output) in the order the serial run produced them
@@ -1060,6 +1349,9 @@ oracle_run_until(void* h, uint64_t t_end)
         }
         else if ( a.kind == KIND_CLOCK ) {
             s->executeClock(*s->clocks[a.target]);
+        }
+        else if ( a.kind == KIND_STAT ) {
+            s->comps[a.target]->statEvent((uint32_t)a.payload);
         }
     }
     return s->outbox.size() / 4;

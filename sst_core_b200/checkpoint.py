@@ -129,6 +129,7 @@ def run_with_checkpoints(engine, period: int, writer: Optional[CheckpointWriter]
 # (same window slot, block of its destination component) of the rank that owns that component now; counters are summed
 # onto rank 0.  Requires both partitions to keep the model's component numbering (sst.linear over contiguous groups).
 _MAGIC = 0x4330303242545353
+_ABI = 2  # SSTB200_ABI_VERSION of include/sstb200.h: the layout of Ctrl and of the sections below belongs to it
 _HDR = 15
 _CTRL = np.dtype([("k", "<u8"), ("T", "<u8"), ("T_end", "<u8"), ("stop_at", "<u8"), ("w", "<u8"),
                   ("events_delivered", "<u8"), ("clock_ticks", "<u8"), ("events_sent", "<u8"), ("max_bin_fill", "<u8"),
@@ -157,7 +158,7 @@ def _parse_blob(blob: np.ndarray) -> dict:
     order = ["ctrl", "ctl", "state", "aux", "bin_count", "ev"] + (["ev_payload"] if g["has_payload"] else []) + \
             (["outbox", "inbox", "gathered"] if g["n_ranks"] > 1 else [])
     rest = len(secs) - len(order)
-    if rest not in (0, 2) or int(h[1]) != 1:
+    if rest not in (0, 2) or int(h[1]) != _ABI:
         raise ValueError("unexpected checkpoint layout")
     order += ["prof_recv", "prof_clock"] if rest == 2 else []
     return {"abi": int(h[1]), "geom": g, **dict(zip(order, secs))}

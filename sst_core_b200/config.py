@@ -37,7 +37,8 @@ class ConfigComponent:
     """A component or subcomponent node of the graph (model/configComponent.h)."""
 
     __slots__ = ("graph", "id", "name", "type", "params", "links", "subs", "parent", "slot", "slot_num",
-                 "rank", "thread", "weight", "stats_enabled", "stat_params", "stat_load_level")
+                 "rank", "thread", "weight", "stats_enabled", "stat_params", "stat_load_level", "stat_cfg",
+                 "all_stat_params", "stat_objs")
 
     def __init__(self, graph, cid, name, ctype, parent=None, slot=None, slot_num=0):
         self.graph = graph
@@ -56,6 +57,11 @@ class ConfigComponent:
         self.stats_enabled = None  # None | "all" | [names]
         self.stat_params = {}
         self.stat_load_level = None
+        # per statistic (configComponent.cc:285-330 enableStatistic): name -> ConfigStatistic; the enable-all config
+        # (allStatConfig, None = not enabled); statistic objects made with createStatistic
+        self.stat_cfg = {}
+        self.all_stat_params = None
+        self.stat_objs = []
 
     # full name rule: componentInfo.cc:125-144 -- parent:slot, with [n] only when the slot holds several
     def full_name(self) -> str:
@@ -75,6 +81,33 @@ class ConfigComponent:
         return sorted((s for s in self.subs if s.slot == slot), key=lambda s: s.slot_num)
 
 
+class ConfigStatistic:
+    """model/configStatistic.h ConfigStatistic: the parameters one statistic was enabled with; `shared` objects
+    (Component.createStatistic) carry their own name and may be bound to several statistic slots (setStatistic)."""
+
+    def __init__(self, params=None, shared=False, name=None):
+        self.params = dict(params or {})
+        self.shared = shared
+        self.name = name
+
+
+class ConfigStatOutput:
+    def __init__(self, otype, params=None):
+        self.type = str(otype)
+        self.params = {str(k): _param_str(v) for k, v in (params or {}).items()}
+
+
+class ConfigStatGroup:
+    """model/configStatistic.h ConfigStatGroup (python/pymodel_statgroup.cc)"""
+
+    def __init__(self, name):
+        self.name = str(name)
+        self.components = []  # ConfigComponent
+        self.stat_map = {}  # statistic name -> params
+        self.frequency = None
+        self.output = None  # ConfigStatOutput, None = the default output
+
+
 class ConfigGraph:
     def __init__(self):
         self.components = []  # top-level, id order
@@ -84,6 +117,7 @@ class ConfigGraph:
         self.stat_output = ("sst.statOutputConsole", {})
         self.stat_load_level = 0
         self.enable_all_stats = None  # None or params dict
+        self.stat_groups = []
         self.name_prefix = []
         self.comp_by_name = {}
         self.n_ranks = 1
@@ -153,13 +187,29 @@ class _CompBase:
         for c in self._each(recursive):
             c.stats_enabled = "all"
             c.stat_params = dict(params or {})
+            _enable_stat(c, None, params)
 
     def enableStatistics(self, names, params=None, recursive=False):
+        names = [names] if isinstance(names, str) else list(names)
         for c in self._each(recursive):
             if c.stats_enabled != "all":
                 cur = c.stats_enabled if isinstance(c.stats_enabled, list) else []
                 c.stats_enabled = cur + list(names)
             c.stat_params = dict(params or {})
+            for n in names:
+                _enable_stat(c, n, params)
+
+    def createStatistic(self, name, params=None):
+        """pymodel_comp.cc compCreateStatistic: a statistic object with its own name that statistic slots can be bound to"""
+        cs = ConfigStatistic({str(k): _param_str(v) for k, v in (params or {}).items()}, shared=True, name=str(name))
+        self._c.top().stat_objs.append(cs)
+        return cs
+
+    def setStatistic(self, stat_name, stat_obj):
+        """pymodel_comp.cc compSetStatistic / ConfigComponent::reuseStatistic: bind slot `stat_name` to the object"""
+        if not isinstance(stat_obj, ConfigStatistic):
+            raise TypeError("setStatistic requires a statistic object made by createStatistic")
+        self._c.stat_cfg[str(stat_name)] = stat_obj
 
     def enableStatistic(self, name, params=None, recursive=False):
         self.enableStatistics([name], params)
@@ -280,6 +330,58 @@ def setStatisticLoadLevel(level):
     _g().stat_load_level = int(level)
 
 
+def _enable_stat(c: ConfigComponent, name, params):
+    """ConfigComponent::enableStatistic (configComponent.cc:285-330): parameters are merged into what the statistic
+    (or the enable-all entry, name None) already has"""
+    p = {str(k): _param_str(v) for k, v in (params or {}).items()}
+    if name is None:
+        if c.all_stat_params is None:
+            c.all_stat_params = {}
+        c.all_stat_params.update(p)
+    else:
+        c.stat_cfg.setdefault(str(name), ConfigStatistic()).params.update(p)
+
+
+class StatisticOutput:
+    """sst.StatisticOutput(type, params) -- python/pymodel_statgroup.cc"""
+
+    def __init__(self, otype, params=None):
+        self._o = ConfigStatOutput(otype, params)
+
+    def addParam(self, k, v):
+        self._o.params[str(k)] = _param_str(v)
+
+    def addParams(self, d):
+        for k, v in d.items():
+            self.addParam(k, v)
+
+
+class StatisticGroup:
+    """sst.StatisticGroup(name): components x statistics dumped together at one frequency into one output
+    (python/pymodel_statgroup.cc; configGraph.cc:222-233 enables the statistics on the components)"""
+
+    def __init__(self, name):
+        self._g = ConfigStatGroup(name)
+        _g().stat_groups.append(self._g)
+
+    def addStatistic(self, name, params=None):
+        self._g.stat_map[str(name)] = {str(k): _param_str(v) for k, v in (params or {}).items()}
+        if self._g.frequency is None and (params or {}).get("rate"):
+            self._g.frequency = str(params["rate"])
+
+    def addComponent(self, comp):
+        if comp._c not in self._g.components:
+            self._g.components.append(comp._c)
+
+    def setFrequency(self, freq):
+        self._g.frequency = str(freq)
+
+    def setOutput(self, out):
+        if not isinstance(out, StatisticOutput):
+            raise TypeError("setOutput requires an sst.StatisticOutput")
+        self._g.output = out._o
+
+
 _NO_ARG = object()
 
 
@@ -289,6 +391,12 @@ def enableAllStatisticsForAllComponents(params=_NO_ARG):
     if params is not _NO_ARG and not isinstance(params, dict):
         raise TypeError(f"argument 1 must be dict, not {type(params).__name__}")
     _g().enable_all_stats = dict(params) if params is not _NO_ARG else {}
+    # pymodel.cc:559-561: applies to the components that exist NOW, recursively
+    todo = list(_g().components)
+    while todo:
+        c = todo.pop()
+        _enable_stat(c, None, params if params is not _NO_ARG else None)
+        todo += c.subs
 
 
 def enableAllStatisticsForComponentName(name, params=None, recursive=False):
@@ -297,6 +405,7 @@ def enableAllStatisticsForComponentName(name, params=None, recursive=False):
         raise ModelError(f"component name {name} not found")
     c.stats_enabled = "all"
     c.stat_params = dict(params or {})
+    _enable_stat(c, None, params)
 
 
 def enableAllStatisticsForComponentType(ctype, params=None, recursive=False):
@@ -304,6 +413,7 @@ def enableAllStatisticsForComponentType(ctype, params=None, recursive=False):
         if c.type == ctype:
             c.stats_enabled = "all"
             c.stat_params = dict(params or {})
+            _enable_stat(c, None, params)
 
 
 def _named(name):
@@ -320,6 +430,8 @@ def enableStatisticsForComponentName(name, stats, params=None, recursive=False):
     cur = c.stats_enabled if isinstance(c.stats_enabled, list) else []
     c.stats_enabled = cur + names if c.stats_enabled != "all" else "all"
     c.stat_params = dict(params or {})
+    for n in names:
+        _enable_stat(c, n, params)
 
 
 def enableStatisticForComponentName(name, stat, params=None, recursive=False):
@@ -333,6 +445,8 @@ def enableStatisticsForComponentType(ctype, stats, params=None, recursive=False)
             cur = c.stats_enabled if isinstance(c.stats_enabled, list) else []
             c.stats_enabled = cur + names if c.stats_enabled != "all" else "all"
             c.stat_params = dict(params or {})
+            for n in names:
+                _enable_stat(c, n, params)
 
 
 def enableStatisticForComponentType(ctype, stat, params=None, recursive=False):
@@ -401,6 +515,7 @@ _API = [
     "addGlobalParam", "addGlobalParams", "exit", "enableStatisticForComponentName", "enableStatisticsForComponentName",
     "enableStatisticForComponentType", "enableStatisticsForComponentType", "setStatisticLoadLevelForComponentName",
     "setStatisticLoadLevelForComponentType", "getElapsedExecutionTime", "getLocalMemoryUsage", "setCallPythonFinalize",
+    "StatisticGroup", "StatisticOutput",
 ]
 
 

@@ -26,6 +26,11 @@
 //                                                         the component, ctx.send() on them may arrive inside the window
 //   getSimulationOutput().output(fmt, ...)                ->  ctx.output(code, a, b): one record of the engine's output
 //                                                         log; the host half owns the format strings
+//   statistics with an output rate / startat / stopat / resetOnOutput (statengine.cc:107-204,346-505)
+//                                                         ->  STAT_CLOCK = true + EngineStat<T> members: static
+//                                                         nextStatTime(State&) / statFire(Ctx&, State&, time) run the
+//                                                         statistics engine's activities of the component (priority 85:
+//                                                         after the clocks and events of the same time)
 //
 // A handler runs on exactly one thread and is never concurrent with another handler of the same component -- the
 // reference's threading contract.  Components touch no memory but their own State, their aux
@@ -43,7 +48,7 @@
 namespace sstb200 {
 
 enum : uint32_t { TYPE_MESH = 1, TYPE_PHOLD = 2, TYPE_CLOCKNODE = 3, TYPE_RNGCOMP = 4, TYPE_CORETEST = 5, TYPE_CLOCKER = 6,
-                  TYPE_MAX = 7 };
+                  TYPE_STATS_INT = 7, TYPE_STATS_FLOAT = 8, TYPE_MAX = 9 };
 constexpr int NPARAM  = 8;
 constexpr int NRESULT = 32;
 
@@ -277,6 +282,166 @@ struct ClockSet
         return calls;
     }
 };
+
+// ------------------------------------------------------------------------------------------------------------------
+// A statistic under the statistics engine (statapi/statbase.h:393-401 addData; statbase.cc:84-142 collection counts
+// and the event-based output trigger; statengine.cc:107-204 "rate" / "startat" / "stopat" / "resetOnOutput", :346-376
+// and :468-505 periodic output and what follows an output), restated per statistic.  Configuration: six int64 from
+// the component's extra parameters (sst_core_b200/elements.py _stat_slot_params): flags (1 exists, 2 resetOnOutput,
+// 4 event-based), rate (cycles or events), startat, stopat, index of the object the slot adds to, unused.
+// An output is one record of the output log: code = slot | end_of_simulation << 8, values Sum, SumSQ, Count, Min, Max
+// as raw 64-bit patterns (Min / Max 0 while Count is 0, stataccumulator.h:171-194).
+enum : uint32_t { ST_EXISTS = 1, ST_CLEAR = 2, ST_EVENT = 4 };
+#if defined(__CUDACC__)
+template <typename T>
+__device__ __forceinline__ uint64_t
+stat_bits(T v)
+{
+    return (uint64_t)(int64_t)v;
+}
+template <>
+__device__ __forceinline__ uint64_t
+stat_bits<float>(float v)
+{
+    return (uint64_t)__float_as_uint(v);
+}
+template <>
+__device__ __forceinline__ uint64_t
+stat_bits<double>(double v)
+{
+    return (uint64_t)__double_as_longlong(v);
+}
+// sum += v, sumsq += v * v exactly as the host compiler evaluates them: separate, correctly rounded operations (never
+// a fused multiply-add)
+template <typename T>
+__device__ __forceinline__ void
+stat_accumulate(T& sum, T& sumsq, T v)
+{
+    sum += v;
+    sumsq += v * v;
+}
+template <>
+__device__ __forceinline__ void
+stat_accumulate<float>(float& sum, float& sumsq, float v)
+{
+    sum   = __fadd_rn(sum, v);
+    sumsq = __fadd_rn(sumsq, __fmul_rn(v, v));
+}
+template <>
+__device__ __forceinline__ void
+stat_accumulate<double>(double& sum, double& sumsq, double v)
+{
+    sum   = __dadd_rn(sum, v);
+    sumsq = __dadd_rn(sumsq, __dmul_rn(v, v));
+}
+
+struct EngineStatCtl
+{
+    uint64_t rate, start, stop; // configuration
+    uint64_t next_out;          // next periodic output, ~0 = none
+    uint64_t count, out_count;  // current_collection_count_, output_collection_count_
+    uint32_t flags;
+    uint8_t  registered, enabled, start_pending, stop_pending;
+    static constexpr uint64_t NEVER = ~0ull;
+    __device__ void configure(const int64_t* x)
+    {
+        flags = x ? (uint32_t)x[0] : 0;
+        rate  = x ? (uint64_t)x[1] : 0;
+        start = x ? (uint64_t)x[2] : 0;
+        stop  = x ? (uint64_t)x[3] : 0;
+        next_out = NEVER;
+        count = out_count = 0;
+        registered = start_pending = stop_pending = 0;
+        enabled                                   = 1;
+    }
+    // registerStatisticWithEngine at time `now` (0 in a constructor)
+    __device__ void registerNow(uint64_t now)
+    {
+        if ( !(flags & ST_EXISTS) || registered ) return;
+        registered = 1;
+        if ( !(flags & ST_EVENT) && rate > 0 ) next_out = (now / rate + 1) * rate; // the rate's statistic clock
+        if ( start > 0 && start > now ) { // setStatisticStartTime: disabled until then
+            enabled       = 0;
+            start_pending = 1;
+        }
+        if ( stop > 0 && stop > now ) stop_pending = 1;
+    }
+    __device__ uint64_t nextTime() const
+    {
+        uint64_t t = next_out;
+        if ( start_pending && start < t ) t = start;
+        if ( stop_pending && stop < t ) t = stop;
+        return t;
+    }
+};
+template <typename T>
+struct EngineStat
+{
+    EngineStatCtl c;
+    T             sum, sumsq, mn, mx;
+    __device__ void clearData()
+    {
+        sum   = 0;
+        sumsq = 0;
+        mn    = std::numeric_limits<T>::max();
+        mx    = std::numeric_limits<T>::min();
+    }
+    __device__ void configure(const int64_t* x)
+    {
+        c.configure(x);
+        clearData();
+    }
+    __device__ void fields(uint64_t* v) const
+    {
+        v[0] = stat_bits(sum);
+        v[1] = stat_bits(sumsq);
+        v[2] = c.count;
+        v[3] = c.count ? stat_bits(mn) : 0;
+        v[4] = c.count ? stat_bits(mx) : 0;
+    }
+    template <class Ctx>
+    __device__ void output(Ctx& ctx, uint32_t slot)
+    {
+        uint64_t v[5];
+        fields(v);
+        ctx.output(slot, v[0], v[1], v[2], v[3], v[4]);
+        // performStatisticOutputImpl: event-based statistics restart their count, resetOnOutput clears the data
+        if ( c.flags & ST_EVENT ) c.out_count = 0;
+        if ( c.flags & ST_CLEAR ) {
+            clearData();
+            c.count = c.out_count = 0;
+        }
+    }
+    template <class Ctx>
+    __device__ void addData(Ctx& ctx, uint32_t slot, T v)
+    {
+        if ( !c.registered || !c.enabled ) return; // NullStatistic / disabled statistic
+        stat_accumulate(sum, sumsq, v);
+        mn = (v < mn) ? v : mn;
+        mx = (v > mx) ? v : mx;
+        c.count++;
+        c.out_count++;
+        if ( (c.flags & ST_EVENT) && c.rate >= 1 && c.out_count >= c.rate ) output(ctx, slot);
+    }
+    // the statistics engine's activities of this statistic at time t
+    template <class Ctx>
+    __device__ void fire(Ctx& ctx, uint32_t slot, uint64_t t)
+    {
+        if ( c.start_pending && c.start == t ) {
+            c.enabled       = 1;
+            c.start_pending = 0;
+        }
+        if ( c.stop_pending && c.stop == t ) {
+            c.enabled      = 0;
+            c.stop_pending = 0;
+        }
+        if ( c.next_out == t ) {
+            output(ctx, slot);
+            c.next_out = t + c.rate;
+        }
+    }
+};
+#endif
 
 // events a component sent to itself over a self link that are due inside the current window: a small queue in the
 // owning thread, ordered by (time, port, sequence)
@@ -1003,6 +1168,268 @@ struct ClockerElement
     }
 };
 
+// ------------------------------------------------------------------------------------------------------------------
+// coreTestElement.StatisticsComponent.int (testElements/coreTest_StatisticsComponent.cc:26-140; tests/
+// test_StatisticsComponent_basic.py): a 1 ns clock draws u32, u64, i32, i64, scales them and adds them to stat1_U32 ..
+// stat4_I64, and to stat5_dyn once it has been registered (at tick `register_dynamic`).  Result record: [0] rng_count,
+// [1 + 5 i ..] the five fields of statistic i.
+struct StatsIntElement
+{
+    static constexpr uint32_t    TYPE            = TYPE_STATS_INT;
+    static constexpr const char* ELI_NAME        = "coreTestElement.StatisticsComponent.int";
+    static constexpr uint32_t    AUX_BYTES       = MT_N * 4;
+    static constexpr bool        AUX_MT_SEED     = false;
+    static constexpr uint32_t    AUX_SEED_OFFSET = 0;
+    __device__ static uint32_t auxSeed(const int64_t*) { return 0; }
+    static constexpr bool HAS_PAYLOAD = false;
+    static constexpr bool STAT_CLOCK  = true;
+    struct State
+    {
+        int64_t              rng_count, max_count, dynamic_reg;
+        uint32_t             kind, a, b, pad0; // generator: mersenne index in a; marsaglia z, w in a, b
+        EngineStat<uint32_t> s1;
+        EngineStat<uint64_t> s2;
+        EngineStat<int32_t>  s3;
+        EngineStat<int64_t>  s4, s5;
+    };
+    static_assert(sizeof(State) % 16 == 0, "State is moved in 16-byte pieces");
+    static constexpr uint32_t STORE_END = sizeof(State), CONST_END = sizeof(State), STATS_END = sizeof(State);
+    static constexpr bool     TIES_INTERCHANGEABLE = true; // the ports are configured and never used
+    static constexpr bool     STATS_EVERY_EVENT    = false;
+    static constexpr bool     PARALLEL_EVENTS      = false;
+    static constexpr uint32_t PERSIST_BYTES = sizeof(State), RECORD_BYTES = sizeof(State);
+    template <class Ctx>
+    __device__ static void beginWindow(Ctx&, State&, uint32_t)
+    {}
+    __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
+    template <class Ctx>
+    __device__ static void construct(Ctx& ctx, State& s, const int64_t* p)
+    {
+        s.rng_count   = 0;
+        s.max_count   = p[3];
+        s.dynamic_reg = p[4];
+        s.kind        = (uint32_t)p[0];
+        s.a = s.b = s.pad0 = 0;
+        if ( s.kind == 0 )
+            mt_seed((uint32_t*)ctx.aux, (uint32_t)p[1]);
+        else {
+            s.a = (uint32_t)p[1];
+            s.b = (uint32_t)p[2];
+        }
+        const int64_t* x = ctx.xparam;
+        s.s1.configure(ctx.nxparam >= 6 ? x : nullptr);
+        s.s2.configure(ctx.nxparam >= 12 ? x + 6 : nullptr);
+        s.s3.configure(ctx.nxparam >= 18 ? x + 12 : nullptr);
+        s.s4.configure(ctx.nxparam >= 24 ? x + 18 : nullptr);
+        s.s5.configure(ctx.nxparam >= 30 ? x + 24 : nullptr);
+        s.s1.c.registerNow(0);
+        s.s2.c.registerNow(0);
+        s.s3.c.registerNow(0);
+        s.s4.c.registerNow(0);
+    }
+    template <class Ctx>
+    __device__ static void setup(Ctx&, State&)
+    {}
+    template <class Ctx>
+    __device__ static void handleEvent(Ctx&, State&, int, uint64_t&)
+    {}
+    template <class Ctx, class G>
+    __device__ static void draw(Ctx& ctx, State& s, G& g)
+    {
+        const uint32_t U32 = g.u32();
+        const uint64_t U64 = rng_u64(g);
+        const int32_t  I32 = rng_i32(g);
+        const int64_t  I64 = rng_i64(g);
+        s.rng_count++;
+        s.s1.addData(ctx, 0, U32 / 10000000u);
+        s.s2.addData(ctx, 1, U64 / 1000000000000000ull);
+        s.s3.addData(ctx, 2, I32 / 10000000);
+        s.s4.addData(ctx, 3, I64 / 1000000000000000ll);
+        s.s5.addData(ctx, 4, I64 / 1000000000000000ll);
+        if ( s.rng_count == s.dynamic_reg ) s.s5.c.registerNow(ctx.now);
+    }
+    template <class Ctx>
+    __device__ static bool clockTick(Ctx& ctx, State& s, uint64_t)
+    {
+        if ( s.kind == 0 ) {
+            MersenneDev g { (uint32_t*)ctx.aux, s.a };
+            draw(ctx, s, g);
+            s.a = g.idx;
+        }
+        else {
+            MarsagliaDev g { s.a, s.b };
+            draw(ctx, s, g);
+            s.a = g.z;
+            s.b = g.w;
+        }
+        if ( s.rng_count >= s.max_count ) {
+            ctx.primaryComponentOKToEndSim();
+            return true;
+        }
+        return false;
+    }
+    __device__ static uint64_t nextStatTime(const State& s)
+    {
+        uint64_t t = s.s1.c.nextTime();
+        uint64_t u = s.s2.c.nextTime();
+        t          = u < t ? u : t;
+        u          = s.s3.c.nextTime();
+        t          = u < t ? u : t;
+        u          = s.s4.c.nextTime();
+        t          = u < t ? u : t;
+        u          = s.s5.c.nextTime();
+        return u < t ? u : t;
+    }
+    template <class Ctx>
+    __device__ static void statFire(Ctx& ctx, State& s, uint64_t t)
+    {
+        s.s1.fire(ctx, 0, t);
+        s.s2.fire(ctx, 1, t);
+        s.s3.fire(ctx, 2, t);
+        s.s4.fire(ctx, 3, t);
+        s.s5.fire(ctx, 4, t);
+    }
+    __device__ static void initStats(State&) {}
+    __device__ static void mergeStats(State&, const State&) {}
+    __device__ static uint64_t statsVersion(const State&) { return 0; }
+    __device__ static void results(const State& s, uint64_t* r)
+    {
+        r[0] = (uint64_t)s.rng_count;
+        s.s1.fields(r + 1);
+        s.s2.fields(r + 6);
+        s.s3.fields(r + 11);
+        s.s4.fields(r + 16);
+        s.s5.fields(r + 21);
+    }
+};
+
+// coreTestElement.StatisticsComponent.float (coreTest_StatisticsComponent.cc:160-260): two nextUniform() per tick;
+// stat1_F32 gets (float)(a * 1000), stat2_F64 b * 1000, stat3_F64 b * 1000 + 10.  A slot may add to another slot's
+// statistic object (createStatistic + setStatistic: extra parameter [4] of the slot).
+struct StatsFloatElement
+{
+    static constexpr uint32_t    TYPE            = TYPE_STATS_FLOAT;
+    static constexpr const char* ELI_NAME        = "coreTestElement.StatisticsComponent.float";
+    static constexpr uint32_t    AUX_BYTES       = MT_N * 4;
+    static constexpr bool        AUX_MT_SEED     = false;
+    static constexpr uint32_t    AUX_SEED_OFFSET = 0;
+    __device__ static uint32_t auxSeed(const int64_t*) { return 0; }
+    static constexpr bool HAS_PAYLOAD = false;
+    static constexpr bool STAT_CLOCK  = true;
+    struct State
+    {
+        int64_t            rng_count, max_count;
+        uint32_t           kind, a, b, target2, target3, pad0, pad1, pad2;
+        EngineStat<float>  s1;
+        EngineStat<double> s2, s3;
+        uint64_t           pad3;
+    };
+    static_assert(sizeof(State) % 16 == 0, "State is moved in 16-byte pieces");
+    static constexpr uint32_t STORE_END = sizeof(State), CONST_END = sizeof(State), STATS_END = sizeof(State);
+    static constexpr bool     TIES_INTERCHANGEABLE = true;
+    static constexpr bool     STATS_EVERY_EVENT    = false;
+    static constexpr bool     PARALLEL_EVENTS      = false;
+    static constexpr uint32_t PERSIST_BYTES = sizeof(State), RECORD_BYTES = sizeof(State);
+    template <class Ctx>
+    __device__ static void beginWindow(Ctx&, State&, uint32_t)
+    {}
+    __device__ static void prefetch(const uint8_t* state, const uint8_t*) { prefetch_l2(state); }
+    template <class Ctx>
+    __device__ static void construct(Ctx& ctx, State& s, const int64_t* p)
+    {
+        s.rng_count = 0;
+        s.max_count = p[3];
+        s.kind      = (uint32_t)p[0];
+        s.a = s.b = s.pad0 = s.pad1 = s.pad2 = 0;
+        s.pad3                               = 0;
+        if ( s.kind == 0 )
+            mt_seed((uint32_t*)ctx.aux, (uint32_t)p[1]);
+        else {
+            s.a = (uint32_t)p[1];
+            s.b = (uint32_t)p[2];
+        }
+        const int64_t* x = ctx.xparam;
+        s.s1.configure(ctx.nxparam >= 6 ? x : nullptr);
+        s.s2.configure(ctx.nxparam >= 12 ? x + 6 : nullptr);
+        s.s3.configure(ctx.nxparam >= 18 ? x + 12 : nullptr);
+        s.target2 = (ctx.nxparam >= 12 && (x[6] & ST_EXISTS)) ? (uint32_t)x[10] : 1u;
+        s.target3 = (ctx.nxparam >= 18 && (x[12] & ST_EXISTS)) ? (uint32_t)x[16] : 2u;
+        s.s1.c.registerNow(0);
+        if ( s.target2 == 1 ) s.s2.c.registerNow(0);
+        if ( s.target3 == 2 ) s.s3.c.registerNow(0);
+    }
+    template <class Ctx>
+    __device__ static void setup(Ctx&, State&)
+    {}
+    template <class Ctx>
+    __device__ static void handleEvent(Ctx&, State&, int, uint64_t&)
+    {}
+    template <class Ctx>
+    __device__ static void addD(Ctx& ctx, State& s, uint32_t target, double v)
+    {
+        if ( target == 1 )
+            s.s2.addData(ctx, 1, v);
+        else if ( target == 2 )
+            s.s3.addData(ctx, 2, v);
+    }
+    template <class Ctx, class G>
+    __device__ static void draw(Ctx& ctx, State& s, G& g)
+    {
+        const double a = g.uniform();
+        const double b = g.uniform();
+        s.rng_count++;
+        s.s1.addData(ctx, 0, __double2float_rn(__dmul_rn(a, 1000.0)));
+        const double sb = __dmul_rn(b, 1000.0);
+        addD(ctx, s, s.target2, sb);
+        addD(ctx, s, s.target3, __dadd_rn(sb, 10.0));
+    }
+    template <class Ctx>
+    __device__ static bool clockTick(Ctx& ctx, State& s, uint64_t)
+    {
+        if ( s.kind == 0 ) {
+            MersenneDev g { (uint32_t*)ctx.aux, s.a };
+            draw(ctx, s, g);
+            s.a = g.idx;
+        }
+        else {
+            MarsagliaDev g { s.a, s.b };
+            draw(ctx, s, g);
+            s.a = g.z;
+            s.b = g.w;
+        }
+        if ( s.rng_count >= s.max_count ) {
+            ctx.primaryComponentOKToEndSim();
+            return true;
+        }
+        return false;
+    }
+    __device__ static uint64_t nextStatTime(const State& s)
+    {
+        uint64_t t = s.s1.c.nextTime();
+        uint64_t u = s.s2.c.nextTime();
+        t          = u < t ? u : t;
+        u          = s.s3.c.nextTime();
+        return u < t ? u : t;
+    }
+    template <class Ctx>
+    __device__ static void statFire(Ctx& ctx, State& s, uint64_t t)
+    {
+        s.s1.fire(ctx, 0, t);
+        s.s2.fire(ctx, 1, t);
+        s.s3.fire(ctx, 2, t);
+    }
+    __device__ static void initStats(State&) {}
+    __device__ static void mergeStats(State&, const State&) {}
+    __device__ static uint64_t statsVersion(const State&) { return 0; }
+    __device__ static void results(const State& s, uint64_t* r)
+    {
+        r[0] = (uint64_t)s.rng_count;
+        s.s1.fields(r + 1);
+        s.s2.fields(r + 6);
+        s.s3.fields(r + 11);
+    }
+};
+
 #endif // __CUDACC__
 
 // ---- the registry: what SST_ELI_REGISTER_COMPONENT's static initialisers build in the reference
@@ -1019,6 +1446,7 @@ struct ElementInfo
     const char* description;
     bool        prints = false;                   // calls ctx.output(): the engine keeps an output log
     bool        self_links = false;               // configures self links
+    bool        stat_clock = false;               // has statistics under the statistics engine (STAT_CLOCK)
 };
 
 } // namespace sstb200

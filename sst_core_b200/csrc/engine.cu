@@ -134,6 +134,8 @@ struct Dev
     const uint32_t* port_off; // [n_local+1] GLOBAL directed-port ids
     const uint4*    link;     // [nport_local] {dst_port, dst_comp, latency lo, latency hi}
     const uint64_t* clock_period; // [n_local] (setup only)
+    const uint32_t* xparam_off;   // [n_local+1] into xparam (GLOBAL offsets), null when the model has none (setup only)
+    const int64_t*  xparam;       // this rank's slice, starting at xparam_off[0]
     CompCtl*        ctl;          // [n_local] per-component engine control block, 32 B
     uint8_t*        state;
     uint32_t        state_stride;
@@ -329,6 +331,9 @@ struct CtxT
     // that are due before it; null for every other element
     uint64_t        T_end  = 0;
     SelfQueue*      selfq  = nullptr;
+    // constructors only: the component's further construction parameters (sstb200_model.xparam)
+    const int64_t*  xparam  = nullptr;
+    uint32_t        nxparam = 0;
 
     __device__ __forceinline__ bool connected(int port) const { return links[port].x != SSTB200_NO_PEER; }
     // getSimulationOutput().output(...): one record of the output log
@@ -423,6 +428,12 @@ with_element(uint32_t type, F&& f)
     case TYPE_CLOCKER:
         f(ClockerElement {});
         break;
+    case TYPE_STATS_INT:
+        f(StatsIntElement {});
+        break;
+    case TYPE_STATS_FLOAT:
+        f(StatsFloatElement {});
+        break;
     default:
         break;
     }
@@ -434,6 +445,12 @@ struct multi_clock_of : std::false_type
 {};
 template <class E>
 struct multi_clock_of<E, std::void_t<decltype(E::MULTI_CLOCK)>> : std::bool_constant<E::MULTI_CLOCK>
+{};
+template <class E, class = void>
+struct stat_clock_of : std::false_type
+{};
+template <class E>
+struct stat_clock_of<E, std::void_t<decltype(E::STAT_CLOCK)>> : std::bool_constant<E::STAT_CLOCK>
 {};
 template <class E, class = void>
 struct self_links_of : std::false_type
@@ -540,15 +557,21 @@ setup_kernel(Dev d)
                          0, 0, d.stats_on, d.link + (p0 - d.P0), Stage {}, nullptr, 0, 0 };
     const uint64_t period = d.clock_period[lc];
     uint64_t       first  = period ? period : TIME_NEVER; // first tick at `period`, never at 0 (clock.cc:400-420)
+    uint32_t       always = 0;
+    if ( d.xparam_off ) {
+        ctx.xparam  = d.xparam + (d.xparam_off[lc] - d.xparam_off[0]);
+        ctx.nxparam = d.xparam_off[lc + 1] - d.xparam_off[lc];
+    }
     with_element(type, [&](auto el) {
         using E = decltype(el);
         typename E::State s;
+        if constexpr ( stat_clock_of<E>::value ) always = 1; // visited every window: its statistics may be due
         E::construct(ctx, s, d.comp_param + (uint64_t)lc * NPARAM);
         E::setup(ctx, s);
         if constexpr ( multi_clock_of<E>::value ) first = E::nextClock(s); // the constructor registered its clocks
         store_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::PERSIST_BYTES);
     });
-    d.ctl[lc] = CompCtl { first, ctx.seq, 0, period, type, 0 };
+    d.ctl[lc] = CompCtl { first, ctx.seq, 0, period, type, always };
     if ( ctx.sent ) {
         atomicAdd(&d.ctrl->events_sent, (unsigned long long)ctx.sent);
         atomicAdd((unsigned long long*)&d.ctrl->local[CW_PENDING], (unsigned long long)ctx.sent);
@@ -850,7 +873,7 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
     uint64_t       next_tick = ((uint64_t)c_lo.y << 32) | c_lo.x;
     const uint64_t period    = ((uint64_t)c_hi.y << 32) | c_hi.x;
     const uint32_t my_type   = d.uniform_type ? d.uniform_type : c_hi.z;
-    const bool     has_work  = valid && (my_cnt > 0 || next_tick < T_end);
+    const bool     has_work  = valid && (my_cnt > 0 || next_tick < T_end || (c_hi.w & 1u));
     const uint32_t p0        = s_port_off[c];
     const uint4*   my_links  = links_in_smem ? (const uint4*)(s_link + (p0 - blk_port0)) : d.link + (p0 - d.P0);
 
@@ -900,6 +923,15 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
                                         (selfq.port[0] == s_dst[e0] && (int32_t)(selfq.seq[0] - s_sc[e0].x) < 0);
                         }
                         if ( from_self ) ev_t = st;
+                    }
+                }
+                if constexpr ( stat_clock_of<E>::value ) {
+                    // the statistics engine's activities (priority 85): after the clocks and events of the same time
+                    const uint64_t st = E::nextStatTime(s);
+                    if ( st < T_end && st < next_tick && st < ev_t ) {
+                        ctx.now = st;
+                        E::statFire(ctx, s, st);
+                        continue;
                     }
                 }
                 if ( REPORT && !snapped && ev_t > R && !(next_tick < T_end && next_tick <= R) ) {
@@ -1580,6 +1612,12 @@ static const ElementInfo kElements[] = {
     { TYPE_CLOCKER, ClockerElement::ELI_NAME, ClockerElement::RECORD_BYTES, ClockerElement::AUX_BYTES,
         ClockerElement::HAS_PAYLOAD, ClockerElement::PARALLEL_EVENTS, ClockerElement::TIES_INTERCHANGEABLE,
         "coreTestClockerComponent: ten clock handlers (ordered and unordered) started and stopped over a self link", true, true },
+    { TYPE_STATS_INT, StatsIntElement::ELI_NAME, StatsIntElement::RECORD_BYTES, StatsIntElement::AUX_BYTES,
+        StatsIntElement::HAS_PAYLOAD, StatsIntElement::PARALLEL_EVENTS, StatsIntElement::TIES_INTERCHANGEABLE,
+        "StatisticsComponent.int: 1 ns clock feeding five integer accumulators under the statistics engine", true, false, true },
+    { TYPE_STATS_FLOAT, StatsFloatElement::ELI_NAME, StatsFloatElement::RECORD_BYTES, StatsFloatElement::AUX_BYTES,
+        StatsFloatElement::HAS_PAYLOAD, StatsFloatElement::PARALLEL_EVENTS, StatsFloatElement::TIES_INTERCHANGEABLE,
+        "StatisticsComponent.float: 1 ns clock feeding three floating-point accumulators under the statistics engine", true, false, true },
 };
 constexpr int kNumElements = (int)(sizeof(kElements) / sizeof(kElements[0]));
 
@@ -2077,6 +2115,10 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         }
         d.link = link_dev;
         rc |= e->upload(&d.clock_period, m->clock_period + c0, d.n_local);
+        if ( m->xparam_off && m->xparam ) {
+            rc |= e->upload(&d.xparam_off, m->xparam_off + c0, (size_t)d.n_local + 1);
+            rc |= e->upload(&d.xparam, m->xparam + m->xparam_off[c0], (size_t)(m->xparam_off[c1] - m->xparam_off[c0]));
+        }
         if ( n_ranks > 1 ) rc |= e->upload(&d.rank_comp_begin, o->rank_comp_begin, (size_t)n_ranks + 1);
         CUDA_OK(cudaEventRecord(ev_up, e->stream));
         e->stream = main_stream;

@@ -24,12 +24,13 @@ from .config import ConfigComponent, ModelError
 from .timelord import TimeLord
 
 TYPE_MESH, TYPE_PHOLD, TYPE_CLOCKNODE, TYPE_RNGCOMP, TYPE_CORETEST, TYPE_CLOCKER = 1, 2, 3, 4, 5, 6
+TYPE_STATS_INT, TYPE_STATS_FLOAT = 7, 8
 NPARAM = 8
 NRESULT = 32
 # words of the result record each element actually fills (the download can stop there)
-RESULT_WORDS = {1: 6, 2: 7, 3: 24, 4: 7, 5: 24, 6: 13}
+RESULT_WORDS = {1: 6, 2: 7, 3: 24, 4: 7, 5: 24, 6: 13, 7: 26, 8: 16}
 # ... and when statistics are disabled (the accumulator words stay zero)
-RESULT_WORDS_NOSTATS = {1: 1, 2: 2, 3: 4, 4: 7, 5: 1, 6: 13}
+RESULT_WORDS_NOSTATS = {1: 1, 2: 2, 3: 4, 4: 7, 5: 1, 6: 13, 7: 26, 8: 16}
 
 
 @dataclass
@@ -54,6 +55,11 @@ class Wired:
     self_links: List[str] = field(default_factory=list)
     # (code, a, b) of a console-output record -> the line getSimulationOutput().output() would have printed
     output_fmt: Optional[Callable] = None
+    xparams: List[int] = field(default_factory=list)  # further int64 construction parameters (sstb200_model.xparam)
+    # statistics that run under the device statistics engine (rate / startat / stopat / resetOnOutput per statistic):
+    # one StatSlot per slot of the element, None = NullStatistic.  Their outputs arrive as output-log records.
+    stat_slots: Optional[list] = None
+    console: List[str] = field(default_factory=list)  # lines the constructor prints
 
 
 def _find_int(c: ConfigComponent, key: str, default=None, required_msg=None) -> int:
@@ -242,6 +248,128 @@ def _wire_clocker(c: ConfigComponent, tl: TimeLord) -> Wired:
     return Wired(TYPE_CLOCKER, [0] * NPARAM, ports, 0, [], None, self_links=["inst_link"], output_fmt=_clocker_line)
 
 
+# ---- coreTestElement.StatisticsComponent.int / .float (testElements/coreTest_StatisticsComponent.{h,cc};
+# tests/test_StatisticsComponent_basic.py).  Which statistics exist and how they are output is decided here exactly as
+# BaseComponent::registerStatistic_impl (baseComponent.h:756-803) and StatisticProcessingEngine::
+# registerStatisticWithEngine (statengine.cc:107-204) decide it; the device runs the result.
+@dataclass
+class StatSlot:
+    comp_name: str
+    name: str        # statistic name as output (the shared object's name for createStatistic objects)
+    subid: str
+    dtype: str       # u32 u64 i32 i64 f32 f64
+    output: object   # config.ConfigStatOutput or None = the model's default statistic output
+    group: Optional[str]
+    alias_of: Optional[int] = None  # slot whose statistic object this slot adds to (setStatistic on a shared object)
+
+
+_STATS_ELI = {
+    "coreTestElement.StatisticsComponent.int": [("stat1_U32", "1", "u32", 1), ("stat2_U64", "2", "u64", 2),
+                                                ("stat3_I32", "3", "i32", 3), ("stat4_I64", "4", "i64", 4),
+                                                ("stat5_dyn", "", "i64", 1)],
+    "coreTestElement.StatisticsComponent.float": [("stat1_F32", "1", "f32", 1), ("stat2_F64", "2", "f64", 2),
+                                                  ("stat3_F64", "3", "f64", 9)],
+}
+ST_EXISTS, ST_CLEAR, ST_EVENT = 1, 2, 4
+
+
+def _truthy(v) -> bool:
+    return str(v).strip().lower() in ("1", "true", "t", "yes", "y", "on")
+
+
+def _value_unit(text: str):
+    import re
+    m = re.match(r"^\s*([-+]?[0-9]*\.?[0-9]+(?:[eE][-+]?[0-9]+)?)\s*([A-Za-z]*)\s*$", str(text))
+    if not m:
+        raise ModelError(f"cannot parse '{text}' as a number with a unit")
+    return float(m.group(1)), m.group(2).lower()
+
+
+def _stat_slot_params(p: dict, tl: TimeLord, group_freq: Optional[str]):
+    """[flags, rate, startat, stopat] of one statistic from its parameter set (statengine.cc:133-201)"""
+    flags = ST_EXISTS | (ST_CLEAR if _truthy(p.get("resetOnOutput", "0")) else 0)
+    rate = str(p.get("rate", "0ns"))
+    val, unit = _value_unit(rate)
+    if unit not in ("s", "ms", "us", "ns", "ps", "hz", "khz", "mhz", "ghz") and not unit.startswith("event"):
+        raise ModelError(f"Collection Rate = {rate} not valid")
+    if group_freq is not None:  # statistics in a group: periodic at the group's frequency, or only at the end
+        if unit.startswith("event"):
+            raise ModelError("Statistics in groups must be periodic or dump at end, event-based output triggers are not allowed")
+        r = tl.cycles(group_freq) if _value_unit(group_freq)[0] != 0 else 0
+    elif unit.startswith("event"):
+        flags |= ST_EVENT
+        r = int(round(val))
+    else:
+        r = tl.cycles(rate) if val != 0 else 0
+
+    def when(key):
+        v = str(p.get(key, "0ns"))
+        return tl.cycles(v) if v != "0ns" and _value_unit(v)[0] != 0 else 0
+    return [flags, r, when("startat"), when("stopat")]
+
+
+def _wire_stats(c: ConfigComponent, tl: TimeLord) -> Wired:
+    if tl.cycles("1ns") != 1000:
+        raise ModelError("StatisticsComponent on the device assumes the default 1 ps time base")
+    is_int = c.type.endswith(".int")
+    count = _find_int(c, "count", 1000)
+    kind_s = c.params.get("rng", "mersenne")
+    console = []
+    if kind_s == "mersenne":
+        kind, s1, s2 = 0, _find_int(c, "seed", 1447) & 0xFFFFFFFF, 0
+        console.append(f"Using Mersenne Random Number Generator with seed = {s1}")
+    elif kind_s == "marsaglia":
+        w = _find_int(c, "seed_w", 0) & 0xFFFFFFFF
+        z = _find_int(c, "seed_z", 0) & 0xFFFFFFFF
+        if w == 0 or z == 0:
+            raise ModelError("marsaglia generator without seeds is time-seeded in the reference; not reproducible")
+        kind, s1, s2 = 1, z, w
+        console.append(f"Using Marsaglia Random Number Generator with seeds m_z = {z}, m_w = {w}")
+    else:
+        kind, s1, s2 = 0, 1447, 0
+        console.append(f"RNG provided but unknown {kind_s}, so using Mersenne with seed = 1447...")
+    console.append("REGISTER CLOCK #1 at 1 ns")
+    dyn = _find_int(c, "register_dynamic", 0) if is_int else 0
+    g = c.graph
+    level = c.stat_load_level if c.stat_load_level is not None else g.stat_load_level
+    groups = [grp for grp in g.stat_groups if c in grp.components]
+    slots, xp, first_of_obj = [], [], {}
+    for i, (name, subid, dtype, eli_level) in enumerate(_STATS_ELI[c.type]):
+        grp = next((gr for gr in groups if name in gr.stat_map), None)
+        cfg = c.stat_cfg.get(name)
+        params = None
+        if grp is not None:  # configGraph.cc:222-233: the group's statistics are enabled on its components
+            params = dict(cfg.params if cfg is not None else {})
+            params.update(grp.stat_map[name])
+        elif cfg is not None:
+            params = cfg.params
+        elif c.all_stat_params is not None and eli_level <= level:
+            params = c.all_stat_params
+        if params is None:
+            slots.append(None)
+            xp += [0, 0, 0, 0, i, 0]
+            continue
+        stat_type = str(params.get("type", "sst.AccumulatorStatistic"))
+        if stat_type != "sst.AccumulatorStatistic":
+            raise ModelError(f"statistic type {stat_type} is not available on the device (only sst.AccumulatorStatistic)")
+        target = i
+        out_name, out_sub = name, subid
+        if cfg is not None and cfg.shared and grp is None:
+            out_name, out_sub = cfg.name, ""
+            if id(cfg) in first_of_obj:
+                target = first_of_obj[id(cfg)]
+            else:
+                first_of_obj[id(cfg)] = i
+        xp += _stat_slot_params(params, tl, grp.frequency or "0ns" if grp is not None else None) + [target, 0]
+        slots.append(StatSlot(c.full_name(), out_name, out_sub, dtype, grp.output if grp is not None else None,
+                              grp.name if grp is not None else None, alias_of=target if target != i else None))
+    p = [kind, s1, s2, count, dyn, len(slots), 0, 0]
+    have = {q for q, _, _ in c.links}
+    ports = [(c, n) if n in have else (c, None) for n in ("left", "right")]  # configured, never used
+    return Wired(TYPE_STATS_INT if is_int else TYPE_STATS_FLOAT, p, ports, tl.cycles("1ns"), [], None, xparams=xp,
+                 stat_slots=slots, console=console)
+
+
 ELEMENTS: Dict[str, Callable[[ConfigComponent, TimeLord], Wired]] = {
     "coreTestElement.message_mesh.enclosing_component": _wire_mesh,
     "pdes.phold": _wire_phold,
@@ -249,6 +377,8 @@ ELEMENTS: Dict[str, Callable[[ConfigComponent, TimeLord], Wired]] = {
     "coreTestElement.coreTestRNGComponent": _wire_rngcomp,
     "coreTestElement.coreTestComponent": _wire_coretest,
     "coreTestElement.coreTestClockerComponent": _wire_clocker,
+    "coreTestElement.StatisticsComponent.int": _wire_stats,
+    "coreTestElement.StatisticsComponent.float": _wire_stats,
 }
 
 TYPE_NAMES = {
@@ -258,4 +388,6 @@ TYPE_NAMES = {
     TYPE_RNGCOMP: "coreTestElement.coreTestRNGComponent",
     TYPE_CORETEST: "coreTestElement.coreTestComponent",
     TYPE_CLOCKER: "coreTestElement.coreTestClockerComponent",
+    TYPE_STATS_INT: "coreTestElement.StatisticsComponent.int",
+    TYPE_STATS_FLOAT: "coreTestElement.StatisticsComponent.float",
 }

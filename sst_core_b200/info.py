@@ -37,6 +37,18 @@ DOCS = {
         params=[("id", "seeds MarsagliaRNG(11+id, 272727)", "required"), ("commFreq", "send with probability 1/commFreq per tick", "1000"),
                 ("clock", "clock frequency", "1GHz"), ("verbose", "print at finish", "1")],
         ports=["port0..port3 (unconnected ones are skipped)"], stats=["N, S, E, W (i32 accumulators)"]),
+    "coreTestElement.StatisticsComponent.int": dict(
+        params=[("rng", "mersenne | marsaglia", "mersenne"), ("seed", "mersenne seed", "1447"),
+                ("seed_w, seed_z", "marsaglia seeds", "required for marsaglia"), ("count", "ticks to run", "1000"),
+                ("register_dynamic", "tick at which stat5_dyn is registered, 0 = never", "0")],
+        ports=["left", "right (configured, never used)"],
+        stats=["stat1_U32 (level 1)", "stat2_U64 (2)", "stat3_I32 (3)", "stat4_I64 (4)", "stat5_dyn (1, registered at run time)",
+               "statistic parameters: rate (time or events), startat, stopat, resetOnOutput"]),
+    "coreTestElement.StatisticsComponent.float": dict(
+        params=[("rng", "mersenne | marsaglia", "mersenne"), ("seed", "mersenne seed", "1447"),
+                ("seed_w, seed_z", "marsaglia seeds", "required for marsaglia"), ("count", "ticks to run", "1000")],
+        ports=["left", "right (configured, never used)"],
+        stats=["stat1_F32 (level 1)", "stat2_F64 (2)", "stat3_F64 (9)"]),
     "coreTestElement.coreTestClockerComponent": dict(
         params=[],
         ports=["left", "right", "inst_link (self link, configured by the component)",

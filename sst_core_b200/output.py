@@ -13,6 +13,7 @@ from typing import List
 
 import numpy as np
 
+from .config import ModelError
 from .timelord import TimeLord
 from .wireup import WiredModel
 
@@ -35,6 +36,127 @@ def console_lines(m: WiredModel, records: np.ndarray, end_time: int, comp_begin:
         if fn is not None and t <= end_time:
             lines.append(fn(code, int(r[2]), int(r[3])))
     return lines
+
+
+def _stat_values(dtype: str, raw) -> list:
+    """Sum, SumSQ, Count, Min, Max of an output record as the numbers the reference would print"""
+    import struct
+
+    def one(v):
+        v = int(v)
+        if dtype == "u32":
+            return v & 0xFFFFFFFF
+        if dtype == "i32":
+            return _signed(v & 0xFFFFFFFF, 32)
+        if dtype == "i64":
+            return _signed(v, 64)
+        if dtype == "f32":
+            return struct.unpack("<f", struct.pack("<I", v & 0xFFFFFFFF))[0]
+        if dtype == "f64":
+            return struct.unpack("<d", struct.pack("<Q", v))[0]
+        return v
+    return [one(raw[0]), one(raw[1]), int(raw[2]), one(raw[3]), one(raw[4])]
+
+
+def _fmt(dtype: str, v) -> str:
+    return f"{v:f}" if dtype in ("f32", "f64") else str(v)
+
+
+def _flag(params: dict, key: str, default: bool) -> bool:
+    v = params.get(key)
+    return default if v is None else str(v).strip().lower() in ("1", "true", "t", "yes", "y", "on")
+
+
+def stat_engine_outputs(m: WiredModel, records: np.ndarray, end_time: int):
+    """Outputs of the statistics that run under the device statistics engine (elements.StatSlot; records as in
+    console_lines, code = slot | end_of_simulation << 8, values = Sum, SumSQ, Count, Min, Max).  Returns
+    (console lines, {file path: lines}) formatted like statapi/statoutputtxt.cc (console, TXT) and statoutputcsv.cc:
+    the model's default statistic output for ungrouped statistics, each group's own output for the others."""
+    if not m.stat_slots or records is None:
+        return [], {}
+    default = (m.stat_output[0], dict(m.stat_output[1]))
+    outs = {}  # id -> (type, params, [(time, comp, slot, values)])
+
+    def out_of(slot):
+        key = id(slot.output) if slot.output is not None else 0
+        if key not in outs:
+            t, p = (slot.output.type, slot.output.params) if slot.output is not None else default
+            outs[key] = (t.lower(), p, [])
+        return outs[key]
+
+    # field registration order = statistic registration order: components in id order, slots in order
+    order = np.argsort(m.orig_id) if m.orig_id is not None else np.arange(m.ncomp)
+    fields = {}
+    for i in order:
+        for sl in (m.stat_slots[i] or []):
+            if sl is not None and sl.alias_of is None:
+                t, p, _ = out_of(sl)
+                fl = fields.setdefault(id(sl.output) if sl.output is not None else 0, [])
+                for f in (f"Sum.{sl.dtype}", f"SumSQ.{sl.dtype}", "Count.u64", f"Min.{sl.dtype}", f"Max.{sl.dtype}"):
+                    if f not in fl:
+                        fl.append(f)
+    for r in records:
+        t, comp, code = int(r[0]), int(r[1]) & 0xFFFFFFFF, int(r[1]) >> 32
+        slots = m.stat_slots[comp]
+        if not slots or t > end_time:
+            continue
+        sl = slots[code & 0xFF]
+        out_of(sl)[2].append((t, comp, sl, _stat_values(sl.dtype, r[2:7])))
+    console, files = [], {}
+    for key, (otype, params, recs) in outs.items():
+        lines = []
+        if otype in ("sst.statoutputconsole", "sst.statoutputtxt"):
+            is_con = otype.endswith("console")
+            simtime, rank = _flag(params, "outputsimtime", not is_con), _flag(params, "outputrank", not is_con)
+            for t, comp, sl, v in recs:
+                name = f"{sl.comp_name}.{sl.name}" + (f".{sl.subid}" if sl.subid != "" else "")
+                rk = int(m.rank[comp]) if m.rank is not None else 0
+                d = sl.dtype
+                lines.append((" " if is_con else "") + f"{name} : Accumulator : " + (f"SimTime = {t}; " if simtime else "")
+                             + (f"Rank = {rk}; " if rank else "")
+                             + f"Sum.{d} = {_fmt(d, v[0])}; SumSQ.{d} = {_fmt(d, v[1])}; Count.u64 = {v[2]}; "
+                               f"Min.{d} = {_fmt(d, v[3])}; Max.{d} = {_fmt(d, v[4])}; ")
+            if is_con:
+                console += lines
+            else:
+                files.setdefault(params.get("filepath", "StatisticOutput.txt"), []).extend(lines)
+        elif otype == "sst.statoutputcsv":
+            sep = params.get("separator", ", ")
+            simtime, rank = _flag(params, "outputsimtime", True), _flag(params, "outputrank", True)
+            fl = fields.get(key, [])
+            head = ["ComponentName", "StatisticName", "StatisticSubId", "StatisticType"] + (["SimTime"] if simtime else []) \
+                + (["Rank"] if rank else []) + fl
+            lines.append(sep.join(head))
+            for t, comp, sl, v in recs:
+                d = sl.dtype
+                mine = dict(zip((f"Sum.{d}", f"SumSQ.{d}", "Count.u64", f"Min.{d}", f"Max.{d}"),
+                                (_fmt(d, v[0]), _fmt(d, v[1]), str(v[2]), _fmt(d, v[3]), _fmt(d, v[4]))))
+                rk = int(m.rank[comp]) if m.rank is not None else 0
+                lines.append(sep.join([sl.comp_name, sl.name, sl.subid, "Accumulator"] + ([str(t)] if simtime else [])
+                                      + ([str(rk)] if rank else []) + [mine.get(f, "0") for f in fl]))
+            files.setdefault(params.get("filepath", "StatisticOutput.csv"), []).extend(lines)
+        else:
+            raise ModelError(f"statistic output {otype} is not supported for device statistics")
+    return console, files
+
+
+def stat_end_records(m: WiredModel, results: np.ndarray, end_time: int) -> np.ndarray:
+    """The end-of-simulation output of every statistic under the device statistics engine
+    (StatisticProcessingEngine::endOfSimulation statengine.cc:296-311), as output records made from the result records
+    ([0] ticks run, [1 + 5 i ..] the fields of statistic i).  A statistic registered at run time (register_dynamic) only
+    exists once its tick has been reached."""
+    rows = []
+    if m.stat_slots:
+        for c in range(m.ncomp):
+            for i, sl in enumerate(m.stat_slots[c] or []):
+                if sl is None or sl.alias_of is not None:
+                    continue
+                if sl.name == "stat5_dyn":
+                    dyn = int(m.comp_param[c, 4])
+                    if dyn <= 0 or int(results[c, 0]) < dyn:
+                        continue
+                rows.append([end_time, c | ((i | 0x100) << 32)] + [int(v) for v in results[c, 1 + 5 * i:6 + 5 * i]] + [0])
+    return np.array(rows, dtype=np.uint64).reshape(-1, 8)
 
 
 def finish_lines(m: WiredModel, results: np.ndarray, end_time: int) -> List[str]:

@@ -89,7 +89,7 @@ def simulate_model(m: wireup.WiredModel, device: int = 0, auto_tune: bool = True
             e.raise_on_error(st)
             if extras is not None and opts.get("handler_counts"):
                 extras["handler_counts"] = e.handler_counts()
-            if extras is not None and m.output_fmt and any(f is not None for f in m.output_fmt):
+            if extras is not None and ((m.output_fmt and any(f is not None for f in m.output_fmt)) or m.stat_slots):
                 extras["output"] = e.output_records()
             return e.results(result_words(m)), st
         finally:
@@ -267,8 +267,21 @@ def main(argv: Optional[list] = None) -> int:
         if recipe is not None:
             ckpt["checkpoint_writer"] = make_writer(0, 1, m)
         res, st = simulate_model(m, device=a.device, extras=extras, **ckpt, **opts)
+    for lines in (m.construct_console or []):  # what the constructors print (before anything runs)
+        for line in lines:
+            print(line)
     for line in output.console_lines(m, extras.get("output"), st.end_time):
         print(line)
+    if m.stat_slots and extras.get("output") is not None:
+        # statistics under the device statistics engine: periodic / event-triggered outputs from the log, then the
+        # end-of-simulation output of every statistic
+        rec = np.concatenate([extras["output"], output.stat_end_records(m, res, st.end_time)])
+        console, files = output.stat_engine_outputs(m, rec, st.end_time)
+        for line in console:
+            print(line)
+        for path, lines in files.items():
+            with open(os.path.join(a.output_directory, path), "w") as f:
+                f.write("\n".join(lines) + "\n")
     for line in output.finish_lines(m, res, st.end_time):
         print(line)
     if tools:

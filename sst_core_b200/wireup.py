@@ -75,6 +75,10 @@ class WiredModel:
     # the component's other ports at equal time; never constrains the lookahead)
     port_self: Optional[np.ndarray] = None
     output_fmt: Optional[list] = None  # per component: (code, a, b) -> console line, or None
+    xparam_off: Optional[np.ndarray] = None  # u32 [ncomp+1] CSR over xparam, None when no component has any
+    xparam: Optional[np.ndarray] = None      # i64
+    stat_slots: Optional[list] = None        # per component: list of elements.StatSlot / None (device statistics engine)
+    construct_console: Optional[list] = None  # per component: lines its constructor prints
 
     @property
     def ncomp(self) -> int:
@@ -175,8 +179,11 @@ def wire(graph: ConfigGraph, stop_at_override: Optional[str] = None) -> WiredMod
     rates = set()
     if graph.enable_all_stats and graph.enable_all_stats.get("rate"):
         rates.add(str(graph.enable_all_stats["rate"]))
-    for c in graph.components:
-        if c.stat_params.get("rate"):
+    legacy = any(w.stats for w in wired)  # statistics output through the result records (one rate per model)
+    if not legacy:
+        rates.clear()
+    for c, w in zip(graph.components, wired):
+        if w.stats and c.stat_params.get("rate"):
             rates.add(str(c.stat_params["rate"]))
     rates = {tl.cycles(r) for r in rates if r not in ("0", "0ns", "0 ns")}
     if len(rates) > 1:
@@ -217,8 +224,14 @@ def wire(graph: ConfigGraph, stop_at_override: Optional[str] = None) -> WiredMod
                    for c, w in zip(graph.components, wired)
                    for owner, pname in list(w.ports) + [(c, n) for n in w.self_links]],
         port_self=port_self, output_fmt=[w.output_fmt for w in wired],
+        stat_slots=[w.stat_slots for w in wired] if any(w.stat_slots for w in wired) else None,
+        construct_console=[w.console for w in wired] if any(w.console for w in wired) else None,
         type_names=[c.type for c in graph.components],
         stat_rate=rates.pop() if rates else 0,
     )
+    if any(w.xparams for w in wired):
+        m.xparam_off = np.zeros(ncomp + 1, dtype=np.uint32)
+        np.cumsum([len(w.xparams) for w in wired], out=m.xparam_off[1:])
+        m.xparam = np.array([v for w in wired for v in w.xparams], dtype=np.int64)
     m.validate()
     return m

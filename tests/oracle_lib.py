@@ -60,6 +60,11 @@ def lib():
         L.oracle_create.argtypes = [C.c_uint32] + [C.c_void_p] * 6 + [C.c_uint64, C.c_int, C.c_int]
         L.oracle_create2.restype = C.c_void_p
         L.oracle_create2.argtypes = [C.c_uint32] + [C.c_void_p] * 7 + [C.c_uint64, C.c_int, C.c_int]
+        L.oracle_create3.restype = C.c_void_p
+        L.oracle_create3.argtypes = [C.c_uint32] + [C.c_void_p] * 9 + [C.c_uint64, C.c_int, C.c_int]
+        L.oracle_output_extra_count.restype = C.c_uint64
+        L.oracle_output_extra_count.argtypes = [C.c_void_p]
+        L.oracle_output_extra.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_output_count.restype = C.c_uint64
         L.oracle_output_count.argtypes = [C.c_void_p]
         L.oracle_output.argtypes = [C.c_void_p] * 6
@@ -94,7 +99,11 @@ def run_model(m, trace=False) -> OracleRun:
             (m.comp_type, m.comp_param, m.port_off, m.peer_port, m.latency, m.clock_period)]
     ps = getattr(m, "port_self", None)
     ps = np.ascontiguousarray(ps, dtype=np.uint8) if ps is not None else None
-    h = L.oracle_create2(m.ncomp, *[_p(a) for a in arrs], _p(ps) if ps is not None else None, int(m.stop_at),
+    xo = getattr(m, "xparam_off", None)
+    xo = np.ascontiguousarray(xo, dtype=np.uint32) if xo is not None else None
+    xp = np.ascontiguousarray(m.xparam, dtype=np.int64) if xo is not None else None
+    h = L.oracle_create3(m.ncomp, *[_p(a) for a in arrs], _p(ps) if ps is not None else None,
+                         _p(xo) if xo is not None else None, _p(xp) if xo is not None else None, int(m.stop_at),
                          int(bool(m.stats_enabled)), int(trace))
     if not h:
         raise RuntimeError("oracle_create failed (unknown component type)")
@@ -115,6 +124,16 @@ def run_model(m, trace=False) -> OracleRun:
                    a=np.zeros(no, np.uint64), b=np.zeros(no, np.uint64))
         if no:
             L.oracle_output(h, *[_p(out[k]) for k in ("time", "comp", "code", "a", "b")])
+        # statistic outputs carry five values: the last three come separately, in record order
+        ne = int(L.oracle_output_extra_count(h))
+        extra = np.zeros((ne, 3), dtype=np.uint64)
+        if ne:
+            L.oracle_output_extra(h, _p(extra))
+        out["cde"] = np.zeros((no, 3), dtype=np.uint64)
+        if ne:
+            is_stat = np.isin(m.comp_type[out["comp"]], (7, 8))
+            assert int(is_stat.sum()) == ne
+            out["cde"][is_stat] = extra
         return OracleRun(res, int(cnt[0]), int(cnt[1]), int(cnt[2]), tr, out)
     finally:
         L.oracle_destroy(h)

@@ -77,7 +77,7 @@ def test_a_foreign_file_is_not_a_registry(tmp_path):
 
 # ---- repartitioned restart: the blob transformation on synthetic blobs (no engine needed)
 def _synthetic_blob(m, c0, c1, rank, n_ranks, W, cap, ss, as_, rng, has_payload, with_prof, outbox_cap=16):
-    from sst_core_b200.checkpoint import _CTRL, _build_blob, _XHDR
+    from sst_core_b200.checkpoint import _ABI, _CTRL, _build_blob, _XHDR
     n, nb = c1 - c0, max(1, -(-(c1 - c0) // 256))
     po = m.port_off.astype(np.int64)
     ctrl = np.zeros(1, dtype=_CTRL)
@@ -111,7 +111,7 @@ def _synthetic_blob(m, c0, c1, rank, n_ranks, W, cap, ss, as_, rng, has_payload,
     geom = {"n_local": n, "nport_local": int(po[c1] - po[c0]), "c0": c0, "P0": int(po[c0]), "W": W, "cap": cap,
             "state_stride": ss, "aux_stride": as_, "has_payload": int(has_payload), "n_ranks": n_ranks, "rank": rank,
             "window": 1000}
-    return _build_blob(1, geom, secs)
+    return _build_blob(_ABI, geom, secs)
 
 
 def _contents(blobs):

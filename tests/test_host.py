@@ -148,6 +148,8 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert L.sstb200_abi_version() == 2
+    from sst_core_b200 import checkpoint
+    assert checkpoint._ABI == L.sstb200_abi_version()  # the repartitioning code parses blobs of exactly this ABI
 
 
 def test_native_registry_matches_host_descriptors():
