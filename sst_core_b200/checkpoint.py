@@ -134,7 +134,7 @@ _HDR = 15
 _CTRL = np.dtype([("k", "<u8"), ("T", "<u8"), ("T_end", "<u8"), ("stop_at", "<u8"), ("w", "<u8"),
                   ("events_delivered", "<u8"), ("clock_ticks", "<u8"), ("events_sent", "<u8"), ("max_bin_fill", "<u8"),
                   ("max_due", "<u8"), ("end_time", "<u8"), ("done", "<u4"), ("error", "<u4"), ("error_info", "<u8", 4),
-                  ("local", "<i8", 8), ("trace_n", "<u8"), ("windows", "<u8"), ("had_primary", "<u4"), ("pad", "<u4"),
+                  ("local", "<i8", 8), ("trace_n", "<u8"), ("windows", "<u8"), ("had_primary", "<u4"), ("slot", "<u4"),
                   ("report_at", "<u8"), ("fb_n", "<u4"), ("maint_n", "<u4"), ("out_n", "<u8")])
 assert _CTRL.itemsize == 240  # sizeof(Ctrl) in csrc/engine.cu (static_assert there)
 _NEVER = np.uint64(0xFFFFFFFFFFFFFFFF)
@@ -245,7 +245,7 @@ def repartition_checkpoints(blobs, model: WiredModel, new_rank_of_component: np.
         ev[key, within] = rec[sel]
         secs = []
         c = np.zeros(1, dtype=_CTRL)[0]
-        for f in ("k", "T", "T_end", "stop_at", "w", "end_time", "done", "windows", "had_primary"):
+        for f in ("k", "T", "T_end", "stop_at", "w", "end_time", "done", "windows", "had_primary", "slot"):
             c[f] = ctrl_old[0][f]
         c["report_at"] = _NEVER
         c["max_bin_fill"] = max(int(x["max_bin_fill"]) for x in ctrl_old)

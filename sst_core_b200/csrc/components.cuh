@@ -48,7 +48,8 @@
 namespace sstb200 {
 
 enum : uint32_t { TYPE_MESH = 1, TYPE_PHOLD = 2, TYPE_CLOCKNODE = 3, TYPE_RNGCOMP = 4, TYPE_CORETEST = 5, TYPE_CLOCKER = 6,
-                  TYPE_STATS_INT = 7, TYPE_STATS_FLOAT = 8, TYPE_MAX = 9 };
+                  TYPE_STATS_INT = 7, TYPE_STATS_FLOAT = 8,
+                  TYPE_MAX = 32 }; // type codes are bits of 32-bit masks; 16..31 are free for elements compiled in from outside
 constexpr int NPARAM  = 8;
 constexpr int NRESULT = 32;
 
@@ -478,6 +479,8 @@ struct MeshElement
 {
     static constexpr uint32_t    TYPE         = TYPE_MESH;
     static constexpr const char* ELI_NAME     = "coreTestElement.message_mesh.enclosing_component";
+    static constexpr const char* DESCRIPTION = "message_mesh enclosing component with message_port/port_slot/route_message";
+    static constexpr bool OWN_KERNEL = true; // a window kernel compiled for this element alone when a rank holds no other
     static constexpr uint32_t    AUX_BYTES    = 2 * MT_N * 4;
     static constexpr bool        HAS_PAYLOAD  = false;
     // the aux block is a MersenneRNG state the engine seeds warp-cooperatively before construct() (seed_mt_kernel):
@@ -636,6 +639,8 @@ struct PholdElement
 {
     static constexpr uint32_t    TYPE        = TYPE_PHOLD;
     static constexpr const char* ELI_NAME    = "pdes.phold";
+    static constexpr const char* DESCRIPTION = "PHOLD-style node, integer delays, 8-byte payload";
+    static constexpr bool OWN_KERNEL = true; // a window kernel compiled for this element alone when a rank holds no other
     static constexpr uint32_t    AUX_BYTES   = 0;
     static constexpr bool        AUX_MT_SEED = false;
     static constexpr uint32_t    AUX_SEED_OFFSET = 0;
@@ -720,6 +725,8 @@ struct ClockNodeElement
 {
     static constexpr uint32_t    TYPE        = TYPE_CLOCKNODE;
     static constexpr const char* ELI_NAME    = "pdes.clocknode";
+    static constexpr const char* DESCRIPTION = "clock-driven node (coreTestComponent style)";
+    static constexpr bool OWN_KERNEL = true; // a window kernel compiled for this element alone when a rank holds no other
     static constexpr uint32_t    AUX_BYTES   = 0;
     static constexpr bool        AUX_MT_SEED = false;
     static constexpr uint32_t    AUX_SEED_OFFSET = 0;
@@ -812,6 +819,8 @@ struct CoreTestElement
 {
     static constexpr uint32_t    TYPE        = TYPE_CORETEST;
     static constexpr const char* ELI_NAME    = "coreTestElement.coreTestComponent";
+    static constexpr const char* DESCRIPTION = "coreTestComponent: clock handler sending to its N/S/E/W neighbours in turn";
+    static constexpr bool OWN_KERNEL = true; // a window kernel compiled for this element alone when a rank holds no other
     static constexpr uint32_t    AUX_BYTES   = 0;
     static constexpr bool        AUX_MT_SEED = false;
     static constexpr uint32_t    AUX_SEED_OFFSET = 0;
@@ -889,6 +898,7 @@ struct RngElement
 {
     static constexpr uint32_t    TYPE        = TYPE_RNGCOMP;
     static constexpr const char* ELI_NAME    = "coreTestElement.coreTestRNGComponent";
+    static constexpr const char* DESCRIPTION = "coreTestRNGComponent: 1 GHz clock drawing from an SST::RNG generator";
     static constexpr uint32_t    AUX_BYTES   = MT_N * 4;
     static constexpr bool        AUX_MT_SEED = false;
     static constexpr uint32_t    AUX_SEED_OFFSET = 0;
@@ -1009,6 +1019,7 @@ struct ClockerElement
 {
     static constexpr uint32_t    TYPE            = TYPE_CLOCKER;
     static constexpr const char* ELI_NAME        = "coreTestElement.coreTestClockerComponent";
+    static constexpr const char* DESCRIPTION = "coreTestClockerComponent: ten clock handlers (ordered and unordered) started and stopped over a self link";
     static constexpr uint32_t    AUX_BYTES       = 0;
     static constexpr bool        AUX_MT_SEED     = false;
     static constexpr uint32_t    AUX_SEED_OFFSET = 0;
@@ -1016,6 +1027,7 @@ struct ClockerElement
     static constexpr bool HAS_PAYLOAD = true; // IntEvent / OpEvent
     static constexpr bool MULTI_CLOCK = true;
     static constexpr bool SELF_LINKS  = true;
+    static constexpr bool PRINTS      = true; // calls ctx.output
     static constexpr uint64_t MASTER_PERIOD = 5000, TEST_PERIOD = 1000; // "5ns", "1ns" at the 1 ps time base
     static constexpr int      TOTAL_COUNT   = 3;
     enum { OP_NOP, OP_START, OP_STOP, OP_TERM };
@@ -1177,12 +1189,14 @@ struct StatsIntElement
 {
     static constexpr uint32_t    TYPE            = TYPE_STATS_INT;
     static constexpr const char* ELI_NAME        = "coreTestElement.StatisticsComponent.int";
+    static constexpr const char* DESCRIPTION = "StatisticsComponent.int: 1 ns clock feeding five integer accumulators under the statistics engine";
     static constexpr uint32_t    AUX_BYTES       = MT_N * 4;
     static constexpr bool        AUX_MT_SEED     = false;
     static constexpr uint32_t    AUX_SEED_OFFSET = 0;
     __device__ static uint32_t auxSeed(const int64_t*) { return 0; }
     static constexpr bool HAS_PAYLOAD = false;
     static constexpr bool STAT_CLOCK  = true;
+    static constexpr bool PRINTS      = true; // statistic outputs are records of the output log
     struct State
     {
         int64_t              rng_count, max_count, dynamic_reg;
@@ -1310,12 +1324,14 @@ struct StatsFloatElement
 {
     static constexpr uint32_t    TYPE            = TYPE_STATS_FLOAT;
     static constexpr const char* ELI_NAME        = "coreTestElement.StatisticsComponent.float";
+    static constexpr const char* DESCRIPTION = "StatisticsComponent.float: 1 ns clock feeding three floating-point accumulators under the statistics engine";
     static constexpr uint32_t    AUX_BYTES       = MT_N * 4;
     static constexpr bool        AUX_MT_SEED     = false;
     static constexpr uint32_t    AUX_SEED_OFFSET = 0;
     __device__ static uint32_t auxSeed(const int64_t*) { return 0; }
     static constexpr bool HAS_PAYLOAD = false;
     static constexpr bool STAT_CLOCK  = true;
+    static constexpr bool PRINTS      = true; // statistic outputs are records of the output log
     struct State
     {
         int64_t            rng_count, max_count;

@@ -21,6 +21,9 @@
 //          nothing AT the stop time runs (StopAction priority 30 < clock 40 < event 50).
 #include "../../include/sstb200.h"
 #include "components.cuh"
+#ifdef SSTB200_EXTRA_ELEMENTS_HEADER
+#include SSTB200_EXTRA_ELEMENTS_HEADER // an element library compiled in (elements.def)
+#endif
 
 #include <cuda_pipeline.h>
 #include <cuda_runtime.h>
@@ -88,7 +91,7 @@ struct Ctrl
     long long          local[CW_WORDS]; // control words folded across ranks by advance_kernel
     unsigned long long trace_n;
     uint64_t           windows;
-    uint32_t           had_primary, pad;
+    uint32_t           had_primary, slot; // slot = k % W, kept by advance (a 64-bit remainder per thread otherwise)
     // periodic statistic output (statengine.cc:346-376): when report_at lies inside the current window every component
     // leaves its result record as of the END of time report_at (StatisticOutput clocks run at priority 85, after the
     // clock handlers and events of their time) in Dev::snapshot; TIME_NEVER otherwise
@@ -104,7 +107,9 @@ static_assert(sizeof(Ctrl) == 240, "Ctrl changed: keep _CTRL in sst_core_b200/ch
 // state, in one 32-byte record (two 16-byte loads; only the first half is ever written back).
 struct CompCtl
 {
-    uint64_t next_tick; // next clock tick time, TIME_NEVER when the component has no (active) clock
+    uint64_t next_tick; // CYCLE number of the next clock tick (its time = cycle x period: no division on the hot path),
+                        // TIME_NEVER when the component has no (active) clock.  Elements with several clocks
+                        // (MULTI_CLOCK) keep the TIME of their next clock activity here, with period 1
     uint32_t send_seq;  // per-component send sequence (link-FIFO tie-break)
     uint32_t deliv_seq; // deliveries so far (trace index)
     uint64_t period;    // clock period in cycles, 0 = none          -- constant
@@ -117,6 +122,10 @@ struct Dev
 {
     Ctrl*           ctrl;
     uint32_t        n_local, c0, nbins, W, cap, emax;
+    // divisions by the window length and remainders by the slot count without the divide unit: floor(x / w) =
+    // mulhi64(x, w_magic) for x < 2^32 (w_magic = floor((2^64 - 1) / w) + 1); W_mask = W - 1 when W is a power of two
+    uint64_t        w_magic;
+    uint32_t        W_mask, pad_div;
     uint32_t        lmax, uniform_nports; // link rows staged per block; ports per component when uniform (else 0)
     uint32_t        uniform_shift;        // log2(uniform_nports) when it is a power of two, else 32
     uint32_t        uniform_type;         // the element type when every local component has the same one, else 0
@@ -191,6 +200,17 @@ raise_error(const Dev& d, uint32_t code, uint64_t a, uint64_t b, uint64_t c)
     }
 }
 
+__device__ __forceinline__ uint32_t
+div_w(const Dev& d, uint32_t x)
+{
+    return d.w_magic ? (uint32_t)__umul64hi((uint64_t)x, d.w_magic) : x; // w_magic 0: w == 1
+}
+__device__ __forceinline__ uint32_t
+wrap_slot(const Dev& d, uint32_t x) // x mod W for x < 2W - 1 + W
+{
+    return d.W_mask ? (x & d.W_mask) : x % d.W;
+}
+
 // The fused "send": most-significant-digit scatter of the delivery key.  Local destination -> calendar bin of the
 // (window slot, destination block); remote destination -> outbox of the owning rank.
 __device__ __forceinline__ void
@@ -236,12 +256,13 @@ emit(const Dev& d, uint64_t k, uint64_t time, uint32_t dst_port, uint32_t dst_co
         raise_error(d, ERR_TIME_FAULT, time, base, dst_comp);
         return;
     }
-    if ( (dt >> 32) == 0 && (d.ctrl->w >> 32) == 0 )
-        dk = (uint32_t)dt / (uint32_t)d.ctrl->w;
+    if ( (dt >> 32) == 0 )
+        dk = div_w(d, (uint32_t)dt);
     else
         dk = dt / d.ctrl->w;
     if ( dk > d.W - 1 ) dk = d.W - 1; // beyond the calendar horizon: parked in the farthest slot, re-binned there
-    const uint32_t slot = (uint32_t)((k + dk) % d.W);
+    // (k == the window being run when called from a window kernel: its slot is in Ctrl; setup / ingest pass other k)
+    const uint32_t slot = wrap_slot(d, (k == d.ctrl->k ? d.ctrl->slot : (uint32_t)(k % d.W)) + (uint32_t)dk);
     const uint32_t idx  = slot * nb + bin;
     const uint32_t pos  = remote ? atomicAdd_system(&counts[idx], 1u) : atomicAdd(&counts[idx], 1u);
     if ( pos >= d.cap ) {
@@ -410,30 +431,12 @@ __device__ __forceinline__ void
 with_element(uint32_t type, F&& f)
 {
     switch ( type ) {
-    case TYPE_MESH:
-        f(MeshElement {});
+#define SSTB200_ELEMENT(E) \
+    case E::TYPE:          \
+        f(E {});           \
         break;
-    case TYPE_PHOLD:
-        f(PholdElement {});
-        break;
-    case TYPE_CLOCKNODE:
-        f(ClockNodeElement {});
-        break;
-    case TYPE_RNGCOMP:
-        f(RngElement {});
-        break;
-    case TYPE_CORETEST:
-        f(CoreTestElement {});
-        break;
-    case TYPE_CLOCKER:
-        f(ClockerElement {});
-        break;
-    case TYPE_STATS_INT:
-        f(StatsIntElement {});
-        break;
-    case TYPE_STATS_FLOAT:
-        f(StatsFloatElement {});
-        break;
+#include "elements.def"
+#undef SSTB200_ELEMENT
     default:
         break;
     }
@@ -445,6 +448,18 @@ struct multi_clock_of : std::false_type
 {};
 template <class E>
 struct multi_clock_of<E, std::void_t<decltype(E::MULTI_CLOCK)>> : std::bool_constant<E::MULTI_CLOCK>
+{};
+template <class E, class = void>
+struct own_kernel_of : std::false_type
+{};
+template <class E>
+struct own_kernel_of<E, std::void_t<decltype(E::OWN_KERNEL)>> : std::bool_constant<E::OWN_KERNEL>
+{};
+template <class E, class = void>
+struct prints_of : std::false_type
+{};
+template <class E>
+struct prints_of<E, std::void_t<decltype(E::PRINTS)>> : std::bool_constant<E::PRINTS>
 {};
 template <class E, class = void>
 struct stat_clock_of : std::false_type
@@ -556,7 +571,8 @@ setup_kernel(Dev d)
     CtxT<false>    ctx { d, 0, 0, 0, d.c0 + lc, p0, d.port_off[lc + 1] - p0, d.aux + (uint64_t)lc * d.aux_stride,
                          0, 0, d.stats_on, d.link + (p0 - d.P0), Stage {}, nullptr, 0, 0 };
     const uint64_t period = d.clock_period[lc];
-    uint64_t       first  = period ? period : TIME_NEVER; // first tick at `period`, never at 0 (clock.cc:400-420)
+    uint64_t       first  = period ? 1 : TIME_NEVER; // first tick at cycle 1 = time `period`, never at 0 (clock.cc:400-420)
+    uint64_t       period_ctl = period;
     uint32_t       always = 0;
     if ( d.xparam_off ) {
         ctx.xparam  = d.xparam + (d.xparam_off[lc] - d.xparam_off[0]);
@@ -568,10 +584,13 @@ setup_kernel(Dev d)
         if constexpr ( stat_clock_of<E>::value ) always = 1; // visited every window: its statistics may be due
         E::construct(ctx, s, d.comp_param + (uint64_t)lc * NPARAM);
         E::setup(ctx, s);
-        if constexpr ( multi_clock_of<E>::value ) first = E::nextClock(s); // the constructor registered its clocks
+        if constexpr ( multi_clock_of<E>::value ) { // the constructor registered its clocks
+            first      = E::nextClock(s);
+            period_ctl = 1;
+        }
         store_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::PERSIST_BYTES);
     });
-    d.ctl[lc] = CompCtl { first, ctx.seq, 0, period, type, always };
+    d.ctl[lc] = CompCtl { first, ctx.seq, 0, period_ctl, type, always };
     if ( ctx.sent ) {
         atomicAdd(&d.ctrl->events_sent, (unsigned long long)ctx.sent);
         atomicAdd((unsigned long long*)&d.ctrl->local[CW_PENDING], (unsigned long long)ctx.sent);
@@ -667,7 +686,7 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
     const uint64_t T     = ctrl->T;
     const uint64_t T_end = ctrl->T_end;
     const uint32_t w     = (uint32_t)ctrl->w; // < 2^31 (checked by the host)
-    const uint32_t slot  = (uint32_t)(k % d.W);
+    const uint32_t slot  = ctrl->slot;
     const uint32_t slot1 = slot + 1 == d.W ? 0 : slot + 1; // where events due in the next window go
     const uint32_t tid   = threadIdx.x;
     const uint32_t lane  = tid & 31;
@@ -863,6 +882,7 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
     const uint32_t  my_cnt = n_due ? s_cnt[c] : 0;
     const uint16_t* seg    = s_ordered + (n_due ? s_off[c] : 0);
     uint32_t        delivered = 0, ticks = 0, sent = 0;
+    uint64_t        next_store = TIME_NEVER; // what goes back into CompCtl::next_tick
     int32_t         clock_delta = 0; // components whose clocks went quiet (-1) / came back (+1) in this window
     uint4           c_lo = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0), c_hi = make_uint4(0, 0, 0, 0);
     if ( valid && !d.ctl_free ) {
@@ -870,8 +890,9 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
         c_lo              = ctlp[0];
         c_hi              = ctlp[1];
     }
-    uint64_t       next_tick = ((uint64_t)c_lo.y << 32) | c_lo.x;
     const uint64_t period    = ((uint64_t)c_hi.y << 32) | c_hi.x;
+    const uint64_t next_cyc  = ((uint64_t)c_lo.y << 32) | c_lo.x;
+    uint64_t       next_tick = next_cyc == TIME_NEVER ? TIME_NEVER : next_cyc * period;
     const uint32_t my_type   = d.uniform_type ? d.uniform_type : c_hi.z;
     const bool     has_work  = valid && (my_cnt > 0 || next_tick < T_end || (c_hi.w & 1u));
     const uint32_t p0        = s_port_off[c];
@@ -895,7 +916,7 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
             if ( !stats_direct ) E::initStats(s);
             E::beginWindow(ctx, s, my_cnt); // issues the element's first loads (MT19937 read-ahead)
             sort_segment(s_perm + s_off[c], my_cnt, s_time, s_dst, s_sc);
-            uint64_t cycle = (next_tick != TIME_NEVER && period) ? next_tick / period : 0;
+            uint64_t cycle = next_cyc;
             uint32_t i     = 0;
             constexpr bool MC = multi_clock_of<E>::value, SL = self_links_of<E>::value;
             const bool     had_clock = next_tick != TIME_NEVER;
@@ -1007,6 +1028,7 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
                 if constexpr ( MC ) next_tick = E::nextClock(s); // the handler may have started or stopped a clock
             }
             clock_delta = (int32_t)(next_tick != TIME_NEVER) - (int32_t)had_clock;
+            next_store  = (MC || next_tick == TIME_NEVER) ? next_tick : cycle;
             store_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::STORE_END);
             // statistics: read-modify-write only when the window added data (a clock-driven element may tick a thousand
             // times between two addData calls)
@@ -1022,7 +1044,7 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
         });
         if ( !d.ctl_free )
             *reinterpret_cast<uint4*>(&d.ctl[lc]) =
-                make_uint4((uint32_t)next_tick, (uint32_t)(next_tick >> 32), ctx.seq, dseq);
+                make_uint4((uint32_t)next_store, (uint32_t)(next_store >> 32), ctx.seq, dseq);
         sent = ctx.sent;
         if ( d.prof_clock && ticks ) d.prof_clock[lc] += ticks;
     }
@@ -1064,9 +1086,9 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
                 else {
                     uint32_t sl = slot1;
                     if ( dt >= 2 * w ) {
-                        uint32_t dk = dt / w;
+                        uint32_t dk = div_w(d, dt);
                         if ( dk > d.W - 1 ) dk = d.W - 1; // beyond the horizon: parked in the farthest slot
-                        sl = (uint32_t)((slot + dk) % d.W);
+                        sl = wrap_slot(d, slot + dk);
                     }
                     ky = remote ? remote_key(d, dcomp, sl) : sl * d.nbins + (dcomp - d.c0) / BLOCK;
                 }
@@ -1143,7 +1165,9 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
     }
 
     PHASE_MARK(5);
-    // ---- phase 5: fold counters (one atomic per warp), recycle the bin
+    // ---- phase 5: fold counters (warp shuffles, then one value per warp through shared memory: ONE atomic per counter
+    // and CTA -- a clock population runs 65 536 CTAs per window, and every same-address atomic is serialised in L2),
+    // recycle the bin
     {
         uint32_t v0 = delivered, v1 = ticks, v2 = sent, v3 = (uint32_t)clock_delta, v4 = dropped;
 #pragma unroll
@@ -1154,7 +1178,26 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
             v3 += __shfl_down_sync(0xffffffffu, v3, o);
             v4 += __shfl_down_sync(0xffffffffu, v4, o);
         }
+        uint32_t* s_red = s_hist; // [5][BLOCK/32]: phase-2 scratch (s_hist + s_hbase, 64 words) is dead by now
         if ( lane == 0 ) {
+            const uint32_t wp = tid >> 5;
+            s_red[0 * (BLOCK / 32) + wp] = v0;
+            s_red[1 * (BLOCK / 32) + wp] = v1;
+            s_red[2 * (BLOCK / 32) + wp] = v2;
+            s_red[3 * (BLOCK / 32) + wp] = v3;
+            s_red[4 * (BLOCK / 32) + wp] = v4;
+        }
+        __syncthreads();
+        if ( tid == 0 ) {
+            v0 = v1 = v2 = v3 = v4 = 0;
+#pragma unroll
+            for ( int wp = 0; wp < BLOCK / 32; ++wp ) {
+                v0 += s_red[0 * (BLOCK / 32) + wp];
+                v1 += s_red[1 * (BLOCK / 32) + wp];
+                v2 += s_red[2 * (BLOCK / 32) + wp];
+                v3 += s_red[3 * (BLOCK / 32) + wp];
+                v4 += s_red[4 * (BLOCK / 32) + wp];
+            }
             if ( v0 ) atomicAdd(&ctrl->events_delivered, (unsigned long long)v0);
             if ( v1 ) atomicAdd(&ctrl->clock_ticks, (unsigned long long)v1);
             if ( v2 ) atomicAdd(&ctrl->events_sent, (unsigned long long)v2);
@@ -1294,6 +1337,7 @@ advance_fold(const Dev& d)
         return;
     }
     c->k     = c->k + 1;
+    c->slot  = (uint32_t)(c->k % d.W);
     c->T     = next_T;
     c->T_end = (c->stop_at && next_T + c->w > c->stop_at) ? c->stop_at : next_T + c->w;
 }
@@ -1598,26 +1642,18 @@ rng_dist_kernel(int dist, const double* params, int np, int kind, uint64_t s1, u
 }
 
 // ================================================================================================ host side
+template <class E>
+constexpr ElementInfo
+element_info()
+{
+    static_assert(E::TYPE > 0 && E::TYPE < TYPE_MAX, "element type codes are 1..31");
+    return ElementInfo { E::TYPE, E::ELI_NAME, E::RECORD_BYTES, E::AUX_BYTES, E::HAS_PAYLOAD, E::PARALLEL_EVENTS,
+        E::TIES_INTERCHANGEABLE, E::DESCRIPTION, prints_of<E>::value, self_links_of<E>::value, stat_clock_of<E>::value };
+}
 static const ElementInfo kElements[] = {
-    { TYPE_MESH, MeshElement::ELI_NAME, MeshElement::RECORD_BYTES, MeshElement::AUX_BYTES,
-        MeshElement::HAS_PAYLOAD, MeshElement::PARALLEL_EVENTS, MeshElement::TIES_INTERCHANGEABLE, "message_mesh enclosing component with message_port/port_slot/route_message" },
-    { TYPE_PHOLD, PholdElement::ELI_NAME, PholdElement::RECORD_BYTES, PholdElement::AUX_BYTES,
-        PholdElement::HAS_PAYLOAD, PholdElement::PARALLEL_EVENTS, PholdElement::TIES_INTERCHANGEABLE, "PHOLD-style node, integer delays, 8-byte payload" },
-    { TYPE_CLOCKNODE, ClockNodeElement::ELI_NAME, ClockNodeElement::RECORD_BYTES,
-        ClockNodeElement::AUX_BYTES, ClockNodeElement::HAS_PAYLOAD, ClockNodeElement::PARALLEL_EVENTS, ClockNodeElement::TIES_INTERCHANGEABLE, "clock-driven node (coreTestComponent style)" },
-    { TYPE_RNGCOMP, RngElement::ELI_NAME, RngElement::RECORD_BYTES, RngElement::AUX_BYTES,
-        RngElement::HAS_PAYLOAD, RngElement::PARALLEL_EVENTS, RngElement::TIES_INTERCHANGEABLE, "coreTestRNGComponent: 1 GHz clock drawing from an SST::RNG generator" },
-    { TYPE_CORETEST, CoreTestElement::ELI_NAME, CoreTestElement::RECORD_BYTES, CoreTestElement::AUX_BYTES,
-        CoreTestElement::HAS_PAYLOAD, CoreTestElement::PARALLEL_EVENTS, CoreTestElement::TIES_INTERCHANGEABLE, "coreTestComponent: clock handler sending to its N/S/E/W neighbours in turn" },
-    { TYPE_CLOCKER, ClockerElement::ELI_NAME, ClockerElement::RECORD_BYTES, ClockerElement::AUX_BYTES,
-        ClockerElement::HAS_PAYLOAD, ClockerElement::PARALLEL_EVENTS, ClockerElement::TIES_INTERCHANGEABLE,
-        "coreTestClockerComponent: ten clock handlers (ordered and unordered) started and stopped over a self link", true, true },
-    { TYPE_STATS_INT, StatsIntElement::ELI_NAME, StatsIntElement::RECORD_BYTES, StatsIntElement::AUX_BYTES,
-        StatsIntElement::HAS_PAYLOAD, StatsIntElement::PARALLEL_EVENTS, StatsIntElement::TIES_INTERCHANGEABLE,
-        "StatisticsComponent.int: 1 ns clock feeding five integer accumulators under the statistics engine", true, false, true },
-    { TYPE_STATS_FLOAT, StatsFloatElement::ELI_NAME, StatsFloatElement::RECORD_BYTES, StatsFloatElement::AUX_BYTES,
-        StatsFloatElement::HAS_PAYLOAD, StatsFloatElement::PARALLEL_EVENTS, StatsFloatElement::TIES_INTERCHANGEABLE,
-        "StatisticsComponent.float: 1 ns clock feeding three floating-point accumulators under the statistics engine", true, false, true },
+#define SSTB200_ELEMENT(E) element_info<E>(),
+#include "elements.def"
+#undef SSTB200_ELEMENT
 };
 constexpr int kNumElements = (int)(sizeof(kElements) / sizeof(kElements[0]));
 
@@ -1715,15 +1751,19 @@ struct sstb200_engine
         else {
             // one element type on the rank and the model's payload setting is that element's own: the kernel compiled
             // for that element alone; else the kernel that switches on the type of every component
-            const uint32_t ut = d.uniform_type;
-            if ( ut == TYPE_PHOLD && d.has_payload == (int)PholdElement::HAS_PAYLOAD )
-                dispatch_kernel<PholdElement::HAS_PAYLOAD, false, PholdElement><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
-            else if ( ut == TYPE_CLOCKNODE && d.has_payload == (int)ClockNodeElement::HAS_PAYLOAD )
-                dispatch_kernel<ClockNodeElement::HAS_PAYLOAD, false, ClockNodeElement><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
-            else if ( ut == TYPE_MESH && d.has_payload == (int)MeshElement::HAS_PAYLOAD )
-                dispatch_kernel<MeshElement::HAS_PAYLOAD, false, MeshElement><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
-            else if ( ut == TYPE_CORETEST && d.has_payload == (int)CoreTestElement::HAS_PAYLOAD )
-                dispatch_kernel<CoreTestElement::HAS_PAYLOAD, false, CoreTestElement><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
+            const uint32_t ut       = d.uniform_type;
+            bool           launched = false;
+#define SSTB200_ELEMENT(E)                                                                                       \
+    if constexpr ( own_kernel_of<E>::value ) {                                                                   \
+        if ( !launched && ut == E::TYPE && d.has_payload == (int)E::HAS_PAYLOAD ) {                               \
+            dispatch_kernel<E::HAS_PAYLOAD, false, E><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);                \
+            launched = true;                                                                                     \
+        }                                                                                                        \
+    }
+#include "elements.def"
+#undef SSTB200_ELEMENT
+            if ( launched ) {
+            }
             else if ( d.has_payload )
                 dispatch_kernel<true><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
             else
@@ -2274,6 +2314,8 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     CUDA_OK(cudaMallocHost((void**)&e->h_ctrl, sizeof(Ctrl)));
     memset(e->h_ctrl, 0, sizeof(Ctrl));
     e->h_ctrl->w       = w;
+    d.w_magic          = w == 1 ? 0 : ~0ull / w + 1; // ceil(2^64 / w): exact quotients for 32-bit dividends
+    d.W_mask           = (d.W & (d.W - 1)) == 0 ? d.W - 1 : 0;
     e->h_ctrl->stop_at = m->stop_at;
     e->h_ctrl->k       = 0;
     e->h_ctrl->T       = 0;
@@ -2294,11 +2336,13 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<PholdElement::HAS_PAYLOAD, false, PholdElement>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<ClockNodeElement::HAS_PAYLOAD, false, ClockNodeElement>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<MeshElement::HAS_PAYLOAD, false, MeshElement>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define SSTB200_ELEMENT(E)                                                                                       \
+    if constexpr ( own_kernel_of<E>::value )                                                                     \
+        CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<E::HAS_PAYLOAD, false, E>,                                  \
+            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#include "elements.def"
+#undef SSTB200_ELEMENT
     CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<false, false, MeshElement, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_OK(cudaFuncSetAttribute(dispatch_kernel<CoreTestElement::HAS_PAYLOAD, false, CoreTestElement>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int n_sm = 148;
     CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, o->device));
     e->maint_grid = (uint32_t)n_sm * 8;

@@ -91,7 +91,7 @@ window_parallel_kernel(Dev d)
     const uint64_t     T     = ctrl->T;
     const uint64_t     T_end = ctrl->T_end;
     const uint32_t     w     = (uint32_t)ctrl->w;
-    const uint32_t     slot  = (uint32_t)(k % d.W);
+    const uint32_t     slot  = ctrl->slot;
     const uint32_t     slot1 = slot + 1 == d.W ? 0 : slot + 1;
     const uint32_t     tid   = threadIdx.x;
     const uint32_t     lane  = tid & 31;

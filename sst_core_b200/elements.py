@@ -391,3 +391,18 @@ TYPE_NAMES = {
     TYPE_STATS_INT: "coreTestElement.StatisticsComponent.int",
     TYPE_STATS_FLOAT: "coreTestElement.StatisticsComponent.float",
 }
+
+
+def register_element(eli_name: str, type_code: int, wire_fn: Callable[[ConfigComponent, TimeLord], Wired],
+                     result_words: int = NRESULT, result_words_nostats: Optional[int] = None) -> None:
+    """The host half of an element compiled into libsstb200 from outside the tree (csrc/elements.def; type codes
+    16..31): the analogue of loading an element library, elemLoader.cc:159-177.  ``wire_fn`` turns a ConfigComponent
+    into the Wired record (type code, parameters, ports in configureLink order, clock, statistics)."""
+    if not (0 < type_code < 32):
+        raise ModelError("element type codes are 1..31")
+    if TYPE_NAMES.get(type_code, eli_name) != eli_name:
+        raise ModelError(f"type code {type_code} already belongs to {TYPE_NAMES[type_code]}")
+    ELEMENTS[eli_name] = wire_fn
+    TYPE_NAMES[type_code] = eli_name
+    RESULT_WORDS[type_code] = result_words
+    RESULT_WORDS_NOSTATS[type_code] = result_words if result_words_nostats is None else result_words_nostats

@@ -74,10 +74,12 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        raise EngineError(f"{LIB_PATH} is missing: build it with `python -m sst_core_b200.build` "
+    import os
+    path = Path(os.environ["SSTB200_LIB"]) if os.environ.get("SSTB200_LIB") else LIB_PATH  # a build with more elements
+    if not path.exists():
+        raise EngineError(f"{path} is missing: build it with `python -m sst_core_b200.build` "
                           f"(the CUDA engine is the only execution path)")
-    L = C.CDLL(str(LIB_PATH))
+    L = C.CDLL(str(path))
     L.sstb200_last_error.restype = C.c_char_p
     L.sstb200_component_type_info.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint32),
                                               C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
@@ -154,7 +156,8 @@ def check_registry():
     """The Python element descriptors and the native type table must agree (names and codes)."""
     native = {code: name for name, code, *_ in component_types()}
     if native != TYPE_NAMES:
-        raise EngineError(f"element registry mismatch: native {native} vs host {TYPE_NAMES}")
+        raise EngineError(f"element registry mismatch: native {native} vs host {TYPE_NAMES} (an element library compiled "
+                          f"into the native side needs its host half: elements.register_element)")
 
 
 def partition_linear(ncomp: int, nocut_pairs: Optional[np.ndarray], n_parts: int) -> np.ndarray:
