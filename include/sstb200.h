@@ -144,6 +144,15 @@ int sstb200_engine_advance(sstb200_engine* e);
 int sstb200_engine_peer_export(sstb200_engine* e, void* handle64, uint32_t* nbins, void** region_dev);
 int sstb200_engine_peer_connect(sstb200_engine* e, const void* handles, const uint32_t* nbins);
 int sstb200_engine_peer_connect_local(sstb200_engine* e, void* const* regions, const uint32_t* nbins);
+/* handler-time profile tools (profile/eventHandlerProfileTool.h:76-120 sst.profile.handler.event.time.*,
+ * clockHandlerProfileTool.h sst.profile.handler.clock.time.*): nanoseconds of SM time spent inside the event handlers of
+ * every receiving port [nport_local] and inside the clock handlers of every component [n_local] of this rank.  Needs
+ * options.handler_counts & 2 (the counts above are collected too).  Either pointer may be NULL. */
+int sstb200_engine_handler_times(sstb200_engine* e, double* event_recv_ns, double* clock_ns);
+/* sync profile tools (profile/syncProfileTool.h:60-140 sst.profile.sync.count / .time.*): out4 = {rank syncs (windows of a
+ * multi-rank run), events sent to other ranks, bytes of those records, nanoseconds this rank waited for its neighbour at the
+ * window barrier (peer mode)} */
+int sstb200_engine_sync_profile(sstb200_engine* e, uint64_t* out4);
 /* console output of device components (Output::output, output.cc:156-215): records of 8 u64 words
  * {time, component | code << 32, v0, v1, v2, v3, v4, 0}; per component in the order it printed them.  *n_inout: capacity of
  * `records` in records on entry, number written on return (records == NULL: only the count).  The host half of the

@@ -135,8 +135,9 @@ _CTRL = np.dtype([("k", "<u8"), ("T", "<u8"), ("T_end", "<u8"), ("stop_at", "<u8
                   ("events_delivered", "<u8"), ("clock_ticks", "<u8"), ("events_sent", "<u8"), ("max_bin_fill", "<u8"),
                   ("max_due", "<u8"), ("end_time", "<u8"), ("done", "<u4"), ("error", "<u4"), ("error_info", "<u8", 4),
                   ("local", "<i8", 8), ("trace_n", "<u8"), ("windows", "<u8"), ("had_primary", "<u4"), ("slot", "<u4"),
-                  ("report_at", "<u8"), ("fb_n", "<u4"), ("maint_n", "<u4"), ("out_n", "<u8")])
-assert _CTRL.itemsize == 240  # sizeof(Ctrl) in csrc/engine.cu (static_assert there)
+                  ("report_at", "<u8"), ("fb_n", "<u4"), ("maint_n", "<u4"), ("out_n", "<u8"),
+                  ("remote_events", "<u8"), ("sync_wait_ns", "<u8")])
+assert _CTRL.itemsize == 256  # sizeof(Ctrl) in csrc/engine.cu (static_assert there)
 _NEVER = np.uint64(0xFFFFFFFFFFFFFFFF)
 _BLOCK = 256
 _XHDR = 10

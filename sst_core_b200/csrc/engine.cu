@@ -100,8 +100,11 @@ struct Ctrl
     // generator needs maintenance after this window; both reset by advance_kernel
     uint32_t           fb_n, maint_n;
     unsigned long long out_n; // console-output records written (Dev::out_log)
+    // sync profile tools (profile/syncProfileTool.h:60-140): events this rank sent to other ranks, nanoseconds this rank
+    // waited for the others at the window barrier (peer mode)
+    unsigned long long remote_events, sync_wait_ns;
 };
-static_assert(sizeof(Ctrl) == 240, "Ctrl changed: keep _CTRL in sst_core_b200/checkpoint.py (repartitioned restart) in step");
+static_assert(sizeof(Ctrl) == 256, "Ctrl changed: keep _CTRL in sst_core_b200/checkpoint.py (repartitioned restart) in step");
 
 // Per-component engine control block: everything the dispatch kernel needs about a component besides its element
 // state, in one 32-byte record (two 16-byte loads; only the first half is ever written back).
@@ -173,6 +176,10 @@ struct Dev
     // deliveries per receiving port and clock-handler calls per component; null unless the option is set
     unsigned long long* prof_recv;  // [nport_local]
     unsigned long long* prof_clock; // [n_local]
+    // handler-time profile tools (eventHandlerProfileTool.h:76-120, clockHandlerProfileTool.h): SM cycles spent inside
+    // the event handlers of every receiving port / the clock handlers of every component; null unless asked for
+    unsigned long long* prof_recv_cyc;  // [nport_local]
+    unsigned long long* prof_clock_cyc; // [n_local]
     uint8_t*            snapshot;   // copy of `state` holding every component's state as of Ctrl::report_at
     // event-parallel form: staging capacity for a bin's records, the two lists (see Ctrl)
     uint32_t            pf_rcap;
@@ -225,6 +232,7 @@ emit(const Dev& d, uint64_t k, uint64_t time, uint32_t dst_port, uint32_t dst_co
         uint32_t r = 0;
         while ( r + 1 < d.n_ranks && dst_comp >= d.rank_comp_begin[r + 1] )
             ++r;
+        atomicAdd(&d.ctrl->remote_events, 1ull);
         if ( !d.peer_on ) {
             unsigned long long* box = d.outbox + (uint64_t)r * d.xwords;
             unsigned long long  pos = atomicAdd(&box[0], 1ull);
@@ -974,6 +982,7 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
                 }
                 if ( next_tick < T_end && next_tick <= ev_t ) {
                     ctx.now = next_tick;
+                    const long long tc0 = d.prof_clock_cyc ? clock64() : 0;
                     if constexpr ( MC ) {
                         // every clock of the component due now, each with all its handlers (ClockSet::fire)
                         ticks += E::clockFire(ctx, s, next_tick);
@@ -988,6 +997,7 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
                         else
                             next_tick += period;
                     }
+                    if ( d.prof_clock_cyc ) d.prof_clock_cyc[lc] += (unsigned long long)(clock64() - tc0);
                     continue;
                 }
                 uint32_t port;
@@ -1023,7 +1033,13 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
                     }
                     dseq++;
                 }
-                E::handleEvent(ctx, s, (int)port, pl);
+                if ( d.prof_recv_cyc ) {
+                    const long long te0 = clock64();
+                    E::handleEvent(ctx, s, (int)port, pl);
+                    atomicAdd(&d.prof_recv_cyc[ctx.port0 + port - d.P0], (unsigned long long)(clock64() - te0));
+                }
+                else
+                    E::handleEvent(ctx, s, (int)port, pl);
                 delivered++;
                 if constexpr ( MC ) next_tick = E::nextClock(s); // the handler may have started or stopped a clock
             }
@@ -1136,8 +1152,10 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
         __syncthreads();
         if ( tid < HT && ht_key[tid] != 0xFFFFFFFFu && ht_cnt[tid] ) {
             const uint32_t ky = ht_key[tid];
-            if ( ky & 0x80000000u )
+            if ( ky & 0x80000000u ) {
                 ht_base[tid] = remote_reserve(d, ky, ht_cnt[tid]);
+                atomicAdd(&ctrl->remote_events, (unsigned long long)ht_cnt[tid]);
+            }
             else
                 ht_base[tid] = atomicAdd(&d.bin_count[ky], ht_cnt[tid]);
         }
@@ -1394,9 +1412,16 @@ peer_advance_kernel(Dev d, int spin, int post_first)
         volatile unsigned long long* m = d.mail + ((uint64_t)par * d.n_ranks + r) * MAILW;
         if ( spin ) {
             const long long t0 = clock64();
+            unsigned long long g0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
             while ( m[CW_WORDS] != seq ) {
                 __nanosleep(200);
                 if ( clock64() - t0 > 20000000000ll ) break; // ~10 s: a peer is gone
+            }
+            if ( r == (d.rank + 1) % d.n_ranks ) { // one sample per window: how long this rank waited for its neighbour
+                unsigned long long g1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+                c->sync_wait_ns += g1 - g0;
             }
         }
         if ( m[CW_WORDS] != seq ) raise_error(d, ERR_PEER_SYNC, r, seq, m[CW_WORDS]);
@@ -2277,6 +2302,10 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         rc |= e->alloc(&d.prof_recv, d.nport_local);
         rc |= e->alloc(&d.prof_clock, d.n_local);
     }
+    if ( o->handler_counts & 2u ) { // ... and the time inside the handlers
+        rc |= e->alloc(&d.prof_recv_cyc, d.nport_local);
+        rc |= e->alloc(&d.prof_clock_cyc, d.n_local);
+    }
     if ( e->pf_on ) {
         rc |= e->alloc(&d.fb_list, d.nbins, false);
         rc |= e->alloc(&d.maint_list, d.n_local, false);
@@ -2959,6 +2988,47 @@ sstb200_engine_handler_counts(sstb200_engine* e, uint64_t* event_recv, uint64_t*
     if ( clock_calls && e->d.n_local )
         CUDA_OK(cudaMemcpyAsync(clock_calls, e->d.prof_clock, (size_t)e->d.n_local * 8, cudaMemcpyDeviceToHost, e->stream));
     CUDA_OK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int
+sstb200_engine_handler_times(sstb200_engine* e, double* event_recv_ns, double* clock_ns)
+{
+    if ( !e ) return -1;
+    if ( !e->d.prof_recv_cyc ) {
+        set_error("engine_handler_times: the engine was created without options.handler_counts & 2");
+        return -1;
+    }
+    CUDA_OK(cudaSetDevice(e->device));
+    int khz = 0;
+    CUDA_OK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->device));
+    const double ns_per_cycle = khz > 0 ? 1.0e6 / (double)khz : 0.5;
+    std::vector<unsigned long long> a(e->d.nport_local), b(e->d.n_local);
+    if ( !a.empty() )
+        CUDA_OK(cudaMemcpyAsync(a.data(), e->d.prof_recv_cyc, a.size() * 8, cudaMemcpyDeviceToHost, e->stream));
+    if ( !b.empty() )
+        CUDA_OK(cudaMemcpyAsync(b.data(), e->d.prof_clock_cyc, b.size() * 8, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_OK(cudaStreamSynchronize(e->stream));
+    if ( event_recv_ns )
+        for ( size_t i = 0; i < a.size(); ++i )
+            event_recv_ns[i] = (double)a[i] * ns_per_cycle;
+    if ( clock_ns )
+        for ( size_t i = 0; i < b.size(); ++i )
+            clock_ns[i] = (double)b[i] * ns_per_cycle;
+    return 0;
+}
+
+int
+sstb200_engine_sync_profile(sstb200_engine* e, uint64_t* out4)
+{
+    if ( !e || !out4 ) return -1;
+    CUDA_OK(cudaSetDevice(e->device));
+    if ( int rc = e->fetch_ctrl() ) return rc;
+    const uint64_t rec_bytes = e->d.has_payload ? 24 : 16;
+    out4[0] = e->n_ranks > 1 ? e->h_ctrl->windows : 0;
+    out4[1] = e->h_ctrl->remote_events;
+    out4[2] = e->h_ctrl->remote_events * rec_bytes;
+    out4[3] = e->h_ctrl->sync_wait_ns;
     return 0;
 }
 

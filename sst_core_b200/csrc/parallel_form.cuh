@@ -279,8 +279,10 @@ window_parallel_kernel(Dev d)
         }
         if ( tid < PF_HT && ht_cnt[tid] ) {
             const uint32_t ky = ht_key[tid];
-            if ( ky & 0x80000000u )
+            if ( ky & 0x80000000u ) {
                 ht_base[tid] = remote_reserve(d, ky, ht_cnt[tid]);
+                atomicAdd(&ctrl->remote_events, (unsigned long long)ht_cnt[tid]); // sync profile tools
+            }
             else
                 ht_base[tid] = atomicAdd(&d.bin_count[ky], ht_cnt[tid]);
         }

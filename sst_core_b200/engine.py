@@ -64,6 +64,7 @@ EXPORTS = [
     "sstb200_engine_stream",
     "sstb200_peer_region_bytes", "sstb200_peer_arena_create", "sstb200_peer_arena_open", "sstb200_peer_arena_destroy",
     "sstb200_engine_in_arena", "sstb200_engine_peer_connect_arena", "sstb200_engine_output",
+    "sstb200_engine_handler_times", "sstb200_engine_sync_profile",
 ]
 
 _lib = None
@@ -99,6 +100,8 @@ def lib():
     L.sstb200_engine_peer_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sstb200_engine_peer_connect_local.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sstb200_engine_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.sstb200_engine_handler_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sstb200_engine_sync_profile.argtypes = [C.c_void_p, C.c_void_p]
     L.sstb200_engine_output.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
     L.sstb200_peer_region_bytes.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
     L.sstb200_peer_region_bytes.restype = C.c_uint64
@@ -318,7 +321,7 @@ class Engine:
             c0, c1 = 0, model.ncomp
         self.comp_begin, self.comp_end = c0, c1
         opt = _Options(device, rank, n_ranks, c0, c1, _p(self._begins), calendar_slots, bin_capacity, smem_events,
-                       outbox_capacity, window, trace_capacity, stream, parallel_max_events, int(bool(handler_counts)),
+                       outbox_capacity, window, trace_capacity, stream, parallel_max_events, int(handler_counts),
                        int(getattr(model, "_type_mask", 0)) if n_ranks > 1 else 0,
                        int(getattr(model, "_uniform_ports", 0)) if n_ranks > 1 else 0, output_capacity)
         h = C.c_void_p()
@@ -406,6 +409,20 @@ class Engine:
         nb = np.ascontiguousarray(nbins, dtype=np.uint32)
         _check(self._L.sstb200_engine_peer_connect_local(self._h, rg, _p(nb)), "engine_peer_connect_local")
         self.peer = "local"
+
+    def handler_times(self):
+        """(ns inside the event handlers per port, ns inside the clock handlers per component) of this rank; the engine
+        must have been created with handler_counts=3."""
+        recv = np.zeros(int(self.model.port_off[self.comp_end]) - int(self.model.port_off[self.comp_begin]), dtype=np.float64)
+        clk = np.zeros(self.comp_end - self.comp_begin, dtype=np.float64)
+        _check(self._L.sstb200_engine_handler_times(self._h, _p(recv), _p(clk)), "engine_handler_times")
+        return recv, clk
+
+    def sync_profile(self):
+        """(rank syncs, events sent to other ranks, their bytes, ns waited at the window barrier) of this rank"""
+        out = np.zeros(4, dtype=np.uint64)
+        _check(self._L.sstb200_engine_sync_profile(self._h, _p(out)), "engine_sync_profile")
+        return tuple(int(v) for v in out)
 
     def output_records(self) -> np.ndarray:
         """Console-output records of this rank's device components: u64 [n, 8] = {time, component | code << 32,

@@ -8,8 +8,11 @@ host-side halves: parsing the option string exactly as ``Simulation::initializeP
 (simulation.cc:1607-1760; same fatal messages) and folding the counters into the reference's keys and text format.
 
 In scope: ``sst.profile.handler.event.count`` (params ``level`` = global|type|component|subcomponent, ``track_ports``,
-``profile_receives``) and ``sst.profile.handler.clock.count`` (``level``).  The ``.time.*`` tools measure host wall
-clock per handler call, which has no meaning on the device; ``profile_sends`` and the ``sync`` point are not provided.
+``profile_receives``), ``sst.profile.handler.clock.count`` (``level``), their ``.time.high_resolution`` / ``.time.steady``
+variants (eventHandlerProfileTool.h:76-120: the time reported is SM time inside the handlers, measured with the SM cycle
+counter around every handler call -- the device has no per-call wall clock) and the sync tools ``sst.profile.sync.count``
+/ ``sst.profile.sync.time.*`` (syncProfileTool.h:60-140: rank syncs = lookahead windows of a multi-rank run, events and
+bytes sent to other ranks, time waited at the window barrier).  ``profile_sends`` is not provided.
 """
 from __future__ import annotations
 
@@ -29,6 +32,11 @@ FORMAT_ERROR = ("ERROR: Invalid format for argument passed to --enable-profiling
 
 EVENT_COUNT = "sst.profile.handler.event.count"
 CLOCK_COUNT = "sst.profile.handler.clock.count"
+EVENT_TIME = ("sst.profile.handler.event.time.high_resolution", "sst.profile.handler.event.time.steady")
+CLOCK_TIME = ("sst.profile.handler.clock.time.high_resolution", "sst.profile.handler.clock.time.steady")
+SYNC_COUNT = "sst.profile.sync.count"
+SYNC_TIME = ("sst.profile.sync.time.high_resolution", "sst.profile.sync.time.steady")
+ALL_TYPES = (EVENT_COUNT, CLOCK_COUNT, SYNC_COUNT) + EVENT_TIME + CLOCK_TIME + SYNC_TIME
 LEVELS = ("global", "type", "component", "subcomponent")
 
 
@@ -76,15 +84,15 @@ def parse_enable_profiling(spec: str) -> List[Tool]:
         for p in pts:
             if p not in ("clock", "event", "sync"):
                 raise ModelError(f"ERROR: Invalid profile point specified: {p}")
-        if typ not in (EVENT_COUNT, CLOCK_COUNT):
+        if typ not in ALL_TYPES:
             raise ModelError(f"profile tool type '{typ}' is not available on the device engine "
-                             f"(supported: {EVENT_COUNT}, {CLOCK_COUNT})")
+                             f"(supported: {', '.join(ALL_TYPES)})")
         level = params.get("level", "type")
-        if level not in LEVELS:
-            what = "EventHandlerProfileTool" if typ == EVENT_COUNT else "ClockHandlerProfileTool"
+        if level not in LEVELS and "sync" not in typ:
+            what = "EventHandlerProfileTool" if ".event." in typ else "ClockHandlerProfileTool"
             raise ModelError(f"ERROR: unsupported level specified for {what}: {level}")
         tool = Tool(name, typ, params, pts)
-        if typ == EVENT_COUNT and tool.flag("profile_sends", False):
+        if ".event." in typ and tool.flag("profile_sends", False):
             raise ModelError("profile_sends is not available on the device engine")
         tools[name] = tool
     return [tools[k] for k in sorted(tools)]
@@ -133,8 +141,27 @@ def clock_counts(m: WiredModel, calls: np.ndarray, tool: Tool, only: Optional[np
     return out
 
 
+def needs_times(tools: List[Tool]) -> bool:
+    return any(t.type in EVENT_TIME + CLOCK_TIME for t in tools)
+
+
+def _si_time(seconds: float) -> str:
+    """UnitAlgebra::toStringBestSI of a time: '1.788 ms', '311 ns', '0 s'"""
+    if seconds <= 0:
+        return "0 s"
+    for pre, scale in (("", 1.0), ("m", 1e-3), ("u", 1e-6), ("n", 1e-9), ("p", 1e-12)):
+        if seconds >= scale:
+            return f"{seconds / scale:.4g} {pre}s"
+    return f"{seconds / 1e-12:.4g} ps"
+
+
+def _aligned(indent: str, items: Dict[str, str]) -> str:
+    width = max(len(k) for k in items) + 1
+    return "".join(f"{indent}{(k + ':').ljust(width)} {v}\n" for k, v in sorted(items.items()))
+
+
 def profiling_text(m: WiredModel, tools: List[Tool], recv: np.ndarray, calls: np.ndarray, end_time: int,
-                   input_file: str, ranks: int = 1, threads: int = 1) -> str:
+                   input_file: str, ranks: int = 1, threads: int = 1, times=None, sync=None) -> str:
     """The file ``--profiling-output`` names, laid out as the reference's PerfReporter does (observed from the
     reference binary; tests/golden holds the fixtures): one ``name:`` record per tool in name order, clock tools
     grouped under ``<rank>_<thread>:`` (one group per GPU here), then the run summary.  ``recv`` / ``calls`` are in
@@ -146,6 +173,41 @@ def profiling_text(m: WiredModel, tools: List[Tool], recv: np.ndarray, calls: np
             if t.flag("profile_receives", True):
                 for k, v in sorted(event_counts(m, recv, t).items()):
                     out.append(f"  {k}:\n    recv_count: {v}\n")
+        elif t.type in EVENT_TIME:
+            # recv_count, recv_time (seconds, best SI), avg_recv_time (whole ns) -- eventHandlerProfileTool.cc:140-155
+            if times is None:
+                raise ModelError("handler-time tools need the engine's handler times (handler_counts=3)")
+            if t.flag("profile_receives", True):
+                cnt = event_counts(m, recv, t)
+                ns = event_counts(m, np.rint(times[0]).astype(np.int64), t)
+                for k in sorted(cnt):
+                    items = {"recv_count": str(cnt[k]), "recv_time": _si_time(ns[k] * 1e-9)}
+                    if cnt[k]:
+                        items["avg_recv_time"] = _si_time((ns[k] // cnt[k]) * 1e-9)
+                    out.append(f"  {k}:\n" + _aligned("    ", items))
+        elif t.type in CLOCK_TIME:
+            if times is None:
+                raise ModelError("handler-time tools need the engine's handler times (handler_counts=3)")
+            for r in (range(m.n_ranks) if m.rank is not None else [0]):
+                out.append(f"  {r}_0:\n")
+                only = (m.rank == r) if m.rank is not None else None
+                cnt = clock_counts(m, calls, t, only)
+                ns = clock_counts(m, np.rint(times[1]).astype(np.int64), t, only)
+                for k in sorted(cnt):
+                    items = {"count": str(cnt[k]), "handler_time": _si_time(ns[k] * 1e-9)}
+                    if cnt[k]:
+                        items["avg_handler_time"] = _si_time((ns[k] // cnt[k]) * 1e-9)
+                    out.append(f"    {k}:\n" + _aligned("      ", items))
+        elif t.type == SYNC_COUNT or t.type in SYNC_TIME:
+            # one child per rank with the tool's keys (syncProfileTool.cc:58-120); threads do not exist here
+            for r, (syncs, events, nbytes, wait_ns) in enumerate(sync or [(0, 0, 0, 0)]):
+                items = {"ranksync_total_count": str(syncs), "threadsync_total_count": "0",
+                         "ranksync_total_events": str(events), "ranksync_total_data": f"{nbytes} B"}
+                if t.type in SYNC_TIME:
+                    items.update({"ranksync_total_time": _si_time(wait_ns * 1e-9),
+                                  "ranksync_avg_time": _si_time((wait_ns // syncs if syncs else 0) * 1e-9),
+                                  "threadsync_total_time": "0 s", "threadsync_avg_time": "0 s"})
+                out.append(f"  rank{r}:\n" + _aligned("    ", items))
         else:
             for r in (range(m.n_ranks) if m.rank is not None else [0]):
                 out.append(f"  {r}_0:\n")

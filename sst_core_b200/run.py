@@ -89,6 +89,9 @@ def simulate_model(m: wireup.WiredModel, device: int = 0, auto_tune: bool = True
             e.raise_on_error(st)
             if extras is not None and opts.get("handler_counts"):
                 extras["handler_counts"] = e.handler_counts()
+                extras["sync_profile"] = [e.sync_profile()]
+                if int(opts["handler_counts"]) & 2:
+                    extras["handler_times"] = e.handler_times()
             if extras is not None and ((m.output_fmt and any(f is not None for f in m.output_fmt)) or m.stat_slots):
                 extras["output"] = e.output_records()
             return e.results(result_words(m)), st
@@ -147,6 +150,9 @@ def simulate_distributed(m: wireup.WiredModel, extras: Optional[dict] = None, ch
             e.raise_on_error(st)
             if extras is not None and engine_opts.get("handler_counts"):
                 extras["handler_counts"] = e.handler_counts()
+                extras["sync_profile"] = [e.sync_profile()]
+                if int(engine_opts["handler_counts"]) & 2:
+                    extras["handler_times"] = e.handler_times()
             return e.results(result_words(pm)), st, pm
         finally:
             e.close()
@@ -216,7 +222,7 @@ def main(argv: Optional[list] = None) -> int:
         opts["bin_capacity"] = a.bin_capacity
     extras = {}
     if tools:
-        opts["handler_counts"] = True
+        opts["handler_counts"] = 3 if profile.needs_times(tools) else 1
     world = int(os.environ.get("WORLD_SIZE", "1"))
     ckpt = {}
     recipe = None
@@ -250,7 +256,8 @@ def main(argv: Optional[list] = None) -> int:
             # m: renumbered so that every rank owns a contiguous range
             part, st, m = simulate_distributed(m, extras=extras, restore_registry=reg, **ckpt, **opts)
             parts = [None] * world if dist.get_rank() == 0 else None
-            dist.gather_object((part, extras.get("handler_counts"), extras.get("periodic", [])), parts, dst=0)
+            dist.gather_object((part, extras.get("handler_counts"), extras.get("periodic", []),
+                                extras.get("handler_times"), extras.get("sync_profile")), parts, dst=0)
             if dist.get_rank() != 0:
                 return 0
             res = np.concatenate([p[0] for p in parts], axis=0)
@@ -258,6 +265,9 @@ def main(argv: Optional[list] = None) -> int:
                                   for i, (t, _) in enumerate(parts[0][2])]
             if tools:
                 extras["handler_counts"] = tuple(np.concatenate([p[1][i] for p in parts]) for i in (0, 1))
+                extras["sync_profile"] = [p[4][0] for p in parts]
+                if parts[0][3] is not None:
+                    extras["handler_times"] = tuple(np.concatenate([p[3][i] for p in parts]) for i in (0, 1))
         finally:
             dist.barrier()
             dist.destroy_process_group()
@@ -286,7 +296,8 @@ def main(argv: Optional[list] = None) -> int:
         print(line)
     if tools:
         recv, calls = extras["handler_counts"]
-        text = profile.profiling_text(m, tools, recv, calls, st.end_time, os.path.abspath(a.script))
+        text = profile.profiling_text(m, tools, recv, calls, st.end_time, os.path.abspath(a.script),
+                                      times=extras.get("handler_times"), sync=extras.get("sync_profile"))
         if a.profiling_output:
             with open(os.path.join(a.output_directory, a.profiling_output), "w") as f:
                 f.write(text)

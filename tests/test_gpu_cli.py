@@ -83,6 +83,28 @@ def test_cli_handler_counts_match_reference_binary_runs(tmp_path, key, script, o
     assert _comparable((tmp_path / "p.txt").read_text()) == _comparable(GOLD[key]["text"])
 
 
+def test_cli_handler_time_and_sync_tools(tmp_path):
+    """sst.profile.handler.{event,clock}.time.* and sst.profile.sync.* on the device: the counts inside the time records
+    equal the count tools' (pinned to the reference above), every handler that ran has a non-zero time, and the layout
+    is the reference's (keys, alignment)"""
+    import re
+    spec = ("ev:sst.profile.handler.event.time.steady(level=component)[event];"
+            "ck:sst.profile.handler.clock.time.high_resolution(level=component)[clock];"
+            "cc:sst.profile.handler.clock.count(level=component)[clock];"
+            "ec:sst.profile.handler.event.count(level=component)[event];sy:sst.profile.sync.count[sync]")
+    _run(["--model-options", "3 2 200ns 10", "--profiling-output", "p.txt", "--enable-profiling", spec,
+          str(ROOT / "tests/models/clockpop.py")], tmp_path)
+    text = (tmp_path / "p.txt").read_text()
+    rec = {name: body for name, body in re.findall(r"\n\n(\w+):\n(.*?)(?=\n\n\w|\Z)", text, re.S)}
+    counts = dict(re.findall(r"    (node\d+):\n      count: (\d+)", rec["cc"]))
+    timed = dict(re.findall(r"    (node\d+):\n      avg_handler_time: [0-9.]+ [munp]?s\n      count: +(\d+)\n      handler_time: +[0-9.]+ [munp]?s", rec["ck"]))
+    assert counts == timed and len(counts) == 6
+    ecounts = dict(re.findall(r"  (node\d+):\n    recv_count: (\d+)", rec["ec"]))
+    etimed = dict(re.findall(r"  (node\d+):\n(?:    avg_recv_time: [0-9.]+ [munp]?s\n)?    recv_count: +(\d+)\n    recv_time: +[0-9.]+ [munp]?s", rec["ev"]))
+    assert ecounts == etimed and len(ecounts) == 6
+    assert "  rank0:\n    ranksync_total_count:   0\n" in rec["sy"]  # one rank: no rank syncs, like the reference
+
+
 def test_handler_counts_sum_to_the_delivered_events_on_a_large_mesh():
     """size-independent property at a size the oracle does not reach quickly: per-port counts add up to the number of
     deliveries, per component they equal the element's own receive counter (event-parallel and sequential forms)"""

@@ -74,7 +74,8 @@ def test_option_string_errors_follow_the_reference():
     with pytest.raises(config.ModelError, match="unsupported level specified for EventHandlerProfileTool: deep"):
         P("e:sst.profile.handler.event.count(level=deep)[event]")
     with pytest.raises(config.ModelError, match="not available on the device engine"):
-        P("e:sst.profile.handler.event.time.high_resolution(level=global)[event]")
+        P("e:sst.profile.handler.event.time.cpu(level=global)[event]")
+    assert P("e:sst.profile.handler.event.time.high_resolution(level=global)[event]")[0].params == {"level": "global"}
     t = P(" b : sst.profile.handler.clock.count [clock] ;a:sst.profile.handler.event.count( level=global )[ event ]")
     assert [x.name for x in t] == ["a", "b"] and t[0].params == {"level": "global"} and t[1].points == ["clock"]
 
@@ -89,3 +90,27 @@ def test_partitioned_models_keep_port_names():
     for c in range(pm.ncomp):
         for p in range(int(pm.port_off[c]), int(pm.port_off[c + 1])):
             assert pm.port_info[p][0].split(":")[0] == pm.names[c]
+
+
+def test_time_and_sync_tools_parse_and_format():
+    """sst.profile.handler.{event,clock}.time.* and sst.profile.sync.*: keys and layout of the reference's records
+    (eventHandlerProfileTool.cc:140-155, clockHandlerProfileTool.cc, syncProfileTool.cc:58-120); the times themselves are
+    measurements"""
+    import numpy as np
+    from sst_core_b200 import config, profile, wireup
+    m = wireup.wire(config.build_graph(str(ROOT / "tests" / "models" / "clockpop.py"), "2 2 200ns 10 1 0"))
+    spec = ("ev:sst.profile.handler.event.time.steady(level=component)[event];"
+            "ck:sst.profile.handler.clock.time.high_resolution(level=type)[clock];"
+            "sy:sst.profile.sync.count[sync];st:sst.profile.sync.time.steady[sync]")
+    tools = profile.parse_enable_profiling(spec)
+    assert [t.name for t in tools] == ["ck", "ev", "st", "sy"] and profile.needs_times(tools)
+    recv = np.arange(m.nport, dtype=np.uint64) % 5
+    calls = np.full(m.ncomp, 100, dtype=np.uint64)
+    times = (recv.astype(np.float64) * 311.0, np.full(m.ncomp, 399000.0))
+    text = profile.profiling_text(m, tools, recv, calls, 200000, "x", times=times, sync=[(199, 40, 640, 1500000)])
+    assert "ck:\n  0_0:\n    pdes.clocknode:\n      avg_handler_time: 3.99 us\n      count:            400\n      handler_time:     1.596 ms\n" in text
+    assert "\nev:\n  node0:\n" in text and "    avg_recv_time: 311 ns\n" in text and "    recv_count:    " in text
+    assert "sy:\n  rank0:\n    ranksync_total_count:   199\n    ranksync_total_data:    640 B\n    ranksync_total_events:  40\n" in text
+    assert "    ranksync_avg_time:      7.537 us\n" in text and "    ranksync_total_time:    1.5 ms\n" in text
+    with pytest.raises(config.ModelError, match="not available on the device engine"):
+        profile.parse_enable_profiling("x:sst.profile.handler.event.bogus[event]")
