@@ -112,6 +112,9 @@ int sstb200_engine_setup(sstb200_engine* e);
  * stream except for a completion check every `check_every` windows.  *finished is set to 1 when the simulation has
  * ended (stop time reached, primary components done, or nothing left to run). */
 int sstb200_engine_run(sstb200_engine* e, uint64_t max_windows, uint32_t check_every, int* finished);
+/* optional: capture the CUDA graph of a chunk of `check_every` windows now (nothing is launched), so that the first
+ * sstb200_engine_run with the same check_every does not pay for the capture */
+int sstb200_engine_prepare_run(sstb200_engine* e, uint32_t check_every);
 
 /* Multi-rank stepping (one lookahead window = SyncManager::execute):
  *   dispatch  : deliver this window's events and clock ticks; cross-rank sends land in per-destination outboxes, and

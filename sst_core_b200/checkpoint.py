@@ -136,8 +136,8 @@ _CTRL = np.dtype([("k", "<u8"), ("T", "<u8"), ("T_end", "<u8"), ("stop_at", "<u8
                   ("max_due", "<u8"), ("end_time", "<u8"), ("done", "<u4"), ("error", "<u4"), ("error_info", "<u8", 4),
                   ("local", "<i8", 8), ("trace_n", "<u8"), ("windows", "<u8"), ("had_primary", "<u4"), ("slot", "<u4"),
                   ("report_at", "<u8"), ("fb_n", "<u4"), ("maint_n", "<u4"), ("out_n", "<u8"),
-                  ("remote_events", "<u8"), ("sync_wait_ns", "<u8")])
-assert _CTRL.itemsize == 256  # sizeof(Ctrl) in csrc/engine.cu (static_assert there)
+                  ("remote_events", "<u8"), ("sync_wait_ns", "<u8"), ("tail_done", "<u4"), ("pf_next", "<u4"), ("fb_taken", "<u4"), ("pad_fb", "<u4")])
+assert _CTRL.itemsize == 272  # sizeof(Ctrl) in csrc/engine.cu (static_assert there)
 _NEVER = np.uint64(0xFFFFFFFFFFFFFFFF)
 _BLOCK = 256
 _XHDR = 10

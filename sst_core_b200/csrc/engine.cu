@@ -103,8 +103,11 @@ struct Ctrl
     // sync profile tools (profile/syncProfileTool.h:60-140): events this rank sent to other ranks, nanoseconds this rank
     // waited for the others at the window barrier (peer mode)
     unsigned long long remote_events, sync_wait_ns;
+    uint32_t           tail_done; // CTAs of maintenance_kernel that have finished (the last one ends the window)
+    uint32_t           pf_next;   // blocks handed out by window_parallel_kernel beyond each CTA's first (reset per window)
+    uint32_t           fb_taken, pad_fb; // entries of fb_list taken by CTAs of window_parallel_kernel that ran out of blocks
 };
-static_assert(sizeof(Ctrl) == 256, "Ctrl changed: keep _CTRL in sst_core_b200/checkpoint.py (repartitioned restart) in step");
+static_assert(sizeof(Ctrl) == 272, "Ctrl changed: keep _CTRL in sst_core_b200/checkpoint.py (repartitioned restart) in step");
 
 // Per-component engine control block: everything the dispatch kernel needs about a component besides its element
 // state, in one 32-byte record (two 16-byte loads; only the first half is ever written back).
@@ -1331,8 +1334,10 @@ advance_fold(const Dev& d)
         exit_time = (uint64_t)c->local[CW_EXIT_TIME];
     }
     c->windows++;
-    c->fb_n    = 0;
-    c->maint_n = 0;
+    c->fb_n     = 0;
+    c->fb_taken = 0;
+    c->maint_n  = 0;
+    c->pf_next  = 0;
     if ( c->error || err ) {
         if ( !c->error ) c->error = (uint32_t)0x80000000u; // another rank failed
         c->done = 1;
@@ -1399,12 +1404,10 @@ peer_post_kernel(Dev d)
 // wait for every rank's mailbox entry of this window (spin: the peers are other GPUs running their own kernels; with
 // all ranks stepped by one process on one GPU the entries are already there and a missing one is an error), then fold
 // the control words and open the next window exactly like advance_kernel
-__global__ void
-peer_advance_kernel(Dev d, int spin, int post_first)
+__device__ __forceinline__ void
+peer_wait_and_fold(const Dev& d, int spin) // called by a whole CTA (>= n_ranks threads)
 {
     Ctrl* c = d.ctrl;
-    if ( c->done || blockIdx.x != 0 ) return;
-    if ( post_first ) peer_post(d); // ranks on their own GPUs: the mailbox write and the wait in one launch
     const unsigned long long seq = c->windows + 1;
     const uint32_t           par = (uint32_t)(seq & 1ull);
     const uint32_t           r   = threadIdx.x;
@@ -1431,6 +1434,15 @@ peer_advance_kernel(Dev d, int spin, int post_first)
     }
     __syncthreads();
     if ( threadIdx.x == 0 ) advance_fold(d);
+}
+
+__global__ void
+peer_advance_kernel(Dev d, int spin, int post_first)
+{
+    Ctrl* c = d.ctrl;
+    if ( c->done || blockIdx.x != 0 ) return;
+    if ( post_first ) peer_post(d); // ranks on their own GPUs: the mailbox write and the wait in one launch
+    peer_wait_and_fold(d, spin);
 }
 
 __global__ void
@@ -1770,7 +1782,7 @@ struct sstb200_engine
         }
         else if ( pf_on ) {
             window_parallel_kernel<MeshElement><<<pf_grid, PF_THREADS, pf_smem, stream>>>(d);
-            dispatch_kernel<false, false, MeshElement, true><<<fb_grid, BLOCK, smem_bytes, stream>>>(d);
+            maintenance_kernel<<<maint_grid, 256, 0, stream>>>(d, 0, 0, 0, 0, 0); // the window is ended by the driver
             launches += 2;
         }
         else {
@@ -1795,21 +1807,28 @@ struct sstb200_engine
                 dispatch_kernel<false><<<d.nbins, BLOCK, smem_bytes, stream>>>(d);
             launches++;
         }
-        if ( pf_on ) {
-            maintenance_kernel<<<maint_grid, 256, 0, stream>>>(d, 0, 0, 0);
-            launches++;
-        }
         CUDA_OK(cudaGetLastError());
         return 0;
     }
-    uint32_t launches_per_window() const { return (pf_on ? 4u : 2u) + (n_ranks > 1 && !(d.peer_on && peer_spin) ? 1u : 0u); }
+    // the native run loop with the event-parallel form: the window kernel (which also re-runs the blocks it could not
+    // take, sequentially) + the maintenance kernel, whose last CTA ends the window -- two launches per window
+    bool     fused_tail() const { return pf_on && (n_ranks == 1 || (d.peer_on && peer_spin)); }
+    uint32_t launches_per_window() const { return fused_tail() ? 2u : (pf_on ? 3u : 2u) + (n_ranks > 1 && !(d.peer_on && peer_spin) ? 1u : 0u); }
+    int      launch_window_fused()
+    {
+        window_parallel_kernel<MeshElement><<<pf_grid, PF_THREADS, pf_smem, stream>>>(d);
+        maintenance_kernel<<<maint_grid, 256, 0, stream>>>(d, 0, 0, 0, n_ranks > 1 ? 2 : 1, peer_spin ? 1 : 0);
+        launches += 2;
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     // `n` windows (dispatch + advance each).  The kernels take the same arguments every window -- the window state
     // lives in device memory -- so a chunk is captured once into a CUDA graph and replayed: small models are bound by
     // launch overhead, not by the kernels.
     cudaGraphExec_t graph_exec  = nullptr;
     uint32_t        graph_chunk = 0;
     bool            graph_failed = false;
-    int launch_windows(uint32_t n)
+    int launch_windows(uint32_t n, bool capture_only = false)
     {
         if ( !graph_failed && n >= 8 && (graph_exec == nullptr || graph_chunk == n) ) {
             if ( graph_exec == nullptr ) {
@@ -1818,6 +1837,10 @@ struct sstb200_engine
                     const uint64_t before = launches;
                     int            rc     = 0;
                     for ( uint32_t i = 0; i < n && !rc; ++i ) {
+                        if ( fused_tail() ) {
+                            rc = launch_window_fused();
+                            continue;
+                        }
                         rc = launch_dispatch();
                         if ( !rc && n_ranks > 1 ) rc = launch_publish();
                         if ( !rc ) rc = launch_advance();
@@ -1834,13 +1857,19 @@ struct sstb200_engine
                     graph_failed = true;
                 (void)cudaGetLastError();
             }
+            if ( capture_only ) return 0;
             if ( graph_exec && graph_chunk == n ) {
                 CUDA_OK(cudaGraphLaunch(graph_exec, stream));
                 launches += (uint64_t)launches_per_window() * n;
                 return 0;
             }
         }
+        if ( capture_only ) return 0;
         for ( uint32_t i = 0; i < n; ++i ) {
+            if ( fused_tail() ) {
+                if ( int rc = launch_window_fused() ) return rc;
+                continue;
+            }
             if ( int rc = launch_dispatch() ) return rc;
             if ( n_ranks > 1 )
                 if ( int rc = launch_publish() ) return rc;
@@ -2199,7 +2228,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
             if ( !rc && d.aux_stride ) {
                 seed_mt_kernel<<<(c.hi - c.lo + 127) / 128, 128, 0, main_stream>>>(d, c.lo, c.hi);
                 // first MT19937 generation (and route digest) of every generator seeded above
-                maintenance_kernel<<<(uint32_t)n_sm0 * 8, 256, 0, main_stream>>>(d, 1, c.lo, c.hi);
+                maintenance_kernel<<<(uint32_t)n_sm0 * 8, 256, 0, main_stream>>>(d, 1, c.lo, c.hi, 0, 0);
                 e->launches += 2;
             }
         }
@@ -2307,7 +2336,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         rc |= e->alloc(&d.prof_clock_cyc, d.n_local);
     }
     if ( e->pf_on ) {
-        rc |= e->alloc(&d.fb_list, d.nbins, false);
+        rc |= e->alloc(&d.fb_list, d.nbins); // zeroed: an entry is block + 1, 0 = not written yet
         rc |= e->alloc(&d.maint_list, d.n_local, false);
     }
     rc |= e->alloc(&e->d_results, (size_t)d.n_local * NRESULT, false); // results_kernel writes every word it exports
@@ -2356,7 +2385,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     e->smem_bytes = (size_t)d.lmax * 16 + (size_t)d.emax * (has_payload ? 8 : 0) + (size_t)d.emax * 16 +
                     (size_t)(BLOCK + 1 + BLOCK + BLOCK + BLOCK / 32 + 1 + 4 + 32 + 32) * 4 + (size_t)d.emax * 2 +
                     (size_t)BLOCK * 2 + 16;
-    if ( e->smem_bytes > 227 * 1024 ) {
+    if ( e->smem_bytes > 226 * 1024 ) {
         set_error("engine_create: smem_events too large for 227 KB of shared memory");
         sstb200_engine_destroy(e);
         return -1;
@@ -2378,7 +2407,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     if ( e->pf_on ) {
         // persistent grid: as many CTAs as fit, each walks blocks b, b + grid, ...
         e->pf_smem = (size_t)BLOCK * MeshElement::RECORD_BYTES + ((size_t)BLOCK * uni0) * 16 + (size_t)d.pf_rcap * 16 +
-                     (size_t)(2 * BLOCK + 3 * PF_HT + 2) * 4 + 3 * 8 + 16;
+                     (size_t)(2 * BLOCK + 3 * PF_HT + 4) * 4 + 3 * 8 + 16;
         CUDA_OK(cudaFuncSetAttribute(window_parallel_kernel<MeshElement>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (int)e->pf_smem));
         int per_sm = 0;
@@ -2388,6 +2417,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         if ( const char* g = getenv("SSTB200_PF_CTAS") ) per_sm = std::max(1, atoi(g));
         e->pf_grid = std::min<uint32_t>(d.nbins, (uint32_t)(per_sm * n_sm));
         e->fb_grid = std::min<uint32_t>(d.nbins, (uint32_t)(2 * n_sm));
+        if ( e->pf_smem < e->smem_bytes ) e->pf_smem = e->smem_bytes; // the kernel re-runs blocks in the sequential form
     }
     // (the Ctrl mirror is pinned memory of the engine: later copies on the same stream are ordered behind this one)
     if ( create_timing ) CUDA_OK(cudaStreamSynchronize(e->stream));
@@ -2432,6 +2462,19 @@ sstb200_engine_setup(sstb200_engine* e)
     CUDA_OK(cudaGetLastError());
     e->is_setup = true;
     return 0;
+}
+
+int
+sstb200_engine_prepare_run(sstb200_engine* e, uint32_t check_every)
+{
+    if ( !e ) return -1;
+    CUDA_OK(cudaSetDevice(e->device));
+    if ( !e->is_setup ) {
+        set_error("engine_prepare_run before engine_setup");
+        return -1;
+    }
+    if ( e->n_ranks > 1 && !(e->d.peer_on && e->peer_spin) ) return 0; // stepped by the driver: nothing to capture
+    return e->launch_windows(check_every ? check_every : 64, true);
 }
 
 int

@@ -35,6 +35,11 @@ constexpr int      PF_ROUNDS  = 5; // records tid, tid+256, ... : up to 1280 sta
 constexpr uint32_t PF_HT      = 128;
 constexpr uint32_t PF_NONE    = 0xFFFFFFFFu;
 
+// the end of a window (engine.cu): maintenance_kernel's last CTA runs it in the native run loop
+__device__ void advance_fold(const Dev& d);
+__device__ __forceinline__ void peer_post(const Dev& d);
+__device__ __forceinline__ void peer_wait_and_fold(const Dev& d, int spin);
+
 __device__ __forceinline__ uint32_t
 smem_addr(const void* p)
 {
@@ -80,9 +85,17 @@ pf_far_slot(uint32_t dt, uint32_t w, uint32_t slot, uint32_t W)
     return (slot + dk) % W;
 }
 
+// the sequential form of one block, kept out of line: the register allocation of the event-parallel loop stays its own
+template <class E>
+__device__ __noinline__ void
+run_block_sequential(const Dev& d, uint32_t bin, uint8_t* smem)
+{
+    dispatch_block<E::HAS_PAYLOAD, false, E>(d, bin, smem);
+}
+
 template <class E>
 __global__ void __launch_bounds__(PF_THREADS, 3)
-window_parallel_kernel(Dev d)
+window_parallel_kernel(const __grid_constant__ Dev d) // (grid constant: run_block_sequential takes it by reference)
 {
     extern __shared__ __align__(128) uint8_t pf_smem[];
     Ctrl* const ctrl = d.ctrl;
@@ -107,7 +120,8 @@ window_parallel_kernel(Dev d)
     uint32_t*   ht_cnt  = ht_key + PF_HT;
     uint32_t*   ht_base = ht_cnt + PF_HT;
     uint32_t*   s_nin   = ht_base + PF_HT;                                    // [2] fill of the bin in s_rec, by parity
-    uint64_t*   s_bar   = reinterpret_cast<uint64_t*>(s_nin + 2);             // [3] hot, link, rec
+    uint32_t*   s_nbin  = s_nin + 2;                                          // [2] the block that bin belongs to
+    uint64_t*   s_bar   = reinterpret_cast<uint64_t*>(s_nbin + 2);            // [3] hot, link, rec
 
     auto issue_hot = [&](uint32_t b) {
         const uint32_t nc    = min((uint32_t)BLOCK, d.n_local - b * BLOCK);
@@ -146,11 +160,16 @@ window_parallel_kernel(Dev d)
     __syncthreads();
 
     uint32_t delivered = 0, unsent = 0, max_fill = 0;
-    for ( uint32_t it = 0; bin < d.nbins; ++it, bin += gridDim.x ) {
+    // Blocks are handed out dynamically (Ctrl::pf_next, reset when a window opens): the CTAs of a rank
+    // that holds 8192 blocks make ~18 rounds each, and with a fixed stride the last round would leave most SMs idle
+    // while the slowest CTAs finish.
+    for ( uint32_t it = 0; bin < d.nbins; ++it, bin = s_nbin[it & 1u] ) {
         const uint32_t ph  = it & 1u;
-        const uint32_t nxt = bin + gridDim.x;
-        uint32_t       n_next = 0;
-        if ( tid == 0 && nxt < d.nbins ) n_next = d.bin_count[slot * d.nbins + nxt]; // used after the first barrier
+        uint32_t       nxt = 0xFFFFFFFFu, n_next = 0; // thread 0 only
+        if ( tid == 0 ) {
+            nxt = gridDim.x + atomicAdd(&ctrl->pf_next, 1u); // the first gridDim.x blocks are the CTAs' own
+            if ( nxt < d.nbins ) n_next = d.bin_count[slot * d.nbins + nxt]; // used after the first barrier
+        }
         if ( tid < PF_HT ) {
             ht_key[tid] = PF_NONE;
             ht_cnt[tid] = 0;
@@ -187,9 +206,12 @@ window_parallel_kernel(Dev d)
         s_hdr[tid]        = my_hdr;
         __syncthreads();
         // the record buffer is free: the next block's bin is copied while this block runs
-        if ( tid == 0 && nxt < d.nbins ) {
-            s_nin[ph ^ 1u] = n_next;
-            issue_rec(nxt, n_next);
+        if ( tid == 0 ) {
+            s_nbin[ph ^ 1u] = nxt;
+            if ( nxt < d.nbins ) {
+                s_nin[ph ^ 1u] = n_next;
+                issue_rec(nxt, n_next);
+            }
         }
         const uint32_t n = s_cnt[tid];
         s_cnt[tid]       = 0;
@@ -199,7 +221,7 @@ window_parallel_kernel(Dev d)
 
         if ( any_bad ) {
             // nothing has been written: the sequential form runs this block after this kernel
-            if ( tid == 0 ) d.fb_list[atomicAdd(&ctrl->fb_n, 1u)] = bin;
+            if ( tid == 0 ) d.fb_list[atomicAdd(&ctrl->fb_n, 1u)] = bin + 1; // 0 = entry not written yet
             __syncthreads();
             if ( tid == 0 && nxt < d.nbins ) {
                 issue_hot(nxt);
@@ -327,6 +349,37 @@ window_parallel_kernel(Dev d)
         if ( max_fill > ctrl->max_bin_fill ) atomicMax(&ctrl->max_bin_fill, (unsigned long long)max_fill);
         if ( max_fill > ctrl->max_due ) atomicMax(&ctrl->max_due, (unsigned long long)max_fill);
     }
+
+    // ---- the blocks left to the sequential form (Ctrl::fb_n entries of fb_list) are run here, by the CTAs that have
+    // no block of their own left: every entry is appended by a CTA that comes through here afterwards, so none is
+    // missed, and a block re-run by one CTA while others still work on theirs is no different from two blocks of the
+    // event-parallel form running side by side.  An index is taken only when an entry exists (CAS), and the entry
+    // itself is waited for: its writer bumps the count first.
+    for ( ;; ) {
+        __syncthreads();
+        if ( tid == 0 ) {
+            uint32_t take = PF_NONE;
+            uint32_t i    = *(volatile uint32_t*)&ctrl->fb_taken;
+            while ( i < *(volatile uint32_t*)&ctrl->fb_n ) {
+                const uint32_t old = atomicCAS(&ctrl->fb_taken, i, i + 1);
+                if ( old == i ) {
+                    volatile uint32_t* ent = d.fb_list + i;
+                    uint32_t           v;
+                    while ( (v = *ent) == 0 ) {}
+                    *ent = 0;
+                    take = v - 1;
+                    break;
+                }
+                i = old;
+            }
+            s_nbin[0] = take;
+        }
+        __syncthreads();
+        const uint32_t fb = s_nbin[0];
+        if ( fb == PF_NONE ) break;
+        __syncthreads(); // s_nbin lies inside the area dispatch_block lays out afresh
+        run_block_sequential<E>(d, fb, pf_smem);
+    }
 }
 
 // ---- MT19937: next generation of one generator by a warp.  gen = 624 words of shared memory owned by the warp.
@@ -391,17 +444,21 @@ MeshElement::maintain(uint32_t op, uint8_t* rec, uint8_t* aux, const int64_t* pa
     if ( ok && lane < (op == MAINT_INIT ? ROUTE_DIGEST_WORDS : ROUTE_DIGEST_SPLIT) ) dig[lane] = route_digest_word(gen, lane, ng);
 }
 
-// after a window (list mode) or before setup() (init_all: every local component in [c_lo, c_hi)): a warp per entry
+// after a window (list mode) or before setup() (init_all: every local component in [c_lo, c_hi)): a warp per entry.
+// advance != 0 (list mode, the native run loop): the last CTA to finish ends the window -- 1 single rank
+// (advance_fold), 2 peer mode (mailbox post, wait for the other ranks, fold): no separate launch for it.
 __global__ void __launch_bounds__(256)
-maintenance_kernel(Dev d, int init_all, uint32_t c_lo, uint32_t c_hi)
+maintenance_kernel(Dev d, int init_all, uint32_t c_lo, uint32_t c_hi, int advance, int spin)
 {
     __shared__ __align__(16) uint32_t s_gen[8][MT_N];
+    __shared__ uint32_t               s_last;
     const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     const uint32_t nw = gridDim.x * 8, gw = blockIdx.x * 8 + wic;
     uint32_t       n  = c_hi - c_lo;
+    Ctrl* const    c  = d.ctrl;
     if ( !init_all ) {
-        if ( d.ctrl->done ) return;
-        n = min(d.ctrl->maint_n, d.n_local);
+        if ( c->done ) return;
+        n = min(c->maint_n, d.n_local);
     }
     for ( uint32_t i = gw; i < n; i += nw ) {
         const uint32_t ent = init_all ? ((c_lo + i) | ((uint32_t)MAINT_INIT << 30)) : d.maint_list[i];
@@ -414,6 +471,20 @@ maintenance_kernel(Dev d, int init_all, uint32_t c_lo, uint32_t c_hi)
         });
         __syncwarp();
     }
+    if ( !advance ) return;
+    __threadfence();
+    __syncthreads();
+    if ( threadIdx.x == 0 ) s_last = atomicAdd(&c->tail_done, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if ( !s_last ) return;
+    __threadfence();
+    if ( threadIdx.x == 0 ) c->tail_done = 0;
+    if ( advance == 2 ) {
+        peer_post(d);
+        peer_wait_and_fold(d, spin);
+    }
+    else if ( threadIdx.x == 0 )
+        advance_fold(d);
 }
 
 } // namespace sstb200

@@ -64,7 +64,7 @@ EXPORTS = [
     "sstb200_engine_stream",
     "sstb200_peer_region_bytes", "sstb200_peer_arena_create", "sstb200_peer_arena_open", "sstb200_peer_arena_destroy",
     "sstb200_engine_in_arena", "sstb200_engine_peer_connect_arena", "sstb200_engine_output",
-    "sstb200_engine_handler_times", "sstb200_engine_sync_profile",
+    "sstb200_engine_handler_times", "sstb200_engine_sync_profile", "sstb200_engine_prepare_run",
 ]
 
 _lib = None
@@ -91,6 +91,7 @@ def lib():
     L.sstb200_engine_destroy.restype = None
     L.sstb200_engine_setup.argtypes = [C.c_void_p]
     L.sstb200_engine_run.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_int)]
+    L.sstb200_engine_prepare_run.argtypes = [C.c_void_p, C.c_uint32]
     for f in ("dispatch", "ingest", "advance"):
         getattr(L, f"sstb200_engine_{f}").argtypes = [C.c_void_p]
     L.sstb200_engine_exchange_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
@@ -366,6 +367,10 @@ class Engine:
             self.raise_on_error()
         _check(rc, "engine_run")
         return bool(fin.value)
+
+    def prepare_run(self, check_every: int = 64):
+        """Capture the CUDA graph of a chunk of `check_every` windows ahead of the first run() with that chunk size."""
+        _check(self._L.sstb200_engine_prepare_run(self._h, check_every), "engine_prepare_run")
 
     def dispatch(self):
         _check(self._L.sstb200_engine_dispatch(self._h), "engine_dispatch")
