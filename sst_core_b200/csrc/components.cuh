@@ -705,6 +705,10 @@ struct PholdElement
     {
         return true;
     }
+    // ordered event-parallel form (ordered_form.cuh): no clock, at most one send per delivery, the handler touches
+    // nothing but its State, the event and the context's now / nports / stats_on / send / connected
+    static constexpr bool     ORDERED_EVENTS = true;
+    static constexpr uint32_t ORD_MAX_EVENTS = 32; // deliveries of one component per window the form takes
     // statistics are collected per window into an empty accumulator and folded into memory only if the window
     // added data: the statistics region is not even read by windows that leave it alone
     __device__ static void initStats(State& s) { s.delay.init(); }
@@ -1463,6 +1467,7 @@ struct ElementInfo
     bool        prints = false;                   // calls ctx.output(): the engine keeps an output log
     bool        self_links = false;               // configures self links
     bool        stat_clock = false;               // has statistics under the statistics engine (STAT_CLOCK)
+    bool        ordered_events = false;           // has the ordered event-parallel form (ORDERED_EVENTS)
 };
 
 } // namespace sstb200

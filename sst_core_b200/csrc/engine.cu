@@ -1260,6 +1260,7 @@ dispatch_kernel(Dev d)
 
 } // namespace sstb200
 #include "parallel_form.cuh"
+#include "ordered_form.cuh"
 namespace sstb200 {
 
 // ---- wire-up on the device: link row of every local directed port = {peer port, component owning the peer (binary
@@ -1685,7 +1686,8 @@ element_info()
 {
     static_assert(E::TYPE > 0 && E::TYPE < TYPE_MAX, "element type codes are 1..31");
     return ElementInfo { E::TYPE, E::ELI_NAME, E::RECORD_BYTES, E::AUX_BYTES, E::HAS_PAYLOAD, E::PARALLEL_EVENTS,
-        E::TIES_INTERCHANGEABLE, E::DESCRIPTION, prints_of<E>::value, self_links_of<E>::value, stat_clock_of<E>::value };
+        E::TIES_INTERCHANGEABLE, E::DESCRIPTION, prints_of<E>::value, self_links_of<E>::value, stat_clock_of<E>::value,
+        ordered_of<E>::value };
 }
 static const ElementInfo kElements[] = {
 #define SSTB200_ELEMENT(E) element_info<E>(),
@@ -1767,6 +1769,7 @@ struct sstb200_engine
     // event-parallel form (parallel_form.cuh): on when every local component is of one element type with
     // PARALLEL_EVENTS and nothing of the model needs what the form leaves out (see engine_create)
     bool     pf_on = false;
+    uint32_t pf_ordered = 0; // element type whose ordered form (ordered_form.cuh) runs the windows, 0 = MessageMesh form
     size_t   pf_smem = 0;
     uint32_t pf_grid = 0, fb_grid = 0, maint_grid = 0;
     // one lookahead window: the event-parallel kernel, the sequential kernel over the blocks it left (or over all
@@ -1781,7 +1784,7 @@ struct sstb200_engine
             launches++;
         }
         else if ( pf_on ) {
-            window_parallel_kernel<MeshElement><<<pf_grid, PF_THREADS, pf_smem, stream>>>(d);
+            launch_form();
             maintenance_kernel<<<maint_grid, 256, 0, stream>>>(d, 0, 0, 0, 0, 0); // the window is ended by the driver
             launches += 2;
         }
@@ -1814,9 +1817,23 @@ struct sstb200_engine
     // take, sequentially) + the maintenance kernel, whose last CTA ends the window -- two launches per window
     bool     fused_tail() const { return pf_on && (n_ranks == 1 || (d.peer_on && peer_spin)); }
     uint32_t launches_per_window() const { return fused_tail() ? 2u : (pf_on ? 3u : 2u) + (n_ranks > 1 && !(d.peer_on && peer_spin) ? 1u : 0u); }
+    // the window kernel of the rank's form: MessageMesh form (pf_ordered 0) or the ordered form of element type pf_ordered
+    void launch_form()
+    {
+        if ( !pf_ordered ) {
+            window_parallel_kernel<MeshElement><<<pf_grid, PF_THREADS, pf_smem, stream>>>(d);
+            return;
+        }
+#define SSTB200_ELEMENT(E)                                                                                       \
+    if constexpr ( ordered_of<E>::value ) {                                                                      \
+        if ( pf_ordered == E::TYPE ) window_ordered_kernel<E><<<pf_grid, OF_THREADS, pf_smem, stream>>>(d);      \
+    }
+#include "elements.def"
+#undef SSTB200_ELEMENT
+    }
     int      launch_window_fused()
     {
-        window_parallel_kernel<MeshElement><<<pf_grid, PF_THREADS, pf_smem, stream>>>(d);
+        launch_form();
         maintenance_kernel<<<maint_grid, 256, 0, stream>>>(d, 0, 0, 0, n_ranks > 1 ? 2 : 1, peer_spin ? 1 : 0);
         launches += 2;
         CUDA_OK(cudaGetLastError());
@@ -2276,6 +2293,19 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     e->pf_on = any_parallel && d.uniform_type == TYPE_MESH && d.ctl_free && uni_ok && uni0 && (uni0 & (uni0 - 1)) == 0 &&
                (size_t)uni0 * BLOCK <= 2048 && !has_payload && !o->handler_counts && mx_lat_all < 0x7fffffffull &&
                getenv("SSTB200_NO_PARALLEL_FORM") == nullptr;
+    // The ordered event-parallel form (ordered_form.cuh): one local element type that declares ORDERED_EVENTS and whose
+    // record is the rank's state stride; no local clocks; the model's payload setting is the element's; no tracing, no
+    // handler counting; a power-of-two port count per component; an even bin capacity (8-byte payloads move in 16-byte
+    // pieces); link latencies below 2^31.
+    if ( !e->pf_on && d.uniform_type && by_type[d.uniform_type] && by_type[d.uniform_type]->ordered_events && !any_clock &&
+         has_payload == by_type[d.uniform_type]->has_payload && has_payload && o->trace_capacity == 0 && !o->handler_counts &&
+         uni_ok && uni0 && (uni0 & (uni0 - 1)) == 0 && (size_t)uni0 * BLOCK <= 2048 && mx_lat_all < 0x7fffffffull &&
+         d.state_stride == by_type[d.uniform_type]->state_bytes && (d.cap & 1u) == 0 && (w * uni0) < (1ull << 32) &&
+         getenv("SSTB200_NO_PARALLEL_FORM") == nullptr ) {
+        e->pf_on      = true;
+        e->pf_ordered = d.uniform_type;
+        d.pf_rcap &= ~1u;
+    }
 
     // (4) the remaining allocations (engine stream)
     rc |= e->alloc(&d.ctl, d.n_local, false); // every record is written by setup_kernel
@@ -2406,13 +2436,29 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     e->maint_grid = (uint32_t)n_sm * 8;
     if ( e->pf_on ) {
         // persistent grid: as many CTAs as fit, each walks blocks b, b + grid, ...
+        int per_sm = 0;
+        if ( e->pf_ordered ) {
+#define SSTB200_ELEMENT(E)                                                                                       \
+    if constexpr ( ordered_of<E>::value ) {                                                                      \
+        if ( e->pf_ordered == E::TYPE ) {                                                                        \
+            e->pf_smem = std::max(of_smem_bytes<E>(d.pf_rcap, d.uniform_shift), e->smem_bytes);                  \
+            CUDA_OK(cudaFuncSetAttribute(window_ordered_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                (int)e->pf_smem));                                                                               \
+            CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, window_ordered_kernel<E>, OF_THREADS, \
+                e->pf_smem));                                                                                    \
+        }                                                                                                        \
+    }
+#include "elements.def"
+#undef SSTB200_ELEMENT
+        }
+        else {
         e->pf_smem = (size_t)BLOCK * MeshElement::RECORD_BYTES + ((size_t)BLOCK * uni0) * 16 + (size_t)d.pf_rcap * 16 +
                      (size_t)(2 * BLOCK + 3 * PF_HT + 4) * 4 + 3 * 8 + 16;
         CUDA_OK(cudaFuncSetAttribute(window_parallel_kernel<MeshElement>, cudaFuncAttributeMaxDynamicSharedMemorySize,
             (int)e->pf_smem));
-        int per_sm = 0;
         CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, window_parallel_kernel<MeshElement>, PF_THREADS,
             e->pf_smem));
+        }
         if ( per_sm < 1 ) per_sm = 1;
         if ( const char* g = getenv("SSTB200_PF_CTAS") ) per_sm = std::max(1, atoi(g));
         e->pf_grid = std::min<uint32_t>(d.nbins, (uint32_t)(per_sm * n_sm));

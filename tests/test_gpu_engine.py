@@ -101,6 +101,37 @@ def test_phold_zero_extra_delay_bursts_keep_link_fifo():
                           bin_capacity=8192, smem_events=6144)
 
 
+def test_phold_ordered_form_and_its_per_block_fallbacks(monkeypatch):
+    # PHOLD on a rank of its own takes the ordered event-parallel form (ordered_form.cuh); blocks it cannot take in some
+    # window are re-run in the sequential form.  Every case below must give the oracle's records bit for bit.
+    m = models.phold_model(40, 30, stop_at="60ns", stats_enabled=True)
+    res, st, _ = assert_same_as_oracle(m, calendar_slots=16)
+    # the whole run in the sequential form: same records
+    monkeypatch.setenv("SSTB200_NO_PARALLEL_FORM", "1")
+    res_seq, _ = run_gpu(m, calendar_slots=16)
+    monkeypatch.delenv("SSTB200_NO_PARALLEL_FORM")
+    assert np.array_equal(res, res_seq)
+    # (1) a staging buffer shorter than the bins: the blocks fall back
+    monkeypatch.setenv("SSTB200_PF_RCAP", "64")
+    assert_same_as_oracle(m, calendar_slots=16)
+    monkeypatch.delenv("SSTB200_PF_RCAP")
+    # (2) a stop time inside a window: events at or after it are never delivered (StopAction)
+    assert_same_as_oracle(models.phold_model(40, 30, stop_at="30500ps", stats_enabled=True), calendar_slots=16)
+    # (3) bursts: more deliveries per component and window than the form takes
+    assert_same_as_oracle(models.phold_model(8, 8, stop_at="40ns", init_events=50, delay_mod=1500, stats_enabled=True),
+                          calendar_slots=16, bin_capacity=8192, smem_events=4096)
+    # (4) unconnected ports: a send through one takes no sequence number and the event is gone
+    m4 = models.phold_model(40, 30, stop_at="60ns", stats_enabled=True)
+    rng = np.random.default_rng(5)
+    for p in rng.choice(m4.peer_port.shape[0], 60, replace=False):
+        q = m4.peer_port[p]
+        if q != 0xFFFFFFFF:
+            m4.peer_port[p] = m4.peer_port[q] = 0xFFFFFFFF
+    assert_same_as_oracle(m4, calendar_slots=16)
+    # (5) a calendar shallower than the delays: parked events are not due when their slot comes round
+    assert_same_as_oracle(m, calendar_slots=4, bin_capacity=8192, smem_events=4096)
+
+
 def test_phold_large_vs_oracle():
     assert_same_as_oracle(models.phold_model(128, 128, stop_at="40ns", stats_enabled=True), calendar_slots=16)
 
