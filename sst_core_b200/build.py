@@ -10,7 +10,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libsstb200.so"
 SOURCES = [CSRC / "engine.cu", CSRC / "partition.cc"]
-DEPS = SOURCES + [CSRC / "components.cuh", CSRC / "rng.cuh", CSRC / "parallel_form.cuh", CSRC / "ordered_form.cuh", CSRC / "elements.def",
+DEPS = SOURCES + [CSRC / "components.cuh", CSRC / "rng.cuh", CSRC / "parallel_form.cuh", CSRC / "ordered_form.cuh", CSRC / "clock_form.cuh", CSRC / "elements.def",
                   HERE.parent / "include" / "sstb200.h"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--expt-relaxed-constexpr",

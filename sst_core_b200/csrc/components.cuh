@@ -738,11 +738,12 @@ struct ClockNodeElement
     static constexpr bool        HAS_PAYLOAD = false;
     struct State
     {
-        // [0,48) mutable core
-        uint64_t     ticks, last_cycle, recv, hash;
+        // [0,48) mutable core; [0,32) is all a clock tick changes (TICK_STORE_END)
         MarsagliaDev rng;
         uint32_t     neighbor;
         uint32_t     pad0;
+        uint64_t     ticks, last_cycle;
+        uint64_t     recv, hash;
         // [48,64) construction constants
         int32_t  commFreq;
         uint32_t pad1;
@@ -751,6 +752,9 @@ struct ClockNodeElement
         Accumulator<int32_t> count[4];
     };
     static constexpr uint32_t STORE_END = 48, CONST_END = 64, STATS_END = 160;
+    // clock form (clock_form.cuh): one clock handler, no self links, no console output, nothing but State / ctx used
+    static constexpr bool     CLOCK_FORM = true;
+    static constexpr uint32_t TICK_STORE_END = 32; // a window without deliveries leaves [32, STORE_END) as it was
     static constexpr bool     TIES_INTERCHANGEABLE = false; // the delivery hash / handlers see port and order
     static constexpr bool     STATS_EVERY_EVENT = false;
     static constexpr bool     PARALLEL_EVENTS = false; // handlers chain through the state (hash, RNG): sequential
@@ -844,6 +848,7 @@ struct CoreTestElement
         Accumulator<int32_t> count[4];
     };
     static constexpr uint32_t STORE_END = 16, CONST_END = 32, STATS_END = 128;
+    static constexpr bool     CLOCK_FORM = true; // clock form (clock_form.cuh)
     static constexpr bool     TIES_INTERCHANGEABLE = true; // handleEvent looks at nothing but the payload it deletes
     static constexpr bool     STATS_EVERY_EVENT = false;
     static constexpr bool     PARALLEL_EVENTS      = false;
@@ -1468,6 +1473,7 @@ struct ElementInfo
     bool        self_links = false;               // configures self links
     bool        stat_clock = false;               // has statistics under the statistics engine (STAT_CLOCK)
     bool        ordered_events = false;           // has the ordered event-parallel form (ORDERED_EVENTS)
+    bool        clock_form = false;               // has the clock form (CLOCK_FORM)
 };
 
 } // namespace sstb200

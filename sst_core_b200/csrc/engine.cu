@@ -1261,6 +1261,7 @@ dispatch_kernel(Dev d)
 } // namespace sstb200
 #include "parallel_form.cuh"
 #include "ordered_form.cuh"
+#include "clock_form.cuh"
 namespace sstb200 {
 
 // ---- wire-up on the device: link row of every local directed port = {peer port, component owning the peer (binary
@@ -1687,7 +1688,7 @@ element_info()
     static_assert(E::TYPE > 0 && E::TYPE < TYPE_MAX, "element type codes are 1..31");
     return ElementInfo { E::TYPE, E::ELI_NAME, E::RECORD_BYTES, E::AUX_BYTES, E::HAS_PAYLOAD, E::PARALLEL_EVENTS,
         E::TIES_INTERCHANGEABLE, E::DESCRIPTION, prints_of<E>::value, self_links_of<E>::value, stat_clock_of<E>::value,
-        ordered_of<E>::value };
+        ordered_of<E>::value, clock_form_of<E>::value };
 }
 static const ElementInfo kElements[] = {
 #define SSTB200_ELEMENT(E) element_info<E>(),
@@ -1770,6 +1771,7 @@ struct sstb200_engine
     // PARALLEL_EVENTS and nothing of the model needs what the form leaves out (see engine_create)
     bool     pf_on = false;
     uint32_t pf_ordered = 0; // element type whose ordered form (ordered_form.cuh) runs the windows, 0 = MessageMesh form
+    uint32_t pf_clock   = 0; // element type whose clock form (clock_form.cuh) runs the windows
     size_t   pf_smem = 0;
     uint32_t pf_grid = 0, fb_grid = 0, maint_grid = 0;
     // one lookahead window: the event-parallel kernel, the sequential kernel over the blocks it left (or over all
@@ -1820,6 +1822,15 @@ struct sstb200_engine
     // the window kernel of the rank's form: MessageMesh form (pf_ordered 0) or the ordered form of element type pf_ordered
     void launch_form()
     {
+        if ( pf_clock ) {
+#define SSTB200_ELEMENT(E)                                                                                       \
+    if constexpr ( clock_form_of<E>::value ) {                                                                   \
+        if ( pf_clock == E::TYPE ) window_clock_kernel<E><<<pf_grid, BLOCK, pf_smem, stream>>>(d);               \
+    }
+#include "elements.def"
+#undef SSTB200_ELEMENT
+            return;
+        }
         if ( !pf_ordered ) {
             window_parallel_kernel<MeshElement><<<pf_grid, PF_THREADS, pf_smem, stream>>>(d);
             return;
@@ -2171,6 +2182,16 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         }
     }
     d.state_stride = (state_stride + 15u) & ~15u;
+    // elements whose hot part is the head of a longer record (statistics behind it): records start on 64-byte
+    // boundaries, so that the 32/64 hot bytes of a component are one DRAM burst and not the tails of two.  The forms
+    // that stage whole records with one bulk copy keep them packed.
+    {
+        bool packed = false;
+        for ( uint32_t ty = 0; ty < TYPE_MAX; ++ty )
+            if ( (seen_local >> ty & 1u) && by_type[ty] && (by_type[ty]->parallel_events || by_type[ty]->ordered_events) )
+                packed = true;
+        if ( !packed && d.state_stride > 64 ) d.state_stride = (d.state_stride + 63u) & ~63u;
+    }
     d.aux_stride   = (aux_stride + 31u) & ~31u;
     d.has_payload  = has_payload;
     lap("element scans", nullptr);
@@ -2306,6 +2327,14 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         e->pf_ordered = d.uniform_type;
         d.pf_rcap &= ~1u;
     }
+    // The clock form (clock_form.cuh): one local element type that declares CLOCK_FORM; the model's payload setting is
+    // the element's; no tracing, no handler counting; a power-of-two port count per component.
+    if ( !e->pf_on && d.uniform_type && by_type[d.uniform_type] && by_type[d.uniform_type]->clock_form &&
+         has_payload == by_type[d.uniform_type]->has_payload && o->trace_capacity == 0 && !o->handler_counts && uni_ok &&
+         uni0 && (uni0 & (uni0 - 1)) == 0 && getenv("SSTB200_NO_PARALLEL_FORM") == nullptr ) {
+        e->pf_on    = true;
+        e->pf_clock = d.uniform_type;
+    }
 
     // (4) the remaining allocations (engine stream)
     rc |= e->alloc(&d.ctl, d.n_local, false); // every record is written by setup_kernel
@@ -2437,13 +2466,27 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
     if ( e->pf_on ) {
         // persistent grid: as many CTAs as fit, each walks blocks b, b + grid, ...
         int per_sm = 0;
-        if ( e->pf_ordered ) {
+        if ( e->pf_clock ) {
+#define SSTB200_ELEMENT(E)                                                                                       \
+    if constexpr ( clock_form_of<E>::value ) {                                                                   \
+        if ( e->pf_clock == E::TYPE ) {                                                                          \
+            e->pf_smem = e->smem_bytes;                                                                          \
+            CUDA_OK(cudaFuncSetAttribute(window_clock_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                226 * 1024)); /* process-wide: engines of several sizes share it; 1 KB for its static arrays */ \
+            CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, window_clock_kernel<E>, BLOCK,        \
+                e->pf_smem));                                                                                    \
+        }                                                                                                        \
+    }
+#include "elements.def"
+#undef SSTB200_ELEMENT
+        }
+        else if ( e->pf_ordered ) {
 #define SSTB200_ELEMENT(E)                                                                                       \
     if constexpr ( ordered_of<E>::value ) {                                                                      \
         if ( e->pf_ordered == E::TYPE ) {                                                                        \
             e->pf_smem = std::max(of_smem_bytes<E>(d.pf_rcap, d.uniform_shift), e->smem_bytes);                  \
             CUDA_OK(cudaFuncSetAttribute(window_ordered_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                (int)e->pf_smem));                                                                               \
+                227 * 1024));                                                                                    \
             CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, window_ordered_kernel<E>, OF_THREADS, \
                 e->pf_smem));                                                                                    \
         }                                                                                                        \
@@ -2455,7 +2498,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         e->pf_smem = (size_t)BLOCK * MeshElement::RECORD_BYTES + ((size_t)BLOCK * uni0) * 16 + (size_t)d.pf_rcap * 16 +
                      (size_t)(2 * BLOCK + 3 * PF_HT + 4) * 4 + 3 * 8 + 16;
         CUDA_OK(cudaFuncSetAttribute(window_parallel_kernel<MeshElement>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            (int)e->pf_smem));
+            227 * 1024));
         CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, window_parallel_kernel<MeshElement>, PF_THREADS,
             e->pf_smem));
         }
