@@ -42,6 +42,17 @@ struct tick_store_end_of<E, std::void_t<decltype(E::TICK_STORE_END)>> : std::int
 
 constexpr uint32_t CF_MAX_IN = 32; // events in a block's bin the form takes
 
+// 16-byte load that asks DRAM for the 64-byte half line only (SASS LDG.E.LTC64B): a plain load of a line that is not
+// in L2 brings all 128 bytes (profiles/r01_notes.md, sector accounting), and a component's hot state is 64 bytes of a
+// record whose rest is cold
+__device__ __forceinline__ uint4
+ldg_half_line(const uint4* p)
+{
+    uint4 v;
+    asm volatile("ld.global.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 template <class E>
 __global__ void __launch_bounds__(BLOCK, 2)
 window_clock_kernel(const __grid_constant__ Dev d)
@@ -92,7 +103,7 @@ window_clock_kernel(const __grid_constant__ Dev d)
         const uint4* g = reinterpret_cast<const uint4*>(d.state + (uint64_t)(b * BLOCK + tid) * d.state_stride);
 #pragma unroll
         for ( int i = 0; i < NHOT; ++i )
-            h[i] = g[i];
+            h[i] = ldg_half_line(g + i);
     };
     Pre  cur      = fetch_ctl(blockIdx.x);
     Pre  nxt      = fetch_ctl(blockIdx.x + gridDim.x);
