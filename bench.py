@@ -529,8 +529,9 @@ def ours(a):
                        **{k: v for k, v in opts.items()}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic,
-                         "kernel": "window_parallel_kernel (+ window_tail_kernel of the same window: fallback blocks, "
-                                   "generator maintenance)" if a.workload == "mesh" else "dispatch_kernel",
+                         "kernel": {"mesh": "window_parallel_kernel (+ maintenance_kernel of the same window: generator upkeep)",
+                                    "phold": "window_ordered_kernel<PholdElement> (+ maintenance_kernel with nothing to do)",
+                                    "clockpop": "window_clock_kernel<ClockNodeElement> (+ maintenance_kernel with nothing to do)"}[a.workload],
                          "ms_per_launch": ms_dispatch,
                          "algorithmic_bytes_per_event": ALGO_BYTES[a.workload], "peak_source": peak_src,
                          # what the kernel really moves (ncu dram__bytes of the same kernel): the route digest replaces

@@ -1499,35 +1499,61 @@ results_kernel(Dev d, uint64_t* out, uint32_t words)
 // Marsaglia / xorshift (8 / 16 bytes of state): a lane per generator, 64 draws at a time through a shared-memory tile;
 // the warp then writes one generator's 64 draws per store instruction (256 contiguous bytes), so the stores are full
 // DRAM lines instead of one 4-byte word per lane at a stride of `draws` words.
-constexpr uint32_t RNG_TILE = 64;
+constexpr uint32_t RNG_TILE = 64, RNG_ROW = RNG_TILE + 4; // row stride 68 words: rows 16-byte aligned, 16-byte
+                                                          // accesses of 8 lanes (a quarter warp) on distinct banks
 template <class G>
 __device__ __forceinline__ void
 small_stream_body(G& g, bool valid, uint64_t draws, uint32_t* warp_out, uint64_t stream_stride, uint32_t lane,
-    uint32_t (*tile)[RNG_TILE + 1], unsigned long long* checksum)
+    uint32_t (*tile)[RNG_ROW], unsigned long long* checksum)
 {
     unsigned long long cs = 0;
+    const bool         wide = warp_out && (stream_stride & 3u) == 0 && (((uintptr_t)warp_out) & 15u) == 0;
     for ( uint64_t base = 0; base < draws; base += RNG_TILE ) {
         const uint32_t n = (uint32_t)min((uint64_t)RNG_TILE, draws - base);
         if ( valid ) {
-#pragma unroll 8
-            for ( uint32_t j = 0; j < n; ++j ) {
-                const uint32_t v = g.u32();
-                cs += (base + j + 1) * (unsigned long long)v;
-                if ( warp_out ) tile[lane][j] = v;
+            if ( n == RNG_TILE && (base >> 32) == 0 ) {
+                const uint32_t b32 = (uint32_t)base;
+#pragma unroll 4
+                for ( uint32_t j = 0; j < RNG_TILE; j += 4 ) { // four draws per 16-byte shared store
+                    uint4 v;
+                    v.x = g.u32();
+                    v.y = g.u32();
+                    v.z = g.u32();
+                    v.w = g.u32();
+                    cs += (unsigned long long)(b32 + j + 1) * v.x;
+                    cs += (unsigned long long)(b32 + j + 2) * v.y;
+                    cs += (unsigned long long)(b32 + j + 3) * v.z;
+                    cs += (unsigned long long)(b32 + j + 4) * v.w;
+                    if ( warp_out ) *reinterpret_cast<uint4*>(&tile[lane][j]) = v;
+                }
             }
+            else
+                for ( uint32_t j = 0; j < n; ++j ) {
+                    const uint32_t v = g.u32();
+                    cs += (base + j + 1) * (unsigned long long)v;
+                    if ( warp_out ) tile[lane][j] = v;
+                }
         }
         if ( warp_out ) {
             __syncwarp();
             const uint32_t valid_mask = __ballot_sync(0xffffffffu, valid);
-            for ( uint32_t sidx = 0; sidx < 32; ++sidx ) {
-                if ( !(valid_mask >> sidx & 1u) ) continue;
-                uint32_t* o = warp_out + (uint64_t)sidx * stream_stride + base;
-                if ( n == RNG_TILE && (((uintptr_t)o) & 7u) == 0 )
-                    reinterpret_cast<uint2*>(o)[lane] = make_uint2(tile[sidx][2 * lane], tile[sidx][2 * lane + 1]);
-                else
+            if ( wide && n == RNG_TILE && valid_mask == 0xffffffffu ) {
+                // two generators' rows per store instruction: a half warp writes 256 contiguous bytes of each
+                const uint32_t half = lane >> 4, q = lane & 15u;
+#pragma unroll 4
+                for ( uint32_t sidx = 0; sidx < 32; sidx += 2 ) {
+                    const uint32_t r = sidx + half;
+                    reinterpret_cast<uint4*>(warp_out + (uint64_t)r * stream_stride + base)[q] =
+                        *reinterpret_cast<const uint4*>(&tile[r][4 * q]);
+                }
+            }
+            else
+                for ( uint32_t sidx = 0; sidx < 32; ++sidx ) {
+                    if ( !(valid_mask >> sidx & 1u) ) continue;
+                    uint32_t* o = warp_out + (uint64_t)sidx * stream_stride + base;
                     for ( uint32_t j = lane; j < n; j += 32 )
                         o[j] = tile[sidx][j];
-            }
+                }
             __syncwarp();
         }
     }
@@ -1538,7 +1564,7 @@ __global__ void __launch_bounds__(128)
 rng_small_stream_kernel(int kind, uint64_t s1, uint64_t s2, uint64_t stride1, uint64_t stride2, uint64_t n_streams,
     uint64_t draws, uint32_t* out, unsigned long long* checksum)
 {
-    __shared__ uint32_t tile[4][32][RNG_TILE + 1];
+    __shared__ __align__(16) uint32_t tile[4][32][RNG_ROW];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t j     = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool     valid = j < n_streams;
@@ -1572,14 +1598,28 @@ rng_mt_stream_kernel(uint64_t s1, uint64_t stride1, uint64_t n_streams, uint64_t
         unsigned long long cs = 0;
         uint32_t*          o  = out ? out + j * draws : nullptr;
         for ( uint64_t base = 0; base < draws; base += MT_N ) {
-            mt_warp_twist(gen, lane);
             const uint32_t n = (uint32_t)min((uint64_t)MT_N, draws - base);
-            for ( uint32_t i = lane; i < n; i += 32 ) {
-                const uint32_t v = mt_temper(gen[i]);
-                cs += (base + i + 1) * (unsigned long long)v;
-                if ( o ) o[base + i] = v;
+            // the twist (mt_warp_twist: chunks of 32 words, reads of a chunk before its writes) with the tempering,
+            // the checksum and the store of every new word folded into the same pass
+            for ( uint32_t c = 0; c < (MT_N + 31) / 32; ++c ) {
+                const uint32_t i   = c * 32 + lane;
+                const bool     act = i < (uint32_t)MT_N;
+                uint32_t       v   = 0;
+                if ( act )
+                    v = mt_twist(gen[i], gen[i + 1 == (uint32_t)MT_N ? 0 : i + 1],
+                        gen[i + MT_M >= (uint32_t)MT_N ? i + MT_M - MT_N : i + MT_M]);
+                __syncwarp();
+                if ( act ) {
+                    gen[i] = v;
+                    if ( i < n ) {
+                        const uint32_t t = mt_temper(v);
+                        const uint64_t pos = base + i + 1;
+                        cs += (pos >> 32) == 0 ? (unsigned long long)(uint32_t)pos * t : pos * (unsigned long long)t;
+                        if ( o ) o[base + i] = t;
+                    }
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
 #pragma unroll
         for ( int off = 16; off > 0; off >>= 1 )
