@@ -1599,23 +1599,33 @@ rng_mt_stream_kernel(uint64_t s1, uint64_t stride1, uint64_t n_streams, uint64_t
         uint32_t*          o  = out ? out + j * draws : nullptr;
         for ( uint64_t base = 0; base < draws; base += MT_N ) {
             const uint32_t n = (uint32_t)min((uint64_t)MT_N, draws - base);
-            // the twist (mt_warp_twist: chunks of 32 words, reads of a chunk before its writes) with the tempering,
-            // the checksum and the store of every new word folded into the same pass
-            for ( uint32_t c = 0; c < (MT_N + 31) / 32; ++c ) {
-                const uint32_t i   = c * 32 + lane;
-                const bool     act = i < (uint32_t)MT_N;
-                uint32_t       v   = 0;
-                if ( act )
-                    v = mt_twist(gen[i], gen[i + 1 == (uint32_t)MT_N ? 0 : i + 1],
-                        gen[i + MT_M >= (uint32_t)MT_N ? i + MT_M - MT_N : i + MT_M]);
+            // the twist (mt_warp_twist: chunks of 32 words in increasing order, reads of a chunk before its writes) with
+            // the tempering, the checksum and the store of every new word folded into the same pass.  Four chunks go
+            // through together: none of them reads a word another one of the four writes (word i reads i, i+1 and
+            // i+397 -- 12.4 chunks ahead or 7.1 behind), so their twelve loads are in flight at once.
+            constexpr uint32_t NCH = (MT_N + 31) / 32, GRP = 4;
+            for ( uint32_t c0 = 0; c0 < NCH; c0 += GRP ) {
+                uint32_t v[GRP];
+#pragma unroll
+                for ( uint32_t u = 0; u < GRP; ++u ) {
+                    const uint32_t i = (c0 + u) * 32 + lane;
+                    v[u]             = 0;
+                    if ( i < (uint32_t)MT_N )
+                        v[u] = mt_twist(gen[i], gen[i + 1 == (uint32_t)MT_N ? 0 : i + 1],
+                            gen[i + MT_M >= (uint32_t)MT_N ? i + MT_M - MT_N : i + MT_M]);
+                }
                 __syncwarp();
-                if ( act ) {
-                    gen[i] = v;
-                    if ( i < n ) {
-                        const uint32_t t = mt_temper(v);
-                        const uint64_t pos = base + i + 1;
-                        cs += (pos >> 32) == 0 ? (unsigned long long)(uint32_t)pos * t : pos * (unsigned long long)t;
-                        if ( o ) o[base + i] = t;
+#pragma unroll
+                for ( uint32_t u = 0; u < GRP; ++u ) {
+                    const uint32_t i = (c0 + u) * 32 + lane;
+                    if ( i < (uint32_t)MT_N ) {
+                        gen[i] = v[u];
+                        if ( i < n ) {
+                            const uint32_t t   = mt_temper(v[u]);
+                            const uint64_t pos = base + i + 1;
+                            cs += (pos >> 32) == 0 ? (unsigned long long)(uint32_t)pos * t : pos * (unsigned long long)t;
+                            if ( o ) o[base + i] = t;
+                        }
                     }
                 }
                 __syncwarp();
