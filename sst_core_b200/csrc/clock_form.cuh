@@ -16,7 +16,8 @@
 //     keeps the one addressed to its component; the component runs its ticks and the event merged in time order
 //     (clock priority 40 before event priority 50 at equal times, activity.h:64-73);
 //   * sends go straight to the calendar (emit: one reservation + one record), statistics are collected per window and
-//     folded into memory only when the window added data -- as in the sequential form;
+//     folded into memory only when the window added data -- as in the sequential form; elements of this form keep
+//     their statistics in the aux block (STATS_IN_AUX), so that the records are nothing but hot heads side by side;
 //   * anything else -- more events than CF_MAX_IN, two events for one component, an event that is not due or lies at /
 //     after a stop time -- sends the block to the fallback list BEFORE anything was written; the CTAs re-run those
 //     blocks in the sequential form once their own blocks are done.
@@ -161,11 +162,12 @@ window_clock_kernel(const __grid_constant__ Dev d)
                               d.stats_on, d.link + (p0 - d.P0), Stage {}, nullptr, 0, 0 };
             State          s;
             uint8_t* const g = d.state + (uint64_t)lc * d.state_stride;
+            uint8_t* const g_st = stats_base<E>(d.state, d.state_stride, d.aux, d.aux_stride, lc);
             const bool stats_direct = E::STATS_EVERY_EVENT && d.stats_on && have_ev;
             if ( !hot_have ) fetch_hot(bin, hot); // woken by an event only
             memcpy(&s, hot, E::CONST_END);
             if ( stats_direct )
-                load_state(s, g, E::CONST_END, E::STATS_END);
+                load_state(s, g_st, E::CONST_END, E::STATS_END);
             else
                 E::initStats(s);
             const bool had_clock = next_tick != TIME_NEVER;
@@ -195,13 +197,13 @@ window_clock_kernel(const __grid_constant__ Dev d)
             const uint64_t next_store = next_tick == TIME_NEVER ? TIME_NEVER : cycle;
             store_state(s, g, 0, have_ev ? E::STORE_END : tick_store_end_of<E>::value);
             if ( stats_direct ) {
-                store_state(s, g, E::CONST_END, E::STATS_END);
+                store_state(s, g_st, E::CONST_END, E::STATS_END);
             }
             else if ( d.stats_on && E::statsVersion(s) != 0 ) {
                 State mem;
-                load_state(mem, g, E::CONST_END, E::STATS_END);
+                load_state(mem, g_st, E::CONST_END, E::STATS_END);
                 E::mergeStats(mem, s);
-                store_state(mem, g, E::CONST_END, E::STATS_END);
+                store_state(mem, g_st, E::CONST_END, E::STATS_END);
             }
             *reinterpret_cast<uint4*>(&d.ctl[lc]) = make_uint4((uint32_t)next_store, (uint32_t)(next_store >> 32), ctx.seq, c_lo.w);
             if ( ctx.sent ) {

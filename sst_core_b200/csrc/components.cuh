@@ -731,7 +731,7 @@ struct ClockNodeElement
     static constexpr const char* ELI_NAME    = "pdes.clocknode";
     static constexpr const char* DESCRIPTION = "clock-driven node (coreTestComponent style)";
     static constexpr bool OWN_KERNEL = true; // a window kernel compiled for this element alone when a rank holds no other
-    static constexpr uint32_t    AUX_BYTES   = 0;
+    static constexpr uint32_t    AUX_BYTES   = 96; // the statistics (STATS_IN_AUX): the record itself is the hot 64 bytes
     static constexpr bool        AUX_MT_SEED = false;
     static constexpr uint32_t    AUX_SEED_OFFSET = 0;
     __device__ static uint32_t auxSeed(const int64_t*) { return 0; }
@@ -758,7 +758,9 @@ struct ClockNodeElement
     static constexpr bool     TIES_INTERCHANGEABLE = false; // the delivery hash / handlers see port and order
     static constexpr bool     STATS_EVERY_EVENT = false;
     static constexpr bool     PARALLEL_EVENTS = false; // handlers chain through the state (hash, RNG): sequential
-    static constexpr uint32_t PERSIST_BYTES = sizeof(State), RECORD_BYTES = sizeof(State);
+    static constexpr uint32_t PERSIST_BYTES = sizeof(State), RECORD_BYTES = CONST_END;
+    static constexpr bool     STATS_IN_AUX = true; // [CONST_END, STATS_END) lives at the start of the aux block
+    static_assert(AUX_BYTES == STATS_END - CONST_END, "aux block = the statistics");
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
     {}
@@ -829,7 +831,7 @@ struct CoreTestElement
     static constexpr const char* ELI_NAME    = "coreTestElement.coreTestComponent";
     static constexpr const char* DESCRIPTION = "coreTestComponent: clock handler sending to its N/S/E/W neighbours in turn";
     static constexpr bool OWN_KERNEL = true; // a window kernel compiled for this element alone when a rank holds no other
-    static constexpr uint32_t    AUX_BYTES   = 0;
+    static constexpr uint32_t    AUX_BYTES   = 96; // the statistics (STATS_IN_AUX): the record itself is the hot 32 bytes
     static constexpr bool        AUX_MT_SEED = false;
     static constexpr uint32_t    AUX_SEED_OFFSET = 0;
     __device__ static uint32_t auxSeed(const int64_t*) { return 0; }
@@ -852,7 +854,9 @@ struct CoreTestElement
     static constexpr bool     TIES_INTERCHANGEABLE = true; // handleEvent looks at nothing but the payload it deletes
     static constexpr bool     STATS_EVERY_EVENT = false;
     static constexpr bool     PARALLEL_EVENTS      = false;
-    static constexpr uint32_t PERSIST_BYTES        = sizeof(State), RECORD_BYTES = sizeof(State);
+    static constexpr uint32_t PERSIST_BYTES        = sizeof(State), RECORD_BYTES = CONST_END;
+    static constexpr bool     STATS_IN_AUX = true; // [CONST_END, STATS_END) lives at the start of the aux block
+    static_assert(AUX_BYTES == STATS_END - CONST_END, "aux block = the statistics");
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)
     {}
@@ -1474,6 +1478,7 @@ struct ElementInfo
     bool        stat_clock = false;               // has statistics under the statistics engine (STAT_CLOCK)
     bool        ordered_events = false;           // has the ordered event-parallel form (ORDERED_EVENTS)
     bool        clock_form = false;               // has the clock form (CLOCK_FORM)
+    bool        stats_in_aux = false;             // keeps its statistics in its aux block (STATS_IN_AUX)
 };
 
 } // namespace sstb200

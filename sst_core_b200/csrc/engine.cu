@@ -184,6 +184,7 @@ struct Dev
     unsigned long long* prof_recv_cyc;  // [nport_local]
     unsigned long long* prof_clock_cyc; // [n_local]
     uint8_t*            snapshot;   // copy of `state` holding every component's state as of Ctrl::report_at
+    uint8_t*            snapshot_aux; // ... and of `aux`, when a local element keeps its statistics there (STATS_IN_AUX)
     // event-parallel form: staging capacity for a bin's records, the two lists (see Ctrl)
     uint32_t            pf_rcap;
     uint32_t*           fb_list;    // [nbins]
@@ -507,11 +508,13 @@ load_state(S& s, const uint8_t* p, uint32_t from, uint32_t to)
 {
     static_assert(sizeof(S) % 8 == 0, "element State must be a multiple of 8 bytes");
     const uint4* src = reinterpret_cast<const uint4*>(p);
-    uint4        tmp[(sizeof(S) + 15) / 16];
+    // (only the pieces asked for are touched: a State is filled by one call per place its pieces live in)
 #pragma unroll
     for ( int i = 0; i < (int)((sizeof(S) + 15) / 16); ++i )
-        if ( (uint32_t)i * 16 >= from && (uint32_t)i * 16 < to ) tmp[i] = src[i];
-    memcpy(&s, tmp, sizeof(S));
+        if ( (uint32_t)i * 16 >= from && (uint32_t)i * 16 < to ) {
+            const uint4 t = src[i];
+            memcpy(reinterpret_cast<uint8_t*>(&s) + (size_t)i * 16, &t, sizeof(S) - (size_t)i * 16 < 16 ? sizeof(S) - (size_t)i * 16 : 16);
+        }
 }
 template <class S>
 __device__ __forceinline__ void
@@ -523,6 +526,27 @@ store_state(const S& s, uint8_t* p, uint32_t from, uint32_t to)
 #pragma unroll
     for ( int i = 0; i < (int)((sizeof(S) + 15) / 16); ++i )
         if ( (uint32_t)i * 16 >= from && (uint32_t)i * 16 < to ) dst[i] = tmp[i];
+}
+
+// Where the statistics pieces [CONST_END, STATS_END) of component lc's State live: behind the rest of the record, or --
+// elements that declare STATS_IN_AUX -- at the start of the component's aux block, so that the records of a
+// clock-driven population are nothing but their hot heads, side by side (a window streams them instead of picking 64
+// bytes out of every 160).  The pointer returned is the one load_state / store_state index with the State's own byte
+// offsets: piece `off` is at base + off.
+template <class E, class = void>
+struct stats_in_aux_of : std::false_type
+{};
+template <class E>
+struct stats_in_aux_of<E, std::void_t<decltype(E::STATS_IN_AUX)>> : std::bool_constant<E::STATS_IN_AUX>
+{};
+template <class E>
+__device__ __forceinline__ uint8_t*
+stats_base(uint8_t* state, uint32_t state_stride, uint8_t* aux, uint32_t aux_stride, uint32_t lc)
+{
+    if constexpr ( stats_in_aux_of<E>::value )
+        return aux + (uint64_t)lc * aux_stride - E::CONST_END;
+    else
+        return state + (uint64_t)lc * state_stride;
 }
 
 // ---- MT19937 seeding (mersenne.cc:149-159) of the aux blocks of elements that declare AUX_MT_SEED.  The recurrence is
@@ -599,7 +623,8 @@ setup_kernel(Dev d)
             first      = E::nextClock(s);
             period_ctl = 1;
         }
-        store_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::PERSIST_BYTES);
+        store_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::CONST_END);
+        store_state(s, stats_base<E>(d.state, d.state_stride, d.aux, d.aux_stride, lc), E::CONST_END, E::PERSIST_BYTES);
     });
     d.ctl[lc] = CompCtl { first, ctx.seq, 0, period_ctl, type, always };
     if ( ctx.sent ) {
@@ -923,8 +948,12 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
             // trip as the rest of the state; for the others this window's statistics start empty and are folded into
             // memory at the end, if the window added any
             const bool stats_direct = E::STATS_EVERY_EVENT && d.stats_on && my_cnt > 0;
-            load_state(s, d.state + (uint64_t)lc * d.state_stride, 0, stats_direct ? E::STATS_END : E::CONST_END);
-            if ( !stats_direct ) E::initStats(s);
+            uint8_t* const st_base = stats_base<E>(d.state, d.state_stride, d.aux, d.aux_stride, lc);
+            load_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::CONST_END);
+            if ( stats_direct )
+                load_state(s, st_base, E::CONST_END, E::STATS_END);
+            else
+                E::initStats(s);
             E::beginWindow(ctx, s, my_cnt); // issues the element's first loads (MT19937 read-ahead)
             sort_segment(s_perm + s_off[c], my_cnt, s_time, s_dst, s_sc);
             uint64_t cycle = next_cyc;
@@ -971,15 +1000,16 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
                     // copy (results_kernel turns it into result records afterwards).  Statistics collected per window
                     // are folded with what is in memory first.
                     uint8_t* const snap = d.snapshot + (uint64_t)lc * d.state_stride;
+                    uint8_t* const snap_st = stats_base<E>(d.snapshot, d.state_stride, d.snapshot_aux, d.aux_stride, lc);
                     store_state(s, snap, 0, E::CONST_END);
                     if ( stats_direct ) {
-                        store_state(s, snap, E::CONST_END, E::STATS_END);
+                        store_state(s, snap_st, E::CONST_END, E::STATS_END);
                     }
                     else if ( d.stats_on && E::statsVersion(s) != 0 ) {
                         typename E::State mem;
-                        load_state(mem, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
+                        load_state(mem, st_base, E::CONST_END, E::STATS_END);
                         E::mergeStats(mem, s);
-                        store_state(mem, snap, E::CONST_END, E::STATS_END);
+                        store_state(mem, snap_st, E::CONST_END, E::STATS_END);
                     }
                     snapped = true;
                 }
@@ -1052,13 +1082,13 @@ dispatch_block(const Dev& d, const uint32_t bin, uint8_t* smem_raw)
             // statistics: read-modify-write only when the window added data (a clock-driven element may tick a thousand
             // times between two addData calls)
             if ( stats_direct ) {
-                store_state(s, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
+                store_state(s, st_base, E::CONST_END, E::STATS_END);
             }
             else if ( d.stats_on && E::statsVersion(s) != 0 ) {
                 typename E::State mem;
-                load_state(mem, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
+                load_state(mem, st_base, E::CONST_END, E::STATS_END);
                 E::mergeStats(mem, s);
-                store_state(mem, d.state + (uint64_t)lc * d.state_stride, E::CONST_END, E::STATS_END);
+                store_state(mem, st_base, E::CONST_END, E::STATS_END);
             }
         });
         if ( !d.ctl_free )
@@ -1485,7 +1515,8 @@ results_kernel(Dev d, uint64_t* out, uint32_t words)
     with_element(d.ctl[lc].type, [&](auto el) {
         using E = decltype(el);
         typename E::State s;
-        load_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::PERSIST_BYTES);
+        load_state(s, d.state + (uint64_t)lc * d.state_stride, 0, E::CONST_END);
+        load_state(s, stats_base<E>(d.state, d.state_stride, d.aux, d.aux_stride, lc), E::CONST_END, E::PERSIST_BYTES);
         E::results(s, r);
     });
 #pragma unroll
@@ -1738,7 +1769,7 @@ element_info()
     static_assert(E::TYPE > 0 && E::TYPE < TYPE_MAX, "element type codes are 1..31");
     return ElementInfo { E::TYPE, E::ELI_NAME, E::RECORD_BYTES, E::AUX_BYTES, E::HAS_PAYLOAD, E::PARALLEL_EVENTS,
         E::TIES_INTERCHANGEABLE, E::DESCRIPTION, prints_of<E>::value, self_links_of<E>::value, stat_clock_of<E>::value,
-        ordered_of<E>::value, clock_form_of<E>::value };
+        ordered_of<E>::value, clock_form_of<E>::value, stats_in_aux_of<E>::value };
 }
 static const ElementInfo kElements[] = {
 #define SSTB200_ELEMENT(E) element_info<E>(),
@@ -1777,6 +1808,7 @@ struct sstb200_engine
     uint64_t           launches    = 0;
     bool               is_setup    = false;
     bool               report_pending = false; // between report_begin and report_end: dispatch uses the REPORT kernel
+    bool               stats_in_aux   = false; // a local element type keeps its statistics in its aux block
     uint32_t           n_ranks     = 1;
     // device buffers that make up the simulation state (checkpoint sections, in a fixed order)
     struct Section
@@ -2206,6 +2238,7 @@ sstb200_engine_create(const sstb200_model* m, const sstb200_options* o, sstb200_
         state_stride = std::max(state_stride, ei->state_bytes);
         aux_stride   = std::max(aux_stride, ei->aux_bytes);
         if ( ei->parallel_events ) any_parallel = true;
+        if ( ei->stats_in_aux ) e->stats_in_aux = true;
         if ( !ei->ties_interchangeable ) d.ties_free = 0;
         if ( (seen_local & (seen_local - 1)) == 0 ) d.uniform_type = ty; // the only type on this rank
     }
@@ -3085,6 +3118,12 @@ sstb200_engine_report_begin(sstb200_engine* e, uint64_t report_time)
     }
     // components that do nothing in the window up to the report time keep the state they have now
     if ( bytes ) CUDA_OK(cudaMemcpyAsync(e->d.snapshot, e->d.state, bytes, cudaMemcpyDeviceToDevice, e->stream));
+    if ( e->stats_in_aux ) { // ... and the statistics they keep in their aux blocks
+        const size_t abytes = (size_t)e->d.n_local * e->d.aux_stride;
+        if ( !e->d.snapshot_aux )
+            if ( int rc = e->alloc(&e->d.snapshot_aux, abytes, false) ) return rc;
+        if ( abytes ) CUDA_OK(cudaMemcpyAsync(e->d.snapshot_aux, e->d.aux, abytes, cudaMemcpyDeviceToDevice, e->stream));
+    }
     CUDA_OK(cudaMemcpyAsync(&e->d.ctrl->report_at, &report_time, 8, cudaMemcpyHostToDevice, e->stream));
     CUDA_OK(cudaStreamSynchronize(e->stream)); // report_time is a stack variable
     e->report_pending = true;
@@ -3102,6 +3141,7 @@ sstb200_engine_report_end(sstb200_engine* e, uint64_t* results, uint32_t words_p
     CUDA_OK(cudaMemcpyAsync(&e->d.ctrl->report_at, &never, 8, cudaMemcpyHostToDevice, e->stream));
     Dev snap   = e->d;
     snap.state = e->d.snapshot; // result records of the snapshot copy
+    if ( e->d.snapshot_aux ) snap.aux = e->d.snapshot_aux;
     results_kernel<<<e->d.nbins, BLOCK, 0, e->stream>>>(snap, e->d_results, words);
     e->launches++;
     CUDA_OK(cudaGetLastError());
