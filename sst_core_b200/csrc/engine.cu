@@ -1612,19 +1612,58 @@ rng_small_stream_kernel(int kind, uint64_t s1, uint64_t s2, uint64_t stride1, ui
     }
 }
 
-// MersenneRNG (2.5 KB of state): a WARP per generator, the state in shared memory.  Seeding is the serial recurrence
-// (one lane); every generation is then built by the 32 lanes together (mt_warp_twist) and its 624 draws are tempered
-// and written by the warp as contiguous 128-byte lines.
+// MersenneRNG seeding (mersenne.cc:149-159) for the stream kernel: the recurrence is serial per generator, so a LANE
+// runs each generator's; 64 words at a time go through a shared-memory tile (16-byte accesses on both sides, as in
+// small_stream_body) and leave as 256-byte rows of the generator's state.  One lane of a warp doing this inside the
+// stream kernel cost it a fifth of its issue slots.
+__global__ void __launch_bounds__(128)
+rng_mt_seed_kernel(uint64_t s1, uint64_t stride1, uint64_t j0, uint64_t n, uint32_t* state /* [n][MT_N] */)
+{
+    __shared__ __align__(16) uint32_t tile[4][32][RNG_ROW];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t g     = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; // generator j0 + g
+    const uint64_t g0    = g - lane;
+    uint32_t       prev  = (uint32_t)(s1 + (j0 + g) * stride1);
+    for ( uint32_t base = 0; base < (uint32_t)MT_N; base += RNG_TILE ) {
+        const uint32_t nw = min((uint32_t)RNG_TILE, (uint32_t)MT_N - base); // 64, the last time 48
+#pragma unroll 4
+        for ( uint32_t j = 0; j < nw; j += 4 ) {
+            uint32_t v[4];
+#pragma unroll
+            for ( uint32_t u = 0; u < 4; ++u ) {
+                const uint32_t i = base + j + u;
+                if ( i ) prev = 1812433253u * (prev ^ (prev >> 30)) + i;
+                v[u] = prev;
+            }
+            *reinterpret_cast<uint4*>(&tile[warp][lane][j]) = make_uint4(v[0], v[1], v[2], v[3]);
+        }
+        __syncwarp();
+        const uint32_t half = lane >> 4, q = lane & 15u;
+        for ( uint32_t r0 = 0; r0 < 32; r0 += 2 ) {
+            const uint32_t r = r0 + half;
+            if ( g0 + r < n && 4 * q < nw )
+                reinterpret_cast<uint4*>(state + (g0 + r) * MT_N + base)[q] = *reinterpret_cast<const uint4*>(&tile[warp][r][4 * q]);
+        }
+        __syncwarp();
+    }
+}
+
+// MersenneRNG (2.5 KB of state): a WARP per generator, the state in shared memory, seeded by rng_mt_seed_kernel (or,
+// without a seeded state, by one lane); every generation is then built by the 32 lanes together and its 624 draws are
+// tempered and written by the warp as contiguous 128-byte lines.
 __global__ void __launch_bounds__(256)
-rng_mt_stream_kernel(uint64_t s1, uint64_t stride1, uint64_t n_streams, uint64_t draws, uint32_t* out,
-    unsigned long long* checksum)
+rng_mt_stream_kernel(uint64_t s1, uint64_t stride1, uint64_t j0, uint64_t n_streams, uint64_t draws, uint32_t* out,
+    unsigned long long* checksum, const uint32_t* seeded /* [n_streams - j0 ...][MT_N] or null */)
 {
     __shared__ __align__(16) uint32_t s_gen[8][MT_N];
     const uint32_t lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
     uint32_t* const gen = s_gen[wic];
     const uint64_t  nw = (uint64_t)gridDim.x * 8;
-    for ( uint64_t j = (uint64_t)blockIdx.x * 8 + wic; j < n_streams; j += nw ) {
-        if ( lane == 0 ) mt_seed(gen, (uint32_t)(s1 + j * stride1));
+    for ( uint64_t j = j0 + (uint64_t)blockIdx.x * 8 + wic; j < n_streams; j += nw ) {
+        if ( seeded )
+            mt_warp_load(gen, seeded + (j - j0) * MT_N, lane);
+        else if ( lane == 0 )
+            mt_seed(gen, (uint32_t)(s1 + j * stride1));
         __syncwarp();
         unsigned long long cs = 0;
         uint32_t*          o  = out ? out + j * draws : nullptr;
@@ -3318,9 +3357,18 @@ sstb200_rng_streams(int device, void* stream, int kind, uint64_t s1, uint64_t s2
     if ( kind == 0 ) {
         int n_sm = 148;
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
-        const uint64_t blocks = std::min<uint64_t>((n_streams + 7) / 8, (uint64_t)n_sm * 8);
-        rng_mt_stream_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s1, stride1, n_streams, draws,
-            (uint32_t*)out_dev, (unsigned long long*)checksum_dev);
+        // groups of 2^16 generators: seeded a lane per generator into a scratch array (164 MB), then streamed
+        const uint64_t group = 1ull << 16;
+        uint32_t*      seeded = nullptr;
+        CUDA_OK(cudaMallocAsync((void**)&seeded, std::min(group, n_streams) * MT_N * 4, (cudaStream_t)stream));
+        for ( uint64_t j0 = 0; j0 < n_streams; j0 += group ) {
+            const uint64_t n = std::min(group, n_streams - j0);
+            rng_mt_seed_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(s1, stride1, j0, n, seeded);
+            const uint64_t blocks = std::min<uint64_t>((n + 7) / 8, (uint64_t)n_sm * 8);
+            rng_mt_stream_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s1, stride1, j0, j0 + n, draws,
+                (uint32_t*)out_dev, (unsigned long long*)checksum_dev, seeded);
+        }
+        CUDA_OK(cudaFreeAsync(seeded, (cudaStream_t)stream));
     }
     else {
         const uint64_t blocks = (n_streams + 127) / 128;
