@@ -3359,8 +3359,20 @@ sstb200_rng_streams(int device, void* stream, int kind, uint64_t s1, uint64_t s2
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
         // groups of 2^16 generators: seeded a lane per generator into a scratch array (164 MB), then streamed
         const uint64_t group = 1ull << 16;
-        uint32_t*      seeded = nullptr;
-        CUDA_OK(cudaMallocAsync((void**)&seeded, std::min(group, n_streams) * MT_N * 4, (cudaStream_t)stream));
+        static uint32_t* scratch[64]; // per device, kept (an allocation per call costs more than the seeding saves)
+        static size_t    scratch_gens[64];
+        const size_t     want = (size_t)std::min(group, n_streams);
+        if ( scratch_gens[device & 63] < want ) {
+            if ( scratch[device & 63] ) {
+                CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+                cudaFree(scratch[device & 63]);
+                scratch[device & 63] = nullptr;
+                scratch_gens[device & 63] = 0;
+            }
+            CUDA_OK(cudaMalloc((void**)&scratch[device & 63], group * MT_N * 4));
+            scratch_gens[device & 63] = group;
+        }
+        uint32_t* const seeded = scratch[device & 63];
         for ( uint64_t j0 = 0; j0 < n_streams; j0 += group ) {
             const uint64_t n = std::min(group, n_streams - j0);
             rng_mt_seed_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(s1, stride1, j0, n, seeded);
@@ -3368,7 +3380,7 @@ sstb200_rng_streams(int device, void* stream, int kind, uint64_t s1, uint64_t s2
             rng_mt_stream_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s1, stride1, j0, j0 + n, draws,
                 (uint32_t*)out_dev, (unsigned long long*)checksum_dev, seeded);
         }
-        CUDA_OK(cudaFreeAsync(seeded, (cudaStream_t)stream));
+
     }
     else {
         const uint64_t blocks = (n_streams + 127) / 128;
