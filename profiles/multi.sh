@@ -13,7 +13,7 @@ PY
 tail -3 gpurun_out/bench_${N}gpu.err
 for w in clockpop phold; do
   X=""; [ $w = phold ] && X="--x 1024 --y 1024"
-  timeout 600 $TR --master-port 29513 bench.py --gpus $N --workload $w $X --steps 20 --warmup 10 --no-e2e > gpurun_out/bench_${w}_${N}gpu.log 2> gpurun_out/bench_${w}_${N}gpu.err
+  timeout 600 $TR --master-port 29513 bench.py --gpus $N --workload $w $X --steps 20 --warmup 5 --no-e2e > gpurun_out/bench_${w}_${N}gpu.log 2> gpurun_out/bench_${w}_${N}gpu.err
   python -c "
 import json;d=json.loads(open('gpurun_out/bench_${w}_${N}gpu.log').read().strip().splitlines()[-1]);print('$w $N gpus', d['value'], d['ms_per_step'], d['roofline']['frac'])"
 done

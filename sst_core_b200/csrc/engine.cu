@@ -627,12 +627,21 @@ setup_kernel(Dev d)
         store_state(s, stats_base<E>(d.state, d.state_stride, d.aux, d.aux_stride, lc), E::CONST_END, E::PERSIST_BYTES);
     });
     d.ctl[lc] = CompCtl { first, ctx.seq, 0, period_ctl, type, always };
-    if ( ctx.sent ) {
-        atomicAdd(&d.ctrl->events_sent, (unsigned long long)ctx.sent);
-        atomicAdd((unsigned long long*)&d.ctrl->local[CW_PENDING], (unsigned long long)ctx.sent);
+    // counters: summed over the lanes that are here, ONE set of atomics per warp.  (One set per thread was 50 M atomics
+    // on one cache line for a 16 M-component model -- and every send's loads of Ctrl::w / k / slot queued behind them:
+    // 28 ms for what a window kernel does in one.)
+    const uint32_t here  = __activemask();
+    const uint32_t sent  = __reduce_add_sync(here, ctx.sent);
+    const uint32_t clks  = __reduce_add_sync(here, first != TIME_NEVER ? 1u : 0u);
+    const uint32_t prims = __popc(here); // every in-scope element is a primary component
+    if ( (threadIdx.x & 31u) == (uint32_t)__ffs(here) - 1u ) {
+        if ( sent ) {
+            atomicAdd(&d.ctrl->events_sent, (unsigned long long)sent);
+            atomicAdd((unsigned long long*)&d.ctrl->local[CW_PENDING], (unsigned long long)sent);
+        }
+        if ( clks ) atomicAdd((unsigned long long*)&d.ctrl->local[CW_CLOCKS], (unsigned long long)clks);
+        atomicAdd((unsigned long long*)&d.ctrl->local[CW_PRIMARY], (unsigned long long)prims);
     }
-    if ( first != TIME_NEVER ) atomicAdd((unsigned long long*)&d.ctrl->local[CW_CLOCKS], 1ull);
-    atomicAdd((unsigned long long*)&d.ctrl->local[CW_PRIMARY], 1ull); // every in-scope element is a primary component
 }
 
 // Exclusive scan of one u32 per thread over the CTA (warp shuffles + one shared round).

@@ -27,4 +27,15 @@ for size in (256, 1024, 2048, 4096):
             d = records_digest(ids, mesh_records_from_counts(counts, bool(stats))[:, :words])
             out["digests"][f"mesh_{size}x{size}_w{windows}_stats{stats}"] = {"digest": f"{d:016x}", "events": events}
         print(size, windows, events, flush=True)
+# PHOLD at the bench's size: the oracle itself (no count-only shortcut exists for it); --phold, about four minutes
+if "--phold" in sys.argv:
+    from sst_core_b200 import models  # noqa: E402
+    from sst_core_b200.run import result_words  # noqa: E402
+    m = models.phold_model(1024, 1024, stop_at="25ns", verbose=0, stats_enabled=True)
+    ref = O.run_model(m)
+    d = records_digest(np.arange(m.ncomp, dtype=np.uint64), ref.results[:, :result_words(m)])
+    out["digests"]["phold_1024x1024_w25"] = {"digest": f"{d:016x}", "events": int(ref.events)}
+else:
+    old = json.loads((ROOT / "tests" / "golden" / "bench_digests.json").read_text())["digests"]
+    out["digests"].update({k: v for k, v in old.items() if k.startswith("phold_")})
 (ROOT / "tests" / "golden" / "bench_digests.json").write_text(json.dumps(out, indent=1) + "\n")
