@@ -47,7 +47,12 @@ class CheckpointWriter:
         if rank == 0:
             os.makedirs(self.root, exist_ok=True)
 
-    def write(self, engine, sim_time: int, engine_opts: dict) -> str:
+    def write(self, engine, sim_time: int, engine_opts: dict, nominal_time: Optional[int] = None) -> str:
+        """``sim_time``: the window boundary the state was taken at; ``nominal_time``: the multiple of the checkpoint
+        period it stands for (CheckpointAction runs exactly there, checkpointAction.cc:143-152) -- directory names and
+        the console line use it, so that they agree with the reference's whenever period % window != 0."""
+        actual_time = int(sim_time)
+        sim_time = int(nominal_time) if nominal_time is not None else actual_time
         base = f"{self.prefix}_{self.next_id}_{sim_time}"
         d = os.path.join(self.root, base)
         os.makedirs(d, exist_ok=True)
@@ -62,7 +67,7 @@ class CheckpointWriter:
         if self.rank == 0:
             with open(reg, "w") as f:
                 json.dump({"format": "sst_core_b200 checkpoint registry", "version": 1, "checkpoint_id": self.next_id,
-                           "sim_time": int(sim_time), "ranks": self.n_ranks, "recipe": self.recipe,
+                           "sim_time": int(sim_time), "state_time": actual_time, "ranks": self.n_ranks, "recipe": self.recipe,
                            "engine_opts": {k: v for k, v in engine_opts.items() if k != "stream"},
                            "model_fingerprint": self.fingerprint,
                            "partition_files": [f"{base}_{r}_0.bin" for r in range(self.n_ranks)]}, f, indent=1)
@@ -115,7 +120,7 @@ def run_with_checkpoints(engine, period: int, writer: Optional[CheckpointWriter]
             return
         if st.now >= nxt:
             if writer is not None:
-                writer.write(engine, st.now, engine_opts)
+                writer.write(engine, st.now, engine_opts, nominal_time=(st.now // period) * period)
             nxt = (st.now // period + 1) * period
 
 

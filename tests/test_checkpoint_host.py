@@ -40,10 +40,13 @@ def test_checkpoints_fall_on_the_first_window_boundary_at_or_after_each_period(t
     e = FakeEngine(w=1000, end=10500)
     checkpoint.run_with_checkpoints(e, 2500, w, {"calendar_slots": 4, "stream": 123})
     dirs = sorted(p.name for p in (tmp_path / "cp").iterdir())
-    assert dirs == ["cp_1_3000", "cp_2_5000", "cp_3_8000", "cp_4_10000"]  # 2500 -> 3000, 5000, 7500 -> 8000, 10000
-    reg = checkpoint.load_registry(str(tmp_path / "cp" / "cp_3_8000" / "cp_3_8000.sstcpt"))
-    assert reg["sim_time"] == 8000 and reg["checkpoint_id"] == 3 and reg["recipe"] == recipe
-    assert reg["engine_opts"] == {"calendar_slots": 4} and reg["partition_files"] == ["cp_3_8000_0_0.bin"]
+    # the state is taken at the first window boundary at or after each multiple of the period (2500 -> 3000, 5000,
+    # 7500 -> 8000, 10000); names and the registry's sim_time carry the multiple itself, like the reference's
+    # CheckpointAction (checkpointAction.cc:143-152), the boundary is kept as state_time
+    assert dirs == ["cp_1_2500", "cp_2_5000", "cp_3_7500", "cp_4_10000"]
+    reg = checkpoint.load_registry(str(tmp_path / "cp" / "cp_3_7500" / "cp_3_7500.sstcpt"))
+    assert reg["sim_time"] == 7500 and reg["state_time"] == 8000 and reg["checkpoint_id"] == 3 and reg["recipe"] == recipe
+    assert reg["engine_opts"] == {"calendar_slots": 4} and reg["partition_files"] == ["cp_3_7500_0_0.bin"]
     assert reg["model_fingerprint"] == checkpoint.model_fingerprint(m)
     assert np.array_equal(checkpoint.read_partition(reg), np.arange(16, dtype=np.uint8) + (8000 % 200))
 
@@ -51,7 +54,7 @@ def test_checkpoints_fall_on_the_first_window_boundary_at_or_after_each_period(t
 def test_period_that_is_a_multiple_of_the_window_is_hit_exactly():
     e = FakeEngine(w=1000, end=9000)
     seen = []
-    w = SimpleNamespace(write=lambda eng, t, o: seen.append(t))
+    w = SimpleNamespace(write=lambda eng, t, o, nominal_time=None: seen.append(t))
     checkpoint.run_with_checkpoints(e, 4000, w, {})
     assert seen == [4000, 8000] and e.calls == [4, 4, 4]
 
