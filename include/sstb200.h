@@ -170,6 +170,11 @@ int sstb200_engine_in_arena(sstb200_engine* e, int* in_arena);
 int sstb200_engine_peer_connect_arena(sstb200_engine* e, const uint32_t* nbins);
 /* the cudaStream_t the engine launches on (options.stream, or the one it created) */
 int sstb200_engine_stream(sstb200_engine* e, void** stream_out);
+/* which window kernel runs this rank's windows, decided at create from what the rank holds -- the analogue of asking
+ * the reference which TimeVortex it loaded (simulation.cc:303-315): 0 the sequential form (dispatch_kernel), 1 the
+ * event-parallel form (MessageMesh), 2 the ordered event-parallel form (PHOLD), 3 the clock form (clock-driven
+ * populations).  Blocks a form cannot take in some window run in the sequential form in that window. */
+int sstb200_engine_form(sstb200_engine* e, int* form_out);
 
 /* device pointers + geometry of the exchange buffers.  Slot layout (u64 words), one slot per rank:
  *   [0] record count, [1..8] the sender's control words, [9] reserved, then capacity x {time, dst_seq, payload,

@@ -30,6 +30,10 @@ struct RelayElement
     static constexpr bool     TIES_INTERCHANGEABLE = false;
     static constexpr bool     STATS_EVERY_EVENT    = false;
     static constexpr bool     PARALLEL_EVENTS      = false;
+    // no clock, one send per delivery, nothing but State / the event / ctx.send used: the ordered event-parallel
+    // window kernel can run a rank of relays -- one declaration, the handler stays as it is
+    static constexpr bool     ORDERED_EVENTS       = true;
+    static constexpr uint32_t ORD_MAX_EVENTS       = 16;
     static constexpr uint32_t PERSIST_BYTES = sizeof(State), RECORD_BYTES = sizeof(State);
     template <class Ctx>
     __device__ static void beginWindow(Ctx&, State&, uint32_t)

@@ -3002,6 +3002,14 @@ sstb200_engine_stream(sstb200_engine* e, void** stream_out)
 }
 
 int
+sstb200_engine_form(sstb200_engine* e, int* form_out)
+{
+    if ( !e || !form_out ) return -1;
+    *form_out = !e->pf_on ? 0 : e->pf_clock ? 3 : e->pf_ordered ? 2 : 1;
+    return 0;
+}
+
+int
 sstb200_engine_exchange_buffers(sstb200_engine* e, void** outbox_dev, void** inbox_dev, uint64_t* words_per_rank)
 {
     if ( !e ) return -1;

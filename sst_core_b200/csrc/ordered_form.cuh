@@ -446,11 +446,13 @@ window_ordered_kernel(const __grid_constant__ Dev d)
                 const uint32_t c = i / NA, q = (REC / 16) * c + (i - c * NA);
                 g[q]             = sm[q];
             }
-            if ( d.stats_on )
-                for ( uint32_t i = tid; i < n_comp * NB; i += OF_THREADS ) {
-                    const uint32_t c = i / NB, q = (REC / 16) * c + E::CONST_END / 16 + (i - c * NB);
-                    g[q]             = sm[q];
-                }
+            if constexpr ( NB > 0 ) {
+                if ( d.stats_on )
+                    for ( uint32_t i = tid; i < n_comp * NB; i += OF_THREADS ) {
+                        const uint32_t c = i / NB, q = (REC / 16) * c + E::CONST_END / 16 + (i - c * NB);
+                        g[q]             = sm[q];
+                    }
+            }
             if ( tid < (uint32_t)BLOCK ) {
                 if ( tid < n_comp && s_cnt[tid] ) d.ctl[lc0 + tid].send_seq = s_seq[tid];
                 s_cnt[tid] = 0;

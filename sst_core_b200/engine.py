@@ -61,7 +61,7 @@ EXPORTS = [
     "sstb200_rng_streams",
     "sstb200_rng_ticks", "sstb200_rng_distribution",
     "sstb200_engine_peer_export", "sstb200_engine_peer_connect", "sstb200_engine_peer_connect_local",
-    "sstb200_engine_stream",
+    "sstb200_engine_stream", "sstb200_engine_form",
     "sstb200_peer_region_bytes", "sstb200_peer_arena_create", "sstb200_peer_arena_open", "sstb200_peer_arena_destroy",
     "sstb200_engine_in_arena", "sstb200_engine_peer_connect_arena", "sstb200_engine_output",
     "sstb200_engine_handler_times", "sstb200_engine_sync_profile", "sstb200_engine_prepare_run",
@@ -101,6 +101,7 @@ def lib():
     L.sstb200_engine_peer_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sstb200_engine_peer_connect_local.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sstb200_engine_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.sstb200_engine_form.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
     L.sstb200_engine_handler_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sstb200_engine_sync_profile.argtypes = [C.c_void_p, C.c_void_p]
     L.sstb200_engine_output.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
@@ -438,6 +439,14 @@ class Engine:
         if n.value:
             _check(self._L.sstb200_engine_output(self._h, C.byref(n), _p(out)), "engine_output")
         return out[:int(n.value)]
+
+    FORMS = ("sequential", "event-parallel", "ordered", "clock")
+
+    def form(self) -> str:
+        """Which window kernel runs this rank's windows: one of ``Engine.FORMS``."""
+        f = C.c_int()
+        _check(self._L.sstb200_engine_form(self._h, C.byref(f)), "engine_form")
+        return self.FORMS[f.value]
 
     def stream_handle(self) -> int:
         st = C.c_void_p()

@@ -132,6 +132,28 @@ def test_phold_ordered_form_and_its_per_block_fallbacks(monkeypatch):
     assert_same_as_oracle(m, calendar_slots=4, bin_capacity=8192, smem_events=4096)
 
 
+def test_every_benchmarked_workload_takes_its_own_window_kernel(monkeypatch):
+    # which window kernel a rank runs is decided at create (sstb200_engine_form): the parity tests above would pass just
+    # as well if every block fell back to the sequential form -- this one pins the choice itself
+    from sst_core_b200.engine import Engine
+
+    def form_of(m, **opts):
+        e = Engine(m, **opts)
+        try:
+            return e.form()
+        finally:
+            e.close()
+
+    assert form_of(models.mesh_model(20, 20, stop_at="10ns")) == "event-parallel"
+    assert form_of(models.phold_model(20, 20, stop_at="10ns"), calendar_slots=16) == "ordered"
+    assert form_of(models.clockpop_model(20, 20, stop_at="10ns")) == "clock"
+    # what the forms leave out: a delivery trace, handler counting
+    assert form_of(models.phold_model(20, 20, stop_at="10ns"), calendar_slots=16, trace_capacity=1 << 12) == "sequential"
+    assert form_of(models.clockpop_model(20, 20, stop_at="10ns"), handler_counts=True) == "sequential"
+    monkeypatch.setenv("SSTB200_NO_PARALLEL_FORM", "1")
+    assert form_of(models.phold_model(20, 20, stop_at="10ns"), calendar_slots=16) == "sequential"
+
+
 def test_phold_large_vs_oracle():
     assert_same_as_oracle(models.phold_model(128, 128, stop_at="40ns", stats_enabled=True), calendar_slots=16)
 
