@@ -561,13 +561,15 @@ def ours(a):
                 parity["e2e_golden"] = gold_e2e["digest"]
                 parity["e2e_match"] = parity["e2e_digest"] == gold_e2e["digest"]
                 parity["match"] = bool(parity["match"]) and parity["e2e_match"] if gold else parity["e2e_match"]
-        elif a.workload == "phold":
+        else:
             gp = ROOT / "tests" / "golden" / "bench_digests.json"
             gall = json.loads(gp.read_text())["digests"] if gp.exists() else {}
-            gold = gall.get(f"phold_{a.x or 4096}x{a.y or 4096}_w{W + K}")
+            gold = gall.get(f"{a.workload}_{a.x or 4096}x{a.y or 4096}_w{W + K}")
             if gold:
                 parity["golden"] = gold["digest"]
-                parity["golden_source"] = "tests/golden/bench_digests.json (oracle/pdes_oracle.cc on CPU, pinned to the reference)"
+                parity["golden_source"] = ("tests/golden/bench_digests.json (oracle/pdes_oracle.cc on CPU, pinned to the reference)"
+                                           if a.workload == "phold" else
+                                           "tests/golden/bench_digests.json (this engine's sequential form: form independence)")
                 parity["match"] = parity["digest"] == gold["digest"]
                 parity["events_total"], parity["golden_events"] = total_all, gold["events"]
         line["parity"] = parity

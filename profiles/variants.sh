@@ -1,6 +1,12 @@
 #!/bin/bash
-# scratch script for one-off GPU experiments during kernel work (gpurun -- 'bash profiles/variants.sh'); the measurement
-# sets that produce the files under profiles/ are r02_set5.sh (one GPU), multi.sh (N GPUs), ncu_full.sh, ncu_traffic.sh,
-# timing.sh
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_element_registration.py tests/test_gpu_engine.py -x -q -m gpu 2>&1 | tail -5
+ARGS="--workload clockpop --steps 20 --warmup 5 --no-e2e --no-cpu-baseline"
+for v in 1 2 3; do
+  timeout 300 python bench.py $ARGS > gpurun_out/bench_clockpop.log 2> gpurun_out/bench_clockpop.err
+  python - <<'PY'
+import json,os
+d=json.loads(open('gpurun_out/bench_clockpop.log').read().strip().splitlines()[-1])
+print('clockpop', round(d['value']/1e9,2), round(d['ms_per_step'],4), round(d['roofline']['frac'],4), d['parity']['digest'])
+PY
+done
+timeout 600 python -m pytest tests/test_coretest_component.py tests/test_gpu_engine.py tests/test_random_graphs.py tests/test_periodic_stats.py tests/test_gpu_checkpoint.py tests/test_gpu_multirank.py tests/test_gpu_fullsize.py -x -q -m gpu 2>&1 | tail -3

@@ -19,8 +19,9 @@
 //     folded into memory only when the window added data -- as in the sequential form; elements of this form keep
 //     their statistics in the aux block (STATS_IN_AUX), so that the records are nothing but hot heads side by side;
 //   * anything else -- more events than CF_MAX_IN, two events for one component, an event that is not due or lies at /
-//     after a stop time -- sends the block to the fallback list BEFORE anything was written; the CTAs re-run those
-//     blocks in the sequential form once their own blocks are done.
+//     after a stop time -- sends the block to the fallback list BEFORE anything was written (every thread reaches the
+//     verdict on its own from the same records: no vote, no barrier); the CTAs re-run those blocks in the sequential
+//     form once their own blocks are done.
 // Counters: ticks are kept per thread over all blocks of the (persistent) CTA, ONE atomic per CTA at the end (the
 // sequential form's one-atomic-per-block costs 65 536 same-address atomics per counter and window on a 16 M
 // population); deliveries, sends and clocks that stop are rare and counted where they happen.
@@ -41,7 +42,7 @@ template <class E>
 struct tick_store_end_of<E, std::void_t<decltype(E::TICK_STORE_END)>> : std::integral_constant<uint32_t, E::TICK_STORE_END>
 {};
 
-constexpr uint32_t CF_MAX_IN = 32; // events in a block's bin the form takes
+constexpr uint32_t CF_MAX_IN = 8; // events in a block's bin the form takes (their components fit one 64-bit register)
 
 // 16-byte load that asks DRAM for the 64-byte half line only (SASS LDG.E.LTC64B): a plain load of a line that is not
 // in L2 brings all 128 bytes (profiles/r01_notes.md, sector accounting), and a component's hot state is 64 bytes of a
@@ -61,6 +62,11 @@ window_clock_kernel(const __grid_constant__ Dev d)
     extern __shared__ __align__(128) uint8_t pf_smem[];
     __shared__ uint32_t s_red[BLOCK / 32];
     __shared__ uint32_t s_take;
+    // which of this CTA's blocks went to the fallback list (bit i = its i-th block).  The bins of the others are
+    // cleared after the last barrier of the kernel: with no barrier inside the loop the warps of a CTA drift apart, and
+    // a warp that fetched the fill of a bin AFTER another one had cleared it would miss the bin's events.
+    constexpr uint32_t CF_MASK_WORDS = 128; // 4096 blocks per CTA = 1.2 M blocks per rank at 296 CTAs
+    __shared__ uint32_t s_fbmask[CF_MASK_WORDS];
     Ctrl* const ctrl = d.ctrl;
     if ( ctrl->done ) return;
     const uint64_t k     = ctrl->k;
@@ -73,6 +79,11 @@ window_clock_kernel(const __grid_constant__ Dev d)
     using State          = typename E::State;
 
     uint32_t ticks = 0; // (deliveries, sends and clocks that stop are rare: counted where they happen)
+    for ( uint32_t i = tid; i < CF_MASK_WORDS; i += BLOCK )
+        s_fbmask[i] = 0;
+    __syncthreads();
+    // (a rank with more blocks per CTA than the mask has bits keeps the warps of a CTA together with a barrier instead)
+    const bool lockstep = (d.nbins + gridDim.x - 1) / gridDim.x > CF_MASK_WORDS * 32;
 
     // Two blocks ahead of the one being run: the control block (first half + clock period) and the bin fill are loaded
     // into registers; one block ahead: the hot part of the state of the components that will tick.  Two blocks' loads
@@ -114,7 +125,7 @@ window_clock_kernel(const __grid_constant__ Dev d)
         hot[i] = hot_next[i] = make_uint4(0, 0, 0, 0);
     if ( hot_have ) fetch_hot(blockIdx.x, hot);
 
-    for ( uint32_t bin = blockIdx.x; bin < d.nbins; bin += gridDim.x ) {
+    for ( uint32_t bin = blockIdx.x, it = 0; bin < d.nbins; bin += gridDim.x, ++it ) {
         const uint32_t lc     = bin * BLOCK + tid;
         const bool     valid  = lc < d.n_local;
         const uint4    c_lo   = cur.lo;
@@ -131,20 +142,30 @@ window_clock_kernel(const __grid_constant__ Dev d)
             bool           bad       = n_in > CF_MAX_IN;
             const uint64_t base      = (uint64_t)(slot * d.nbins + bin) * d.cap;
             const uint32_t blk_port0 = d.P0 + ((bin * BLOCK) << sh);
+            // Every thread sees the same records and comes to the same verdict -- also on "two events for one
+            // component" (the sequential form orders those): the components seen so far ride along in one register,
+            // a byte each.  No vote and no barrier: the warps of a block with events stay as independent as the others.
+            uint64_t seen = 0;
             if ( !bad )
                 for ( uint32_t i = 0; i < n_in; ++i ) {
                     const ulonglong2 r = d.ev[base + i];
                     const uint32_t   c = ((uint32_t)(r.y >> 32) - blk_port0) >> sh;
                     if ( r.x < T || r.x >= T_end || c >= (uint32_t)BLOCK ) bad = true; // fault / not due / stop time
+                    for ( uint32_t j = 0; j < i; ++j )
+                        if ( (uint32_t)(seen >> (8 * j) & 0xFFu) == c ) bad = true;
+                    seen |= (uint64_t)(c & 0xFFu) << (8 * i);
                     if ( c == tid ) {
-                        if ( have_ev ) bad = true; // two events for one component: the sequential form orders them
                         have_ev = true;
                         evr     = r;
                         if ( E::HAS_PAYLOAD ) ev_pl = d.ev_payload[base + i];
                     }
                 }
-            if ( __syncthreads_or(bad ? 1 : 0) ) {
-                if ( tid == 0 ) d.fb_list[atomicAdd(&ctrl->fb_n, 1u)] = bin + 1; // 0 = entry not written yet
+            if ( lockstep ) __syncthreads();
+            if ( bad ) {
+                if ( tid == 0 ) {
+                    d.fb_list[atomicAdd(&ctrl->fb_n, 1u)] = bin + 1; // 0 = entry not written yet
+                    if ( !lockstep ) s_fbmask[it >> 5] |= 1u << (it & 31u);
+                }
                 cur      = nxt;
                 nxt      = nn;
                 hot_have = hot_next_have;
@@ -212,7 +233,7 @@ window_clock_kernel(const __grid_constant__ Dev d)
             }
         }
         if ( n_in && tid == 0 ) {
-            d.bin_count[slot * d.nbins + bin] = 0; // every thread read the records before the barrier above
+            if ( lockstep ) d.bin_count[slot * d.nbins + bin] = 0; // (every warp read the fill before the barrier above)
             if ( n_in > ctrl->max_bin_fill ) atomicMax(&ctrl->max_bin_fill, (unsigned long long)n_in);
             if ( n_in > ctrl->max_due ) atomicMax(&ctrl->max_due, (unsigned long long)n_in);
         }
@@ -240,6 +261,10 @@ window_clock_kernel(const __grid_constant__ Dev d)
             if ( v1 ) atomicAdd(&ctrl->clock_ticks, (unsigned long long)v1);
         }
     }
+    // ---- every warp of the CTA is through its blocks: the bins this CTA consumed are cleared now
+    if ( !lockstep )
+        for ( uint32_t it = tid, bin = blockIdx.x + tid * gridDim.x; bin < d.nbins; it += BLOCK, bin += BLOCK * gridDim.x )
+            if ( !(s_fbmask[it >> 5] >> (it & 31u) & 1u) && d.bin_count[slot * d.nbins + bin] ) d.bin_count[slot * d.nbins + bin] = 0;
 
     // ---- the blocks left to the sequential form (see window_parallel_kernel: same protocol)
     for ( ;; ) {

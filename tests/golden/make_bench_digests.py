@@ -37,5 +37,5 @@ if "--phold" in sys.argv:
     out["digests"]["phold_1024x1024_w25"] = {"digest": f"{d:016x}", "events": int(ref.events)}
 else:
     old = json.loads((ROOT / "tests" / "golden" / "bench_digests.json").read_text())["digests"]
-    out["digests"].update({k: v for k, v in old.items() if k.startswith("phold_")})
+    out["digests"].update({k: v for k, v in old.items() if k.startswith(("phold_", "clockpop_"))})
 (ROOT / "tests" / "golden" / "bench_digests.json").write_text(json.dumps(out, indent=1) + "\n")

@@ -121,3 +121,20 @@ def test_mesh_4096x4096_25_windows_digest_equals_cpu_golden_model():
     want = fix["mesh_4096x4096_w25_stats1"]
     assert st.events_delivered == want["events"] == 24 * 4 * n
     assert f"{records_digest(np.arange(n), res[:, :6]):016x}" == want["digest"]
+
+
+def test_clock_population_with_several_blocks_per_cta_equals_the_sequential_form(monkeypatch):
+    # 2048 blocks on ~300 persistent CTAs: the warps of a CTA run their blocks without a barrier between them and drift
+    # apart (clock_form.cuh) -- a bin cleared by one warp before another one had fetched its fill lost that bin's events
+    # (seen at the bench's size only: every smaller test has at most one block per CTA).  The sequential form, which
+    # the other tests pin to the oracle, is the reference here (the oracle needs minutes at this size).
+    from sst_core_b200.run import simulate_model
+    m = models.clockpop_model(1024, 512, stop_at="40ns", comm_freq=60, verbose=0, stats_enabled=True)
+    opts = dict(calendar_slots=2, bin_capacity=512, smem_events=512)
+    monkeypatch.setenv("SSTB200_NO_PARALLEL_FORM", "1")
+    want, st0 = simulate_model(m, **opts)
+    monkeypatch.delenv("SSTB200_NO_PARALLEL_FORM")
+    for _ in range(3):
+        res, st = simulate_model(m, **opts)
+        assert np.array_equal(res, want)
+        assert st.events_delivered == st0.events_delivered and st.clock_ticks == st0.clock_ticks
