@@ -138,8 +138,11 @@ window_clock_kernel(const __grid_constant__ Dev d)
         bool       have_ev = false;
         ulonglong2 evr     = make_ulonglong2(0, 0);
         uint64_t   ev_pl   = 0;
-        if ( n_in ) { // (uniform over the CTA)
-            bool           bad       = n_in > CF_MAX_IN;
+        // A block this CTA has handed to the fallback list may already have been run by another CTA (bin cleared, state
+        // advanced) when a warp that lags behind fetches its fill: the mask, set before the hand-over, tells it.
+        const bool handed_over = !lockstep && ((*(volatile uint32_t*)&s_fbmask[it >> 5] >> (it & 31u)) & 1u);
+        if ( n_in || handed_over ) { // (n_in: uniform over the CTA up to such laggards)
+            bool           bad       = handed_over || n_in > CF_MAX_IN;
             const uint64_t base      = (uint64_t)(slot * d.nbins + bin) * d.cap;
             const uint32_t blk_port0 = d.P0 + ((bin * BLOCK) << sh);
             // Every thread sees the same records and comes to the same verdict -- also on "two events for one
@@ -163,8 +166,11 @@ window_clock_kernel(const __grid_constant__ Dev d)
             if ( lockstep ) __syncthreads();
             if ( bad ) {
                 if ( tid == 0 ) {
+                    if ( !lockstep ) {
+                        s_fbmask[it >> 5] |= 1u << (it & 31u);
+                        __threadfence_block();
+                    }
                     d.fb_list[atomicAdd(&ctrl->fb_n, 1u)] = bin + 1; // 0 = entry not written yet
-                    if ( !lockstep ) s_fbmask[it >> 5] |= 1u << (it & 31u);
                 }
                 cur      = nxt;
                 nxt      = nn;
