@@ -1,3 +1,7 @@
 #!/bin/bash
-export SSTB200_LIB=$PWD/profiles/micro/libsstb200_racy.so
-for i in 1 2; do timeout 300 python -m pytest tests/test_gpu_fullsize.py -x -q -m gpu -k "clock_population" 2>&1 | tail -1; done
+# scratch script for one-off GPU experiments during kernel work (gpurun -- 'bash profiles/variants.sh'); the measurement
+# sets that produce the files under profiles/ are r02_set5.sh (one GPU), multi.sh (N GPUs), ncu_full.sh, ncu_traffic.sh,
+# timing.sh
+mkdir -p gpurun_out
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()"
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
