@@ -435,7 +435,13 @@ MeshElement::maintain(uint32_t op, uint8_t* rec, uint8_t* aux, const int64_t* pa
     }
     if ( op == MAINT_TAIL ) { // a generation has just become the current one: digest entries of its pairs [208,312)
         if ( !ok ) return;
-        mt_warp_load(gen, buf + par * MT_N, lane);
+        // only the words those entries are made of: the draws of pairs [208,312) are words [416,624) -- a third of the
+        // generation (this read is 1 of the 3 x 2.5 KB a generator costs per 624 draws)
+        constexpr uint32_t Q0 = ROUTE_DIGEST_SPLIT * 32 / 4; // first 16-byte piece
+        static_assert(ROUTE_DIGEST_SPLIT * 32 % 4 == 0, "tail words start on a 16-byte piece");
+        for ( uint32_t i = Q0 + lane; i < MT_N / 4; i += 32 )
+            reinterpret_cast<uint4*>(gen)[i] = reinterpret_cast<const uint4*>(buf + par * MT_N)[i];
+        __syncwarp();
         if ( lane >= ROUTE_DIGEST_SPLIT && lane < ROUTE_DIGEST_WORDS ) dig[lane] = route_digest_word(gen, lane, ng);
         return;
     }
